@@ -1,0 +1,193 @@
+/*
+ * vlfb.h -- C ABI of libvlfb.so: the B200 (sm_100a) hot path of
+ * facebookresearch/video-long-term-feature-banks (R50/R101-I3D-NL backbone fwd/bwd +
+ * Feature-Bank-Operator attention).
+ *
+ * The reference has no FFI of its own: its hot path sits behind the Caffe2 operator
+ * registry (REGISTER_CUDA_OPERATOR, caffe2_customized_ops/video/affine_nd_op.cu:106-109)
+ * and the CNNModelHelper op emitters called from lib/models/*.py.  Each entry point
+ * below names the reference operator call site(s) it replaces (file:line relative to
+ * the reference root).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named host_*; the caller owns all memory
+ *   - activations are fp32, channels-last ("NDHWC": [N][T][H][W][C]); conv weights are
+ *     [Cout][kT][kH][kW][Cin]
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     synchronise, never allocate, keep no mutable global state
+ *   - return value: 0 = ok, <0 = error (see VLFB_E_*); vlfb_last_error() gives the text
+ */
+#ifndef VLFB_H_
+#define VLFB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLFB_OK 0
+#define VLFB_E_BADARG (-1)
+#define VLFB_E_UNSUPPORTED (-2)
+#define VLFB_E_CUDA (-3)
+
+/* ---- library ------------------------------------------------------------------------- */
+int vlfb_version(void);                 /* 100 * major + minor */
+const char* vlfb_last_error(void);      /* thread-local message of the last failing call */
+/* which contraction engine vlfb_gemm uses: 0 = tcgen05 tensor cores (default),
+ * 1 = SIMT fp32 debug kernel (bring-up / on-GPU cross-check only). */
+int vlfb_set_gemm_backend(int backend);
+int vlfb_get_gemm_backend(void);
+
+/* ---- gathered GEMM: D[m,n] = epi( sum_k A[m,k] * B[n,k] ) ------------------------------ */
+/* One descriptor per operand.  `kind`:
+ *   VLFB_OP_DENSE_K   rows (m or n) at ptr + batch*batch_stride + row*ld, k contiguous
+ *   VLFB_OP_DENSE_MN  rows indexed by k at ptr + batch*batch_stride + k*ld, m (or n) contiguous
+ *   VLFB_OP_CONV_K    A of conv forward : row m = output position, k = (tap, cin)
+ *   VLFB_OP_DGRAD_K   A of conv dgrad   : row m = input position,  k = (tap, cout)
+ *   VLFB_OP_CONV_MN   B of conv wgrad   : k = output position, n = cin, tap fixed per z-slice
+ *   VLFB_OP_STEM_K / VLFB_OP_STEM_MN    conv1 (Cin padded to 4): k = (kt,kh) x (8 pixels x 4 ch)
+ */
+enum {
+  VLFB_OP_DENSE_K = 0, VLFB_OP_DENSE_MN = 1, VLFB_OP_CONV_K = 2, VLFB_OP_DGRAD_K = 3,
+  VLFB_OP_CONV_MN = 4, VLFB_OP_STEM_K = 5, VLFB_OP_STEM_MN = 6
+};
+
+typedef struct {
+  int N, T, H, W, C;          /* input tensor  [N][T][H][W][C]              */
+  int To, Ho, Wo, Co;         /* output tensor [N][To][Ho][Wo][Co]          */
+  int kT, kH, kW;             /* filter taps                                 */
+  int sT, sH, sW;             /* strides                                     */
+  int pT, pH, pW;             /* symmetric zero padding                      */
+  int dT, dH, dW;             /* dilations                                   */
+} vlfb_conv_geom_t;
+
+typedef struct {
+  const float* ptr;
+  int kind;                   /* VLFB_OP_*                                   */
+  int64_t ld;                 /* DENSE_*: elements between consecutive rows  */
+  int64_t batch_stride;       /* DENSE_*: elements between batches           */
+} vlfb_operand_t;
+
+/* VLFB_EPI_TF32: round the stored value to TF32 (round-to-nearest, ties away: cvt.rna.tf32.f32) so that a
+ * consumer GEMM reads operands that the tensor core would otherwise truncate. */
+enum { VLFB_EPI_RELU = 1, VLFB_EPI_ACCUM = 2, VLFB_EPI_ATOMIC = 4, VLFB_EPI_TF32 = 8 };
+
+typedef struct {
+  vlfb_operand_t a, b;
+  vlfb_conv_geom_t g;         /* used by the CONV_ / DGRAD_ / STEM_ kinds    */
+  int M, N, K;                /* logical GEMM extent (K per z-slice for wgrad) */
+  int batch;                  /* >= 1 (DENSE only)                           */
+  int taps;                   /* wgrad: number of taps (z-slices), else 1    */
+  int split_k;                /* >= 1; >1 forces atomic accumulation         */
+  float* d;                   /* output rows: d + batch*d_batch_stride + m*ldd + n (+ tap*d_tap_stride) */
+  int64_t ldd, d_batch_stride, d_tap_stride;
+  float alpha;                /* applied first                               */
+  const float* col_scale;     /* [N] or NULL : v = v*col_scale[n]            */
+  const float* col_bias;      /* [N] or NULL : v += col_bias[n]              */
+  const float* row_scale;     /* [M] or NULL : v *= row_scale[m]             */
+  const float* residual;      /* same addressing as d, or NULL : v += res    */
+  int flags;                  /* VLFB_EPI_*                                  */
+} vlfb_gemm_params_t;
+
+/* Replaces: Caffe2 Conv (cuDNN) at resnet_video.py:169-179, model_builder_video.py:211-217,
+ * nonlocal_helper.py:36-78,131-144, lfb_helper.py:175-202,244-251,305-334; its gradients;
+ * BatchMatMul (cuBLAS) at nonlocal_helper.py:94-95,121 and lfb_helper.py:223-224,234;
+ * FC at resnet_video.py:327-331; and the AffineNd / Relu / Sum epilogues that follow
+ * them (model_builder_video.py:218-219, resnet_helper.py:112-117). */
+int vlfb_gemm(const vlfb_gemm_params_t* p, void* stream);
+
+/* ---- AffineNd (standalone; caffe2_customized_ops/video/affine_nd_op.cu:62-104) ---------- */
+int vlfb_affine_nd_fwd(const float* x, const float* scale, const float* bias, float* y,
+                       int64_t rows, int C, void* stream);
+int vlfb_affine_nd_bwd(const float* dy, const float* scale, float* dx, int64_t rows, int C,
+                       void* stream);
+
+/* ---- pooling (MaxPool/AveragePool: resnet_video.py:190-196,219-225, nonlocal_helper.py:48-54,
+ *      head_helper.py:37-40,92-98,113-115) -------------------------------------------------- */
+int vlfb_maxpool3d_fwd(const float* x, float* y, int32_t* argmax /* may be NULL */,
+                       const vlfb_conv_geom_t* g, void* stream);
+int vlfb_maxpool3d_bwd(const float* dy, const int32_t* argmax, float* dx /* pre-zeroed or accumulated */,
+                       const vlfb_conv_geom_t* g, void* stream);
+int vlfb_avgpool3d_fwd(const float* x, float* y, const vlfb_conv_geom_t* g, void* stream);
+int vlfb_avgpool3d_bwd(const float* dy, float* dx, const vlfb_conv_geom_t* g, int accumulate,
+                       void* stream);
+
+/* ---- RoIAlign, legacy Caffe2 semantics (lfb_helper.py:130-152) ------------------------ */
+/* feat [N][H][W][C], rois [R][5] = (batch, x1, y1, x2, y2), out [R][PH][PW][C] */
+int vlfb_roi_align_fwd(const float* feat, const float* rois, float* out, int N, int H, int W,
+                       int C, int R, int PH, int PW, float spatial_scale, int sampling_ratio,
+                       void* stream);
+int vlfb_roi_align_bwd(const float* dout, const float* rois, float* dfeat /* accumulated */,
+                       int N, int H, int W, int C, int R, int PH, int PW, float spatial_scale,
+                       int sampling_ratio, void* stream);
+/* Bilinear sample table for bit-exact index tests: per (r,ph,pw,iy,ix) with iy,ix < max_grid:
+ * pos[4] (y*W+x or -1) and w[4]; grid[r][2] = (grid_h, grid_w). */
+int vlfb_roi_align_table(const float* rois, int32_t* pos, float* w, int32_t* grid, int H, int W,
+                         int R, int PH, int PW, int max_grid, float spatial_scale,
+                         int sampling_ratio, void* stream);
+
+/* ---- row softmax with fused pre-scale (Scale+Softmax: nonlocal_helper.py:96-105,
+ *      lfb_helper.py:226-231) -------------------------------------------------------------- */
+int vlfb_softmax_fwd(const float* x, float* p, int64_t rows, int cols, float scale, void* stream);
+int vlfb_softmax_bwd(const float* p, const float* dp, float* dx, int64_t rows, int cols, float scale,
+                     void* stream);
+
+/* ---- LayerNorm(axis=1, eps, no affine) over rows (lfb_helper.py:160-167,253-256) ------- */
+int vlfb_layernorm_fwd(const float* x, float* y, float* mean, float* std, int64_t rows, int cols,
+                       float eps, void* stream);
+int vlfb_layernorm_bwd(const float* dy, const float* y, const float* std, float* dx, int64_t rows,
+                       int cols, void* stream);
+
+/* ---- elementwise ------------------------------------------------------------------------ */
+int vlfb_relu_fwd(const float* x, float* y, int64_t n, void* stream);
+int vlfb_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream); /* dx = dy*(y>0) */
+int vlfb_axpby(const float* x, float a, const float* y, float b, float* out, int64_t n, void* stream);
+int vlfb_fill(float* x, float v, int64_t n, void* stream);
+/* y = round-to-nearest TF32 of x (operand preparation for kind::tf32 MMAs; y may alias x) */
+int vlfb_round_tf32(const float* x, float* y, int64_t n, void* stream);
+int vlfb_sigmoid_fwd(const float* x, float* y, int64_t n, void* stream);
+/* Dropout (Caffe2 train mode: y = x*mask/(1-ratio)); mask = Philox(seed, offset+i) >= ratio */
+int vlfb_dropout_fwd(const float* x, float* y, int64_t n, float ratio, uint64_t seed, uint64_t offset,
+                     void* stream);
+/* 2-D strided copy: dst[r*ldd + c] = src[r*lds + c] (Concat / slicing; head_helper.py:82-85) */
+int vlfb_copy2d(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols,
+                int accumulate, void* stream);
+/* layout: NCTHW (reference blob layout) <-> NDHWC; inner = T*H*W */
+int vlfb_nc_to_cl(const float* src, float* dst, int N, int C, int64_t inner, int Cpad, void* stream);
+int vlfb_cl_to_nc(const float* src, float* dst, int N, int C, int64_t inner, int Cpad, void* stream);
+/* weights: wt[ci][tap][co] = w[co][tap][ci] * (scale ? scale[co] : 1) */
+int vlfb_weight_transpose(const float* w, float* wt, const float* scale, int Co, int taps, int Ci,
+                          void* stream);
+
+/* ---- losses (resnet_video.py:333-349) --------------------------------------------------- */
+/* Detectron SigmoidCrossEntropyLoss: loss[0] = scale * sum(per-elt) / max(#valid,1e-5) */
+int vlfb_sigmoid_ce_fwd(const float* logits, const int32_t* targets, float* loss, int64_t n,
+                        float scale, void* stream);
+int vlfb_sigmoid_ce_bwd(const float* logits, const int32_t* targets, const float* dloss /* device scalar or NULL=1 */,
+                        float* dlogits, int64_t n, float scale, void* stream);
+int vlfb_softmax_ce_fwd(const float* logits, const int32_t* labels, float* prob, float* loss,
+                        int rows, int cols, float scale, void* stream);
+int vlfb_softmax_ce_bwd(const float* prob, const int32_t* labels, float* dlogits, int rows, int cols,
+                        float scale, void* stream);
+
+/* ---- optimizer: WeightedSum + MomentumSGDUpdate fused (model_builder_video.py:375-388) -- */
+/* p_tf32 (may be NULL): also writes the TF32-rounded copy of the updated parameter (GEMM operand). */
+int vlfb_sgd_nesterov(float* p, float* g, float* m, float* p_tf32, int64_t n,
+                      const float* lr /* device scalar */, float momentum, float wd, int nesterov,
+                      void* stream);
+
+/* ---- fused FBO-NL attention core: one query per RoI over L bank rows
+ *      (lfb_helper.NLCore :223-234 BatchMatMul/Scale/Softmax/BatchMatMul) ----------------- */
+/* theta [R][d], phi,g [R][L][d] -> prob [R][L], y [R][d] */
+int vlfb_fbo_attend_fwd(const float* theta, const float* phi, const float* g, float* prob, float* y,
+                        int R, int L, int d, float scale, void* stream);
+int vlfb_fbo_attend_bwd(const float* theta, const float* phi, const float* g, const float* prob,
+                        const float* dy, float* dtheta, float* dphi,
+                        float* dg, int R, int L, int d, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLFB_H_ */

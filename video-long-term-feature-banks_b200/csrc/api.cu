@@ -1,0 +1,93 @@
+// C-ABI surface of libvlfb.so: argument validation + dispatch (see include/vlfb.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace vlfb {
+
+static thread_local char g_err[512] = "";
+static int g_backend = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int validate_gemm(const vlfb_gemm_params_t& p) {
+  VLFB_CHECK_ARG(p.a.ptr && p.b.ptr && p.d);
+  VLFB_CHECK_ARG(p.M > 0 && p.N > 0 && p.K >= 0);
+  VLFB_CHECK_ARG(p.batch >= 1 && p.taps >= 1 && p.split_k >= 1);
+  VLFB_CHECK_ARG(!(p.taps > 1 && p.batch > 1));
+  VLFB_CHECK_ARG(p.split_k == 1 || (p.flags & VLFB_EPI_ATOMIC));
+  VLFB_CHECK_ARG(!(p.split_k > 1 && (p.col_bias || p.residual || (p.flags & VLFB_EPI_RELU))));
+  VLFB_CHECK_ARG(aligned16(p.a.ptr) && aligned16(p.b.ptr));
+  const vlfb_operand_t* ops[2] = {&p.a, &p.b};
+  for (int i = 0; i < 2; ++i) {
+    const vlfb_operand_t& o = *ops[i];
+    const int extent = (i == 0) ? p.M : p.N;
+    switch (o.kind) {
+      case VLFB_OP_DENSE_K:
+        VLFB_CHECK_ARG((o.ld & 3) == 0 && (o.batch_stride & 3) == 0 && (p.K & 3) == 0);
+        break;
+      case VLFB_OP_DENSE_MN:
+        VLFB_CHECK_ARG((o.ld & 3) == 0 && (o.batch_stride & 3) == 0 && (extent & 3) == 0);
+        break;
+      case VLFB_OP_CONV_K:
+        VLFB_CHECK_ARG(i == 0 && p.g.C % 32 == 0 && p.K == p.g.kT * p.g.kH * p.g.kW * p.g.C);
+        VLFB_CHECK_ARG((int64_t)p.M == (int64_t)p.g.N * p.g.To * p.g.Ho * p.g.Wo);
+        break;
+      case VLFB_OP_DGRAD_K:
+        VLFB_CHECK_ARG(i == 0 && p.g.Co % 32 == 0 && p.K == p.g.kT * p.g.kH * p.g.kW * p.g.Co);
+        VLFB_CHECK_ARG((int64_t)p.M == (int64_t)p.g.N * p.g.T * p.g.H * p.g.W);
+        break;
+      case VLFB_OP_CONV_MN:
+        VLFB_CHECK_ARG(i == 1 && p.N == p.g.C && (p.g.C & 3) == 0 && p.taps == p.g.kT * p.g.kH * p.g.kW);
+        VLFB_CHECK_ARG((int64_t)p.K == (int64_t)p.g.N * p.g.To * p.g.Ho * p.g.Wo);
+        break;
+      case VLFB_OP_STEM_K:
+        VLFB_CHECK_ARG(i == 0 && p.g.C == 4 && p.g.kW <= 8 && p.K == p.g.kT * p.g.kH * 32);
+        VLFB_CHECK_ARG(p.g.dT == 1 && p.g.dH == 1 && p.g.dW == 1);
+        VLFB_CHECK_ARG((int64_t)p.M == (int64_t)p.g.N * p.g.To * p.g.Ho * p.g.Wo);
+        break;
+      case VLFB_OP_STEM_MN:
+        VLFB_CHECK_ARG(i == 1 && p.g.C == 4 && p.g.kW <= 8 && p.N == 32 && p.taps == p.g.kT * p.g.kH);
+        VLFB_CHECK_ARG(p.g.dT == 1 && p.g.dH == 1 && p.g.dW == 1);
+        VLFB_CHECK_ARG((int64_t)p.K == (int64_t)p.g.N * p.g.To * p.g.Ho * p.g.Wo);
+        break;
+      default:
+        set_error("vlfb_gemm: unknown operand kind %d", o.kind);
+        return VLFB_E_BADARG;
+    }
+  }
+  return VLFB_OK;
+}
+
+}  // namespace vlfb
+
+using namespace vlfb;
+
+extern "C" {
+
+int vlfb_version(void) { return 100; }
+const char* vlfb_last_error(void) { return g_err; }
+int vlfb_set_gemm_backend(int backend) {
+  VLFB_CHECK_ARG(backend == 0 || backend == 1);
+  g_backend = backend;
+  return VLFB_OK;
+}
+int vlfb_get_gemm_backend(void) { return g_backend; }
+
+int vlfb_gemm(const vlfb_gemm_params_t* p, void* stream) {
+  VLFB_CHECK_ARG(p != nullptr);
+  int rc = validate_gemm(*p);
+  if (rc != VLFB_OK) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return g_backend == 1 ? gemm_simt(*p, s) : gemm_tc(*p, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,529 @@
+// tcgen05 (5th-gen tensor core) gathered GEMM for sm_100a.
+//
+//   D[m,n] = epi( sum_k A[m,k] * B[n,k] ),  fp32 storage, kind::tf32 MMA, fp32 accumulate in TMEM.
+//
+// One CTA = one 128 x BN output tile (UMMA M=128, N=BN, cta_group::1).
+//   warps 0-3 (128 threads): PRODUCERS -- im2col-free gather of the A/B K-chunks (32 fp32 = one
+//                            128-byte swizzle row) straight from NDHWC tensors into the UMMA
+//                            canonical SWIZZLE_128B shared-memory layout with 16-byte cp.async
+//                            (zero-fill = conv padding); afterwards the same warps are the
+//                            EPILOGUE (tcgen05.ld TMEM -> registers -> fused affine/residual/ReLU
+//                            -> 128-bit global stores).
+//   warp 4: TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit releases the
+//           smem stage back to the producers and finally signals the epilogue.
+// Synchronisation is mbarrier-only inside the main loop (full[s] / empty[s] / tmem_full).
+//
+// Operand kinds are described in include/vlfb.h; their element-level definition is
+// operand_elem() in common.cuh, which the SIMT engine evaluates literally and the tests
+// compare this kernel against.
+#include "common.cuh"
+
+namespace vlfb {
+namespace tc {
+
+constexpr int BM = 128;        // tile rows (UMMA M)
+constexpr int KC = 32;         // fp32 per K chunk (128 B)
+constexpr int NPROD = 128;     // producer / epilogue threads
+constexpr int NTHREADS = 160;  // + MMA warp
+constexpr int A_TILE_BYTES = BM * KC * 4;  // 16 KB
+constexpr int MAX_STAGES = 8;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 6000000000LL) {
+      printf("vlfb gemm_tc: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;   // src-size 0 => 16 bytes of zeros (conv padding / tails)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);                 // [0,14)  start address
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;        // [16,30) leading byte offset
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;        // [32,46) stride byte offset
+  d |= (uint64_t)1 << 46;                                  // [46,48) descriptor version 1 (sm_100)
+  d |= (uint64_t)2 << 61;                                  // [61,64) SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): tf32 x tf32 -> f32, M=128, N=bn.
+__host__ __device__ inline uint32_t make_idesc(int bn, int a_mn_major, int b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;                          // c_format  = F32
+  d |= 2u << 7;                          // a_format  = TF32
+  d |= 2u << 10;                         // b_format  = TF32
+  d |= (uint32_t)(a_mn_major & 1) << 15; // a_major
+  d |= (uint32_t)(b_mn_major & 1) << 16; // b_major
+  d |= (uint32_t)(bn >> 3) << 17;        // n_dim
+  d |= (uint32_t)(BM >> 4) << 24;        // m_dim
+  return d;
+}
+
+__host__ __device__ constexpr bool is_mn(int kind) { return kind == VLFB_OP_DENSE_MN || kind == VLFB_OP_CONV_MN || kind == VLFB_OP_STEM_MN; }
+
+// ---------------------------------------------------------------- K-major loaders
+// Tile = `rows` rows x 128 B.  Thread t copies the 16-byte chunk (t & 7) of rows (t >> 3) + 16 j.
+template <int KIND, int MAXR>
+struct KLoader {
+  const float* base;
+  int64_t ld;
+  int nrow;          // rows of this tile handled per thread (rows / 16)
+  int kend;          // DENSE_K: K limit for the 16-byte tail predicate
+  // conv state per owned row
+  int s_n[MAXR], s_t[MAXR], s_hw[MAXR];
+  uint32_t rowmask;  // DENSE_K: bit j set when row j is inside the matrix
+
+  __device__ __forceinline__ void init(const vlfb_gemm_params_t& p, const vlfb_operand_t& op, int row0, int rows,
+                                       int limit, int batch) {
+    const int tid = threadIdx.x;
+    nrow = rows >> 4;
+    base = op.ptr;
+    ld = op.ld;
+    kend = p.K;
+    rowmask = 0;
+    const vlfb_conv_geom_t& g = p.g;
+    if (KIND == VLFB_OP_DENSE_K) base += (int64_t)batch * op.batch_stride;
+#pragma unroll
+    for (int j = 0; j < MAXR; ++j) {
+      if (j >= nrow) break;
+      const int row = row0 + (tid >> 3) + 16 * j;
+      const bool ok = row < limit;
+      if (KIND == VLFB_OP_DENSE_K) {
+        if (ok) rowmask |= 1u << j;
+      } else if (KIND == VLFB_OP_CONV_K || KIND == VLFB_OP_STEM_K) {
+        Pos4 o = decode_pos(ok ? row : 0, g.To, g.Ho, g.Wo);
+        s_n[j] = o.n * g.T;
+        s_t[j] = ok ? o.t * g.sT - g.pT : -100000;
+        s_hw[j] = ((o.h * g.sH - g.pH) << 16) | ((o.w * g.sW - g.pW) & 0xFFFF);
+      } else {  // DGRAD_K: rows are input positions
+        Pos4 i = decode_pos(ok ? row : 0, g.T, g.H, g.W);
+        s_n[j] = i.n * g.To;
+        s_t[j] = ok ? i.t + g.pT : -100000;
+        s_hw[j] = ((i.h + g.pH) << 16) | ((i.w + g.pW) & 0xFFFF);
+      }
+    }
+  }
+
+  // Issue the cp.asyncs of K chunk `kc` (global chunk index) into the tile at smem address `tile`.
+  __device__ __forceinline__ void issue(const vlfb_gemm_params_t& p, int row0, int kc, uint32_t tile) const {
+    const int tid = threadIdx.x;
+    const int c = tid & 7;
+    const int r0 = tid >> 3;
+    const vlfb_conv_geom_t& g = p.g;
+    if (KIND == VLFB_OP_DENSE_K) {
+      const int k = kc * KC + c * 4;
+      const bool kok = k < kend;
+#pragma unroll
+      for (int j = 0; j < MAXR; ++j) {
+        if (j >= nrow) break;
+        const int r = r0 + 16 * j;
+        const bool ok = kok && ((rowmask >> j) & 1u);
+        const float* src = ok ? base + (int64_t)(row0 + r) * ld + k : base;
+        cp_async16(tile + r * 128 + ((c ^ (r & 7)) << 4), src, ok);
+      }
+    } else if (KIND == VLFB_OP_CONV_K) {
+      const int cpt = g.C / KC;
+      const int tap = kc / cpt;
+      const int c0 = (kc - tap * cpt) * KC + c * 4;
+      int kt, kh, kw;
+      decode_tap(tap, g.kH, g.kW, kt, kh, kw);
+      const int dt = kt * g.dT, dh = kh * g.dH, dw = kw * g.dW;
+#pragma unroll
+      for (int j = 0; j < MAXR; ++j) {
+        if (j >= nrow) break;
+        const int r = r0 + 16 * j;
+        const int ti = s_t[j] + dt, hi = (s_hw[j] >> 16) + dh, wi = (int)(short)(s_hw[j] & 0xFFFF) + dw;
+        const bool ok = (unsigned)ti < (unsigned)g.T && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
+        const int64_t pos = ((int64_t)(s_n[j] + ti) * g.H + hi) * g.W + wi;
+        const float* src = ok ? base + pos * g.C + c0 : base;
+        cp_async16(tile + r * 128 + ((c ^ (r & 7)) << 4), src, ok);
+      }
+    } else if (KIND == VLFB_OP_STEM_K) {
+      const int kt = kc / g.kH, kh = kc - kt * g.kH;   // chunk = one (kt,kh) row of 8 pixels x 4 ch
+#pragma unroll
+      for (int j = 0; j < MAXR; ++j) {
+        if (j >= nrow) break;
+        const int r = r0 + 16 * j;
+        const int ti = s_t[j] + kt, hi = (s_hw[j] >> 16) + kh, wi = (int)(short)(s_hw[j] & 0xFFFF) + c;
+        const bool ok = (unsigned)ti < (unsigned)g.T && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
+        const int64_t pos = ((int64_t)(s_n[j] + ti) * g.H + hi) * g.W + wi;
+        const float* src = ok ? base + pos * 4 : base;
+        cp_async16(tile + r * 128 + ((c ^ (r & 7)) << 4), src, ok);
+      }
+    } else {  // DGRAD_K
+      const int cpt = g.Co / KC;
+      const int tap = kc / cpt;
+      const int c0 = (kc - tap * cpt) * KC + c * 4;
+      int kt, kh, kw;
+      decode_tap(tap, g.kH, g.kW, kt, kh, kw);
+      const int dt = kt * g.dT, dh = kh * g.dH, dw = kw * g.dW;
+#pragma unroll
+      for (int j = 0; j < MAXR; ++j) {
+        if (j >= nrow) break;
+        const int r = r0 + 16 * j;
+        const int a = s_t[j] - dt, b = (s_hw[j] >> 16) - dh, cc = (int)(short)(s_hw[j] & 0xFFFF) - dw;
+        bool ok = a >= 0 && b >= 0 && cc >= 0;
+        int to = a, ho = b, wo = cc;
+        if (g.sT != 1) { ok = ok && (a % g.sT == 0); to = a / g.sT; }
+        if (g.sH != 1) { ok = ok && (b % g.sH == 0); ho = b / g.sH; }
+        if (g.sW != 1) { ok = ok && (cc % g.sW == 0); wo = cc / g.sW; }
+        ok = ok && to < g.To && ho < g.Ho && wo < g.Wo;
+        const int64_t pos = ((int64_t)(s_n[j] + to) * g.Ho + ho) * g.Wo + wo;
+        const float* src = ok ? base + pos * g.Co + c0 : base;
+        cp_async16(tile + r * 128 + ((c ^ (r & 7)) << 4), src, ok);
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------- MN-major loaders
+// Tile = 32 k-rows, each `rows`*4 bytes of the m (or n) extent, stored as
+// [k-group of 8][atom of 32 elements][8 k-rows][128 B] (UMMA canonical MN-major SWIZZLE_128B).
+template <int KIND>
+struct MNLoader {
+  const float* base;
+  int64_t ld;
+  int rows, limit, row0, tapz;
+
+  __device__ __forceinline__ void init(const vlfb_gemm_params_t& p, const vlfb_operand_t& op, int row0_, int rows_,
+                                       int limit_, int batch, int tap) {
+    base = op.ptr;
+    if (KIND == VLFB_OP_DENSE_MN) base += (int64_t)batch * op.batch_stride;
+    ld = op.ld;
+    rows = rows_;
+    limit = limit_;
+    row0 = row0_;
+    tapz = tap;
+  }
+
+  // k0 = first k of this chunk, kend = exclusive k limit of this CTA's K range.
+  __device__ __forceinline__ void issue(const vlfb_gemm_params_t& p, int k0, int kend, uint32_t tile) const {
+    const vlfb_conv_geom_t& g = p.g;
+    const int cpr = rows >> 2;            // 16-byte chunks per k-row
+    const int natoms = rows >> 5;
+    const int total = KC * cpr;
+    int kt = 0, kh = 0, kw = 0;
+    if (KIND == VLFB_OP_CONV_MN) decode_tap(tapz, g.kH, g.kW, kt, kh, kw);
+    if (KIND == VLFB_OP_STEM_MN) { kt = tapz / g.kH; kh = tapz - kt * g.kH; }
+    for (int idx = threadIdx.x; idx < total; idx += NPROD) {
+      const int kk = idx / cpr;
+      const int c = idx - kk * cpr;
+      const int k = k0 + kk;
+      const int mn = row0 + c * 4;
+      bool ok = k < kend && mn < limit;
+      const float* src = base;
+      if (KIND == VLFB_OP_DENSE_MN) {
+        if (ok) src = base + (int64_t)k * ld + mn;
+      } else if (KIND == VLFB_OP_CONV_MN) {
+        Pos4 o = decode_pos(ok ? k : 0, g.To, g.Ho, g.Wo);
+        const int ti = o.t * g.sT - g.pT + kt * g.dT, hi = o.h * g.sH - g.pH + kh * g.dH,
+                  wi = o.w * g.sW - g.pW + kw * g.dW;
+        ok = ok && (unsigned)ti < (unsigned)g.T && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
+        if (ok) src = base + ((((int64_t)o.n * g.T + ti) * g.H + hi) * g.W + wi) * g.C + mn;
+      } else {  // STEM_MN: rows == 32, chunk c = pixel
+        Pos4 o = decode_pos(ok ? k : 0, g.To, g.Ho, g.Wo);
+        const int ti = o.t * g.sT - g.pT + kt, hi = o.h * g.sH - g.pH + kh, wi = o.w * g.sW - g.pW + c;
+        ok = ok && (unsigned)ti < (unsigned)g.T && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
+        if (ok) src = base + ((((int64_t)o.n * g.T + ti) * g.H + hi) * g.W + wi) * 4;
+      }
+      const int r = kk & 7;
+      const uint32_t dst = tile + (kk >> 3) * (natoms * 1024) + (c >> 3) * 1024 + r * 128 + (((c & 7) ^ r) << 4);
+      cp_async16(dst, src, ok);
+    }
+  }
+};
+
+// ---------------------------------------------------------------- the kernel
+struct Launch {
+  int bn;        // tile N (32/64/128/256) = UMMA N = TMEM columns
+  int stages;
+};
+
+template <int AK, int BK>
+__global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_params_t p, const Launch L) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int bn = L.bn, S = L.stages;
+  const uint32_t b_tile_bytes = (uint32_t)bn * KC * 4;
+  const uint32_t stage_bytes = A_TILE_BYTES + b_tile_bytes;
+  const uint32_t bar_base = smem_base + S * stage_bytes;      // full[S], empty[S], tmem_full, tmem_ptr
+  const uint32_t full0 = bar_base, empty0 = bar_base + 8 * MAX_STAGES, tfull = bar_base + 16 * MAX_STAGES;
+  const uint32_t tptr_addr = tfull + 8;
+  volatile uint32_t* tptr_generic =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr_addr - smem_u32(smem_raw)));
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  // z decomposition
+  const int z = blockIdx.z;
+  const int split = z % p.split_k;
+  const int zz = z / p.split_k;
+  const int batch = (p.taps > 1) ? 0 : zz;
+  const int tap = (p.taps > 1) ? zz : 0;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * bn;
+  int kper = (p.K + p.split_k - 1) / p.split_k;
+  kper = (kper + KC - 1) / KC * KC;
+  const int k_begin = split * kper;
+  const int k_end = min(p.K, k_begin + kper);
+  const int nk = (k_end > k_begin) ? (k_end - k_begin + KC - 1) / KC : 0;
+  if (nk == 0 && p.split_k > 1) return;   // empty split (uniform across the CTA)
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full0 + 8 * s, NPROD);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) tmem_alloc(tptr_addr, (uint32_t)(bn < 32 ? 32 : bn));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tptr_generic;
+
+  if (warp < 4) {
+    // ============================ PRODUCERS ============================
+    if (nk > 0) {
+      KLoader<is_mn(AK) ? VLFB_OP_DENSE_K : AK, 8> ka;
+      MNLoader<is_mn(AK) ? AK : VLFB_OP_DENSE_MN> ma;
+      KLoader<is_mn(BK) ? VLFB_OP_DENSE_K : BK, 16> kb;
+      MNLoader<is_mn(BK) ? BK : VLFB_OP_DENSE_MN> mb;
+      if (is_mn(AK)) ma.init(p, p.a, m0, BM, p.M, batch, tap); else ka.init(p, p.a, m0, BM, p.M, batch);
+      if (is_mn(BK)) mb.init(p, p.b, n0, bn, p.N, batch, tap); else kb.init(p, p.b, n0, bn, p.N, batch);
+      if (!is_mn(AK)) ka.kend = k_end;
+      if (!is_mn(BK)) kb.kend = k_end;
+      const int kc0 = k_begin / KC;
+      constexpr int LAG = 2;
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % S;
+        if (i >= S) mbar_wait(empty0 + 8 * s, ((i / S) - 1) & 1);
+        const uint32_t a_tile = smem_base + s * stage_bytes;
+        const uint32_t b_tile = a_tile + A_TILE_BYTES;
+        if (is_mn(AK)) ma.issue(p, k_begin + i * KC, k_end, a_tile); else ka.issue(p, m0, kc0 + i, a_tile);
+        if (is_mn(BK)) mb.issue(p, k_begin + i * KC, k_end, b_tile); else kb.issue(p, n0, kc0 + i, b_tile);
+        cp_async_commit();
+        if (i >= LAG) {
+          cp_async_wait<LAG>();
+          fence_proxy_async();
+          mbar_arrive(full0 + 8 * ((i - LAG) % S));
+        }
+      }
+      cp_async_wait<0>();
+      fence_proxy_async();
+      for (int i = (nk > LAG ? nk - LAG : 0); i < nk; ++i) mbar_arrive(full0 + 8 * (i % S));
+    }
+    // ============================ EPILOGUE =============================
+    if (nk > 0) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+    }
+    const int m = m0 + tid;                 // TMEM lane == tile row
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const int64_t row_off = (int64_t)batch * p.d_batch_stride + (int64_t)tap * p.d_tap_stride + (int64_t)m * p.ldd;
+    const bool vec_ok = ((p.ldd & 3) == 0) && ((p.d_batch_stride & 3) == 0) && ((p.d_tap_stride & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0) &&
+                        (!p.residual || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) &&
+                        !(p.flags & (VLFB_EPI_ATOMIC | VLFB_EPI_ACCUM));
+    const float rs = (p.row_scale && m < p.M) ? p.row_scale[m] : 1.f;
+    for (int c0 = 0; c0 < bn; c0 += 32) {
+      if (n0 + c0 >= p.N) break;            // uniform
+      float v[32];
+      if (nk > 0) {
+        tmem_ld32(lane_addr + c0, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = 0.f;
+      }
+      if (m < p.M) {
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+          const int n = n0 + c0 + q;
+          if (vec_ok && n + 3 < p.N) {
+            float4 o = make_float4(v[q] * p.alpha, v[q + 1] * p.alpha, v[q + 2] * p.alpha, v[q + 3] * p.alpha);
+            if (p.col_scale) {
+              const float4 s4 = *reinterpret_cast<const float4*>(p.col_scale + n);
+              o.x *= s4.x; o.y *= s4.y; o.z *= s4.z; o.w *= s4.w;
+            }
+            if (p.col_bias) {
+              const float4 b4 = *reinterpret_cast<const float4*>(p.col_bias + n);
+              o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            }
+            o.x *= rs; o.y *= rs; o.z *= rs; o.w *= rs;
+            if (p.residual) {
+              const float4 r4 = *reinterpret_cast<const float4*>(p.residual + row_off + n);
+              o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+            }
+            if (p.flags & VLFB_EPI_RELU) {
+              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            }
+            if (p.flags & VLFB_EPI_TF32) {
+              o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+            }
+            *reinterpret_cast<float4*>(p.d + row_off + n) = o;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (n + e < p.N) epilogue_store(p, batch, tap, m, n + e, v[q + e]);
+          }
+        }
+      }
+    }
+  } else if (nk > 0) {
+    // ============================ MMA ISSUER ===========================
+    if ((tid & 31) == 0) {
+      const uint32_t idesc = make_idesc(bn, is_mn(AK) ? 1 : 0, is_mn(BK) ? 1 : 0);
+      const uint32_t a_atoms = BM / 32, b_atoms = bn / 32;
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % S;
+        mbar_wait(full0 + 8 * s, (i / S) & 1);
+        tc_fence_after();
+        const uint32_t a_tile = smem_base + s * stage_bytes;
+        const uint32_t b_tile = a_tile + A_TILE_BYTES;
+#pragma unroll
+        for (int j = 0; j < KC / 8; ++j) {   // UMMA K = 8 for tf32
+          const uint64_t da = is_mn(AK) ? make_desc(a_tile + j * (a_atoms * 1024), 1024, a_atoms * 1024)
+                                        : make_desc(a_tile + j * 32, 16, 1024);
+          const uint64_t db = is_mn(BK) ? make_desc(b_tile + j * (b_atoms * 1024), 1024, b_atoms * 1024)
+                                        : make_desc(b_tile + j * 32, 16, 1024);
+          umma_tf32(tmem, da, db, idesc, (i | j) ? 1u : 0u);
+        }
+        umma_commit(empty0 + 8 * s);       // frees the smem stage when these MMAs retire
+      }
+      umma_commit(tfull);                  // accumulator complete -> epilogue
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, (uint32_t)(bn < 32 ? 32 : bn));
+  }
+}
+
+// ---------------------------------------------------------------- host dispatch
+template <int AK, int BK>
+int launch(const vlfb_gemm_params_t& p, cudaStream_t stream) {
+  Launch L;
+  if (BK == VLFB_OP_STEM_MN) L.bn = 32;
+  else if (p.N > 128) L.bn = 256;
+  else if (p.N > 64) L.bn = 128;
+  else if (p.N > 32) L.bn = 64;
+  else L.bn = 32;
+  // keep >= 2 waves of CTAs on 148 SMs when the wide tile would leave the chip underfilled
+  const int64_t zdim = (int64_t)(p.taps > 1 ? p.taps : p.batch) * p.split_k;
+  if (L.bn == 256 && (int64_t)ceil_div(p.M, BM) * ceil_div(p.N, 256) * zdim < 148) L.bn = 128;
+  const int stage_bytes = A_TILE_BYTES + L.bn * KC * 4;
+  L.stages = (L.bn == 256) ? 4 : (L.bn == 128 ? 3 : 4);
+  const int smem = L.stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
+      return VLFB_E_CUDA;
+    }
+    attr_done = true;
+  }
+  dim3 grid(ceil_div(p.M, BM), ceil_div(p.N, L.bn), (unsigned)zdim);
+  gemm_tc_kernel<AK, BK><<<grid, NTHREADS, smem, stream>>>(p, L);
+  VLFB_CHECK_LAUNCH();
+  return VLFB_OK;
+}
+
+}  // namespace tc
+
+int gemm_tc(const vlfb_gemm_params_t& p, cudaStream_t stream) {
+  const int ak = p.a.kind, bk = p.b.kind;
+#define VLFB_TC_CASE(A, B) if (ak == A && bk == B) return tc::launch<A, B>(p, stream)
+  VLFB_TC_CASE(VLFB_OP_CONV_K, VLFB_OP_DENSE_K);
+  VLFB_TC_CASE(VLFB_OP_STEM_K, VLFB_OP_DENSE_K);
+  VLFB_TC_CASE(VLFB_OP_DGRAD_K, VLFB_OP_DENSE_K);
+  VLFB_TC_CASE(VLFB_OP_DENSE_MN, VLFB_OP_CONV_MN);
+  VLFB_TC_CASE(VLFB_OP_DENSE_MN, VLFB_OP_STEM_MN);
+  VLFB_TC_CASE(VLFB_OP_DENSE_K, VLFB_OP_DENSE_K);
+  VLFB_TC_CASE(VLFB_OP_DENSE_K, VLFB_OP_DENSE_MN);
+  VLFB_TC_CASE(VLFB_OP_DENSE_MN, VLFB_OP_DENSE_K);
+  VLFB_TC_CASE(VLFB_OP_DENSE_MN, VLFB_OP_DENSE_MN);
+#undef VLFB_TC_CASE
+  set_error("gemm_tc: unsupported operand kinds (%d, %d)", ak, bk);
+  return VLFB_E_UNSUPPORTED;
+}
+
+}  // namespace vlfb

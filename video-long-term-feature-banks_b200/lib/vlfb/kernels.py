@@ -1,0 +1,410 @@
+"""Tensor-level wrappers around the C ABI (libvlfb.so).
+
+PyTorch tensors are used purely as device-memory containers: every function takes
+CUDA fp32 tensors, validates shapes/strides and passes raw pointers to the library.
+Physical layout of activations is channels-last: [N, T, H, W, C] contiguous.
+"""
+import ctypes as C
+
+import torch
+
+from . import libvlfb as L
+
+NUM_SMS = 148
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda, 'vlfb kernels need CUDA tensors (there is no CPU fallback)'
+    return C.c_void_p(t.data_ptr())
+
+
+def _f32c(t, name='tensor'):
+    assert t.dtype == torch.float32 and t.is_contiguous(), '%s must be contiguous fp32' % name
+    return t
+
+
+def set_gemm_backend(name):
+    """'tcgen05' (default) or 'simt' (debug cross-check engine)."""
+    L.check(L.load().vlfb_set_gemm_backend({'tcgen05': 0, 'simt': 1}[name]), 'set_gemm_backend')
+
+
+def get_gemm_backend():
+    return ['tcgen05', 'simt'][L.load().vlfb_get_gemm_backend()]
+
+
+# --------------------------------------------------------------------------- geometry
+def conv_geom(in_shape, cout, kernels, strides, pads, dilations=(1, 1, 1)):
+    """in_shape = physical (N,T,H,W,C).  Output extents follow Caffe2 Conv/Pool (floor)."""
+    n, t, h, w, c = [int(v) for v in in_shape]
+    g = L.ConvGeom()
+    g.N, g.T, g.H, g.W, g.C = n, t, h, w, c
+    g.kT, g.kH, g.kW = [int(v) for v in kernels]
+    g.sT, g.sH, g.sW = [int(v) for v in strides]
+    g.pT, g.pH, g.pW = [int(v) for v in pads]
+    g.dT, g.dH, g.dW = [int(v) for v in dilations]
+    g.To = (t + 2 * g.pT - g.dT * (g.kT - 1) - 1) // g.sT + 1
+    g.Ho = (h + 2 * g.pH - g.dH * (g.kH - 1) - 1) // g.sH + 1
+    g.Wo = (w + 2 * g.pW - g.dW * (g.kW - 1) - 1) // g.sW + 1
+    g.Co = int(cout)
+    return g
+
+
+def out_shape(g):
+    return (g.N, g.To, g.Ho, g.Wo, g.Co)
+
+
+def _is_pointwise(g):
+    return (g.kT, g.kH, g.kW, g.sT, g.sH, g.sW, g.pT, g.pH, g.pW) == (1, 1, 1, 1, 1, 1, 0, 0, 0)
+
+
+def _operand(ptr_t, kind, ld=0, batch_stride=0):
+    o = L.Operand()
+    o.ptr = ptr_t.data_ptr()
+    o.kind = kind
+    o.ld = int(ld)
+    o.batch_stride = int(batch_stride)
+    return o
+
+
+def _run_gemm(p):
+    L.check(L.load().vlfb_gemm(C.byref(p), _stream()), 'vlfb_gemm')
+
+
+def _base_params(M, N, K, d, ldd, alpha=1.0):
+    p = L.GemmParams()
+    p.M, p.N, p.K = int(M), int(N), int(K)
+    p.batch, p.taps, p.split_k = 1, 1, 1
+    p.d = d.data_ptr()
+    p.ldd = int(ldd)
+    p.d_batch_stride = 0
+    p.d_tap_stride = 0
+    p.alpha = float(alpha)
+    p.flags = 0
+    return p
+
+
+def _set_epilogue(p, scale=None, bias=None, row_scale=None, residual=None, relu=False, tf32=False):
+    keep = []
+    if tf32:
+        p.flags |= L.EPI_TF32
+    if scale is not None:
+        p.col_scale = _f32c(scale).data_ptr()
+    if bias is not None:
+        p.col_bias = _f32c(bias).data_ptr()
+    if row_scale is not None:
+        p.row_scale = _f32c(row_scale).data_ptr()
+    if residual is not None:
+        p.residual = _f32c(residual).data_ptr()
+    if relu:
+        p.flags |= L.EPI_RELU
+    return keep
+
+
+# --------------------------------------------------------------------------- convolution
+def conv_fwd(x, w, y, g, scale=None, bias=None, residual=None, relu=False, tf32_out=False):
+    """y = epi(conv(x, w)).  x [N,T,H,W,C], w [Co,kT,kH,kW,C], y [N,To,Ho,Wo,Co];
+    epi: *scale[co] + bias[co] (+ residual) (ReLU).  C == 4 selects the stem (conv1) path with
+    w [Co,kT,kH,8,4]."""
+    _f32c(x, 'x'), _f32c(w, 'w'), _f32c(y, 'y')
+    assert tuple(x.shape) == (g.N, g.T, g.H, g.W, g.C) and tuple(y.shape) == out_shape(g)
+    M = g.N * g.To * g.Ho * g.Wo
+    if g.C == 4:
+        K = g.kT * g.kH * 32
+        assert tuple(w.shape) == (g.Co, g.kT, g.kH, 8, 4)
+        a = _operand(x, L.OP_STEM_K)
+    elif _is_pointwise(g):
+        K = g.C
+        a = _operand(x, L.OP_DENSE_K, ld=g.C)
+    else:
+        K = g.kT * g.kH * g.kW * g.C
+        assert tuple(w.shape) == (g.Co, g.kT, g.kH, g.kW, g.C)
+        a = _operand(x, L.OP_CONV_K)
+    p = _base_params(M, g.Co, K, y, g.Co)
+    p.a = a
+    p.b = _operand(w, L.OP_DENSE_K, ld=K)
+    p.g = g
+    _set_epilogue(p, scale, bias, None, residual, relu, tf32_out)
+    _run_gemm(p)
+
+
+def conv_dgrad(dy, wt, dx, g, accumulate=False):
+    """dx (+)= conv_transpose(dy, w).  wt [C, kT,kH,kW, Co] (see weight_transpose), dx [N,T,H,W,C]."""
+    _f32c(dy, 'dy'), _f32c(wt, 'wt'), _f32c(dx, 'dx')
+    assert tuple(dy.shape) == out_shape(g) and tuple(dx.shape) == (g.N, g.T, g.H, g.W, g.C)
+    M = g.N * g.T * g.H * g.W
+    if _is_pointwise(g):
+        K = g.Co
+        a = _operand(dy, L.OP_DENSE_K, ld=g.Co)
+    else:
+        K = g.kT * g.kH * g.kW * g.Co
+        a = _operand(dy, L.OP_DGRAD_K)
+    p = _base_params(M, g.C, K, dx, g.C)
+    p.a = a
+    p.b = _operand(wt, L.OP_DENSE_K, ld=K)
+    p.g = g
+    if accumulate:
+        p.flags |= L.EPI_ACCUM
+    _run_gemm(p)
+
+
+def _split_k(tiles, kdim):
+    """Split the reduction so that >= ~2 waves of CTAs cover the 148 SMs."""
+    want = (2 * NUM_SMS + tiles - 1) // tiles
+    cap = max(1, kdim // 256)
+    return max(1, min(want, cap, 64))
+
+
+def conv_wgrad(dy, x, dw, g, row_scale=None, col_mask=None):
+    """dw[co,tap,ci] += row_scale[co] * sum_m dy[m,co] * x[gather(m,tap),ci]  (atomic accumulate:
+    dw must be zero-initialised or hold a partial sum).  Stem path when C == 4 (dw [Co,kT,kH,8,4],
+    col_mask [32] zeroes the padding lanes)."""
+    _f32c(dy, 'dy'), _f32c(x, 'x'), _f32c(dw, 'dw')
+    Kpos = g.N * g.To * g.Ho * g.Wo
+    if g.C == 4:
+        taps, n = g.kT * g.kH, 32
+        b = _operand(x, L.OP_STEM_MN)
+    elif _is_pointwise(g):
+        taps, n = 1, g.C
+        b = _operand(x, L.OP_DENSE_MN, ld=g.C)
+    else:
+        taps, n = g.kT * g.kH * g.kW, g.C
+        b = _operand(x, L.OP_CONV_MN)
+    p = _base_params(g.Co, n, Kpos, dw, taps * n)
+    p.a = _operand(dy, L.OP_DENSE_MN, ld=g.Co)
+    p.b = b
+    p.g = g
+    p.taps = taps
+    p.d_tap_stride = n
+    bn = 256 if n > 128 else (128 if n > 64 else (64 if n > 32 else 32))
+    tiles = ((g.Co + 127) // 128) * ((n + bn - 1) // bn) * taps
+    p.split_k = _split_k(tiles, Kpos)
+    p.flags |= L.EPI_ATOMIC
+    _set_epilogue(p, col_mask, None, row_scale, None, False)
+    _run_gemm(p)
+
+
+def weight_transpose(w, wt, scale=None):
+    """wt[ci][tap][co] = w[co][tap][ci] * scale[co]."""
+    _f32c(w), _f32c(wt)
+    co, ci = w.shape[0], w.shape[-1]
+    taps = w.numel() // (co * ci)
+    L.check(L.load().vlfb_weight_transpose(_ptr(w), _ptr(wt), _ptr(scale), co, taps, ci, _stream()),
+            'weight_transpose')
+
+
+# --------------------------------------------------------------------------- generic matmul
+def _dim_ok(stride, size):
+    return size == 1 or stride == 1
+
+
+def _mat_operand(t, rows_dim, k_dim):
+    """Describe logical matrix op[row,k] = t[..., row(s), k(s)] (3-D strided view, dim 0 = batch)."""
+    sb, sr, sk = t.stride(0), t.stride(rows_dim), t.stride(k_dim)
+    R, K = t.shape[rows_dim], t.shape[k_dim]
+    if t.shape[0] == 1:
+        sb = 0
+    if _dim_ok(sk, K) and (R == 1 or sr % 4 == 0) and K % 4 == 0 and sb % 4 == 0:
+        return L.OP_DENSE_K, (sr if R > 1 else K), sb
+    if _dim_ok(sr, R) and (K == 1 or sk % 4 == 0) and R % 4 == 0 and sb % 4 == 0:
+        return L.OP_DENSE_MN, (sk if K > 1 else R), sb
+    raise ValueError('matmul operand with shape %s strides %s is not tensor-core addressable'
+                     % (tuple(t.shape), tuple(t.stride())))
+
+
+def matmul(a, b, d, alpha=1.0, accumulate=False, bias=None, tf32_out=False):
+    """d[i] (+)= alpha * a[i] @ b[i] (+ bias[n]) for 3-D strided views a (B,M,K), b (B,K,N), d (B,M,N).
+    Each matrix needs unit stride along one of its two dims (16-byte aligned rows)."""
+    assert a.dim() == 3 and b.dim() == 3 and d.dim() == 3
+    Bt, M, K = a.shape
+    N = b.shape[2]
+    assert b.shape[0] == Bt and b.shape[1] == K and tuple(d.shape) == (Bt, M, N)
+    if not _dim_ok(d.stride(2), N):
+        # output is column-major: compute d^T = b^T a^T
+        assert _dim_ok(d.stride(1), M), 'matmul output needs a unit stride'
+        assert bias is None
+        return matmul(b.transpose(1, 2), a.transpose(1, 2), d.transpose(1, 2), alpha, accumulate, None, tf32_out)
+    ka, lda, sba = _mat_operand(a, 1, 2)
+    kb, ldb, sbb = _mat_operand(b, 2, 1)
+    p = _base_params(M, N, K, d, d.stride(1) if M > 1 else N)
+    p.a = _operand(a, ka, lda, sba)
+    p.b = _operand(b, kb, ldb, sbb)
+    p.batch = Bt
+    p.d_batch_stride = d.stride(0) if Bt > 1 else 0
+    if accumulate:
+        p.flags |= L.EPI_ACCUM
+    _set_epilogue(p, None, bias, None, None, False, tf32_out)
+    _run_gemm(p)
+
+
+# --------------------------------------------------------------------------- streaming ops
+def affine_fwd(x, s, b, y):
+    L.check(L.load().vlfb_affine_nd_fwd(_ptr(_f32c(x)), _ptr(s), _ptr(b), _ptr(_f32c(y)),
+                                        x.numel() // x.shape[-1], x.shape[-1], _stream()), 'affine_fwd')
+
+
+def affine_bwd(dy, s, dx):
+    L.check(L.load().vlfb_affine_nd_bwd(_ptr(_f32c(dy)), _ptr(s), _ptr(_f32c(dx)),
+                                        dy.numel() // dy.shape[-1], dy.shape[-1], _stream()), 'affine_bwd')
+
+
+def maxpool_fwd(x, y, argmax, g):
+    L.check(L.load().vlfb_maxpool3d_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), _ptr(argmax), C.byref(g), _stream()),
+            'maxpool_fwd')
+
+
+def maxpool_bwd(dy, argmax, dx, g):
+    L.check(L.load().vlfb_maxpool3d_bwd(_ptr(_f32c(dy)), _ptr(argmax), _ptr(_f32c(dx)), C.byref(g), _stream()),
+            'maxpool_bwd')
+
+
+def avgpool_fwd(x, y, g):
+    L.check(L.load().vlfb_avgpool3d_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), C.byref(g), _stream()), 'avgpool_fwd')
+
+
+def avgpool_bwd(dy, dx, g, accumulate=False):
+    L.check(L.load().vlfb_avgpool3d_bwd(_ptr(_f32c(dy)), _ptr(_f32c(dx)), C.byref(g), int(accumulate), _stream()),
+            'avgpool_bwd')
+
+
+def roi_align_fwd(feat, rois, out, spatial_scale, sampling_ratio=0):
+    """feat [N,H,W,C], rois [R,5], out [R,PH,PW,C]."""
+    n, h, w, c = feat.shape
+    r, ph, pw, _ = out.shape
+    L.check(L.load().vlfb_roi_align_fwd(_ptr(_f32c(feat)), _ptr(_f32c(rois)), _ptr(_f32c(out)), n, h, w, c, r, ph, pw,
+                                        float(spatial_scale), int(sampling_ratio), _stream()), 'roi_align_fwd')
+
+
+def roi_align_bwd(dout, rois, dfeat, spatial_scale, sampling_ratio=0):
+    n, h, w, c = dfeat.shape
+    r, ph, pw, _ = dout.shape
+    L.check(L.load().vlfb_roi_align_bwd(_ptr(_f32c(dout)), _ptr(_f32c(rois)), _ptr(_f32c(dfeat)), n, h, w, c, r, ph,
+                                        pw, float(spatial_scale), int(sampling_ratio), _stream()), 'roi_align_bwd')
+
+
+def roi_align_table(rois, h, w, ph, pw, max_grid, spatial_scale, sampling_ratio=0):
+    r = rois.shape[0]
+    pos = torch.empty((r, ph, pw, max_grid, max_grid, 4), dtype=torch.int32, device=rois.device)
+    wts = torch.empty((r, ph, pw, max_grid, max_grid, 4), dtype=torch.float32, device=rois.device)
+    grid = torch.empty((r, 2), dtype=torch.int32, device=rois.device)
+    L.check(L.load().vlfb_roi_align_table(_ptr(_f32c(rois)), _ptr(pos), _ptr(wts), _ptr(grid), h, w, r, ph, pw,
+                                          max_grid, float(spatial_scale), int(sampling_ratio), _stream()),
+            'roi_align_table')
+    return pos, wts, grid
+
+
+def softmax_fwd(x, p, scale=1.0):
+    cols = x.shape[-1]
+    L.check(L.load().vlfb_softmax_fwd(_ptr(_f32c(x)), _ptr(_f32c(p)), x.numel() // cols, cols, float(scale),
+                                      _stream()), 'softmax_fwd')
+
+
+def softmax_bwd(p, dp, dx, scale=1.0):
+    cols = p.shape[-1]
+    L.check(L.load().vlfb_softmax_bwd(_ptr(_f32c(p)), _ptr(_f32c(dp)), _ptr(_f32c(dx)), p.numel() // cols, cols,
+                                      float(scale), _stream()), 'softmax_bwd')
+
+
+def layernorm_fwd(x, y, mean, std, cols, eps=1e-5):
+    L.check(L.load().vlfb_layernorm_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), _ptr(mean), _ptr(std), x.numel() // cols,
+                                        cols, float(eps), _stream()), 'layernorm_fwd')
+
+
+def layernorm_bwd(dy, y, std, dx, cols):
+    L.check(L.load().vlfb_layernorm_bwd(_ptr(_f32c(dy)), _ptr(_f32c(y)), _ptr(std), _ptr(_f32c(dx)),
+                                        dy.numel() // cols, cols, _stream()), 'layernorm_bwd')
+
+
+def relu_fwd(x, y):
+    L.check(L.load().vlfb_relu_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), x.numel(), _stream()), 'relu_fwd')
+
+
+def relu_bwd(dy, y, dx):
+    L.check(L.load().vlfb_relu_bwd(_ptr(_f32c(dy)), _ptr(_f32c(y)), _ptr(_f32c(dx)), dy.numel(), _stream()),
+            'relu_bwd')
+
+
+def axpby(x, a, y, b, out):
+    """out = a*x + b*y (y may be None when b == 0)."""
+    L.check(L.load().vlfb_axpby(_ptr(_f32c(x)), float(a), _ptr(y), float(b), _ptr(_f32c(out)), x.numel(),
+                                _stream()), 'axpby')
+
+
+def fill(x, v):
+    L.check(L.load().vlfb_fill(_ptr(_f32c(x)), float(v), x.numel(), _stream()), 'fill')
+
+
+def round_tf32(x, y):
+    L.check(L.load().vlfb_round_tf32(_ptr(_f32c(x)), _ptr(_f32c(y)), x.numel(), _stream()), 'round_tf32')
+
+
+def sigmoid_fwd(x, y):
+    L.check(L.load().vlfb_sigmoid_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), x.numel(), _stream()), 'sigmoid_fwd')
+
+
+def dropout(x, y, ratio, seed, offset):
+    """y = x * mask / (1-ratio); the mask is a pure function of (seed, offset, index), so the same
+    call on dy is the backward."""
+    L.check(L.load().vlfb_dropout_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), x.numel(), float(ratio), int(seed),
+                                      int(offset), _stream()), 'dropout')
+
+
+def copy2d(src, lds, dst, ldd, rows, cols, accumulate=False, src_off=0, dst_off=0):
+    sp = C.c_void_p(src.data_ptr() + 4 * src_off)
+    dp = C.c_void_p(dst.data_ptr() + 4 * dst_off)
+    L.check(L.load().vlfb_copy2d(sp, int(lds), dp, int(ldd), int(rows), int(cols), int(accumulate), _stream()),
+            'copy2d')
+
+
+def nc_to_cl(src, dst, n, c, inner, cpad=None):
+    L.check(L.load().vlfb_nc_to_cl(_ptr(_f32c(src)), _ptr(_f32c(dst)), n, c, inner, cpad or c, _stream()), 'nc_to_cl')
+
+
+def cl_to_nc(src, dst, n, c, inner, cpad=None):
+    L.check(L.load().vlfb_cl_to_nc(_ptr(_f32c(src)), _ptr(_f32c(dst)), n, c, inner, cpad or c, _stream()), 'cl_to_nc')
+
+
+def sigmoid_ce_fwd(logits, targets, loss, scale):
+    assert targets.dtype == torch.int32
+    L.check(L.load().vlfb_sigmoid_ce_fwd(_ptr(_f32c(logits)), _ptr(targets), _ptr(loss), logits.numel(),
+                                         float(scale), _stream()), 'sigmoid_ce_fwd')
+
+
+def sigmoid_ce_bwd(logits, targets, dloss, dlogits, scale):
+    L.check(L.load().vlfb_sigmoid_ce_bwd(_ptr(_f32c(logits)), _ptr(targets), _ptr(dloss), _ptr(_f32c(dlogits)),
+                                         logits.numel(), float(scale), _stream()), 'sigmoid_ce_bwd')
+
+
+def softmax_ce_fwd(logits, labels, prob, loss, scale):
+    assert labels.dtype == torch.int32
+    L.check(L.load().vlfb_softmax_ce_fwd(_ptr(_f32c(logits)), _ptr(labels), _ptr(_f32c(prob)), _ptr(loss),
+                                         logits.shape[0], logits.shape[1], float(scale), _stream()), 'softmax_ce_fwd')
+
+
+def softmax_ce_bwd(prob, labels, dlogits, scale):
+    L.check(L.load().vlfb_softmax_ce_bwd(_ptr(_f32c(prob)), _ptr(labels), _ptr(_f32c(dlogits)), prob.shape[0],
+                                         prob.shape[1], float(scale), _stream()), 'softmax_ce_bwd')
+
+
+def sgd_nesterov(p, g, m, lr, momentum, wd, nesterov=True, p_tf32=None):
+    """In place: g += wd*p; m' = mu*m + lr*g; p -= (1+mu)*m' - mu*m  (lr is a 1-element device tensor)."""
+    L.check(L.load().vlfb_sgd_nesterov(_ptr(_f32c(p)), _ptr(_f32c(g)), _ptr(_f32c(m)), _ptr(p_tf32), p.numel(), _ptr(lr),
+                                       float(momentum), float(wd), int(bool(nesterov)), _stream()), 'sgd_nesterov')
+
+
+def fbo_attend_fwd(theta, phi, g, prob, y, scale):
+    r, l, d = phi.shape
+    L.check(L.load().vlfb_fbo_attend_fwd(_ptr(_f32c(theta)), _ptr(_f32c(phi)), _ptr(_f32c(g)), _ptr(_f32c(prob)),
+                                         _ptr(_f32c(y)), r, l, d, float(scale), _stream()), 'fbo_attend_fwd')
+
+
+def fbo_attend_bwd(theta, phi, g, prob, dy, dtheta, dphi, dg, scale):
+    r, l, d = phi.shape
+    L.check(L.load().vlfb_fbo_attend_bwd(_ptr(_f32c(theta)), _ptr(_f32c(phi)), _ptr(_f32c(g)), _ptr(_f32c(prob)),
+                                         _ptr(_f32c(dy)), _ptr(_f32c(dtheta)), _ptr(_f32c(dphi)), _ptr(_f32c(dg)),
+                                         r, l, d, float(scale), _stream()), 'fbo_attend_bwd')

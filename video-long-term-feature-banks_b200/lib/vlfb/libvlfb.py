@@ -1,0 +1,107 @@
+"""ctypes binding of libvlfb.so (the C ABI declared in include/vlfb.h).
+
+There is deliberately NO fallback: if the shared library is missing or a CUDA
+device is absent the import of the kernels fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_HERE, '..', '..', 'csrc', 'libvlfb.so'))
+
+OP_DENSE_K, OP_DENSE_MN, OP_CONV_K, OP_DGRAD_K, OP_CONV_MN, OP_STEM_K, OP_STEM_MN = range(7)
+EPI_RELU, EPI_ACCUM, EPI_ATOMIC, EPI_TF32 = 1, 2, 4, 8
+
+
+class ConvGeom(C.Structure):
+    _fields_ = [(n, C.c_int) for n in
+                ('N', 'T', 'H', 'W', 'C', 'To', 'Ho', 'Wo', 'Co', 'kT', 'kH', 'kW',
+                 'sT', 'sH', 'sW', 'pT', 'pH', 'pW', 'dT', 'dH', 'dW')]
+
+
+class Operand(C.Structure):
+    _fields_ = [('ptr', C.c_void_p), ('kind', C.c_int), ('ld', C.c_int64), ('batch_stride', C.c_int64)]
+
+
+class GemmParams(C.Structure):
+    _fields_ = [('a', Operand), ('b', Operand), ('g', ConvGeom),
+                ('M', C.c_int), ('N', C.c_int), ('K', C.c_int),
+                ('batch', C.c_int), ('taps', C.c_int), ('split_k', C.c_int),
+                ('d', C.c_void_p), ('ldd', C.c_int64), ('d_batch_stride', C.c_int64),
+                ('d_tap_stride', C.c_int64), ('alpha', C.c_float),
+                ('col_scale', C.c_void_p), ('col_bias', C.c_void_p), ('row_scale', C.c_void_p),
+                ('residual', C.c_void_p), ('flags', C.c_int)]
+
+
+_P, _I, _L, _F, _U = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
+_GP = C.POINTER(ConvGeom)
+
+# name -> argtypes (restype int unless noted).  Mirrors include/vlfb.h one to one.
+SIGNATURES = {
+    'vlfb_version': [],
+    'vlfb_last_error': [],
+    'vlfb_set_gemm_backend': [_I],
+    'vlfb_get_gemm_backend': [],
+    'vlfb_gemm': [C.POINTER(GemmParams), _P],
+    'vlfb_affine_nd_fwd': [_P, _P, _P, _P, _L, _I, _P],
+    'vlfb_affine_nd_bwd': [_P, _P, _P, _L, _I, _P],
+    'vlfb_maxpool3d_fwd': [_P, _P, _P, _GP, _P],
+    'vlfb_maxpool3d_bwd': [_P, _P, _P, _GP, _P],
+    'vlfb_avgpool3d_fwd': [_P, _P, _GP, _P],
+    'vlfb_avgpool3d_bwd': [_P, _P, _GP, _I, _P],
+    'vlfb_roi_align_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    'vlfb_roi_align_bwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    'vlfb_roi_align_table': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    'vlfb_softmax_fwd': [_P, _P, _L, _I, _F, _P],
+    'vlfb_softmax_bwd': [_P, _P, _P, _L, _I, _F, _P],
+    'vlfb_layernorm_fwd': [_P, _P, _P, _P, _L, _I, _F, _P],
+    'vlfb_layernorm_bwd': [_P, _P, _P, _P, _L, _I, _P],
+    'vlfb_relu_fwd': [_P, _P, _L, _P],
+    'vlfb_relu_bwd': [_P, _P, _P, _L, _P],
+    'vlfb_axpby': [_P, _F, _P, _F, _P, _L, _P],
+    'vlfb_fill': [_P, _F, _L, _P],
+    'vlfb_round_tf32': [_P, _P, _L, _P],
+    'vlfb_sigmoid_fwd': [_P, _P, _L, _P],
+    'vlfb_dropout_fwd': [_P, _P, _L, _F, _U, _U, _P],
+    'vlfb_copy2d': [_P, _L, _P, _L, _L, _I, _I, _P],
+    'vlfb_nc_to_cl': [_P, _P, _I, _I, _L, _I, _P],
+    'vlfb_cl_to_nc': [_P, _P, _I, _I, _L, _I, _P],
+    'vlfb_weight_transpose': [_P, _P, _P, _I, _I, _I, _P],
+    'vlfb_sigmoid_ce_fwd': [_P, _P, _P, _L, _F, _P],
+    'vlfb_sigmoid_ce_bwd': [_P, _P, _P, _P, _L, _F, _P],
+    'vlfb_softmax_ce_fwd': [_P, _P, _P, _P, _I, _I, _F, _P],
+    'vlfb_softmax_ce_bwd': [_P, _P, _P, _I, _I, _F, _P],
+    'vlfb_sgd_nesterov': [_P, _P, _P, _P, _L, _P, _F, _F, _I, _P],
+    'vlfb_fbo_attend_fwd': [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
+    'vlfb_fbo_attend_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
+}
+
+_lib = None
+
+
+def load():
+    """Load libvlfb.so and declare every prototype.  Raises if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            'libvlfb.so not found at %s -- build it first (python -c "import __graft_entry__ as g; '
+            'g.build()" or make -C csrc).  There is no CPU fallback.' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)        # AttributeError if the symbol is missing
+        fn.argtypes = argtypes
+        fn.restype = C.c_char_p if name == 'vlfb_last_error' else C.c_int
+    _lib = lib
+    return lib
+
+
+class VlfbError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().vlfb_last_error()
+        raise VlfbError('%s failed (%d): %s' % (what, rc, msg.decode() if msg else ''))
