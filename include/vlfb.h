@@ -130,7 +130,8 @@ int vlfb_roi_align_table(const float* rois, int32_t* pos, float* w, int32_t* gri
 
 /* ---- row softmax with fused pre-scale (Scale+Softmax: nonlocal_helper.py:96-105,
  *      lfb_helper.py:226-231) -------------------------------------------------------------- */
-int vlfb_softmax_fwd(const float* x, float* p, int64_t rows, int cols, float scale, void* stream);
+/* tf32 != 0: store TF32-rounded probabilities (they are the A operand of the next GEMM) */
+int vlfb_softmax_fwd(const float* x, float* p, int64_t rows, int cols, float scale, int tf32, void* stream);
 int vlfb_softmax_bwd(const float* p, const float* dp, float* dx, int64_t rows, int cols, float scale,
                      void* stream);
 
@@ -145,6 +146,11 @@ int vlfb_relu_fwd(const float* x, float* y, int64_t n, void* stream);
 int vlfb_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream); /* dx = dy*(y>0) */
 int vlfb_axpby(const float* x, float a, const float* y, float b, float* out, int64_t n, void* stream);
 int vlfb_fill(float* x, float v, int64_t n, void* stream);
+/* TF32-rounding variants used where the result feeds a tensor-core GEMM */
+int vlfb_add_tf32(const float* x, const float* y, float* out, int64_t n, void* stream);   /* round(x+y) */
+int vlfb_relu_tf32(const float* x, float* y, int64_t n, void* stream);                    /* round(max(x,0)) */
+/* out[c] (+)= sum_r x[r*ld + c]  (bias gradients of Conv/FC) */
+int vlfb_colsum(const float* x, int64_t ld, float* out, int64_t rows, int cols, int accumulate, void* stream);
 /* y = round-to-nearest TF32 of x (operand preparation for kind::tf32 MMAs; y may alias x) */
 int vlfb_round_tf32(const float* x, float* y, int64_t n, void* stream);
 int vlfb_sigmoid_fwd(const float* x, float* y, int64_t n, void* stream);

@@ -205,7 +205,7 @@ class Graph(object):
         return y
 
     # ---- lfb_helper.py -----------------------------------------------------
-    def fbo_nl_head(self, box, dim_in, lfb, num_lfb_feat, test_mode):
+    def fbo_nl_head(self, box, dim_in, lfb, num_lfb_feat, test_mode, box_name='box_pooled'):
         """add_fbo_nl_head / prepare_nl_input / prepare_lfb / NLLayers / NLCore
         (lfb_helper.py:78-103, 160-338)."""
         cfg = self.cfg
@@ -214,11 +214,11 @@ class Graph(object):
         d = fb.LATENT_DIM
         a, dim_a = box, dim_in
         if fb.INPUT_REDUCE_DIM:
-            a = self.conv(a, 'box_pooled_fbonl_reduc', dim_in, d, (1, 1, 1), no_bias=nb, kind='fc')
+            a = self.conv(a, box_name + '_fbonl_reduc', dim_in, d, (1, 1, 1), no_bias=nb, kind='fc')
             dim_a = d
         if fb.INPUT_DROPOUT_ON and not test_mode:
-            a = self.dropout(a, 'box_pooled_fbonl_reduc_fbonl_drop' if fb.INPUT_REDUCE_DIM
-                             else 'box_pooled_fbonl_drop', fb.DROPOUT_RATE)
+            a = self.dropout(a, (box_name + '_fbonl_reduc_fbonl_drop') if fb.INPUT_REDUCE_DIM
+                             else (box_name + '_fbonl_drop'), fb.DROPOUT_RATE)
         b = None
         if self.run:
             # get_lfb_blob / NTC_to_NCT11 (lfb_helper.py:43-53,155-157)
@@ -278,10 +278,10 @@ class Graph(object):
             self.blobs['fbo_max_out'] = y
         return y, self.cfg.LFB.LFB_DIM
 
-    def fbo_head(self, box, dim_in, lfb, num_lfb_feat, test_mode):
+    def fbo_head(self, box, dim_in, lfb, num_lfb_feat, test_mode, box_name='box_pooled'):
         t = self.cfg.LFB.FBO_TYPE
         if t == 'nl':
-            return self.fbo_nl_head(box, dim_in, lfb, num_lfb_feat, test_mode)
+            return self.fbo_nl_head(box, dim_in, lfb, num_lfb_feat, test_mode, box_name)
         return self.fbo_pool_head(lfb, num_lfb_feat, t)
 
     # ---- head_helper.py ----------------------------------------------------
@@ -323,7 +323,8 @@ class Graph(object):
             self.blobs['res5_2_branch2c_bn_pooled'] = pooled
         heads, dims = [pooled], [dim_in]
         if cfg.LFB.ENABLED and not lfb_infer_only:
-            f, fd = self.fbo_head(pooled, dim_in, lfb, cfg.LFB.WINDOW_SIZE, test_mode)
+            f, fd = self.fbo_head(pooled, dim_in, lfb, cfg.LFB.WINDOW_SIZE, test_mode,
+                                  box_name='res5_2_branch2c_bn_pooled')
             heads.append(f)
             dims.append(fd)
         out = None

@@ -1,0 +1,310 @@
+"""TEST-ONLY stand-in for vlfb.kernels implemented with torch CPU ops.
+
+It lets the host-side logic (net recording, lowering, fusion, autograd tape, ParamStore,
+optimizer plan, data-parallel plumbing) be exercised on a machine without a GPU.  It lives
+under tests/ on purpose: the product package has no CPU path and fails loudly without
+libvlfb.so + CUDA.  Semantics mirror include/vlfb.h; TF32 rounding is the identity here.
+"""
+import torch
+import torch.nn.functional as F
+
+from vlfb import libvlfb as L
+from vlfb.kernels import conv_geom, out_shape, _is_pointwise  # noqa: F401  (pure python helpers)
+
+
+def set_gemm_backend(name):
+    pass
+
+
+def _nc(x):     # [N,T,H,W,C] -> (N,C,T,H,W)
+    return x.permute(0, 4, 1, 2, 3)
+
+
+def _w_nc(w):   # [Co,kT,kH,kW,Ci] -> (Co,Ci,kT,kH,kW)
+    return w.permute(0, 4, 1, 2, 3)
+
+
+def _conv(x, w, g):
+    return F.conv3d(_nc(x), w, None, (g.sT, g.sH, g.sW), (g.pT, g.pH, g.pW), (g.dT, g.dH, g.dW))
+
+
+def _stem_w(w, g):
+    return w[:, :, :, :g.kW, :3].permute(0, 4, 1, 2, 3)
+
+
+def conv_fwd(x, w, y, g, scale=None, bias=None, residual=None, relu=False, tf32_out=False):
+    if g.C == 4:
+        o = F.conv3d(_nc(x)[:, :3], _stem_w(w, g), None, (g.sT, g.sH, g.sW), (g.pT, g.pH, g.pW))
+    else:
+        o = _conv(x, _w_nc(w.view(g.Co, g.kT, g.kH, g.kW, g.C)), g)
+    o = o.permute(0, 2, 3, 4, 1)
+    if scale is not None:
+        o = o * scale
+    if bias is not None:
+        o = o + bias
+    if residual is not None:
+        o = o + residual
+    if relu:
+        o = torch.relu(o)
+    y.copy_(o)
+
+
+def conv_dgrad(dy, wt, dx, g, accumulate=False):
+    taps = g.kT * g.kH * g.kW
+    w = wt.view(g.C, taps, g.Co).permute(2, 1, 0).reshape(g.Co, g.kT, g.kH, g.kW, g.C)
+    x = torch.zeros((g.N, g.C, g.T, g.H, g.W), dtype=dy.dtype, requires_grad=True)
+    y = F.conv3d(x, _w_nc(w), None, (g.sT, g.sH, g.sW), (g.pT, g.pH, g.pW), (g.dT, g.dH, g.dW))
+    y.backward(_nc(dy))
+    r = x.grad.permute(0, 2, 3, 4, 1)
+    if accumulate:
+        dx.add_(r)
+    else:
+        dx.copy_(r)
+
+
+def conv_wgrad(dy, x, dw, g, row_scale=None, col_mask=None):
+    if g.C == 4:
+        w = torch.zeros((g.Co, 3, g.kT, g.kH, g.kW), dtype=dy.dtype, requires_grad=True)
+        y = F.conv3d(_nc(x)[:, :3], w, None, (g.sT, g.sH, g.sW), (g.pT, g.pH, g.pW))
+        y.backward(_nc(dy))
+        gw = torch.zeros_like(dw)
+        gw[:, :, :, :g.kW, :3] = w.grad.permute(0, 2, 3, 4, 1)
+    else:
+        w = torch.zeros((g.Co, g.C, g.kT, g.kH, g.kW), dtype=dy.dtype, requires_grad=True)
+        y = _conv(x, w, g)
+        y.backward(_nc(dy))
+        gw = w.grad.permute(0, 2, 3, 4, 1).reshape(dw.shape)
+    if row_scale is not None:
+        gw = gw * row_scale.view([-1] + [1] * (gw.dim() - 1))
+    dw.add_(gw)
+
+
+def weight_transpose(w, wt, scale=None):
+    co, ci = w.shape[0], w.shape[-1]
+    taps = w.numel() // (co * ci)
+    s = w.reshape(co, taps, ci)
+    if scale is not None:
+        s = s * scale.view(-1, 1, 1)
+    wt.copy_(s.permute(2, 1, 0).reshape(wt.shape))
+
+
+def matmul(a, b, d, alpha=1.0, accumulate=False, bias=None, tf32_out=False):
+    r = torch.bmm(a, b) * alpha
+    if bias is not None:
+        r = r + bias
+    if accumulate:
+        d.add_(r)
+    else:
+        d.copy_(r)
+
+
+def affine_fwd(x, s, b, y):
+    y.copy_(x * s + b)
+
+
+def affine_bwd(dy, s, dx):
+    dx.copy_(dy * s)
+
+
+def _pool_args(g):
+    return (g.kT, g.kH, g.kW), (g.sT, g.sH, g.sW), (g.pT, g.pH, g.pW)
+
+
+def maxpool_fwd(x, y, argmax, g):
+    k, s, p = _pool_args(g)
+    o, idx = F.max_pool3d(_nc(x), k, s, p, return_indices=True)
+    y.copy_(o.permute(0, 2, 3, 4, 1))
+    if argmax is not None:
+        # F returns per-(n,c) flat THW indices; convert to global position index n*THW + idx
+        n = torch.arange(g.N).view(-1, 1, 1, 1, 1) * (g.T * g.H * g.W)
+        argmax.copy_((idx + n).permute(0, 2, 3, 4, 1).to(torch.int32))
+
+
+def maxpool_bwd(dy, argmax, dx, g):
+    c = dy.shape[-1]
+    flat = dx.view(-1, c)
+    idx = argmax.view(-1, c).long()
+    flat.scatter_add_(0, idx, dy.reshape(-1, c))
+
+
+def avgpool_fwd(x, y, g):
+    k, s, p = _pool_args(g)
+    y.copy_(F.avg_pool3d(_nc(x), k, s, p).permute(0, 2, 3, 4, 1))
+
+
+def avgpool_bwd(dy, dx, g, accumulate=False):
+    k, s, p = _pool_args(g)
+    x = torch.zeros((g.N, g.C, g.T, g.H, g.W), dtype=dy.dtype, requires_grad=True)
+    F.avg_pool3d(x, k, s, p).backward(_nc(dy))
+    r = x.grad.permute(0, 2, 3, 4, 1)
+    if accumulate:
+        dx.add_(r)
+    else:
+        dx.copy_(r)
+
+
+def roi_align_fwd(feat, rois, out, spatial_scale, sampling_ratio=0):
+    import torchvision
+    o = torchvision.ops.roi_align(feat.permute(0, 3, 1, 2), rois, (out.shape[1], out.shape[2]), spatial_scale,
+                                  sampling_ratio, False)
+    out.copy_(o.permute(0, 2, 3, 1))
+
+
+def roi_align_bwd(dout, rois, dfeat, spatial_scale, sampling_ratio=0):
+    import torchvision
+    f = torch.zeros(dfeat.permute(0, 3, 1, 2).shape, dtype=dout.dtype, requires_grad=True)
+    o = torchvision.ops.roi_align(f, rois, (dout.shape[1], dout.shape[2]), spatial_scale, sampling_ratio, False)
+    o.backward(dout.permute(0, 3, 1, 2))
+    dfeat.add_(f.grad.permute(0, 2, 3, 1))
+
+
+def softmax_fwd(x, p, scale=1.0, tf32_out=False):
+    p.copy_(torch.softmax(x * scale, dim=-1))
+
+
+def softmax_bwd(p, dp, dx, scale=1.0):
+    dot = (p * dp).sum(-1, keepdim=True)
+    dx.copy_(scale * p * (dp - dot))
+
+
+def layernorm_fwd(x, y, mean, std, cols, eps=1e-5):
+    x2 = x.view(-1, cols)
+    mu = x2.mean(1, keepdim=True)
+    sd = torch.sqrt(((x2 - mu) ** 2).mean(1, keepdim=True) + eps)
+    y.view(-1, cols).copy_((x2 - mu) / sd)
+    if mean is not None:
+        mean.copy_(mu.view(-1))
+    if std is not None:
+        std.copy_(sd.view(-1))
+
+
+def layernorm_bwd(dy, y, std, dx, cols):
+    d2, y2 = dy.view(-1, cols), y.view(-1, cols)
+    a = d2.mean(1, keepdim=True)
+    b = (d2 * y2).mean(1, keepdim=True)
+    dx.view(-1, cols).copy_((d2 - a - y2 * b) / std.view(-1, 1))
+
+
+def relu_fwd(x, y):
+    y.copy_(torch.relu(x))
+
+
+relu_tf32 = relu_fwd
+
+
+def relu_bwd(dy, y, dx):
+    dx.copy_(dy * (y > 0))
+
+
+def axpby(x, a, y, b, out):
+    r = a * x
+    if y is not None and b != 0.0:
+        r = r + b * y
+    out.copy_(r)
+
+
+def add_tf32(x, y, out):
+    out.copy_(x + y)
+
+
+def fill(x, v):
+    x.fill_(v)
+
+
+def round_tf32(x, y):
+    if y.data_ptr() != x.data_ptr():
+        y.copy_(x)
+
+
+def colsum(x, ld, out, rows, cols, accumulate=False):
+    r = x.reshape(-1)[:rows * ld].view(rows, ld)[:, :cols].sum(0)
+    if accumulate:
+        out.view(-1).add_(r)
+    else:
+        out.view(-1).copy_(r)
+
+
+def sigmoid_fwd(x, y):
+    y.copy_(torch.sigmoid(x))
+
+
+def dropout(x, y, ratio, seed, offset):
+    g = torch.Generator().manual_seed(int(seed) * 1000003 + int(offset))
+    mask = (torch.rand(x.shape, generator=g) >= ratio).to(x.dtype)
+    y.copy_(x * mask / (1.0 - ratio))
+
+
+def copy2d(src, lds, dst, ldd, rows, cols, accumulate=False, src_off=0, dst_off=0):
+    s = torch.as_strided(src, (rows, cols), (lds, 1), src.storage_offset() + src_off)
+    d = torch.as_strided(dst, (rows, cols), (ldd, 1), dst.storage_offset() + dst_off)
+    if accumulate:
+        d.add_(s)
+    else:
+        d.copy_(s)
+
+
+def nc_to_cl(src, dst, n, c, inner, cpad=None):
+    cpad = cpad or c
+    d = dst.view(n, inner, cpad)
+    d.zero_()
+    d[:, :, :c] = src.reshape(n, c, inner).permute(0, 2, 1)
+
+
+def cl_to_nc(src, dst, n, c, inner, cpad=None):
+    cpad = cpad or c
+    dst.view(n, c, inner).copy_(src.view(n, inner, cpad)[:, :, :c].permute(0, 2, 1))
+
+
+def _sce(x, t, scale):
+    from oracle import ops as O
+    return O.sigmoid_cross_entropy_loss(x, t, scale)
+
+
+def sigmoid_ce_fwd(logits, targets, loss, scale):
+    loss.copy_(_sce(logits, targets, scale).view(1))
+
+
+def sigmoid_ce_bwd(logits, targets, dloss, dlogits, scale):
+    x = logits.detach().clone().requires_grad_(True)
+    _sce(x, targets, scale).backward()
+    g = x.grad
+    if dloss is not None:
+        g = g * dloss.view(())
+    dlogits.copy_(g)
+
+
+def softmax_ce_fwd(logits, labels, prob, loss, scale):
+    from oracle import ops as O
+    p, l = O.softmax_with_loss(logits, labels, scale)
+    prob.copy_(p)
+    loss.copy_(l.view(1))
+
+
+def softmax_ce_bwd(prob, labels, dlogits, scale):
+    onehot = torch.zeros_like(prob)
+    onehot[torch.arange(prob.shape[0]), labels.long()] = 1.0
+    dlogits.copy_((prob - onehot) * scale / prob.shape[0])
+
+
+def sgd_nesterov(p, g, m, lr, momentum, wd, nesterov=True, p_tf32=None):
+    lr = float(lr.view(-1)[0])
+    gi = g + wd * p
+    mn = momentum * m + lr * gi
+    ng = (1 + momentum) * mn - momentum * m if nesterov else mn
+    m.copy_(mn)
+    g.copy_(ng)
+    p.sub_(ng)
+    if p_tf32 is not None:
+        p_tf32.copy_(p)
+
+
+def install():
+    """Route vlfb.executor / vlfb.workspace onto this module and the CPU device."""
+    import sys
+    from vlfb import executor
+    executor.set_backend(sys.modules[__name__], 'cpu', torch.float64)
+
+
+def uninstall():
+    from vlfb import executor, kernels
+    executor.set_backend(kernels, 'cuda', torch.float32)

@@ -1,0 +1,131 @@
+"""Host-logic tests on CPU: the recorded net, its lowering/fusion, the autograd tape, the
+ParamStore and the optimizer are run through a torch-CPU kernel stand-in (tests/fake_kernels.py)
+and compared with the oracle (forward blobs, loss, every parameter gradient, one SGD step)."""
+import numpy as np
+import pytest
+import torch
+
+import harness as H
+
+TINY = ['NUM_GPUS', 1, 'TRAIN.BATCH_SIZE', 2, 'TRAIN.CROP_SIZE', 64, 'TRAIN.VIDEO_LENGTH', 8,
+        'TEST.BATCH_SIZE', 2, 'TEST.CROP_SIZE', 64, 'TEST.VIDEO_LENGTH', 8, 'LFB.WINDOW_SIZE', 4,
+        'TRAIN.DROPOUT_RATE', 0.0, 'FBO_NL.INPUT_DROPOUT_ON', False, 'FBO_NL.LFB_DROPOUT_ON', False]
+
+
+@pytest.fixture
+def fake():
+    import fake_kernels
+    from vlfb import workspace
+    fake_kernels.install()
+    workspace.ResetWorkspace()
+    yield fake_kernels
+    workspace.ResetWorkspace()
+    fake_kernels.uninstall()
+
+
+def _run(yaml_name, overrides, fake, check_blobs):
+    from oracle import model as OM
+    from vlfb import workspace
+    H.setup_cfg(yaml_name, overrides)
+    ocfg = H.oracle_cfg(yaml_name, overrides)
+    params = OM.make_params(ocfg, seed=2)
+    inputs = OM.make_inputs(ocfg, n_clips=2, rois_per_clip=2, crop=64, frames=8)
+    model, sfx = H.build('train', True)
+    H.feed_params(params)
+    H.feed_inputs(inputs, sfx)
+    # oracle forward/backward in fp64
+    p64 = dict((k, v.double().requires_grad_(True)) for k, v in params.items())
+    i64 = dict((k, (v.double() if v.dtype == torch.float32 else v)) for k, v in inputs.items())
+    blobs, prob, loss = OM.forward(ocfg, p64, i64, 'train')
+    loss.backward()
+    # product: forward + backward only (no update) to compare gradients
+    net = workspace.current().nets[model.net.Proto().name]
+    upd, net.update_ops = net.update_ops, []
+    workspace.RunNet(model.net.Proto().name)
+    net.update_ops = upd
+    assert H.rel(workspace.FetchBlob('gpu_0/loss'), loss.item()) < 1e-9
+    for b in check_blobs:
+        assert H.rel(workspace.FetchBlob('gpu_0/' + b), blobs[b].detach().numpy()) < 1e-9, b
+    trainable = model.TrainableParams()
+    expected = [k for k in params if not (k.endswith('_bn_s') or k.endswith('_bn_b'))]
+    assert sorted(trainable) == sorted(expected)
+    worst = 0.0
+    for name in trainable:
+        g = workspace.FetchBlob('gpu_0/' + name + '_grad')
+        ref = p64[name].grad.numpy()
+        e = float(np.abs(g - ref).max() / max(np.abs(ref).max(), 1e-5))   # e.g. phi_b has a zero gradient
+        worst = max(worst, e)
+        assert e < 1e-7, (name, e)
+    print("worst grad rel err", worst)
+    return model, params, p64, worst
+
+
+def test_ava_fbo_nl_forward_backward_matches_oracle(fake):
+    _run('ava_r50_lfb_nl.yaml', TINY, fake,
+         ['pool1', 'res2_2_branch2c_bn', 'nonlocal_conv3_1_sum', 'res3_3_branch2c_bn', 'nonlocal_conv4_1_sum',
+          'res5_2_branch2c_bn', 'blob_pooled', 'roi_feat_3d', 'box_pooled', 'lfb_1x1', 'lfb_nl0_affinity_prob',
+          'lfb_nl1_sum', 'pool5', 'pred', 'prob'])
+
+
+def test_charades_post_act_variant(fake):
+    _run('charades_r50_lfb_nl.yaml', TINY + ['MODEL.NUM_CLASSES', 157], fake, ['pool5', 'pred'])
+
+
+@pytest.mark.parametrize('yaml_name', ['ava_r50_lfb_avg.yaml', 'ava_r50_lfb_max.yaml', 'ava_r50_baseline.yaml'])
+def test_other_heads(fake, yaml_name):
+    _run(yaml_name, TINY, fake, ['pool5', 'pred'])
+
+
+def test_sgd_step_matches_oracle(fake):
+    from oracle import ops as O
+    from core.config import config as cfg
+    from vlfb import workspace
+    model, params, p64, _ = _run('ava_r50_lfb_nl.yaml', TINY, fake, [])
+    model.UpdateWorkspaceLr(10)
+    lr = float(workspace.FetchBlob('gpu_0/lr'))
+    workspace.RunNet(model.net.Proto().name)          # full step (momentum starts at 0)
+    for name in ['conv1_w', 'res4_3_branch2b_w', 'nonlocal_conv4_1_theta_b', 'lfb_nl1_out_w', 'pred_w', 'pred_b']:
+        p_ref, m_ref = O.nesterov_update(params[name].double(), p64[name].grad, torch.zeros_like(p64[name]), lr,
+                                         cfg.SOLVER.MOMENTUM, cfg.SOLVER.WEIGHT_DECAY)
+        assert H.rel(workspace.FetchBlob('gpu_0/' + name), p_ref.detach().numpy()) < 1e-5, name
+        assert H.rel(workspace.FetchBlob('gpu_0/' + name + '_momentum'), m_ref.detach().numpy()) < 1e-4, name
+    # frozen affine parameters must not move
+    assert np.array_equal(workspace.FetchBlob('gpu_0/res2_0_branch2a_bn_s'), params['res2_0_branch2a_bn_s'].numpy())
+
+
+def test_test_split_graph_and_lfb_infer_only(fake):
+    from oracle import model as OM
+    from vlfb import workspace
+    ov = TINY
+    H.setup_cfg('ava_r50_lfb_nl.yaml', ov)
+    ocfg = H.oracle_cfg('ava_r50_lfb_nl.yaml', ov)
+    params = OM.make_params(ocfg, seed=2, split='val', lfb_infer_only=True)
+    inputs = OM.make_inputs(ocfg, n_clips=2, rois_per_clip=3, crop=64, frames=8)
+    model, sfx = H.build('val', False, lfb_infer_only=True)
+    H.feed_params(params)
+    H.feed_inputs(inputs, sfx)
+    workspace.RunNet(model.net.Proto().name)
+    blobs, _, _ = OM.forward(ocfg, params, inputs, 'val', lfb_infer_only=True)
+    assert H.rel(workspace.FetchBlob('gpu_0/box_pooled'), blobs['box_pooled'].numpy()) < 1e-4
+    assert not workspace.HasBlob('gpu_0/pred')
+
+
+def test_fusion_plan(fake):
+    """Every conv is lowered with its AffineNd (and Sum/Relu where the reference has them) fused."""
+    from vlfb import executor as X
+    from vlfb import workspace
+    H.setup_cfg('ava_r50_lfb_nl.yaml', TINY)
+    model, _ = H.build('train', True)
+    net = workspace.current().nets[model.net.Proto().name]
+    convs = [s for s in net.steps if isinstance(s, X.ConvStep)]
+    by_name = dict((s.out, s) for s in convs)
+    assert len([s for s in net.steps if isinstance(s, X.AffineStep)]) == 0
+    assert by_name['res_conv1_bn'].relu and by_name['res_conv1_bn'].affine
+    s = by_name['res3_1_branch2c_bn']
+    assert s.relu and s.affine and s.res_key[0] == 'res3_0_branch2c_bn'
+    s = by_name['res2_0_branch2c_bn']
+    assert s.relu and s.res_key[0] == 'res2_0_branch1_bn'
+    s = by_name['nonlocal_conv4_1_sum']
+    assert s.affine and s.res_key[0] == 'res4_1_branch2c_bn' and not s.relu and s.b
+    assert len([s for s in net.steps if isinstance(s, X.ScaleStep)]) == 0       # folded into the softmax
+    assert len(convs) == 53 + 20 + 2 + 8

@@ -1,0 +1,391 @@
+"""GPU parity tests of the individual kernels, called through the C ABI (ctypes) and
+checked against fp64 PyTorch-CPU references / the oracle.  TF32 tolerance: operands are
+pre-rounded to TF32 so the tensor-core result must match fp64 to accumulation error."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import rel_err, stem_pack, tf32_round, to_cl, to_nc, w_to_cl
+
+pytestmark = pytest.mark.gpu
+
+BACKENDS = ['tcgen05', 'simt']
+
+
+@pytest.fixture(scope='module')
+def K():
+    from vlfb import kernels
+    assert torch.cuda.is_available()
+    yield kernels
+    kernels.set_gemm_backend('tcgen05')
+
+
+def rnd(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return tf32_round(torch.randn(shape, generator=g) * scale)
+
+
+# -------------------------------------------------------------------------- dense matmul
+@pytest.mark.parametrize('backend', BACKENDS)
+@pytest.mark.parametrize('ta,tb', [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize('B,M,N,K_', [(1, 128, 128, 64), (2, 200, 80, 300), (3, 1, 300, 512), (1, 264, 512, 96),
+                                       (2, 392, 196, 128)])
+def test_matmul_layouts(K, backend, ta, tb, B, M, N, K_):
+    K.set_gemm_backend(backend)
+    if ta and M % 4:
+        pytest.skip('MN-major A needs M % 4 == 0')
+    if tb == 0 and N % 4:
+        pytest.skip('MN-major B needs N % 4 == 0')
+    a = rnd((B, K_, M) if ta else (B, M, K_), 1)
+    b = rnd((B, N, K_) if tb else (B, K_, N), 2)
+    A = a.transpose(1, 2) if ta else a
+    Bm = b.transpose(1, 2) if tb else b
+    ref = torch.bmm(A.double(), Bm.double()) * 0.5
+    ad, bd = a.cuda(), b.cuda()
+    d = torch.full((B, M, N), float('nan'), device='cuda')
+    K.matmul(ad.transpose(1, 2) if ta else ad, bd.transpose(1, 2) if tb else bd, d, alpha=0.5)
+    torch.cuda.synchronize()
+    assert rel_err(d, ref) < 2e-5
+    # transposed (column-major) output + accumulate
+    dt = torch.ones((B, N, M), device='cuda')
+    K.matmul(ad.transpose(1, 2) if ta else ad, bd.transpose(1, 2) if tb else bd, dt.transpose(1, 2), alpha=0.5,
+             accumulate=True) if M % 4 == 0 and N % 4 == 0 else None
+    if M % 4 == 0 and N % 4 == 0:
+        torch.cuda.synchronize()
+        assert rel_err(dt.transpose(1, 2), ref + 1.0) < 2e-5
+
+
+# -------------------------------------------------------------------------- convolution
+GEOMS = [
+    # N, T, H, W, Ci, Co, kernels, strides, pads, dilations
+    (2, 4, 8, 8, 32, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), (1, 1, 1)),
+    (1, 3, 9, 10, 64, 32, (1, 3, 3), (1, 1, 1), (0, 1, 1), (1, 1, 1)),
+    (2, 2, 14, 14, 32, 96, (1, 3, 3), (1, 2, 2), (0, 1, 1), (1, 1, 1)),
+    (1, 2, 14, 14, 64, 64, (1, 3, 3), (1, 1, 1), (0, 2, 2), (1, 2, 2)),
+    (2, 3, 6, 6, 64, 160, (1, 1, 1), (1, 1, 1), (0, 0, 0), (1, 1, 1)),
+    (2, 2, 8, 8, 32, 64, (1, 1, 1), (1, 2, 2), (0, 0, 0), (1, 1, 1)),
+    (1, 4, 7, 7, 256, 288, (3, 1, 1), (1, 1, 1), (1, 0, 0), (1, 1, 1)),
+]
+
+
+def _conv_ref(x, w, strides, pads, dil):
+    return F.conv3d(x.double(), w.double(), None, strides, pads, dil)
+
+
+@pytest.mark.parametrize('backend', BACKENDS)
+@pytest.mark.parametrize('geom', GEOMS)
+def test_conv_fwd_dgrad_wgrad(K, backend, geom):
+    K.set_gemm_backend(backend)
+    N, T, H, W, Ci, Co, ker, st, pd, dil = geom
+    x = rnd((N, Ci, T, H, W), 3)
+    w = rnd((Co, Ci) + ker, 4, 0.1)
+    s = torch.rand(Co) + 0.5
+    b = torch.randn(Co) * 0.1
+    xd = x.double().requires_grad_(True)
+    wd = w.double().requires_grad_(True)
+    y = F.conv3d(xd, wd, None, st, pd, dil)
+    res = rnd(tuple(y.shape), 5)
+    out_ref = torch.relu(y * s.double().view(1, -1, 1, 1, 1) + b.double().view(1, -1, 1, 1, 1) + res.double())
+    g = K.conv_geom((N, T, H, W, Ci), Co, ker, st, pd, dil)
+    assert K.out_shape(g) == (N, y.shape[2], y.shape[3], y.shape[4], Co)
+    x_cl, w_cl = to_cl(x).cuda(), w_to_cl(w).cuda()
+    yd = torch.full(K.out_shape(g), float('nan'), device='cuda')
+    K.conv_fwd(x_cl, w_cl, yd, g, scale=s.cuda(), bias=b.cuda(), residual=to_cl(res).cuda(), relu=True)
+    torch.cuda.synchronize()
+    assert rel_err(to_nc(yd), out_ref) < 2e-5
+    # plain (no epilogue) forward
+    K.conv_fwd(x_cl, w_cl, yd, g)
+    torch.cuda.synchronize()
+    assert rel_err(to_nc(yd), y) < 2e-5
+    # backward
+    dy = rnd(tuple(y.shape), 6)
+    y.backward(dy.double())
+    dy_cl = to_cl(dy).cuda()
+    taps = ker[0] * ker[1] * ker[2]
+    wt = torch.empty((Ci, taps, Co), device='cuda')
+    K.weight_transpose(w_cl, wt)
+    torch.cuda.synchronize()
+    assert torch.equal(wt.cpu(), w_to_cl(w).reshape(Co, taps, Ci).permute(2, 1, 0))
+    dx = torch.full((N, T, H, W, Ci), float('nan'), device='cuda')
+    K.conv_dgrad(dy_cl, wt, dx, g)
+    torch.cuda.synchronize()
+    assert rel_err(to_nc(dx), xd.grad) < 2e-5
+    K.conv_dgrad(dy_cl, wt, dx, g, accumulate=True)
+    torch.cuda.synchronize()
+    assert rel_err(to_nc(dx), 2 * xd.grad) < 2e-5
+    dw = torch.zeros((Co,) + ker + (Ci,), device='cuda')
+    K.conv_wgrad(dy_cl, x_cl, dw, g)
+    torch.cuda.synchronize()
+    assert rel_err(dw.permute(0, 4, 1, 2, 3), wd.grad) < 2e-5
+
+
+@pytest.mark.parametrize('backend', BACKENDS)
+def test_stem_conv(K, backend):
+    K.set_gemm_backend(backend)
+    N, T, S = 2, 6, 20
+    x = rnd((N, 3, T, S, S), 7)
+    w = rnd((64, 3, 5, 7, 7), 8, 0.1)
+    xd = x.double().requires_grad_(True)
+    wd = w.double().requires_grad_(True)
+    y = F.conv3d(xd, wd, None, (1, 2, 2), (2, 3, 3))
+    g = K.conv_geom((N, T, S, S, 4), 64, (5, 7, 7), (1, 2, 2), (2, 3, 3))
+    x4 = torch.zeros((N, T, S, S, 4))
+    x4[..., :3] = to_cl(x)
+    x4 = x4.cuda()
+    ws = stem_pack(w).cuda()
+    yd = torch.full(K.out_shape(g), float('nan'), device='cuda')
+    K.conv_fwd(x4, ws, yd, g)
+    torch.cuda.synchronize()
+    assert rel_err(to_nc(yd), y) < 2e-5
+    dy = rnd(tuple(y.shape), 9)
+    y.backward(dy.double())
+    dw = torch.zeros((64, 5, 7, 8, 4), device='cuda')
+    mask = torch.ones((8, 4))
+    mask[7, :] = 0
+    mask[:, 3] = 0
+    K.conv_wgrad(to_cl(dy).cuda(), x4, dw, g, col_mask=mask.reshape(32).cuda())
+    torch.cuda.synchronize()
+    ref = stem_pack(wd.grad)
+    assert rel_err(dw, ref) < 2e-5
+    assert float(dw[:, :, :, 7, :].abs().max()) == 0.0 and float(dw[..., 3].abs().max()) == 0.0
+
+
+# -------------------------------------------------------------------------- TF32 rounding
+def test_round_tf32(K):
+    x = torch.randn(10007)
+    y = torch.empty_like(x).cuda()
+    K.round_tf32(x.cuda(), y)
+    assert torch.equal(y.cpu(), tf32_round(x))
+
+
+def test_truncation_vs_rounding(K):
+    """Documents what the tensor core does with un-rounded fp32 operands (info for DESIGN.md)."""
+    K.set_gemm_backend('tcgen05')
+    g = torch.Generator().manual_seed(11)
+    a = torch.randn((1, 128, 256), generator=g)
+    b = torch.randn((1, 256, 128), generator=g)
+    d = torch.empty((1, 128, 128), device='cuda')
+    K.matmul(a.cuda(), b.cuda(), d)
+    ref_exact = torch.bmm(a.double(), b.double())
+    ref_rna = torch.bmm(tf32_round(a).double(), tf32_round(b).double())
+    trunc = lambda t: (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+    ref_trunc = torch.bmm(trunc(a).double(), trunc(b).double())
+    print('raw fp32 operands: err vs exact %.3e, vs rna-rounded %.3e, vs truncated %.3e' % (
+        rel_err(d, ref_exact), rel_err(d, ref_rna), rel_err(d, ref_trunc)))
+    assert rel_err(d, ref_exact) < 5e-3
+
+
+# -------------------------------------------------------------------------- streaming ops
+def test_affine_nd(K):
+    from oracle import ops as O
+    x = torch.randn(2, 64, 3, 5, 5)
+    s, b = torch.rand(64) + 0.5, torch.randn(64)
+    y = torch.empty((2, 3, 5, 5, 64), device='cuda')
+    K.affine_fwd(to_cl(x).cuda(), s.cuda(), b.cuda(), y)
+    assert rel_err(to_nc(y), O.affine_nd(x, s, b)) < 1e-6
+    K.affine_bwd(to_cl(x).cuda(), s.cuda(), y)
+    assert rel_err(to_nc(y), O.affine_nd_grad(x, s)) < 1e-6
+
+
+@pytest.mark.parametrize('ker,st,pd,shape', [((1, 3, 3), (1, 2, 2), (0, 1, 1), (2, 64, 4, 12, 12)),
+                                             ((2, 1, 1), (2, 1, 1), (0, 0, 0), (2, 32, 8, 6, 6)),
+                                             ((1, 2, 2), (1, 2, 2), (0, 0, 0), (3, 64, 4, 14, 14)),
+                                             ((1, 7, 7), (1, 1, 1), (0, 0, 0), (5, 128, 1, 7, 7))])
+def test_maxpool(K, ker, st, pd, shape):
+    x = torch.randn(shape).double().requires_grad_(True)
+    y = F.max_pool3d(x, ker, st, pd)
+    dy = torch.randn(y.shape).double()
+    y.backward(dy)
+    N, Cc, T, H, W = shape
+    g = K.conv_geom((N, T, H, W, Cc), Cc, ker, st, pd)
+    xd = to_cl(x.detach().float()).cuda()
+    yd = torch.empty(K.out_shape(g), device='cuda')
+    arg = torch.empty(K.out_shape(g), dtype=torch.int32, device='cuda')
+    K.maxpool_fwd(xd, yd, arg, g)
+    assert rel_err(to_nc(yd), y) < 1e-6
+    dx = torch.zeros_like(xd)
+    K.maxpool_bwd(to_cl(dy.float()).cuda(), arg, dx, g)
+    assert rel_err(to_nc(dx), x.grad) < 1e-5
+
+
+@pytest.mark.parametrize('ker,shape', [((4, 1, 1), (2, 64, 4, 7, 7)), ((4, 7, 7), (2, 64, 4, 7, 7)),
+                                       ((20, 1, 1), (3, 128, 20, 1, 1))])
+def test_avgpool(K, ker, shape):
+    x = torch.randn(shape).double().requires_grad_(True)
+    y = F.avg_pool3d(x, ker, (1, 1, 1))
+    dy = torch.randn(y.shape).double()
+    y.backward(dy)
+    N, Cc, T, H, W = shape
+    g = K.conv_geom((N, T, H, W, Cc), Cc, ker, (1, 1, 1), (0, 0, 0))
+    xd = to_cl(x.detach().float()).cuda()
+    yd = torch.empty(K.out_shape(g), device='cuda')
+    K.avgpool_fwd(xd, yd, g)
+    assert rel_err(to_nc(yd), y) < 1e-5
+    dx = torch.empty_like(xd)
+    K.avgpool_bwd(to_cl(dy.float()).cuda(), dx, g)
+    assert rel_err(to_nc(dx), x.grad) < 1e-5
+
+
+def _rois(n_img, r, size, seed):
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.randint(0, n_img, (r,), generator=g).float()
+    x1 = torch.rand(r, generator=g) * size * 0.6
+    y1 = torch.rand(r, generator=g) * size * 0.6
+    x2 = torch.clamp(x1 + torch.rand(r, generator=g) * size * 0.6 + 2, max=size - 1)
+    y2 = torch.clamp(y1 + torch.rand(r, generator=g) * size * 0.6 + 2, max=size - 1)
+    rois = torch.stack([idx, x1, y1, x2, y2], 1)
+    rois[0, 1:] = torch.tensor([0., 0., size - 1., size - 1.])      # full frame
+    rois[1, 1:] = torch.tensor([3.3, 4.4, 3.9, 5.0])                # degenerate (< 1 cell)
+    return rois
+
+
+def test_roi_align_index_math_bit_exact(K):
+    from oracle import roi_align_np
+    for size, hw in ((224, 14), (256, 16)):
+        rois = _rois(2, 40, size, 13 + size)
+        pos, wts, grid = K.roi_align_table(rois.cuda(), hw, hw, 7, 7, 3, 1.0 / 16)
+        pos, wts, grid = pos.cpu().numpy(), wts.cpu().numpy(), grid.cpu().numpy()
+        table = roi_align_np.sample_table(rois.numpy(), hw, hw, 7, 7, 1.0 / 16, 0)
+        for r, t in enumerate(table):
+            assert (grid[r, 0], grid[r, 1]) == (t['grid_h'], t['grid_w'])
+            gh, gw = t['grid_h'], t['grid_w']
+            assert np.array_equal(pos[r, :, :, :gh, :gw], t['pos'])
+            assert np.array_equal(wts[r, :, :, :gh, :gw].view(np.int32), t['w'].view(np.int32))   # bit-exact
+
+
+def test_roi_align_fwd_bwd(K):
+    import torchvision
+    feat = torch.randn(2, 64, 14, 14).double().requires_grad_(True)
+    rois = _rois(2, 9, 224, 3)
+    out = torchvision.ops.roi_align(feat, rois.double(), (7, 7), 1.0 / 16, 0, False)
+    dout = torch.randn(out.shape).double()
+    out.backward(dout)
+    fd = feat.detach().float().permute(0, 2, 3, 1).contiguous().cuda()
+    od = torch.empty((9, 7, 7, 64), device='cuda')
+    K.roi_align_fwd(fd, rois.cuda(), od, 1.0 / 16)
+    assert rel_err(od.permute(0, 3, 1, 2), out) < 1e-5
+    df = torch.zeros_like(fd)
+    K.roi_align_bwd(dout.float().permute(0, 2, 3, 1).contiguous().cuda(), rois.cuda(), df, 1.0 / 16)
+    assert rel_err(df.permute(0, 3, 1, 2), feat.grad) < 1e-5
+
+
+@pytest.mark.parametrize('rows,cols', [(37, 784), (5, 300), (3, 3600), (64, 20)])
+def test_softmax(K, rows, cols):
+    x = (torch.randn(rows, cols) * 3).double().requires_grad_(True)
+    p = torch.softmax(x * 0.25, dim=1)
+    dp = torch.randn(rows, cols).double()
+    p.backward(dp)
+    pd = torch.empty((rows, cols), device='cuda')
+    K.softmax_fwd(x.detach().float().cuda(), pd, 0.25)
+    assert rel_err(pd, p) < 1e-5
+    dx = torch.empty_like(pd)
+    K.softmax_bwd(pd, dp.float().cuda(), dx, 0.25)
+    assert rel_err(dx, x.grad) < 1e-4
+
+
+def test_layernorm(K):
+    from oracle import ops as O
+    x = torch.randn(7, 512).double().requires_grad_(True)
+    y, mean, std = O.layer_norm_axis1(x)
+    dy = torch.randn(7, 512).double()
+    y.backward(dy)
+    yd = torch.empty((7, 512), device='cuda')
+    md, sd = torch.empty(7, device='cuda'), torch.empty(7, device='cuda')
+    K.layernorm_fwd(x.detach().float().cuda(), yd, md, sd, 512)
+    assert rel_err(yd, y) < 1e-5 and rel_err(sd, std.view(-1)) < 1e-5 and rel_err(md, mean.view(-1)) < 1e-4
+    dx = torch.empty_like(yd)
+    K.layernorm_bwd(dy.float().cuda(), yd, sd, dx, 512)
+    assert rel_err(dx, x.grad) < 1e-4
+
+
+def test_elementwise_and_layout(K):
+    x = torch.randn(1003)
+    y = torch.randn(1003)
+    o = torch.empty(1003, device='cuda')
+    K.relu_fwd(x.cuda(), o)
+    assert torch.equal(o.cpu(), torch.relu(x))
+    K.relu_bwd(x.cuda(), y.cuda(), o)
+    assert torch.equal(o.cpu(), x * (y > 0))
+    K.axpby(x.cuda(), 2.0, y.cuda(), -0.5, o)
+    assert rel_err(o, 2 * x - 0.5 * y) < 1e-6
+    K.fill(o, 3.0)
+    assert float(o.min()) == 3.0 and float(o.max()) == 3.0
+    K.sigmoid_fwd(x.cuda(), o)
+    assert rel_err(o, torch.sigmoid(x)) < 1e-6
+    # layouts
+    t = torch.randn(2, 3, 4, 5, 6)
+    cl = torch.empty((2, 4, 5, 6, 4), device='cuda')
+    K.nc_to_cl(t.cuda(), cl, 2, 3, 4 * 5 * 6, 4)
+    assert torch.equal(cl[..., :3].cpu(), to_cl(t)) and float(cl[..., 3].abs().max()) == 0
+    t2 = torch.randn(3, 70, 2, 3, 3)
+    cl2 = torch.empty((3, 2, 3, 3, 70), device='cuda')
+    K.nc_to_cl(t2.cuda(), cl2, 3, 70, 18)
+    assert torch.equal(cl2.cpu(), to_cl(t2))
+    back = torch.empty((3, 70, 2, 3, 3), device='cuda')
+    K.cl_to_nc(cl2, back, 3, 70, 18)
+    assert torch.equal(back.cpu(), t2)
+    # copy2d / dropout
+    src = torch.randn(5, 7).cuda()
+    dst = torch.zeros(5, 20).cuda()
+    K.copy2d(src, 7, dst, 20, 5, 7, dst_off=8)
+    assert torch.equal(dst[:, 8:15], src) and float(dst[:, :8].abs().max()) == 0
+    big = torch.ones(100000).cuda()
+    out = torch.empty_like(big)
+    K.dropout(big, out, 0.3, 1234, 0)
+    keep = float((out > 0).float().mean())
+    assert abs(keep - 0.7) < 0.01 and abs(float(out.max()) - 1 / 0.7) < 1e-5
+    out2 = torch.empty_like(big)
+    K.dropout(big, out2, 0.3, 1234, 0)
+    assert torch.equal(out, out2)
+
+
+def test_losses_and_sgd(K):
+    from oracle import ops as O
+    x = (torch.randn(6, 80) * 2).double().requires_grad_(True)
+    t = (torch.rand(6, 80) < 0.1).int()
+    t[0, :5] = -1
+    loss = O.sigmoid_cross_entropy_loss(x, t, 0.125)
+    loss.backward()
+    ld = torch.empty(1, device='cuda')
+    K.sigmoid_ce_fwd(x.detach().float().cuda(), t.cuda(), ld, 0.125)
+    assert rel_err(ld, loss.view(1)) < 1e-5
+    dx = torch.empty((6, 80), device='cuda')
+    K.sigmoid_ce_bwd(x.detach().float().cuda(), t.cuda(), None, dx, 0.125)
+    assert rel_err(dx, x.grad) < 1e-5
+    x2 = torch.randn(5, 157).double().requires_grad_(True)
+    lab = torch.randint(0, 157, (5,)).int()
+    prob, l2 = O.softmax_with_loss(x2, lab, 0.5)
+    l2.backward()
+    pd, l2d = torch.empty((5, 157), device='cuda'), torch.empty(1, device='cuda')
+    K.softmax_ce_fwd(x2.detach().float().cuda(), lab.cuda(), pd, l2d, 0.5)
+    assert rel_err(pd, prob) < 1e-5 and rel_err(l2d, l2.view(1)) < 1e-5
+    dx2 = torch.empty_like(pd)
+    K.softmax_ce_bwd(pd, lab.cuda(), dx2, 0.5)
+    assert rel_err(dx2, x2.grad) < 1e-5
+    p, g, m = torch.randn(1001), torch.randn(1001), torch.randn(1001)
+    pr, mr = O.nesterov_update(p.double(), g.double(), m.double(), 0.04, 0.9, 1e-3)
+    pd_, gd_, md_ = p.cuda(), g.cuda(), m.cuda()
+    pt = torch.empty_like(pd_)
+    K.sgd_nesterov(pd_, gd_, md_, torch.tensor([0.04], device='cuda'), 0.9, 1e-3, True, pt)
+    assert rel_err(pd_, pr) < 1e-6 and rel_err(md_, mr) < 1e-6
+    assert torch.equal(pt.cpu(), tf32_round(pd_.cpu()))
+
+
+def test_fbo_attend(K):
+    R, Lb, d = 3, 300, 512
+    th = (torch.randn(R, d) * 0.3).double().requires_grad_(True)
+    ph = (torch.randn(R, Lb, d) * 0.3).double().requires_grad_(True)
+    gg = torch.randn(R, Lb, d).double().requires_grad_(True)
+    sc = d ** -0.5
+    p = torch.softmax(torch.einsum('rd,rld->rl', th, ph) * sc, dim=1)
+    y = torch.einsum('rl,rld->rd', p, gg)
+    dy = torch.randn(R, d).double()
+    y.backward(dy)
+    f = lambda t: t.detach().float().cuda()
+    pd, yd = torch.empty((R, Lb), device='cuda'), torch.empty((R, d), device='cuda')
+    K.fbo_attend_fwd(f(th), f(ph), f(gg), pd, yd, sc)
+    assert rel_err(pd, p) < 1e-5 and rel_err(yd, y) < 1e-5
+    dth, dph, dg = torch.empty_like(yd), torch.empty((R, Lb, d), device='cuda'), torch.empty((R, Lb, d), device='cuda')
+    K.fbo_attend_bwd(f(th), f(ph), f(gg), pd, f(dy), dth, dph, dg, sc)
+    assert rel_err(dth, th.grad) < 1e-4 and rel_err(dph, ph.grad) < 1e-4 and rel_err(dg, gg.grad) < 1e-5

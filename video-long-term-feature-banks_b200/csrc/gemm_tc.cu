@@ -16,6 +16,8 @@
 // Operand kinds are described in include/vlfb.h; their element-level definition is
 // operand_elem() in common.cuh, which the SIMT engine evaluates literally and the tests
 // compare this kernel against.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vlfb {
@@ -112,13 +114,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                 uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);                 // [0,14)  start address
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;        // [16,30) leading byte offset
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;        // [32,46) stride byte offset
   d |= (uint64_t)1 << 46;                                  // [46,48) descriptor version 1 (sm_100)
-  d |= (uint64_t)2 << 61;                                  // [61,64) SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;                        // [61,64) 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): tf32 x tf32 -> f32, M=128, N=bn.
@@ -253,7 +256,7 @@ struct KLoader {
 
 // ---------------------------------------------------------------- MN-major loaders
 // Tile = 32 k-rows, each `rows`*4 bytes of the m (or n) extent, stored as
-// [k-group of 8][atom of 32 elements][8 k-rows][128 B] (UMMA canonical MN-major SWIZZLE_128B).
+// [k-group of 4][atom of 32 elements][4 k-rows][128 B] (UMMA canonical MN-major SWIZZLE_128B_BASE32B).
 template <int KIND>
 struct MNLoader {
   const float* base;
@@ -301,8 +304,12 @@ struct MNLoader {
         ok = ok && (unsigned)ti < (unsigned)g.T && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
         if (ok) src = base + ((((int64_t)o.n * g.T + ti) * g.H + hi) * g.W + wi) * 4;
       }
-      const int r = kk & 7;
-      const uint32_t dst = tile + (kk >> 3) * (natoms * 1024) + (c >> 3) * 1024 + r * 128 + (((c & 7) ^ r) << 4);
+      // SWIZZLE_128B_BASE32B (the MN-major layout 32-bit operands need; plain SWIZZLE_128B returns
+      // zeros for tf32 -- measured, profiles/r01_gemm_layout_diag.txt): atoms of 4 k-rows x 128 B,
+      // 32-byte units XOR (k & 3).
+      const int r = kk & 3, cc = c & 7;
+      const uint32_t dst = tile + (kk >> 2) * (natoms * 512) + (c >> 3) * 512 + r * 128 +
+                           ((((cc >> 1) ^ r) << 5) | ((cc & 1) << 4));
       cp_async16(dst, src, ok);
     }
   }
@@ -457,10 +464,11 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_param
         const uint32_t b_tile = a_tile + A_TILE_BYTES;
 #pragma unroll
         for (int j = 0; j < KC / 8; ++j) {   // UMMA K = 8 for tf32
-          const uint64_t da = is_mn(AK) ? make_desc(a_tile + j * (a_atoms * 1024), 1024, a_atoms * 1024)
-                                        : make_desc(a_tile + j * 32, 16, 1024);
-          const uint64_t db = is_mn(BK) ? make_desc(b_tile + j * (b_atoms * 1024), 1024, b_atoms * 1024)
-                                        : make_desc(b_tile + j * 32, 16, 1024);
+          uint64_t da, db;
+          if (!is_mn(AK)) da = make_desc(a_tile + j * 32, 16, 1024);
+          else da = make_desc(a_tile + 2 * j * (a_atoms * 512), 512, a_atoms * 512, 1);
+          if (!is_mn(BK)) db = make_desc(b_tile + j * 32, 16, 1024);
+          else db = make_desc(b_tile + 2 * j * (b_atoms * 512), 512, b_atoms * 512, 1);
           umma_tf32(tmem, da, db, idesc, (i | j) ? 1u : 0u);
         }
         umma_commit(empty0 + 8 * s);       // frees the smem stage when these MMAs retire

@@ -271,7 +271,8 @@ __global__ void roi_table_k(const float* __restrict__ rois, int32_t* __restrict_
 }
 
 // ------------------------------------------------------------------ softmax / layernorm (warp per row)
-__global__ void softmax_fwd_k(const float* __restrict__ x, float* __restrict__ p, int64_t rows, int cols, float scale) {
+__global__ void softmax_fwd_k(const float* __restrict__ x, float* __restrict__ p, int64_t rows, int cols, float scale,
+                              int tf32) {
   const int lane = threadIdx.x & 31;
   const int64_t wpb = blockDim.x >> 5;
   for (int64_t row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
@@ -284,7 +285,10 @@ __global__ void softmax_fwd_k(const float* __restrict__ x, float* __restrict__ p
     for (int c = lane; c < cols; c += 32) sum += __expf(xr[c] * scale - mx);
     sum = warp_sum(sum);
     const float inv = 1.f / sum;
-    for (int c = lane; c < cols; c += 32) pr[c] = __expf(xr[c] * scale - mx) * inv;
+    for (int c = lane; c < cols; c += 32) {
+      const float v = __expf(xr[c] * scale - mx) * inv;
+      pr[c] = tf32 ? round_tf32(v) : v;
+    }
   }
 }
 
@@ -336,7 +340,7 @@ __global__ void layernorm_bwd_k(const float* __restrict__ dy, const float* __res
 }
 
 // ------------------------------------------------------------------ elementwise
-enum { EW_RELU = 0, EW_RELU_BWD = 1, EW_AXPBY = 2, EW_FILL = 3, EW_SIGMOID = 4, EW_TF32 = 5 };
+enum { EW_RELU = 0, EW_RELU_BWD = 1, EW_AXPBY = 2, EW_FILL = 3, EW_SIGMOID = 4, EW_TF32 = 5, EW_ADD_TF32 = 6, EW_RELU_TF32 = 7 };
 
 template <int OP>
 __device__ __forceinline__ float ew_op(float a, float b, float s0, float s1) {
@@ -345,6 +349,8 @@ __device__ __forceinline__ float ew_op(float a, float b, float s0, float s1) {
   if (OP == EW_AXPBY) return s0 * a + s1 * b;
   if (OP == EW_FILL) return s0;
   if (OP == EW_TF32) return round_tf32(a);
+  if (OP == EW_ADD_TF32) return round_tf32(a + b);
+  if (OP == EW_RELU_TF32) return round_tf32(fmaxf(a, 0.f));
   return 1.f / (1.f + __expf(-a));
 }
 
@@ -416,6 +422,24 @@ __global__ void copy2d_k(const float* __restrict__ src, int64_t lds, float* __re
     const int c = (int)(i - r * cols);
     const float v = src[r * lds + c];
     if (accumulate) dst[r * ldd + c] += v; else dst[r * ldd + c] = v;
+  }
+}
+
+// out[c] (+)= sum_r x[r*ld+c]: block = 32 columns x 8 row-lanes
+__global__ void colsum_k(const float* __restrict__ x, int64_t ld, float* __restrict__ out, int64_t rows, int cols,
+                         int accumulate) {
+  __shared__ float part[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (c < cols)
+    for (int64_t r = threadIdx.y; r < rows; r += 8) s += x[r * ld + c];
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += part[j][threadIdx.x];
+    out[c] = accumulate ? out[c] + t : t;
   }
 }
 
@@ -735,10 +759,10 @@ int vlfb_roi_align_table(const float* rois, int32_t* pos, float* w, int32_t* gri
   return VLFB_OK;
 }
 
-int vlfb_softmax_fwd(const float* x, float* p, int64_t rows, int cols, float scale, void* stream) {
+int vlfb_softmax_fwd(const float* x, float* p, int64_t rows, int cols, float scale, int tf32, void* stream) {
   VLFB_CHECK_ARG(x && p && rows >= 0 && cols > 0);
   if (rows == 0) return VLFB_OK;
-  softmax_fwd_k<<<stream_grid(rows, TPB / 32), TPB, 0, ST(stream)>>>(x, p, rows, cols, scale);
+  softmax_fwd_k<<<stream_grid(rows, TPB / 32), TPB, 0, ST(stream)>>>(x, p, rows, cols, scale, tf32);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -788,6 +812,20 @@ int vlfb_fill(float* x, float v, int64_t n, void* stream) {
 int vlfb_round_tf32(const float* x, float* y, int64_t n, void* stream) {
   VLFB_CHECK_ARG(x && y && n >= 0);
   return ew_launch<EW_TF32>(x, nullptr, y, n, 0.f, 0.f, ST(stream));
+}
+int vlfb_add_tf32(const float* x, const float* y, float* out, int64_t n, void* stream) {
+  VLFB_CHECK_ARG(x && y && out && n >= 0);
+  return ew_launch<EW_ADD_TF32>(x, y, out, n, 0.f, 0.f, ST(stream));
+}
+int vlfb_relu_tf32(const float* x, float* y, int64_t n, void* stream) {
+  VLFB_CHECK_ARG(x && y && n >= 0);
+  return ew_launch<EW_RELU_TF32>(x, nullptr, y, n, 0.f, 0.f, ST(stream));
+}
+int vlfb_colsum(const float* x, int64_t ld, float* out, int64_t rows, int cols, int accumulate, void* stream) {
+  VLFB_CHECK_ARG(x && out && rows >= 0 && cols > 0);
+  colsum_k<<<ceil_div(cols, 32), dim3(32, 8), 0, ST(stream)>>>(x, ld, out, rows, cols, accumulate);
+  VLFB_CHECK_LAUNCH();
+  return VLFB_OK;
 }
 int vlfb_sigmoid_fwd(const float* x, float* y, int64_t n, void* stream) {
   VLFB_CHECK_ARG(x && y && n >= 0);

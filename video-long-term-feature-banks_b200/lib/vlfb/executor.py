@@ -1,0 +1,869 @@
+"""Lowers a recorded net (vlfb.net.Net) onto the B200 kernels and runs forward / backward /
+optimizer.  Replaces the Caffe2 `dag` executor behind `workspace.RunNet`
+(reference tools/train_net.py:152) for the hot path.
+
+Representation
+  * a blob is a torch tensor used as a strided *logical* view (reference NCTHW shape) over
+    channels-last storage; Transpose/Reshape/Squeeze are metadata-only (so the reference's
+    grouped-NL transposes, nonlocal_helper.py:191-211, and NTC_to_NCT11, lfb_helper.py:43-53,
+    cost nothing), compute ops assert the layout their kernel needs;
+  * Conv -> AffineNd -> [Sum] -> [Relu] chains are fused into one tensor-core GEMM with an
+    epilogue (the reference runs 3-4 kernels, model_builder_video.py:211-219,
+    resnet_helper.py:112-117); Scale -> Softmax likewise;
+  * every tensor that feeds a tensor-core GEMM is rounded to TF32 (round-to-nearest) by its
+    producer, because kind::tf32 MMAs truncate fp32 operands.
+"""
+import math
+
+import torch
+
+from . import kernels as K_default
+
+K = K_default          # tests may swap in a torch-CPU kernel set (tests/fake_kernels.py)
+DEVICE = 'cuda'
+DTYPE = torch.float32      # the CUDA kernels are fp32-only; the CPU test stand-in may run the host logic in fp64
+
+
+def set_backend(kernels_module, device, dtype=torch.float32):
+    global K, DEVICE, DTYPE
+    K = kernels_module
+    DEVICE = device
+    DTYPE = dtype
+
+
+def empty(shape, dtype=None):
+    return torch.empty(tuple(int(s) for s in shape), dtype=dtype or DTYPE, device=DEVICE)
+
+
+def empty_like_strided(t):
+    return torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, device=t.device)
+
+
+def cl_alloc(logical_shape):
+    """Allocate channels-last storage for a logical (N, C, spatial...) shape; returns the logical view."""
+    n, c = logical_shape[0], logical_shape[1]
+    spatial = list(logical_shape[2:])
+    phys = empty([n] + spatial + [c])
+    return phys.permute([0, len(spatial) + 1] + list(range(1, len(spatial) + 1)))
+
+
+def phys(t):
+    """Physical channels-last view [N, spatial..., C] of a logical (N, C, spatial...) tensor."""
+    if t.dim() <= 2:
+        assert t.is_contiguous()
+        return t
+    p = t.permute([0] + list(range(2, t.dim())) + [1])
+    assert p.is_contiguous(), 'blob is not channels-last contiguous: shape %s strides %s' % (
+        tuple(t.shape), tuple(t.stride()))
+    return p
+
+
+def flat(t):
+    """1-D view of a dense tensor in storage order."""
+    order = sorted(range(t.dim()), key=lambda d: (-t.stride(d), d))
+    p = t.permute(order)
+    if not p.is_contiguous():
+        # size-1 dims can carry arbitrary strides; drop them
+        keep = [d for d in order if t.shape[d] != 1]
+        p = t.permute(keep + [d for d in order if t.shape[d] == 1])
+    assert p.is_contiguous(), 'tensor is not dense: shape %s strides %s' % (tuple(t.shape), tuple(t.stride()))
+    return p.reshape(-1)
+
+
+def as5d(p):
+    """[N, spatial..., C] physical tensor -> 5-D [N,T,H,W,C] (missing dims = 1)."""
+    while p.dim() < 5:
+        p = p.unsqueeze(1)
+    return p
+
+
+class Step(object):
+    """One lowered kernel group.  fwd(ctx) computes outputs; bwd(ctx) consumes output grads."""
+    params = ()
+
+    def __init__(self, op, in_keys, out_keys):
+        self.op = op
+        self.in_keys = in_keys
+        self.out_keys = out_keys
+
+    def fwd(self, ctx):
+        raise NotImplementedError(self.op.type)
+
+    def bwd(self, ctx):
+        raise NotImplementedError(self.op.type + ' backward')
+
+
+# ======================================================================================
+class Ctx(object):
+    """Per-run state: blob tensors by name, gradients by (name, version) key."""
+
+    def __init__(self, ws, net):
+        self.ws = ws
+        self.net = net
+        self.grads = {}
+        self.owned = {}
+        self.saved = {}
+
+    # ---- blobs
+    def get(self, name):
+        return self.ws.blobs[name]
+
+    def put(self, name, t, rounded=False):
+        self.ws.blobs[name] = t
+        if rounded:
+            self.ws.rounded.add(name)
+        else:
+            self.ws.rounded.discard(name)
+
+    def rounded(self, name):
+        """TF32-rounded version of blob `name` (GEMM operand)."""
+        t = self.ws.blobs[name]
+        if name in self.ws.rounded or self.ws.params.has(name):
+            return self.ws.params.tf32(name) if self.ws.params.has(name) else t
+        r = empty_like_strided(t)
+        K.round_tf32(flat(t), flat(r))
+        return r
+
+    # ---- grads
+    def add_grad(self, key, g, owned):
+        if not self.net.requires.get(key, False):
+            return
+        cur = self.grads.get(key)
+        if cur is None:
+            self.grads[key] = g
+            self.owned[key] = owned
+        else:
+            if self.owned[key]:
+                K.axpby(flat(cur), 1.0, flat(g), 1.0, flat(cur))
+            else:
+                s = empty_like_strided(cur)
+                K.axpby(flat(cur), 1.0, flat(g), 1.0, flat(s))
+                self.grads[key] = s
+                self.owned[key] = True
+
+    def pop_grad(self, key):
+        self.owned.pop(key, None)
+        return self.grads.pop(key, None)
+
+    def pop_grad_owned(self, key):
+        """Gradient that may be modified in place."""
+        own = self.owned.pop(key, False)
+        g = self.grads.pop(key, None)
+        if g is not None and not own:
+            c = empty_like_strided(g)
+            K.axpby(flat(g), 1.0, None, 0.0, flat(c))
+            g = c
+        return g
+
+
+# ====================================================================================== steps
+def _pads3(pads, n):
+    return list(pads[:n])
+
+
+class ConvStep(Step):
+    """Conv [+bias] [+AffineNd] [+Sum residual] [+Relu] as one gathered tensor-core GEMM."""
+
+    def __init__(self, op, in_keys, out_keys, affine=None, residual_key=None, relu=False, out_name=None):
+        Step.__init__(self, op, in_keys, out_keys)
+        self.x, self.w = op.inputs[0], op.inputs[1]
+        self.b = op.inputs[2] if len(op.inputs) > 2 else None
+        self.affine = affine              # (scale_name, bias_name) or None
+        self.res_key = residual_key
+        self.relu = relu
+        self.out = out_name or op.outputs[0]
+        self.params = [self.w] + ([self.b] if self.b else [])
+
+    def _geom(self, ctx, xp):
+        a = self.op.args
+        k = list(a['kernels'])
+        assert len(k) == 3
+        wshape = ctx.ws.params.logical_shape(self.w)
+        return K.conv_geom(xp.shape, wshape[0], k, a['strides'], _pads3(a['pads'], 3), a['dilations'])
+
+    def fwd(self, ctx):
+        x = ctx.rounded(self.x)
+        xp = as5d(phys(x))
+        g = self._geom(ctx, xp)
+        w = ctx.ws.params.tf32(self.w)
+        y = cl_alloc((g.N, g.Co, g.To, g.Ho, g.Wo))
+        scale = bias = None
+        if self.affine:
+            scale = ctx.ws.params.phys(self.affine[0])
+            bias = ctx.ws.params.phys(self.affine[1])
+            if self.b:                      # (conv + b) * s + bb  ==  conv * s + (b * s + bb)
+                eb = empty((1, g.Co))
+                K.affine_fwd(ctx.ws.params.phys(self.b).view(1, -1), scale, bias, eb)
+                bias = eb.view(-1)
+        elif self.b:
+            bias = ctx.ws.params.phys(self.b)
+        res = None
+        if self.res_key is not None:
+            res = phys(ctx.get(self.res_key[0]))
+        K.conv_fwd(xp, w, phys(y), g, scale=scale, bias=bias, residual=res, relu=self.relu, tf32_out=True)
+        ctx.saved[id(self)] = (xp, g)
+        ctx.put(self.out, y, rounded=True)
+
+    def bwd(self, ctx):
+        gy = ctx.pop_grad_owned(self.out_keys[0]) if self.relu else ctx.pop_grad(self.out_keys[0])
+        if gy is None:
+            return
+        xp, g = ctx.saved.pop(id(self))
+        gp = as5d(phys(gy))
+        if self.relu:
+            y = phys(ctx.get(self.out))
+            K.relu_bwd(flat(gp), flat(y), flat(gp))
+        if self.res_key is not None:
+            ctx.add_grad(self.res_key, gy, owned=False)
+        scale = ctx.ws.params.phys(self.affine[0]) if self.affine else None
+        store = ctx.ws.params
+        if store.trainable(self.w):
+            mask = store.stem_mask() if g.C == 4 else None
+            K.conv_wgrad(gp, xp, store.grad(self.w), g, row_scale=scale, col_mask=mask)
+        if self.b and store.trainable(self.b):
+            db = store.grad(self.b)
+            rows = gp.numel() // g.Co
+            if scale is None:
+                K.colsum(gp, g.Co, db, rows, g.Co, accumulate=True)
+            else:
+                t = empty((1, g.Co))
+                K.colsum(gp, g.Co, t, rows, g.Co, accumulate=False)
+                K.affine_bwd(t, scale, t)
+                K.axpby(db, 1.0, t.view(-1), 1.0, db)
+        xkey = self.in_keys[0]
+        if ctx.net.requires.get(xkey, False):
+            assert g.C != 4, 'the stem never propagates a gradient to the input clip'
+            taps = g.kT * g.kH * g.kW
+            wt = empty((g.C, taps, g.Co))
+            K.weight_transpose(store.tf32(self.w), wt, scale)
+            cur = ctx.grads.get(xkey)
+            if cur is not None and ctx.owned.get(xkey, False):
+                K.conv_dgrad(gp, wt, as5d(phys(cur)), g, accumulate=True)
+            else:
+                dx = cl_alloc((g.N, g.C, g.T, g.H, g.W))
+                K.conv_dgrad(gp, wt, phys(dx), g, accumulate=False)
+                ctx.add_grad(xkey, dx.view(ctx.get(self.x).shape) if dx.shape != ctx.get(self.x).shape else dx,
+                             owned=True)
+
+
+class AffineStep(Step):
+    """Stand-alone AffineNd (reference caffe2_customized_ops/video/affine_nd_op.cu:62-104)."""
+
+    def fwd(self, ctx):
+        x = ctx.get(self.op.inputs[0])
+        y = empty_like_strided(x)
+        s, b = ctx.ws.params.phys(self.op.inputs[1]), ctx.ws.params.phys(self.op.inputs[2])
+        K.affine_fwd(phys(x), s, b, phys(y))
+        ctx.put(self.op.outputs[0], y)
+
+    def bwd(self, ctx):
+        gy = ctx.pop_grad(self.out_keys[0])
+        if gy is None:
+            return
+        dx = empty_like_strided(gy)
+        K.affine_bwd(phys(gy), ctx.ws.params.phys(self.op.inputs[1]), phys(dx))
+        ctx.add_grad(self.in_keys[0], dx, owned=True)
+
+
+class ReluStep(Step):
+    def fwd(self, ctx):
+        x = ctx.get(self.op.inputs[0])
+        y = x if self.op.outputs[0] == self.op.inputs[0] else empty_like_strided(x)
+        K.relu_tf32(flat(x), flat(y))
+        ctx.put(self.op.outputs[0], y, rounded=True)
+
+    def bwd(self, ctx):
+        gy = ctx.pop_grad_owned(self.out_keys[0])
+        if gy is None:
+            return
+        K.relu_bwd(flat(gy), flat(ctx.get(self.op.outputs[0])), flat(gy))
+        ctx.add_grad(self.in_keys[0], gy, owned=True)
+
+
+class SumStep(Step):
+    def fwd(self, ctx):
+        ins = [ctx.get(n) for n in self.op.inputs]
+        assert len(ins) == 2 and ins[0].shape == ins[1].shape and ins[0].stride() == ins[1].stride()
+        y = ins[0] if self.op.outputs[0] == self.op.inputs[0] else empty_like_strided(ins[0])
+        K.add_tf32(flat(ins[0]), flat(ins[1]), flat(y))
+        ctx.put(self.op.outputs[0], y, rounded=True)
+
+    def bwd(self, ctx):
+        gy = ctx.pop_grad(self.out_keys[0])
+        if gy is None:
+            return
+        for k in self.in_keys:
+            ctx.add_grad(k, gy, owned=False)
+
+
+class ScaleStep(Step):
+    def fwd(self, ctx):
+        x = ctx.get(self.op.inputs[0])
+        y = x if self.op.outputs[0] == self.op.inputs[0] else empty_like_strided(x)
+        K.axpby(flat(x), self.op.args['scale'], None, 0.0, flat(y))
+        ctx.put(self.op.outputs[0], y)
+
+    def bwd(self, ctx):
+        gy = ctx.pop_grad(self.out_keys[0])
+        if gy is None:
+            return
+        dx = empty_like_strided(gy)
+        K.axpby(flat(gy), self.op.args['scale'], None, 0.0, flat(dx))
+        ctx.add_grad(self.in_keys[0], dx, owned=True)
+
+
+class SoftmaxStep(Step):
+    """Softmax over the last axis with an optional fused pre-scale (Scale -> Softmax chain)."""
+
+    def __init__(self, op, in_keys, out_keys, scale=1.0, src=None):
+        Step.__init__(self, op, in_keys, out_keys)
+        self.scale = scale
+        self.src = src or op.inputs[0]
+
+    def fwd(self, ctx):
+        x = ctx.get(self.src)
+        assert x.is_contiguous() and self.op.args.get('axis', 1) == x.dim() - 1
+        p = empty(x.shape)
+        K.softmax_fwd(x, p, self.scale, tf32_out=True)
+        ctx.put(self.op.outputs[0], p, rounded=True)
+
+    def bwd(self, ctx):
+        gp = ctx.pop_grad(self.out_keys[0])
+        if gp is None:
+            return
+        p = ctx.get(self.op.outputs[0])
+        if not gp.is_contiguous():
+            gp = gp.contiguous()
+        dx = empty(p.shape)
+        K.softmax_bwd(p, gp, dx, self.scale)
+        ctx.add_grad(self.in_keys[0], dx, owned=True)
+
+
+class PoolStep(Step):
+    """MaxPool / AveragePool on channels-last storage (3-D windows; 2-D windows on 4-D blobs)."""
+
+    def _geom(self, x):
+        a = self.op.args
+        k, s, p = list(a['kernels']), list(a['strides']), list(a['pads'])
+        nd = len(k)
+        p = p[:nd]
+        k = [1] * (3 - nd) + k
+        s = [1] * (3 - nd) + s
+        p = [0] * (3 - nd) + p
+        xp = as5d(phys(x))
+        return xp, K.conv_geom(xp.shape, xp.shape[-1], k, s, p)
+
+    def fwd(self, ctx):
+        xname = self.op.inputs[0]
+        x = ctx.get(xname)
+        xp, g = self._geom(x)
+        spatial = [g.To, g.Ho, g.Wo][5 - x.dim():]
+        y = cl_alloc([g.N, g.C] + spatial)
+        yp = as5d(phys(y))
+        if self.op.type == 'MaxPool':
+            arg = empty(yp.shape, torch.int32) if ctx.net.train else None
+            K.maxpool_fwd(xp, yp, arg, g)
+            ctx.saved[id(self)] = (g, arg, x.shape, x.stride())
+        else:
+            K.avgpool_fwd(xp, yp, g)
+            ctx.saved[id(self)] = (g, None, x.shape, x.stride())
+        ctx.put(self.op.outputs[0], y, rounded=(self.op.type == 'MaxPool' and xname in ctx.ws.rounded))
+
+    def bwd(self, ctx):
+        gy = ctx.pop_grad(self.out_keys[0])
+        if gy is None:
+            return
+        g, arg, xshape, xstride = ctx.saved.pop(id(self))
+        dx = torch.empty_strided(xshape, xstride, dtype=DTYPE, device=DEVICE)
+        gp = as5d(phys(gy))
+        if self.op.type == 'MaxPool':
+            K.fill(flat(dx), 0.0)
+            K.maxpool_bwd(gp, arg, as5d(phys(dx)), g)
+        else:
+            K.avgpool_bwd(gp, as5d(phys(dx)), g, accumulate=False)
+        ctx.add_grad(self.in_keys[0], dx, owned=True)
+
+
+class ReshapeStep(Step):
+    def fwd(self, ctx):
+        x = ctx.get(self.op.inputs[0])
+        if 'shape' in self.op.args:
+            shape = [int(v) for v in self.op.args['shape']]
+        else:
+            shape = list(ctx.get(self.op.inputs[1]))
+        y = x.view(shape)        # metadata only; raises if a copy would be needed
+        ctx.put(self.op.outputs[0], y, rounded=self.op.inputs[0] in ctx.ws.rounded)
+        if len(self.op.outputs) > 1:
+            ctx.ws.blobs[self.op.outputs[1]] = tuple(x.shape)
+        ctx.saved[id(self)] = tuple(x.shape)
+
+    def bwd(self, ctx):
+        gy = ctx.pop_grad(self.out_keys[0])
+        if gy is None:
+            return
+        ctx.add_grad(self.in_keys[0], gy.view(ctx.saved.pop(id(self))), owned=ctx.owned.get(self.out_keys[0], False))
+
+
+class TransposeStep(Step):
+    def fwd(self, ctx):
+        x = ctx.get(self.op.inputs[0])
+        ctx.put(self.op.outputs[0], x.permute(self.op.args['axes']), rounded=self.op.inputs[0] in ctx.ws.rounded)
+
+    def bwd(self, ctx):
+        gy = ctx.pop_grad(self.out_keys[0])
+        if gy is None:
+            return
+        axes = self.op.args['axes']
+        inv = [0] * len(axes)
+        for i, a in enumerate(axes):
+            inv[a] = i
+        ctx.add_grad(self.in_keys[0], gy.permute(inv), owned=False)
+
+
+class SqueezeStep(Step):
+    def fwd(self, ctx):
+        x = ctx.get(self.op.inputs[0])
+        y = x
+        for d in sorted(self.op.args['dims'], reverse=True):
+            y = y.squeeze(d)
+        ctx.put(self.op.outputs[0], y, rounded=self.op.inputs[0] in ctx.ws.rounded)
+        ctx.saved[id(self)] = tuple(x.shape)
+
+    def bwd(self, ctx):
+        gy = ctx.pop_grad(self.out_keys[0])
+        if gy is None:
+            return
+        ctx.add_grad(self.in_keys[0], gy.view(ctx.saved.pop(id(self))), owned=False)
+
+
+class StopGradientStep(Step):
+    def fwd(self, ctx):
+        if self.op.outputs[0] != self.op.inputs[0]:
+            ctx.put(self.op.outputs[0], ctx.get(self.op.inputs[0]), rounded=self.op.inputs[0] in ctx.ws.rounded)
+
+    def bwd(self, ctx):
+        ctx.pop_grad(self.out_keys[0])
+
+
+class NoopStep(Step):
+    def fwd(self, ctx):
+        pass
+
+    def bwd(self, ctx):
+        pass
+
+
+class BatchMatMulStep(Step):
+    """BatchMatMul([a, b], trans_a=, trans_b=) on strided views (nonlocal_helper.py:94-95,121)."""
+
+    def _views(self, a, b):
+        A = a.transpose(1, 2) if self.op.args.get('trans_a', 0) else a
+        B = b.transpose(1, 2) if self.op.args.get('trans_b', 0) else b
+        return A, B
+
+    def fwd(self, ctx):
+        a, b = ctx.rounded(self.op.inputs[0]), ctx.rounded(self.op.inputs[1])
+        A, B = self._views(a, b)
+        Bt, M, N = A.shape[0], A.shape[1], B.shape[2]
+        if A.stride(1) == 1 and M > 1:        # rows of the output are "channels": keep channels-last
+            d = empty((Bt, N, M)).transpose(1, 2)
+        else:
+            d = empty((Bt, M, N))
+        K.matmul(A, B, d, tf32_out=True)
+        ctx.saved[id(self)] = (a, b)
+        ctx.put(self.op.outputs[0], d, rounded=True)
+
+    def bwd(self, ctx):
+        g = ctx.pop_grad(self.out_keys[0])
+        if g is None:
+            return
+        a, b = ctx.saved.pop(id(self))
+        A, B = self._views(a, b)
+        ta, tb = self.op.args.get('trans_a', 0), self.op.args.get('trans_b', 0)
+        if ctx.net.requires.get(self.in_keys[0], False):
+            da = empty_like_strided(a)
+            dA = da.transpose(1, 2) if ta else da
+            K.matmul(g, B.transpose(1, 2), dA)
+            ctx.add_grad(self.in_keys[0], da, owned=True)
+        if ctx.net.requires.get(self.in_keys[1], False):
+            db = empty_like_strided(b)
+            dB = db.transpose(1, 2) if tb else db
+            K.matmul(A.transpose(1, 2), g, dB)
+            ctx.add_grad(self.in_keys[1], db, owned=True)
+
+
+class LayerNormStep(Step):
+    def fwd(self, ctx):
+        x = ctx.get(self.op.inputs[0])
+        assert self.op.args.get('axis', 1) == 1
+        rows = x.shape[0]
+        cols = x.numel() // rows
+        xf = flat(x)
+        y = empty_like_strided(x)
+        mean, std = empty((rows,)), empty((rows,))
+        K.layernorm_fwd(xf, flat(y), mean, std, cols, self.op.args.get('epsilon', 1e-5))
+        outs = self.op.outputs
+        ctx.put(outs[0], y)
+        if len(outs) > 1:
+            ctx.put(outs[1], mean.view(rows, 1))
+        if len(outs) > 2:
+            ctx.put(outs[2], std.view(rows, 1))
+        ctx.saved[id(self)] = (std, cols)
+
+    def bwd(self, ctx):
+        gy = ctx.pop_grad(self.out_keys[0])
+        if gy is None:
+            return
+        std, cols = ctx.saved.pop(id(self))
+        y = ctx.get(self.op.outputs[0])
+        dx = empty_like_strided(y)
+        K.layernorm_bwd(flat(gy), flat(y), std, flat(dx), cols)
+        ctx.add_grad(self.in_keys[0], dx, owned=True)
+
+
+class DropoutStep(Step):
+    def fwd(self, ctx):
+        x = ctx.get(self.op.inputs[0])
+        ratio = self.op.args.get('ratio', 0.5)
+        if self.op.args.get('is_test', False) or ratio <= 0.0 or not ctx.ws.dropout_enabled:
+            ctx.put(self.op.outputs[0], x, rounded=self.op.inputs[0] in ctx.ws.rounded)
+            ctx.saved[id(self)] = None
+            return
+        y = empty_like_strided(x)
+        seed, offset = ctx.ws.next_rng(x.numel())
+        K.dropout(flat(x), flat(y), ratio, seed, offset)
+        ctx.saved[id(self)] = (ratio, seed, offset)
+        ctx.put(self.op.outputs[0], y)
+
+    def bwd(self, ctx):
+        gy = ctx.pop_grad(self.out_keys[0])
+        if gy is None:
+            return
+        st = ctx.saved.pop(id(self))
+        if st is None:
+            ctx.add_grad(self.in_keys[0], gy, owned=False)
+            return
+        dx = empty_like_strided(gy)
+        K.dropout(flat(gy), flat(dx), st[0], st[1], st[2])
+        ctx.add_grad(self.in_keys[0], dx, owned=True)
+
+
+class FCStep(Step):
+    def __init__(self, op, in_keys, out_keys):
+        Step.__init__(self, op, in_keys, out_keys)
+        self.params = [op.inputs[1], op.inputs[2]]
+
+    def fwd(self, ctx):
+        x = ctx.rounded(self.op.inputs[0])
+        x2 = flat(x).view(x.shape[0], -1)
+        w = ctx.ws.params.tf32(self.op.inputs[1])
+        b = ctx.ws.params.phys(self.op.inputs[2])
+        y = empty((x2.shape[0], w.shape[0]))
+        K.matmul(x2.unsqueeze(0), w.t().unsqueeze(0), y.unsqueeze(0), bias=b)
+        ctx.saved[id(self)] = (x2, x.shape, x.stride())
+        ctx.put(self.op.outputs[0], y)
+
+    def bwd(self, ctx):
+        gy = ctx.pop_grad(self.out_keys[0])
+        if gy is None:
+            return
+        x2, xshape, xstride = ctx.saved.pop(id(self))
+        store = ctx.ws.params
+        wname, bname = self.op.inputs[1], self.op.inputs[2]
+        if store.trainable(wname):
+            K.matmul(gy.t().unsqueeze(0), x2.unsqueeze(0), store.grad(wname).unsqueeze(0), accumulate=True)
+        if store.trainable(bname):
+            K.colsum(gy, gy.shape[1], store.grad(bname), gy.shape[0], gy.shape[1], accumulate=True)
+        if ctx.net.requires.get(self.in_keys[0], False):
+            dx = torch.empty_strided(xshape, xstride, dtype=DTYPE, device=DEVICE)
+            K.matmul(gy.unsqueeze(0), store.tf32(wname).unsqueeze(0), flat(dx).view(1, x2.shape[0], -1))
+            ctx.add_grad(self.in_keys[0], dx, owned=True)
+
+
+class ConcatStep(Step):
+    def fwd(self, ctx):
+        ins = [ctx.get(n) for n in self.op.inputs]
+        assert self.op.args.get('axis', 1) == 1
+        rows = ins[0].shape[0]
+        cols = [t.numel() // rows for t in ins]
+        for t, c in zip(ins, cols):
+            assert t.shape[1] == c, 'Concat expects (R, C, 1, 1, 1) heads'
+        total = sum(cols)
+        y = cl_alloc([rows, total] + list(ins[0].shape[2:]))
+        yp = flat(y)
+        off = 0
+        for t, c in zip(ins, cols):
+            K.copy2d(flat(t), c, yp, total, rows, c, dst_off=off)
+            off += c
+        ctx.put(self.op.outputs[0], y)
+        ctx.saved[id(self)] = (cols, [(t.shape, t.stride()) for t in ins])
+
+    def bwd(self, ctx):
+        gy = ctx.pop_grad(self.out_keys[0])
+        if gy is None:
+            return
+        cols, metas = ctx.saved.pop(id(self))
+        total = sum(cols)
+        rows = gy.shape[0]
+        gp = flat(gy)
+        off = 0
+        for key, c, (shape, stride) in zip(self.in_keys, cols, metas):
+            d = torch.empty_strided(shape, stride, dtype=DTYPE, device=DEVICE)
+            K.copy2d(gp, total, flat(d), c, rows, c, src_off=off)
+            ctx.add_grad(key, d, owned=True)
+            off += c
+
+
+class RoIAlignStep(Step):
+    def fwd(self, ctx):
+        feat = ctx.get(self.op.inputs[0])
+        rois = ctx.get(self.op.inputs[1])
+        a = self.op.args
+        fp = phys(feat)                               # [N,H,W,C]
+        r = rois.shape[0]
+        y = cl_alloc((r, feat.shape[1], a['pooled_h'], a['pooled_w']))
+        K.roi_align_fwd(fp, rois, phys(y), a['spatial_scale'], a['sampling_ratio'])
+        ctx.put(self.op.outputs[0], y)
+        ctx.saved[id(self)] = (rois, feat.shape, feat.stride())
+
+    def bwd(self, ctx):
+        gy = ctx.pop_grad(self.out_keys[0])
+        if gy is None:
+            return
+        rois, shape, stride = ctx.saved.pop(id(self))
+        a = self.op.args
+        d = torch.empty_strided(shape, stride, dtype=DTYPE, device=DEVICE)
+        K.fill(flat(d), 0.0)
+        K.roi_align_bwd(phys(gy), rois, phys(d), a['spatial_scale'], a['sampling_ratio'])
+        ctx.add_grad(self.in_keys[0], d, owned=True)
+
+
+class SigmoidStep(Step):
+    def fwd(self, ctx):
+        x = ctx.get(self.op.inputs[0])
+        y = empty_like_strided(x)
+        K.sigmoid_fwd(flat(x), flat(y))
+        ctx.put(self.op.outputs[0], y)
+
+    def bwd(self, ctx):
+        assert ctx.pop_grad(self.out_keys[0]) is None, 'Sigmoid(prob) is an output head without gradient'
+
+
+class SigmoidCELossStep(Step):
+    def fwd(self, ctx):
+        x, t = ctx.get(self.op.inputs[0]), ctx.get(self.op.inputs[1])
+        loss = empty((1,))
+        K.sigmoid_ce_fwd(x, t, loss, self.op.args['scale'])
+        ctx.put(self.op.outputs[0], loss)
+
+    def bwd(self, ctx):
+        gl = ctx.pop_grad(self.out_keys[0])
+        x, t = ctx.get(self.op.inputs[0]), ctx.get(self.op.inputs[1])
+        dx = empty(x.shape)
+        K.sigmoid_ce_bwd(x, t, gl, dx, self.op.args['scale'])
+        ctx.add_grad(self.in_keys[0], dx, owned=True)
+
+
+class SoftmaxCELossStep(Step):
+    def fwd(self, ctx):
+        x, t = ctx.get(self.op.inputs[0]), ctx.get(self.op.inputs[1])
+        prob, loss = empty(x.shape), empty((1,))
+        K.softmax_ce_fwd(x, t.view(-1), prob, loss, self.op.args['scale'])
+        ctx.put(self.op.outputs[0], prob)
+        ctx.put(self.op.outputs[1], loss)
+
+    def bwd(self, ctx):
+        ctx.pop_grad(self.out_keys[0])
+        ctx.pop_grad(self.out_keys[1])
+        prob, t = ctx.get(self.op.outputs[0]), ctx.get(self.op.inputs[1])
+        dx = empty(prob.shape)
+        K.softmax_ce_bwd(prob, t.view(-1), dx, self.op.args['scale'])
+        ctx.add_grad(self.in_keys[0], dx, owned=True)
+
+
+STEP_TYPES = {
+    'AffineNd': AffineStep, 'Relu': ReluStep, 'Sum': SumStep, 'Scale': ScaleStep, 'Softmax': SoftmaxStep,
+    'MaxPool': PoolStep, 'AveragePool': PoolStep, 'Reshape': ReshapeStep, 'Transpose': TransposeStep,
+    'Squeeze': SqueezeStep, 'StopGradient': StopGradientStep, 'BatchMatMul': BatchMatMulStep,
+    'LayerNorm': LayerNormStep, 'Dropout': DropoutStep, 'FC': FCStep, 'Concat': ConcatStep,
+    'RoIAlign': RoIAlignStep, 'Sigmoid': SigmoidStep, 'SigmoidCrossEntropyLoss': SigmoidCELossStep,
+    'SoftmaxWithLoss': SoftmaxCELossStep, 'DequeueBlobs': NoopStep,
+}
+OPTIMIZER_OPS = ('WeightedSum', 'MomentumSGDUpdate')
+
+
+# ====================================================================================== lowering
+class CompiledNet(object):
+    def __init__(self, model, ws):
+        self.model = model
+        self.ws = ws
+        self.name = model.net.Proto().name
+        ops = [op for op in model.net.ops if op.type not in OPTIMIZER_OPS]
+        self.update_ops = [op for op in model.net.ops if op.type in OPTIMIZER_OPS]
+        self.losses = list(getattr(model, '_losses', []) or [])
+        self.train = bool(self.losses) and bool(self.update_ops or getattr(model, '_want_grads', False))
+        self._version(ops)
+        self.steps = self._lower(ops)
+        self.requires = {}
+        self.trainable = []
+        if self.losses:
+            self._analyse()
+        self.num_launch_groups = len(self.steps)
+
+    # ---- SSA-style versioning of in-place blobs
+    def _version(self, ops):
+        ver = {}
+        self.in_keys, self.out_keys = [], []
+        self.consumers = {}
+        for i, op in enumerate(ops):
+            ik = [(n, ver.get(n, 0)) for n in op.inputs]
+            for k in ik:
+                self.consumers.setdefault(k, []).append(i)
+            ok = []
+            for n in op.outputs:
+                ver[n] = ver.get(n, 0) + 1
+                ok.append((n, ver[n]))
+            self.in_keys.append(ik)
+            self.out_keys.append(ok)
+        self.final_ver = ver
+
+    def _sole_consumer(self, key, ops, type_, taken=()):
+        c = self.consumers.get(key, [])
+        if len(c) == 1 and ops[c[0]].type == type_ and c[0] not in taken:
+            return c[0]
+        return None
+
+    def _lower(self, ops):
+        consumed = set()
+        placed = {}                     # op index where a fused step is emitted -> step
+        for i, op in enumerate(ops):
+            if i in consumed:
+                continue
+            if op.type == 'Conv':
+                chain = [i]
+                key = self.out_keys[i][0]
+                affine = None
+                j = self._sole_consumer(key, ops, 'AffineNd', consumed)
+                if j is not None and ops[j].inputs[0] == key[0]:
+                    affine = (ops[j].inputs[1], ops[j].inputs[2])
+                    chain.append(j)
+                    key = self.out_keys[j][0]
+                res_key = None
+                j = self._sole_consumer(key, ops, 'Sum', consumed)
+                if j is not None and len(ops[j].inputs) == 2 and self._safe_to_move(ops, i, j, op.inputs[0]):
+                    other = [k for k in self.in_keys[j] if k != key]
+                    if len(other) == 1:
+                        res_key = other[0]
+                        chain.append(j)
+                        key = self.out_keys[j][0]
+                relu = False
+                j = self._sole_consumer(key, ops, 'Relu', consumed)
+                if j is not None and self._safe_to_move(ops, i, j, op.inputs[0]):
+                    relu = True
+                    chain.append(j)
+                    key = self.out_keys[j][0]
+                consumed.update(chain)
+                placed[chain[-1]] = ConvStep(op, self.in_keys[i], [key], affine, res_key, relu, key[0])
+            elif op.type == 'Scale':
+                key = self.out_keys[i][0]
+                j = self._sole_consumer(key, ops, 'Softmax', consumed)
+                if j is not None:
+                    consumed.update([i, j])
+                    placed[j] = SoftmaxStep(ops[j], self.in_keys[i], self.out_keys[j], op.args['scale'],
+                                            src=op.inputs[0])
+        steps = []
+        for i, op in enumerate(ops):
+            if i in placed:
+                steps.append(placed[i])
+            elif i in consumed:
+                continue
+            elif op.type == 'Conv':
+                steps.append(ConvStep(op, self.in_keys[i], self.out_keys[i]))
+            else:
+                cls = STEP_TYPES.get(op.type)
+                if cls is None:
+                    raise NotImplementedError('op type %s has no B200 lowering' % op.type)
+                steps.append(cls(op, self.in_keys[i], self.out_keys[i]))
+        return steps
+
+    def _safe_to_move(self, ops, i, j, xname):
+        """The conv at position i is executed at position j: its input must not be overwritten in between."""
+        for k in range(i + 1, j + 1):
+            if xname in ops[k].outputs:
+                return False
+        return True
+
+    # ---- which keys need gradients / which params are trainable
+    def _analyse(self):
+        store_frozen = self.model.frozen_params
+        loss_keys = set((n, self.final_ver.get(n, 1)) for n in self.losses)
+        # backward reachability from the losses
+        reach = set(loss_keys)
+        for st in reversed(self.steps):
+            if isinstance(st, StopGradientStep):
+                continue
+            if any(k in reach for k in st.out_keys):
+                for k in st.in_keys:
+                    reach.add(k)
+                if isinstance(st, ConvStep) and st.res_key is not None:
+                    reach.add(st.res_key)
+        trainable = []
+        for st in self.steps:
+            if st.params and any(k in reach for k in st.out_keys):
+                for p in st.params:
+                    if p not in store_frozen and p not in trainable:
+                        trainable.append(p)
+        self.trainable = trainable
+        # forward propagation of "requires grad"
+        req = {}
+        pset = set(trainable)
+        for st in self.steps:
+            if isinstance(st, StopGradientStep):
+                for k in st.out_keys:
+                    req[k] = False
+                continue
+            ins = list(st.in_keys) + ([st.res_key] if isinstance(st, ConvStep) and st.res_key else [])
+            r = any(req.get(k, False) for k in ins) or any(p in pset for p in st.params)
+            for k in st.out_keys:
+                req[k] = r and (k in reach)
+        self.requires = req
+        self.model.param_to_grad = dict((p, p + '_grad') for p in trainable)
+
+    # ---- execution
+    def run(self):
+        ws = self.ws
+        ctx = Ctx(ws, self)
+        for st in self.steps:
+            st.fwd(ctx)
+        if not self.train:
+            return
+        store = ws.params
+        store.begin_step(self.trainable)
+        for n in self.losses:
+            ctx.grads[(n, self.final_ver.get(n, 1))] = None
+            ctx.requires_loss = True
+        for st in reversed(self.steps):
+            if isinstance(st, (SigmoidCELossStep, SoftmaxCELossStep)):
+                st.bwd(ctx)
+            elif any(k in ctx.grads for k in st.out_keys):
+                st.bwd(ctx)
+        ws.last_grads = ctx.grads
+        if ws.allreduce is not None:
+            ws.allreduce(store)
+        if self.update_ops:
+            self._update(store)
+
+    def _update(self, store):
+        from core.config import config as cfg
+        lr = self.ws.blobs['lr']
+        wd_map = {}
+        for op in self.update_ops:
+            if op.type == 'WeightedSum':
+                wd_map[op.inputs[2]] = op.inputs[3]
+        mom = nesterov = None
+        for op in self.update_ops:
+            if op.type == 'MomentumSGDUpdate':
+                mom, nesterov = op.args.get('momentum', 0.9), op.args.get('nesterov', 1)
+        wd_val = {'weight_decay': cfg.SOLVER.WEIGHT_DECAY, 'weight_decay_bn': cfg.SOLVER.WEIGHT_DECAY_BN}
+        store.sgd(self.trainable, lr, mom, bool(nesterov),
+                  dict((p, wd_val.get(wd_map.get(p, 'weight_decay'), 0.0)) for p in self.trainable))

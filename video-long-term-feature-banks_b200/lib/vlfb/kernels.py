@@ -231,7 +231,7 @@ def matmul(a, b, d, alpha=1.0, accumulate=False, bias=None, tf32_out=False):
         return matmul(b.transpose(1, 2), a.transpose(1, 2), d.transpose(1, 2), alpha, accumulate, None, tf32_out)
     ka, lda, sba = _mat_operand(a, 1, 2)
     kb, ldb, sbb = _mat_operand(b, 2, 1)
-    p = _base_params(M, N, K, d, d.stride(1) if M > 1 else N)
+    p = _base_params(M, N, K, d, d.stride(1) if M > 1 else N, alpha)
     p.a = _operand(a, ka, lda, sba)
     p.b = _operand(b, kb, ldb, sbb)
     p.batch = Bt
@@ -298,10 +298,10 @@ def roi_align_table(rois, h, w, ph, pw, max_grid, spatial_scale, sampling_ratio=
     return pos, wts, grid
 
 
-def softmax_fwd(x, p, scale=1.0):
+def softmax_fwd(x, p, scale=1.0, tf32_out=False):
     cols = x.shape[-1]
     L.check(L.load().vlfb_softmax_fwd(_ptr(_f32c(x)), _ptr(_f32c(p)), x.numel() // cols, cols, float(scale),
-                                      _stream()), 'softmax_fwd')
+                                      int(tf32_out), _stream()), 'softmax_fwd')
 
 
 def softmax_bwd(p, dp, dx, scale=1.0):
@@ -341,6 +341,19 @@ def fill(x, v):
 
 def round_tf32(x, y):
     L.check(L.load().vlfb_round_tf32(_ptr(_f32c(x)), _ptr(_f32c(y)), x.numel(), _stream()), 'round_tf32')
+
+
+def add_tf32(x, y, out):
+    L.check(L.load().vlfb_add_tf32(_ptr(_f32c(x)), _ptr(_f32c(y)), _ptr(_f32c(out)), x.numel(), _stream()), 'add_tf32')
+
+
+def relu_tf32(x, y):
+    L.check(L.load().vlfb_relu_tf32(_ptr(_f32c(x)), _ptr(_f32c(y)), x.numel(), _stream()), 'relu_tf32')
+
+
+def colsum(x, ld, out, rows, cols, accumulate=False):
+    L.check(L.load().vlfb_colsum(_ptr(x), int(ld), _ptr(out), int(rows), int(cols), int(accumulate), _stream()),
+            'colsum')
 
 
 def sigmoid_fwd(x, y):

@@ -52,7 +52,7 @@ SIGNATURES = {
     'vlfb_roi_align_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     'vlfb_roi_align_bwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     'vlfb_roi_align_table': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P],
-    'vlfb_softmax_fwd': [_P, _P, _L, _I, _F, _P],
+    'vlfb_softmax_fwd': [_P, _P, _L, _I, _F, _I, _P],
     'vlfb_softmax_bwd': [_P, _P, _P, _L, _I, _F, _P],
     'vlfb_layernorm_fwd': [_P, _P, _P, _P, _L, _I, _F, _P],
     'vlfb_layernorm_bwd': [_P, _P, _P, _P, _L, _I, _P],
@@ -61,6 +61,9 @@ SIGNATURES = {
     'vlfb_axpby': [_P, _F, _P, _F, _P, _L, _P],
     'vlfb_fill': [_P, _F, _L, _P],
     'vlfb_round_tf32': [_P, _P, _L, _P],
+    'vlfb_add_tf32': [_P, _P, _P, _L, _P],
+    'vlfb_relu_tf32': [_P, _P, _L, _P],
+    'vlfb_colsum': [_P, _L, _P, _L, _I, _I, _P],
     'vlfb_sigmoid_fwd': [_P, _P, _L, _P],
     'vlfb_dropout_fwd': [_P, _P, _L, _F, _U, _U, _P],
     'vlfb_copy2d': [_P, _L, _P, _L, _L, _I, _I, _P],
