@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- clips/sec of the LFB hot path (BASELINE.json config 2: R50-I3D-NL + FBO-NL-2L,
+forward + backward + SGD, 2 synthetic 32x224x224 clips / 4 RoIs / 300-row bank per GPU).
+
+  python bench.py --gpus N --steps K --warmup W            # this implementation (tcgen05 path)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle restatement)
+
+One JSON line on stdout (rank 0).  `value` = device-resident throughput (inputs already in
+HBM), `e2e` = through FeedBlob/RunNet/FetchBlob with pinned host buffers (H2D + D2H inside the
+timed region), `roofline` = the tcgen05 gathered-GEMM kernel (all launches of one step) against the
+measured tensor peak, `cpu_baseline` = the oracle timed on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, 'video-long-term-feature-banks_b200', 'lib'), ROOT, os.path.join(ROOT, 'tests')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+YAML = 'ava_r50_lfb_nl.yaml'
+CLIPS_PER_GPU = 2
+ROIS_PER_CLIP = 2
+BANK_ROWS = 300
+# algorithmic FLOPs per 32x224x224 clip, R50-I3D-NL, fwd+bwd (3x fwd - conv1 dgrad)
+GFLOP_PER_CLIP_FWD_BWD = 1106.0
+
+
+def fbo_gflop(rois, bank_rows, layers):
+    fwd = 2.0 * rois * (2048 * 512 + bank_rows * 2048 * 512 +
+                        layers * (2 * 512 ** 2 + 2 * bank_rows * 512 ** 2 + 2 * bank_rows * 512))
+    return 3.0 * fwd / 1e9
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.check_output(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                               '--format=csv,noheader,nounits'], timeout=5).decode().strip()
+                self.samples.append([v.strip() for v in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i] == 'Active' for s in self.samples)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': int(self.samples[0][1]),
+                'reasons': reasons, 'samples': len(self.samples)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return json.load(f), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+# ------------------------------------------------------------------------------------ CPU reference arm
+def oracle_setup(n_clips, num_gpus):
+    import harness as H
+    from oracle import model as OM
+    ov = ['NUM_GPUS', num_gpus, 'TRAIN.BATCH_SIZE', n_clips * num_gpus, 'TRAIN.DROPOUT_RATE', 0.0]
+    ocfg = H.oracle_cfg(YAML, ov)
+    params = OM.make_params(ocfg, seed=2)
+    for v in params.values():
+        v.requires_grad_(True)
+    inputs = OM.make_inputs(ocfg, n_clips=n_clips, rois_per_clip=ROIS_PER_CLIP)
+    return OM, ocfg, params, inputs
+
+
+def oracle_step(OM, ocfg, params, inputs, lr=0.01):
+    import torch
+    blobs, prob, loss = OM.forward(ocfg, params, inputs, 'train')
+    loss.backward()
+    with torch.no_grad():
+        for name, p in params.items():
+            if p.grad is not None and not (name.endswith('_bn_s') or name.endswith('_bn_b')):
+                p.add_(p.grad, alpha=-lr)
+            p.grad = None
+    return float(loss)
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    OM, ocfg, params, inputs = oracle_setup(1, 1)
+    for _ in range(args.warmup):
+        oracle_step(OM, ocfg, params, inputs)
+    t0 = time.time()
+    for _ in range(args.steps):
+        oracle_step(OM, ocfg, params, inputs)
+    dt = (time.time() - t0) / max(args.steps, 1)
+    value = 1.0 / dt
+    sample = '1 clip (32x224x224, 2 RoIs, 300-row bank) fwd+bwd+SGD per step, oracle restatement on PyTorch-CPU fp32'
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'clips/sec (32x224^2) R50-I3D-NL+FBO-NL-2L fwd+bwd', 'value': value,
+        'unit': 'clips/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'BASELINE.json configs[1]: R50-I3D-NL + FBO-NL-2L fwd+bwd, 32x224x224 clips, '
+                               'R=2 RoIs/clip, L=300 bank rows', 'clips_per_step': 1},
+        'cpu_baseline': {'value': value, 'unit': 'clips/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'clips/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    import harness as H
+    from core.config import config as cfg
+    from oracle import model as OM   # synthetic-input generator only; never on the timed path
+    from vlfb import dist as vdist
+    from vlfb import kernels as K
+    from vlfb import workspace
+
+    rank, world = vdist.init_from_env()
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    assert world == args.gpus or world == 1, 'launch with torchrun --nproc-per-node %d' % args.gpus
+    n_gpus = world
+
+    ov = ['NUM_GPUS', n_gpus, 'TRAIN.BATCH_SIZE', CLIPS_PER_GPU * n_gpus]
+    H.setup_cfg(YAML, ov)
+    cfg.RNG_SEED = 2                       # identical initial weights on every rank
+    workspace.ResetWorkspace()
+    model, sfx = H.build('train', True)
+    ocfg = H.oracle_cfg(YAML, ov)
+    if rank == 0:      # synthetic weights of bounded dynamic range (SURVEY section 8d generator), then broadcast
+        H.feed_params(OM.make_params(ocfg, seed=2))
+    vdist.install(workspace.current())
+    vdist.broadcast_params(workspace.current().params)
+    workspace.FeedBlob('gpu_0/lr', np.array(1e-4, dtype=np.float32))    # keeps random-weight training finite
+
+    inputs = OM.make_inputs(ocfg, n_clips=CLIPS_PER_GPU, rois_per_clip=ROIS_PER_CLIP, seed=100 + rank)
+    host = dict((k, v.contiguous().pin_memory()) for k, v in inputs.items())
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    name = model.net.Proto().name
+
+    def feed():
+        for k, v in host.items():
+            workspace.FeedBlob('gpu_0/%s%s' % (k, sfx), v)
+
+    def barrier():
+        if n_gpus > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if n_gpus == 1:
+            return ms
+        t = torch.tensor([ms], device='cuda')
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput: inputs already in HBM
+    feed()
+    for _ in range(args.warmup):
+        workspace.RunNet(name)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    K.LAUNCHES = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        workspace.RunNet(name)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    launches = K.LAUNCHES // max(args.steps, 1)
+
+    # ---- end to end: H2D of every input from pinned memory + D2H of the loss, every step
+    for _ in range(2):
+        feed()
+        workspace.RunNet(name)
+        loss = float(workspace.FetchBlob('gpu_0/loss'))
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        feed()
+        workspace.RunNet(name)
+        loss = float(workspace.FetchBlob('gpu_0/loss'))
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)) / args.steps
+    sampler.stop_flag = True
+
+    # ---- roofline of the dominant kernel: every tcgen05 GEMM launch of one more step, CUDA events
+    K.start_profile()
+    workspace.RunNet(name)
+    recs = K.stop_profile()
+    gemm_ms = sum(r[1] for r in recs)
+    by_kind = {}
+    for kind, t, f in recs:
+        a = by_kind.setdefault(kind, [0.0, 0.0, 0])
+        a[0] += t
+        a[1] += f
+        a[2] += 1
+    if rank != 0:
+        return
+    assert np.isfinite(loss), 'loss is not finite'
+    peaks, peak_src = measured_peaks()
+    layers = cfg.FBO_NL.NUM_LAYERS
+    rois = CLIPS_PER_GPU * ROIS_PER_CLIP
+    gflop_step = CLIPS_PER_GPU * GFLOP_PER_CLIP_FWD_BWD + fbo_gflop(rois, BANK_ROWS, layers)
+    achieved = gflop_step / gemm_ms if gemm_ms > 0 else 0.0          # GFLOP/ms == TFLOP/s
+    peak_tf32 = peaks['bf16_tflops_sustained'] / 2.0                  # kind::tf32 issues at half the bf16 rate
+    clips = CLIPS_PER_GPU * n_gpus
+
+    # ---- CPU baseline: the oracle on this box's host cores, bounded sample (N=1 only)
+    cpu = None
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        OMo, oc, op, oi = oracle_setup(1, 1)
+        oracle_step(OMo, oc, op, oi)
+        t0 = time.time()
+        nrep = 2
+        for _ in range(nrep):
+            oracle_step(OMo, oc, op, oi)
+        cpu = {'value': nrep / (time.time() - t0), 'unit': 'clips/s', 'cores': cores, 'kind': 'port',
+               'sample': '%d timed steps of 1 clip (32x224x224, 2 RoIs, L=300) fwd+bwd+SGD, PyTorch-CPU fp32 '
+                         'oracle restatement (the Caffe2 reference cannot run here)' % nrep}
+
+    print(json.dumps({
+        'metric': 'clips/sec (32x224^2) R50-I3D-NL+FBO-NL-2L fwd+bwd', 'value': clips / (ms / 1e3),
+        'unit': 'clips/s', 'n_gpus': n_gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32', 'data': 'synthetic',
+        'config': {'workload': 'BASELINE.json configs[1]: R50-I3D-NL + FBO-NL-2L fwd+bwd+SGD, %d clips/GPU of '
+                               '32x224x224, R=%d RoIs, L=%d bank rows x 2048; random-init weights' % (
+                                   CLIPS_PER_GPU, rois, BANK_ROWS),
+                   'clips_per_gpu': CLIPS_PER_GPU, 'parallelism': 'dp%d' % n_gpus,
+                   'l2': 'activations (>1 GB/step) exceed the 126 MB L2 between launches; no explicit flush',
+                   'dropout': 'Philox, enabled'},
+        'e2e': {'value': clips / (e2e_ms / 1e3), 'unit': 'clips/s', 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms},
+        'gpu_launches': launches,
+        'clocks': sampler.summary(),
+        'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf32, 'unit': 'TFLOP/s',
+                     'frac': achieved / peak_tf32 if peak_tf32 else None, 'traffic': None,
+                     'kernel': 'vlfb::tc::gemm_tc_kernel (all %d launches of one step, %.2f ms of %.2f ms)' % (
+                         len(recs), gemm_ms, ms),
+                     'peak_source': '%s bf16_tflops_sustained / 2 (kind::tf32)' % peak_src,
+                     'by_kind': dict((k, {'ms': v[0], 'tflops': v[1] / 1e9 / v[0] if v[0] else 0, 'launches': v[2]})
+                                     for k, v in by_kind.items())},
+        'cpu_baseline': cpu,
+        'loss': loss,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

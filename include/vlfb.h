@@ -149,6 +149,7 @@ int vlfb_fill(float* x, float v, int64_t n, void* stream);
 /* TF32-rounding variants used where the result feeds a tensor-core GEMM */
 int vlfb_add_tf32(const float* x, const float* y, float* out, int64_t n, void* stream);   /* round(x+y) */
 int vlfb_relu_tf32(const float* x, float* y, int64_t n, void* stream);                    /* round(max(x,0)) */
+int vlfb_relu_bwd_tf32(const float* dy, const float* y, float* dx, int64_t n, void* stream); /* round(dy*(y>0)) */
 /* out[c] (+)= sum_r x[r*ld + c]  (bias gradients of Conv/FC) */
 int vlfb_colsum(const float* x, int64_t ld, float* out, int64_t rows, int cols, int accumulate, void* stream);
 /* y = round-to-nearest TF32 of x (operand preparation for kind::tf32 MMAs; y may alias x) */
@@ -163,7 +164,7 @@ int vlfb_copy2d(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t 
 /* layout: NCTHW (reference blob layout) <-> NDHWC; inner = T*H*W */
 int vlfb_nc_to_cl(const float* src, float* dst, int N, int C, int64_t inner, int Cpad, void* stream);
 int vlfb_cl_to_nc(const float* src, float* dst, int N, int C, int64_t inner, int Cpad, void* stream);
-/* weights: wt[ci][tap][co] = w[co][tap][ci] * (scale ? scale[co] : 1) */
+/* weights: wt[ci][tap][co] = round_tf32( w[co][tap][ci] * (scale ? scale[co] : 1) )  (dgrad B operand) */
 int vlfb_weight_transpose(const float* w, float* wt, const float* scale, int Co, int taps, int Ci,
                           void* stream);
 

@@ -40,7 +40,13 @@ class Graph(object):
     """Walks the reference graph; in 'spec' mode it only records parameter shapes,
     in 'run' mode it evaluates with torch ops."""
 
-    def __init__(self, cfg, params=None, dropout_masks=None):
+    def __init__(self, cfg, params=None, dropout_masks=None, emulate_tf32=False):
+        """emulate_tf32: round (to nearest, straight-through gradient) every tensor that the B200 path
+        stores as a TF32 tensor-core operand, at the same points of the graph.  The
+        resulting forward agrees with the GPU to fp32-accumulation error, so ReLU / max-pool decisions
+        coincide and gradients can be compared tightly.  The default (False) is the plain fp32/fp64
+        restatement of the reference."""
+        self.emulate_tf32 = emulate_tf32
         self.cfg = cfg
         self.params = params
         self.spec = OrderedDict()       # name -> (shape, kind)
@@ -49,18 +55,27 @@ class Graph(object):
         self.dilations = 1
         self.dropout_masks = dropout_masks or {}
 
+    def q(self, x):
+        if not self.emulate_tf32 or x is None:
+            return x
+        i = x.detach().to(torch.float32).contiguous().view(torch.int32)
+        r = ((i + 0x1000) & ~0x1FFF).view(torch.float32).to(x.dtype)      # cvt.rna.tf32.f32
+        return x + (r - x).detach()
+
     # ---- parameter helpers -------------------------------------------------
     def _p(self, name, shape, kind):
         self.spec[name] = (tuple(shape), kind)
         return self.params[name] if self.run else None
 
     def conv(self, x, name, cin, cout, kernels, strides=(1, 1, 1), pads=(0, 0, 0),
-             dilations=(1, 1, 1), no_bias=1, kind='msra'):
+             dilations=(1, 1, 1), no_bias=1, kind='msra', round_out=True):
         w = self._p(name + '_w', (cout, cin) + tuple(kernels), kind)
         b = None if no_bias else self._p(name + '_b', (cout,), 'zero')
         if not self.run:
             return None
-        y = ops.conv_nd(x, w, b, strides, pads, dilations)
+        y = ops.conv_nd(self.q(x), self.q(w), b, strides, pads, dilations)
+        if round_out:
+            y = self.q(y)
         self.blobs[name] = y
         return y
 
@@ -75,11 +90,11 @@ class Graph(object):
 
     def conv_affine(self, x, prefix, cin, cout, kernels, strides, pads, dilations=(1, 1, 1)):
         """ModelBuilder.Conv3dAffine (model_builder_video.py:200-221)."""
-        y = self.conv(x, prefix, cin, cout, kernels, strides, pads, dilations, no_bias=1)
+        y = self.conv(x, prefix, cin, cout, kernels, strides, pads, dilations, no_bias=1, round_out=False)
         return self.affine(y, prefix + '_bn', cout)
 
     def relu(self, x):
-        return torch.relu(x) if self.run else None
+        return self.q(torch.relu(x)) if self.run else None
 
     def dropout(self, x, name, ratio):
         """Caffe2 Dropout train mode: mask*x/(1-ratio).  Masks are injected (the
@@ -112,11 +127,11 @@ class Graph(object):
         if dim_in == dim_out and ts == 1 and stride == 1:
             sc = x
         else:
-            sc = self.conv_affine(x, prefix + '_branch1', dim_in, dim_out, (1, 1, 1),
-                                  (ts, stride, stride), (0, 0, 0))
+            sc = self.q(self.conv_affine(x, prefix + '_branch1', dim_in, dim_out, (1, 1, 1),
+                                         (ts, stride, stride), (0, 0, 0)))
         if not self.run:
             return None
-        y = torch.relu(tr + sc)
+        y = self.q(torch.relu(tr + sc))
         self.blobs[prefix + '_branch2c_bn'] = y   # in-place Sum + Relu (resnet_helper.py:112-117)
         return y
 
@@ -158,18 +173,19 @@ class Graph(object):
             th = theta.reshape(batch_size, dim_inner, -1)
             ph = phi.reshape(batch_size, dim_inner, -1)
             gg = g.reshape(batch_size, dim_inner, -1)
-            aff = ops.batch_matmul(th, ph, trans_a=1)                 # (B, M, K)
+            aff = self.q(ops.batch_matmul(th, ph, trans_a=1))         # (B, M, K)
             assert nl.USE_SOFTMAX, 'oracle covers the softmax variant used by every shipped config'
             if nl.USE_SCALE:
                 aff = aff * (dim_inner ** -.5)
             self.blobs[prefix + '_affinity'] = aff
-            p = ops.softmax_axis2(aff)
+            p = self.q(ops.softmax_axis2(aff))
             self.blobs[prefix + '_affinity_prob'] = p
-            t = ops.batch_matmul(gg, p, trans_b=1)                    # (B, C/2, M)
+            t = self.q(ops.batch_matmul(gg, p, trans_b=1))            # (B, C/2, M)
             y = t.reshape(shape5d)
             self.blobs[prefix + '_y'] = y
         kind = 'zero_w' if nl.USE_ZERO_INIT_CONV else 'nl'
-        out = self.conv(y, prefix + '_out', dim_inner, dim_out, (1, 1, 1), no_bias=nb, kind=kind)
+        out = self.conv(y, prefix + '_out', dim_inner, dim_out, (1, 1, 1), no_bias=nb, kind=kind,
+                        round_out=not nl.USE_AFFINE)
         assert not nl.USE_BN, 'oracle covers NONLOCAL.USE_BN False (all shipped configs)'
         if nl.USE_AFFINE:
             out = self.affine(out, prefix + '_bn', dim_out)
@@ -180,7 +196,7 @@ class Graph(object):
         out = self.spacetime_nonlocal(x, dim_in, dim_out, batch_size, prefix, dim_inner)
         if not self.run:
             return None
-        y = x + out
+        y = self.q(x + out)
         self.blobs[prefix + '_sum'] = y
         return y
 
@@ -197,7 +213,7 @@ class Graph(object):
         out = self.spacetime_nonlocal(x, dim_in, dim_out, batch_size * group_num, prefix, dim_inner)
         if not self.run:
             return None
-        y = x + out
+        y = self.q(x + out)
         self.blobs[prefix + '_sum_grouped'] = y
         if group_num > 1:
             y = y.permute(0, 2, 1, 3, 4).reshape(shape5d).permute(0, 2, 1, 3, 4)
@@ -237,20 +253,21 @@ class Graph(object):
                 th = theta.reshape(-1, d, 1)
                 ph = phi.reshape(-1, d, num_lfb_feat)
                 gg = g.reshape(-1, d, num_lfb_feat)
-                aff = ops.batch_matmul(th, ph, trans_a=1)             # (R,1,L)
+                aff = self.q(ops.batch_matmul(th, ph, trans_a=1))     # (R,1,L)
                 if fb.SCALE:
                     aff = aff * (d ** -.5)
                 self.blobs[pre + '_affinity'] = aff
-                p = ops.softmax_axis2(aff)
+                p = self.q(ops.softmax_axis2(aff))
                 self.blobs[pre + '_affinity_prob'] = p
-                t = ops.batch_matmul(gg, p, trans_b=1).reshape(theta.shape)
+                t = self.q(ops.batch_matmul(gg, p, trans_b=1)).reshape(theta.shape)
                 self.blobs[pre + '_y'] = t
                 if fb.PRE_ACT:
                     if fb.PRE_ACT_LN:
                         t = ops.layer_norm_axis1(t)[0]
                         self.blobs[pre + '_y_ln'] = t
-                    t = torch.relu(t)
-            o = self.conv(t, pre + '_out', d, dim_a, (1, 1, 1), no_bias=nb, kind='zero_w')
+                    t = self.q(torch.relu(t))
+            fused_sum = fb.PRE_ACT and not (fb.LFB_DROPOUT_ON and not test_mode)   # Conv -> Sum fused on the GPU
+            o = self.conv(t, pre + '_out', d, dim_a, (1, 1, 1), no_bias=nb, kind='zero_w', round_out=not fused_sum)
             if not fb.PRE_ACT and self.run:
                 o = ops.layer_norm_axis1(o)[0]
                 self.blobs[pre + '_ln'] = o
@@ -258,10 +275,10 @@ class Graph(object):
                 o = self.dropout(o, (pre + '_out_drop') if fb.PRE_ACT else (pre + '_ln_drop'),
                                  fb.DROPOUT_RATE)
             if self.run:
-                out = o + a
+                out = self.q(o + a)
                 self.blobs[pre + '_sum'] = out
                 if not fb.PRE_ACT:
-                    out = torch.relu(out)
+                    out = self.q(torch.relu(out))
                 a = out
         return out, dim_a
 
@@ -353,7 +370,7 @@ class Graph(object):
         x = self.conv(data, 'conv1', 3, 64, (1 + tc[0][0] * 2, 7, 7), (ts[0][0], 2, 2), (tc[0][0], 3, 3))
         x = self.affine(x, 'res_conv1_bn', 64)
         if self.run:
-            x = torch.relu(x)
+            x = self.q(torch.relu(x))
             self.blobs['res_conv1_bn'] = x
             x = ops.max_pool_nd(x, (1, 3, 3), (1, 2, 2), (0, 1, 1))
             self.blobs['pool1'] = x
@@ -383,7 +400,7 @@ class Graph(object):
         if self.run and cfg.MODEL.FREEZE_BACKBONE:
             x = x.detach()
 
-        lfb = inputs.get('lfb') if self.run else None
+        lfb = self.q(inputs.get('lfb')) if self.run else None     # the bank is fed TF32-rounded
         if cfg.DATASET == 'ava':
             out, dim = self.roi_head(x, dim, inputs.get('proposals') if self.run else None, lfb,
                                      lfb_infer_only, test_mode)
@@ -397,7 +414,7 @@ class Graph(object):
         b = self._p('pred_b', (cfg.MODEL.NUM_CLASSES,), 'zero')
         if not self.run:
             return None, None
-        pred = ops.fc(out, w, b)
+        pred = ops.fc(self.q(out), self.q(w), b)
         self.blobs['pred'] = pred
         scale = 1.0 / cfg.NUM_GPUS
         labels = inputs.get('labels')
@@ -493,8 +510,8 @@ def make_inputs(cfg, n_clips=2, rois_per_clip=2, crop=None, frames=None, seed=0,
     return inputs
 
 
-def forward(cfg, params, inputs, split='train', lfb_infer_only=False, dropout_masks=None):
+def forward(cfg, params, inputs, split='train', lfb_infer_only=False, dropout_masks=None, emulate_tf32=False):
     """Run the graph; returns (blobs OrderedDict, prob, loss)."""
-    g = Graph(cfg, params, dropout_masks)
+    g = Graph(cfg, params, dropout_masks, emulate_tf32)
     prob, loss = g.create_model(inputs, split, lfb_infer_only)
     return g.blobs, prob, loss

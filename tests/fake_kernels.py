@@ -88,7 +88,18 @@ def weight_transpose(w, wt, scale=None):
     wt.copy_(s.permute(2, 1, 0).reshape(wt.shape))
 
 
+def _check_addressable(a, b, d):
+    """Run the real wrapper's operand analysis so layout problems surface in the CPU tests."""
+    from vlfb import kernels as RK
+    if not RK._dim_ok(d.stride(2), d.shape[2]):
+        assert RK._dim_ok(d.stride(1), d.shape[1])
+        return _check_addressable(b.transpose(1, 2), a.transpose(1, 2), d.transpose(1, 2))
+    RK._mat_operand(a, 1, 2)
+    RK._mat_operand(b, 2, 1)
+
+
 def matmul(a, b, d, alpha=1.0, accumulate=False, bias=None, tf32_out=False):
+    _check_addressable(a, b, d)
     r = torch.bmm(a, b) * alpha
     if bias is not None:
         r = r + bias
@@ -194,6 +205,9 @@ relu_tf32 = relu_fwd
 
 def relu_bwd(dy, y, dx):
     dx.copy_(dy * (y > 0))
+
+
+relu_bwd_tf32 = relu_bwd
 
 
 def axpby(x, a, y, b, out):

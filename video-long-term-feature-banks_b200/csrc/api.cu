@@ -18,24 +18,27 @@ void set_error(const char* fmt, ...) {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-static int validate_gemm(const vlfb_gemm_params_t& p) {
+// tc_ok = false: a dense operand is not 16-byte addressable for the tensor-core loaders (odd row
+// strides / extents such as a 157-class FC); such (tiny) problems run on the SIMT engine.
+static int validate_gemm(const vlfb_gemm_params_t& p, bool& tc_ok) {
+  tc_ok = true;
   VLFB_CHECK_ARG(p.a.ptr && p.b.ptr && p.d);
   VLFB_CHECK_ARG(p.M > 0 && p.N > 0 && p.K >= 0);
   VLFB_CHECK_ARG(p.batch >= 1 && p.taps >= 1 && p.split_k >= 1);
   VLFB_CHECK_ARG(!(p.taps > 1 && p.batch > 1));
   VLFB_CHECK_ARG(p.split_k == 1 || (p.flags & VLFB_EPI_ATOMIC));
   VLFB_CHECK_ARG(!(p.split_k > 1 && (p.col_bias || p.residual || (p.flags & VLFB_EPI_RELU))));
-  VLFB_CHECK_ARG(aligned16(p.a.ptr) && aligned16(p.b.ptr));
+  if (!(aligned16(p.a.ptr) && aligned16(p.b.ptr))) tc_ok = false;
   const vlfb_operand_t* ops[2] = {&p.a, &p.b};
   for (int i = 0; i < 2; ++i) {
     const vlfb_operand_t& o = *ops[i];
     const int extent = (i == 0) ? p.M : p.N;
     switch (o.kind) {
       case VLFB_OP_DENSE_K:
-        VLFB_CHECK_ARG((o.ld & 3) == 0 && (o.batch_stride & 3) == 0 && (p.K & 3) == 0);
+        if (!((o.ld & 3) == 0 && (o.batch_stride & 3) == 0 && (p.K & 3) == 0)) tc_ok = false;
         break;
       case VLFB_OP_DENSE_MN:
-        VLFB_CHECK_ARG((o.ld & 3) == 0 && (o.batch_stride & 3) == 0 && (extent & 3) == 0);
+        if (!((o.ld & 3) == 0 && (o.batch_stride & 3) == 0 && (extent & 3) == 0)) tc_ok = false;
         break;
       case VLFB_OP_CONV_K:
         VLFB_CHECK_ARG(i == 0 && p.g.C % 32 == 0 && p.K == p.g.kT * p.g.kH * p.g.kW * p.g.C);
@@ -84,10 +87,11 @@ int vlfb_get_gemm_backend(void) { return g_backend; }
 
 int vlfb_gemm(const vlfb_gemm_params_t* p, void* stream) {
   VLFB_CHECK_ARG(p != nullptr);
-  int rc = validate_gemm(*p);
+  bool tc_ok = true;
+  int rc = validate_gemm(*p, tc_ok);
   if (rc != VLFB_OK) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return g_backend == 1 ? gemm_simt(*p, s) : gemm_tc(*p, s);
+  return (g_backend == 1 || !tc_ok) ? gemm_simt(*p, s) : gemm_tc(*p, s);
 }
 
 }  // extern "C"

@@ -340,7 +340,7 @@ __global__ void layernorm_bwd_k(const float* __restrict__ dy, const float* __res
 }
 
 // ------------------------------------------------------------------ elementwise
-enum { EW_RELU = 0, EW_RELU_BWD = 1, EW_AXPBY = 2, EW_FILL = 3, EW_SIGMOID = 4, EW_TF32 = 5, EW_ADD_TF32 = 6, EW_RELU_TF32 = 7 };
+enum { EW_RELU = 0, EW_RELU_BWD = 1, EW_AXPBY = 2, EW_FILL = 3, EW_SIGMOID = 4, EW_TF32 = 5, EW_ADD_TF32 = 6, EW_RELU_TF32 = 7, EW_RELU_BWD_TF32 = 8 };
 
 template <int OP>
 __device__ __forceinline__ float ew_op(float a, float b, float s0, float s1) {
@@ -351,6 +351,7 @@ __device__ __forceinline__ float ew_op(float a, float b, float s0, float s1) {
   if (OP == EW_TF32) return round_tf32(a);
   if (OP == EW_ADD_TF32) return round_tf32(a + b);
   if (OP == EW_RELU_TF32) return round_tf32(fmaxf(a, 0.f));
+  if (OP == EW_RELU_BWD_TF32) return b > 0.f ? round_tf32(a) : 0.f;
   return 1.f / (1.f + __expf(-a));
 }
 
@@ -499,7 +500,7 @@ __global__ void weight_transpose_k(const float* __restrict__ w, float* __restric
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int ci = ci0 + r, co = co0 + threadIdx.x;
-    if (ci < Ci && co < Co) wt[((int64_t)ci * taps + tap) * Co + co] = tile[threadIdx.x][r];
+    if (ci < Ci && co < Co) wt[((int64_t)ci * taps + tap) * Co + co] = round_tf32(tile[threadIdx.x][r]);
   }
 }
 
@@ -820,6 +821,10 @@ int vlfb_add_tf32(const float* x, const float* y, float* out, int64_t n, void* s
 int vlfb_relu_tf32(const float* x, float* y, int64_t n, void* stream) {
   VLFB_CHECK_ARG(x && y && n >= 0);
   return ew_launch<EW_RELU_TF32>(x, nullptr, y, n, 0.f, 0.f, ST(stream));
+}
+int vlfb_relu_bwd_tf32(const float* dy, const float* y, float* dx, int64_t n, void* stream) {
+  VLFB_CHECK_ARG(dy && y && dx && n >= 0);
+  return ew_launch<EW_RELU_BWD_TF32>(dy, y, dx, n, 0.f, 0.f, ST(stream));
 }
 int vlfb_colsum(const float* x, int64_t ld, float* out, int64_t rows, int cols, int accumulate, void* stream) {
   VLFB_CHECK_ARG(x && out && rows >= 0 && cols > 0);

@@ -205,14 +205,17 @@ class ConvStep(Step):
         ctx.put(self.out, y, rounded=True)
 
     def bwd(self, ctx):
-        gy = ctx.pop_grad_owned(self.out_keys[0]) if self.relu else ctx.pop_grad(self.out_keys[0])
+        # the gradient is a GEMM operand of dgrad/wgrad: mask (ReLU) and round it to TF32 in one pass
+        gy = ctx.pop_grad_owned(self.out_keys[0])
         if gy is None:
             return
         xp, g = ctx.saved.pop(id(self))
         gp = as5d(phys(gy))
         if self.relu:
             y = phys(ctx.get(self.out))
-            K.relu_bwd(flat(gp), flat(y), flat(gp))
+            K.relu_bwd_tf32(flat(gp), flat(y), flat(gp))
+        else:
+            K.round_tf32(flat(gp), flat(gp))
         if self.res_key is not None:
             ctx.add_grad(self.res_key, gy, owned=False)
         scale = ctx.ws.params.phys(self.affine[0]) if self.affine else None
@@ -235,7 +238,7 @@ class ConvStep(Step):
             assert g.C != 4, 'the stem never propagates a gradient to the input clip'
             taps = g.kT * g.kH * g.kW
             wt = empty((g.C, taps, g.Co))
-            K.weight_transpose(store.tf32(self.w), wt, scale)
+            K.weight_transpose(store.phys(self.w), wt, scale)     # wt = round_tf32(w * s)
             cur = ctx.grads.get(xkey)
             if cur is not None and ctx.owned.get(xkey, False):
                 K.conv_dgrad(gp, wt, as5d(phys(cur)), g, accumulate=True)
@@ -474,9 +477,10 @@ class BatchMatMulStep(Step):
         ctx.put(self.op.outputs[0], d, rounded=True)
 
     def bwd(self, ctx):
-        g = ctx.pop_grad(self.out_keys[0])
+        g = ctx.pop_grad_owned(self.out_keys[0])
         if g is None:
             return
+        K.round_tf32(flat(g), flat(g))
         a, b = ctx.saved.pop(id(self))
         A, B = self._views(a, b)
         ta, tb = self.op.args.get('trans_a', 0), self.op.args.get('trans_b', 0)
@@ -564,9 +568,10 @@ class FCStep(Step):
         ctx.put(self.op.outputs[0], y)
 
     def bwd(self, ctx):
-        gy = ctx.pop_grad(self.out_keys[0])
+        gy = ctx.pop_grad_owned(self.out_keys[0])
         if gy is None:
             return
+        K.round_tf32(flat(gy), flat(gy))
         x2, xshape, xstride = ctx.saved.pop(id(self))
         store = ctx.ws.params
         wname, bname = self.op.inputs[1], self.op.inputs[2]

@@ -13,6 +13,29 @@ from . import libvlfb as L
 NUM_SMS = 148
 
 
+LAUNCHES = 0            # kernels launched through this module (bench.py reports it as gpu_launches)
+_PROFILE = None         # when a list: (name, start_event, end_event, flops) per tensor-core GEMM launch
+
+
+def _check(rc, what):
+    global LAUNCHES
+    LAUNCHES += 1
+    L.check(rc, what)
+
+
+def start_profile():
+    global _PROFILE
+    _PROFILE = []
+
+
+def stop_profile():
+    """Returns [(kind, milliseconds, flops)] of the GEMM launches since start_profile()."""
+    global _PROFILE
+    recs, _PROFILE = _PROFILE, None
+    torch.cuda.synchronize()
+    return [(k, s.elapsed_time(e), f) for k, s, e, f in (recs or [])]
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -72,8 +95,17 @@ def _operand(ptr_t, kind, ld=0, batch_stride=0):
     return o
 
 
-def _run_gemm(p):
-    L.check(L.load().vlfb_gemm(C.byref(p), _stream()), 'vlfb_gemm')
+def _run_gemm(p, kind='gemm', flops=None):
+    if _PROFILE is not None:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        _check(L.load().vlfb_gemm(C.byref(p), _stream()), 'vlfb_gemm')
+        e.record()
+        if flops is None:
+            flops = 2.0 * p.M * p.N * p.K * max(p.batch, 1) * max(p.taps, 1)
+        _PROFILE.append((kind, s, e, flops))
+        return
+    _check(L.load().vlfb_gemm(C.byref(p), _stream()), 'vlfb_gemm')
 
 
 def _base_params(M, N, K, d, ldd, alpha=1.0):
@@ -130,7 +162,7 @@ def conv_fwd(x, w, y, g, scale=None, bias=None, residual=None, relu=False, tf32_
     p.b = _operand(w, L.OP_DENSE_K, ld=K)
     p.g = g
     _set_epilogue(p, scale, bias, None, residual, relu, tf32_out)
-    _run_gemm(p)
+    _run_gemm(p, 'conv_fwd', 2.0 * M * g.Co * g.kT * g.kH * g.kW * (3 if g.C == 4 else g.C))
 
 
 def conv_dgrad(dy, wt, dx, g, accumulate=False):
@@ -150,7 +182,8 @@ def conv_dgrad(dy, wt, dx, g, accumulate=False):
     p.g = g
     if accumulate:
         p.flags |= L.EPI_ACCUM
-    _run_gemm(p)
+    # algorithmic dgrad work = forward MACs of the same layer
+    _run_gemm(p, 'conv_dgrad', 2.0 * g.N * g.To * g.Ho * g.Wo * g.Co * g.kT * g.kH * g.kW * g.C)
 
 
 def _split_k(tiles, kdim):
@@ -186,7 +219,7 @@ def conv_wgrad(dy, x, dw, g, row_scale=None, col_mask=None):
     p.split_k = _split_k(tiles, Kpos)
     p.flags |= L.EPI_ATOMIC
     _set_epilogue(p, col_mask, None, row_scale, None, False)
-    _run_gemm(p)
+    _run_gemm(p, 'conv_wgrad', 2.0 * Kpos * g.Co * g.kT * g.kH * g.kW * (3 if g.C == 4 else g.C))
 
 
 def weight_transpose(w, wt, scale=None):
@@ -194,7 +227,7 @@ def weight_transpose(w, wt, scale=None):
     _f32c(w), _f32c(wt)
     co, ci = w.shape[0], w.shape[-1]
     taps = w.numel() // (co * ci)
-    L.check(L.load().vlfb_weight_transpose(_ptr(w), _ptr(wt), _ptr(scale), co, taps, ci, _stream()),
+    _check(L.load().vlfb_weight_transpose(_ptr(w), _ptr(wt), _ptr(scale), co, taps, ci, _stream()),
             'weight_transpose')
 
 
@@ -209,10 +242,13 @@ def _mat_operand(t, rows_dim, k_dim):
     R, K = t.shape[rows_dim], t.shape[k_dim]
     if t.shape[0] == 1:
         sb = 0
-    if _dim_ok(sk, K) and (R == 1 or sr % 4 == 0) and K % 4 == 0 and sb % 4 == 0:
+    k_ok, mn_ok = _dim_ok(sk, K), _dim_ok(sr, R)
+    k_al = (R == 1 or sr % 4 == 0) and K % 4 == 0 and sb % 4 == 0       # 16-byte addressable for tcgen05
+    mn_al = (K == 1 or sk % 4 == 0) and R % 4 == 0 and sb % 4 == 0
+    if k_ok and (k_al or not (mn_ok and mn_al)):
         return L.OP_DENSE_K, (sr if R > 1 else K), sb
-    if _dim_ok(sr, R) and (K == 1 or sk % 4 == 0) and R % 4 == 0 and sb % 4 == 0:
-        return L.OP_DENSE_MN, (sk if K > 1 else R), sb
+    if mn_ok:
+        return L.OP_DENSE_MN, (sk if K > 1 else R), sb       # unaligned cases run on the SIMT engine (api.cu)
     raise ValueError('matmul operand with shape %s strides %s is not tensor-core addressable'
                      % (tuple(t.shape), tuple(t.stride())))
 
@@ -239,36 +275,36 @@ def matmul(a, b, d, alpha=1.0, accumulate=False, bias=None, tf32_out=False):
     if accumulate:
         p.flags |= L.EPI_ACCUM
     _set_epilogue(p, None, bias, None, None, False, tf32_out)
-    _run_gemm(p)
+    _run_gemm(p, 'matmul', 2.0 * Bt * M * N * K)
 
 
 # --------------------------------------------------------------------------- streaming ops
 def affine_fwd(x, s, b, y):
-    L.check(L.load().vlfb_affine_nd_fwd(_ptr(_f32c(x)), _ptr(s), _ptr(b), _ptr(_f32c(y)),
+    _check(L.load().vlfb_affine_nd_fwd(_ptr(_f32c(x)), _ptr(s), _ptr(b), _ptr(_f32c(y)),
                                         x.numel() // x.shape[-1], x.shape[-1], _stream()), 'affine_fwd')
 
 
 def affine_bwd(dy, s, dx):
-    L.check(L.load().vlfb_affine_nd_bwd(_ptr(_f32c(dy)), _ptr(s), _ptr(_f32c(dx)),
+    _check(L.load().vlfb_affine_nd_bwd(_ptr(_f32c(dy)), _ptr(s), _ptr(_f32c(dx)),
                                         dy.numel() // dy.shape[-1], dy.shape[-1], _stream()), 'affine_bwd')
 
 
 def maxpool_fwd(x, y, argmax, g):
-    L.check(L.load().vlfb_maxpool3d_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), _ptr(argmax), C.byref(g), _stream()),
+    _check(L.load().vlfb_maxpool3d_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), _ptr(argmax), C.byref(g), _stream()),
             'maxpool_fwd')
 
 
 def maxpool_bwd(dy, argmax, dx, g):
-    L.check(L.load().vlfb_maxpool3d_bwd(_ptr(_f32c(dy)), _ptr(argmax), _ptr(_f32c(dx)), C.byref(g), _stream()),
+    _check(L.load().vlfb_maxpool3d_bwd(_ptr(_f32c(dy)), _ptr(argmax), _ptr(_f32c(dx)), C.byref(g), _stream()),
             'maxpool_bwd')
 
 
 def avgpool_fwd(x, y, g):
-    L.check(L.load().vlfb_avgpool3d_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), C.byref(g), _stream()), 'avgpool_fwd')
+    _check(L.load().vlfb_avgpool3d_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), C.byref(g), _stream()), 'avgpool_fwd')
 
 
 def avgpool_bwd(dy, dx, g, accumulate=False):
-    L.check(L.load().vlfb_avgpool3d_bwd(_ptr(_f32c(dy)), _ptr(_f32c(dx)), C.byref(g), int(accumulate), _stream()),
+    _check(L.load().vlfb_avgpool3d_bwd(_ptr(_f32c(dy)), _ptr(_f32c(dx)), C.byref(g), int(accumulate), _stream()),
             'avgpool_bwd')
 
 
@@ -276,14 +312,14 @@ def roi_align_fwd(feat, rois, out, spatial_scale, sampling_ratio=0):
     """feat [N,H,W,C], rois [R,5], out [R,PH,PW,C]."""
     n, h, w, c = feat.shape
     r, ph, pw, _ = out.shape
-    L.check(L.load().vlfb_roi_align_fwd(_ptr(_f32c(feat)), _ptr(_f32c(rois)), _ptr(_f32c(out)), n, h, w, c, r, ph, pw,
+    _check(L.load().vlfb_roi_align_fwd(_ptr(_f32c(feat)), _ptr(_f32c(rois)), _ptr(_f32c(out)), n, h, w, c, r, ph, pw,
                                         float(spatial_scale), int(sampling_ratio), _stream()), 'roi_align_fwd')
 
 
 def roi_align_bwd(dout, rois, dfeat, spatial_scale, sampling_ratio=0):
     n, h, w, c = dfeat.shape
     r, ph, pw, _ = dout.shape
-    L.check(L.load().vlfb_roi_align_bwd(_ptr(_f32c(dout)), _ptr(_f32c(rois)), _ptr(_f32c(dfeat)), n, h, w, c, r, ph,
+    _check(L.load().vlfb_roi_align_bwd(_ptr(_f32c(dout)), _ptr(_f32c(rois)), _ptr(_f32c(dfeat)), n, h, w, c, r, ph,
                                         pw, float(spatial_scale), int(sampling_ratio), _stream()), 'roi_align_bwd')
 
 
@@ -292,7 +328,7 @@ def roi_align_table(rois, h, w, ph, pw, max_grid, spatial_scale, sampling_ratio=
     pos = torch.empty((r, ph, pw, max_grid, max_grid, 4), dtype=torch.int32, device=rois.device)
     wts = torch.empty((r, ph, pw, max_grid, max_grid, 4), dtype=torch.float32, device=rois.device)
     grid = torch.empty((r, 2), dtype=torch.int32, device=rois.device)
-    L.check(L.load().vlfb_roi_align_table(_ptr(_f32c(rois)), _ptr(pos), _ptr(wts), _ptr(grid), h, w, r, ph, pw,
+    _check(L.load().vlfb_roi_align_table(_ptr(_f32c(rois)), _ptr(pos), _ptr(wts), _ptr(grid), h, w, r, ph, pw,
                                           max_grid, float(spatial_scale), int(sampling_ratio), _stream()),
             'roi_align_table')
     return pos, wts, grid
@@ -300,124 +336,129 @@ def roi_align_table(rois, h, w, ph, pw, max_grid, spatial_scale, sampling_ratio=
 
 def softmax_fwd(x, p, scale=1.0, tf32_out=False):
     cols = x.shape[-1]
-    L.check(L.load().vlfb_softmax_fwd(_ptr(_f32c(x)), _ptr(_f32c(p)), x.numel() // cols, cols, float(scale),
+    _check(L.load().vlfb_softmax_fwd(_ptr(_f32c(x)), _ptr(_f32c(p)), x.numel() // cols, cols, float(scale),
                                       int(tf32_out), _stream()), 'softmax_fwd')
 
 
 def softmax_bwd(p, dp, dx, scale=1.0):
     cols = p.shape[-1]
-    L.check(L.load().vlfb_softmax_bwd(_ptr(_f32c(p)), _ptr(_f32c(dp)), _ptr(_f32c(dx)), p.numel() // cols, cols,
+    _check(L.load().vlfb_softmax_bwd(_ptr(_f32c(p)), _ptr(_f32c(dp)), _ptr(_f32c(dx)), p.numel() // cols, cols,
                                       float(scale), _stream()), 'softmax_bwd')
 
 
 def layernorm_fwd(x, y, mean, std, cols, eps=1e-5):
-    L.check(L.load().vlfb_layernorm_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), _ptr(mean), _ptr(std), x.numel() // cols,
+    _check(L.load().vlfb_layernorm_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), _ptr(mean), _ptr(std), x.numel() // cols,
                                         cols, float(eps), _stream()), 'layernorm_fwd')
 
 
 def layernorm_bwd(dy, y, std, dx, cols):
-    L.check(L.load().vlfb_layernorm_bwd(_ptr(_f32c(dy)), _ptr(_f32c(y)), _ptr(std), _ptr(_f32c(dx)),
+    _check(L.load().vlfb_layernorm_bwd(_ptr(_f32c(dy)), _ptr(_f32c(y)), _ptr(std), _ptr(_f32c(dx)),
                                         dy.numel() // cols, cols, _stream()), 'layernorm_bwd')
 
 
 def relu_fwd(x, y):
-    L.check(L.load().vlfb_relu_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), x.numel(), _stream()), 'relu_fwd')
+    _check(L.load().vlfb_relu_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), x.numel(), _stream()), 'relu_fwd')
 
 
 def relu_bwd(dy, y, dx):
-    L.check(L.load().vlfb_relu_bwd(_ptr(_f32c(dy)), _ptr(_f32c(y)), _ptr(_f32c(dx)), dy.numel(), _stream()),
+    _check(L.load().vlfb_relu_bwd(_ptr(_f32c(dy)), _ptr(_f32c(y)), _ptr(_f32c(dx)), dy.numel(), _stream()),
             'relu_bwd')
 
 
 def axpby(x, a, y, b, out):
     """out = a*x + b*y (y may be None when b == 0)."""
-    L.check(L.load().vlfb_axpby(_ptr(_f32c(x)), float(a), _ptr(y), float(b), _ptr(_f32c(out)), x.numel(),
+    _check(L.load().vlfb_axpby(_ptr(_f32c(x)), float(a), _ptr(y), float(b), _ptr(_f32c(out)), x.numel(),
                                 _stream()), 'axpby')
 
 
 def fill(x, v):
-    L.check(L.load().vlfb_fill(_ptr(_f32c(x)), float(v), x.numel(), _stream()), 'fill')
+    _check(L.load().vlfb_fill(_ptr(_f32c(x)), float(v), x.numel(), _stream()), 'fill')
 
 
 def round_tf32(x, y):
-    L.check(L.load().vlfb_round_tf32(_ptr(_f32c(x)), _ptr(_f32c(y)), x.numel(), _stream()), 'round_tf32')
+    _check(L.load().vlfb_round_tf32(_ptr(_f32c(x)), _ptr(_f32c(y)), x.numel(), _stream()), 'round_tf32')
 
 
 def add_tf32(x, y, out):
-    L.check(L.load().vlfb_add_tf32(_ptr(_f32c(x)), _ptr(_f32c(y)), _ptr(_f32c(out)), x.numel(), _stream()), 'add_tf32')
+    _check(L.load().vlfb_add_tf32(_ptr(_f32c(x)), _ptr(_f32c(y)), _ptr(_f32c(out)), x.numel(), _stream()), 'add_tf32')
 
 
 def relu_tf32(x, y):
-    L.check(L.load().vlfb_relu_tf32(_ptr(_f32c(x)), _ptr(_f32c(y)), x.numel(), _stream()), 'relu_tf32')
+    _check(L.load().vlfb_relu_tf32(_ptr(_f32c(x)), _ptr(_f32c(y)), x.numel(), _stream()), 'relu_tf32')
+
+
+def relu_bwd_tf32(dy, y, dx):
+    _check(L.load().vlfb_relu_bwd_tf32(_ptr(_f32c(dy)), _ptr(_f32c(y)), _ptr(_f32c(dx)), dy.numel(), _stream()),
+           'relu_bwd_tf32')
 
 
 def colsum(x, ld, out, rows, cols, accumulate=False):
-    L.check(L.load().vlfb_colsum(_ptr(x), int(ld), _ptr(out), int(rows), int(cols), int(accumulate), _stream()),
+    _check(L.load().vlfb_colsum(_ptr(x), int(ld), _ptr(out), int(rows), int(cols), int(accumulate), _stream()),
             'colsum')
 
 
 def sigmoid_fwd(x, y):
-    L.check(L.load().vlfb_sigmoid_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), x.numel(), _stream()), 'sigmoid_fwd')
+    _check(L.load().vlfb_sigmoid_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), x.numel(), _stream()), 'sigmoid_fwd')
 
 
 def dropout(x, y, ratio, seed, offset):
     """y = x * mask / (1-ratio); the mask is a pure function of (seed, offset, index), so the same
     call on dy is the backward."""
-    L.check(L.load().vlfb_dropout_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), x.numel(), float(ratio), int(seed),
+    _check(L.load().vlfb_dropout_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), x.numel(), float(ratio), int(seed),
                                       int(offset), _stream()), 'dropout')
 
 
 def copy2d(src, lds, dst, ldd, rows, cols, accumulate=False, src_off=0, dst_off=0):
     sp = C.c_void_p(src.data_ptr() + 4 * src_off)
     dp = C.c_void_p(dst.data_ptr() + 4 * dst_off)
-    L.check(L.load().vlfb_copy2d(sp, int(lds), dp, int(ldd), int(rows), int(cols), int(accumulate), _stream()),
+    _check(L.load().vlfb_copy2d(sp, int(lds), dp, int(ldd), int(rows), int(cols), int(accumulate), _stream()),
             'copy2d')
 
 
 def nc_to_cl(src, dst, n, c, inner, cpad=None):
-    L.check(L.load().vlfb_nc_to_cl(_ptr(_f32c(src)), _ptr(_f32c(dst)), n, c, inner, cpad or c, _stream()), 'nc_to_cl')
+    _check(L.load().vlfb_nc_to_cl(_ptr(_f32c(src)), _ptr(_f32c(dst)), n, c, inner, cpad or c, _stream()), 'nc_to_cl')
 
 
 def cl_to_nc(src, dst, n, c, inner, cpad=None):
-    L.check(L.load().vlfb_cl_to_nc(_ptr(_f32c(src)), _ptr(_f32c(dst)), n, c, inner, cpad or c, _stream()), 'cl_to_nc')
+    _check(L.load().vlfb_cl_to_nc(_ptr(_f32c(src)), _ptr(_f32c(dst)), n, c, inner, cpad or c, _stream()), 'cl_to_nc')
 
 
 def sigmoid_ce_fwd(logits, targets, loss, scale):
     assert targets.dtype == torch.int32
-    L.check(L.load().vlfb_sigmoid_ce_fwd(_ptr(_f32c(logits)), _ptr(targets), _ptr(loss), logits.numel(),
+    _check(L.load().vlfb_sigmoid_ce_fwd(_ptr(_f32c(logits)), _ptr(targets), _ptr(loss), logits.numel(),
                                          float(scale), _stream()), 'sigmoid_ce_fwd')
 
 
 def sigmoid_ce_bwd(logits, targets, dloss, dlogits, scale):
-    L.check(L.load().vlfb_sigmoid_ce_bwd(_ptr(_f32c(logits)), _ptr(targets), _ptr(dloss), _ptr(_f32c(dlogits)),
+    _check(L.load().vlfb_sigmoid_ce_bwd(_ptr(_f32c(logits)), _ptr(targets), _ptr(dloss), _ptr(_f32c(dlogits)),
                                          logits.numel(), float(scale), _stream()), 'sigmoid_ce_bwd')
 
 
 def softmax_ce_fwd(logits, labels, prob, loss, scale):
     assert labels.dtype == torch.int32
-    L.check(L.load().vlfb_softmax_ce_fwd(_ptr(_f32c(logits)), _ptr(labels), _ptr(_f32c(prob)), _ptr(loss),
+    _check(L.load().vlfb_softmax_ce_fwd(_ptr(_f32c(logits)), _ptr(labels), _ptr(_f32c(prob)), _ptr(loss),
                                          logits.shape[0], logits.shape[1], float(scale), _stream()), 'softmax_ce_fwd')
 
 
 def softmax_ce_bwd(prob, labels, dlogits, scale):
-    L.check(L.load().vlfb_softmax_ce_bwd(_ptr(_f32c(prob)), _ptr(labels), _ptr(_f32c(dlogits)), prob.shape[0],
+    _check(L.load().vlfb_softmax_ce_bwd(_ptr(_f32c(prob)), _ptr(labels), _ptr(_f32c(dlogits)), prob.shape[0],
                                          prob.shape[1], float(scale), _stream()), 'softmax_ce_bwd')
 
 
 def sgd_nesterov(p, g, m, lr, momentum, wd, nesterov=True, p_tf32=None):
     """In place: g += wd*p; m' = mu*m + lr*g; p -= (1+mu)*m' - mu*m  (lr is a 1-element device tensor)."""
-    L.check(L.load().vlfb_sgd_nesterov(_ptr(_f32c(p)), _ptr(_f32c(g)), _ptr(_f32c(m)), _ptr(p_tf32), p.numel(), _ptr(lr),
+    _check(L.load().vlfb_sgd_nesterov(_ptr(_f32c(p)), _ptr(_f32c(g)), _ptr(_f32c(m)), _ptr(p_tf32), p.numel(), _ptr(lr),
                                        float(momentum), float(wd), int(bool(nesterov)), _stream()), 'sgd_nesterov')
 
 
 def fbo_attend_fwd(theta, phi, g, prob, y, scale):
     r, l, d = phi.shape
-    L.check(L.load().vlfb_fbo_attend_fwd(_ptr(_f32c(theta)), _ptr(_f32c(phi)), _ptr(_f32c(g)), _ptr(_f32c(prob)),
+    _check(L.load().vlfb_fbo_attend_fwd(_ptr(_f32c(theta)), _ptr(_f32c(phi)), _ptr(_f32c(g)), _ptr(_f32c(prob)),
                                          _ptr(_f32c(y)), r, l, d, float(scale), _stream()), 'fbo_attend_fwd')
 
 
 def fbo_attend_bwd(theta, phi, g, prob, dy, dtheta, dphi, dg, scale):
     r, l, d = phi.shape
-    L.check(L.load().vlfb_fbo_attend_bwd(_ptr(_f32c(theta)), _ptr(_f32c(phi)), _ptr(_f32c(g)), _ptr(_f32c(prob)),
+    _check(L.load().vlfb_fbo_attend_bwd(_ptr(_f32c(theta)), _ptr(_f32c(phi)), _ptr(_f32c(g)), _ptr(_f32c(prob)),
                                          _ptr(_f32c(dy)), _ptr(_f32c(dtheta)), _ptr(_f32c(dphi)), _ptr(_f32c(dg)),
                                          r, l, d, float(scale), _stream()), 'fbo_attend_bwd')

@@ -309,6 +309,13 @@ def RunNet(name, num_iter=1):
 
 
 def _feed_activation(name, arr):
+    if isinstance(arr, torch.Tensor):
+        # already a tensor (e.g. a pinned host staging buffer): async H2D copy on the current stream
+        if arr.dtype in (torch.int32, torch.int64, torch.uint8, torch.bool):
+            _ws.blobs[name] = arr.to(torch.int32).to(X.DEVICE, non_blocking=True)
+            _ws.rounded.discard(name)
+            return
+        return _feed_float(name, arr.to(X.DTYPE).to(X.DEVICE, non_blocking=True))
     a = np.ascontiguousarray(arr)
     if a.dtype in (np.int32, np.int64, np.uint8, np.bool_):
         _ws.blobs[name] = torch.as_tensor(a.astype(np.int32)).to(X.DEVICE)
@@ -316,7 +323,11 @@ def _feed_activation(name, arr):
         return
     t = torch.as_tensor(a).to(X.DTYPE)
     if X.DEVICE != 'cpu':
-        t = t.pin_memory().to(X.DEVICE, non_blocking=True)
+        t = t.to(X.DEVICE)
+    _feed_float(name, t)
+
+
+def _feed_float(name, t):
     if t.dim() == 5:
         n, c = t.shape[0], t.shape[1]
         inner = t.shape[2] * t.shape[3] * t.shape[4]
