@@ -147,6 +147,7 @@ def run_b200(args):
     ov = ['NUM_GPUS', n_gpus, 'TRAIN.BATCH_SIZE', CLIPS_PER_GPU * n_gpus]
     H.setup_cfg(YAML, ov)
     cfg.RNG_SEED = 2                       # identical initial weights on every rank
+    cfg.B200.CUDA_GRAPH = not args.no_graph
     workspace.ResetWorkspace()
     model, sfx = H.build('train', True)
     ocfg = H.oracle_cfg(YAML, ov)
@@ -213,12 +214,19 @@ def run_b200(args):
     sampler.stop_flag = True
 
     # ---- roofline of the dominant kernel: every tcgen05 GEMM launch of one more step, CUDA events
+    workspace.current().force_eager = True       # per-launch CUDA events need the eager path
     K.start_profile()
     workspace.RunNet(name)
     recs = K.stop_profile()
+    workspace.current().force_eager = False
     gemm_ms = sum(r[1] for r in recs)
     by_kind = {}
+    if rank == 0 and args.dump_gemms:
+        with open(args.dump_gemms, 'w') as f:
+            for kind, t, fl in sorted(recs, key=lambda r: -r[1]):
+                f.write('%8.3f ms %8.1f TFLOP/s  %s\n' % (t, fl / 1e9 / t if t else 0, kind))
     for kind, t, f in recs:
+        kind = kind.split(' ')[0]
         a = by_kind.setdefault(kind, [0.0, 0.0, 0])
         a[0] += t
         a[1] += f
@@ -258,7 +266,7 @@ def run_b200(args):
                                    CLIPS_PER_GPU, rois, BANK_ROWS),
                    'clips_per_gpu': CLIPS_PER_GPU, 'parallelism': 'dp%d' % n_gpus,
                    'l2': 'activations (>1 GB/step) exceed the 126 MB L2 between launches; no explicit flush',
-                   'dropout': 'Philox, enabled'},
+                   'dropout': 'Philox, enabled', 'cuda_graph': bool(cfg.B200.CUDA_GRAPH)},
         'e2e': {'value': clips / (e2e_ms / 1e3), 'unit': 'clips/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms},
         'gpu_launches': launches,
@@ -282,6 +290,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--dump-gemms', default='', help='write the per-launch GEMM table of one step here')
+    ap.add_argument('--no-graph', action='store_true', help='eager launches (for ncu / debugging)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':

@@ -155,9 +155,11 @@ int vlfb_colsum(const float* x, int64_t ld, float* out, int64_t rows, int cols, 
 /* y = round-to-nearest TF32 of x (operand preparation for kind::tf32 MMAs; y may alias x) */
 int vlfb_round_tf32(const float* x, float* y, int64_t n, void* stream);
 int vlfb_sigmoid_fwd(const float* x, float* y, int64_t n, void* stream);
-/* Dropout (Caffe2 train mode: y = x*mask/(1-ratio)); mask = Philox(seed, offset+i) >= ratio */
+/* Dropout (Caffe2 train mode: y = x*mask/(1-ratio)); mask = Philox(seed, counter) >= ratio with
+ * counter = offset + i/4 + (step ? step[0] << 32 : 0).  `step` is an optional DEVICE scalar so that a
+ * captured CUDA graph draws a fresh mask at every replay.  The same call on dy is the backward. */
 int vlfb_dropout_fwd(const float* x, float* y, int64_t n, float ratio, uint64_t seed, uint64_t offset,
-                     void* stream);
+                     const int64_t* step, void* stream);
 /* 2-D strided copy: dst[r*ldd + c] = src[r*lds + c] (Concat / slicing; head_helper.py:82-85) */
 int vlfb_copy2d(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols,
                 int accumulate, void* stream);

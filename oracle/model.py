@@ -367,7 +367,8 @@ class Graph(object):
         tc, ts, pool_stride = obtain_arc(cfg.MODEL.VIDEO_ARC_CHOICE, cfg.TRAIN.VIDEO_LENGTH)
         assert cfg.MODEL.USE_AFFINE, 'oracle covers the Affine (frozen-BN) variant'
 
-        x = self.conv(data, 'conv1', 3, 64, (1 + tc[0][0] * 2, 7, 7), (ts[0][0], 2, 2), (tc[0][0], 3, 3))
+        x = self.conv(data, 'conv1', 3, 64, (1 + tc[0][0] * 2, 7, 7), (ts[0][0], 2, 2), (tc[0][0], 3, 3),
+                      round_out=False)
         x = self.affine(x, 'res_conv1_bn', 64)
         if self.run:
             x = self.q(torch.relu(x))

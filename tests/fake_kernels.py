@@ -12,6 +12,18 @@ from vlfb import libvlfb as L
 from vlfb.kernels import conv_geom, out_shape, _is_pointwise  # noqa: F401  (pure python helpers)
 
 
+EMULATE_TF32 = False     # True: perform the TF32 roundings of the CUDA path (in whatever dtype the tensors have)
+
+
+def _rt(t):
+    i = t.detach().to(torch.float32).contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32).to(t.dtype)
+
+
+def _q(t, on=True):
+    return _rt(t) if (EMULATE_TF32 and on) else t
+
+
 def set_gemm_backend(name):
     pass
 
@@ -46,7 +58,7 @@ def conv_fwd(x, w, y, g, scale=None, bias=None, residual=None, relu=False, tf32_
         o = o + residual
     if relu:
         o = torch.relu(o)
-    y.copy_(o)
+    y.copy_(_q(o, tf32_out))
 
 
 def conv_dgrad(dy, wt, dx, g, accumulate=False):
@@ -85,7 +97,7 @@ def weight_transpose(w, wt, scale=None):
     s = w.reshape(co, taps, ci)
     if scale is not None:
         s = s * scale.view(-1, 1, 1)
-    wt.copy_(s.permute(2, 1, 0).reshape(wt.shape))
+    wt.copy_(_q(s.permute(2, 1, 0).reshape(wt.shape)))
 
 
 def _check_addressable(a, b, d):
@@ -106,7 +118,7 @@ def matmul(a, b, d, alpha=1.0, accumulate=False, bias=None, tf32_out=False):
     if accumulate:
         d.add_(r)
     else:
-        d.copy_(r)
+        d.copy_(_q(r, tf32_out))
 
 
 def affine_fwd(x, s, b, y):
@@ -170,7 +182,7 @@ def roi_align_bwd(dout, rois, dfeat, spatial_scale, sampling_ratio=0):
 
 
 def softmax_fwd(x, p, scale=1.0, tf32_out=False):
-    p.copy_(torch.softmax(x * scale, dim=-1))
+    p.copy_(_q(torch.softmax(x * scale, dim=-1), tf32_out))
 
 
 def softmax_bwd(p, dp, dx, scale=1.0):
@@ -200,14 +212,16 @@ def relu_fwd(x, y):
     y.copy_(torch.relu(x))
 
 
-relu_tf32 = relu_fwd
+def relu_tf32(x, y):
+    y.copy_(_q(torch.relu(x)))
 
 
 def relu_bwd(dy, y, dx):
     dx.copy_(dy * (y > 0))
 
 
-relu_bwd_tf32 = relu_bwd
+def relu_bwd_tf32(dy, y, dx):
+    dx.copy_(_q(dy * (y > 0)))
 
 
 def axpby(x, a, y, b, out):
@@ -218,7 +232,7 @@ def axpby(x, a, y, b, out):
 
 
 def add_tf32(x, y, out):
-    out.copy_(x + y)
+    out.copy_(_q(x + y))
 
 
 def fill(x, v):
@@ -226,7 +240,9 @@ def fill(x, v):
 
 
 def round_tf32(x, y):
-    if y.data_ptr() != x.data_ptr():
+    if EMULATE_TF32:
+        y.copy_(_rt(x))
+    elif y.data_ptr() != x.data_ptr():
         y.copy_(x)
 
 
@@ -242,8 +258,8 @@ def sigmoid_fwd(x, y):
     y.copy_(torch.sigmoid(x))
 
 
-def dropout(x, y, ratio, seed, offset):
-    g = torch.Generator().manual_seed(int(seed) * 1000003 + int(offset))
+def dropout(x, y, ratio, seed, offset, step=None):
+    g = torch.Generator().manual_seed(int(seed) * 1000003 + int(offset) + (int(step.item()) << 20 if step is not None else 0))
     mask = (torch.rand(x.shape, generator=g) >= ratio).to(x.dtype)
     y.copy_(x * mask / (1.0 - ratio))
 
@@ -309,7 +325,7 @@ def sgd_nesterov(p, g, m, lr, momentum, wd, nesterov=True, p_tf32=None):
     g.copy_(ng)
     p.sub_(ng)
     if p_tf32 is not None:
-        p_tf32.copy_(p)
+        p_tf32.copy_(_q(p))
 
 
 def install():

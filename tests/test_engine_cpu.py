@@ -129,3 +129,33 @@ def test_fusion_plan(fake):
     assert s.affine and s.res_key[0] == 'res4_1_branch2c_bn' and not s.relu and s.b
     assert len([s for s in net.steps if isinstance(s, X.ScaleStep)]) == 0       # folded into the softmax
     assert len(convs) == 53 + 20 + 2 + 8
+
+
+def test_tf32_rounding_points_match_oracle_emulation(fake):
+    """The engine rounds GEMM operands to TF32 at their producers.  With the
+    CPU stand-in performing the same roundings, the forward must coincide with the oracle's
+    `emulate_tf32` mode except for the rare elements that sit on a TF32 rounding boundary."""
+    from oracle import model as OM
+    from vlfb import workspace
+    fake.EMULATE_TF32 = True
+    try:
+        H.setup_cfg('ava_r50_lfb_nl.yaml', TINY)
+        ocfg = H.oracle_cfg('ava_r50_lfb_nl.yaml', TINY)
+        params = OM.make_params(ocfg, seed=2)
+        inputs = OM.make_inputs(ocfg, n_clips=2, rois_per_clip=2, crop=64, frames=8)
+        model, sfx = H.build('val', False)
+        H.feed_params(dict((k, v) for k, v in params.items() if workspace.HasBlob(k)))
+        H.feed_inputs(inputs, sfx)
+        workspace.RunNet(model.net.Proto().name)
+        p64 = dict((k, v.double()) for k, v in params.items())
+        i64 = dict((k, (v.double() if v.dtype == torch.float32 else v)) for k, v in inputs.items())
+        blobs, _, _ = OM.forward(ocfg, p64, i64, 'val', emulate_tf32=True)
+        for name in ('pool1', 'res3_3_branch2c_bn', 'nonlocal_conv4_1_sum', 'res5_2_branch2c_bn', 'lfb_nl1_sum'):
+            a = workspace.FetchBlob('gpu_0/' + name)
+            b = blobs[name].numpy()
+            differing = float((np.abs(a - b) > 1e-9 * np.abs(b).max()).mean())
+            print(name, 'fraction of elements differing from the emulating oracle: %.2e' % differing)
+            assert differing < 1e-3, (name, differing)          # one-ulp boundary cases only
+            assert H.rel(a, b) < 2.5e-3, name                   # and never more than a TF32 ulp or two
+    finally:
+        fake.EMULATE_TF32 = False

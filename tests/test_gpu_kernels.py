@@ -338,6 +338,12 @@ def test_elementwise_and_layout(K):
     out2 = torch.empty_like(big)
     K.dropout(big, out2, 0.3, 1234, 0)
     assert torch.equal(out, out2)
+    step = torch.zeros(1, dtype=torch.int64, device='cuda')
+    K.dropout(big, out2, 0.3, 1234, 0, step)
+    assert torch.equal(out, out2)                    # step 0 == no step
+    step.fill_(5)
+    K.dropout(big, out2, 0.3, 1234, 0, step)
+    assert not torch.equal(out, out2) and abs(float((out2 > 0).float().mean()) - 0.7) < 0.01
 
 
 def test_losses_and_sgd(K):

@@ -254,6 +254,36 @@ struct KLoader {
   }
 };
 
+// ---------------------------------------------------------------- fast integer division
+// q = x / d for 0 <= x < 2^31 with a precomputed multiplier (the gather loaders decode an output
+// position per 16-byte copy; 64-bit hardware division there cost more than the copy itself).
+struct FastDiv { uint32_t mul, shr, d; };
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = (uint32_t)d;
+  if (d <= 1) { f.mul = 0; f.shr = 0; return f; }
+  int lg = 31 - __builtin_clz((unsigned)d);
+  if (d & (d - 1)) ++lg;                       // ceil(log2 d)
+  const int p = 31 + lg;
+  f.mul = (uint32_t)(((1ull << p) + (uint64_t)d - 1) / (uint64_t)d);
+  f.shr = (uint32_t)(p - 32);
+  return f;
+}
+__device__ __forceinline__ void fd_divmod(uint32_t x, const FastDiv& f, uint32_t& q, uint32_t& r) {
+  q = (f.d <= 1) ? x : (__umulhi(x, f.mul) >> f.shr);
+  r = x - q * f.d;
+}
+struct PosDiv { FastDiv w, h, t; };
+__device__ __forceinline__ Pos4 decode_pos_fast(uint32_t idx, const PosDiv& pd) {
+  Pos4 p;
+  uint32_t q, r;
+  fd_divmod(idx, pd.w, q, r); p.w = (int)r;
+  fd_divmod(q, pd.h, q, r); p.h = (int)r;
+  fd_divmod(q, pd.t, q, r); p.t = (int)r;
+  p.n = (int)q;
+  return p;
+}
+
 // ---------------------------------------------------------------- MN-major loaders
 // Tile = 32 k-rows, each `rows`*4 bytes of the m (or n) extent, stored as
 // [k-group of 4][atom of 32 elements][4 k-rows][128 B] (UMMA canonical MN-major SWIZZLE_128B_BASE32B).
@@ -275,17 +305,19 @@ struct MNLoader {
   }
 
   // k0 = first k of this chunk, kend = exclusive k limit of this CTA's K range.
-  __device__ __forceinline__ void issue(const vlfb_gemm_params_t& p, int k0, int kend, uint32_t tile) const {
+  __device__ __forceinline__ void issue(const vlfb_gemm_params_t& p, const PosDiv& pd, int k0, int kend,
+                                        uint32_t tile) const {
     const vlfb_conv_geom_t& g = p.g;
-    const int cpr = rows >> 2;            // 16-byte chunks per k-row
+    const int cpr = rows >> 2;            // 16-byte chunks per k-row (8, 16, 32 or 64)
+    const int lcpr = 31 - __clz(cpr);
     const int natoms = rows >> 5;
     const int total = KC * cpr;
     int kt = 0, kh = 0, kw = 0;
     if (KIND == VLFB_OP_CONV_MN) decode_tap(tapz, g.kH, g.kW, kt, kh, kw);
     if (KIND == VLFB_OP_STEM_MN) { kt = tapz / g.kH; kh = tapz - kt * g.kH; }
     for (int idx = threadIdx.x; idx < total; idx += NPROD) {
-      const int kk = idx / cpr;
-      const int c = idx - kk * cpr;
+      const int kk = idx >> lcpr;
+      const int c = idx & (cpr - 1);
       const int k = k0 + kk;
       const int mn = row0 + c * 4;
       bool ok = k < kend && mn < limit;
@@ -293,16 +325,16 @@ struct MNLoader {
       if (KIND == VLFB_OP_DENSE_MN) {
         if (ok) src = base + (int64_t)k * ld + mn;
       } else if (KIND == VLFB_OP_CONV_MN) {
-        Pos4 o = decode_pos(ok ? k : 0, g.To, g.Ho, g.Wo);
+        const Pos4 o = decode_pos_fast(ok ? (uint32_t)k : 0u, pd);
         const int ti = o.t * g.sT - g.pT + kt * g.dT, hi = o.h * g.sH - g.pH + kh * g.dH,
                   wi = o.w * g.sW - g.pW + kw * g.dW;
         ok = ok && (unsigned)ti < (unsigned)g.T && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
-        if (ok) src = base + ((((int64_t)o.n * g.T + ti) * g.H + hi) * g.W + wi) * g.C + mn;
+        if (ok) src = base + (int64_t)(((o.n * g.T + ti) * g.H + hi) * g.W + wi) * g.C + mn;
       } else {  // STEM_MN: rows == 32, chunk c = pixel
-        Pos4 o = decode_pos(ok ? k : 0, g.To, g.Ho, g.Wo);
+        const Pos4 o = decode_pos_fast(ok ? (uint32_t)k : 0u, pd);
         const int ti = o.t * g.sT - g.pT + kt, hi = o.h * g.sH - g.pH + kh, wi = o.w * g.sW - g.pW + c;
         ok = ok && (unsigned)ti < (unsigned)g.T && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
-        if (ok) src = base + ((((int64_t)o.n * g.T + ti) * g.H + hi) * g.W + wi) * 4;
+        if (ok) src = base + (int64_t)(((o.n * g.T + ti) * g.H + hi) * g.W + wi) * 4;
       }
       // SWIZZLE_128B_BASE32B (the MN-major layout 32-bit operands need; plain SWIZZLE_128B returns
       // zeros for tf32 -- measured, profiles/r01_gemm_layout_diag.txt): atoms of 4 k-rows x 128 B,
@@ -319,6 +351,7 @@ struct MNLoader {
 struct Launch {
   int bn;        // tile N (32/64/128/256) = UMMA N = TMEM columns
   int stages;
+  PosDiv out;    // fast divisors of the conv OUTPUT extents (Wo, Ho, To)
 };
 
 template <int AK, int BK>
@@ -381,8 +414,8 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_param
         if (i >= S) mbar_wait(empty0 + 8 * s, ((i / S) - 1) & 1);
         const uint32_t a_tile = smem_base + s * stage_bytes;
         const uint32_t b_tile = a_tile + A_TILE_BYTES;
-        if (is_mn(AK)) ma.issue(p, k_begin + i * KC, k_end, a_tile); else ka.issue(p, m0, kc0 + i, a_tile);
-        if (is_mn(BK)) mb.issue(p, k_begin + i * KC, k_end, b_tile); else kb.issue(p, n0, kc0 + i, b_tile);
+        if (is_mn(AK)) ma.issue(p, L.out, k_begin + i * KC, k_end, a_tile); else ka.issue(p, m0, kc0 + i, a_tile);
+        if (is_mn(BK)) mb.issue(p, L.out, k_begin + i * KC, k_end, b_tile); else kb.issue(p, n0, kc0 + i, b_tile);
         cp_async_commit();
         if (i >= LAG) {
           cp_async_wait<LAG>();
@@ -488,6 +521,9 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_param
 template <int AK, int BK>
 int launch(const vlfb_gemm_params_t& p, cudaStream_t stream) {
   Launch L;
+  L.out.w = make_fastdiv(p.g.Wo);
+  L.out.h = make_fastdiv(p.g.Ho);
+  L.out.t = make_fastdiv(p.g.To);
   if (BK == VLFB_OP_STEM_MN) L.bn = 32;
   else if (p.N > 128) L.bn = 256;
   else if (p.N > 64) L.bn = 128;

@@ -399,8 +399,9 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t ctr, uint64_t key) {
 }
 
 __global__ void dropout_k(const float* __restrict__ x, float* __restrict__ y, int64_t n, float ratio, float inv_keep,
-                          uint64_t seed, uint64_t offset) {
+                          uint64_t seed, uint64_t offset, const int64_t* __restrict__ step) {
   const int64_t n4 = (n + 3) >> 2;
+  if (step) offset += (uint64_t)step[0] << 32;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const uint4 r = philox4x32(offset + (uint64_t)i, seed);
     const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
@@ -837,10 +838,12 @@ int vlfb_sigmoid_fwd(const float* x, float* y, int64_t n, void* stream) {
   return ew_launch<EW_SIGMOID>(x, nullptr, y, n, 0.f, 0.f, ST(stream));
 }
 
-int vlfb_dropout_fwd(const float* x, float* y, int64_t n, float ratio, uint64_t seed, uint64_t offset, void* stream) {
+int vlfb_dropout_fwd(const float* x, float* y, int64_t n, float ratio, uint64_t seed, uint64_t offset,
+                     const int64_t* step, void* stream) {
   VLFB_CHECK_ARG(x && y && n >= 0 && ratio >= 0.f && ratio < 1.f);
   if (n == 0) return VLFB_OK;
-  dropout_k<<<stream_grid((n + 3) / 4, TPB), TPB, 0, ST(stream)>>>(x, y, n, ratio, 1.f / (1.f - ratio), seed, offset);
+  dropout_k<<<stream_grid((n + 3) / 4, TPB), TPB, 0, ST(stream)>>>(x, y, n, ratio, 1.f / (1.f - ratio), seed, offset,
+                                                                   step);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }

@@ -100,7 +100,7 @@ __C = _tree({
     'GET_TRAIN_LFB': False,
     # ---- additions of this implementation (not in the reference) -------------
     # B200.COMPUTE: 'tf32' = parity mode (fp32 storage, tcgen05 kind::tf32, fp32 accumulate).
-    'B200': {'COMPUTE': 'tf32', 'GEMM_BACKEND': 'tcgen05'},
+    'B200': {'COMPUTE': 'tf32', 'GEMM_BACKEND': 'tcgen05', 'CUDA_GRAPH': True},
 })
 config = __C
 _DEFAULTS = None

@@ -535,7 +535,7 @@ class DropoutStep(Step):
             return
         y = empty_like_strided(x)
         seed, offset = ctx.ws.next_rng(x.numel())
-        K.dropout(flat(x), flat(y), ratio, seed, offset)
+        K.dropout(flat(x), flat(y), ratio, seed, offset, ctx.ws.step_tensor())
         ctx.saved[id(self)] = (ratio, seed, offset)
         ctx.put(self.op.outputs[0], y)
 
@@ -548,7 +548,7 @@ class DropoutStep(Step):
             ctx.add_grad(self.in_keys[0], gy, owned=False)
             return
         dx = empty_like_strided(gy)
-        K.dropout(flat(gy), flat(dx), st[0], st[1], st[2])
+        K.dropout(flat(gy), flat(dx), st[0], st[1], st[2], ctx.ws.step_tensor())
         ctx.add_grad(self.in_keys[0], dx, owned=True)
 
 
@@ -714,6 +714,17 @@ class CompiledNet(object):
         if self.losses:
             self._analyse()
         self.num_launch_groups = len(self.steps)
+        produced = set()
+        self.external_inputs = []
+        for op in ops:
+            for n in op.inputs:
+                if n not in produced and n not in self.external_inputs and n not in model.params:
+                    self.external_inputs.append(n)
+            produced.update(op.outputs)
+        self._graphs = None
+        self._graph_key = None
+        self._eager_key = None
+        self._eager_runs = 0
 
     # ---- SSA-style versioning of in-place blobs
     def _version(self, ops):
@@ -835,28 +846,95 @@ class CompiledNet(object):
         self.model.param_to_grad = dict((p, p + '_grad') for p in trainable)
 
     # ---- execution
-    def run(self):
-        ws = self.ws
-        ctx = Ctx(ws, self)
+    def _input_key(self):
+        """Shapes + addresses of every external input: a captured graph is only valid for these."""
+        key = []
+        for name in self.external_inputs:
+            t = self.ws.blobs.get(name)
+            if isinstance(t, torch.Tensor):
+                key.append((name, tuple(t.shape), t.data_ptr()))
+        return tuple(key)
+
+    def _forward_backward(self, ctx):
         for st in self.steps:
             st.fwd(ctx)
         if not self.train:
             return
-        store = ws.params
-        store.begin_step(self.trainable)
+        self.ws.params.begin_step(self.trainable)
         for n in self.losses:
             ctx.grads[(n, self.final_ver.get(n, 1))] = None
-            ctx.requires_loss = True
         for st in reversed(self.steps):
             if isinstance(st, (SigmoidCELossStep, SoftmaxCELossStep)):
                 st.bwd(ctx)
             elif any(k in ctx.grads for k in st.out_keys):
                 st.bwd(ctx)
-        ws.last_grads = ctx.grads
+
+    def run(self):
+        """One pass.  Eager for the first runs of a given input signature; after that the whole
+        step (forward + backward [+ SGD]) is replayed from a captured CUDA graph, which removes the
+        per-launch host cost of the ~700 kernels of a step.  The gradient all-reduce (N > 1) stays
+        eager between the two captured halves."""
+        from core.config import config as cfg
+        ws = self.ws
+        ws.begin_run()
+        use_graph = (DEVICE != 'cpu' and cfg.B200.CUDA_GRAPH and not ws.force_eager and K is K_default)
+        key = self._input_key() if use_graph else None
+        if use_graph and self._graphs is not None and self._graph_key == key:
+            g1, g2, n1, n2 = self._graphs
+            g1.replay()
+            K.LAUNCHES += n1
+            if self.train and ws.allreduce is not None:
+                ws.allreduce(ws.params)
+            if g2 is not None:
+                g2.replay()
+                K.LAUNCHES += n2
+            return
+        if use_graph and self._eager_key == key and self._eager_runs >= 2:
+            self._capture(key)
+            return self.run_replay_after_capture()
+        if self._eager_key != key:
+            self._eager_key, self._eager_runs = key, 0
+        self._eager_runs += 1
+        ctx = Ctx(ws, self)
+        self._forward_backward(ctx)
+        if not self.train:
+            return
         if ws.allreduce is not None:
-            ws.allreduce(store)
+            ws.allreduce(ws.params)
         if self.update_ops:
-            self._update(store)
+            self._update(ws.params)
+
+    def _capture(self, key):
+        ws = self.ws
+        torch.cuda.synchronize()
+        split = self.train and ws.allreduce is not None
+        n0 = K.LAUNCHES
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            ctx = Ctx(ws, self)
+            self._forward_backward(ctx)
+            if self.train and self.update_ops and not split:
+                self._update(ws.params)
+        n1 = K.LAUNCHES - n0
+        g2, n2 = None, 0
+        if split and self.update_ops:
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                self._update(ws.params)
+            n2 = K.LAUNCHES - n0 - n1
+        K.LAUNCHES = n0
+        self._graphs = (g1, g2, n1, n2)
+        self._graph_key = key
+
+    def run_replay_after_capture(self):
+        g1, g2, n1, n2 = self._graphs
+        g1.replay()
+        K.LAUNCHES += n1
+        if self.train and self.ws.allreduce is not None:
+            self.ws.allreduce(self.ws.params)
+        if g2 is not None:
+            g2.replay()
+            K.LAUNCHES += n2
 
     def _update(self, store):
         from core.config import config as cfg

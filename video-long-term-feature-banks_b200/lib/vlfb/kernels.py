@@ -103,7 +103,7 @@ def _run_gemm(p, kind='gemm', flops=None):
         e.record()
         if flops is None:
             flops = 2.0 * p.M * p.N * p.K * max(p.batch, 1) * max(p.taps, 1)
-        _PROFILE.append((kind, s, e, flops))
+        _PROFILE.append(('%s M=%d N=%d K=%d z=%d' % (kind, p.M, p.N, p.K, max(p.batch, p.taps) * p.split_k), s, e, flops))
         return
     _check(L.load().vlfb_gemm(C.byref(p), _stream()), 'vlfb_gemm')
 
@@ -401,11 +401,11 @@ def sigmoid_fwd(x, y):
     _check(L.load().vlfb_sigmoid_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), x.numel(), _stream()), 'sigmoid_fwd')
 
 
-def dropout(x, y, ratio, seed, offset):
+def dropout(x, y, ratio, seed, offset, step=None):
     """y = x * mask / (1-ratio); the mask is a pure function of (seed, offset, index), so the same
     call on dy is the backward."""
     _check(L.load().vlfb_dropout_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), x.numel(), float(ratio), int(seed),
-                                      int(offset), _stream()), 'dropout')
+                                      int(offset), _ptr(step), _stream()), 'dropout')
 
 
 def copy2d(src, lds, dst, ldd, rows, cols, accumulate=False, src_off=0, dst_off=0):

@@ -66,7 +66,7 @@ SIGNATURES = {
     'vlfb_relu_bwd_tf32': [_P, _P, _P, _L, _P],
     'vlfb_colsum': [_P, _L, _P, _L, _I, _I, _P],
     'vlfb_sigmoid_fwd': [_P, _P, _L, _P],
-    'vlfb_dropout_fwd': [_P, _P, _L, _F, _U, _U, _P],
+    'vlfb_dropout_fwd': [_P, _P, _L, _F, _U, _U, _P, _P],
     'vlfb_copy2d': [_P, _L, _P, _L, _L, _I, _I, _P],
     'vlfb_nc_to_cl': [_P, _P, _I, _I, _L, _I, _P],
     'vlfb_cl_to_nc': [_P, _P, _I, _I, _L, _I, _P],

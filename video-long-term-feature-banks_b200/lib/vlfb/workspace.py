@@ -202,6 +202,20 @@ class Workspace(object):
         self.rng_offset = 0
         self.last_grads = {}
         self.input_cache = {}
+        self.force_eager = False
+        self.step = 0
+        self._step_t = None
+
+    def begin_run(self):
+        """Advance the device-side step counter (dropout masks of captured graphs depend on it)."""
+        if X.DEVICE != 'cpu' or self._step_t is not None:
+            self.step_tensor().fill_(self.step)
+        self.step += 1
+
+    def step_tensor(self):
+        if self._step_t is None:
+            self._step_t = torch.zeros(1, dtype=torch.int64, device=X.DEVICE)
+        return self._step_t
 
     def next_rng(self, n):
         off = self.rng_offset
@@ -308,42 +322,44 @@ def RunNet(name, num_iter=1):
     return True
 
 
+def _static(key, shape, dtype):
+    """Persistent device buffer: the address is stable while the shape is unchanged (CUDA-graph replay
+    and allocation-free feeding)."""
+    t = _ws.input_cache.get(key)
+    if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+        t = torch.empty(tuple(shape), dtype=dtype, device=X.DEVICE)
+        _ws.input_cache[key] = t
+    return t
+
+
 def _feed_activation(name, arr):
-    if isinstance(arr, torch.Tensor):
-        # already a tensor (e.g. a pinned host staging buffer): async H2D copy on the current stream
-        if arr.dtype in (torch.int32, torch.int64, torch.uint8, torch.bool):
-            _ws.blobs[name] = arr.to(torch.int32).to(X.DEVICE, non_blocking=True)
-            _ws.rounded.discard(name)
-            return
-        return _feed_float(name, arr.to(X.DTYPE).to(X.DEVICE, non_blocking=True))
-    a = np.ascontiguousarray(arr)
-    if a.dtype in (np.int32, np.int64, np.uint8, np.bool_):
-        _ws.blobs[name] = torch.as_tensor(a.astype(np.int32)).to(X.DEVICE)
+    src = arr if isinstance(arr, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(arr))
+    if src.dtype in (torch.int32, torch.int64, torch.uint8, torch.bool, torch.int16, torch.int8):
+        dst = _static(name, src.shape, torch.int32)
+        dst.copy_(src, non_blocking=True)
+        _ws.blobs[name] = dst
         _ws.rounded.discard(name)
         return
-    t = torch.as_tensor(a).to(X.DTYPE)
-    if X.DEVICE != 'cpu':
-        t = t.to(X.DEVICE)
-    _feed_float(name, t)
-
-
-def _feed_float(name, t):
-    if t.dim() == 5:
-        n, c = t.shape[0], t.shape[1]
-        inner = t.shape[2] * t.shape[3] * t.shape[4]
+    if src.dim() == 5:
+        n, c = src.shape[0], src.shape[1]
+        inner = src.shape[2] * src.shape[3] * src.shape[4]
         cpad = 4 if c == 3 else c
-        p = X.empty((n, t.shape[2], t.shape[3], t.shape[4], cpad))
-        X.K.nc_to_cl(t, p, n, c, inner, cpad)
-        X.K.round_tf32(X.flat(p), X.flat(p))
+        stage = _static(name + '/ncthw', src.shape, X.DTYPE)
+        stage.copy_(src, non_blocking=True)                       # H2D (async from pinned memory)
+        p = _static(name, (n, src.shape[2], src.shape[3], src.shape[4], cpad), X.DTYPE)
+        X.K.nc_to_cl(stage, p, n, c, inner, cpad)                 # reference NCTHW blob -> NDHWC (+pad 3->4)
+        X.K.round_tf32(p.view(-1), p.view(-1))
         _ws.blobs[name] = p.permute(0, 4, 1, 2, 3)
         _ws.rounded.add(name)
+        return
+    dst = _static(name, src.shape, X.DTYPE)
+    dst.copy_(src, non_blocking=True)
+    if dst.dim() >= 2 and dst.shape[-1] >= 64:                    # feature banks are GEMM operands
+        X.K.round_tf32(dst.view(-1), dst.view(-1))
+        _ws.rounded.add(name)
     else:
-        if t.dim() >= 2 and t.shape[-1] >= 64:        # feature banks: GEMM operands
-            X.K.round_tf32(t.view(-1), t.view(-1))
-            _ws.rounded.add(name)
-        else:
-            _ws.rounded.discard(name)
-        _ws.blobs[name] = t
+        _ws.rounded.discard(name)
+    _ws.blobs[name] = dst
 
 
 def FeedBlob(name, arr, device_option=None):
@@ -356,7 +372,12 @@ def FeedBlob(name, arr, device_option=None):
         _ws.params.logical(base, 'Mo').copy_(torch.as_tensor(np.asarray(arr)).to(X.DTYPE).to(X.DEVICE))
         return True
     if np.ndim(arr) == 0 or name in ('lr', 'weight_decay', 'weight_decay_bn', 'ONE'):
-        _ws.blobs[name] = torch.as_tensor(np.asarray(arr).reshape(-1)).to(X.DTYPE).to(X.DEVICE)
+        v = torch.as_tensor(np.asarray(arr).reshape(-1)).to(X.DTYPE)
+        cur = _ws.blobs.get(name)
+        if isinstance(cur, torch.Tensor) and cur.shape == v.shape:
+            cur.copy_(v)                                           # in place: captured graphs read this address
+        else:
+            _ws.blobs[name] = v.to(X.DEVICE)
         return True
     _feed_activation(name, arr)
     return True
