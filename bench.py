@@ -75,6 +75,13 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------ CPU reference arm
+def cpu_threads():
+    """Threads for the CPU arm.  Measured on the B200 host (profiles/r01_cpu_thread_sweep.txt, 128
+    logical cores): 8 -> 3.0 s/clip, 16 -> 2.65, 32 -> 2.95, 64 -> 4.7, 128 -> 95: oneDNN's 3-D
+    convolutions stop scaling at 16 threads, so that is what the baseline uses (all cores if fewer)."""
+    return min(os.cpu_count() or 1, 16)
+
+
 def oracle_setup(n_clips, num_gpus):
     import harness as H
     from oracle import model as OM
@@ -104,7 +111,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     OM, ocfg, params, inputs = oracle_setup(1, 1)
     for _ in range(args.warmup):
@@ -245,7 +252,7 @@ def run_b200(args):
     # ---- CPU baseline: the oracle on this box's host cores, bounded sample (N=1 only)
     cpu = None
     if n_gpus == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = cpu_threads()
         torch.set_num_threads(cores)
         OMo, oc, op, oi = oracle_setup(1, 1)
         oracle_step(OMo, oc, op, oi)

@@ -46,8 +46,8 @@ int vlfb_get_gemm_backend(void);
  *   VLFB_OP_DENSE_MN  rows indexed by k at ptr + batch*batch_stride + k*ld, m (or n) contiguous
  *   VLFB_OP_CONV_K    A of conv forward : row m = output position, k = (tap, cin)
  *   VLFB_OP_DGRAD_K   A of conv dgrad   : row m = input position,  k = (tap, cout)
- *   VLFB_OP_CONV_MN   B of conv wgrad   : k = output position, n = cin, tap fixed per z-slice
- *   VLFB_OP_STEM_K / VLFB_OP_STEM_MN    conv1 (Cin padded to 4): k = (kt,kh) x (8 pixels x 4 ch)
+ *   VLFB_OP_CONV_MN   B of conv wgrad   : k = output position, n = (kh,kw,cin), one kt per z-slice
+ *   VLFB_OP_STEM_K / VLFB_OP_STEM_MN    conv1 (Cin padded to 4): k (resp. n) = (kt,kh) x (8 pixels x 4 ch)
  */
 enum {
   VLFB_OP_DENSE_K = 0, VLFB_OP_DENSE_MN = 1, VLFB_OP_CONV_K = 2, VLFB_OP_DGRAD_K = 3,
@@ -79,7 +79,7 @@ typedef struct {
   vlfb_conv_geom_t g;         /* used by the CONV_ / DGRAD_ / STEM_ kinds    */
   int M, N, K;                /* logical GEMM extent (K per z-slice for wgrad) */
   int batch;                  /* >= 1 (DENSE only)                           */
-  int taps;                   /* wgrad: number of taps (z-slices), else 1    */
+  int taps;                   /* wgrad: number of temporal taps kT (z-slices), else 1 */
   int split_k;                /* >= 1; >1 forces atomic accumulation         */
   float* d;                   /* output rows: d + batch*d_batch_stride + m*ldd + n (+ tap*d_tap_stride) */
   int64_t ldd, d_batch_stride, d_tap_stride;

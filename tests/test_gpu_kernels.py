@@ -395,3 +395,13 @@ def test_fbo_attend(K):
     dth, dph, dg = torch.empty_like(yd), torch.empty((R, Lb, d), device='cuda'), torch.empty((R, Lb, d), device='cuda')
     K.fbo_attend_bwd(f(th), f(ph), f(gg), pd, f(dy), dth, dph, dg, sc)
     assert rel_err(dth, th.grad) < 1e-4 and rel_err(dph, ph.grad) < 1e-4 and rel_err(dg, gg.grad) < 1e-5
+
+
+@pytest.mark.parametrize('rows,cols', [(1200, 512), (25088, 256), (3, 80), (70000, 64)])
+def test_colsum(K, rows, cols):
+    x = torch.randn(rows, cols)
+    out = torch.full((cols,), 7.0, device='cuda')
+    K.colsum(x.cuda(), cols, out, rows, cols, accumulate=False)
+    assert rel_err(out, x.double().sum(0)) < 1e-5
+    K.colsum(x.cuda(), cols, out, rows, cols, accumulate=True)
+    assert rel_err(out, 2 * x.double().sum(0)) < 1e-5

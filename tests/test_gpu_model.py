@@ -75,7 +75,8 @@ def _train_case(ws, yaml_name, overrides, crop, frames, rois_per_clip, backend='
     report = {}
     report['loss'] = H.rel(ws.FetchBlob('gpu_0/loss'), loss.item())
     for b in FWD_BLOBS:
-        report[b] = H.rel(ws.FetchBlob('gpu_0/' + b), blobs[b].detach().numpy())
+        if b in blobs:
+            report[b] = H.rel(ws.FetchBlob('gpu_0/' + b), blobs[b].detach().numpy())
     gerr, gcos = {}, {}
     names = model.TrainableParams() if check_all_grads else [
         'pred_w', 'lfb_1x1_w', 'lfb_nl1_out_w', 'res5_2_branch2c_w', 'res4_3_branch2b_w', 'nonlocal_conv4_1_theta_w',

@@ -49,7 +49,7 @@ static int validate_gemm(const vlfb_gemm_params_t& p, bool& tc_ok) {
         VLFB_CHECK_ARG((int64_t)p.M == (int64_t)p.g.N * p.g.T * p.g.H * p.g.W);
         break;
       case VLFB_OP_CONV_MN:
-        VLFB_CHECK_ARG(i == 1 && p.N == p.g.C && (p.g.C & 3) == 0 && p.taps == p.g.kT * p.g.kH * p.g.kW);
+        VLFB_CHECK_ARG(i == 1 && p.N == p.g.kH * p.g.kW * p.g.C && (p.g.C & 3) == 0 && p.taps == p.g.kT);
         VLFB_CHECK_ARG((int64_t)p.K == (int64_t)p.g.N * p.g.To * p.g.Ho * p.g.Wo);
         break;
       case VLFB_OP_STEM_K:
@@ -58,7 +58,7 @@ static int validate_gemm(const vlfb_gemm_params_t& p, bool& tc_ok) {
         VLFB_CHECK_ARG((int64_t)p.M == (int64_t)p.g.N * p.g.To * p.g.Ho * p.g.Wo);
         break;
       case VLFB_OP_STEM_MN:
-        VLFB_CHECK_ARG(i == 1 && p.g.C == 4 && p.g.kW <= 8 && p.N == 32 && p.taps == p.g.kT * p.g.kH);
+        VLFB_CHECK_ARG(i == 1 && p.g.C == 4 && p.g.kW <= 8 && p.N == 32 * p.g.kH && p.taps == p.g.kT);
         VLFB_CHECK_ARG(p.g.dT == 1 && p.g.dH == 1 && p.g.dW == 1);
         VLFB_CHECK_ARG((int64_t)p.K == (int64_t)p.g.N * p.g.To * p.g.Ho * p.g.Wo);
         break;

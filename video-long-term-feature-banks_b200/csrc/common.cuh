@@ -82,14 +82,14 @@ __device__ __forceinline__ float operand_elem(const vlfb_operand_t& op, const vl
       if (to >= g.To || ho >= g.Ho || wo >= g.Wo) return 0.f;
       return op.ptr[((((int64_t)i.n * g.To + to) * g.Ho + ho) * g.Wo + wo) * g.Co + c];
     }
-    case VLFB_OP_CONV_MN: {
+    case VLFB_OP_CONV_MN: {   // k = output position, row = (kh*kW+kw)*C + ci, tap_z = kt
       Pos4 o = decode_pos(k, g.To, g.Ho, g.Wo);
-      int kt, kh, kw;
-      decode_tap(tap_z, g.kH, g.kW, kt, kh, kw);
+      int tap_hw = (int)row / g.C, ci = (int)row % g.C;
+      int kt = tap_z, kh = tap_hw / g.kW, kw = tap_hw % g.kW;
       int ti = o.t * g.sT - g.pT + kt * g.dT, hi = o.h * g.sH - g.pH + kh * g.dH,
           wi = o.w * g.sW - g.pW + kw * g.dW;
       if (ti < 0 || ti >= g.T || hi < 0 || hi >= g.H || wi < 0 || wi >= g.W) return 0.f;
-      return op.ptr[((((int64_t)o.n * g.T + ti) * g.H + hi) * g.W + wi) * g.C + row];
+      return op.ptr[((((int64_t)o.n * g.T + ti) * g.H + hi) * g.W + wi) * g.C + ci];
     }
     case VLFB_OP_STEM_K: {   // C == 4 (3 + zero pad); k = (kt*kH+kh)*32 + px*4 + ch
       Pos4 o = decode_pos(row, g.To, g.Ho, g.Wo);
@@ -99,10 +99,10 @@ __device__ __forceinline__ float operand_elem(const vlfb_operand_t& op, const vl
       if (ti < 0 || ti >= g.T || hi < 0 || hi >= g.H || wi < 0 || wi >= g.W) return 0.f;
       return op.ptr[((((int64_t)o.n * g.T + ti) * g.H + hi) * g.W + wi) * 4 + ch];
     }
-    case VLFB_OP_STEM_MN: {  // k = output position, row = px*4+ch, tap_z = kt*kH+kh
+    case VLFB_OP_STEM_MN: {  // k = output position, row = kh*32 + px*4 + ch, tap_z = kt
       Pos4 o = decode_pos(k, g.To, g.Ho, g.Wo);
-      int px = (int)row >> 2, ch = (int)row & 3;
-      int kt = tap_z / g.kH, kh = tap_z % g.kH;
+      int kh = (int)row >> 5, px = ((int)row & 31) >> 2, ch = (int)row & 3;
+      int kt = tap_z;
       int ti = o.t * g.sT - g.pT + kt, hi = o.h * g.sH - g.pH + kh, wi = o.w * g.sW - g.pW + px;
       if (ti < 0 || ti >= g.T || hi < 0 || hi >= g.H || wi < 0 || wi >= g.W) return 0.f;
       return op.ptr[((((int64_t)o.n * g.T + ti) * g.H + hi) * g.W + wi) * 4 + ch];

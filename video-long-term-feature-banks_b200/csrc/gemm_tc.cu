@@ -305,43 +305,60 @@ struct MNLoader {
   }
 
   // k0 = first k of this chunk, kend = exclusive k limit of this CTA's K range.
-  __device__ __forceinline__ void issue(const vlfb_gemm_params_t& p, const PosDiv& pd, int k0, int kend,
-                                        uint32_t tile) const {
+  // Conv kinds (wgrad B operand): the N extent spans ALL (kh,kw) taps of one kt slice,
+  // n = (kh*kW + kw)*C + ci, so one pass over dY feeds up to 256 (tap, ci) columns.  Each lane
+  // decodes ONE of the 32 k-rows (output positions) of the chunk; the copy loop fetches the row
+  // info it needs with warp shuffles, so there is one position decode per thread per chunk.
+  __device__ __forceinline__ void issue(const vlfb_gemm_params_t& p, const PosDiv& pd, const FastDiv& cdiv,
+                                        const FastDiv& kwdiv, int k0, int kend, uint32_t tile) const {
     const vlfb_conv_geom_t& g = p.g;
     const int cpr = rows >> 2;            // 16-byte chunks per k-row (8, 16, 32 or 64)
     const int lcpr = 31 - __clz(cpr);
     const int natoms = rows >> 5;
     const int total = KC * cpr;
-    int kt = 0, kh = 0, kw = 0;
-    if (KIND == VLFB_OP_CONV_MN) decode_tap(tapz, g.kH, g.kW, kt, kh, kw);
-    if (KIND == VLFB_OP_STEM_MN) { kt = tapz / g.kH; kh = tapz - kt * g.kH; }
+    int info_a = 0, info_b = 0;           // per-lane k-row: (n*T + t0) and (h0 << 16 | w0 & 0xffff)
+    if (KIND != VLFB_OP_DENSE_MN) {
+      const int k = k0 + (threadIdx.x & 31);
+      const bool okr = k < kend;
+      const Pos4 o = decode_pos_fast(okr ? (uint32_t)k : 0u, pd);
+      const int kt = tapz;                // z slice = temporal tap
+      const int t0 = o.t * g.sT - g.pT + kt * g.dT;
+      const bool okt = okr && (unsigned)t0 < (unsigned)g.T;
+      info_a = okt ? (o.n * g.T + t0) : -1;
+      info_b = ((o.h * g.sH - g.pH) << 16) | ((o.w * g.sW - g.pW) & 0xFFFF);
+    }
     for (int idx = threadIdx.x; idx < total; idx += NPROD) {
       const int kk = idx >> lcpr;
       const int c = idx & (cpr - 1);
-      const int k = k0 + kk;
       const int mn = row0 + c * 4;
-      bool ok = k < kend && mn < limit;
+      bool ok = mn < limit;
       const float* src = base;
       if (KIND == VLFB_OP_DENSE_MN) {
+        const int k = k0 + kk;
+        ok = ok && k < kend;
         if (ok) src = base + (int64_t)k * ld + mn;
-      } else if (KIND == VLFB_OP_CONV_MN) {
-        const Pos4 o = decode_pos_fast(ok ? (uint32_t)k : 0u, pd);
-        const int ti = o.t * g.sT - g.pT + kt * g.dT, hi = o.h * g.sH - g.pH + kh * g.dH,
-                  wi = o.w * g.sW - g.pW + kw * g.dW;
-        ok = ok && (unsigned)ti < (unsigned)g.T && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
-        if (ok) src = base + (int64_t)(((o.n * g.T + ti) * g.H + hi) * g.W + wi) * g.C + mn;
-      } else {  // STEM_MN: rows == 32, chunk c = pixel
-        const Pos4 o = decode_pos_fast(ok ? (uint32_t)k : 0u, pd);
-        const int ti = o.t * g.sT - g.pT + kt, hi = o.h * g.sH - g.pH + kh, wi = o.w * g.sW - g.pW + c;
-        ok = ok && (unsigned)ti < (unsigned)g.T && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
-        if (ok) src = base + (int64_t)(((o.n * g.T + ti) * g.H + hi) * g.W + wi) * 4;
+      } else {
+        const int ra = __shfl_sync(0xffffffffu, info_a, kk);
+        const int rb = __shfl_sync(0xffffffffu, info_b, kk);
+        int kh, kw, ci;
+        if (KIND == VLFB_OP_CONV_MN) {
+          uint32_t tap_hw, cc, qh, qw;
+          fd_divmod((uint32_t)mn, cdiv, tap_hw, cc);     // n = tap_hw * C + ci
+          fd_divmod(tap_hw, kwdiv, qh, qw);
+          kh = (int)qh * g.dH; kw = (int)qw * g.dW; ci = (int)cc;
+        } else {                                         // STEM_MN: n = kh*32 + px*4 (+ch)
+          kh = mn >> 5; kw = (mn & 31) >> 2; ci = 0;
+        }
+        const int hi = (rb >> 16) + kh, wi = (int)(short)(rb & 0xFFFF) + kw;
+        ok = ok && ra >= 0 && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
+        if (ok) src = base + (int64_t)((ra * g.H + hi) * g.W + wi) * g.C + ci;
       }
       // SWIZZLE_128B_BASE32B (the MN-major layout 32-bit operands need; plain SWIZZLE_128B returns
       // zeros for tf32 -- measured, profiles/r01_gemm_layout_diag.txt): atoms of 4 k-rows x 128 B,
       // 32-byte units XOR (k & 3).
-      const int r = kk & 3, cc = c & 7;
+      const int r = kk & 3, cc8 = c & 7;
       const uint32_t dst = tile + (kk >> 2) * (natoms * 512) + (c >> 3) * 512 + r * 128 +
-                           ((((cc >> 1) ^ r) << 5) | ((cc & 1) << 4));
+                           ((((cc8 >> 1) ^ r) << 5) | ((cc8 & 1) << 4));
       cp_async16(dst, src, ok);
     }
   }
@@ -352,6 +369,8 @@ struct Launch {
   int bn;        // tile N (32/64/128/256) = UMMA N = TMEM columns
   int stages;
   PosDiv out;    // fast divisors of the conv OUTPUT extents (Wo, Ho, To)
+  FastDiv cdiv;  // input channels C (wgrad: n -> (tap, ci))
+  FastDiv kwdiv; // kW
 };
 
 template <int AK, int BK>
@@ -414,8 +433,8 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_param
         if (i >= S) mbar_wait(empty0 + 8 * s, ((i / S) - 1) & 1);
         const uint32_t a_tile = smem_base + s * stage_bytes;
         const uint32_t b_tile = a_tile + A_TILE_BYTES;
-        if (is_mn(AK)) ma.issue(p, L.out, k_begin + i * KC, k_end, a_tile); else ka.issue(p, m0, kc0 + i, a_tile);
-        if (is_mn(BK)) mb.issue(p, L.out, k_begin + i * KC, k_end, b_tile); else kb.issue(p, n0, kc0 + i, b_tile);
+        if (is_mn(AK)) ma.issue(p, L.out, L.cdiv, L.kwdiv, k_begin + i * KC, k_end, a_tile); else ka.issue(p, m0, kc0 + i, a_tile);
+        if (is_mn(BK)) mb.issue(p, L.out, L.cdiv, L.kwdiv, k_begin + i * KC, k_end, b_tile); else kb.issue(p, n0, kc0 + i, b_tile);
         cp_async_commit();
         if (i >= LAG) {
           cp_async_wait<LAG>();
@@ -432,14 +451,17 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_param
       mbar_wait(tfull, 0);
       tc_fence_after();
     }
-    const int m = m0 + tid;                 // TMEM lane == tile row
+    // TMEM lane == tile row: thread (warp w, lane l) owns row 32w + l.  Each 32x32 block is transposed
+    // through a padded shared-memory tile (the pipeline stages are idle by now) so that every warp
+    // store / residual load / atomic touches whole 128-byte lines: lanes 0-7 cover one row's 128 B.
+    const int lane = tid & 31;
     const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-    const int64_t row_off = (int64_t)batch * p.d_batch_stride + (int64_t)tap * p.d_tap_stride + (int64_t)m * p.ldd;
+    float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + warp * (32 * 36);
+    const int64_t tile_off = (int64_t)batch * p.d_batch_stride + (int64_t)tap * p.d_tap_stride;
     const bool vec_ok = ((p.ldd & 3) == 0) && ((p.d_batch_stride & 3) == 0) && ((p.d_tap_stride & 3) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0) &&
-                        (!p.residual || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) &&
-                        !(p.flags & (VLFB_EPI_ATOMIC | VLFB_EPI_ACCUM));
-    const float rs = (p.row_scale && m < p.M) ? p.row_scale[m] : 1.f;
+                        (!p.residual || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+    const int col = (lane & 7) * 4;
     for (int c0 = 0; c0 < bn; c0 += 32) {
       if (n0 + c0 >= p.N) break;            // uniform
       float v[32];
@@ -450,39 +472,56 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_param
 #pragma unroll
         for (int q = 0; q < 32; ++q) v[q] = 0.f;
       }
-      if (m < p.M) {
 #pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-          const int n = n0 + c0 + q;
-          if (vec_ok && n + 3 < p.N) {
-            float4 o = make_float4(v[q] * p.alpha, v[q + 1] * p.alpha, v[q + 2] * p.alpha, v[q + 3] * p.alpha);
-            if (p.col_scale) {
-              const float4 s4 = *reinterpret_cast<const float4*>(p.col_scale + n);
-              o.x *= s4.x; o.y *= s4.y; o.z *= s4.z; o.w *= s4.w;
-            }
-            if (p.col_bias) {
-              const float4 b4 = *reinterpret_cast<const float4*>(p.col_bias + n);
-              o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-            }
-            o.x *= rs; o.y *= rs; o.z *= rs; o.w *= rs;
-            if (p.residual) {
-              const float4 r4 = *reinterpret_cast<const float4*>(p.residual + row_off + n);
-              o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
-            }
-            if (p.flags & VLFB_EPI_RELU) {
-              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-            }
-            if (p.flags & VLFB_EPI_TF32) {
-              o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
-            }
-            *reinterpret_cast<float4*>(p.d + row_off + n) = o;
-          } else {
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(stg + lane * 36 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      __syncwarp();
+      const int n = n0 + c0 + col;
+      float4 cs = make_float4(1.f, 1.f, 1.f, 1.f), cb = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool nfull = n + 3 < p.N;
+      if (nfull) {
+        if (p.col_scale) cs = *reinterpret_cast<const float4*>(p.col_scale + n);
+        if (p.col_bias) cb = *reinterpret_cast<const float4*>(p.col_bias + n);
+      }
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (n + e < p.N) epilogue_store(p, batch, tap, m, n + e, v[q + e]);
+      for (int i = 0; i < 8; ++i) {
+        const int row = (lane >> 3) + 4 * i;
+        const int m = m0 + warp * 32 + row;
+        if (m >= p.M || n >= p.N) continue;
+        const float4 a4 = *reinterpret_cast<const float4*>(stg + row * 36 + col);
+        if (nfull && vec_ok) {
+          const float rs = p.row_scale ? p.row_scale[m] : 1.f;
+          float4 o = make_float4(a4.x * p.alpha, a4.y * p.alpha, a4.z * p.alpha, a4.w * p.alpha);
+          o.x = (o.x * cs.x + cb.x) * rs; o.y = (o.y * cs.y + cb.y) * rs;
+          o.z = (o.z * cs.z + cb.z) * rs; o.w = (o.w * cs.w + cb.w) * rs;
+          const int64_t off = tile_off + (int64_t)m * p.ldd + n;
+          if (p.residual) {
+            const float4 r4 = *reinterpret_cast<const float4*>(p.residual + off);
+            o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
           }
+          if (p.flags & VLFB_EPI_RELU) {
+            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+          }
+          if (p.flags & VLFB_EPI_TF32) {
+            o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+          }
+          float* dst = p.d + off;
+          if (p.flags & VLFB_EPI_ATOMIC) {
+            atomicAdd(dst, o.x); atomicAdd(dst + 1, o.y); atomicAdd(dst + 2, o.z); atomicAdd(dst + 3, o.w);
+          } else if (p.flags & VLFB_EPI_ACCUM) {
+            const float4 d4 = *reinterpret_cast<const float4*>(dst);
+            *reinterpret_cast<float4*>(dst) = make_float4(d4.x + o.x, d4.y + o.y, d4.z + o.z, d4.w + o.w);
+          } else {
+            *reinterpret_cast<float4*>(dst) = o;
+          }
+        } else {
+          const float e4[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (n + e < p.N) epilogue_store(p, batch, tap, m, n + e, e4[e]);
         }
       }
+      __syncwarp();
     }
   } else if (nk > 0) {
     // ============================ MMA ISSUER ===========================
@@ -524,8 +563,9 @@ int launch(const vlfb_gemm_params_t& p, cudaStream_t stream) {
   L.out.w = make_fastdiv(p.g.Wo);
   L.out.h = make_fastdiv(p.g.Ho);
   L.out.t = make_fastdiv(p.g.To);
-  if (BK == VLFB_OP_STEM_MN) L.bn = 32;
-  else if (p.N > 128) L.bn = 256;
+  L.cdiv = make_fastdiv(p.g.C);
+  L.kwdiv = make_fastdiv(p.g.kW);
+  if (p.N > 128) L.bn = 256;
   else if (p.N > 64) L.bn = 128;
   else if (p.N > 32) L.bn = 64;
   else L.bn = 32;

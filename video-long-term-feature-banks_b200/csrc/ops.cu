@@ -427,21 +427,24 @@ __global__ void copy2d_k(const float* __restrict__ src, int64_t lds, float* __re
   }
 }
 
-// out[c] (+)= sum_r x[r*ld+c]: block = 32 columns x 8 row-lanes
+// out[c] += sum_r x[r*ld+c]: block = 32 columns x 8 row-lanes over a slab of rows; slabs combine with
+// one atomicAdd per column (out is zeroed first unless accumulating).
 __global__ void colsum_k(const float* __restrict__ x, int64_t ld, float* __restrict__ out, int64_t rows, int cols,
-                         int accumulate) {
+                         int64_t rows_per_block) {
   __shared__ float part[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
   float s = 0.f;
   if (c < cols)
-    for (int64_t r = threadIdx.y; r < rows; r += 8) s += x[r * ld + c];
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s += x[r * ld + c];
   part[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && c < cols) {
     float t = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) t += part[j][threadIdx.x];
-    out[c] = accumulate ? out[c] + t : t;
+    atomicAdd(out + c, t);
   }
 }
 
@@ -829,7 +832,18 @@ int vlfb_relu_bwd_tf32(const float* dy, const float* y, float* dx, int64_t n, vo
 }
 int vlfb_colsum(const float* x, int64_t ld, float* out, int64_t rows, int cols, int accumulate, void* stream) {
   VLFB_CHECK_ARG(x && out && rows >= 0 && cols > 0);
-  colsum_k<<<ceil_div(cols, 32), dim3(32, 8), 0, ST(stream)>>>(x, ld, out, rows, cols, accumulate);
+  if (!accumulate) {
+    int rc = ew_launch<EW_FILL>(nullptr, nullptr, out, cols, 0.f, 0.f, ST(stream));
+    if (rc != VLFB_OK) return rc;
+  }
+  if (rows == 0) return VLFB_OK;
+  const int cb = ceil_div(cols, 32);
+  int slabs = (int)((2 * 148 + cb - 1) / cb);                 // ~2 waves of blocks on 148 SMs
+  const int64_t max_slabs = (rows + 63) / 64;
+  if (slabs > max_slabs) slabs = (int)max_slabs;
+  if (slabs < 1) slabs = 1;
+  const int64_t rpb = (rows + slabs - 1) / slabs;
+  colsum_k<<<dim3(cb, slabs), dim3(32, 8), 0, ST(stream)>>>(x, ld, out, rows, cols, rpb);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }

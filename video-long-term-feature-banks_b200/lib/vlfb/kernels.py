@@ -200,13 +200,15 @@ def conv_wgrad(dy, x, dw, g, row_scale=None, col_mask=None):
     _f32c(dy, 'dy'), _f32c(x, 'x'), _f32c(dw, 'dw')
     Kpos = g.N * g.To * g.Ho * g.Wo
     if g.C == 4:
-        taps, n = g.kT * g.kH, 32
+        taps, n = g.kT, g.kH * 32
         b = _operand(x, L.OP_STEM_MN)
+        if col_mask is not None and col_mask.numel() == 32:
+            col_mask = col_mask.repeat(g.kH)
     elif _is_pointwise(g):
         taps, n = 1, g.C
         b = _operand(x, L.OP_DENSE_MN, ld=g.C)
     else:
-        taps, n = g.kT * g.kH * g.kW, g.C
+        taps, n = g.kT, g.kH * g.kW * g.C          # one z-slice per temporal tap; N spans (kh, kw, ci)
         b = _operand(x, L.OP_CONV_MN)
     p = _base_params(g.Co, n, Kpos, dw, taps * n)
     p.a = _operand(dy, L.OP_DENSE_MN, ld=g.Co)
