@@ -16,7 +16,9 @@
 // Operand kinds are described in include/vlfb.h; their element-level definition is
 // operand_elem() in common.cuh, which the SIMT engine evaluates literally and the tests
 // compare this kernel against.
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -25,8 +27,12 @@ namespace tc {
 
 constexpr int BM = 128;        // tile rows (UMMA M)
 constexpr int KC = 32;         // fp32 per K chunk (128 B)
-constexpr int NPROD = 128;     // producer / epilogue threads
-constexpr int NTHREADS = 160;  // + MMA warp
+constexpr int NPROD = 256;     // producer / epilogue threads: 8 warps = 2 per scheduler, so the address-
+                               // generation ALU latency of one warp hides behind the other (ncu r01: with one
+                               // producer warp per scheduler 'wait'+'selected' stalls dominated, no unit >14% busy)
+constexpr int NPW = NPROD / 32;
+constexpr int RSTEP = NPROD / 8;   // rows covered by one pass of the K-major loaders
+constexpr int NTHREADS = NPROD + 32;  // + MMA warp
 constexpr int A_TILE_BYTES = BM * KC * 4;  // 16 KB
 constexpr int MAX_STAGES = 8;
 
@@ -66,6 +72,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
   const int sz = valid ? 16 : 0;   // src-size 0 => 16 bytes of zeros (conv padding / tails)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+// TMA: one thread arms the stage barrier with the byte count, then issues the bulk tensor copy; the copy
+// engine writes the box into shared memory in the SWIZZLE_128B pattern and completes the transaction.
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -140,7 +157,7 @@ __host__ __device__ inline uint32_t make_idesc(int bn, int a_mn_major, int b_mn_
 __host__ __device__ constexpr bool is_mn(int kind) { return kind == VLFB_OP_DENSE_MN || kind == VLFB_OP_CONV_MN || kind == VLFB_OP_STEM_MN; }
 
 // ---------------------------------------------------------------- K-major loaders
-// Tile = `rows` rows x 128 B.  Thread t copies the 16-byte chunk (t & 7) of rows (t >> 3) + 16 j.
+// Tile = `rows` rows x 128 B.  Thread t copies the 16-byte chunk (t & 7) of rows (t >> 3) + RSTEP j.
 template <int KIND, int MAXR>
 struct KLoader {
   const float* base;
@@ -154,7 +171,7 @@ struct KLoader {
   __device__ __forceinline__ void init(const vlfb_gemm_params_t& p, const vlfb_operand_t& op, int row0, int rows,
                                        int limit, int batch) {
     const int tid = threadIdx.x;
-    nrow = rows >> 4;
+    nrow = rows / RSTEP;
     base = op.ptr;
     ld = op.ld;
     kend = p.K;
@@ -164,7 +181,7 @@ struct KLoader {
 #pragma unroll
     for (int j = 0; j < MAXR; ++j) {
       if (j >= nrow) break;
-      const int row = row0 + (tid >> 3) + 16 * j;
+      const int row = row0 + (tid >> 3) + RSTEP * j;
       const bool ok = row < limit;
       if (KIND == VLFB_OP_DENSE_K) {
         if (ok) rowmask |= 1u << j;
@@ -194,7 +211,7 @@ struct KLoader {
 #pragma unroll
       for (int j = 0; j < MAXR; ++j) {
         if (j >= nrow) break;
-        const int r = r0 + 16 * j;
+        const int r = r0 + RSTEP * j;
         const bool ok = kok && ((rowmask >> j) & 1u);
         const float* src = ok ? base + (int64_t)(row0 + r) * ld + k : base;
         cp_async16(tile + r * 128 + ((c ^ (r & 7)) << 4), src, ok);
@@ -209,7 +226,7 @@ struct KLoader {
 #pragma unroll
       for (int j = 0; j < MAXR; ++j) {
         if (j >= nrow) break;
-        const int r = r0 + 16 * j;
+        const int r = r0 + RSTEP * j;
         const int ti = s_t[j] + dt, hi = (s_hw[j] >> 16) + dh, wi = (int)(short)(s_hw[j] & 0xFFFF) + dw;
         const bool ok = (unsigned)ti < (unsigned)g.T && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
         const int64_t pos = ((int64_t)(s_n[j] + ti) * g.H + hi) * g.W + wi;
@@ -221,7 +238,7 @@ struct KLoader {
 #pragma unroll
       for (int j = 0; j < MAXR; ++j) {
         if (j >= nrow) break;
-        const int r = r0 + 16 * j;
+        const int r = r0 + RSTEP * j;
         const int ti = s_t[j] + kt, hi = (s_hw[j] >> 16) + kh, wi = (int)(short)(s_hw[j] & 0xFFFF) + c;
         const bool ok = (unsigned)ti < (unsigned)g.T && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
         const int64_t pos = ((int64_t)(s_n[j] + ti) * g.H + hi) * g.W + wi;
@@ -238,7 +255,7 @@ struct KLoader {
 #pragma unroll
       for (int j = 0; j < MAXR; ++j) {
         if (j >= nrow) break;
-        const int r = r0 + 16 * j;
+        const int r = r0 + RSTEP * j;
         const int a = s_t[j] - dt, b = (s_hw[j] >> 16) - dh, cc = (int)(short)(s_hw[j] & 0xFFFF) - dw;
         bool ok = a >= 0 && b >= 0 && cc >= 0;
         int to = a, ho = b, wo = cc;
@@ -371,10 +388,13 @@ struct Launch {
   PosDiv out;    // fast divisors of the conv OUTPUT extents (Wo, Ho, To)
   FastDiv cdiv;  // input channels C (wgrad: n -> (tap, ci))
   FastDiv kwdiv; // kW
+  int tma_a, tma_b;  // operand fetched by TMA (dense K-major 2-D tiles) instead of cp.async
 };
 
 template <int AK, int BK>
-__global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_params_t p, const Launch L) {
+__global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_params_t p, const Launch L,
+                                                           const __grid_constant__ CUtensorMap tmA,
+                                                           const __grid_constant__ CUtensorMap tmB) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int bn = L.bn, S = L.stages;
@@ -403,24 +423,24 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_param
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full0 + 8 * s, NPROD);
+      mbar_init(full0 + 8 * s, ((L.tma_a && L.tma_b) ? 0 : NPROD) + ((L.tma_a || L.tma_b) ? 1 : 0));
       mbar_init(empty0 + 8 * s, 1);
     }
     mbar_init(tfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) tmem_alloc(tptr_addr, (uint32_t)(bn < 32 ? 32 : bn));
+  if (warp == NPW) tmem_alloc(tptr_addr, (uint32_t)(bn < 32 ? 32 : bn));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tptr_generic;
 
-  if (warp < 4) {
+  if (warp < NPW) {
     // ============================ PRODUCERS ============================
     if (nk > 0) {
-      KLoader<is_mn(AK) ? VLFB_OP_DENSE_K : AK, 8> ka;
+      KLoader<is_mn(AK) ? VLFB_OP_DENSE_K : AK, BM / RSTEP> ka;
       MNLoader<is_mn(AK) ? AK : VLFB_OP_DENSE_MN> ma;
-      KLoader<is_mn(BK) ? VLFB_OP_DENSE_K : BK, 16> kb;
+      KLoader<is_mn(BK) ? VLFB_OP_DENSE_K : BK, 256 / RSTEP> kb;
       MNLoader<is_mn(BK) ? BK : VLFB_OP_DENSE_MN> mb;
       if (is_mn(AK)) ma.init(p, p.a, m0, BM, p.M, batch, tap); else ka.init(p, p.a, m0, BM, p.M, batch);
       if (is_mn(BK)) mb.init(p, p.b, n0, bn, p.N, batch, tap); else kb.init(p, p.b, n0, bn, p.N, batch);
@@ -428,23 +448,38 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_param
       if (!is_mn(BK)) kb.kend = k_end;
       const int kc0 = k_begin / KC;
       constexpr int LAG = 2;
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % S;
-        if (i >= S) mbar_wait(empty0 + 8 * s, ((i / S) - 1) & 1);
-        const uint32_t a_tile = smem_base + s * stage_bytes;
-        const uint32_t b_tile = a_tile + A_TILE_BYTES;
-        if (is_mn(AK)) ma.issue(p, L.out, L.cdiv, L.kwdiv, k_begin + i * KC, k_end, a_tile); else ka.issue(p, m0, kc0 + i, a_tile);
-        if (is_mn(BK)) mb.issue(p, L.out, L.cdiv, L.kwdiv, k_begin + i * KC, k_end, b_tile); else kb.issue(p, n0, kc0 + i, b_tile);
-        cp_async_commit();
-        if (i >= LAG) {
-          cp_async_wait<LAG>();
+      const bool tma_a = !is_mn(AK) && L.tma_a, tma_b = !is_mn(BK) && L.tma_b;
+      const bool cp_any = !(tma_a && tma_b);
+      const uint32_t tma_bytes = (tma_a ? A_TILE_BYTES : 0u) + (tma_b ? b_tile_bytes : 0u);
+      if (cp_any || tid == 0) {
+        for (int i = 0; i < nk; ++i) {
+          const int s = i % S;
+          if (i >= S) mbar_wait(empty0 + 8 * s, ((i / S) - 1) & 1);
+          const uint32_t a_tile = smem_base + s * stage_bytes;
+          const uint32_t b_tile = a_tile + A_TILE_BYTES;
+          if (tid == 0 && tma_bytes) {
+            mbar_expect_tx(full0 + 8 * s, tma_bytes);
+            if (tma_a) tma_load_3d(a_tile, &tmA, (kc0 + i) * KC, m0, batch, full0 + 8 * s);
+            if (tma_b) tma_load_3d(b_tile, &tmB, (kc0 + i) * KC, n0, batch, full0 + 8 * s);
+          }
+          if (!cp_any) continue;
+          if (is_mn(AK)) ma.issue(p, L.out, L.cdiv, L.kwdiv, k_begin + i * KC, k_end, a_tile);
+          else if (!tma_a) ka.issue(p, m0, kc0 + i, a_tile);
+          if (is_mn(BK)) mb.issue(p, L.out, L.cdiv, L.kwdiv, k_begin + i * KC, k_end, b_tile);
+          else if (!tma_b) kb.issue(p, n0, kc0 + i, b_tile);
+          cp_async_commit();
+          if (i >= LAG) {
+            cp_async_wait<LAG>();
+            fence_proxy_async();
+            mbar_arrive(full0 + 8 * ((i - LAG) % S));
+          }
+        }
+        if (cp_any) {
+          cp_async_wait<0>();
           fence_proxy_async();
-          mbar_arrive(full0 + 8 * ((i - LAG) % S));
+          for (int i = (nk > LAG ? nk - LAG : 0); i < nk; ++i) mbar_arrive(full0 + 8 * (i % S));
         }
       }
-      cp_async_wait<0>();
-      fence_proxy_async();
-      for (int i = (nk > LAG ? nk - LAG : 0); i < nk; ++i) mbar_arrive(full0 + 8 * (i % S));
     }
     // ============================ EPILOGUE =============================
     if (nk > 0) {
@@ -455,15 +490,17 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_param
     // through a padded shared-memory tile (the pipeline stages are idle by now) so that every warp
     // store / residual load / atomic touches whole 128-byte lines: lanes 0-7 cover one row's 128 B.
     const int lane = tid & 31;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    // TMEM lane quarter = warp % 4 (hardware rule); warps w and w+4 split the 32-column blocks.
+    const int quarter = warp & 3;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + warp * (32 * 36);
     const int64_t tile_off = (int64_t)batch * p.d_batch_stride + (int64_t)tap * p.d_tap_stride;
     const bool vec_ok = ((p.ldd & 3) == 0) && ((p.d_batch_stride & 3) == 0) && ((p.d_tap_stride & 3) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0) &&
                         (!p.residual || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
     const int col = (lane & 7) * 4;
-    for (int c0 = 0; c0 < bn; c0 += 32) {
-      if (n0 + c0 >= p.N) break;            // uniform
+    for (int c0 = (warp >> 2) * 32; c0 < bn; c0 += 32 * (NPW / 4)) {
+      if (n0 + c0 >= p.N) break;            // warp-uniform
       float v[32];
       if (nk > 0) {
         tmem_ld32(lane_addr + c0, v);
@@ -483,22 +520,31 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_param
         if (p.col_scale) cs = *reinterpret_cast<const float4*>(p.col_scale + n);
         if (p.col_bias) cb = *reinterpret_cast<const float4*>(p.col_bias + n);
       }
+      // residual / accumulate operands of the 8 row groups are fetched up front (8 independent 128-bit
+      // loads in flight per lane) so that their latency overlaps instead of serialising per row
+      float4 rr[8];
+      const bool want_res = (p.residual != nullptr) || (p.flags & VLFB_EPI_ACCUM);
+      const float* res_src = p.residual ? p.residual : p.d;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + quarter * 32 + (lane >> 3) + 4 * i;
+        rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (want_res && nfull && vec_ok && m < p.M && !(p.residual && (p.flags & VLFB_EPI_ACCUM)))
+          rr[i] = *reinterpret_cast<const float4*>(res_src + tile_off + (int64_t)m * p.ldd + n);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int row = (lane >> 3) + 4 * i;
-        const int m = m0 + warp * 32 + row;
+        const int m = m0 + quarter * 32 + row;
         if (m >= p.M || n >= p.N) continue;
         const float4 a4 = *reinterpret_cast<const float4*>(stg + row * 36 + col);
-        if (nfull && vec_ok) {
+        if (nfull && vec_ok && !(p.residual && (p.flags & VLFB_EPI_ACCUM))) {
           const float rs = p.row_scale ? p.row_scale[m] : 1.f;
           float4 o = make_float4(a4.x * p.alpha, a4.y * p.alpha, a4.z * p.alpha, a4.w * p.alpha);
           o.x = (o.x * cs.x + cb.x) * rs; o.y = (o.y * cs.y + cb.y) * rs;
           o.z = (o.z * cs.z + cb.z) * rs; o.w = (o.w * cs.w + cb.w) * rs;
           const int64_t off = tile_off + (int64_t)m * p.ldd + n;
-          if (p.residual) {
-            const float4 r4 = *reinterpret_cast<const float4*>(p.residual + off);
-            o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
-          }
+          if (p.residual) { o.x += rr[i].x; o.y += rr[i].y; o.z += rr[i].z; o.w += rr[i].w; }
           if (p.flags & VLFB_EPI_RELU) {
             o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
           }
@@ -509,8 +555,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_param
           if (p.flags & VLFB_EPI_ATOMIC) {
             atomicAdd(dst, o.x); atomicAdd(dst + 1, o.y); atomicAdd(dst + 2, o.z); atomicAdd(dst + 3, o.w);
           } else if (p.flags & VLFB_EPI_ACCUM) {
-            const float4 d4 = *reinterpret_cast<const float4*>(dst);
-            *reinterpret_cast<float4*>(dst) = make_float4(d4.x + o.x, d4.y + o.y, d4.z + o.z, d4.w + o.w);
+            *reinterpret_cast<float4*>(dst) = make_float4(rr[i].x + o.x, rr[i].y + o.y, rr[i].z + o.z, rr[i].w + o.w);
           } else {
             *reinterpret_cast<float4*>(dst) = o;
           }
@@ -550,13 +595,49 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_param
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == NPW) {
     tc_fence_after();
     tmem_dealloc(tmem, (uint32_t)(bn < 32 ? 32 : bn));
   }
 }
 
 // ---------------------------------------------------------------- host dispatch
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    const char* e = getenv("VLFB_TMA");
+    if (e && atoi(e) == 0) fn = nullptr;
+  }
+  return fn;
+}
+
+// 3-D tensor map {K, rows, batch} of a dense K-major fp32 matrix; box = {32 floats (one 128-byte swizzle
+// row), box_rows, 1}; out-of-range rows / K tail read as zeros.
+static bool make_tmap(CUtensorMap* tm, const vlfb_operand_t& op, int rows, int K, int batch, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc || op.kind != VLFB_OP_DENSE_K || K < KC || rows < box_rows) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(batch > 1 ? batch : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)op.ld * 4,
+                           (cuuint64_t)(batch > 1 ? op.batch_stride : (int64_t)rows * op.ld) * 4};
+  if ((strides[0] & 15) || (strides[1] & 15) || strides[1] == 0) return false;
+  cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(op.ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int AK, int BK>
 int launch(const vlfb_gemm_params_t& p, cudaStream_t stream) {
   Launch L;
@@ -574,6 +655,13 @@ int launch(const vlfb_gemm_params_t& p, cudaStream_t stream) {
   if (L.bn == 256 && (int64_t)ceil_div(p.M, BM) * ceil_div(p.N, 256) * zdim < 148) L.bn = 128;
   const int stage_bytes = A_TILE_BYTES + L.bn * KC * 4;
   L.stages = (L.bn == 256) ? 4 : (L.bn == 128 ? 3 : 4);
+  {
+    // short-K (memory-bound) layers: fewer stages -> less shared memory -> more resident CTAs to overlap
+    // one CTA's epilogue with another's loads
+    int kper = (p.K + p.split_k - 1) / p.split_k;
+    const int nk = (kper + KC - 1) / KC;
+    if (nk < L.stages) L.stages = nk < 2 ? 2 : nk;
+  }
   const int smem = L.stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
   static bool attr_done = false;
   if (!attr_done) {
@@ -586,7 +674,12 @@ int launch(const vlfb_gemm_params_t& p, cudaStream_t stream) {
     attr_done = true;
   }
   dim3 grid(ceil_div(p.M, BM), ceil_div(p.N, L.bn), (unsigned)zdim);
-  gemm_tc_kernel<AK, BK><<<grid, NTHREADS, smem, stream>>>(p, L);
+  alignas(64) CUtensorMap tmA, tmB;
+  memset(&tmA, 0, sizeof(tmA));
+  memset(&tmB, 0, sizeof(tmB));
+  L.tma_a = (!is_mn(AK) && AK == VLFB_OP_DENSE_K && make_tmap(&tmA, p.a, p.M, p.K, p.batch, BM)) ? 1 : 0;
+  L.tma_b = (!is_mn(BK) && BK == VLFB_OP_DENSE_K && make_tmap(&tmB, p.b, p.N, p.K, p.batch, L.bn)) ? 1 : 0;
+  gemm_tc_kernel<AK, BK><<<grid, NTHREADS, smem, stream>>>(p, L, tmA, tmB);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
