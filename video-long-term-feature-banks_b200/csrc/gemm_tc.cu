@@ -89,6 +89,16 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    default: cp_async_wait<5>(); break;
+  }
+}
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -389,6 +399,7 @@ struct Launch {
   FastDiv cdiv;  // input channels C (wgrad: n -> (tap, ci))
   FastDiv kwdiv; // kW
   int tma_a, tma_b;  // operand fetched by TMA (dense K-major 2-D tiles) instead of cp.async
+  int lag;           // cp.async groups kept in flight before a stage is published (< stages)
 };
 
 template <int AK, int BK>
@@ -447,7 +458,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_param
       if (!is_mn(AK)) ka.kend = k_end;
       if (!is_mn(BK)) kb.kend = k_end;
       const int kc0 = k_begin / KC;
-      constexpr int LAG = 2;
+      const int LAG = L.lag;
       const bool tma_a = !is_mn(AK) && L.tma_a, tma_b = !is_mn(BK) && L.tma_b;
       const bool cp_any = !(tma_a && tma_b);
       const uint32_t tma_bytes = (tma_a ? A_TILE_BYTES : 0u) + (tma_b ? b_tile_bytes : 0u);
@@ -469,7 +480,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_param
           else if (!tma_b) kb.issue(p, n0, kc0 + i, b_tile);
           cp_async_commit();
           if (i >= LAG) {
-            cp_async_wait<LAG>();
+            cp_async_wait_dyn(LAG);
             fence_proxy_async();
             mbar_arrive(full0 + 8 * ((i - LAG) % S));
           }
@@ -662,7 +673,20 @@ int launch(const vlfb_gemm_params_t& p, cudaStream_t stream) {
     const int nk = (kper + KC - 1) / KC;
     if (nk < L.stages) L.stages = nk < 2 ? 2 : nk;
   }
-  const int smem = L.stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  {
+    // tuning overrides (scripts/tune_gemm.py)
+    const char* e;
+    if ((e = getenv("VLFB_BN")) && atoi(e) > 0 && atoi(e) >= 32) { int v = atoi(e); if (p.N > v / 2 || v == 32) L.bn = v; }
+    if ((e = getenv("VLFB_STAGES")) && atoi(e) >= 2) L.stages = atoi(e);
+  }
+  int stage_bytes2 = A_TILE_BYTES + L.bn * KC * 4;
+  while (L.stages > 2 && L.stages * stage_bytes2 + 1280 > 227 * 1024) --L.stages;
+  L.lag = L.stages - 1 < 2 ? L.stages - 1 : 2;
+  {
+    const char* e = getenv("VLFB_LAG");
+    if (e && atoi(e) >= 1 && atoi(e) < L.stages) L.lag = atoi(e);
+  }
+  const int smem = L.stages * stage_bytes2 + 1024 /*align*/ + 256 /*barriers*/;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
