@@ -313,7 +313,8 @@ __device__ __forceinline__ Pos4 decode_pos_fast(uint32_t idx, const PosDiv& pd) 
 
 // ---------------------------------------------------------------- MN-major loaders
 // Tile = 32 k-rows, each `rows`*4 bytes of the m (or n) extent, stored as
-// [k-group of 4][atom of 32 elements][4 k-rows][128 B] (UMMA canonical MN-major SWIZZLE_128B_BASE32B).
+// [atom of 32 elements][32 k-rows][128 B] (UMMA canonical MN-major SWIZZLE_128B_BASE32B: LBO = 4096 between
+// atoms, SBO = 512 between groups of 4 k-rows).
 template <int KIND>
 struct MNLoader {
   const float* base;
@@ -341,7 +342,6 @@ struct MNLoader {
     const vlfb_conv_geom_t& g = p.g;
     const int cpr = rows >> 2;            // 16-byte chunks per k-row (8, 16, 32 or 64)
     const int lcpr = 31 - __clz(cpr);
-    const int natoms = rows >> 5;
     const int total = KC * cpr;
     int info_a = 0, info_b = 0;           // per-lane k-row: (n*T + t0) and (h0 << 16 | w0 & 0xffff)
     if (KIND != VLFB_OP_DENSE_MN) {
@@ -383,9 +383,10 @@ struct MNLoader {
       // SWIZZLE_128B_BASE32B (the MN-major layout 32-bit operands need; plain SWIZZLE_128B returns
       // zeros for tf32 -- measured, profiles/r01_gemm_layout_diag.txt): atoms of 4 k-rows x 128 B,
       // 32-byte units XOR (k & 3).
+      // atom-major tile [atom of 32 elements][32 k-rows][128 B]: the same image a TMA box {32 elems, 32 rows}
+      // with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B produces
       const int r = kk & 3, cc8 = c & 7;
-      const uint32_t dst = tile + (kk >> 2) * (natoms * 512) + (c >> 3) * 512 + r * 128 +
-                           ((((cc8 >> 1) ^ r) << 5) | ((cc8 & 1) << 4));
+      const uint32_t dst = tile + (c >> 3) * 4096 + kk * 128 + ((((cc8 >> 1) ^ r) << 5) | ((cc8 & 1) << 4));
       cp_async16(dst, src, ok);
     }
   }
@@ -441,6 +442,20 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_param
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == NPW) tmem_alloc(tptr_addr, (uint32_t)(bn < 32 ? 32 : bn));
+  if (warp < NPW && ((is_mn(AK) && L.tma_a) || (is_mn(BK) && L.tma_b))) {
+    // TMA only fetches the 32-element atoms that intersect the matrix; clear the rest of every stage once
+    const int av = (is_mn(AK) && L.tma_a) ? min(BM / 32, (p.M - m0 + 31) / 32) : BM / 32;
+    const int bv = (is_mn(BK) && L.tma_b) ? min(bn / 32, (p.N - n0 + 31) / 32) : bn / 32;
+    float4* base4 = reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)));
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int st = 0; st < S; ++st) {
+      float4* a4 = base4 + (size_t)st * (stage_bytes / 16);
+      for (int q = av * 256 + tid; q < (BM / 32) * 256; q += NPROD) a4[q] = z4;
+      float4* b4 = a4 + A_TILE_BYTES / 16;
+      for (int q = bv * 256 + tid; q < (bn / 32) * 256; q += NPROD) b4[q] = z4;
+    }
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -459,9 +474,13 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_param
       if (!is_mn(BK)) kb.kend = k_end;
       const int kc0 = k_begin / KC;
       const int LAG = L.lag;
-      const bool tma_a = !is_mn(AK) && L.tma_a, tma_b = !is_mn(BK) && L.tma_b;
+      const bool tma_a = L.tma_a != 0, tma_b = L.tma_b != 0;
       const bool cp_any = !(tma_a && tma_b);
-      const uint32_t tma_bytes = (tma_a ? A_TILE_BYTES : 0u) + (tma_b ? b_tile_bytes : 0u);
+      // MN-major operands: one {32 elements x 32 k-rows} box per atom that intersects the matrix
+      const int a_atoms_v = is_mn(AK) ? min(BM / 32, (p.M - m0 + 31) / 32) : 0;
+      const int b_atoms_v = is_mn(BK) ? min(bn / 32, (p.N - n0 + 31) / 32) : 0;
+      const uint32_t tma_bytes = (tma_a ? (is_mn(AK) ? a_atoms_v * 4096u : (uint32_t)A_TILE_BYTES) : 0u) +
+                                 (tma_b ? (is_mn(BK) ? b_atoms_v * 4096u : b_tile_bytes) : 0u);
       if (cp_any || tid == 0) {
         for (int i = 0; i < nk; ++i) {
           const int s = i % S;
@@ -470,14 +489,32 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_param
           const uint32_t b_tile = a_tile + A_TILE_BYTES;
           if (tid == 0 && tma_bytes) {
             mbar_expect_tx(full0 + 8 * s, tma_bytes);
-            if (tma_a) tma_load_3d(a_tile, &tmA, (kc0 + i) * KC, m0, batch, full0 + 8 * s);
-            if (tma_b) tma_load_3d(b_tile, &tmB, (kc0 + i) * KC, n0, batch, full0 + 8 * s);
+            if (tma_a) {
+              if (is_mn(AK)) {
+                for (int a = 0; a < a_atoms_v; ++a)
+                  tma_load_3d(a_tile + a * 4096, &tmA, m0 + a * 32, k_begin + i * KC, batch, full0 + 8 * s);
+              } else {
+                tma_load_3d(a_tile, &tmA, (kc0 + i) * KC, m0, batch, full0 + 8 * s);
+              }
+            }
+            if (tma_b) {
+              if (is_mn(BK)) {
+                for (int a = 0; a < b_atoms_v; ++a)
+                  tma_load_3d(b_tile + a * 4096, &tmB, n0 + a * 32, k_begin + i * KC, batch, full0 + 8 * s);
+              } else {
+                tma_load_3d(b_tile, &tmB, (kc0 + i) * KC, n0, batch, full0 + 8 * s);
+              }
+            }
           }
           if (!cp_any) continue;
-          if (is_mn(AK)) ma.issue(p, L.out, L.cdiv, L.kwdiv, k_begin + i * KC, k_end, a_tile);
-          else if (!tma_a) ka.issue(p, m0, kc0 + i, a_tile);
-          if (is_mn(BK)) mb.issue(p, L.out, L.cdiv, L.kwdiv, k_begin + i * KC, k_end, b_tile);
-          else if (!tma_b) kb.issue(p, n0, kc0 + i, b_tile);
+          if (!tma_a) {
+            if (is_mn(AK)) ma.issue(p, L.out, L.cdiv, L.kwdiv, k_begin + i * KC, k_end, a_tile);
+            else ka.issue(p, m0, kc0 + i, a_tile);
+          }
+          if (!tma_b) {
+            if (is_mn(BK)) mb.issue(p, L.out, L.cdiv, L.kwdiv, k_begin + i * KC, k_end, b_tile);
+            else kb.issue(p, n0, kc0 + i, b_tile);
+          }
           cp_async_commit();
           if (i >= LAG) {
             cp_async_wait_dyn(LAG);
@@ -583,7 +620,6 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_param
     // ============================ MMA ISSUER ===========================
     if ((tid & 31) == 0) {
       const uint32_t idesc = make_idesc(bn, is_mn(AK) ? 1 : 0, is_mn(BK) ? 1 : 0);
-      const uint32_t a_atoms = BM / 32, b_atoms = bn / 32;
       for (int i = 0; i < nk; ++i) {
         const int s = i % S;
         mbar_wait(full0 + 8 * s, (i / S) & 1);
@@ -594,9 +630,9 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_param
         for (int j = 0; j < KC / 8; ++j) {   // UMMA K = 8 for tf32
           uint64_t da, db;
           if (!is_mn(AK)) da = make_desc(a_tile + j * 32, 16, 1024);
-          else da = make_desc(a_tile + 2 * j * (a_atoms * 512), 512, a_atoms * 512, 1);
+          else da = make_desc(a_tile + j * 1024, 4096, 512, 1);
           if (!is_mn(BK)) db = make_desc(b_tile + j * 32, 16, 1024);
-          else db = make_desc(b_tile + 2 * j * (b_atoms * 512), 512, b_atoms * 512, 1);
+          else db = make_desc(b_tile + j * 1024, 4096, 512, 1);
           umma_tf32(tmem, da, db, idesc, (i | j) ? 1u : 0u);
         }
         umma_commit(empty0 + 8 * s);       // frees the smem stage when these MMAs retire
@@ -646,6 +682,21 @@ static bool make_tmap(CUtensorMap* tm, const vlfb_operand_t& op, int rows, int K
   cuuint32_t estr[3] = {1, 1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(op.ptr), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Dense MN-major fp32 matrix [K rows][extent] (+batch): box = {32 elements, 32 k-rows, 1} written in the
+// SWIZZLE_128B_ATOM_32B pattern = one UMMA MN-major atom column (4 KB) per copy.
+static bool make_tmap_mn(CUtensorMap* tm, const vlfb_operand_t& op, int extent, int K, int batch) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc || op.kind != VLFB_OP_DENSE_MN || K < KC || extent < 32) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)extent, (cuuint64_t)K, (cuuint64_t)(batch > 1 ? batch : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)op.ld * 4, (cuuint64_t)(batch > 1 ? op.batch_stride : (int64_t)K * op.ld) * 4};
+  if ((strides[0] & 15) || (strides[1] & 15) || strides[1] == 0) return false;
+  cuuint32_t box[3] = {32, (cuuint32_t)KC, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(op.ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -701,8 +752,11 @@ int launch(const vlfb_gemm_params_t& p, cudaStream_t stream) {
   alignas(64) CUtensorMap tmA, tmB;
   memset(&tmA, 0, sizeof(tmA));
   memset(&tmB, 0, sizeof(tmB));
-  L.tma_a = (!is_mn(AK) && AK == VLFB_OP_DENSE_K && make_tmap(&tmA, p.a, p.M, p.K, p.batch, BM)) ? 1 : 0;
-  L.tma_b = (!is_mn(BK) && BK == VLFB_OP_DENSE_K && make_tmap(&tmB, p.b, p.N, p.K, p.batch, L.bn)) ? 1 : 0;
+  const bool mn_tma = !(getenv("VLFB_TMA_MN") && atoi(getenv("VLFB_TMA_MN")) == 0);
+  L.tma_a = (AK == VLFB_OP_DENSE_K && make_tmap(&tmA, p.a, p.M, p.K, p.batch, BM)) ||
+            (AK == VLFB_OP_DENSE_MN && mn_tma && make_tmap_mn(&tmA, p.a, p.M, p.K, p.batch)) ? 1 : 0;
+  L.tma_b = (BK == VLFB_OP_DENSE_K && make_tmap(&tmB, p.b, p.N, p.K, p.batch, L.bn)) ||
+            (BK == VLFB_OP_DENSE_MN && mn_tma && make_tmap_mn(&tmB, p.b, p.N, p.K, p.batch)) ? 1 : 0;
   gemm_tc_kernel<AK, BK><<<grid, NTHREADS, smem, stream>>>(p, L, tmA, tmB);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
