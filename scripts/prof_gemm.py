@@ -1,6 +1,6 @@
 """Runs a handful of representative hot-path GEMM launches (for `ncu --set full -k regex:gemm_tc`).
 Order of launches: [0,1] res5 2b conv fwd (3x3 dil 2, M=6272 N=512 K=4608), [2,3] res2 2c fwd (+residual+relu,
-M=200704 N=256 K=64), [4,5] res4 2b wgrad (M=256 N=2304 K=6272), [6,7] res3 2a dgrad pointwise."""
+M=200704 N=256 K=64), [4,5] res4 2b wgrad (M=256 N=2304 K=6272), [6,7] res3 2a dgrad pointwise, [8,9] res2 2b 3x3 fwd (M=200704 N=64 K=576)."""
 import os
 import sys
 
@@ -40,6 +40,9 @@ def main():
     dx = torch.empty_like(x4)
     for _ in range(reps):
         K.conv_dgrad(y4, wt, dx, g4)
+    g5, x5, w5, y5, s5, b5, _ = conv_case(2, 32, 56, 56, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), (1, 1, 1))
+    for _ in range(reps):
+        K.conv_fwd(x5, w5, y5, g5, scale=s5, bias=b5, relu=True, tf32_out=True)
     torch.cuda.synchronize()
     print('done')
 

@@ -28,6 +28,7 @@ SHAPES = {
     'res3_2a 3x1x1 512->128': (2, 16, 28, 28, 512, 128, (3, 1, 1), (1, 1, 1), (1, 0, 0), (1, 1, 1)),
     'res2_2c 1x1 64->256': (2, 32, 56, 56, 64, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0), (1, 1, 1)),
     'res2_2b 3x3 64->64': (2, 32, 56, 56, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), (1, 1, 1)),
+    'res2_2a 3x1x1 256->64': (2, 32, 56, 56, 256, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), (1, 1, 1)),
 }
 
 
@@ -44,17 +45,15 @@ def timeit(fn, reps=5):
 
 
 def main():
-    configs = [dict()] + [dict(VLFB_TMA='0')] + [dict(VLFB_STAGES=str(s), VLFB_LAG=str(l)) for s, l in
-                                                   ((3, 1), (4, 2), (4, 3), (5, 3), (6, 4))] + \
-              [dict(VLFB_BN='128', VLFB_STAGES='6', VLFB_LAG='4'), dict(VLFB_BN='256', VLFB_STAGES='4', VLFB_LAG='3'),
-               dict(VLFB_BN='64', VLFB_STAGES='6', VLFB_LAG='4')]
+    configs = [dict(), dict(VLFB_FENCE='1'), dict(VLFB_FENCE='1', VLFB_LAG='3'), dict(VLFB_FENCE='1', VLFB_LAG='4'),
+               dict(VLFB_LAG='1'), dict(VLFB_LAG='3'), dict(VLFB_TMA='0'), dict(VLFB_TMA='0', VLFB_FENCE='1', VLFB_LAG='3')]
     for name, shp in SHAPES.items():
         g, x, w, y, wt = make(*shp)
         dw = torch.zeros_like(w)
         dx = torch.empty_like(x)
         flops = 2.0 * g.N * g.To * g.Ho * g.Wo * g.Co * g.C * g.kT * g.kH * g.kW
         for cfg in configs:
-            for k in ('VLFB_BN', 'VLFB_STAGES', 'VLFB_LAG', 'VLFB_TMA'):
+            for k in ('VLFB_BN', 'VLFB_STAGES', 'VLFB_LAG', 'VLFB_TMA', 'VLFB_FENCE'):
                 os.environ.pop(k, None)
             os.environ.update(cfg)
             tf = timeit(lambda: K.conv_fwd(x, w, y, g, relu=True, tf32_out=True))

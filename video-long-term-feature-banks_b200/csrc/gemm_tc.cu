@@ -2,16 +2,19 @@
 //
 //   D[m,n] = epi( sum_k A[m,k] * B[n,k] ),  fp32 storage, kind::tf32 MMA, fp32 accumulate in TMEM.
 //
-// One CTA = one 128 x BN output tile (UMMA M=128, N=BN, cta_group::1).
-//   warps 0-3 (128 threads): PRODUCERS -- im2col-free gather of the A/B K-chunks (32 fp32 = one
-//                            128-byte swizzle row) straight from NDHWC tensors into the UMMA
-//                            canonical SWIZZLE_128B shared-memory layout with 16-byte cp.async
-//                            (zero-fill = conv padding); afterwards the same warps are the
-//                            EPILOGUE (tcgen05.ld TMEM -> registers -> fused affine/residual/ReLU
-//                            -> 128-bit global stores).
-//   warp 4: TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit releases the
-//           smem stage back to the producers and finally signals the epilogue.
-// Synchronisation is mbarrier-only inside the main loop (full[s] / empty[s] / tmem_full).
+// Persistent kernel: grid = min(#tiles, #SMs), one CTA per SM walks a static sequence of 128 x BN output
+// tiles (UMMA M=128, N=BN, cta_group::1), 416 threads:
+//   warps 0-7  PRODUCERS -- im2col-free gather of the A/B K-chunks (32 fp32 = one 128-byte swizzle row)
+//              straight from NDHWC tensors into the UMMA canonical swizzled shared-memory layouts with
+//              16-byte cp.async (zero-fill = conv padding); dense operands are fetched by TMA instead
+//              (cp.async.bulk.tensor, SWIZZLE_128B for K-major, SWIZZLE_128B_ATOM_32B for MN-major);
+//   warp 8     TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit releases each smem
+//              stage back to the producers and hands finished accumulators to the epilogue;
+//   warps 9-12 EPILOGUE -- tcgen05.ld TMEM -> registers -> smem transpose -> fused affine / residual /
+//              ReLU / TF32 rounding -> coalesced 128-bit global stores (or atomics for split-K).
+// The smem ring (full[s]/empty[s] mbarriers) runs continuously across tiles and the accumulator is double
+// buffered in TMEM (tmem_full[a]/tmem_empty[a]), so the epilogue of one tile overlaps the loads and MMAs
+// of the next.
 //
 // Operand kinds are described in include/vlfb.h; their element-level definition is
 // operand_elem() in common.cuh, which the SIMT engine evaluates literally and the tests
@@ -32,7 +35,9 @@ constexpr int NPROD = 256;     // producer / epilogue threads: 8 warps = 2 per s
                                // producer warp per scheduler 'wait'+'selected' stalls dominated, no unit >14% busy)
 constexpr int NPW = NPROD / 32;
 constexpr int RSTEP = NPROD / 8;   // rows covered by one pass of the K-major loaders
-constexpr int NTHREADS = NPROD + 32;  // + MMA warp
+constexpr int NEPI = 128;          // 4 epilogue warps (one per TMEM lane quarter)
+constexpr int NTHREADS = NPROD + 32 + NEPI;  // producers + MMA warp + epilogue
+constexpr int EPI_STAGE_BYTES = 4 * 32 * 36 * 4;
 constexpr int A_TILE_BYTES = BM * KC * 4;  // 16 KB
 constexpr int MAX_STAGES = 8;
 
@@ -57,15 +62,20 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
-// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.  The clock is only read
+// every 4096 polls so that the spin loop stays 3 instructions long (try_wait suspends in hardware).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  long long t0 = 0;
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 6000000000LL) {
-      printf("vlfb gemm_tc: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x);
-      __trap();
+    if ((++spins & 0xFFFu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) {
+        printf("vlfb gemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+        __trap();
+      }
     }
   }
 }
@@ -166,121 +176,6 @@ __host__ __device__ inline uint32_t make_idesc(int bn, int a_mn_major, int b_mn_
 
 __host__ __device__ constexpr bool is_mn(int kind) { return kind == VLFB_OP_DENSE_MN || kind == VLFB_OP_CONV_MN || kind == VLFB_OP_STEM_MN; }
 
-// ---------------------------------------------------------------- K-major loaders
-// Tile = `rows` rows x 128 B.  Thread t copies the 16-byte chunk (t & 7) of rows (t >> 3) + RSTEP j.
-template <int KIND, int MAXR>
-struct KLoader {
-  const float* base;
-  int64_t ld;
-  int nrow;          // rows of this tile handled per thread (rows / 16)
-  int kend;          // DENSE_K: K limit for the 16-byte tail predicate
-  // conv state per owned row
-  int s_n[MAXR], s_t[MAXR], s_hw[MAXR];
-  uint32_t rowmask;  // DENSE_K: bit j set when row j is inside the matrix
-
-  __device__ __forceinline__ void init(const vlfb_gemm_params_t& p, const vlfb_operand_t& op, int row0, int rows,
-                                       int limit, int batch) {
-    const int tid = threadIdx.x;
-    nrow = rows / RSTEP;
-    base = op.ptr;
-    ld = op.ld;
-    kend = p.K;
-    rowmask = 0;
-    const vlfb_conv_geom_t& g = p.g;
-    if (KIND == VLFB_OP_DENSE_K) base += (int64_t)batch * op.batch_stride;
-#pragma unroll
-    for (int j = 0; j < MAXR; ++j) {
-      if (j >= nrow) break;
-      const int row = row0 + (tid >> 3) + RSTEP * j;
-      const bool ok = row < limit;
-      if (KIND == VLFB_OP_DENSE_K) {
-        if (ok) rowmask |= 1u << j;
-      } else if (KIND == VLFB_OP_CONV_K || KIND == VLFB_OP_STEM_K) {
-        Pos4 o = decode_pos(ok ? row : 0, g.To, g.Ho, g.Wo);
-        s_n[j] = o.n * g.T;
-        s_t[j] = ok ? o.t * g.sT - g.pT : -100000;
-        s_hw[j] = ((o.h * g.sH - g.pH) << 16) | ((o.w * g.sW - g.pW) & 0xFFFF);
-      } else {  // DGRAD_K: rows are input positions
-        Pos4 i = decode_pos(ok ? row : 0, g.T, g.H, g.W);
-        s_n[j] = i.n * g.To;
-        s_t[j] = ok ? i.t + g.pT : -100000;
-        s_hw[j] = ((i.h + g.pH) << 16) | ((i.w + g.pW) & 0xFFFF);
-      }
-    }
-  }
-
-  // Issue the cp.asyncs of K chunk `kc` (global chunk index) into the tile at smem address `tile`.
-  __device__ __forceinline__ void issue(const vlfb_gemm_params_t& p, int row0, int kc, uint32_t tile) const {
-    const int tid = threadIdx.x;
-    const int c = tid & 7;
-    const int r0 = tid >> 3;
-    const vlfb_conv_geom_t& g = p.g;
-    if (KIND == VLFB_OP_DENSE_K) {
-      const int k = kc * KC + c * 4;
-      const bool kok = k < kend;
-#pragma unroll
-      for (int j = 0; j < MAXR; ++j) {
-        if (j >= nrow) break;
-        const int r = r0 + RSTEP * j;
-        const bool ok = kok && ((rowmask >> j) & 1u);
-        const float* src = ok ? base + (int64_t)(row0 + r) * ld + k : base;
-        cp_async16(tile + r * 128 + ((c ^ (r & 7)) << 4), src, ok);
-      }
-    } else if (KIND == VLFB_OP_CONV_K) {
-      const int cpt = g.C / KC;
-      const int tap = kc / cpt;
-      const int c0 = (kc - tap * cpt) * KC + c * 4;
-      int kt, kh, kw;
-      decode_tap(tap, g.kH, g.kW, kt, kh, kw);
-      const int dt = kt * g.dT, dh = kh * g.dH, dw = kw * g.dW;
-#pragma unroll
-      for (int j = 0; j < MAXR; ++j) {
-        if (j >= nrow) break;
-        const int r = r0 + RSTEP * j;
-        const int ti = s_t[j] + dt, hi = (s_hw[j] >> 16) + dh, wi = (int)(short)(s_hw[j] & 0xFFFF) + dw;
-        const bool ok = (unsigned)ti < (unsigned)g.T && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
-        const int64_t pos = ((int64_t)(s_n[j] + ti) * g.H + hi) * g.W + wi;
-        const float* src = ok ? base + pos * g.C + c0 : base;
-        cp_async16(tile + r * 128 + ((c ^ (r & 7)) << 4), src, ok);
-      }
-    } else if (KIND == VLFB_OP_STEM_K) {
-      const int kt = kc / g.kH, kh = kc - kt * g.kH;   // chunk = one (kt,kh) row of 8 pixels x 4 ch
-#pragma unroll
-      for (int j = 0; j < MAXR; ++j) {
-        if (j >= nrow) break;
-        const int r = r0 + RSTEP * j;
-        const int ti = s_t[j] + kt, hi = (s_hw[j] >> 16) + kh, wi = (int)(short)(s_hw[j] & 0xFFFF) + c;
-        const bool ok = (unsigned)ti < (unsigned)g.T && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
-        const int64_t pos = ((int64_t)(s_n[j] + ti) * g.H + hi) * g.W + wi;
-        const float* src = ok ? base + pos * 4 : base;
-        cp_async16(tile + r * 128 + ((c ^ (r & 7)) << 4), src, ok);
-      }
-    } else {  // DGRAD_K
-      const int cpt = g.Co / KC;
-      const int tap = kc / cpt;
-      const int c0 = (kc - tap * cpt) * KC + c * 4;
-      int kt, kh, kw;
-      decode_tap(tap, g.kH, g.kW, kt, kh, kw);
-      const int dt = kt * g.dT, dh = kh * g.dH, dw = kw * g.dW;
-#pragma unroll
-      for (int j = 0; j < MAXR; ++j) {
-        if (j >= nrow) break;
-        const int r = r0 + RSTEP * j;
-        const int a = s_t[j] - dt, b = (s_hw[j] >> 16) - dh, cc = (int)(short)(s_hw[j] & 0xFFFF) - dw;
-        bool ok = a >= 0 && b >= 0 && cc >= 0;
-        int to = a, ho = b, wo = cc;
-        if (g.sT != 1) { ok = ok && (a % g.sT == 0); to = a / g.sT; }
-        if (g.sH != 1) { ok = ok && (b % g.sH == 0); ho = b / g.sH; }
-        if (g.sW != 1) { ok = ok && (cc % g.sW == 0); wo = cc / g.sW; }
-        ok = ok && to < g.To && ho < g.Ho && wo < g.Wo;
-        const int64_t pos = ((int64_t)(s_n[j] + to) * g.Ho + ho) * g.Wo + wo;
-        const float* src = ok ? base + pos * g.Co + c0 : base;
-        cp_async16(tile + r * 128 + ((c ^ (r & 7)) << 4), src, ok);
-      }
-    }
-  }
-};
-
 // ---------------------------------------------------------------- fast integer division
 // q = x / d for 0 <= x < 2^31 with a precomputed multiplier (the gather loaders decode an output
 // position per 16-byte copy; 64-bit hardware division there cost more than the copy itself).
@@ -311,18 +206,158 @@ __device__ __forceinline__ Pos4 decode_pos_fast(uint32_t idx, const PosDiv& pd) 
   return p;
 }
 
+// ---------------------------------------------------------------- K-major loaders
+// Tile = `rows` rows x 128 B.  Thread t copies the 16-byte chunk (t & 7) of rows (t >> 3) + RSTEP j.
+template <int KIND, int MAXR>
+struct KLoader {
+  const float* base;
+  int64_t ld;
+  int nrow;          // rows of this tile handled per thread (rows / RSTEP)
+  int kend;          // DENSE_K: K limit for the 16-byte tail predicate
+  int row0;
+  // per owned row: decoded position (conv kinds) and the swizzled shared-memory offset of its 16-byte chunk
+  int s_n[MAXR], s_t[MAXR], s_hw[MAXR];
+  uint32_t dst[MAXR];
+  uint32_t rowmask;  // DENSE_K: bit j set when row j is inside the matrix
+  // Filter-tap cursor.  Chunks are issued in order, so the tap advances incrementally (no division per
+  // chunk) and the gathered element offset / validity of every owned row is recomputed only when the
+  // tap changes (ncu r01: the per-chunk divisions and 64-bit address math made the producers
+  // instruction-bound at ~330 instructions per chunk per warp).
+  int cpt, tc, kt, kh, kw;
+  int off[MAXR];
+  uint32_t okmask;
+
+  __device__ __forceinline__ void init(const vlfb_gemm_params_t& p, const vlfb_operand_t& op, int row0_, int rows,
+                                       int limit, int batch, const PosDiv& pdo, const PosDiv& pdi, int kc_first) {
+    const int tid = threadIdx.x;
+    const int c = tid & 7;
+    nrow = rows / RSTEP;
+    base = op.ptr;
+    ld = op.ld;
+    kend = p.K;
+    rowmask = 0;
+    row0 = row0_;
+    const vlfb_conv_geom_t& g = p.g;
+    if (KIND == VLFB_OP_DENSE_K) base += (int64_t)batch * op.batch_stride;
+#pragma unroll
+    for (int j = 0; j < MAXR; ++j) {
+      if (j >= nrow) break;
+      const int r = (tid >> 3) + RSTEP * j;
+      const int row = row0 + r;
+      const bool ok = row < limit;
+      dst[j] = (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
+      if (KIND == VLFB_OP_DENSE_K) {
+        if (ok) rowmask |= 1u << j;
+      } else if (KIND == VLFB_OP_CONV_K || KIND == VLFB_OP_STEM_K) {
+        Pos4 o = decode_pos_fast(ok ? (uint32_t)row : 0u, pdo);
+        s_n[j] = o.n * g.T;
+        s_t[j] = ok ? o.t * g.sT - g.pT : -100000;
+        s_hw[j] = ((o.h * g.sH - g.pH) << 16) | ((o.w * g.sW - g.pW) & 0xFFFF);
+      } else {  // DGRAD_K: rows are input positions
+        Pos4 i = decode_pos_fast(ok ? (uint32_t)row : 0u, pdi);
+        s_n[j] = i.n * g.To;
+        s_t[j] = ok ? i.t + g.pT : -100000;
+        s_hw[j] = ((i.h + g.pH) << 16) | ((i.w + g.pW) & 0xFFFF);
+      }
+    }
+    if (KIND == VLFB_OP_CONV_K || KIND == VLFB_OP_DGRAD_K) {
+      cpt = (KIND == VLFB_OP_CONV_K ? g.C : g.Co) / KC;
+      const int tap = kc_first / cpt;              // one division per tile
+      tc = kc_first - tap * cpt;
+      decode_tap(tap, g.kH, g.kW, kt, kh, kw);
+      compute_tap(g);
+    } else if (KIND == VLFB_OP_STEM_K) {
+      kt = kc_first / g.kH;
+      kh = kc_first - kt * g.kH;
+    }
+  }
+
+  __device__ __forceinline__ void compute_tap(const vlfb_conv_geom_t& g) {
+    okmask = 0;
+    const int dt = kt * g.dT, dh = kh * g.dH, dw = kw * g.dW;
+#pragma unroll
+    for (int j = 0; j < MAXR; ++j) {
+      if (j >= nrow) break;
+      if (KIND == VLFB_OP_CONV_K) {
+        const int ti = s_t[j] + dt, hi = (s_hw[j] >> 16) + dh, wi = (int)(short)(s_hw[j] & 0xFFFF) + dw;
+        const bool ok = (unsigned)ti < (unsigned)g.T && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
+        off[j] = ok ? (((s_n[j] + ti) * g.H + hi) * g.W + wi) * g.C : 0;
+        if (ok) okmask |= 1u << j;
+      } else {  // DGRAD_K
+        const int a = s_t[j] - dt, b = (s_hw[j] >> 16) - dh, cc = (int)(short)(s_hw[j] & 0xFFFF) - dw;
+        bool ok = a >= 0 && b >= 0 && cc >= 0;
+        int to = a, ho = b, wo = cc;
+        if (g.sT != 1) { ok = ok && (a % g.sT == 0); to = a / g.sT; }
+        if (g.sH != 1) { ok = ok && (b % g.sH == 0); ho = b / g.sH; }
+        if (g.sW != 1) { ok = ok && (cc % g.sW == 0); wo = cc / g.sW; }
+        ok = ok && to < g.To && ho < g.Ho && wo < g.Wo;
+        off[j] = ok ? (((s_n[j] + to) * g.Ho + ho) * g.Wo + wo) * g.Co : 0;
+        if (ok) okmask |= 1u << j;
+      }
+    }
+  }
+
+  // Issue the cp.asyncs of the NEXT K chunk (`kc` = its global index, used by DENSE_K only) into `tile`.
+  __device__ __forceinline__ void issue(const vlfb_gemm_params_t& p, int kc, uint32_t tile) {
+    const int c = threadIdx.x & 7;
+    const vlfb_conv_geom_t& g = p.g;
+    if (KIND == VLFB_OP_DENSE_K) {
+      const int k = kc * KC + c * 4;
+      const bool kok = k < kend;
+      const int r0 = threadIdx.x >> 3;
+#pragma unroll
+      for (int j = 0; j < MAXR; ++j) {
+        if (j >= nrow) break;
+        const bool ok = kok && ((rowmask >> j) & 1u);
+        const float* src = ok ? base + (int64_t)(row0 + r0 + RSTEP * j) * ld + k : base;
+        cp_async16(tile + dst[j], src, ok);
+      }
+    } else if (KIND == VLFB_OP_CONV_K || KIND == VLFB_OP_DGRAD_K) {
+      const int c0 = tc * KC + c * 4;
+#pragma unroll
+      for (int j = 0; j < MAXR; ++j) {
+        if (j >= nrow) break;
+        const bool ok = (okmask >> j) & 1u;
+        cp_async16(tile + dst[j], base + (off[j] + c0), ok);
+      }
+      if (++tc == cpt) {          // next tap
+        tc = 0;
+        if (++kw == g.kW) { kw = 0; if (++kh == g.kH) { kh = 0; ++kt; } }
+        compute_tap(g);
+      }
+    } else {  // STEM_K: chunk = one (kt,kh) filter row of 8 pixels x 4 channels; this thread's pixel = c
+#pragma unroll
+      for (int j = 0; j < MAXR; ++j) {
+        if (j >= nrow) break;
+        const int ti = s_t[j] + kt, hi = (s_hw[j] >> 16) + kh, wi = (int)(short)(s_hw[j] & 0xFFFF) + c;
+        const bool ok = (unsigned)ti < (unsigned)g.T && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
+        const int o = ok ? (((s_n[j] + ti) * g.H + hi) * g.W + wi) * 4 : 0;
+        cp_async16(tile + dst[j], base + o, ok);
+      }
+      if (++kh == g.kH) { kh = 0; ++kt; }
+    }
+  }
+};
+
 // ---------------------------------------------------------------- MN-major loaders
 // Tile = 32 k-rows, each `rows`*4 bytes of the m (or n) extent, stored as
 // [atom of 32 elements][32 k-rows][128 B] (UMMA canonical MN-major SWIZZLE_128B_BASE32B: LBO = 4096 between
 // atoms, SBO = 512 between groups of 4 k-rows).
 template <int KIND>
 struct MNLoader {
+  static constexpr int MAXS = (32 * 64) / NPROD;   // copies per thread per chunk at the widest tile (256 cols)
   const float* base;
   int64_t ld;
-  int rows, limit, row0, tapz;
+  int rows, limit, row0, tapz, nslot, lcpr;
+  // per copy slot (fixed for the whole tile): shared-memory offset, k-row within the chunk, and for the conv
+  // kinds the filter-tap offsets / channel of the 16-byte chunk -- nothing of this depends on the K chunk
+  uint32_t dst[MAXS];
+  int s_kk[MAXS], s_mn[MAXS], s_hw[MAXS], s_ci[MAXS];
+  uint32_t okmask;
 
   __device__ __forceinline__ void init(const vlfb_gemm_params_t& p, const vlfb_operand_t& op, int row0_, int rows_,
-                                       int limit_, int batch, int tap) {
+                                       int limit_, int batch, int tap, const FastDiv& cdiv, const FastDiv& kwdiv) {
+    const vlfb_conv_geom_t& g = p.g;
     base = op.ptr;
     if (KIND == VLFB_OP_DENSE_MN) base += (int64_t)batch * op.batch_stride;
     ld = op.ld;
@@ -330,64 +365,71 @@ struct MNLoader {
     limit = limit_;
     row0 = row0_;
     tapz = tap;
+    const int cpr = rows >> 2;            // 16-byte chunks per k-row (8, 16, 32 or 64)
+    lcpr = 31 - __clz(cpr);
+    nslot = (KC * cpr) / NPROD;
+    okmask = 0;
+#pragma unroll
+    for (int j = 0; j < MAXS; ++j) {
+      if (j >= nslot) break;
+      const int idx = threadIdx.x + NPROD * j;
+      const int kk = idx >> lcpr;
+      const int c = idx & (cpr - 1);
+      const int mn = row0 + c * 4;
+      s_kk[j] = kk;
+      s_mn[j] = mn;
+      if (mn < limit) okmask |= 1u << j;
+      // atom-major tile [atom of 32 elements][32 k-rows][128 B] in the SWIZZLE_128B_BASE32B pattern (32-byte
+      // units XOR (k & 3)); plain SWIZZLE_128B returns zeros for tf32 MN-major operands (measured,
+      // profiles/r01_gemm_layout_diag.txt).  Same image as a TMA box with SWIZZLE_128B_ATOM_32B.
+      const int r = kk & 3, cc8 = c & 7;
+      dst[j] = (uint32_t)((c >> 3) * 4096 + kk * 128 + ((((cc8 >> 1) ^ r) << 5) | ((cc8 & 1) << 4)));
+      if (KIND == VLFB_OP_CONV_MN) {
+        uint32_t tap_hw, cc, qh, qw;
+        fd_divmod((uint32_t)mn, cdiv, tap_hw, cc);     // n = (kh*kW + kw) * C + ci
+        fd_divmod(tap_hw, kwdiv, qh, qw);
+        s_hw[j] = (((int)qh * g.dH) << 16) | (((int)qw * g.dW) & 0xFFFF);
+        s_ci[j] = (int)cc;
+      } else if (KIND == VLFB_OP_STEM_MN) {            // n = kh*32 + px*4 (+ch)
+        s_hw[j] = ((mn >> 5) << 16) | ((mn & 31) >> 2);
+        s_ci[j] = 0;
+      }
+    }
   }
 
   // k0 = first k of this chunk, kend = exclusive k limit of this CTA's K range.
-  // Conv kinds (wgrad B operand): the N extent spans ALL (kh,kw) taps of one kt slice,
-  // n = (kh*kW + kw)*C + ci, so one pass over dY feeds up to 256 (tap, ci) columns.  Each lane
-  // decodes ONE of the 32 k-rows (output positions) of the chunk; the copy loop fetches the row
-  // info it needs with warp shuffles, so there is one position decode per thread per chunk.
-  __device__ __forceinline__ void issue(const vlfb_gemm_params_t& p, const PosDiv& pd, const FastDiv& cdiv,
-                                        const FastDiv& kwdiv, int k0, int kend, uint32_t tile) const {
+  // Conv kinds (wgrad B operand): the N extent spans ALL (kh,kw) taps of one kt slice, so one pass over dY
+  // feeds up to 256 (tap, ci) columns.  Each lane decodes ONE of the 32 k-rows (output positions) of the
+  // chunk; the copy slots fetch the row info they need with warp shuffles.
+  __device__ __forceinline__ void issue(const vlfb_gemm_params_t& p, const PosDiv& pd, int k0, int kend, uint32_t tile) const {
     const vlfb_conv_geom_t& g = p.g;
-    const int cpr = rows >> 2;            // 16-byte chunks per k-row (8, 16, 32 or 64)
-    const int lcpr = 31 - __clz(cpr);
-    const int total = KC * cpr;
     int info_a = 0, info_b = 0;           // per-lane k-row: (n*T + t0) and (h0 << 16 | w0 & 0xffff)
     if (KIND != VLFB_OP_DENSE_MN) {
       const int k = k0 + (threadIdx.x & 31);
       const bool okr = k < kend;
       const Pos4 o = decode_pos_fast(okr ? (uint32_t)k : 0u, pd);
-      const int kt = tapz;                // z slice = temporal tap
-      const int t0 = o.t * g.sT - g.pT + kt * g.dT;
+      const int t0 = o.t * g.sT - g.pT + tapz * g.dT;          // z slice = temporal tap
       const bool okt = okr && (unsigned)t0 < (unsigned)g.T;
       info_a = okt ? (o.n * g.T + t0) : -1;
       info_b = ((o.h * g.sH - g.pH) << 16) | ((o.w * g.sW - g.pW) & 0xFFFF);
     }
-    for (int idx = threadIdx.x; idx < total; idx += NPROD) {
-      const int kk = idx >> lcpr;
-      const int c = idx & (cpr - 1);
-      const int mn = row0 + c * 4;
-      bool ok = mn < limit;
+#pragma unroll
+    for (int j = 0; j < MAXS; ++j) {
+      if (j >= nslot) break;
+      bool ok = (okmask >> j) & 1u;
       const float* src = base;
       if (KIND == VLFB_OP_DENSE_MN) {
-        const int k = k0 + kk;
+        const int k = k0 + s_kk[j];
         ok = ok && k < kend;
-        if (ok) src = base + (int64_t)k * ld + mn;
+        if (ok) src = base + (int64_t)k * ld + s_mn[j];
       } else {
-        const int ra = __shfl_sync(0xffffffffu, info_a, kk);
-        const int rb = __shfl_sync(0xffffffffu, info_b, kk);
-        int kh, kw, ci;
-        if (KIND == VLFB_OP_CONV_MN) {
-          uint32_t tap_hw, cc, qh, qw;
-          fd_divmod((uint32_t)mn, cdiv, tap_hw, cc);     // n = tap_hw * C + ci
-          fd_divmod(tap_hw, kwdiv, qh, qw);
-          kh = (int)qh * g.dH; kw = (int)qw * g.dW; ci = (int)cc;
-        } else {                                         // STEM_MN: n = kh*32 + px*4 (+ch)
-          kh = mn >> 5; kw = (mn & 31) >> 2; ci = 0;
-        }
-        const int hi = (rb >> 16) + kh, wi = (int)(short)(rb & 0xFFFF) + kw;
+        const int ra = __shfl_sync(0xffffffffu, info_a, s_kk[j]);
+        const int rb = __shfl_sync(0xffffffffu, info_b, s_kk[j]);
+        const int hi = (rb >> 16) + (s_hw[j] >> 16), wi = (int)(short)(rb & 0xFFFF) + (int)(short)(s_hw[j] & 0xFFFF);
         ok = ok && ra >= 0 && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
-        if (ok) src = base + (int64_t)((ra * g.H + hi) * g.W + wi) * g.C + ci;
+        if (ok) src = base + (((ra * g.H + hi) * g.W + wi) * g.C + s_ci[j]);
       }
-      // SWIZZLE_128B_BASE32B (the MN-major layout 32-bit operands need; plain SWIZZLE_128B returns
-      // zeros for tf32 -- measured, profiles/r01_gemm_layout_diag.txt): atoms of 4 k-rows x 128 B,
-      // 32-byte units XOR (k & 3).
-      // atom-major tile [atom of 32 elements][32 k-rows][128 B]: the same image a TMA box {32 elems, 32 rows}
-      // with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B produces
-      const int r = kk & 3, cc8 = c & 7;
-      const uint32_t dst = tile + (c >> 3) * 4096 + kk * 128 + ((((cc8 >> 1) ^ r) << 5) | ((cc8 & 1) << 4));
-      cp_async16(dst, src, ok);
+      cp_async16(tile + dst[j], src, ok);
     }
   }
 };
@@ -397,254 +439,282 @@ struct Launch {
   int bn;        // tile N (32/64/128/256) = UMMA N = TMEM columns
   int stages;
   PosDiv out;    // fast divisors of the conv OUTPUT extents (Wo, Ho, To)
+  PosDiv in;     // ... and of the INPUT extents (W, H, T) for the dgrad row decode
   FastDiv cdiv;  // input channels C (wgrad: n -> (tap, ci))
   FastDiv kwdiv; // kW
   int tma_a, tma_b;  // operand fetched by TMA (dense K-major 2-D tiles) instead of cp.async
   int lag;           // cp.async groups kept in flight before a stage is published (< stages)
+  int tiles_m, tiles_n, total_tiles;
+  int fence_mode;    // 0: producers fence.proxy.async before publishing a stage; 1: the MMA thread fences after acquiring it
 };
 
+struct TileInfo { int m0, n0, batch, tap, k_begin, k_end, nk; };
+
+// Linear tile index -> (m tile fastest, n tile, z = batch|tap x split): CTAs that run concurrently share the
+// same weight (B) tile in L2.
+__device__ __forceinline__ TileInfo decode_tile(const vlfb_gemm_params_t& p, const Launch& L, int t) {
+  TileInfo ti;
+  const int mt = t % L.tiles_m;
+  const int r = t / L.tiles_m;
+  const int nt = r % L.tiles_n;
+  const int z = r / L.tiles_n;
+  const int split = z % p.split_k, zz = z / p.split_k;
+  ti.batch = (p.taps > 1) ? 0 : zz;
+  ti.tap = (p.taps > 1) ? zz : 0;
+  ti.m0 = mt * BM;
+  ti.n0 = nt * L.bn;
+  int kper = (p.K + p.split_k - 1) / p.split_k;
+  kper = (kper + KC - 1) / KC * KC;
+  ti.k_begin = split * kper;
+  ti.k_end = min(p.K, ti.k_begin + kper);
+  ti.nk = (ti.k_end > ti.k_begin) ? (ti.k_end - ti.k_begin + KC - 1) / KC : 0;
+  return ti;
+}
+
+// Persistent, warp-specialised: grid = min(#tiles, #SMs); every role walks the same static tile sequence
+// (t = blockIdx.x, += gridDim.x).  The smem ring (full/empty) runs continuously across tiles and the TMEM
+// accumulator is double-buffered (tmem_full/tmem_empty), so the epilogue of tile i overlaps the loads and
+// MMAs of tile i+1.
 template <int AK, int BK>
-__global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const vlfb_gemm_params_t p, const Launch L,
-                                                           const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmB) {
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_params_t p, const Launch L,
+                                                              const __grid_constant__ CUtensorMap tmA,
+                                                              const __grid_constant__ CUtensorMap tmB) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int bn = L.bn, S = L.stages;
   const uint32_t b_tile_bytes = (uint32_t)bn * KC * 4;
   const uint32_t stage_bytes = A_TILE_BYTES + b_tile_bytes;
-  const uint32_t bar_base = smem_base + S * stage_bytes;      // full[S], empty[S], tmem_full, tmem_ptr
-  const uint32_t full0 = bar_base, empty0 = bar_base + 8 * MAX_STAGES, tfull = bar_base + 16 * MAX_STAGES;
-  const uint32_t tptr_addr = tfull + 8;
+  const uint32_t epi_base = smem_base + S * stage_bytes;                  // 4 x 32x36 floats staging
+  const uint32_t bar_base = epi_base + EPI_STAGE_BYTES;
+  const uint32_t full0 = bar_base, empty0 = bar_base + 8 * MAX_STAGES;
+  const uint32_t tfull0 = bar_base + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
+  const uint32_t tptr_addr = tempty0 + 16;
   volatile uint32_t* tptr_generic =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr_addr - smem_u32(smem_raw)));
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  // z decomposition
-  const int z = blockIdx.z;
-  const int split = z % p.split_k;
-  const int zz = z / p.split_k;
-  const int batch = (p.taps > 1) ? 0 : zz;
-  const int tap = (p.taps > 1) ? zz : 0;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * bn;
-  int kper = (p.K + p.split_k - 1) / p.split_k;
-  kper = (kper + KC - 1) / KC * KC;
-  const int k_begin = split * kper;
-  const int k_end = min(p.K, k_begin + kper);
-  const int nk = (k_end > k_begin) ? (k_end - k_begin + KC - 1) / KC : 0;
-  if (nk == 0 && p.split_k > 1) return;   // empty split (uniform across the CTA)
+  const int total = L.total_tiles;
+  const bool tma_a = L.tma_a != 0, tma_b = L.tma_b != 0;
+  const bool cp_any = !(tma_a && tma_b);
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full0 + 8 * s, ((L.tma_a && L.tma_b) ? 0 : NPROD) + ((L.tma_a || L.tma_b) ? 1 : 0));
+      mbar_init(full0 + 8 * s, (cp_any ? NPROD : 0) + ((tma_a || tma_b) ? 1 : 0));
       mbar_init(empty0 + 8 * s, 1);
     }
-    mbar_init(tfull, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, NEPI);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == NPW) tmem_alloc(tptr_addr, (uint32_t)(bn < 32 ? 32 : bn));
-  if (warp < NPW && ((is_mn(AK) && L.tma_a) || (is_mn(BK) && L.tma_b))) {
-    // TMA only fetches the 32-element atoms that intersect the matrix; clear the rest of every stage once
-    const int av = (is_mn(AK) && L.tma_a) ? min(BM / 32, (p.M - m0 + 31) / 32) : BM / 32;
-    const int bv = (is_mn(BK) && L.tma_b) ? min(bn / 32, (p.N - n0 + 31) / 32) : bn / 32;
-    float4* base4 = reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)));
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int st = 0; st < S; ++st) {
-      float4* a4 = base4 + (size_t)st * (stage_bytes / 16);
-      for (int q = av * 256 + tid; q < (BM / 32) * 256; q += NPROD) a4[q] = z4;
-      float4* b4 = a4 + A_TILE_BYTES / 16;
-      for (int q = bv * 256 + tid; q < (bn / 32) * 256; q += NPROD) b4[q] = z4;
-    }
-    fence_proxy_async();
-  }
+  const uint32_t tmem_cols = (uint32_t)(2 * bn < 32 ? 32 : 2 * bn);
+  if (warp == NPW) tmem_alloc(tptr_addr, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tptr_generic;
 
   if (warp < NPW) {
-    // ============================ PRODUCERS ============================
-    if (nk > 0) {
+    // ============================ PRODUCERS (8 warps) ============================
+    if (cp_any || tid == 0) {
       KLoader<is_mn(AK) ? VLFB_OP_DENSE_K : AK, BM / RSTEP> ka;
       MNLoader<is_mn(AK) ? AK : VLFB_OP_DENSE_MN> ma;
       KLoader<is_mn(BK) ? VLFB_OP_DENSE_K : BK, 256 / RSTEP> kb;
       MNLoader<is_mn(BK) ? BK : VLFB_OP_DENSE_MN> mb;
-      if (is_mn(AK)) ma.init(p, p.a, m0, BM, p.M, batch, tap); else ka.init(p, p.a, m0, BM, p.M, batch);
-      if (is_mn(BK)) mb.init(p, p.b, n0, bn, p.N, batch, tap); else kb.init(p, p.b, n0, bn, p.N, batch);
-      if (!is_mn(AK)) ka.kend = k_end;
-      if (!is_mn(BK)) kb.kend = k_end;
-      const int kc0 = k_begin / KC;
       const int LAG = L.lag;
-      const bool tma_a = L.tma_a != 0, tma_b = L.tma_b != 0;
-      const bool cp_any = !(tma_a && tma_b);
-      // MN-major operands: one {32 elements x 32 k-rows} box per atom that intersects the matrix
-      const int a_atoms_v = is_mn(AK) ? min(BM / 32, (p.M - m0 + 31) / 32) : 0;
-      const int b_atoms_v = is_mn(BK) ? min(bn / 32, (p.N - n0 + 31) / 32) : 0;
-      const uint32_t tma_bytes = (tma_a ? (is_mn(AK) ? a_atoms_v * 4096u : (uint32_t)A_TILE_BYTES) : 0u) +
-                                 (tma_b ? (is_mn(BK) ? b_atoms_v * 4096u : b_tile_bytes) : 0u);
-      if (cp_any || tid == 0) {
-        for (int i = 0; i < nk; ++i) {
-          const int s = i % S;
-          if (i >= S) mbar_wait(empty0 + 8 * s, ((i / S) - 1) & 1);
+      const uint32_t tma_bytes = (tma_a ? (uint32_t)A_TILE_BYTES : 0u) + (tma_b ? b_tile_bytes : 0u);
+      int it = 0;                                   // chunk counter over the CTA's whole tile sequence
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const TileInfo ti = decode_tile(p, L, t);
+        if (ti.nk == 0) continue;
+        if (cp_any) {
+          if (!tma_a) { if (is_mn(AK)) ma.init(p, p.a, ti.m0, BM, p.M, ti.batch, ti.tap, L.cdiv, L.kwdiv); else { ka.init(p, p.a, ti.m0, BM, p.M, ti.batch, L.out, L.in, ti.k_begin / KC); ka.kend = ti.k_end; } }
+          if (!tma_b) { if (is_mn(BK)) mb.init(p, p.b, ti.n0, bn, p.N, ti.batch, ti.tap, L.cdiv, L.kwdiv); else { kb.init(p, p.b, ti.n0, bn, p.N, ti.batch, L.out, L.in, ti.k_begin / KC); kb.kend = ti.k_end; } }
+        }
+        const int kc0 = ti.k_begin / KC;
+        for (int i = 0; i < ti.nk; ++i, ++it) {
+          const int s = it % S;
+          if (it >= S) mbar_wait(empty0 + 8 * s, ((it / S) - 1) & 1);
           const uint32_t a_tile = smem_base + s * stage_bytes;
           const uint32_t b_tile = a_tile + A_TILE_BYTES;
           if (tid == 0 && tma_bytes) {
             mbar_expect_tx(full0 + 8 * s, tma_bytes);
             if (tma_a) {
               if (is_mn(AK)) {
-                for (int a = 0; a < a_atoms_v; ++a)
-                  tma_load_3d(a_tile + a * 4096, &tmA, m0 + a * 32, k_begin + i * KC, batch, full0 + 8 * s);
+                for (int a = 0; a < BM / 32; ++a)
+                  tma_load_3d(a_tile + a * 4096, &tmA, ti.m0 + a * 32, ti.k_begin + i * KC, ti.batch, full0 + 8 * s);
               } else {
-                tma_load_3d(a_tile, &tmA, (kc0 + i) * KC, m0, batch, full0 + 8 * s);
+                tma_load_3d(a_tile, &tmA, (kc0 + i) * KC, ti.m0, ti.batch, full0 + 8 * s);
               }
             }
             if (tma_b) {
               if (is_mn(BK)) {
-                for (int a = 0; a < b_atoms_v; ++a)
-                  tma_load_3d(b_tile + a * 4096, &tmB, n0 + a * 32, k_begin + i * KC, batch, full0 + 8 * s);
+                for (int a = 0; a < bn / 32; ++a)
+                  tma_load_3d(b_tile + a * 4096, &tmB, ti.n0 + a * 32, ti.k_begin + i * KC, ti.batch, full0 + 8 * s);
               } else {
-                tma_load_3d(b_tile, &tmB, (kc0 + i) * KC, n0, batch, full0 + 8 * s);
+                tma_load_3d(b_tile, &tmB, (kc0 + i) * KC, ti.n0, ti.batch, full0 + 8 * s);
               }
             }
           }
           if (!cp_any) continue;
           if (!tma_a) {
-            if (is_mn(AK)) ma.issue(p, L.out, L.cdiv, L.kwdiv, k_begin + i * KC, k_end, a_tile);
-            else ka.issue(p, m0, kc0 + i, a_tile);
+            if (is_mn(AK)) ma.issue(p, L.out, ti.k_begin + i * KC, ti.k_end, a_tile);
+            else ka.issue(p, kc0 + i, a_tile);
           }
           if (!tma_b) {
-            if (is_mn(BK)) mb.issue(p, L.out, L.cdiv, L.kwdiv, k_begin + i * KC, k_end, b_tile);
-            else kb.issue(p, n0, kc0 + i, b_tile);
+            if (is_mn(BK)) mb.issue(p, L.out, ti.k_begin + i * KC, ti.k_end, b_tile);
+            else kb.issue(p, kc0 + i, b_tile);
           }
           cp_async_commit();
-          if (i >= LAG) {
+          if (it >= LAG) {
             cp_async_wait_dyn(LAG);
-            fence_proxy_async();
-            mbar_arrive(full0 + 8 * ((i - LAG) % S));
+            if (L.fence_mode == 0) fence_proxy_async();
+            mbar_arrive(full0 + 8 * ((it - LAG) % S));
           }
         }
-        if (cp_any) {
-          cp_async_wait<0>();
-          fence_proxy_async();
-          for (int i = (nk > LAG ? nk - LAG : 0); i < nk; ++i) mbar_arrive(full0 + 8 * (i % S));
-        }
+      }
+      if (cp_any) {
+        cp_async_wait<0>();
+        fence_proxy_async();
+        for (int c = (it > LAG ? it - LAG : 0); c < it; ++c) mbar_arrive(full0 + 8 * (c % S));
       }
     }
-    // ============================ EPILOGUE =============================
-    if (nk > 0) {
-      mbar_wait(tfull, 0);
-      tc_fence_after();
-    }
-    // TMEM lane == tile row: thread (warp w, lane l) owns row 32w + l.  Each 32x32 block is transposed
-    // through a padded shared-memory tile (the pipeline stages are idle by now) so that every warp
-    // store / residual load / atomic touches whole 128-byte lines: lanes 0-7 cover one row's 128 B.
-    const int lane = tid & 31;
-    // TMEM lane quarter = warp % 4 (hardware rule); warps w and w+4 split the 32-column blocks.
-    const int quarter = warp & 3;
-    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw))) + warp * (32 * 36);
-    const int64_t tile_off = (int64_t)batch * p.d_batch_stride + (int64_t)tap * p.d_tap_stride;
-    const bool vec_ok = ((p.ldd & 3) == 0) && ((p.d_batch_stride & 3) == 0) && ((p.d_tap_stride & 3) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0) &&
-                        (!p.residual || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
-    const int col = (lane & 7) * 4;
-    for (int c0 = (warp >> 2) * 32; c0 < bn; c0 += 32 * (NPW / 4)) {
-      if (n0 + c0 >= p.N) break;            // warp-uniform
-      float v[32];
-      if (nk > 0) {
-        tmem_ld32(lane_addr + c0, v);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int q = 0; q < 32; ++q) v[q] = 0.f;
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        *reinterpret_cast<float4*>(stg + lane * 36 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      __syncwarp();
-      const int n = n0 + c0 + col;
-      float4 cs = make_float4(1.f, 1.f, 1.f, 1.f), cb = make_float4(0.f, 0.f, 0.f, 0.f);
-      const bool nfull = n + 3 < p.N;
-      if (nfull) {
-        if (p.col_scale) cs = *reinterpret_cast<const float4*>(p.col_scale + n);
-        if (p.col_bias) cb = *reinterpret_cast<const float4*>(p.col_bias + n);
-      }
-      // residual / accumulate operands of the 8 row groups are fetched up front (8 independent 128-bit
-      // loads in flight per lane) so that their latency overlaps instead of serialising per row
-      float4 rr[8];
-      const bool want_res = (p.residual != nullptr) || (p.flags & VLFB_EPI_ACCUM);
-      const float* res_src = p.residual ? p.residual : p.d;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = m0 + quarter * 32 + (lane >> 3) + 4 * i;
-        rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (want_res && nfull && vec_ok && m < p.M && !(p.residual && (p.flags & VLFB_EPI_ACCUM)))
-          rr[i] = *reinterpret_cast<const float4*>(res_src + tile_off + (int64_t)m * p.ldd + n);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = (lane >> 3) + 4 * i;
-        const int m = m0 + quarter * 32 + row;
-        if (m >= p.M || n >= p.N) continue;
-        const float4 a4 = *reinterpret_cast<const float4*>(stg + row * 36 + col);
-        if (nfull && vec_ok && !(p.residual && (p.flags & VLFB_EPI_ACCUM))) {
-          const float rs = p.row_scale ? p.row_scale[m] : 1.f;
-          float4 o = make_float4(a4.x * p.alpha, a4.y * p.alpha, a4.z * p.alpha, a4.w * p.alpha);
-          o.x = (o.x * cs.x + cb.x) * rs; o.y = (o.y * cs.y + cb.y) * rs;
-          o.z = (o.z * cs.z + cb.z) * rs; o.w = (o.w * cs.w + cb.w) * rs;
-          const int64_t off = tile_off + (int64_t)m * p.ldd + n;
-          if (p.residual) { o.x += rr[i].x; o.y += rr[i].y; o.z += rr[i].z; o.w += rr[i].w; }
-          if (p.flags & VLFB_EPI_RELU) {
-            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-          }
-          if (p.flags & VLFB_EPI_TF32) {
-            o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
-          }
-          float* dst = p.d + off;
-          if (p.flags & VLFB_EPI_ATOMIC) {
-            atomicAdd(dst, o.x); atomicAdd(dst + 1, o.y); atomicAdd(dst + 2, o.z); atomicAdd(dst + 3, o.w);
-          } else if (p.flags & VLFB_EPI_ACCUM) {
-            *reinterpret_cast<float4*>(dst) = make_float4(rr[i].x + o.x, rr[i].y + o.y, rr[i].z + o.z, rr[i].w + o.w);
-          } else {
-            *reinterpret_cast<float4*>(dst) = o;
-          }
-        } else {
-          const float e4[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (n + e < p.N) epilogue_store(p, batch, tap, m, n + e, e4[e]);
-        }
-      }
-      __syncwarp();
-    }
-  } else if (nk > 0) {
-    // ============================ MMA ISSUER ===========================
+  } else if (warp == NPW) {
+    // ============================ MMA ISSUER (1 thread) ============================
     if ((tid & 31) == 0) {
       const uint32_t idesc = make_idesc(bn, is_mn(AK) ? 1 : 0, is_mn(BK) ? 1 : 0);
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % S;
-        mbar_wait(full0 + 8 * s, (i / S) & 1);
-        tc_fence_after();
-        const uint32_t a_tile = smem_base + s * stage_bytes;
-        const uint32_t b_tile = a_tile + A_TILE_BYTES;
-#pragma unroll
-        for (int j = 0; j < KC / 8; ++j) {   // UMMA K = 8 for tf32
-          uint64_t da, db;
-          if (!is_mn(AK)) da = make_desc(a_tile + j * 32, 16, 1024);
-          else da = make_desc(a_tile + j * 1024, 4096, 512, 1);
-          if (!is_mn(BK)) db = make_desc(b_tile + j * 32, 16, 1024);
-          else db = make_desc(b_tile + j * 1024, 4096, 512, 1);
-          umma_tf32(tmem, da, db, idesc, (i | j) ? 1u : 0u);
+      int it = 0, tile_iter = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const TileInfo ti = decode_tile(p, L, t);
+        if (ti.nk == 0) continue;
+        const int acc = tile_iter & 1;
+        if (tile_iter >= 2) {                          // wait until the epilogue drained this accumulator
+          mbar_wait(tempty0 + 8 * acc, ((tile_iter >> 1) - 1) & 1);
+          tc_fence_after();
         }
-        umma_commit(empty0 + 8 * s);       // frees the smem stage when these MMAs retire
+        const uint32_t d_tmem = tmem + (uint32_t)(acc * bn);
+        for (int i = 0; i < ti.nk; ++i, ++it) {
+          const int s = it % S;
+          mbar_wait(full0 + 8 * s, (it / S) & 1);
+          if (L.fence_mode == 1) fence_proxy_async();
+          tc_fence_after();
+          const uint32_t a_tile = smem_base + s * stage_bytes;
+          const uint32_t b_tile = a_tile + A_TILE_BYTES;
+#pragma unroll
+          for (int j = 0; j < KC / 8; ++j) {          // UMMA K = 8 for tf32
+            uint64_t da, db;
+            if (!is_mn(AK)) da = make_desc(a_tile + j * 32, 16, 1024);
+            else da = make_desc(a_tile + j * 1024, 4096, 512, 1);
+            if (!is_mn(BK)) db = make_desc(b_tile + j * 32, 16, 1024);
+            else db = make_desc(b_tile + j * 1024, 4096, 512, 1);
+            umma_tf32(d_tmem, da, db, idesc, (i | j) ? 1u : 0u);
+          }
+          umma_commit(empty0 + 8 * s);               // frees the smem stage when these MMAs retire
+        }
+        umma_commit(tfull0 + 8 * acc);               // accumulator complete -> epilogue
+        ++tile_iter;
       }
-      umma_commit(tfull);                  // accumulator complete -> epilogue
+    }
+  } else {
+    // ============================ EPILOGUE (4 warps) ============================
+    // TMEM lane quarter = warp % 4 (hardware rule).  Each 32x32 block is transposed through a padded
+    // shared-memory tile so that every warp store / residual load / atomic touches whole 128-byte lines.
+    const int ew = warp - NPW - 1;
+    const int quarter = warp & 3;
+    const int lane = tid & 31;
+    float* stg = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw))) + ew * (32 * 36);
+    const bool vec_ok = ((p.ldd & 3) == 0) && ((p.d_batch_stride & 3) == 0) && ((p.d_tap_stride & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0) &&
+                        (!p.residual || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) &&
+                        !(p.residual && (p.flags & VLFB_EPI_ACCUM));
+    const int col = (lane & 7) * 4;
+    const bool want_res = (p.residual != nullptr) || (p.flags & VLFB_EPI_ACCUM);
+    const float* res_src = p.residual ? p.residual : p.d;
+    int tile_iter = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      const TileInfo ti = decode_tile(p, L, t);
+      if (ti.nk == 0) continue;
+      const int acc = tile_iter & 1;
+      mbar_wait(tfull0 + 8 * acc, (tile_iter >> 1) & 1);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem + (uint32_t)(acc * bn) + ((uint32_t)(quarter * 32) << 16);
+      const int64_t tile_off = (int64_t)ti.batch * p.d_batch_stride + (int64_t)ti.tap * p.d_tap_stride;
+      for (int c0 = 0; c0 < bn; c0 += 32) {
+        if (ti.n0 + c0 >= p.N) break;            // warp-uniform
+        float v[32];
+        tmem_ld32(lane_addr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(stg + lane * 36 + q * 4) =
+              make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
+        const int n = ti.n0 + c0 + col;
+        float4 cs = make_float4(1.f, 1.f, 1.f, 1.f), cb = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool nfull = n + 3 < p.N;
+        if (nfull) {
+          if (p.col_scale) cs = *reinterpret_cast<const float4*>(p.col_scale + n);
+          if (p.col_bias) cb = *reinterpret_cast<const float4*>(p.col_bias + n);
+        }
+        // residual / accumulate operands of the 8 row groups are fetched up front (8 independent 128-bit
+        // loads in flight per lane) so that their latency overlaps instead of serialising per row
+        float4 rr[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = ti.m0 + quarter * 32 + (lane >> 3) + 4 * i;
+          rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (want_res && nfull && vec_ok && m < p.M)
+            rr[i] = *reinterpret_cast<const float4*>(res_src + tile_off + (int64_t)m * p.ldd + n);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = (lane >> 3) + 4 * i;
+          const int m = ti.m0 + quarter * 32 + row;
+          if (m >= p.M || n >= p.N) continue;
+          const float4 a4 = *reinterpret_cast<const float4*>(stg + row * 36 + col);
+          if (nfull && vec_ok) {
+            const float rs = p.row_scale ? p.row_scale[m] : 1.f;
+            float4 o = make_float4(a4.x * p.alpha, a4.y * p.alpha, a4.z * p.alpha, a4.w * p.alpha);
+            o.x = (o.x * cs.x + cb.x) * rs; o.y = (o.y * cs.y + cb.y) * rs;
+            o.z = (o.z * cs.z + cb.z) * rs; o.w = (o.w * cs.w + cb.w) * rs;
+            const int64_t off = tile_off + (int64_t)m * p.ldd + n;
+            if (p.residual) { o.x += rr[i].x; o.y += rr[i].y; o.z += rr[i].z; o.w += rr[i].w; }
+            if (p.flags & VLFB_EPI_RELU) {
+              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            }
+            if (p.flags & VLFB_EPI_TF32) {
+              o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+            }
+            float* dst = p.d + off;
+            if (p.flags & VLFB_EPI_ATOMIC) {
+              atomicAdd(dst, o.x); atomicAdd(dst + 1, o.y); atomicAdd(dst + 2, o.z); atomicAdd(dst + 3, o.w);
+            } else if (p.flags & VLFB_EPI_ACCUM) {
+              *reinterpret_cast<float4*>(dst) =
+                  make_float4(rr[i].x + o.x, rr[i].y + o.y, rr[i].z + o.z, rr[i].w + o.w);
+            } else {
+              *reinterpret_cast<float4*>(dst) = o;
+            }
+          } else {
+            const float e4[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (n + e < p.N) epilogue_store(p, ti.batch, ti.tap, m, n + e, e4[e]);
+          }
+        }
+        __syncwarp();
+      }
+      // every TMEM read of this accumulator has completed (tcgen05.wait::ld above): hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(tempty0 + 8 * acc);
+      ++tile_iter;
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == NPW) {
     tc_fence_after();
-    tmem_dealloc(tmem, (uint32_t)(bn < 32 ? 32 : bn));
+    tmem_dealloc(tmem, tmem_cols);
   }
 }
 
@@ -706,38 +776,55 @@ int launch(const vlfb_gemm_params_t& p, cudaStream_t stream) {
   L.out.w = make_fastdiv(p.g.Wo);
   L.out.h = make_fastdiv(p.g.Ho);
   L.out.t = make_fastdiv(p.g.To);
+  L.in.w = make_fastdiv(p.g.W);
+  L.in.h = make_fastdiv(p.g.H);
+  L.in.t = make_fastdiv(p.g.T);
   L.cdiv = make_fastdiv(p.g.C);
   L.kwdiv = make_fastdiv(p.g.kW);
-  if (p.N > 128) L.bn = 256;
-  else if (p.N > 64) L.bn = 128;
-  else if (p.N > 32) L.bn = 64;
-  else L.bn = 32;
-  // keep >= 2 waves of CTAs on 148 SMs when the wide tile would leave the chip underfilled
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  }
   const int64_t zdim = (int64_t)(p.taps > 1 ? p.taps : p.batch) * p.split_k;
-  if (L.bn == 256 && (int64_t)ceil_div(p.M, BM) * ceil_div(p.N, 256) * zdim < 148) L.bn = 128;
-  const int stage_bytes = A_TILE_BYTES + L.bn * KC * 4;
-  L.stages = (L.bn == 256) ? 4 : (L.bn == 128 ? 3 : 4);
+  const int tiles_m = ceil_div(p.M, BM);
+  // Tile width: the persistent grid runs ceil(tiles / #SMs) waves and a 128 x bn tile costs ~(128 + bn) bytes of
+  // operand traffic per k, so pick the bn that minimises waves * (128 + bn).
   {
-    // short-K (memory-bound) layers: fewer stages -> less shared memory -> more resident CTAs to overlap
-    // one CTA's epilogue with another's loads
-    int kper = (p.K + p.split_k - 1) / p.split_k;
-    const int nk = (kper + KC - 1) / KC;
-    if (nk < L.stages) L.stages = nk < 2 ? 2 : nk;
+    int best = 32;
+    double best_score = 1e30;
+    for (int bn = 256; bn >= 32; bn >>= 1) {
+      if (bn > 32 && p.N <= bn / 2) continue;                       // do not pad N by 2x
+      const int64_t tiles = (int64_t)tiles_m * ceil_div(p.N, bn) * zdim;
+      const double waves = (double)((tiles + num_sms - 1) / num_sms);
+      const double score = waves * (128 + bn);
+      if (score < best_score) { best_score = score; best = bn; }
+    }
+    L.bn = best;
   }
   {
     // tuning overrides (scripts/tune_gemm.py)
     const char* e;
-    if ((e = getenv("VLFB_BN")) && atoi(e) > 0 && atoi(e) >= 32) { int v = atoi(e); if (p.N > v / 2 || v == 32) L.bn = v; }
-    if ((e = getenv("VLFB_STAGES")) && atoi(e) >= 2) L.stages = atoi(e);
+    if ((e = getenv("VLFB_BN")) && atoi(e) >= 32) { int v = atoi(e); if (p.N > v / 2 || v == 32) L.bn = v; }
   }
-  int stage_bytes2 = A_TILE_BYTES + L.bn * KC * 4;
-  while (L.stages > 2 && L.stages * stage_bytes2 + 1280 > 227 * 1024) --L.stages;
+  const int stage_bytes = A_TILE_BYTES + L.bn * KC * 4;
+  L.stages = (227 * 1024 - EPI_STAGE_BYTES - 2048) / stage_bytes;
+  if (L.stages > 6) L.stages = 6;
+  {
+    const char* e = getenv("VLFB_STAGES");
+    if (e && atoi(e) >= 2 && atoi(e) <= L.stages) L.stages = atoi(e);
+  }
   L.lag = L.stages - 1 < 2 ? L.stages - 1 : 2;
   {
     const char* e = getenv("VLFB_LAG");
-    if (e && atoi(e) >= 1 && atoi(e) < L.stages) L.lag = atoi(e);
+    if (e && atoi(e) >= 1 && atoi(e) < L.stages && atoi(e) <= 5) L.lag = atoi(e);
   }
-  const int smem = L.stages * stage_bytes2 + 1024 /*align*/ + 256 /*barriers*/;
+  L.fence_mode = (getenv("VLFB_FENCE") ? atoi(getenv("VLFB_FENCE")) : 0);
+  L.tiles_m = tiles_m;
+  L.tiles_n = ceil_div(p.N, L.bn);
+  L.total_tiles = (int)((int64_t)L.tiles_m * L.tiles_n * zdim);
+  const int smem = L.stages * stage_bytes + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -748,7 +835,7 @@ int launch(const vlfb_gemm_params_t& p, cudaStream_t stream) {
     }
     attr_done = true;
   }
-  dim3 grid(ceil_div(p.M, BM), ceil_div(p.N, L.bn), (unsigned)zdim);
+  dim3 grid((unsigned)(L.total_tiles < num_sms ? L.total_tiles : num_sms));
   alignas(64) CUtensorMap tmA, tmB;
   memset(&tmA, 0, sizeof(tmA));
   memset(&tmB, 0, sizeof(tmB));
