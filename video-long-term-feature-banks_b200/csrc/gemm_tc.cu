@@ -3,14 +3,14 @@
 //   D[m,n] = epi( sum_k A[m,k] * B[n,k] ),  fp32 storage, kind::tf32 MMA, fp32 accumulate in TMEM.
 //
 // Persistent kernel: grid = min(#tiles, #SMs), one CTA per SM walks a static sequence of 128 x BN output
-// tiles (UMMA M=128, N=BN, cta_group::1), 416 threads:
+// tiles (UMMA M=128, N=BN, cta_group::1), 544 threads:
 //   warps 0-7  PRODUCERS -- im2col-free gather of the A/B K-chunks (32 fp32 = one 128-byte swizzle row)
 //              straight from NDHWC tensors into the UMMA canonical swizzled shared-memory layouts with
 //              16-byte cp.async (zero-fill = conv padding); dense operands are fetched by TMA instead
 //              (cp.async.bulk.tensor, SWIZZLE_128B for K-major, SWIZZLE_128B_ATOM_32B for MN-major);
 //   warp 8     TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit releases each smem
 //              stage back to the producers and hands finished accumulators to the epilogue;
-//   warps 9-12 EPILOGUE -- tcgen05.ld TMEM -> registers -> smem transpose -> fused affine / residual /
+//   warps 9-16 EPILOGUE -- tcgen05.ld TMEM -> registers -> smem transpose -> fused affine / residual /
 //              ReLU / TF32 rounding -> coalesced 128-bit global stores (or atomics for split-K).
 // The smem ring (full[s]/empty[s] mbarriers) runs continuously across tiles and the accumulator is double
 // buffered in TMEM (tmem_full[a]/tmem_empty[a]), so the epilogue of one tile overlaps the loads and MMAs
@@ -35,9 +35,11 @@ constexpr int NPROD = 256;     // producer / epilogue threads: 8 warps = 2 per s
                                // producer warp per scheduler 'wait'+'selected' stalls dominated, no unit >14% busy)
 constexpr int NPW = NPROD / 32;
 constexpr int RSTEP = NPROD / 8;   // rows covered by one pass of the K-major loaders
-constexpr int NEPI = 128;          // 4 epilogue warps (one per TMEM lane quarter)
+constexpr int NEPI = 256;          // 8 epilogue warps (two per TMEM lane quarter, splitting the column blocks)
+constexpr int EPC = 16;            // accumulator columns per epilogue step (tcgen05.ld.32x32b.x16)
+constexpr int EPITCH = EPC + 4;    // padded staging row (floats)
 constexpr int NTHREADS = NPROD + 32 + NEPI;  // producers + MMA warp + epilogue
-constexpr int EPI_STAGE_BYTES = 4 * 32 * 36 * 4;
+constexpr int EPI_STAGE_BYTES = (NEPI / 32) * 32 * EPITCH * 4;
 constexpr int A_TILE_BYTES = BM * KC * 4;  // 16 KB
 constexpr int MAX_STAGES = 8;
 
@@ -145,6 +147,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }
@@ -484,7 +496,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
   const int bn = L.bn, S = L.stages;
   const uint32_t b_tile_bytes = (uint32_t)bn * KC * 4;
   const uint32_t stage_bytes = A_TILE_BYTES + b_tile_bytes;
-  const uint32_t epi_base = smem_base + S * stage_bytes;                  // 4 x 32x36 floats staging
+  const uint32_t epi_base = smem_base + S * stage_bytes;                  // per-epilogue-warp transpose tiles
   const uint32_t bar_base = epi_base + EPI_STAGE_BYTES;
   const uint32_t full0 = bar_base, empty0 = bar_base + 8 * MAX_STAGES;
   const uint32_t tfull0 = bar_base + 16 * MAX_STAGES, tempty0 = tfull0 + 16;
@@ -617,18 +629,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
       }
     }
   } else {
-    // ============================ EPILOGUE (4 warps) ============================
-    // TMEM lane quarter = warp % 4 (hardware rule).  Each 32x32 block is transposed through a padded
-    // shared-memory tile so that every warp store / residual load / atomic touches whole 128-byte lines.
+    // ============================ EPILOGUE (8 warps) ============================
+    // TMEM lane quarter = warp % 4 (hardware rule); the two warps of a quarter take alternate 16-column
+    // blocks.  Each 32x16 block is transposed through a padded shared-memory tile so that a warp store /
+    // residual load / atomic covers 8 rows x 64 contiguous bytes (whole 32-byte sectors).
     const int ew = warp - NPW - 1;
     const int quarter = warp & 3;
+    const int half = ew >> 2;
     const int lane = tid & 31;
-    float* stg = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw))) + ew * (32 * 36);
+    float* stg = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw))) + ew * (32 * EPITCH);
     const bool vec_ok = ((p.ldd & 3) == 0) && ((p.d_batch_stride & 3) == 0) && ((p.d_tap_stride & 3) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0) &&
                         (!p.residual || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) &&
                         !(p.residual && (p.flags & VLFB_EPI_ACCUM));
-    const int col = (lane & 7) * 4;
+    const int col = (lane & 3) * 4;
     const bool want_res = (p.residual != nullptr) || (p.flags & VLFB_EPI_ACCUM);
     const float* res_src = p.residual ? p.residual : p.d;
     int tile_iter = 0;
@@ -640,14 +654,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
       tc_fence_after();
       const uint32_t lane_addr = tmem + (uint32_t)(acc * bn) + ((uint32_t)(quarter * 32) << 16);
       const int64_t tile_off = (int64_t)ti.batch * p.d_batch_stride + (int64_t)ti.tap * p.d_tap_stride;
-      for (int c0 = 0; c0 < bn; c0 += 32) {
+      for (int c0 = half * EPC; c0 < bn; c0 += 2 * EPC) {
         if (ti.n0 + c0 >= p.N) break;            // warp-uniform
-        float v[32];
-        tmem_ld32(lane_addr + c0, v);
+        float v[EPC];
+        tmem_ld16(lane_addr + c0, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(stg + lane * 36 + q * 4) =
+        for (int q = 0; q < EPC / 4; ++q)
+          *reinterpret_cast<float4*>(stg + lane * EPITCH + q * 4) =
               make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         __syncwarp();
         const int n = ti.n0 + c0 + col;
@@ -657,22 +671,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
           if (p.col_scale) cs = *reinterpret_cast<const float4*>(p.col_scale + n);
           if (p.col_bias) cb = *reinterpret_cast<const float4*>(p.col_bias + n);
         }
-        // residual / accumulate operands of the 8 row groups are fetched up front (8 independent 128-bit
-        // loads in flight per lane) so that their latency overlaps instead of serialising per row
-        float4 rr[8];
+        // residual / accumulate operands of the 4 row groups are fetched up front so their latencies overlap
+        float4 rr[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int m = ti.m0 + quarter * 32 + (lane >> 3) + 4 * i;
+        for (int i = 0; i < 4; ++i) {
+          const int m = ti.m0 + quarter * 32 + (lane >> 2) + 8 * i;
           rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (want_res && nfull && vec_ok && m < p.M)
             rr[i] = *reinterpret_cast<const float4*>(res_src + tile_off + (int64_t)m * p.ldd + n);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = (lane >> 3) + 4 * i;
+        for (int i = 0; i < 4; ++i) {
+          const int row = (lane >> 2) + 8 * i;
           const int m = ti.m0 + quarter * 32 + row;
           if (m >= p.M || n >= p.N) continue;
-          const float4 a4 = *reinterpret_cast<const float4*>(stg + row * 36 + col);
+          const float4 a4 = *reinterpret_cast<const float4*>(stg + row * EPITCH + col);
           if (nfull && vec_ok) {
             const float rs = p.row_scale ? p.row_scale[m] : 1.f;
             float4 o = make_float4(a4.x * p.alpha, a4.y * p.alpha, a4.z * p.alpha, a4.w * p.alpha);
