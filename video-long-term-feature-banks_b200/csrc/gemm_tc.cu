@@ -39,7 +39,9 @@ constexpr int NEPI = 256;          // 8 epilogue warps (two per TMEM lane quarte
 constexpr int EPC = 16;            // accumulator columns per epilogue step (tcgen05.ld.32x32b.x16)
 constexpr int EPITCH = EPC + 4;    // padded staging row (floats)
 constexpr int NTHREADS = NPROD + 32 + NEPI;  // producers + MMA warp + epilogue
-constexpr int EPI_STAGE_BYTES = (NEPI / 32) * 32 * EPITCH * 4;
+constexpr int EPI_COLV = 2 * 128;     // per-warp column scale + bias of its 128 columns (floats)
+constexpr int EPI_WARP_FLOATS = 32 * EPITCH + EPI_COLV;
+constexpr int EPI_STAGE_BYTES = (NEPI / 32) * EPI_WARP_FLOATS * 4;
 constexpr int A_TILE_BYTES = BM * KC * 4;  // 16 KB
 constexpr int MAX_STAGES = 8;
 
@@ -149,6 +151,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
+}
+// residual / accumulate reads: plain (coherent) 128-bit loads -- D may have been written by an earlier launch
+// on the same stream, never by this one
+__device__ __forceinline__ float4 ld_nc_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -637,7 +645,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
     const int quarter = warp & 3;
     const int half = ew >> 2;
     const int lane = tid & 31;
-    float* stg = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw))) + ew * (32 * EPITCH);
+    float* stg = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw))) + ew * EPI_WARP_FLOATS;
+    float* wsc = stg + 32 * EPITCH;      // column scale of this warp's column blocks, then the bias
+    float* wbi = wsc + 128;
+    int colv_n0 = -1;
     const bool vec_ok = ((p.ldd & 3) == 0) && ((p.d_batch_stride & 3) == 0) && ((p.d_tap_stride & 3) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0) &&
                         (!p.residual || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) &&
@@ -650,12 +661,56 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
       const TileInfo ti = decode_tile(p, L, t);
       if (ti.nk == 0) continue;
       const int acc = tile_iter & 1;
-      mbar_wait(tfull0 + 8 * acc, (tile_iter >> 1) & 1);
-      tc_fence_after();
       const uint32_t lane_addr = tmem + (uint32_t)(acc * bn) + ((uint32_t)(quarter * 32) << 16);
       const int64_t tile_off = (int64_t)ti.batch * p.d_batch_stride + (int64_t)ti.tap * p.d_tap_stride;
+      if (want_res && t + (int)gridDim.x < total) {
+        // pull the NEXT tile's residual rows into L2 while this tile is being written out
+        const TileInfo tn = decode_tile(p, L, t + gridDim.x);
+        const int64_t noff = (int64_t)tn.batch * p.d_batch_stride + (int64_t)tn.tap * p.d_tap_stride;
+        const int segs = bn >> 5;
+        for (int idx = tid - (NPROD + 32); idx < BM * segs; idx += NEPI) {
+          const int row = idx / segs, seg = idx - row * segs;
+          const int m = tn.m0 + row, n = tn.n0 + seg * 32;
+          if (m < p.M && n < p.N) prefetch_l2(res_src + noff + (int64_t)m * p.ldd + n);
+        }
+      }
+      // residual / accumulate operands are fetched one column block ahead (register double buffer): with only
+      // 8 epilogue warps per SM the loads must be in flight while the previous block is stored, otherwise the
+      // epilogue is DRAM-latency bound (Little's law) instead of bandwidth bound
+      auto load_res = [&](int c0, float4* r) {
+        const int n = ti.n0 + c0 + col;
+        const bool ok = want_res && vec_ok && c0 < bn && n + 3 < p.N;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int m = ti.m0 + quarter * 32 + (lane >> 2) + 8 * i;
+          r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok && m < p.M) r[i] = ld_nc_f4(res_src + tile_off + (int64_t)m * p.ldd + n);
+        }
+      };
+      float4 rr[4], rn[4];
+      load_res(half * EPC, rr);                  // independent of the accumulator: issued before the wait
+      if (ti.n0 != colv_n0) {
+        // per-column affine of this warp's blocks -> shared memory, once per N tile (not per block: the
+        // global-load latency used to sit in front of every block's first FFMA)
+        colv_n0 = ti.n0;
+        for (int i = lane; i < (bn >> 1); i += 32) {
+          const int n = ti.n0 + half * EPC + (i >> 4) * (2 * EPC) + (i & 15);
+          wsc[i] = (p.col_scale && n < p.N) ? p.col_scale[n] : 1.f;
+          wbi[i] = (p.col_bias && n < p.N) ? p.col_bias[n] : 0.f;
+        }
+        __syncwarp();
+      }
+      float rs[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = ti.m0 + quarter * 32 + (lane >> 2) + 8 * i;
+        rs[i] = (p.row_scale && m < p.M) ? p.row_scale[m] : 1.f;
+      }
+      mbar_wait(tfull0 + 8 * acc, (tile_iter >> 1) & 1);
+      tc_fence_after();
       for (int c0 = half * EPC; c0 < bn; c0 += 2 * EPC) {
         if (ti.n0 + c0 >= p.N) break;            // warp-uniform
+        load_res(c0 + 2 * EPC, rn);
         float v[EPC];
         tmem_ld16(lane_addr + c0, v);
         tmem_ld_wait();
@@ -665,21 +720,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
               make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         __syncwarp();
         const int n = ti.n0 + c0 + col;
-        float4 cs = make_float4(1.f, 1.f, 1.f, 1.f), cb = make_float4(0.f, 0.f, 0.f, 0.f);
         const bool nfull = n + 3 < p.N;
-        if (nfull) {
-          if (p.col_scale) cs = *reinterpret_cast<const float4*>(p.col_scale + n);
-          if (p.col_bias) cb = *reinterpret_cast<const float4*>(p.col_bias + n);
-        }
-        // residual / accumulate operands of the 4 row groups are fetched up front so their latencies overlap
-        float4 rr[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int m = ti.m0 + quarter * 32 + (lane >> 2) + 8 * i;
-          rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (want_res && nfull && vec_ok && m < p.M)
-            rr[i] = *reinterpret_cast<const float4*>(res_src + tile_off + (int64_t)m * p.ldd + n);
-        }
+        const int cvi = ((c0 - half * EPC) >> 1) + col;
+        const float4 cs = *reinterpret_cast<const float4*>(wsc + cvi);
+        const float4 cb = *reinterpret_cast<const float4*>(wbi + cvi);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int row = (lane >> 2) + 8 * i;
@@ -687,10 +731,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
           if (m >= p.M || n >= p.N) continue;
           const float4 a4 = *reinterpret_cast<const float4*>(stg + row * EPITCH + col);
           if (nfull && vec_ok) {
-            const float rs = p.row_scale ? p.row_scale[m] : 1.f;
             float4 o = make_float4(a4.x * p.alpha, a4.y * p.alpha, a4.z * p.alpha, a4.w * p.alpha);
-            o.x = (o.x * cs.x + cb.x) * rs; o.y = (o.y * cs.y + cb.y) * rs;
-            o.z = (o.z * cs.z + cb.z) * rs; o.w = (o.w * cs.w + cb.w) * rs;
+            o.x = (o.x * cs.x + cb.x) * rs[i]; o.y = (o.y * cs.y + cb.y) * rs[i];
+            o.z = (o.z * cs.z + cb.z) * rs[i]; o.w = (o.w * cs.w + cb.w) * rs[i];
             const int64_t off = tile_off + (int64_t)m * p.ldd + n;
             if (p.residual) { o.x += rr[i].x; o.y += rr[i].y; o.z += rr[i].z; o.w += rr[i].w; }
             if (p.flags & VLFB_EPI_RELU) {
@@ -716,6 +759,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
           }
         }
         __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rr[i] = rn[i];
       }
       // every TMEM read of this accumulator has completed (tcgen05.wait::ld above): hand it back to the MMA warp
       tc_fence_before();
