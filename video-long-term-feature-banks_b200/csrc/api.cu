@@ -51,6 +51,7 @@ static int validate_gemm(const vlfb_gemm_params_t& p, bool& tc_ok) {
       case VLFB_OP_CONV_MN:
         VLFB_CHECK_ARG(i == 1 && p.N == p.g.kH * p.g.kW * p.g.C && (p.g.C & 3) == 0 && p.taps == p.g.kT);
         VLFB_CHECK_ARG((int64_t)p.K == (int64_t)p.g.N * p.g.To * p.g.Ho * p.g.Wo);
+        VLFB_CHECK_ARG(p.g.kH <= 8 && p.g.kW <= 8);      // per-row validity bits of the gather loader
         break;
       case VLFB_OP_STEM_K:
         VLFB_CHECK_ARG(i == 0 && p.g.C == 4 && p.g.kW <= 8 && p.K == p.g.kT * p.g.kH * 32);
@@ -58,13 +59,22 @@ static int validate_gemm(const vlfb_gemm_params_t& p, bool& tc_ok) {
         VLFB_CHECK_ARG((int64_t)p.M == (int64_t)p.g.N * p.g.To * p.g.Ho * p.g.Wo);
         break;
       case VLFB_OP_STEM_MN:
-        VLFB_CHECK_ARG(i == 1 && p.g.C == 4 && p.g.kW <= 8 && p.N == 32 * p.g.kH && p.taps == p.g.kT);
+        VLFB_CHECK_ARG(i == 1 && p.g.C == 4 && p.g.kW <= 8 && p.g.kH <= 8 && p.N == 32 * p.g.kH && p.taps == p.g.kT);
         VLFB_CHECK_ARG(p.g.dT == 1 && p.g.dH == 1 && p.g.dW == 1);
         VLFB_CHECK_ARG((int64_t)p.K == (int64_t)p.g.N * p.g.To * p.g.Ho * p.g.Wo);
         break;
       default:
         set_error("vlfb_gemm: unknown operand kind %d", o.kind);
         return VLFB_E_BADARG;
+    }
+  }
+  if (p.a.kind >= VLFB_OP_CONV_K || p.b.kind >= VLFB_OP_CONV_K) {
+    // the gather loaders keep element offsets in 32 bits
+    const int64_t in_elems = (int64_t)p.g.N * p.g.T * p.g.H * p.g.W * p.g.C;
+    const int64_t out_elems = (int64_t)p.g.N * p.g.To * p.g.Ho * p.g.Wo * p.g.Co;
+    if (in_elems >= (1ll << 31) || out_elems >= (1ll << 31)) {
+      set_error("vlfb_gemm: conv tensors of >= 2^31 elements are not supported (split the batch)");
+      return VLFB_E_BADARG;
     }
   }
   return VLFB_OK;

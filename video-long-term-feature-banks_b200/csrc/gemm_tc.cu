@@ -368,88 +368,96 @@ struct MNLoader {
   static constexpr int MAXS = (32 * 64) / NPROD;   // copies per thread per chunk at the widest tile (256 cols)
   const float* base;
   int64_t ld;
-  int rows, limit, row0, tapz, nslot, lcpr;
-  // per copy slot (fixed for the whole tile): shared-memory offset, k-row within the chunk, and for the conv
-  // kinds the filter-tap offsets / channel of the 16-byte chunk -- nothing of this depends on the K chunk
-  uint32_t dst[MAXS];
-  int s_kk[MAXS], s_mn[MAXS], s_hw[MAXS], s_ci[MAXS];
-  uint32_t okmask;
+  int tapz, nslot;
+  // A thread copies the SAME 16-byte column chunk c of the k-rows kk0, kk0 + kstep, ... (NPROD is a multiple of
+  // the chunks per k-row), so everything that depends on the column -- bounds, filter tap (kh,kw), channel,
+  // swizzled shared-memory offset -- is one scalar per tile, and the per-chunk work per copy is two shuffles,
+  // a bit test and an add (ncu r01: the previous per-slot arrays cost ~100 instructions per 16-byte copy).
+  int mn, kk0, kstep;
+  bool colok;
+  uint32_t dst0, dstep;
+  int slotoff;       // conv kinds: element offset of (kh,kw,ci) relative to the k-row's window origin
+  int sh, sw;        // bit positions of this column's kh / kw in the k-row's validity word
 
-  __device__ __forceinline__ void init(const vlfb_gemm_params_t& p, const vlfb_operand_t& op, int row0_, int rows_,
-                                       int limit_, int batch, int tap, const FastDiv& cdiv, const FastDiv& kwdiv) {
+  __device__ __forceinline__ void init(const vlfb_gemm_params_t& p, const vlfb_operand_t& op, int row0, int rows,
+                                       int limit, int batch, int tap, const FastDiv& cdiv, const FastDiv& kwdiv) {
     const vlfb_conv_geom_t& g = p.g;
     base = op.ptr;
     if (KIND == VLFB_OP_DENSE_MN) base += (int64_t)batch * op.batch_stride;
     ld = op.ld;
-    rows = rows_;
-    limit = limit_;
-    row0 = row0_;
     tapz = tap;
     const int cpr = rows >> 2;            // 16-byte chunks per k-row (8, 16, 32 or 64)
-    lcpr = 31 - __clz(cpr);
+    const int lcpr = 31 - __clz(cpr);
     nslot = (KC * cpr) / NPROD;
-    okmask = 0;
-#pragma unroll
-    for (int j = 0; j < MAXS; ++j) {
-      if (j >= nslot) break;
-      const int idx = threadIdx.x + NPROD * j;
-      const int kk = idx >> lcpr;
-      const int c = idx & (cpr - 1);
-      const int mn = row0 + c * 4;
-      s_kk[j] = kk;
-      s_mn[j] = mn;
-      if (mn < limit) okmask |= 1u << j;
-      // atom-major tile [atom of 32 elements][32 k-rows][128 B] in the SWIZZLE_128B_BASE32B pattern (32-byte
-      // units XOR (k & 3)); plain SWIZZLE_128B returns zeros for tf32 MN-major operands (measured,
-      // profiles/r01_gemm_layout_diag.txt).  Same image as a TMA box with SWIZZLE_128B_ATOM_32B.
-      const int r = kk & 3, cc8 = c & 7;
-      dst[j] = (uint32_t)((c >> 3) * 4096 + kk * 128 + ((((cc8 >> 1) ^ r) << 5) | ((cc8 & 1) << 4)));
-      if (KIND == VLFB_OP_CONV_MN) {
-        uint32_t tap_hw, cc, qh, qw;
-        fd_divmod((uint32_t)mn, cdiv, tap_hw, cc);     // n = (kh*kW + kw) * C + ci
-        fd_divmod(tap_hw, kwdiv, qh, qw);
-        s_hw[j] = (((int)qh * g.dH) << 16) | (((int)qw * g.dW) & 0xFFFF);
-        s_ci[j] = (int)cc;
-      } else if (KIND == VLFB_OP_STEM_MN) {            // n = kh*32 + px*4 (+ch)
-        s_hw[j] = ((mn >> 5) << 16) | ((mn & 31) >> 2);
-        s_ci[j] = 0;
-      }
+    kstep = NPROD >> lcpr;
+    kk0 = threadIdx.x >> lcpr;
+    const int c = threadIdx.x & (cpr - 1);
+    mn = row0 + c * 4;
+    colok = mn < limit;
+    // atom-major tile [atom of 32 elements][32 k-rows][128 B] in the SWIZZLE_128B_BASE32B pattern (32-byte
+    // units XOR (k & 3)); plain SWIZZLE_128B returns zeros for tf32 MN-major operands (measured,
+    // profiles/r01_gemm_layout_diag.txt).  Same image as a TMA box with SWIZZLE_128B_ATOM_32B.
+    // kstep is a multiple of 4 whenever a thread owns more than one copy, so the XOR term is per-thread.
+    const int r = kk0 & 3, cc8 = c & 7;
+    dst0 = (uint32_t)((c >> 3) * 4096 + kk0 * 128 + ((((cc8 >> 1) ^ r) << 5) | ((cc8 & 1) << 4)));
+    dstep = (uint32_t)(kstep * 128);
+    slotoff = 0; sh = 0; sw = 8;
+    if (KIND == VLFB_OP_CONV_MN) {
+      uint32_t tap_hw, cc, qh, qw;
+      fd_divmod((uint32_t)(colok ? mn : 0), cdiv, tap_hw, cc);     // n = (kh*kW + kw) * C + ci
+      fd_divmod(tap_hw, kwdiv, qh, qw);
+      slotoff = ((int)qh * g.dH * g.W + (int)qw * g.dW) * g.C + (int)cc;
+      sh = (int)qh; sw = 8 + (int)qw;
+    } else if (KIND == VLFB_OP_STEM_MN) {            // n = kh*32 + px*4 (+ch)
+      const int qh = mn >> 5, qw = (mn & 31) >> 2;
+      slotoff = (qh * g.W + qw) * 4;
+      sh = qh; sw = 8 + qw;
     }
   }
 
   // k0 = first k of this chunk, kend = exclusive k limit of this CTA's K range.
   // Conv kinds (wgrad B operand): the N extent spans ALL (kh,kw) taps of one kt slice, so one pass over dY
   // feeds up to 256 (tap, ci) columns.  Each lane decodes ONE of the 32 k-rows (output positions) of the
-  // chunk; the copy slots fetch the row info they need with warp shuffles.
+  // chunk into (element offset of its window origin, validity bits per kh and per kw); the copies fetch the
+  // row they need with warp shuffles.
   __device__ __forceinline__ void issue(const vlfb_gemm_params_t& p, const PosDiv& pd, int k0, int kend, uint32_t tile) const {
     const vlfb_conv_geom_t& g = p.g;
-    int info_a = 0, info_b = 0;           // per-lane k-row: (n*T + t0) and (h0 << 16 | w0 & 0xffff)
+    int info_a = 0, info_b = 0;
     if (KIND != VLFB_OP_DENSE_MN) {
       const int k = k0 + (threadIdx.x & 31);
       const bool okr = k < kend;
       const Pos4 o = decode_pos_fast(okr ? (uint32_t)k : 0u, pd);
       const int t0 = o.t * g.sT - g.pT + tapz * g.dT;          // z slice = temporal tap
       const bool okt = okr && (unsigned)t0 < (unsigned)g.T;
-      info_a = okt ? (o.n * g.T + t0) : -1;
-      info_b = ((o.h * g.sH - g.pH) << 16) | ((o.w * g.sW - g.pW) & 0xFFFF);
+      const int h0 = o.h * g.sH - g.pH, w0 = o.w * g.sW - g.pW;
+      info_a = (((o.n * g.T + t0) * g.H + h0) * g.W + w0) * g.C;
+      const int nh = g.kH, nw = (KIND == VLFB_OP_STEM_MN) ? 8 : g.kW;
+      const int dh = (KIND == VLFB_OP_STEM_MN) ? 1 : g.dH, dw = (KIND == VLFB_OP_STEM_MN) ? 1 : g.dW;
+      int hm = 0, wm = 0;
+      for (int q = 0, h = h0; q < nh; ++q, h += dh) hm |= ((unsigned)h < (unsigned)g.H) ? (1 << q) : 0;
+      for (int q = 0, w = w0; q < nw; ++q, w += dw) wm |= ((unsigned)w < (unsigned)g.W) ? (256 << q) : 0;
+      info_b = okt ? (hm | wm) : 0;
     }
+    int lane_src = kk0;
+    uint32_t d = tile + dst0;
 #pragma unroll
     for (int j = 0; j < MAXS; ++j) {
       if (j >= nslot) break;
-      bool ok = (okmask >> j) & 1u;
+      bool ok = colok;
       const float* src = base;
       if (KIND == VLFB_OP_DENSE_MN) {
-        const int k = k0 + s_kk[j];
+        const int k = k0 + lane_src;
         ok = ok && k < kend;
-        if (ok) src = base + (int64_t)k * ld + s_mn[j];
+        if (ok) src = base + (int64_t)k * ld + mn;
       } else {
-        const int ra = __shfl_sync(0xffffffffu, info_a, s_kk[j]);
-        const int rb = __shfl_sync(0xffffffffu, info_b, s_kk[j]);
-        const int hi = (rb >> 16) + (s_hw[j] >> 16), wi = (int)(short)(rb & 0xFFFF) + (int)(short)(s_hw[j] & 0xFFFF);
-        ok = ok && ra >= 0 && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
-        if (ok) src = base + (((ra * g.H + hi) * g.W + wi) * g.C + s_ci[j]);
+        const int ra = __shfl_sync(0xffffffffu, info_a, lane_src);
+        const int rb = __shfl_sync(0xffffffffu, info_b, lane_src);
+        ok = ok && (((rb >> sh) & (rb >> sw) & 1) != 0);
+        if (ok) src = base + (ra + slotoff);
       }
-      cp_async16(tile + dst[j], src, ok);
+      cp_async16(d, src, ok);
+      lane_src += kstep;
+      d += dstep;
     }
   }
 };
@@ -544,7 +552,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
       MNLoader<is_mn(BK) ? BK : VLFB_OP_DENSE_MN> mb;
       const int LAG = L.lag;
       const uint32_t tma_bytes = (tma_a ? (uint32_t)A_TILE_BYTES : 0u) + (tma_b ? b_tile_bytes : 0u);
-      int it = 0;                                   // chunk counter over the CTA's whole tile sequence
+      // chunk counter over the CTA's whole tile sequence; ring slot / phase / lagged slot advance
+      // incrementally (S is a run-time value: `it % S` cost three integer divisions per chunk per thread)
+      int it = 0, s = 0, sl = 0;
+      uint32_t ph = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         const TileInfo ti = decode_tile(p, L, t);
         if (ti.nk == 0) continue;
@@ -554,26 +565,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
         }
         const int kc0 = ti.k_begin / KC;
         for (int i = 0; i < ti.nk; ++i, ++it) {
-          const int s = it % S;
-          if (it >= S) mbar_wait(empty0 + 8 * s, ((it / S) - 1) & 1);
-          const uint32_t a_tile = smem_base + s * stage_bytes;
+          if (it >= S) mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          const int s_cur = s;
+          if (++s == S) { s = 0; ph ^= 1u; }
+          const uint32_t a_tile = smem_base + s_cur * stage_bytes;
           const uint32_t b_tile = a_tile + A_TILE_BYTES;
           if (tid == 0 && tma_bytes) {
-            mbar_expect_tx(full0 + 8 * s, tma_bytes);
+            mbar_expect_tx(full0 + 8 * s_cur, tma_bytes);
             if (tma_a) {
               if (is_mn(AK)) {
                 for (int a = 0; a < BM / 32; ++a)
-                  tma_load_3d(a_tile + a * 4096, &tmA, ti.m0 + a * 32, ti.k_begin + i * KC, ti.batch, full0 + 8 * s);
+                  tma_load_3d(a_tile + a * 4096, &tmA, ti.m0 + a * 32, ti.k_begin + i * KC, ti.batch, full0 + 8 * s_cur);
               } else {
-                tma_load_3d(a_tile, &tmA, (kc0 + i) * KC, ti.m0, ti.batch, full0 + 8 * s);
+                tma_load_3d(a_tile, &tmA, (kc0 + i) * KC, ti.m0, ti.batch, full0 + 8 * s_cur);
               }
             }
             if (tma_b) {
               if (is_mn(BK)) {
                 for (int a = 0; a < bn / 32; ++a)
-                  tma_load_3d(b_tile + a * 4096, &tmB, ti.n0 + a * 32, ti.k_begin + i * KC, ti.batch, full0 + 8 * s);
+                  tma_load_3d(b_tile + a * 4096, &tmB, ti.n0 + a * 32, ti.k_begin + i * KC, ti.batch, full0 + 8 * s_cur);
               } else {
-                tma_load_3d(b_tile, &tmB, (kc0 + i) * KC, ti.n0, ti.batch, full0 + 8 * s);
+                tma_load_3d(b_tile, &tmB, (kc0 + i) * KC, ti.n0, ti.batch, full0 + 8 * s_cur);
               }
             }
           }
@@ -590,21 +602,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
           if (it >= LAG) {
             cp_async_wait_dyn(LAG);
             if (L.fence_mode == 0) fence_proxy_async();
-            mbar_arrive(full0 + 8 * ((it - LAG) % S));
+            mbar_arrive(full0 + 8 * sl);
+            if (++sl == S) sl = 0;
           }
         }
       }
       if (cp_any) {
         cp_async_wait<0>();
         fence_proxy_async();
-        for (int c = (it > LAG ? it - LAG : 0); c < it; ++c) mbar_arrive(full0 + 8 * (c % S));
+        for (int c = (it > LAG ? it - LAG : 0); c < it; ++c) {
+          mbar_arrive(full0 + 8 * sl);
+          if (++sl == S) sl = 0;
+        }
       }
     }
   } else if (warp == NPW) {
     // ============================ MMA ISSUER (1 thread) ============================
     if ((tid & 31) == 0) {
       const uint32_t idesc = make_idesc(bn, is_mn(AK) ? 1 : 0, is_mn(BK) ? 1 : 0);
-      int it = 0, tile_iter = 0;
+      int it = 0, tile_iter = 0, s = 0;
+      uint32_t ph = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         const TileInfo ti = decode_tile(p, L, t);
         if (ti.nk == 0) continue;
@@ -615,8 +632,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
         }
         const uint32_t d_tmem = tmem + (uint32_t)(acc * bn);
         for (int i = 0; i < ti.nk; ++i, ++it) {
-          const int s = it % S;
-          mbar_wait(full0 + 8 * s, (it / S) & 1);
+          mbar_wait(full0 + 8 * s, ph);
           if (L.fence_mode == 1) fence_proxy_async();
           tc_fence_after();
           const uint32_t a_tile = smem_base + s * stage_bytes;
@@ -631,6 +647,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
             umma_tf32(d_tmem, da, db, idesc, (i | j) ? 1u : 0u);
           }
           umma_commit(empty0 + 8 * s);               // frees the smem stage when these MMAs retire
+          if (++s == S) { s = 0; ph ^= 1u; }
         }
         umma_commit(tfull0 + 8 * acc);               // accumulator complete -> epilogue
         ++tile_iter;
