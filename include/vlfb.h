@@ -80,7 +80,7 @@ typedef struct {
   int M, N, K;                /* logical GEMM extent (K per z-slice for wgrad) */
   int batch;                  /* >= 1 (DENSE only)                           */
   int taps;                   /* wgrad: number of temporal taps kT (z-slices), else 1 */
-  int split_k;                /* >= 1; >1 forces atomic accumulation         */
+  int split_k;                /* >= 1 (>1 needs VLFB_EPI_ATOMIC); 0 = the library picks it with the tile width */
   float* d;                   /* output rows: d + batch*d_batch_stride + m*ldd + n (+ tap*d_tap_stride) */
   int64_t ldd, d_batch_stride, d_tap_stride;
   float alpha;                /* applied first                               */

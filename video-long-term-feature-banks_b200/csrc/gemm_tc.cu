@@ -84,8 +84,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-  const int sz = valid ? 16 : 0;   // src-size 0 => 16 bytes of zeros (conv padding / tails)
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+  // ignore-src predicate => 16 bytes of zeros (conv padding / tails); one LDGSTS.ZFILL, no size arithmetic
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t"
+      "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t}"
+      ::"r"(dst), "l"(src), "r"((uint32_t)valid) : "memory");
 }
 // TMA: one thread arms the stage barrier with the byte count, then issues the bulk tensor copy; the copy
 // engine writes the box into shared memory in the SWIZZLE_128B pattern and completes the transaction.
@@ -455,7 +458,9 @@ struct MNLoader {
         ok = ok && (((rb >> sh) & (rb >> sw) & 1) != 0);
         if (ok) src = base + (ra + slotoff);
       }
-      cp_async16(d, src, ok);
+      // columns beyond the matrix are never copied: whatever shared memory holds there only reaches accumulator
+      // columns >= N, which the epilogue does not store (k tails of real columns ARE zero-filled)
+      if (colok) cp_async16(d, src, ok);
       lane_src += kstep;
       d += dstep;
     }
@@ -845,8 +850,22 @@ static bool make_tmap_mn(CUtensorMap* tm, const vlfb_operand_t& op, int extent, 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// tuning overrides, read once (scripts/tune_gemm.py)
+struct Env { int bn, stages, lag, fence; bool tma_mn; };
+static Env read_env() {
+  Env e;
+  auto geti = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
+  e.bn = geti("VLFB_BN", 0);
+  e.stages = geti("VLFB_STAGES", 0);
+  e.lag = geti("VLFB_LAG", 0);
+  e.fence = geti("VLFB_FENCE", 0);
+  e.tma_mn = geti("VLFB_TMA_MN", 1) != 0;
+  return e;
+}
+
 template <int AK, int BK>
-int launch(const vlfb_gemm_params_t& p, cudaStream_t stream) {
+int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
+  vlfb_gemm_params_t p = p_in;       // split_k == 0 is resolved below
   Launch L;
   L.out.w = make_fastdiv(p.g.Wo);
   L.out.h = make_fastdiv(p.g.Ho);
@@ -862,40 +881,41 @@ int launch(const vlfb_gemm_params_t& p, cudaStream_t stream) {
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
   }
-  const int64_t zdim = (int64_t)(p.taps > 1 ? p.taps : p.batch) * p.split_k;
+  static const Env env = read_env();
+  const int zbase = p.taps > 1 ? p.taps : p.batch;
   const int tiles_m = ceil_div(p.M, BM);
-  // Tile width: the persistent grid runs ceil(tiles / #SMs) waves and a 128 x bn tile costs ~(128 + bn) bytes of
-  // operand traffic per k, so pick the bn that minimises waves * (128 + bn).
+  // Tile width and split-K (p.split_k == 0: chosen here).  The persistent grid runs ceil(tiles / #SMs) rounds;
+  // a round of a 128 x bn tile costs ~(128 + bn) bytes of operand traffic per k over (K / split) chunks plus a
+  // fixed fill + epilogue overhead (~8 chunks), so take the (bn, split) pair that minimises
+  // rounds * (chunks + 8) * (128 + bn).  With the old fixed rules conv1's wgrad ran 300 tiles on 148 SMs
+  // (3 rounds for 2.03 waves of work) and the res2 3x3 wgrads 192 tiles (2 rounds for 1.3 waves).
   {
-    int best = 32;
+    int best_bn = 32, best_split = p.split_k > 0 ? p.split_k : 1;
     double best_score = 1e30;
+    const int smax = p.split_k > 0 ? p.split_k : (p.K >= 512 ? (p.K / 256 < 128 ? p.K / 256 : 128) : 1);
     for (int bn = 256; bn >= 32; bn >>= 1) {
       if (bn > 32 && p.N <= bn / 2) continue;                       // do not pad N by 2x
-      const int64_t tiles = (int64_t)tiles_m * ceil_div(p.N, bn) * zdim;
-      const double waves = (double)((tiles + num_sms - 1) / num_sms);
-      const double score = waves * (128 + bn);
-      if (score < best_score) { best_score = score; best = bn; }
+      const int64_t base_tiles = (int64_t)tiles_m * ceil_div(p.N, bn) * zbase;
+      for (int sp = (p.split_k > 0 ? p.split_k : 1); sp <= smax; ++sp) {
+        const int64_t tiles = base_tiles * sp;
+        const double rounds = (double)((tiles + num_sms - 1) / num_sms);
+        const double chunks = (double)ceil_div(ceil_div(p.K, sp), KC) + 8.0;
+        const double score = rounds * chunks * (128 + bn);
+        if (score < best_score * 0.999) { best_score = score; best_bn = bn; best_split = sp; }
+      }
     }
-    L.bn = best;
+    L.bn = best_bn;
+    p.split_k = best_split;
   }
-  {
-    // tuning overrides (scripts/tune_gemm.py)
-    const char* e;
-    if ((e = getenv("VLFB_BN")) && atoi(e) >= 32) { int v = atoi(e); if (p.N > v / 2 || v == 32) L.bn = v; }
-  }
+  if (env.bn >= 32 && (p.N > env.bn / 2 || env.bn == 32)) L.bn = env.bn;      // tuning overrides (scripts/tune_gemm.py)
+  const int64_t zdim = (int64_t)zbase * p.split_k;
   const int stage_bytes = A_TILE_BYTES + L.bn * KC * 4;
   L.stages = (227 * 1024 - EPI_STAGE_BYTES - 2048) / stage_bytes;
   if (L.stages > 6) L.stages = 6;
-  {
-    const char* e = getenv("VLFB_STAGES");
-    if (e && atoi(e) >= 2 && atoi(e) <= L.stages) L.stages = atoi(e);
-  }
+  if (env.stages >= 2 && env.stages <= L.stages) L.stages = env.stages;
   L.lag = L.stages - 1 < 2 ? L.stages - 1 : 2;
-  {
-    const char* e = getenv("VLFB_LAG");
-    if (e && atoi(e) >= 1 && atoi(e) < L.stages && atoi(e) <= 5) L.lag = atoi(e);
-  }
-  L.fence_mode = (getenv("VLFB_FENCE") ? atoi(getenv("VLFB_FENCE")) : 0);
+  if (env.lag >= 1 && env.lag < L.stages && env.lag <= 5) L.lag = env.lag;
+  L.fence_mode = env.fence;
   L.tiles_m = tiles_m;
   L.tiles_n = ceil_div(p.N, L.bn);
   L.total_tiles = (int)((int64_t)L.tiles_m * L.tiles_n * zdim);
@@ -914,7 +934,7 @@ int launch(const vlfb_gemm_params_t& p, cudaStream_t stream) {
   alignas(64) CUtensorMap tmA, tmB;
   memset(&tmA, 0, sizeof(tmA));
   memset(&tmB, 0, sizeof(tmB));
-  const bool mn_tma = !(getenv("VLFB_TMA_MN") && atoi(getenv("VLFB_TMA_MN")) == 0);
+  const bool mn_tma = env.tma_mn;
   L.tma_a = (AK == VLFB_OP_DENSE_K && make_tmap(&tmA, p.a, p.M, p.K, p.batch, BM)) ||
             (AK == VLFB_OP_DENSE_MN && mn_tma && make_tmap_mn(&tmA, p.a, p.M, p.K, p.batch)) ? 1 : 0;
   L.tma_b = (BK == VLFB_OP_DENSE_K && make_tmap(&tmB, p.b, p.N, p.K, p.batch, L.bn)) ||

@@ -103,7 +103,7 @@ def _run_gemm(p, kind='gemm', flops=None):
         e.record()
         if flops is None:
             flops = 2.0 * p.M * p.N * p.K * max(p.batch, 1) * max(p.taps, 1)
-        _PROFILE.append(('%s M=%d N=%d K=%d z=%d' % (kind, p.M, p.N, p.K, max(p.batch, p.taps) * p.split_k), s, e, flops))
+        _PROFILE.append(('%s M=%d N=%d K=%d z=%d%s' % (kind, p.M, p.N, p.K, max(p.batch, p.taps), 'xauto' if p.split_k == 0 else ''), s, e, flops))
         return
     _check(L.load().vlfb_gemm(C.byref(p), _stream()), 'vlfb_gemm')
 
@@ -186,13 +186,6 @@ def conv_dgrad(dy, wt, dx, g, accumulate=False):
     _run_gemm(p, 'conv_dgrad', 2.0 * g.N * g.To * g.Ho * g.Wo * g.Co * g.kT * g.kH * g.kW * g.C)
 
 
-def _split_k(tiles, kdim):
-    """Split the reduction so that >= ~2 waves of CTAs cover the 148 SMs."""
-    want = (2 * NUM_SMS + tiles - 1) // tiles
-    cap = max(1, kdim // 256)
-    return max(1, min(want, cap, 64))
-
-
 def conv_wgrad(dy, x, dw, g, row_scale=None, col_mask=None):
     """dw[co,tap,ci] += row_scale[co] * sum_m dy[m,co] * x[gather(m,tap),ci]  (atomic accumulate:
     dw must be zero-initialised or hold a partial sum).  Stem path when C == 4 (dw [Co,kT,kH,8,4],
@@ -216,9 +209,7 @@ def conv_wgrad(dy, x, dw, g, row_scale=None, col_mask=None):
     p.g = g
     p.taps = taps
     p.d_tap_stride = n
-    bn = 256 if n > 128 else (128 if n > 64 else (64 if n > 32 else 32))
-    tiles = ((g.Co + 127) // 128) * ((n + bn - 1) // bn) * taps
-    p.split_k = _split_k(tiles, Kpos)
+    p.split_k = 0            # split-K and the tile width are chosen together by the library (gemm_tc.cu launch())
     p.flags |= L.EPI_ATOMIC
     _set_epilogue(p, col_mask, None, row_scale, None, False)
     _run_gemm(p, 'conv_wgrad', 2.0 * Kpos * g.Co * g.kT * g.kH * g.kW * (3 if g.C == 4 else g.C))
