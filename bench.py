@@ -305,6 +305,8 @@ def main():
         run_reference(args)
     else:
         run_b200(args)
+        from vlfb import dist as vdist
+        vdist.shutdown()
 
 
 if __name__ == '__main__':
