@@ -72,6 +72,7 @@ typedef struct {
 
 /* VLFB_EPI_TF32: round the stored value to TF32 (round-to-nearest, ties away: cvt.rna.tf32.f32) so that a
  * consumer GEMM reads operands that the tensor core would otherwise truncate. */
+/* VLFB_EPI_ACCUM: the previous contents of d are added like a residual (v += d, then ReLU / mask / rounding). */
 enum { VLFB_EPI_RELU = 1, VLFB_EPI_ACCUM = 2, VLFB_EPI_ATOMIC = 4, VLFB_EPI_TF32 = 8 };
 
 typedef struct {
@@ -88,6 +89,9 @@ typedef struct {
   const float* col_bias;      /* [N] or NULL : v += col_bias[n]              */
   const float* row_scale;     /* [M] or NULL : v *= row_scale[m]             */
   const float* residual;      /* same addressing as d, or NULL : v += res    */
+  const float* relu_mask;     /* same addressing as d, or NULL : v = mask > 0 ? v : 0  (applied after the
+                               * residual / ReLU, before the TF32 rounding).  Backward of a ReLU fused into the
+                               * dgrad GEMM that produces the gradient: mask = the ReLU's output */
   int flags;                  /* VLFB_EPI_*                                  */
 } vlfb_gemm_params_t;
 

@@ -61,7 +61,7 @@ def conv_fwd(x, w, y, g, scale=None, bias=None, residual=None, relu=False, tf32_
     y.copy_(_q(o, tf32_out))
 
 
-def conv_dgrad(dy, wt, dx, g, accumulate=False):
+def conv_dgrad(dy, wt, dx, g, accumulate=False, residual=None, relu_mask=None, tf32_out=False):
     taps = g.kT * g.kH * g.kW
     w = wt.view(g.C, taps, g.Co).permute(2, 1, 0).reshape(g.Co, g.kT, g.kH, g.kW, g.C)
     x = torch.zeros((g.N, g.C, g.T, g.H, g.W), dtype=dy.dtype, requires_grad=True)
@@ -69,9 +69,12 @@ def conv_dgrad(dy, wt, dx, g, accumulate=False):
     y.backward(_nc(dy))
     r = x.grad.permute(0, 2, 3, 4, 1)
     if accumulate:
-        dx.add_(r)
-    else:
-        dx.copy_(r)
+        r = r + dx
+    if residual is not None:
+        r = r + residual
+    if relu_mask is not None:
+        r = torch.where(relu_mask > 0, r, torch.zeros_like(r))
+    dx.copy_(_q(r, tf32_out))
 
 
 def conv_wgrad(dy, x, dw, g, row_scale=None, col_mask=None):

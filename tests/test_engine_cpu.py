@@ -23,7 +23,7 @@ def fake():
     fake_kernels.uninstall()
 
 
-def _run(yaml_name, overrides, fake, check_blobs):
+def _run(yaml_name, overrides, fake, check_blobs, reps=1):
     from oracle import model as OM
     from vlfb import workspace
     H.setup_cfg(yaml_name, overrides)
@@ -40,23 +40,37 @@ def _run(yaml_name, overrides, fake, check_blobs):
     loss.backward()
     # product: forward + backward only (no update) to compare gradients
     net = workspace.current().nets[model.net.Proto().name]
+    from vlfb import executor as X
     upd, net.update_ops = net.update_ops, []
-    workspace.RunNet(model.net.Proto().name)
+    first = {}
+    fuse0, X.FUSE_GRAD_FINISH = X.FUSE_GRAD_FINISH, True
+    # run 1 records how many contributions every gradient receives; from run 2 on the dgrad GEMM that
+    # delivers the last one also applies the ReLU backward + TF32 rounding (executor "grad finish" fusion):
+    # both runs must match the oracle, and each other exactly
+    for rep in range(reps):
+        fused0 = X.STATS['fused_grad_finish']
+        workspace.RunNet(model.net.Proto().name)
+        assert (X.STATS['fused_grad_finish'] > fused0) == (rep == 1)
+        assert H.rel(workspace.FetchBlob('gpu_0/loss'), loss.item()) < 1e-9
+        for b in check_blobs:
+            assert H.rel(workspace.FetchBlob('gpu_0/' + b), blobs[b].detach().numpy()) < 1e-9, b
+        trainable = model.TrainableParams()
+        expected = [k for k in params if not (k.endswith('_bn_s') or k.endswith('_bn_b'))]
+        assert sorted(trainable) == sorted(expected)
+        worst = 0.0
+        for name in trainable:
+            g = workspace.FetchBlob('gpu_0/' + name + '_grad')
+            ref = p64[name].grad.numpy()
+            e = float(np.abs(g - ref).max() / max(np.abs(ref).max(), 1e-5))   # e.g. phi_b has a zero gradient
+            worst = max(worst, e)
+            assert e < 1e-7, (name, e)
+            if rep == 0:
+                first[name] = g.copy()
+            else:
+                assert np.array_equal(g, first[name]), name
+        print("run %d: worst grad rel err %.2e" % (rep, worst))
     net.update_ops = upd
-    assert H.rel(workspace.FetchBlob('gpu_0/loss'), loss.item()) < 1e-9
-    for b in check_blobs:
-        assert H.rel(workspace.FetchBlob('gpu_0/' + b), blobs[b].detach().numpy()) < 1e-9, b
-    trainable = model.TrainableParams()
-    expected = [k for k in params if not (k.endswith('_bn_s') or k.endswith('_bn_b'))]
-    assert sorted(trainable) == sorted(expected)
-    worst = 0.0
-    for name in trainable:
-        g = workspace.FetchBlob('gpu_0/' + name + '_grad')
-        ref = p64[name].grad.numpy()
-        e = float(np.abs(g - ref).max() / max(np.abs(ref).max(), 1e-5))   # e.g. phi_b has a zero gradient
-        worst = max(worst, e)
-        assert e < 1e-7, (name, e)
-    print("worst grad rel err", worst)
+    X.FUSE_GRAD_FINISH = fuse0
     return model, params, p64, worst
 
 
@@ -64,7 +78,7 @@ def test_ava_fbo_nl_forward_backward_matches_oracle(fake):
     _run('ava_r50_lfb_nl.yaml', TINY, fake,
          ['pool1', 'res2_2_branch2c_bn', 'nonlocal_conv3_1_sum', 'res3_3_branch2c_bn', 'nonlocal_conv4_1_sum',
           'res5_2_branch2c_bn', 'blob_pooled', 'roi_feat_3d', 'box_pooled', 'lfb_1x1', 'lfb_nl0_affinity_prob',
-          'lfb_nl1_sum', 'pool5', 'pred', 'prob'])
+          'lfb_nl1_sum', 'pool5', 'pred', 'prob'], reps=2)
 
 
 def test_charades_post_act_variant(fake):
@@ -159,3 +173,33 @@ def test_tf32_rounding_points_match_oracle_emulation(fake):
             assert H.rel(a, b) < 2.5e-3, name                   # and never more than a TF32 ulp or two
     finally:
         fake.EMULATE_TF32 = False
+
+
+def test_grad_finish_fusion_is_exact_under_tf32_emulation(fake):
+    """Run 1 (separate ReLU-backward / rounding passes) and run 2 (folded into the last dgrad GEMM's epilogue)
+    must produce bit-identical gradients also when the TF32 roundings are emulated."""
+    from oracle import model as OM
+    from vlfb import executor as X, workspace
+    fake.EMULATE_TF32 = True
+    fuse0, X.FUSE_GRAD_FINISH = X.FUSE_GRAD_FINISH, True
+    try:
+        H.setup_cfg('ava_r50_lfb_nl.yaml', TINY)
+        ocfg = H.oracle_cfg('ava_r50_lfb_nl.yaml', TINY)
+        params = OM.make_params(ocfg, seed=2)
+        inputs = OM.make_inputs(ocfg, n_clips=2, rois_per_clip=2, crop=64, frames=8)
+        model, sfx = H.build('train', True)
+        H.feed_params(params)
+        H.feed_inputs(inputs, sfx)
+        net = workspace.current().nets[model.net.Proto().name]
+        net.update_ops = []
+        grads = []
+        for rep in range(2):
+            n0 = X.STATS['fused_grad_finish']
+            workspace.RunNet(model.net.Proto().name)
+            assert (X.STATS['fused_grad_finish'] - n0 > 40) == (rep == 1)
+            grads.append(dict((n, workspace.FetchBlob('gpu_0/' + n + '_grad').copy()) for n in model.TrainableParams()))
+        for n in grads[0]:
+            assert np.array_equal(grads[0][n], grads[1][n]), n
+    finally:
+        fake.EMULATE_TF32 = False
+        X.FUSE_GRAD_FINISH = fuse0

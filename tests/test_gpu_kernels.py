@@ -114,6 +114,20 @@ def test_conv_fwd_dgrad_wgrad(K, backend, geom):
     K.conv_dgrad(dy_cl, wt, dx, g, accumulate=True)
     torch.cuda.synchronize()
     assert rel_err(to_nc(dx), 2 * xd.grad) < 2e-5
+    # fused "gradient finish": (+ residual | + previous dx), ReLU mask by the layer input, TF32 rounding
+    res = rnd((N, T, H, W, Ci), 8).cuda()
+    mask = rnd((N, T, H, W, Ci), 9).cuda()
+    want = to_nc((to_cl(xd.grad.float()).cuda() + res) * (mask > 0))
+    dx2 = torch.full((N, T, H, W, Ci), float('nan'), device='cuda')
+    K.conv_dgrad(dy_cl, wt, dx2, g, residual=res, relu_mask=mask, tf32_out=True)
+    torch.cuda.synchronize()
+    assert rel_err(to_nc(dx2), want) < 6e-4                          # one TF32 rounding of the result
+    assert (dx2.view(torch.int32) & 0x1FFF).eq(0).all()              # low 13 mantissa bits cleared
+    assert (dx2[mask <= 0] == 0).all()
+    dx3 = res.clone()
+    K.conv_dgrad(dy_cl, wt, dx3, g, accumulate=True, relu_mask=mask, tf32_out=True)
+    torch.cuda.synchronize()
+    assert torch.equal(dx3, dx2)
     dw = torch.zeros((Co,) + ker + (Ci,), device='cuda')
     K.conv_wgrad(dy_cl, x_cl, dw, g)
     torch.cuda.synchronize()

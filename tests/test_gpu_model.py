@@ -149,6 +149,38 @@ def test_tiny_gradients_vs_tf32_emulating_oracle(ws):
         assert v < GRAD_L2_TOL and coss[k] > GRAD_COS_TOL, (k, v, coss[k])
 
 
+def test_grad_finish_fusion_and_graph_replay_agree_with_first_run(ws):
+    """Run 1 = separate ReLU-backward / rounding passes; run 2 = folded into the last dgrad GEMM's epilogue
+    (executor "grad finish" fusion); run 3+ = the captured CUDA graph.  Same arithmetic, so the gradients may
+    differ only by the order of the split-K atomics."""
+    from oracle import model as OM
+    from vlfb import executor as X
+    H.setup_cfg('ava_r50_lfb_nl.yaml', TINY)
+    ocfg = H.oracle_cfg('ava_r50_lfb_nl.yaml', TINY)
+    params = OM.make_params(ocfg, seed=2)
+    inputs = OM.make_inputs(ocfg, n_clips=2, rois_per_clip=2, crop=64, frames=8)
+    model, sfx = H.build('train', True)
+    H.feed_params(params)
+    H.feed_inputs(inputs, sfx)
+    net = ws.current().nets[model.net.Proto().name]
+    net.update_ops = []
+    runs = []
+    fuse0, X.FUSE_GRAD_FINISH = X.FUSE_GRAD_FINISH, True       # off by default (slower on B200), still supported
+    for rep in range(4):
+        n0 = X.STATS['fused_grad_finish']
+        ws.RunNet(model.net.Proto().name)
+        torch.cuda.synchronize()
+        if rep < 2:
+            assert (X.STATS['fused_grad_finish'] - n0 > 40) == (rep == 1)
+        runs.append(dict((n, ws.FetchBlob('gpu_0/' + n + '_grad').copy()) for n in model.TrainableParams()))
+    X.FUSE_GRAD_FINISH = fuse0
+    assert net._graphs is not None, 'the step should have been captured into a CUDA graph by now'
+    for rep in (1, 2, 3):
+        worst = max(float(np.abs(runs[rep][n] - runs[0][n]).max() / (np.abs(runs[0][n]).max() + 1e-12)) for n in runs[0])
+        print('run %d vs run 0: worst gradient difference %.2e' % (rep, worst))
+        assert worst < 2e-5, (rep, worst)
+
+
 def test_tiny_simt_engine_agrees(ws):
     """Same graph on the SIMT fp32 engine: isolates TF32 effects from logic errors."""
     _train_case(ws, 'ava_r50_lfb_nl.yaml', TINY, 64, 8, 2, backend='simt')

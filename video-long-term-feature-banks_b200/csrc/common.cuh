@@ -126,10 +126,11 @@ __device__ __forceinline__ void epilogue_store(const vlfb_gemm_params_t& p, int 
   if (p.row_scale) v *= p.row_scale[m];
   int64_t off = (int64_t)batch * p.d_batch_stride + (int64_t)tap * p.d_tap_stride + (int64_t)m * p.ldd + n;
   if (p.residual) v += p.residual[off];
+  if (p.flags & VLFB_EPI_ACCUM) v += p.d[off];
   if (p.flags & VLFB_EPI_RELU) v = fmaxf(v, 0.f);
+  if (p.relu_mask && !(p.relu_mask[off] > 0.f)) v = 0.f;
   if (p.flags & VLFB_EPI_TF32) v = round_tf32(v);
   if (p.flags & VLFB_EPI_ATOMIC) atomicAdd(p.d + off, v);
-  else if (p.flags & VLFB_EPI_ACCUM) p.d[off] += v;
   else p.d[off] = v;
 }
 

@@ -30,9 +30,11 @@ namespace tc {
 
 constexpr int BM = 128;        // tile rows (UMMA M)
 constexpr int KC = 32;         // fp32 per K chunk (128 B)
-constexpr int NPROD = 256;     // producer / epilogue threads: 8 warps = 2 per scheduler, so the address-
-                               // generation ALU latency of one warp hides behind the other (ncu r01: with one
-                               // producer warp per scheduler 'wait'+'selected' stalls dominated, no unit >14% busy)
+constexpr int NPROD = 256;     // 8 producer warps = 2 per scheduler, so the address-generation latency of one warp
+                               // hides behind the other (ncu r01: with one producer warp per scheduler 'wait' +
+                               // 'selected' stalls dominated).  Measured alternatives (profiles/r01_perf_log.md):
+                               // 7 producer warps (16 warps total -> 128 instead of 96 registers, no spills) lose
+                               // 3-5% of the step on the gather-bound convs; 4 epilogue warps lose ~4%.
 constexpr int NPW = NPROD / 32;
 constexpr int RSTEP = NPROD / 8;   // rows covered by one pass of the K-major loaders
 constexpr int NEPI = 256;          // 8 epilogue warps (two per TMEM lane quarter, splitting the column blocks)
@@ -508,7 +510,7 @@ __device__ __forceinline__ TileInfo decode_tile(const vlfb_gemm_params_t& p, con
 // (t = blockIdx.x, += gridDim.x).  The smem ring (full/empty) runs continuously across tiles and the TMEM
 // accumulator is double-buffered (tmem_full/tmem_empty), so the epilogue of tile i overlaps the loads and
 // MMAs of tile i+1.
-template <int AK, int BK>
+template <int AK, int BK, bool MASK>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_params_t p, const Launch L,
                                                               const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB) {
@@ -674,6 +676,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
     const bool vec_ok = ((p.ldd & 3) == 0) && ((p.d_batch_stride & 3) == 0) && ((p.d_tap_stride & 3) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0) &&
                         (!p.residual || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) &&
+                        (!p.relu_mask || (reinterpret_cast<uintptr_t>(p.relu_mask) & 15) == 0) &&
                         !(p.residual && (p.flags & VLFB_EPI_ACCUM));
     const int col = (lane & 3) * 4;
     const bool want_res = (p.residual != nullptr) || (p.flags & VLFB_EPI_ACCUM);
@@ -696,6 +699,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
           if (m < p.M && n < p.N) prefetch_l2(res_src + noff + (int64_t)m * p.ldd + n);
         }
       }
+      if (MASK && t + (int)gridDim.x < total) {
+        const TileInfo tn = decode_tile(p, L, t + gridDim.x);
+        const int64_t noff = (int64_t)tn.batch * p.d_batch_stride + (int64_t)tn.tap * p.d_tap_stride;
+        const int segs = bn >> 5;
+        for (int idx = tid - (NPROD + 32); idx < BM * segs; idx += NEPI) {
+          const int row = idx / segs, seg = idx - row * segs;
+          const int m = tn.m0 + row, n = tn.n0 + seg * 32;
+          if (m < p.M && n < p.N) prefetch_l2(p.relu_mask + noff + (int64_t)m * p.ldd + n);
+        }
+      }
       // residual / accumulate operands are fetched one column block ahead (register double buffer): with only
       // 8 epilogue warps per SM the loads must be in flight while the previous block is stored, otherwise the
       // epilogue is DRAM-latency bound (Little's law) instead of bandwidth bound
@@ -709,8 +722,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
           if (ok && m < p.M) r[i] = ld_nc_f4(res_src + tile_off + (int64_t)m * p.ldd + n);
         }
       };
+      // ReLU mask (backward of the ReLU that produced this GEMM's D-shaped input): fetched one block ahead like
+      // the residual, but AFTER the accumulator block has left the registers and packed to 16 bits as soon as
+      // it arrives, so that it never coexists with v[] / both residual buffers (the kernel is capped at 96
+      // registers; holding it as 4 more float4 spilled the whole epilogue loop -- measured 1.5-2.8x slower).
+      auto load_mask = [&](int c0, float4* mk) {
+        const int n = ti.n0 + c0 + col;
+        const bool ok = vec_ok && c0 < bn && n + 3 < p.N;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int m = ti.m0 + quarter * 32 + (lane >> 2) + 8 * i;
+          mk[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (ok && m < p.M) mk[i] = ld_nc_f4(p.relu_mask + tile_off + (int64_t)m * p.ldd + n);
+        }
+      };
+      auto pack_mask = [](const float4* mk) {
+        uint32_t b = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          b |= ((mk[i].x > 0.f ? 1u : 0u) | (mk[i].y > 0.f ? 2u : 0u) | (mk[i].z > 0.f ? 4u : 0u) |
+                (mk[i].w > 0.f ? 8u : 0u)) << (4 * i);
+        return b;
+      };
+      uint32_t mbits = 0xFFFFu;
+      if (MASK) {
+        float4 mk[4];
+        load_mask(half * EPC, mk);
+        mbits = pack_mask(mk);
+      }
+      // MASK instantiations keep one residual buffer (register budget: 96/thread with 17 warps)
+      constexpr bool DB = !MASK;
       float4 rr[4], rn[4];
-      load_res(half * EPC, rr);                  // independent of the accumulator: issued before the wait
+      if (DB) load_res(half * EPC, rr);          // independent of the accumulator: issued before the wait
       if (ti.n0 != colv_n0) {
         // per-column affine of this warp's blocks -> shared memory, once per N tile (not per block: the
         // global-load latency used to sit in front of every block's first FFMA)
@@ -732,7 +775,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
       tc_fence_after();
       for (int c0 = half * EPC; c0 < bn; c0 += 2 * EPC) {
         if (ti.n0 + c0 >= p.N) break;            // warp-uniform
-        load_res(c0 + 2 * EPC, rn);
+        if (DB) load_res(c0 + 2 * EPC, rn);
+        else load_res(c0, rr);                   // L2-resident (tile-ahead prefetch); overlaps the TMEM load
         float v[EPC];
         tmem_ld16(lane_addr + c0, v);
         tmem_ld_wait();
@@ -741,6 +785,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
           *reinterpret_cast<float4*>(stg + lane * EPITCH + q * 4) =
               make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         __syncwarp();
+        float4 mk[4];
+        if (MASK) load_mask(c0 + 2 * EPC, mk);
         const int n = ti.n0 + c0 + col;
         const bool nfull = n + 3 < p.N;
         const int cvi = ((c0 - half * EPC) >> 1) + col;
@@ -757,9 +803,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
             o.x = (o.x * cs.x + cb.x) * rs[i]; o.y = (o.y * cs.y + cb.y) * rs[i];
             o.z = (o.z * cs.z + cb.z) * rs[i]; o.w = (o.w * cs.w + cb.w) * rs[i];
             const int64_t off = tile_off + (int64_t)m * p.ldd + n;
-            if (p.residual) { o.x += rr[i].x; o.y += rr[i].y; o.z += rr[i].z; o.w += rr[i].w; }
+            if (want_res) { o.x += rr[i].x; o.y += rr[i].y; o.z += rr[i].z; o.w += rr[i].w; }   // residual or D (ACCUM)
             if (p.flags & VLFB_EPI_RELU) {
               o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            }
+            if (MASK) {
+              const uint32_t mb = mbits >> (4 * i);
+              o.x = (mb & 1u) ? o.x : 0.f; o.y = (mb & 2u) ? o.y : 0.f;
+              o.z = (mb & 4u) ? o.z : 0.f; o.w = (mb & 8u) ? o.w : 0.f;
             }
             if (p.flags & VLFB_EPI_TF32) {
               o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
@@ -767,9 +818,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
             float* dst = p.d + off;
             if (p.flags & VLFB_EPI_ATOMIC) {
               atomicAdd(dst, o.x); atomicAdd(dst + 1, o.y); atomicAdd(dst + 2, o.z); atomicAdd(dst + 3, o.w);
-            } else if (p.flags & VLFB_EPI_ACCUM) {
-              *reinterpret_cast<float4*>(dst) =
-                  make_float4(rr[i].x + o.x, rr[i].y + o.y, rr[i].z + o.z, rr[i].w + o.w);
             } else {
               *reinterpret_cast<float4*>(dst) = o;
             }
@@ -781,8 +829,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
           }
         }
         __syncwarp();
+        if (MASK) mbits = pack_mask(mk);
+        if (DB) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) rr[i] = rn[i];
+          for (int i = 0; i < 4; ++i) rr[i] = rn[i];
+        }
       }
       // every TMEM read of this accumulator has completed (tcgen05.wait::ld above): hand it back to the MMA warp
       tc_fence_before();
@@ -863,7 +914,7 @@ static Env read_env() {
   return e;
 }
 
-template <int AK, int BK>
+template <int AK, int BK, bool MASK>
 int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
   vlfb_gemm_params_t p = p_in;       // split_k == 0 is resolved below
   Launch L;
@@ -922,7 +973,7 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
   const int smem = L.stages * stage_bytes + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AK, BK, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
@@ -939,7 +990,7 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
             (AK == VLFB_OP_DENSE_MN && mn_tma && make_tmap_mn(&tmA, p.a, p.M, p.K, p.batch)) ? 1 : 0;
   L.tma_b = (BK == VLFB_OP_DENSE_K && make_tmap(&tmB, p.b, p.N, p.K, p.batch, L.bn)) ||
             (BK == VLFB_OP_DENSE_MN && mn_tma && make_tmap_mn(&tmB, p.b, p.N, p.K, p.batch)) ? 1 : 0;
-  gemm_tc_kernel<AK, BK><<<grid, NTHREADS, smem, stream>>>(p, L, tmA, tmB);
+  gemm_tc_kernel<AK, BK, MASK><<<grid, NTHREADS, smem, stream>>>(p, L, tmA, tmB);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -948,7 +999,14 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
 
 int gemm_tc(const vlfb_gemm_params_t& p, cudaStream_t stream) {
   const int ak = p.a.kind, bk = p.b.kind;
-#define VLFB_TC_CASE(A, B) if (ak == A && bk == B) return tc::launch<A, B>(p, stream)
+  if (p.relu_mask) {
+    // ReLU-backward mask: only the dgrad shapes need it (two more instantiations, not eighteen)
+    if (ak == VLFB_OP_DGRAD_K && bk == VLFB_OP_DENSE_K) return tc::launch<VLFB_OP_DGRAD_K, VLFB_OP_DENSE_K, true>(p, stream);
+    if (ak == VLFB_OP_DENSE_K && bk == VLFB_OP_DENSE_K) return tc::launch<VLFB_OP_DENSE_K, VLFB_OP_DENSE_K, true>(p, stream);
+    set_error("vlfb_gemm: relu_mask is supported for DGRAD_K/DENSE_K x DENSE_K operands only (tensor-core engine)");
+    return VLFB_E_BADARG;
+  }
+#define VLFB_TC_CASE(A, B) if (ak == A && bk == B) return tc::launch<A, B, false>(p, stream)
   VLFB_TC_CASE(VLFB_OP_CONV_K, VLFB_OP_DENSE_K);
   VLFB_TC_CASE(VLFB_OP_STEM_K, VLFB_OP_DENSE_K);
   VLFB_TC_CASE(VLFB_OP_DGRAD_K, VLFB_OP_DENSE_K);

@@ -15,6 +15,8 @@ Representation
 """
 import math
 
+import os
+
 import torch
 
 from . import kernels as K_default
@@ -22,6 +24,13 @@ from . import kernels as K_default
 K = K_default          # tests may swap in a torch-CPU kernel set (tests/fake_kernels.py)
 DEVICE = 'cuda'
 DTYPE = torch.float32      # the CUDA kernels are fp32-only; the CPU test stand-in may run the host logic in fp64
+STATS = {'fused_grad_finish': 0}
+# Fold the ReLU backward + TF32 rounding of a conv's incoming gradient (and the sum of its earlier contributions)
+# into the epilogue of the dgrad GEMM that delivers the last contribution.  Exact (tests run both ways), but OFF by
+# default: measured on B200 the step is 2-3% SLOWER with it (19.0 vs 18.6 ms) -- the 8 epilogue warps of the
+# persistent GEMM hide the two extra operand streams far worse than the bandwidth-bound elementwise kernels they
+# replace (profiles/r01_perf_log.md).  Revisit once residual/mask tiles are staged by TMA.
+FUSE_GRAD_FINISH = os.environ.get('VLFB_FUSE_GRAD_FINISH', '0') == '1'
 
 
 def set_backend(kernels_module, device, dtype=torch.float32):
@@ -56,6 +65,13 @@ def phys(t):
     assert p.is_contiguous(), 'blob is not channels-last contiguous: shape %s strides %s' % (
         tuple(t.shape), tuple(t.stride()))
     return p
+
+
+def is_cl(t):
+    """True when phys(t) would succeed."""
+    if t.dim() <= 2:
+        return t.is_contiguous()
+    return t.permute([0] + list(range(2, t.dim())) + [1]).is_contiguous()
 
 
 def flat(t):
@@ -103,6 +119,12 @@ class Ctx(object):
         self.grads = {}
         self.owned = {}
         self.saved = {}
+        # gradient-finalisation fusion: `counts` = contributions each key received so far in this run;
+        # net.contrib (recorded by the first run of the net) = how many it receives in total, so the LAST
+        # contributor can be recognised; `final` = keys whose gradient already got its producer's ReLU mask
+        # and TF32 rounding from that last contributor's GEMM epilogue.
+        self.counts = {}
+        self.final = set()
 
     # ---- blobs
     def get(self, name):
@@ -125,9 +147,22 @@ class Ctx(object):
         return r
 
     # ---- grads
+    def is_last_contribution(self, key):
+        total = self.net.contrib.get(key) if self.net.contrib is not None else None
+        return total is not None and self.counts.get(key, 0) == total - 1
+
+    def set_final_grad(self, key, g):
+        """The last contribution, already summed with the earlier ones, masked and rounded."""
+        self.counts[key] = self.counts.get(key, 0) + 1
+        self.grads[key] = g
+        self.owned[key] = True
+        self.final.add(key)
+
     def add_grad(self, key, g, owned):
         if not self.net.requires.get(key, False):
             return
+        assert key not in self.final, 'gradient of %s was finalised before its last contribution' % (key,)
+        self.counts[key] = self.counts.get(key, 0) + 1
         cur = self.grads.get(key)
         if cur is None:
             self.grads[key] = g
@@ -206,16 +241,24 @@ class ConvStep(Step):
 
     def bwd(self, ctx):
         # the gradient is a GEMM operand of dgrad/wgrad: mask (ReLU) and round it to TF32 in one pass
-        gy = ctx.pop_grad_owned(self.out_keys[0])
-        if gy is None:
-            return
-        xp, g = ctx.saved.pop(id(self))
-        gp = as5d(phys(gy))
-        if self.relu:
-            y = phys(ctx.get(self.out))
-            K.relu_bwd_tf32(flat(gp), flat(y), flat(gp))
+        okey = self.out_keys[0]
+        if okey in ctx.final:
+            # masked + rounded by the dgrad GEMM that delivered the last contribution
+            ctx.final.discard(okey)
+            gy = ctx.pop_grad(okey)
+            xp, g = ctx.saved.pop(id(self))
+            gp = as5d(phys(gy))
         else:
-            K.round_tf32(flat(gp), flat(gp))
+            gy = ctx.pop_grad_owned(okey)
+            if gy is None:
+                return
+            xp, g = ctx.saved.pop(id(self))
+            gp = as5d(phys(gy))
+            if self.relu:
+                y = phys(ctx.get(self.out))
+                K.relu_bwd_tf32(flat(gp), flat(y), flat(gp))
+            else:
+                K.round_tf32(flat(gp), flat(gp))
         if self.res_key is not None:
             ctx.add_grad(self.res_key, gy, owned=False)
         scale = ctx.ws.params.phys(self.affine[0]) if self.affine else None
@@ -240,7 +283,26 @@ class ConvStep(Step):
             wt = empty((g.C, taps, g.Co))
             K.weight_transpose(store.phys(self.w), wt, scale)     # wt = round_tf32(w * s)
             cur = ctx.grads.get(xkey)
-            if cur is not None and ctx.owned.get(xkey, False):
+            prod = ctx.net.producer.get(xkey)
+            if (isinstance(prod, ConvStep) and ctx.is_last_contribution(xkey) and FUSE_GRAD_FINISH
+                    and (cur is None or (is_cl(cur) and as5d(phys(cur)).shape == xp.shape))):
+                # Last contribution to the gradient of a conv output: sum the earlier contributions, apply that
+                # conv's ReLU backward (mask = its output = our input xp) and the TF32 rounding its own
+                # dgrad / wgrad GEMMs need -- all in this GEMM's epilogue (saves ~6 passes over the tensor).
+                mask = xp if prod.relu else None
+                if cur is not None and ctx.owned.get(xkey, False):
+                    dx = cur
+                    K.conv_dgrad(gp, wt, as5d(phys(cur)), g, accumulate=True, relu_mask=mask, tf32_out=True)
+                else:
+                    dx = cl_alloc((g.N, g.C, g.T, g.H, g.W))
+                    if dx.shape != ctx.get(self.x).shape:
+                        dx = dx.view(ctx.get(self.x).shape)
+                    K.conv_dgrad(gp, wt, as5d(phys(dx)), g, residual=None if cur is None else as5d(phys(cur)),
+                                 relu_mask=mask, tf32_out=True)
+                ctx.set_final_grad(xkey, dx)
+                STATS['fused_grad_finish'] += 1
+            elif cur is not None and ctx.owned.get(xkey, False):
+                ctx.counts[xkey] = ctx.counts.get(xkey, 0) + 1
                 K.conv_dgrad(gp, wt, as5d(phys(cur)), g, accumulate=True)
             else:
                 dx = cl_alloc((g.N, g.C, g.T, g.H, g.W))
@@ -714,6 +776,11 @@ class CompiledNet(object):
         if self.losses:
             self._analyse()
         self.num_launch_groups = len(self.steps)
+        self.producer = {}
+        for st in self.steps:
+            for k in st.out_keys:
+                self.producer[k] = st
+        self.contrib = None          # key -> number of gradient contributions, recorded by the first eager run
         produced = set()
         self.external_inputs = []
         for op in ops:
@@ -868,6 +935,10 @@ class CompiledNet(object):
                 st.bwd(ctx)
             elif any(k in ctx.grads for k in st.out_keys):
                 st.bwd(ctx)
+        if self.contrib is None:
+            self.contrib = dict(ctx.counts)
+        else:
+            assert self.contrib == ctx.counts, 'gradient contribution counts changed between runs'
 
     def run(self):
         """One pass.  Eager for the first runs of a given input signature; after that the whole

@@ -165,8 +165,11 @@ def conv_fwd(x, w, y, g, scale=None, bias=None, residual=None, relu=False, tf32_
     _run_gemm(p, 'conv_fwd', 2.0 * M * g.Co * g.kT * g.kH * g.kW * (3 if g.C == 4 else g.C))
 
 
-def conv_dgrad(dy, wt, dx, g, accumulate=False):
-    """dx (+)= conv_transpose(dy, w).  wt [C, kT,kH,kW, Co] (see weight_transpose), dx [N,T,H,W,C]."""
+def conv_dgrad(dy, wt, dx, g, accumulate=False, residual=None, relu_mask=None, tf32_out=False):
+    """dx = finish(conv_transpose(dy, w) [+ dx if accumulate] [+ residual]).  wt [C, kT,kH,kW, Co] (see
+    weight_transpose), dx [N,T,H,W,C].  finish = the backward of the ReLU that produced this layer's input
+    (relu_mask = that activation, dx zeroed where it is <= 0) and the TF32 rounding the next GEMM needs: when
+    this GEMM is the last contribution to the gradient, both are done here instead of in two more passes."""
     _f32c(dy, 'dy'), _f32c(wt, 'wt'), _f32c(dx, 'dx')
     assert tuple(dy.shape) == out_shape(g) and tuple(dx.shape) == (g.N, g.T, g.H, g.W, g.C)
     M = g.N * g.T * g.H * g.W
@@ -182,6 +185,14 @@ def conv_dgrad(dy, wt, dx, g, accumulate=False):
     p.g = g
     if accumulate:
         p.flags |= L.EPI_ACCUM
+    if residual is not None:
+        assert tuple(residual.shape) == tuple(dx.shape)
+        p.residual = _f32c(residual, 'residual').data_ptr()
+    if relu_mask is not None:
+        assert tuple(relu_mask.shape) == tuple(dx.shape)
+        p.relu_mask = _f32c(relu_mask, 'relu_mask').data_ptr()
+    if tf32_out:
+        p.flags |= L.EPI_TF32
     # algorithmic dgrad work = forward MACs of the same layer
     _run_gemm(p, 'conv_dgrad', 2.0 * g.N * g.To * g.Ho * g.Wo * g.Co * g.kT * g.kH * g.kW * g.C)
 

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, '..', '..', 'csrc', 'libvlfb.so'))
+LIB_PATH = os.environ.get('VLFB_LIB') or os.path.normpath(os.path.join(_HERE, '..', '..', 'csrc', 'libvlfb.so'))   # VLFB_LIB: kernel-variant experiments (scripts/)
 
 OP_DENSE_K, OP_DENSE_MN, OP_CONV_K, OP_DGRAD_K, OP_CONV_MN, OP_STEM_K, OP_STEM_MN = range(7)
 EPI_RELU, EPI_ACCUM, EPI_ATOMIC, EPI_TF32 = 1, 2, 4, 8
@@ -30,7 +30,7 @@ class GemmParams(C.Structure):
                 ('d', C.c_void_p), ('ldd', C.c_int64), ('d_batch_stride', C.c_int64),
                 ('d_tap_stride', C.c_int64), ('alpha', C.c_float),
                 ('col_scale', C.c_void_p), ('col_bias', C.c_void_p), ('row_scale', C.c_void_p),
-                ('residual', C.c_void_p), ('flags', C.c_int)]
+                ('residual', C.c_void_p), ('relu_mask', C.c_void_p), ('flags', C.c_int)]
 
 
 _P, _I, _L, _F, _U = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
