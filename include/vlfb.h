@@ -39,6 +39,9 @@ const char* vlfb_last_error(void);      /* thread-local message of the last fail
  * 1 = SIMT fp32 debug kernel (bring-up / on-GPU cross-check only). */
 int vlfb_set_gemm_backend(int backend);
 int vlfb_get_gemm_backend(void);
+/* Programmatic dependent launch of every kernel of the library (default off; env VLFB_PDL=1 enables): each
+ * kernel's launch and prologue overlap the tail of its predecessor in the stream. */
+int vlfb_set_pdl(int enabled);
 
 /* ---- gathered GEMM: D[m,n] = epi( sum_k A[m,k] * B[n,k] ) ------------------------------ */
 /* One descriptor per operand.  `kind`:

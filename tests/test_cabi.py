@@ -31,9 +31,20 @@ def test_argument_validation_without_gpu():
     assert lib.vlfb_relu_fwd(None, None, 4, None) == -1
 
 
-def test_struct_layout_matches_header():
+def test_struct_layout_matches_header(tmp_path):
+    """sizeof / offsetof of the C structs, as the C compiler sees include/vlfb.h, equal the ctypes mirror."""
+    import subprocess
     from vlfb import libvlfb as L
-    assert ctypes.sizeof(L.ConvGeom) == 21 * 4
-    assert ctypes.sizeof(L.Operand) == 32
-    # a, b, g, 6 ints, d, 3 int64, alpha(+pad), 4 pointers, flags(+pad)
-    assert ctypes.sizeof(L.GemmParams) == 32 + 32 + 84 + 4 + 24 + 8 + 24 + 8 + 32 + 8
+    fields = ['a', 'b', 'g', 'M', 'split_k', 'd', 'ldd', 'alpha', 'col_scale', 'residual', 'relu_mask', 'flags']
+    src = tmp_path / 'layout.c'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vlfb.h"\nint main(void) {\n'
+                   '  printf("%zu %zu %zu\\n", sizeof(vlfb_conv_geom_t), sizeof(vlfb_operand_t), sizeof(vlfb_gemm_params_t));\n'
+                   + ''.join('  printf("%%zu\\n", offsetof(vlfb_gemm_params_t, %s));\n' % f for f in fields)
+                   + '  return 0;\n}\n')
+    exe = tmp_path / 'layout'
+    subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    sizes, offs = [int(v) for v in out[:3]], [int(v) for v in out[3:]]
+    assert sizes == [ctypes.sizeof(L.ConvGeom), ctypes.sizeof(L.Operand), ctypes.sizeof(L.GemmParams)]
+    assert offs == [getattr(L.GemmParams, f).offset for f in fields]
+

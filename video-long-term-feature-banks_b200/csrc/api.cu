@@ -1,5 +1,6 @@
 // C-ABI surface of libvlfb.so: argument validation + dispatch (see include/vlfb.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -8,6 +9,14 @@ namespace vlfb {
 
 static thread_local char g_err[512] = "";
 static int g_backend = 0;
+static int g_pdl = -1;          // -1: read VLFB_PDL on first use
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("VLFB_PDL");
+    g_pdl = (e && atoi(e) != 0) ? 1 : 0;      // default off: measured no gain inside the captured step (r01_perf_log)
+  }
+  return g_pdl != 0;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -94,6 +103,10 @@ int vlfb_set_gemm_backend(int backend) {
   return VLFB_OK;
 }
 int vlfb_get_gemm_backend(void) { return g_backend; }
+int vlfb_set_pdl(int enabled) {
+  g_pdl = enabled ? 1 : 0;
+  return VLFB_OK;
+}
 
 int vlfb_gemm(const vlfb_gemm_params_t* p, void* stream) {
   VLFB_CHECK_ARG(p != nullptr);

@@ -10,6 +10,7 @@ namespace {
 constexpr int TM = 32, TN = 32, TK = 16;
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const vlfb_gemm_params_t p) {
+  pdl_prologue();
   __shared__ float sa[TK][TM + 1];
   __shared__ float sb[TK][TN + 1];
   const int z = blockIdx.z;
@@ -58,7 +59,7 @@ int gemm_simt(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
   vlfb_gemm_params_t p = p_in;
   if (p.split_k == 0) p.split_k = p.K >= 2048 ? (p.K / 1024 < 32 ? p.K / 1024 : 32) : 1;   // "library's choice"
   dim3 grid(ceil_div(p.M, TM), ceil_div(p.N, TN), (p.taps > 1 ? p.taps : p.batch) * p.split_k);
-  gemm_simt_kernel<<<grid, 256, 0, stream>>>(p);
+  launch_k(gemm_simt_kernel, grid, 256, 0, stream, p);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }

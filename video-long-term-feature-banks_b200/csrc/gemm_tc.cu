@@ -231,6 +231,20 @@ __device__ __forceinline__ Pos4 decode_pos_fast(uint32_t idx, const PosDiv& pd) 
   return p;
 }
 
+// TMA im2col mode (measured semantics: profiles/r01_im2col_probe.txt): the 5-D map of an NDHWC tensor walks
+// `pixelsPerColumn` window origins in W -> H -> D -> N order inside the bounding box [lower, dim-1+upper] with the
+// convolution strides as traversal strides; {w,h,d} = origin of the first window (= out*stride - pad), the u16
+// offsets select the filter tap (tap*dilation); out-of-range pixels (padding, tensor tail) read as zeros.
+__device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap* tm, int c, int w, int h, int d, int n,
+                                                int ow, int oh, int od, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4, %5, %6}], [%7], {%8, %9, %10};"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "r"(bar),
+        "h"((uint16_t)ow), "h"((uint16_t)oh), "h"((uint16_t)od)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- K-major loaders
 // Tile = `rows` rows x 128 B.  Thread t copies the 16-byte chunk (t & 7) of rows (t >> 3) + RSTEP j.
 template <int KIND, int MAXR>
@@ -477,7 +491,7 @@ struct Launch {
   PosDiv in;     // ... and of the INPUT extents (W, H, T) for the dgrad row decode
   FastDiv cdiv;  // input channels C (wgrad: n -> (tap, ci))
   FastDiv kwdiv; // kW
-  int tma_a, tma_b;  // operand fetched by TMA (dense K-major 2-D tiles) instead of cp.async
+  int tma_a, tma_b;  // operand fetched by TMA instead of cp.async: 1 = dense tiled boxes, 2 = im2col (conv gathers)
   int lag;           // cp.async groups kept in flight before a stage is published (< stages)
   int tiles_m, tiles_n, total_tiles;
   int fence_mode;    // 0: producers fence.proxy.async before publishing a stage; 1: the MMA thread fences after acquiring it
@@ -549,6 +563,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tptr_generic;
+  // Everything above touched only shared memory / TMEM: it overlaps the tail of the previous kernel (PDL).
+  pdl_prologue();
 
   if (warp < NPW) {
     // ============================ PRODUCERS (8 warps) ============================
@@ -558,7 +574,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
       KLoader<is_mn(BK) ? VLFB_OP_DENSE_K : BK, 256 / RSTEP> kb;
       MNLoader<is_mn(BK) ? BK : VLFB_OP_DENSE_MN> mb;
       const int LAG = L.lag;
-      const uint32_t tma_bytes = (tma_a ? (uint32_t)A_TILE_BYTES : 0u) + (tma_b ? b_tile_bytes : 0u);
+      const bool im2col_a = L.tma_a == 2, im2col_b = L.tma_b == 2;
+      // im2col state of the issuing thread: window origin of the tile's first row + filter-tap cursor (A), and
+      // per 32-column atom the channel slice / tap offsets of the wgrad B tile
+      int ia_w = 0, ia_h = 0, ia_d = 0, ia_n = 0, ic_t = 0, ic_h = 0, ic_w = 0, ic_c = 0, icpt = 1;
+      int ib_c[8], ib_off[8], ib_atoms = 0;
       // chunk counter over the CTA's whole tile sequence; ring slot / phase / lagged slot advance
       // incrementally (S is a run-time value: `it % S` cost three integer divisions per chunk per thread)
       int it = 0, s = 0, sl = 0;
@@ -571,6 +591,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
           if (!tma_b) { if (is_mn(BK)) mb.init(p, p.b, ti.n0, bn, p.N, ti.batch, ti.tap, L.cdiv, L.kwdiv); else { kb.init(p, p.b, ti.n0, bn, p.N, ti.batch, L.out, L.in, ti.k_begin / KC); kb.kend = ti.k_end; } }
         }
         const int kc0 = ti.k_begin / KC;
+        uint32_t tma_bytes = (tma_a ? (uint32_t)A_TILE_BYTES : 0u) + (tma_b ? b_tile_bytes : 0u);
+        if (tid == 0 && im2col_a) {
+          const vlfb_conv_geom_t& g = p.g;
+          if (AK == VLFB_OP_CONV_K) {
+            const Pos4 o = decode_pos_fast((uint32_t)ti.m0, L.out);
+            ia_w = o.w * g.sW - g.pW; ia_h = o.h * g.sH - g.pH; ia_d = o.t * g.sT - g.pT; ia_n = o.n;
+            icpt = g.C / KC;
+          } else {  // DGRAD_K, unit strides: dx[i] = sum_tap dy[i + pad - tap*dil] -> origin i + pad - (k-1)*dil
+            const Pos4 o = decode_pos_fast((uint32_t)ti.m0, L.in);
+            ia_w = o.w + g.pW - (g.kW - 1) * g.dW; ia_h = o.h + g.pH - (g.kH - 1) * g.dH;
+            ia_d = o.t + g.pT - (g.kT - 1) * g.dT; ia_n = o.n;
+            icpt = g.Co / KC;
+          }
+          const int tap = kc0 / icpt;
+          ic_c = kc0 - tap * icpt;
+          decode_tap(tap, g.kH, g.kW, ic_t, ic_h, ic_w);
+        }
+        if (tid == 0 && im2col_b) {
+          const vlfb_conv_geom_t& g = p.g;
+          ib_atoms = 0;
+#pragma unroll
+          for (int a = 0; a < 8; ++a) {
+            const int ncol = ti.n0 + a * 32;
+            if (a * 32 < bn && ncol < p.N) {
+              uint32_t tap_hw, ci, qh, qw;
+              fd_divmod((uint32_t)ncol, L.cdiv, tap_hw, ci);       // n = (kh*kW + kw) * C + ci
+              fd_divmod(tap_hw, L.kwdiv, qh, qw);
+              ib_c[a] = (int)ci;
+              ib_off[a] = ((int)qh * g.dH << 16) | ((int)qw * g.dW);
+              ib_atoms = a + 1;
+            }
+          }
+          tma_bytes = (tma_a ? (uint32_t)A_TILE_BYTES : 0u) + 4096u * (uint32_t)ib_atoms;
+        }
         for (int i = 0; i < ti.nk; ++i, ++it) {
           if (it >= S) mbar_wait(empty0 + 8 * s, ph ^ 1u);
           const int s_cur = s;
@@ -579,7 +633,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
           const uint32_t b_tile = a_tile + A_TILE_BYTES;
           if (tid == 0 && tma_bytes) {
             mbar_expect_tx(full0 + 8 * s_cur, tma_bytes);
-            if (tma_a) {
+            if (im2col_a) {
+              const vlfb_conv_geom_t& g = p.g;
+              if (AK == VLFB_OP_CONV_K)
+                tma_load_im2col(a_tile, &tmA, ic_c * KC, ia_w, ia_h, ia_d, ia_n, ic_w * g.dW, ic_h * g.dH, ic_t * g.dT,
+                                full0 + 8 * s_cur);
+              else
+                tma_load_im2col(a_tile, &tmA, ic_c * KC, ia_w, ia_h, ia_d, ia_n, (g.kW - 1 - ic_w) * g.dW,
+                                (g.kH - 1 - ic_h) * g.dH, (g.kT - 1 - ic_t) * g.dT, full0 + 8 * s_cur);
+              if (++ic_c == icpt) {
+                ic_c = 0;
+                if (++ic_w == g.kW) { ic_w = 0; if (++ic_h == g.kH) { ic_h = 0; ++ic_t; } }
+              }
+            } else if (tma_a) {
               if (is_mn(AK)) {
                 for (int a = 0; a < BM / 32; ++a)
                   tma_load_3d(a_tile + a * 4096, &tmA, ti.m0 + a * 32, ti.k_begin + i * KC, ti.batch, full0 + 8 * s_cur);
@@ -587,7 +653,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
                 tma_load_3d(a_tile, &tmA, (kc0 + i) * KC, ti.m0, ti.batch, full0 + 8 * s_cur);
               }
             }
-            if (tma_b) {
+            if (im2col_b) {
+              // wgrad B tile: 32 output positions (k rows) x one (kh, kw, 32-channel) atom per copy
+              const vlfb_conv_geom_t& g = p.g;
+              const Pos4 o = decode_pos_fast((uint32_t)(ti.k_begin + i * KC), L.out);
+              const int bw = o.w * g.sW - g.pW, bh = o.h * g.sH - g.pH, bd = o.t * g.sT - g.pT;
+#pragma unroll
+              for (int a = 0; a < 8; ++a)
+                if (a < ib_atoms)
+                  tma_load_im2col(b_tile + a * 4096, &tmB, ib_c[a], bw, bh, bd, o.n, ib_off[a] & 0xFFFF, ib_off[a] >> 16,
+                                  ti.tap * g.dT, full0 + 8 * s_cur);
+            } else if (tma_b) {
               if (is_mn(BK)) {
                 for (int a = 0; a < bn / 32; ++a)
                   tma_load_3d(b_tile + a * 4096, &tmB, ti.n0 + a * 32, ti.k_begin + i * KC, ti.batch, full0 + 8 * s_cur);
@@ -901,8 +977,37 @@ static bool make_tmap_mn(CUtensorMap* tm, const vlfb_operand_t& op, int extent, 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 5-D im2col map of an NDHWC fp32 tensor [N, D, H, W, C]: `pixels` window origins x 32 channels per copy.
+// lower/upper = bounding-box corners {W, H, D}; strides = traversal strides {W, H, D}.
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+static bool make_tmap_im2col(CUtensorMap* tm, const float* base, int N, int D, int H, int W, int C, const int lower[3],
+                             const int upper[3], const int strides[3], int pixels, CUtensorMapSwizzle swz) {
+  static EncodeIm2colFn enc = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (encode_fn() && cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      enc = reinterpret_cast<EncodeIm2colFn>(ptr);
+  }
+  if (!enc || (C % KC) != 0 || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+  for (int i = 0; i < 3; ++i)
+    if (lower[i] < -16 || lower[i] > 15 || upper[i] < -16 || upper[i] > 15 || strides[i] < 1 || strides[i] > 8) return false;
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t gstr[4] = {(cuuint64_t)C * 4, (cuuint64_t)C * 4 * W, (cuuint64_t)C * 4 * W * H, (cuuint64_t)C * 4 * W * H * D};
+  cuuint32_t estr[5] = {1, (cuuint32_t)strides[0], (cuuint32_t)strides[1], (cuuint32_t)strides[2], 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, gstr, lower, upper, KC,
+             (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // tuning overrides, read once (scripts/tune_gemm.py)
-struct Env { int bn, stages, lag, fence; bool tma_mn; };
+struct Env { int bn, stages, lag, fence; bool tma_mn, im2col; };
 static Env read_env() {
   Env e;
   auto geti = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
@@ -911,6 +1016,7 @@ static Env read_env() {
   e.lag = geti("VLFB_LAG", 0);
   e.fence = geti("VLFB_FENCE", 0);
   e.tma_mn = geti("VLFB_TMA_MN", 1) != 0;
+  e.im2col = geti("VLFB_IM2COL", 1) != 0;
   return e;
 }
 
@@ -990,7 +1096,28 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
             (AK == VLFB_OP_DENSE_MN && mn_tma && make_tmap_mn(&tmA, p.a, p.M, p.K, p.batch)) ? 1 : 0;
   L.tma_b = (BK == VLFB_OP_DENSE_K && make_tmap(&tmB, p.b, p.N, p.K, p.batch, L.bn)) ||
             (BK == VLFB_OP_DENSE_MN && mn_tma && make_tmap_mn(&tmB, p.b, p.N, p.K, p.batch)) ? 1 : 0;
-  gemm_tc_kernel<AK, BK, MASK><<<grid, NTHREADS, smem, stream>>>(p, L, tmA, tmB);
+  if (env.im2col) {
+    // conv gathers as TMA im2col copies: one instruction per K chunk instead of 1024 16-byte cp.asyncs
+    const vlfb_conv_geom_t& g = p.g;
+    const int pad_lo[3] = {-g.pW, -g.pH, -g.pT};
+    const int pad_hi[3] = {g.pW - (g.kW - 1) * g.dW, g.pH - (g.kH - 1) * g.dH, g.pT - (g.kT - 1) * g.dT};
+    const int cstr[3] = {g.sW, g.sH, g.sT};
+    const int ones[3] = {1, 1, 1};
+    if (AK == VLFB_OP_CONV_K &&
+        make_tmap_im2col(&tmA, p.a.ptr, g.N, g.T, g.H, g.W, g.C, pad_lo, pad_hi, cstr, BM, CU_TENSOR_MAP_SWIZZLE_128B))
+      L.tma_a = 2;
+    if (AK == VLFB_OP_DGRAD_K && g.sT == 1 && g.sH == 1 && g.sW == 1) {
+      const int lo[3] = {g.pW - (g.kW - 1) * g.dW, g.pH - (g.kH - 1) * g.dH, g.pT - (g.kT - 1) * g.dT};
+      const int hi[3] = {-g.pW, -g.pH, -g.pT};
+      if (make_tmap_im2col(&tmA, p.a.ptr, g.N, g.To, g.Ho, g.Wo, g.Co, lo, hi, ones, BM, CU_TENSOR_MAP_SWIZZLE_128B))
+        L.tma_a = 2;
+    }
+    if (BK == VLFB_OP_CONV_MN && (g.C % KC) == 0 && L.tma_a &&
+        make_tmap_im2col(&tmB, p.b.ptr, g.N, g.T, g.H, g.W, g.C, pad_lo, pad_hi, cstr, KC,
+                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+      L.tma_b = 2;
+  }
+  launch_k(gemm_tc_kernel<AK, BK, MASK>, grid, dim3(NTHREADS), (size_t)smem, stream, p, L, tmA, tmB);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }

@@ -48,6 +48,7 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // ------------------------------------------------------------------ AffineNd
 __global__ void affine_fwd_k(const float4* __restrict__ x, const float4* __restrict__ s, const float4* __restrict__ b,
                              float4* __restrict__ y, int64_t n4, int c4) {
+  pdl_prologue();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % c4);
     const float4 v = x[i], sc = s[c];
@@ -65,6 +66,7 @@ __global__ void affine_fwd_k(const float4* __restrict__ x, const float4* __restr
 // ------------------------------------------------------------------ pooling
 __global__ void maxpool_fwd_k(const float* __restrict__ x, float* __restrict__ y, int32_t* __restrict__ arg,
                               const vlfb_conv_geom_t g, int64_t total) {
+  pdl_prologue();
   const int c4 = g.C >> 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % c4) * 4;
@@ -96,6 +98,7 @@ __global__ void maxpool_fwd_k(const float* __restrict__ x, float* __restrict__ y
 
 __global__ void maxpool_bwd_k(const float* __restrict__ dy, const int32_t* __restrict__ arg, float* __restrict__ dx,
                               int C, int64_t total) {
+  pdl_prologue();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int pos = arg[i];
     if (pos >= 0) atomicAdd(dx + (int64_t)pos * C + (i % C), dy[i]);
@@ -104,6 +107,7 @@ __global__ void maxpool_bwd_k(const float* __restrict__ dy, const int32_t* __res
 
 __global__ void avgpool_fwd_k(const float* __restrict__ x, float* __restrict__ y, const vlfb_conv_geom_t g,
                               int64_t total) {
+  pdl_prologue();
   const int c4 = g.C >> 2;
   const float inv = 1.f / (float)(g.kT * g.kH * g.kW);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -124,6 +128,7 @@ __global__ void avgpool_fwd_k(const float* __restrict__ x, float* __restrict__ y
 
 __global__ void avgpool_bwd_k(const float* __restrict__ dy, float* __restrict__ dx, const vlfb_conv_geom_t g,
                               int accumulate, int64_t total) {
+  pdl_prologue();
   const int c4 = g.C >> 2;
   const float inv = 1.f / (float)(g.kT * g.kH * g.kW);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -194,6 +199,7 @@ __device__ __forceinline__ bool roi_sample(const RoiBox& b, int ph, int pw, int 
 
 __global__ void roi_align_fwd_k(const float* __restrict__ feat, const float* __restrict__ rois, float* __restrict__ out,
                                 int H, int W, int C, int PH, int PW, float scale, int sr, int64_t total) {
+  pdl_prologue();
   const int c4 = C >> 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % c4) * 4;
@@ -222,6 +228,7 @@ __global__ void roi_align_fwd_k(const float* __restrict__ feat, const float* __r
 
 __global__ void roi_align_bwd_k(const float* __restrict__ dout, const float* __restrict__ rois, float* __restrict__ dfeat,
                                 int H, int W, int C, int PH, int PW, float scale, int sr, int64_t total) {
+  pdl_prologue();
   const int c4 = C >> 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % c4) * 4;
@@ -252,6 +259,7 @@ __global__ void roi_align_bwd_k(const float* __restrict__ dout, const float* __r
 __global__ void roi_table_k(const float* __restrict__ rois, int32_t* __restrict__ pos, float* __restrict__ wts,
                             int32_t* __restrict__ grid, int H, int W, int R, int PH, int PW, int mg, float scale,
                             int sr) {
+  pdl_prologue();
   const int64_t total = (int64_t)R * PH * PW * mg * mg;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t q = i;
@@ -273,6 +281,7 @@ __global__ void roi_table_k(const float* __restrict__ rois, int32_t* __restrict_
 // ------------------------------------------------------------------ softmax / layernorm (warp per row)
 __global__ void softmax_fwd_k(const float* __restrict__ x, float* __restrict__ p, int64_t rows, int cols, float scale,
                               int tf32) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t wpb = blockDim.x >> 5;
   for (int64_t row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
@@ -294,6 +303,7 @@ __global__ void softmax_fwd_k(const float* __restrict__ x, float* __restrict__ p
 
 __global__ void softmax_bwd_k(const float* __restrict__ p, const float* __restrict__ dp, float* __restrict__ dx,
                               int64_t rows, int cols, float scale) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t wpb = blockDim.x >> 5;
   for (int64_t row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
@@ -308,6 +318,7 @@ __global__ void softmax_bwd_k(const float* __restrict__ p, const float* __restri
 
 __global__ void layernorm_fwd_k(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ mean,
                                 float* __restrict__ sd, int64_t rows, int cols, float eps) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t wpb = blockDim.x >> 5;
   for (int64_t row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
@@ -325,6 +336,7 @@ __global__ void layernorm_fwd_k(const float* __restrict__ x, float* __restrict__
 
 __global__ void layernorm_bwd_k(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ sd,
                                 float* __restrict__ dx, int64_t rows, int cols) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t wpb = blockDim.x >> 5;
   for (int64_t row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
@@ -358,6 +370,7 @@ __device__ __forceinline__ float ew_op(float a, float b, float s0, float s1) {
 template <int OP>
 __global__ void ew_k(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, int64_t n,
                      float s0, float s1, int vec) {
+  pdl_prologue();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (vec) {
@@ -378,7 +391,7 @@ template <int OP>
 int ew_launch(const float* a, const float* b, float* o, int64_t n, float s0, float s1, cudaStream_t st) {
   if (n <= 0) return VLFB_OK;
   const bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(o)) & 15) == 0;
-  ew_k<OP><<<stream_grid(n, TPB, 4), TPB, 0, st>>>(a, b, o, n, s0, s1, vec ? 1 : 0);
+  launch_k(ew_k<OP>, stream_grid(n, TPB, 4), TPB, 0, st, a, b, o, n, s0, s1, vec ? 1 : 0);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -400,6 +413,7 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t ctr, uint64_t key) {
 
 __global__ void dropout_k(const float* __restrict__ x, float* __restrict__ y, int64_t n, float ratio, float inv_keep,
                           uint64_t seed, uint64_t offset, const int64_t* __restrict__ step) {
+  pdl_prologue();
   const int64_t n4 = (n + 3) >> 2;
   if (step) offset += (uint64_t)step[0] << 32;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -418,6 +432,7 @@ __global__ void dropout_k(const float* __restrict__ x, float* __restrict__ y, in
 
 __global__ void copy2d_k(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int64_t rows,
                          int cols, int accumulate) {
+  pdl_prologue();
   const int64_t total = rows * cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols;
@@ -431,6 +446,7 @@ __global__ void copy2d_k(const float* __restrict__ src, int64_t lds, float* __re
 // one atomicAdd per column (out is zeroed first unless accumulating).
 __global__ void colsum_k(const float* __restrict__ x, int64_t ld, float* __restrict__ out, int64_t rows, int cols,
                          int64_t rows_per_block) {
+  pdl_prologue();
   __shared__ float part[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
@@ -451,6 +467,7 @@ __global__ void colsum_k(const float* __restrict__ x, int64_t ld, float* __restr
 // ------------------------------------------------------------------ layouts
 // src [N][C][inner] <-> dst [N][inner][Cpad]; tiled 32x32 transposes through shared memory.
 __global__ void nc_to_cl_k(const float* __restrict__ src, float* __restrict__ dst, int C, int64_t inner, int Cpad) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int64_t i0 = (int64_t)blockIdx.x * 32;
@@ -469,6 +486,7 @@ __global__ void nc_to_cl_k(const float* __restrict__ src, float* __restrict__ ds
 }
 
 __global__ void cl_to_nc_k(const float* __restrict__ src, float* __restrict__ dst, int C, int64_t inner, int Cpad) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int64_t i0 = (int64_t)blockIdx.x * 32;
@@ -489,6 +507,7 @@ __global__ void cl_to_nc_k(const float* __restrict__ src, float* __restrict__ ds
 // wt[ci][tap][co] = w[co][tap][ci] * scale[co]
 __global__ void weight_transpose_k(const float* __restrict__ w, float* __restrict__ wt, const float* __restrict__ scale,
                                    int Co, int taps, int Ci) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const int tap = blockIdx.z;
   const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
@@ -517,6 +536,7 @@ __device__ __forceinline__ float sce_elem(float x, float t) {
 
 __global__ void sigmoid_ce_fwd_k(const float* __restrict__ x, const int32_t* __restrict__ t, float* __restrict__ loss,
                                  int64_t n, float scale) {
+  pdl_prologue();
   __shared__ float red[32];
   float s = 0.f, cnt = 0.f;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
@@ -530,6 +550,7 @@ __global__ void sigmoid_ce_fwd_k(const float* __restrict__ x, const int32_t* __r
 
 __global__ void sigmoid_ce_bwd_k(const float* __restrict__ x, const int32_t* __restrict__ t,
                                  const float* __restrict__ dloss, float* __restrict__ dx, int64_t n, float scale) {
+  pdl_prologue();
   __shared__ float red[32];
   float cnt = 0.f;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) cnt += (t[i] != -1) ? 1.f : 0.f;
@@ -543,6 +564,7 @@ __global__ void sigmoid_ce_bwd_k(const float* __restrict__ x, const int32_t* __r
 
 __global__ void softmax_ce_fwd_k(const float* __restrict__ x, const int32_t* __restrict__ lab, float* __restrict__ prob,
                                  float* __restrict__ loss, int rows, int cols, float scale) {
+  pdl_prologue();
   __shared__ float red[32];
   float total = 0.f;
   for (int r = 0; r < rows; ++r) {
@@ -561,6 +583,7 @@ __global__ void softmax_ce_fwd_k(const float* __restrict__ x, const int32_t* __r
 
 __global__ void softmax_ce_bwd_k(const float* __restrict__ prob, const int32_t* __restrict__ lab, float* __restrict__ dx,
                                  int rows, int cols, float scale) {
+  pdl_prologue();
   const int64_t total = (int64_t)rows * cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols), c = (int)(i % cols);
@@ -571,6 +594,7 @@ __global__ void softmax_ce_bwd_k(const float* __restrict__ prob, const int32_t* 
 // ------------------------------------------------------------------ optimizer
 __global__ void sgd_k(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ pt, int64_t n,
                       const float* __restrict__ lrp, float mom, float wd, int nesterov) {
+  pdl_prologue();
   const float lr = lrp[0];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float pi = p[i], mi = m[i];
@@ -589,6 +613,7 @@ __global__ void sgd_k(float* __restrict__ p, float* __restrict__ g, float* __res
 __global__ void fbo_attend_fwd_k(const float* __restrict__ theta, const float* __restrict__ phi,
                                  const float* __restrict__ g, float* __restrict__ prob, float* __restrict__ y, int L,
                                  int d, float scale) {
+  pdl_prologue();
   extern __shared__ float sc[];
   __shared__ float red[32];
   const int r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -626,6 +651,7 @@ __global__ void fbo_attend_bwd_k(const float* __restrict__ theta, const float* _
                                  const float* __restrict__ g, const float* __restrict__ prob,
                                  const float* __restrict__ dy, float* __restrict__ dtheta, float* __restrict__ dphi,
                                  float* __restrict__ dg, int L, int d, float scale) {
+  pdl_prologue();
   extern __shared__ float ds[];   // L floats: dp then ds
   __shared__ float red[32];
   const int r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -679,7 +705,7 @@ int vlfb_affine_nd_fwd(const float* x, const float* scale, const float* bias, fl
   VLFB_CHECK_ARG(x && scale && bias && y && rows >= 0 && C > 0 && (C & 3) == 0);
   const int64_t n4 = rows * (C >> 2);
   if (n4 == 0) return VLFB_OK;
-  affine_fwd_k<<<stream_grid(n4, TPB), TPB, 0, ST(stream)>>>((const float4*)x, (const float4*)scale, (const float4*)bias,
+  launch_k(affine_fwd_k, stream_grid(n4, TPB), TPB, 0, ST(stream), (const float4*)x, (const float4*)scale, (const float4*)bias,
                                                              (float4*)y, n4, C >> 2);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
@@ -689,7 +715,7 @@ int vlfb_affine_nd_bwd(const float* dy, const float* scale, float* dx, int64_t r
   VLFB_CHECK_ARG(dy && scale && dx && rows >= 0 && C > 0 && (C & 3) == 0);
   const int64_t n4 = rows * (C >> 2);
   if (n4 == 0) return VLFB_OK;
-  affine_fwd_k<<<stream_grid(n4, TPB), TPB, 0, ST(stream)>>>((const float4*)dy, (const float4*)scale, nullptr,
+  launch_k(affine_fwd_k, stream_grid(n4, TPB), TPB, 0, ST(stream), (const float4*)dy, (const float4*)scale, nullptr,
                                                              (float4*)dx, n4, C >> 2);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
@@ -699,7 +725,7 @@ int vlfb_maxpool3d_fwd(const float* x, float* y, int32_t* argmax, const vlfb_con
   VLFB_CHECK_ARG(x && y && g && (g->C & 3) == 0 && g->Co == g->C);
   const int64_t total = (int64_t)g->N * g->To * g->Ho * g->Wo * (g->C >> 2);
   if (total == 0) return VLFB_OK;
-  maxpool_fwd_k<<<stream_grid(total, TPB), TPB, 0, ST(stream)>>>(x, y, argmax, *g, total);
+  launch_k(maxpool_fwd_k, stream_grid(total, TPB), TPB, 0, ST(stream), x, y, argmax, *g, total);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -708,7 +734,7 @@ int vlfb_maxpool3d_bwd(const float* dy, const int32_t* argmax, float* dx, const 
   VLFB_CHECK_ARG(dy && argmax && dx && g);
   const int64_t total = (int64_t)g->N * g->To * g->Ho * g->Wo * g->C;
   if (total == 0) return VLFB_OK;
-  maxpool_bwd_k<<<stream_grid(total, TPB), TPB, 0, ST(stream)>>>(dy, argmax, dx, g->C, total);
+  launch_k(maxpool_bwd_k, stream_grid(total, TPB), TPB, 0, ST(stream), dy, argmax, dx, g->C, total);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -717,7 +743,7 @@ int vlfb_avgpool3d_fwd(const float* x, float* y, const vlfb_conv_geom_t* g, void
   VLFB_CHECK_ARG(x && y && g && (g->C & 3) == 0 && g->pT == 0 && g->pH == 0 && g->pW == 0);
   const int64_t total = (int64_t)g->N * g->To * g->Ho * g->Wo * (g->C >> 2);
   if (total == 0) return VLFB_OK;
-  avgpool_fwd_k<<<stream_grid(total, TPB), TPB, 0, ST(stream)>>>(x, y, *g, total);
+  launch_k(avgpool_fwd_k, stream_grid(total, TPB), TPB, 0, ST(stream), x, y, *g, total);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -726,7 +752,7 @@ int vlfb_avgpool3d_bwd(const float* dy, float* dx, const vlfb_conv_geom_t* g, in
   VLFB_CHECK_ARG(dy && dx && g && (g->C & 3) == 0 && g->pT == 0 && g->pH == 0 && g->pW == 0);
   const int64_t total = (int64_t)g->N * g->T * g->H * g->W * (g->C >> 2);
   if (total == 0) return VLFB_OK;
-  avgpool_bwd_k<<<stream_grid(total, TPB), TPB, 0, ST(stream)>>>(dy, dx, *g, accumulate, total);
+  launch_k(avgpool_bwd_k, stream_grid(total, TPB), TPB, 0, ST(stream), dy, dx, *g, accumulate, total);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -736,7 +762,7 @@ int vlfb_roi_align_fwd(const float* feat, const float* rois, float* out, int N, 
   VLFB_CHECK_ARG(feat && rois && out && N > 0 && H > 0 && W > 0 && (C & 3) == 0 && R >= 0 && PH > 0 && PW > 0);
   const int64_t total = (int64_t)R * PH * PW * (C >> 2);
   if (total == 0) return VLFB_OK;
-  roi_align_fwd_k<<<stream_grid(total, TPB), TPB, 0, ST(stream)>>>(feat, rois, out, H, W, C, PH, PW, spatial_scale,
+  launch_k(roi_align_fwd_k, stream_grid(total, TPB), TPB, 0, ST(stream), feat, rois, out, H, W, C, PH, PW, spatial_scale,
                                                                   sampling_ratio, total);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
@@ -747,7 +773,7 @@ int vlfb_roi_align_bwd(const float* dout, const float* rois, float* dfeat, int N
   VLFB_CHECK_ARG(dout && rois && dfeat && N > 0 && H > 0 && W > 0 && (C & 3) == 0 && R >= 0 && PH > 0 && PW > 0);
   const int64_t total = (int64_t)R * PH * PW * (C >> 2);
   if (total == 0) return VLFB_OK;
-  roi_align_bwd_k<<<stream_grid(total, TPB), TPB, 0, ST(stream)>>>(dout, rois, dfeat, H, W, C, PH, PW, spatial_scale,
+  launch_k(roi_align_bwd_k, stream_grid(total, TPB), TPB, 0, ST(stream), dout, rois, dfeat, H, W, C, PH, PW, spatial_scale,
                                                                   sampling_ratio, total);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
@@ -758,7 +784,7 @@ int vlfb_roi_align_table(const float* rois, int32_t* pos, float* w, int32_t* gri
   VLFB_CHECK_ARG(rois && pos && w && grid && R >= 0 && max_grid > 0);
   const int64_t total = (int64_t)R * PH * PW * max_grid * max_grid;
   if (total == 0) return VLFB_OK;
-  roi_table_k<<<stream_grid(total, TPB), TPB, 0, ST(stream)>>>(rois, pos, w, grid, H, W, R, PH, PW, max_grid,
+  launch_k(roi_table_k, stream_grid(total, TPB), TPB, 0, ST(stream), rois, pos, w, grid, H, W, R, PH, PW, max_grid,
                                                               spatial_scale, sampling_ratio);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
@@ -767,7 +793,7 @@ int vlfb_roi_align_table(const float* rois, int32_t* pos, float* w, int32_t* gri
 int vlfb_softmax_fwd(const float* x, float* p, int64_t rows, int cols, float scale, int tf32, void* stream) {
   VLFB_CHECK_ARG(x && p && rows >= 0 && cols > 0);
   if (rows == 0) return VLFB_OK;
-  softmax_fwd_k<<<stream_grid(rows, TPB / 32), TPB, 0, ST(stream)>>>(x, p, rows, cols, scale, tf32);
+  launch_k(softmax_fwd_k, stream_grid(rows, TPB / 32), TPB, 0, ST(stream), x, p, rows, cols, scale, tf32);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -775,7 +801,7 @@ int vlfb_softmax_fwd(const float* x, float* p, int64_t rows, int cols, float sca
 int vlfb_softmax_bwd(const float* p, const float* dp, float* dx, int64_t rows, int cols, float scale, void* stream) {
   VLFB_CHECK_ARG(p && dp && dx && rows >= 0 && cols > 0);
   if (rows == 0) return VLFB_OK;
-  softmax_bwd_k<<<stream_grid(rows, TPB / 32), TPB, 0, ST(stream)>>>(p, dp, dx, rows, cols, scale);
+  launch_k(softmax_bwd_k, stream_grid(rows, TPB / 32), TPB, 0, ST(stream), p, dp, dx, rows, cols, scale);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -784,7 +810,7 @@ int vlfb_layernorm_fwd(const float* x, float* y, float* mean, float* std, int64_
                        void* stream) {
   VLFB_CHECK_ARG(x && y && rows >= 0 && cols > 0);
   if (rows == 0) return VLFB_OK;
-  layernorm_fwd_k<<<stream_grid(rows, TPB / 32), TPB, 0, ST(stream)>>>(x, y, mean, std, rows, cols, eps);
+  launch_k(layernorm_fwd_k, stream_grid(rows, TPB / 32), TPB, 0, ST(stream), x, y, mean, std, rows, cols, eps);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -793,7 +819,7 @@ int vlfb_layernorm_bwd(const float* dy, const float* y, const float* std, float*
                        void* stream) {
   VLFB_CHECK_ARG(dy && y && std && dx && rows >= 0 && cols > 0);
   if (rows == 0) return VLFB_OK;
-  layernorm_bwd_k<<<stream_grid(rows, TPB / 32), TPB, 0, ST(stream)>>>(dy, y, std, dx, rows, cols);
+  launch_k(layernorm_bwd_k, stream_grid(rows, TPB / 32), TPB, 0, ST(stream), dy, y, std, dx, rows, cols);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -843,7 +869,7 @@ int vlfb_colsum(const float* x, int64_t ld, float* out, int64_t rows, int cols, 
   if (slabs > max_slabs) slabs = (int)max_slabs;
   if (slabs < 1) slabs = 1;
   const int64_t rpb = (rows + slabs - 1) / slabs;
-  colsum_k<<<dim3(cb, slabs), dim3(32, 8), 0, ST(stream)>>>(x, ld, out, rows, cols, rpb);
+  launch_k(colsum_k, dim3(cb, slabs), dim3(32, 8), 0, ST(stream), x, ld, out, rows, cols, rpb);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -856,7 +882,7 @@ int vlfb_dropout_fwd(const float* x, float* y, int64_t n, float ratio, uint64_t 
                      const int64_t* step, void* stream) {
   VLFB_CHECK_ARG(x && y && n >= 0 && ratio >= 0.f && ratio < 1.f);
   if (n == 0) return VLFB_OK;
-  dropout_k<<<stream_grid((n + 3) / 4, TPB), TPB, 0, ST(stream)>>>(x, y, n, ratio, 1.f / (1.f - ratio), seed, offset,
+  launch_k(dropout_k, stream_grid((n + 3) / 4, TPB), TPB, 0, ST(stream), x, y, n, ratio, 1.f / (1.f - ratio), seed, offset,
                                                                    step);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
@@ -866,7 +892,7 @@ int vlfb_copy2d(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t 
                 void* stream) {
   VLFB_CHECK_ARG(src && dst && rows >= 0 && cols >= 0);
   if (rows * cols == 0) return VLFB_OK;
-  copy2d_k<<<stream_grid(rows * cols, TPB), TPB, 0, ST(stream)>>>(src, lds, dst, ldd, rows, cols, accumulate);
+  launch_k(copy2d_k, stream_grid(rows * cols, TPB), TPB, 0, ST(stream), src, lds, dst, ldd, rows, cols, accumulate);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -874,7 +900,7 @@ int vlfb_copy2d(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t 
 int vlfb_nc_to_cl(const float* src, float* dst, int N, int C, int64_t inner, int Cpad, void* stream) {
   VLFB_CHECK_ARG(src && dst && N > 0 && C > 0 && inner > 0 && Cpad >= C);
   dim3 grid(ceil_div(inner, 32), ceil_div(Cpad, 32), N), block(32, 8);
-  nc_to_cl_k<<<grid, block, 0, ST(stream)>>>(src, dst, C, inner, Cpad);
+  launch_k(nc_to_cl_k, grid, block, 0, ST(stream), src, dst, C, inner, Cpad);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -882,7 +908,7 @@ int vlfb_nc_to_cl(const float* src, float* dst, int N, int C, int64_t inner, int
 int vlfb_cl_to_nc(const float* src, float* dst, int N, int C, int64_t inner, int Cpad, void* stream) {
   VLFB_CHECK_ARG(src && dst && N > 0 && C > 0 && inner > 0 && Cpad >= C);
   dim3 grid(ceil_div(inner, 32), ceil_div(C, 32), N), block(32, 8);
-  cl_to_nc_k<<<grid, block, 0, ST(stream)>>>(src, dst, C, inner, Cpad);
+  launch_k(cl_to_nc_k, grid, block, 0, ST(stream), src, dst, C, inner, Cpad);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -890,14 +916,14 @@ int vlfb_cl_to_nc(const float* src, float* dst, int N, int C, int64_t inner, int
 int vlfb_weight_transpose(const float* w, float* wt, const float* scale, int Co, int taps, int Ci, void* stream) {
   VLFB_CHECK_ARG(w && wt && Co > 0 && taps > 0 && Ci > 0);
   dim3 grid(ceil_div(Ci, 32), ceil_div(Co, 32), taps), block(32, 8);
-  weight_transpose_k<<<grid, block, 0, ST(stream)>>>(w, wt, scale, Co, taps, Ci);
+  launch_k(weight_transpose_k, grid, block, 0, ST(stream), w, wt, scale, Co, taps, Ci);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
 
 int vlfb_sigmoid_ce_fwd(const float* logits, const int32_t* targets, float* loss, int64_t n, float scale, void* stream) {
   VLFB_CHECK_ARG(logits && targets && loss && n > 0);
-  sigmoid_ce_fwd_k<<<1, 1024, 0, ST(stream)>>>(logits, targets, loss, n, scale);
+  launch_k(sigmoid_ce_fwd_k, 1, 1024, 0, ST(stream), logits, targets, loss, n, scale);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -905,7 +931,7 @@ int vlfb_sigmoid_ce_fwd(const float* logits, const int32_t* targets, float* loss
 int vlfb_sigmoid_ce_bwd(const float* logits, const int32_t* targets, const float* dloss, float* dlogits, int64_t n,
                         float scale, void* stream) {
   VLFB_CHECK_ARG(logits && targets && dlogits && n > 0);
-  sigmoid_ce_bwd_k<<<1, 1024, 0, ST(stream)>>>(logits, targets, dloss, dlogits, n, scale);
+  launch_k(sigmoid_ce_bwd_k, 1, 1024, 0, ST(stream), logits, targets, dloss, dlogits, n, scale);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -913,7 +939,7 @@ int vlfb_sigmoid_ce_bwd(const float* logits, const int32_t* targets, const float
 int vlfb_softmax_ce_fwd(const float* logits, const int32_t* labels, float* prob, float* loss, int rows, int cols,
                         float scale, void* stream) {
   VLFB_CHECK_ARG(logits && labels && prob && loss && rows > 0 && cols > 0);
-  softmax_ce_fwd_k<<<1, 256, 0, ST(stream)>>>(logits, labels, prob, loss, rows, cols, scale);
+  launch_k(softmax_ce_fwd_k, 1, 256, 0, ST(stream), logits, labels, prob, loss, rows, cols, scale);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -921,7 +947,7 @@ int vlfb_softmax_ce_fwd(const float* logits, const int32_t* labels, float* prob,
 int vlfb_softmax_ce_bwd(const float* prob, const int32_t* labels, float* dlogits, int rows, int cols, float scale,
                         void* stream) {
   VLFB_CHECK_ARG(prob && labels && dlogits && rows > 0 && cols > 0);
-  softmax_ce_bwd_k<<<stream_grid((int64_t)rows * cols, TPB), TPB, 0, ST(stream)>>>(prob, labels, dlogits, rows, cols,
+  launch_k(softmax_ce_bwd_k, stream_grid((int64_t)rows * cols, TPB), TPB, 0, ST(stream), prob, labels, dlogits, rows, cols,
                                                                                   scale);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
@@ -931,7 +957,7 @@ int vlfb_sgd_nesterov(float* p, float* g, float* m, float* p_tf32, int64_t n, co
                       int nesterov, void* stream) {
   VLFB_CHECK_ARG(p && g && m && lr && n >= 0);
   if (n == 0) return VLFB_OK;
-  sgd_k<<<stream_grid(n, TPB, 4), TPB, 0, ST(stream)>>>(p, g, m, p_tf32, n, lr, momentum, wd, nesterov);
+  launch_k(sgd_k, stream_grid(n, TPB, 4), TPB, 0, ST(stream), p, g, m, p_tf32, n, lr, momentum, wd, nesterov);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -940,7 +966,7 @@ int vlfb_fbo_attend_fwd(const float* theta, const float* phi, const float* g, fl
                         float scale, void* stream) {
   VLFB_CHECK_ARG(theta && phi && g && prob && y && R >= 0 && L > 0 && d > 0 && (d & 3) == 0 && L <= 12000);
   if (R == 0) return VLFB_OK;
-  fbo_attend_fwd_k<<<R, 512, L * sizeof(float), ST(stream)>>>(theta, phi, g, prob, y, L, d, scale);
+  launch_k(fbo_attend_fwd_k, R, 512, L * sizeof(float), ST(stream), theta, phi, g, prob, y, L, d, scale);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -950,7 +976,7 @@ int vlfb_fbo_attend_bwd(const float* theta, const float* phi, const float* g, co
   VLFB_CHECK_ARG(theta && phi && g && prob && dy && dtheta && dphi && dg && R >= 0 && L > 0 && d > 0 && (d & 3) == 0 &&
                  L <= 12000);
   if (R == 0) return VLFB_OK;
-  fbo_attend_bwd_k<<<R, 512, L * sizeof(float), ST(stream)>>>(theta, phi, g, prob, dy, dtheta, dphi, dg, L, d, scale);
+  launch_k(fbo_attend_bwd_k, R, 512, L * sizeof(float), ST(stream), theta, phi, g, prob, dy, dtheta, dphi, dg, L, d, scale);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }

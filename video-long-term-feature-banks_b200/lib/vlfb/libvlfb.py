@@ -42,6 +42,7 @@ SIGNATURES = {
     'vlfb_last_error': [],
     'vlfb_set_gemm_backend': [_I],
     'vlfb_get_gemm_backend': [],
+    'vlfb_set_pdl': [_I],
     'vlfb_gemm': [C.POINTER(GemmParams), _P],
     'vlfb_affine_nd_fwd': [_P, _P, _P, _P, _L, _I, _P],
     'vlfb_affine_nd_bwd': [_P, _P, _P, _L, _I, _P],
