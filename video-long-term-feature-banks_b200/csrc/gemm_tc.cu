@@ -574,11 +574,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
       KLoader<is_mn(BK) ? VLFB_OP_DENSE_K : BK, 256 / RSTEP> kb;
       MNLoader<is_mn(BK) ? BK : VLFB_OP_DENSE_MN> mb;
       const int LAG = L.lag;
-      const bool im2col_a = L.tma_a == 2, im2col_b = L.tma_b == 2;
+      // compile-time gates keep the im2col state out of the instantiations that cannot use it (registers)
+      const bool im2col_a = (AK == VLFB_OP_CONV_K || AK == VLFB_OP_DGRAD_K) && L.tma_a == 2;
+      const bool im2col_b = BK == VLFB_OP_CONV_MN && L.tma_b == 2;
+      constexpr int NATOM = BK == VLFB_OP_CONV_MN ? 8 : 1;
       // im2col state of the issuing thread: window origin of the tile's first row + filter-tap cursor (A), and
       // per 32-column atom the channel slice / tap offsets of the wgrad B tile
       int ia_w = 0, ia_h = 0, ia_d = 0, ia_n = 0, ic_t = 0, ic_h = 0, ic_w = 0, ic_c = 0, icpt = 1;
-      int ib_c[8], ib_off[8], ib_atoms = 0;
+      int ib_c[NATOM], ib_off[NATOM], ib_atoms = 0;
       // chunk counter over the CTA's whole tile sequence; ring slot / phase / lagged slot advance
       // incrementally (S is a run-time value: `it % S` cost three integer divisions per chunk per thread)
       int it = 0, s = 0, sl = 0;
@@ -612,7 +615,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
           const vlfb_conv_geom_t& g = p.g;
           ib_atoms = 0;
 #pragma unroll
-          for (int a = 0; a < 8; ++a) {
+          for (int a = 0; a < NATOM; ++a) {
             const int ncol = ti.n0 + a * 32;
             if (a * 32 < bn && ncol < p.N) {
               uint32_t tap_hw, ci, qh, qw;
@@ -659,7 +662,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
               const Pos4 o = decode_pos_fast((uint32_t)(ti.k_begin + i * KC), L.out);
               const int bw = o.w * g.sW - g.pW, bh = o.h * g.sH - g.pH, bd = o.t * g.sT - g.pT;
 #pragma unroll
-              for (int a = 0; a < 8; ++a)
+              for (int a = 0; a < NATOM; ++a)
                 if (a < ib_atoms)
                   tma_load_im2col(b_tile + a * 4096, &tmB, ib_c[a], bw, bh, bd, o.n, ib_off[a] & 0xFFFF, ib_off[a] >> 16,
                                   ti.tap * g.dT, full0 + 8 * s_cur);
