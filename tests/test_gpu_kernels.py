@@ -28,6 +28,24 @@ def rnd(shape, seed, scale=1.0):
 
 # -------------------------------------------------------------------------- dense matmul
 @pytest.mark.parametrize('backend', BACKENDS)
+@pytest.mark.parametrize('M,N,K_', [(4, 80, 2560), (8, 160, 4100), (130, 36, 1024)])
+def test_skinny_long_k_matmul_uses_split_k_with_bias(K, backend, M, N, K_):
+    """The classifier FC (4 RoIs x 80 classes x 2560): few output tiles, long reduction -> split-K with atomic
+    accumulation; the bias must be added exactly once, and accumulate=True must keep the previous contents."""
+    K.set_gemm_backend(backend)
+    a, b = rnd((1, M, K_), 11), rnd((1, K_, N), 12)
+    bias = torch.randn(N)
+    ref = torch.bmm(a.double(), b.double()) + bias.double()
+    d = torch.full((1, M, N), float('nan'), device='cuda')
+    K.matmul(a.cuda(), b.cuda(), d, bias=bias.cuda())
+    torch.cuda.synchronize()
+    assert rel_err(d, ref) < 2e-5
+    K.matmul(a.cuda(), b.cuda(), d, accumulate=True)
+    torch.cuda.synchronize()
+    assert rel_err(d, 2 * ref - bias.double()) < 2e-5
+
+
+@pytest.mark.parametrize('backend', BACKENDS)
 @pytest.mark.parametrize('ta,tb', [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize('B,M,N,K_', [(1, 128, 128, 64), (2, 200, 80, 300), (3, 1, 300, 512), (1, 264, 512, 96),
                                        (2, 392, 196, 128)])

@@ -36,7 +36,7 @@ static int validate_gemm(const vlfb_gemm_params_t& p, bool& tc_ok) {
   VLFB_CHECK_ARG(p.batch >= 1 && p.taps >= 1 && p.split_k >= 0);          // split_k 0 = chosen by the library
   VLFB_CHECK_ARG(!(p.taps > 1 && p.batch > 1));
   VLFB_CHECK_ARG(p.split_k == 1 || (p.flags & VLFB_EPI_ATOMIC));
-  VLFB_CHECK_ARG(!(p.split_k != 1 && (p.col_bias || p.residual || p.relu_mask || (p.flags & VLFB_EPI_RELU))));
+  VLFB_CHECK_ARG(!(p.split_k != 1 && (p.residual || p.relu_mask || (p.flags & (VLFB_EPI_RELU | VLFB_EPI_TF32)))));
   if (!(aligned16(p.a.ptr) && aligned16(p.b.ptr))) tc_ok = false;
   const vlfb_operand_t* ops[2] = {&p.a, &p.b};
   for (int i = 0; i < 2; ++i) {

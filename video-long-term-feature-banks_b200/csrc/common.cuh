@@ -152,10 +152,10 @@ __device__ __forceinline__ float round_tf32(float v) {
 
 // Epilogue applied to one accumulator value (shared by both GEMM engines).
 __device__ __forceinline__ void epilogue_store(const vlfb_gemm_params_t& p, int batch, int tap, int m,
-                                               int n, float v) {
+                                               int n, float v, bool first_split = true) {
   v *= p.alpha;
   if (p.col_scale) v *= p.col_scale[n];
-  if (p.col_bias) v += p.col_bias[n];
+  if (p.col_bias && first_split) v += p.col_bias[n];      // split-K: the bias is added by the first K slice only
   if (p.row_scale) v *= p.row_scale[m];
   int64_t off = (int64_t)batch * p.d_batch_stride + (int64_t)tap * p.d_tap_stride + (int64_t)m * p.ldd + n;
   if (p.residual) v += p.residual[off];

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const vlfb_gemm_params_t
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       int m = m0 + ty + 16 * i, n = n0 + tx + 16 * j;
-      if (m < p.M && n < p.N) epilogue_store(p, batch, tap, m, n, acc[i][j]);
+      if (m < p.M && n < p.N) epilogue_store(p, batch, tap, m, n, acc[i][j], split == 0);
     }
 }
 

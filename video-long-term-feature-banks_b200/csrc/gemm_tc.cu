@@ -870,7 +870,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
         const bool nfull = n + 3 < p.N;
         const int cvi = ((c0 - half * EPC) >> 1) + col;
         const float4 cs = *reinterpret_cast<const float4*>(wsc + cvi);
-        const float4 cb = *reinterpret_cast<const float4*>(wbi + cvi);
+        float4 cb = *reinterpret_cast<const float4*>(wbi + cvi);
+        if (ti.k_begin != 0) cb = make_float4(0.f, 0.f, 0.f, 0.f);      // split-K: bias from the first K slice only
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int row = (lane >> 2) + 8 * i;
@@ -904,7 +905,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
             const float e4[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              if (n + e < p.N) epilogue_store(p, ti.batch, ti.tap, m, n + e, e4[e]);
+              if (n + e < p.N) epilogue_store(p, ti.batch, ti.tap, m, n + e, e4[e], ti.k_begin == 0);
           }
         }
         __syncwarp();
