@@ -157,6 +157,9 @@ int vlfb_fill(float* x, float v, int64_t n, void* stream);
 int vlfb_add_tf32(const float* x, const float* y, float* out, int64_t n, void* stream);   /* round(x+y) */
 int vlfb_relu_tf32(const float* x, float* y, int64_t n, void* stream);                    /* round(max(x,0)) */
 int vlfb_relu_bwd_tf32(const float* dy, const float* y, float* dx, int64_t n, void* stream); /* round(dy*(y>0)) */
+/* out = (y == NULL || y > 0) ? round_tf32(a + b) : 0 : sum of two gradient contributions + ReLU backward + TF32
+ * rounding in one pass (out may alias a or b). */
+int vlfb_add_relu_bwd_tf32(const float* a, const float* b, const float* y, float* out, int64_t n, void* stream);
 /* out[c] (+)= sum_r x[r*ld + c]  (bias gradients of Conv/FC) */
 int vlfb_colsum(const float* x, int64_t ld, float* out, int64_t rows, int cols, int accumulate, void* stream);
 /* y = round-to-nearest TF32 of x (operand preparation for kind::tf32 MMAs; y may alias x) */

@@ -223,6 +223,13 @@ def relu_bwd(dy, y, dx):
     dx.copy_(dy * (y > 0))
 
 
+def add_relu_bwd_tf32(a, b, y, out):
+    r = a + b
+    if y is not None:
+        r = torch.where(y > 0, r, torch.zeros_like(r))
+    out.copy_(_q(r))
+
+
 def relu_bwd_tf32(dy, y, dx):
     dx.copy_(_q(dy * (y > 0)))
 

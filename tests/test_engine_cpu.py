@@ -44,10 +44,13 @@ def _run(yaml_name, overrides, fake, check_blobs, reps=1):
     upd, net.update_ops = net.update_ops, []
     first = {}
     fuse0, X.FUSE_GRAD_FINISH = X.FUSE_GRAD_FINISH, True
-    # run 1 records how many contributions every gradient receives; from run 2 on the dgrad GEMM that
-    # delivers the last one also applies the ReLU backward + TF32 rounding (executor "grad finish" fusion):
-    # both runs must match the oracle, and each other exactly
+    lazy0 = X.LAZY_GRAD_SUM
+    # run 1: the default engine (deferred two-term gradient sums folded into the consumer's mask/round pass); it
+    # also records how many contributions every gradient receives.  Run 2: the dgrad GEMM that delivers the last
+    # contribution applies the ReLU backward + TF32 rounding itself (executor "grad finish" fusion, eager sums).
+    # Both must match the oracle; they differ from each other only by the association of three-term sums.
     for rep in range(reps):
+        X.LAZY_GRAD_SUM = lazy0 if rep == 0 else False
         fused0 = X.STATS['fused_grad_finish']
         workspace.RunNet(model.net.Proto().name)
         assert (X.STATS['fused_grad_finish'] > fused0) == (rep == 1)
@@ -67,10 +70,10 @@ def _run(yaml_name, overrides, fake, check_blobs, reps=1):
             if rep == 0:
                 first[name] = g.copy()
             else:
-                assert np.array_equal(g, first[name]), name
+                assert np.abs(g - first[name]).max() <= 1e-12 * max(np.abs(g).max(), 1e-5), name   # phi_b: zero gradient
         print("run %d: worst grad rel err %.2e" % (rep, worst))
     net.update_ops = upd
-    X.FUSE_GRAD_FINISH = fuse0
+    X.FUSE_GRAD_FINISH, X.LAZY_GRAD_SUM = fuse0, lazy0
     return model, params, p64, worst
 
 
@@ -182,6 +185,7 @@ def test_grad_finish_fusion_is_exact_under_tf32_emulation(fake):
     from vlfb import executor as X, workspace
     fake.EMULATE_TF32 = True
     fuse0, X.FUSE_GRAD_FINISH = X.FUSE_GRAD_FINISH, True
+    lazy0, X.LAZY_GRAD_SUM = X.LAZY_GRAD_SUM, False      # same association of the sums in both runs
     try:
         H.setup_cfg('ava_r50_lfb_nl.yaml', TINY)
         ocfg = H.oracle_cfg('ava_r50_lfb_nl.yaml', TINY)
@@ -202,4 +206,4 @@ def test_grad_finish_fusion_is_exact_under_tf32_emulation(fake):
             assert np.array_equal(grads[0][n], grads[1][n]), n
     finally:
         fake.EMULATE_TF32 = False
-        X.FUSE_GRAD_FINISH = fuse0
+        X.FUSE_GRAD_FINISH, X.LAZY_GRAD_SUM = fuse0, lazy0

@@ -345,6 +345,16 @@ def test_elementwise_and_layout(K):
     assert float(o.min()) == 3.0 and float(o.max()) == 3.0
     K.sigmoid_fwd(x.cuda(), o)
     assert rel_err(o, torch.sigmoid(x)) < 1e-6
+    # fused gradient finish: sum of two contributions + ReLU backward + TF32 rounding, bit-exact vs the two-pass form
+    for n in (1003, 4096):
+        a, b, m = torch.randn(n), torch.randn(n), torch.randn(n)
+        want = tf32_round(a + b) * (m > 0)
+        ad = a.cuda()
+        K.add_relu_bwd_tf32(ad, b.cuda(), m.cuda(), ad)          # in place on a
+        assert torch.equal(ad.cpu(), want)
+        od = torch.empty(n, device='cuda')
+        K.add_relu_bwd_tf32(a.cuda(), b.cuda(), None, od)
+        assert torch.equal(od.cpu(), tf32_round(a + b))
     # layouts
     t = torch.randn(2, 3, 4, 5, 6)
     cl = torch.empty((2, 4, 5, 6, 4), device='cuda')

@@ -166,6 +166,7 @@ def test_grad_finish_fusion_and_graph_replay_agree_with_first_run(ws):
     net.update_ops = []
     runs = []
     fuse0, X.FUSE_GRAD_FINISH = X.FUSE_GRAD_FINISH, True       # off by default (slower on B200), still supported
+    lazy0, X.LAZY_GRAD_SUM = X.LAZY_GRAD_SUM, False            # same association of three-term sums in every run
     for rep in range(4):
         n0 = X.STATS['fused_grad_finish']
         ws.RunNet(model.net.Proto().name)
@@ -173,7 +174,7 @@ def test_grad_finish_fusion_and_graph_replay_agree_with_first_run(ws):
         if rep < 2:
             assert (X.STATS['fused_grad_finish'] - n0 > 40) == (rep == 1)
         runs.append(dict((n, ws.FetchBlob('gpu_0/' + n + '_grad').copy()) for n in model.TrainableParams()))
-    X.FUSE_GRAD_FINISH = fuse0
+    X.FUSE_GRAD_FINISH, X.LAZY_GRAD_SUM = fuse0, lazy0
     assert net._graphs is not None, 'the step should have been captured into a CUDA graph by now'
     for rep in (1, 2, 3):
         worst = max(float(np.abs(runs[rep][n] - runs[0][n]).max() / (np.abs(runs[0][n]).max() + 1e-12)) for n in runs[0])

@@ -396,6 +396,28 @@ int ew_launch(const float* a, const float* b, float* o, int64_t n, float s0, flo
   return VLFB_OK;
 }
 
+// out = (y == nullptr || y > 0) ? round_tf32(a + b) : 0 -- the sum of two gradient contributions, the ReLU backward
+// of the layer that owns the gradient and the TF32 rounding its GEMMs need, in ONE pass (4 tensor streams instead
+// of the 6 of axpby + relu_bwd_tf32).  `out` may alias a or b.
+__global__ void add_mask_tf32_k(const float* a, const float* b, const float* y, float* o, int64_t n, int vec) {
+  pdl_prologue();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (vec) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = t; i < n4; i += stride) {
+      const float4 va = reinterpret_cast<const float4*>(a)[i], vb = reinterpret_cast<const float4*>(b)[i];
+      const float4 vy = y ? reinterpret_cast<const float4*>(y)[i] : make_float4(1.f, 1.f, 1.f, 1.f);
+      reinterpret_cast<float4*>(o)[i] =
+          make_float4(vy.x > 0.f ? round_tf32(va.x + vb.x) : 0.f, vy.y > 0.f ? round_tf32(va.y + vb.y) : 0.f,
+                      vy.z > 0.f ? round_tf32(va.z + vb.z) : 0.f, vy.w > 0.f ? round_tf32(va.w + vb.w) : 0.f);
+    }
+    for (int64_t i = (n4 << 2) + t; i < n; i += stride) o[i] = (!y || y[i] > 0.f) ? round_tf32(a[i] + b[i]) : 0.f;
+  } else {
+    for (int64_t i = t; i < n; i += stride) o[i] = (!y || y[i] > 0.f) ? round_tf32(a[i] + b[i]) : 0.f;
+  }
+}
+
 // Philox4x32-10 counter-based generator (Salmon et al. 2011), self-contained.
 __device__ __forceinline__ uint4 philox4x32(uint64_t ctr, uint64_t key) {
   uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0u, c3 = 0u;
@@ -855,6 +877,15 @@ int vlfb_relu_tf32(const float* x, float* y, int64_t n, void* stream) {
 int vlfb_relu_bwd_tf32(const float* dy, const float* y, float* dx, int64_t n, void* stream) {
   VLFB_CHECK_ARG(dy && y && dx && n >= 0);
   return ew_launch<EW_RELU_BWD_TF32>(dy, y, dx, n, 0.f, 0.f, ST(stream));
+}
+int vlfb_add_relu_bwd_tf32(const float* a, const float* b, const float* y, float* out, int64_t n, void* stream) {
+  VLFB_CHECK_ARG(a && b && out && n >= 0);
+  if (n == 0) return VLFB_OK;
+  const bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(y) |
+                     reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  launch_k(add_mask_tf32_k, stream_grid(n, TPB, 4), TPB, 0, ST(stream), a, b, y, out, n, vec ? 1 : 0);
+  VLFB_CHECK_LAUNCH();
+  return VLFB_OK;
 }
 int vlfb_colsum(const float* x, int64_t ld, float* out, int64_t rows, int cols, int accumulate, void* stream) {
   VLFB_CHECK_ARG(x && out && rows >= 0 && cols > 0);

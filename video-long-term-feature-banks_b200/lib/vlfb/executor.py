@@ -25,6 +25,7 @@ K = K_default          # tests may swap in a torch-CPU kernel set (tests/fake_ke
 DEVICE = 'cuda'
 DTYPE = torch.float32      # the CUDA kernels are fp32-only; the CPU test stand-in may run the host logic in fp64
 STATS = {'fused_grad_finish': 0}
+LAZY_GRAD_SUM = os.environ.get('VLFB_LAZY_GRAD_SUM', '1') != '0'   # defer residual + dgrad sums into the consumer's mask/round pass
 # Fold the ReLU backward + TF32 rounding of a conv's incoming gradient (and the sum of its earlier contributions)
 # into the epilogue of the dgrad GEMM that delivers the last contribution.  Exact (tests run both ways), but OFF by
 # default: measured on B200 the step is 2-3% SLOWER with it (19.0 vs 18.6 ms) -- the 8 epilogue warps of the
@@ -125,6 +126,9 @@ class Ctx(object):
         # and TF32 rounding from that last contributor's GEMM epilogue.
         self.counts = {}
         self.final = set()
+        # lazy two-term sums: grads[key] (owned) + pending[key] (an alias of somebody else's gradient, e.g. the
+        # residual branch).  A conv that owns `key` folds the sum into its ReLU-backward / rounding pass.
+        self.pending = {}
 
     # ---- blobs
     def get(self, name):
@@ -170,18 +174,49 @@ class Ctx(object):
         else:
             if self.owned[key]:
                 K.axpby(flat(cur), 1.0, flat(g), 1.0, flat(cur))
+            elif (LAZY_GRAD_SUM and owned and key not in self.pending and cur.shape == g.shape
+                  and cur.stride() == g.stride()):
+                self.pending[key] = cur          # summed when the gradient is consumed
+                self.grads[key] = g
+                self.owned[key] = True
             else:
                 s = empty_like_strided(cur)
                 K.axpby(flat(cur), 1.0, flat(g), 1.0, flat(s))
                 self.grads[key] = s
                 self.owned[key] = True
 
+    def _settle(self, key):
+        """Materialise a deferred two-term sum in place."""
+        pend = self.pending.pop(key, None)
+        if pend is not None:
+            cur = self.grads[key]
+            K.axpby(flat(cur), 1.0, flat(pend), 1.0, flat(cur))
+
+    def pop_grad_finished(self, key, y):
+        """Gradient of a conv output, ready to be a GEMM operand: summed, masked by the conv's ReLU (y = its
+        output, or None) and TF32-rounded -- in one pass when a deferred sum is pending."""
+        pend = self.pending.pop(key, None)
+        if pend is None:
+            g = self.pop_grad_owned(key)
+            if g is not None:
+                if y is not None:
+                    K.relu_bwd_tf32(flat(g), flat(y), flat(g))
+                else:
+                    K.round_tf32(flat(g), flat(g))
+            return g
+        self.owned.pop(key, None)
+        g = self.grads.pop(key)
+        K.add_relu_bwd_tf32(flat(g), flat(pend), None if y is None else flat(y), flat(g))
+        return g
+
     def pop_grad(self, key):
+        self._settle(key)
         self.owned.pop(key, None)
         return self.grads.pop(key, None)
 
     def pop_grad_owned(self, key):
         """Gradient that may be modified in place."""
+        self._settle(key)
         own = self.owned.pop(key, False)
         g = self.grads.pop(key, None)
         if g is not None and not own:
@@ -249,16 +284,11 @@ class ConvStep(Step):
             xp, g = ctx.saved.pop(id(self))
             gp = as5d(phys(gy))
         else:
-            gy = ctx.pop_grad_owned(okey)
+            gy = ctx.pop_grad_finished(okey, ctx.get(self.out) if self.relu else None)
             if gy is None:
                 return
             xp, g = ctx.saved.pop(id(self))
             gp = as5d(phys(gy))
-            if self.relu:
-                y = phys(ctx.get(self.out))
-                K.relu_bwd_tf32(flat(gp), flat(y), flat(gp))
-            else:
-                K.round_tf32(flat(gp), flat(gp))
         if self.res_key is not None:
             ctx.add_grad(self.res_key, gy, owned=False)
         scale = ctx.ws.params.phys(self.affine[0]) if self.affine else None
@@ -290,6 +320,7 @@ class ConvStep(Step):
                 # conv's ReLU backward (mask = its output = our input xp) and the TF32 rounding its own
                 # dgrad / wgrad GEMMs need -- all in this GEMM's epilogue (saves ~6 passes over the tensor).
                 mask = xp if prod.relu else None
+                ctx._settle(xkey)                 # a deferred sum must be complete before the gradient is finalised
                 if cur is not None and ctx.owned.get(xkey, False):
                     dx = cur
                     K.conv_dgrad(gp, wt, as5d(phys(cur)), g, accumulate=True, relu_mask=mask, tf32_out=True)

@@ -400,6 +400,12 @@ def relu_tf32(x, y):
     _check(L.load().vlfb_relu_tf32(_ptr(_f32c(x)), _ptr(_f32c(y)), x.numel(), _stream()), 'relu_tf32')
 
 
+def add_relu_bwd_tf32(a, b, y, out):
+    """out = (y is None or y > 0) ? round_tf32(a + b) : 0 (one pass; out may alias a or b)."""
+    _check(L.load().vlfb_add_relu_bwd_tf32(_ptr(_f32c(a)), _ptr(_f32c(b)), _ptr(y), _ptr(_f32c(out)), a.numel(),
+                                            _stream()), 'add_relu_bwd_tf32')
+
+
 def relu_bwd_tf32(dy, y, dx):
     _check(L.load().vlfb_relu_bwd_tf32(_ptr(_f32c(dy)), _ptr(_f32c(y)), _ptr(_f32c(dx)), dy.numel(), _stream()),
            'relu_bwd_tf32')

@@ -65,6 +65,7 @@ SIGNATURES = {
     'vlfb_add_tf32': [_P, _P, _P, _L, _P],
     'vlfb_relu_tf32': [_P, _P, _L, _P],
     'vlfb_relu_bwd_tf32': [_P, _P, _P, _L, _P],
+    'vlfb_add_relu_bwd_tf32': [_P, _P, _P, _P, _L, _P],
     'vlfb_colsum': [_P, _L, _P, _L, _I, _I, _P],
     'vlfb_sigmoid_fwd': [_P, _P, _L, _P],
     'vlfb_dropout_fwd': [_P, _P, _L, _F, _U, _U, _P, _P],
