@@ -179,6 +179,16 @@ int vlfb_cl_to_nc(const float* src, float* dst, int N, int C, int64_t inner, int
 /* weights: wt[ci][tap][co] = round_tf32( w[co][tap][ci] * (scale ? scale[co] : 1) )  (dgrad B operand) */
 int vlfb_weight_transpose(const float* w, float* wt, const float* scale, int Co, int taps, int Ci,
                           void* stream);
+/* All dgrad weight operands of a step in ONE launch (81 convolutions -> 81 tiny kernels otherwise): `jobs` is a
+ * device array; job i owns the blocks [block_begin, next block_begin) of ceil(Ci/32) x ceil(Co/32) x taps tiles. */
+typedef struct {
+  const float* w;             /* [Co][taps][Ci] master weights                */
+  float* wt;                  /* [Ci][taps][Co] = round_tf32(w * scale[co])    */
+  const float* scale;         /* [Co] or NULL                                 */
+  int Co, taps, Ci;
+  int block_begin;
+} vlfb_wt_job_t;
+int vlfb_weight_transpose_multi(const vlfb_wt_job_t* jobs, int njobs, int total_blocks, void* stream);
 
 /* ---- losses (resnet_video.py:333-349) --------------------------------------------------- */
 /* Detectron SigmoidCrossEntropyLoss: loss[0] = scale * sum(per-elt) / max(#valid,1e-5) */

@@ -103,6 +103,11 @@ def weight_transpose(w, wt, scale=None):
     wt.copy_(_q(s.permute(2, 1, 0).reshape(wt.shape)))
 
 
+def weight_transpose_multi(jobs, cache):
+    for w, wt, s in jobs:
+        weight_transpose(w, wt, s)
+
+
 def _check_addressable(a, b, d):
     """Run the real wrapper's operand analysis so layout problems surface in the CPU tests."""
     from vlfb import kernels as RK

@@ -447,3 +447,24 @@ def test_colsum(K, rows, cols):
     assert rel_err(out, x.double().sum(0)) < 1e-5
     K.colsum(x.cuda(), cols, out, rows, cols, accumulate=True)
     assert rel_err(out, 2 * x.double().sum(0)) < 1e-5
+
+
+def test_weight_transpose_multi_matches_single(K):
+    """One launch for all dgrad weight operands of a step == the per-conv kernel."""
+    shapes = [(64, 1, 1, 1, 64), (96, 3, 1, 1, 32), (40, 1, 3, 3, 72), (512, 1, 1, 1, 2048)]
+    jobs, refs = [], []
+    for i, shp in enumerate(shapes):
+        w = torch.randn(shp, device='cuda')
+        sc = (torch.rand(shp[0], device='cuda') + 0.5) if i % 2 == 0 else None
+        taps = shp[1] * shp[2] * shp[3]
+        wt = torch.full((shp[4], taps, shp[0]), float('nan'), device='cuda')
+        ref = torch.empty_like(wt)
+        K.weight_transpose(w, ref, sc)
+        jobs.append((w, wt, sc))
+        refs.append(ref)
+    cache = {}
+    K.weight_transpose_multi(jobs, cache)
+    K.weight_transpose_multi(jobs, cache)          # second call reuses the device job table
+    torch.cuda.synchronize()
+    for (w, wt, sc), ref in zip(jobs, refs):
+        assert torch.equal(wt, ref)

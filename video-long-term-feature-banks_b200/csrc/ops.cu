@@ -549,6 +549,35 @@ __global__ void weight_transpose_k(const float* __restrict__ w, float* __restric
   }
 }
 
+// the same for every convolution of the net in one launch (block -> job by binary search over block_begin)
+__global__ void weight_transpose_multi_k(const vlfb_wt_job_t* __restrict__ jobs, int njobs) {
+  pdl_prologue();
+  __shared__ float tile[32][33];
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].block_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const vlfb_wt_job_t jb = jobs[lo];
+  const int local = blockIdx.x - jb.block_begin;
+  const int tci = (jb.Ci + 31) >> 5, tco = (jb.Co + 31) >> 5;
+  const int ci0 = (local % tci) * 32, co0 = ((local / tci) % tco) * 32, tap = local / (tci * tco);
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int co = co0 + r, ci = ci0 + threadIdx.x;
+    float v = 0.f;
+    if (co < jb.Co && ci < jb.Ci) {
+      v = jb.w[((int64_t)co * jb.taps + tap) * jb.Ci + ci];
+      if (jb.scale) v *= jb.scale[co];
+    }
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int ci = ci0 + r, co = co0 + threadIdx.x;
+    if (ci < jb.Ci && co < jb.Co) jb.wt[((int64_t)ci * jb.taps + tap) * jb.Co + co] = round_tf32(tile[threadIdx.x][r]);
+  }
+}
+
 // ------------------------------------------------------------------ losses (single block; R*classes is small)
 __device__ __forceinline__ float sce_elem(float x, float t) {
   // -(x*(t-(x>=0)) - log(1+exp(x-2x(x>=0))))
@@ -948,6 +977,13 @@ int vlfb_weight_transpose(const float* w, float* wt, const float* scale, int Co,
   VLFB_CHECK_ARG(w && wt && Co > 0 && taps > 0 && Ci > 0);
   dim3 grid(ceil_div(Ci, 32), ceil_div(Co, 32), taps), block(32, 8);
   launch_k(weight_transpose_k, grid, block, 0, ST(stream), w, wt, scale, Co, taps, Ci);
+  VLFB_CHECK_LAUNCH();
+  return VLFB_OK;
+}
+
+int vlfb_weight_transpose_multi(const vlfb_wt_job_t* jobs, int njobs, int total_blocks, void* stream) {
+  VLFB_CHECK_ARG(jobs && njobs > 0 && total_blocks > 0);
+  launch_k(weight_transpose_multi_k, dim3(total_blocks), dim3(32, 8), 0, ST(stream), jobs, njobs);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }

@@ -310,8 +310,10 @@ class ConvStep(Step):
         if ctx.net.requires.get(xkey, False):
             assert g.C != 4, 'the stem never propagates a gradient to the input clip'
             taps = g.kT * g.kH * g.kW
-            wt = empty((g.C, taps, g.Co))
-            K.weight_transpose(store.phys(self.w), wt, scale)     # wt = round_tf32(w * s)
+            wt = ctx.net.wt_buffers.get(id(self))                 # filled for all convs by one launch (_prepare_wt)
+            if wt is None:
+                wt = empty((g.C, taps, g.Co))
+                K.weight_transpose(store.phys(self.w), wt, scale)     # wt = round_tf32(w * s)
             cur = ctx.grads.get(xkey)
             prod = ctx.net.producer.get(xkey)
             if (isinstance(prod, ConvStep) and ctx.is_last_contribution(xkey) and FUSE_GRAD_FINISH
@@ -812,6 +814,9 @@ class CompiledNet(object):
             for k in st.out_keys:
                 self.producer[k] = st
         self.contrib = None          # key -> number of gradient contributions, recorded by the first eager run
+        self.wt_buffers = {}         # id(ConvStep) -> persistent [Ci][taps][Co] dgrad weight operand
+        self._wt_jobs = None
+        self._wt_cache = {}
         produced = set()
         self.external_inputs = []
         for op in ops:
@@ -959,6 +964,7 @@ class CompiledNet(object):
         if not self.train:
             return
         self.ws.params.begin_step(self.trainable)
+        self._prepare_wt(ctx)
         for n in self.losses:
             ctx.grads[(n, self.final_ver.get(n, 1))] = None
         for st in reversed(self.steps):
@@ -970,6 +976,27 @@ class CompiledNet(object):
             self.contrib = dict(ctx.counts)
         else:
             assert self.contrib == ctx.counts, 'gradient contribution counts changed between runs'
+
+    def _prepare_wt(self, ctx):
+        """Transposed, affine-scaled, TF32-rounded weights of every conv whose input needs a gradient: persistent
+        buffers (static addresses -> one device job table) filled by ONE launch per step instead of one per conv."""
+        if self._wt_jobs is None:
+            store = self.ws.params
+            jobs = []
+            for st in self.steps:
+                if isinstance(st, ConvStep) and self.requires.get(st.in_keys[0], False) and \
+                        any(self.requires.get(k, False) for k in st.out_keys):
+                    w = store.phys(st.w)
+                    co, ci = w.shape[0], w.shape[-1]
+                    if ci == 4:
+                        continue                                # the stem never propagates a gradient
+                    taps = w.numel() // (co * ci)
+                    wt = empty((ci, taps, co))
+                    self.wt_buffers[id(st)] = wt
+                    jobs.append((w, wt, store.phys(st.affine[0]) if st.affine else None))
+            self._wt_jobs = jobs
+        if self._wt_jobs:
+            K.weight_transpose_multi(self._wt_jobs, self._wt_cache)
 
     def run(self):
         """One pass.  Eager for the first runs of a given input signature; after that the whole

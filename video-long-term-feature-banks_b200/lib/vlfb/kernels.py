@@ -291,6 +291,30 @@ def matmul(a, b, d, alpha=1.0, accumulate=False, bias=None, tf32_out=False):
     _run_gemm(p, 'matmul', 2.0 * Bt * M * N * K)
 
 
+def weight_transpose_multi(jobs, cache):
+    """jobs = [(w, wt, scale_or_None)]: every dgrad weight operand of the step in one launch.  The device job
+    table is built once and kept in `cache` (all addresses are static: parameters and persistent wt buffers)."""
+    import numpy as np
+    key = tuple((w.data_ptr(), wt.data_ptr(), 0 if s is None else s.data_ptr()) for w, wt, s in jobs)
+    if cache.get('key') != key:
+        dt = np.dtype([('w', '<u8'), ('wt', '<u8'), ('scale', '<u8'), ('co', '<i4'), ('taps', '<i4'), ('ci', '<i4'),
+                       ('bb', '<i4')])
+        tab = np.zeros(len(jobs), dtype=dt)
+        blocks = 0
+        for i, (w, wt, s) in enumerate(jobs):
+            _f32c(w), _f32c(wt)
+            co, ci = w.shape[0], w.shape[-1]
+            taps = w.numel() // (co * ci)
+            tab[i] = (w.data_ptr(), wt.data_ptr(), 0 if s is None else s.data_ptr(), co, taps, ci, blocks)
+            blocks += ((ci + 31) // 32) * ((co + 31) // 32) * taps
+        assert tab.dtype.itemsize == 40
+        cache['table'] = torch.from_numpy(tab.view(np.uint8).copy()).to(jobs[0][0].device)
+        cache['blocks'] = blocks
+        cache['key'] = key
+    _check(L.load().vlfb_weight_transpose_multi(_ptr(cache['table']), len(jobs), cache['blocks'], _stream()),
+           'weight_transpose_multi')
+
+
 # --------------------------------------------------------------------------- streaming ops
 def affine_fwd(x, s, b, y):
     _check(L.load().vlfb_affine_nd_fwd(_ptr(_f32c(x)), _ptr(s), _ptr(b), _ptr(_f32c(y)),

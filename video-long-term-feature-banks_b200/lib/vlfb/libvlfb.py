@@ -73,6 +73,7 @@ SIGNATURES = {
     'vlfb_nc_to_cl': [_P, _P, _I, _I, _L, _I, _P],
     'vlfb_cl_to_nc': [_P, _P, _I, _I, _L, _I, _P],
     'vlfb_weight_transpose': [_P, _P, _P, _I, _I, _I, _P],
+    'vlfb_weight_transpose_multi': [_P, _I, _I, _P],
     'vlfb_sigmoid_ce_fwd': [_P, _P, _P, _L, _F, _P],
     'vlfb_sigmoid_ce_bwd': [_P, _P, _P, _P, _L, _F, _P],
     'vlfb_softmax_ce_fwd': [_P, _P, _P, _P, _I, _I, _F, _P],
