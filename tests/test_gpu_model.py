@@ -182,6 +182,34 @@ def test_grad_finish_fusion_and_graph_replay_agree_with_first_run(ws):
         assert worst < 2e-5, (rep, worst)
 
 
+def test_enqueue_blobs_matches_feed_blob(ws):
+    """Asynchronous feeding (copy stream + staging slots + dequeue at RunNet) gives the same step as FeedBlob,
+    batch after batch, including after the step has been captured into a CUDA graph."""
+    from oracle import model as OM
+    H.setup_cfg('ava_r50_lfb_nl.yaml', TINY)
+    ocfg = H.oracle_cfg('ava_r50_lfb_nl.yaml', TINY)
+    params = OM.make_params(ocfg, seed=2)
+    model, sfx = H.build('train', True)
+    H.feed_params(params)
+    net = ws.current().nets[model.net.Proto().name]
+    net.update_ops = []
+    batches = [OM.make_inputs(ocfg, n_clips=2, rois_per_clip=2, crop=64, frames=8, seed=50 + i) for i in range(4)]
+    want = []
+    for b in batches:
+        H.feed_inputs(b, sfx)
+        ws.RunNet(model.net.Proto().name)
+        want.append((float(ws.FetchBlob('gpu_0/loss')), ws.FetchBlob('gpu_0/pred').copy()))
+    assert len(set(w[0] for w in want)) == 4, 'the batches must differ'
+    host = [dict(('gpu_0/%s%s' % (k, sfx), v.contiguous().pin_memory()) for k, v in b.items()) for b in batches]
+    ws.EnqueueBlobs(host[0])
+    for i in range(4):
+        ws.RunNet(model.net.Proto().name)
+        if i + 1 < 4:
+            ws.EnqueueBlobs(host[i + 1])             # overlaps the step that is running
+        assert abs(float(ws.FetchBlob('gpu_0/loss')) - want[i][0]) <= 1e-6 * abs(want[i][0])
+        assert H.rel(ws.FetchBlob('gpu_0/pred'), want[i][1]) < 1e-6
+
+
 def test_tiny_simt_engine_agrees(ws):
     """Same graph on the SIMT fp32 engine: isolates TF32 effects from logic errors."""
     _train_case(ws, 'ava_r50_lfb_nl.yaml', TINY, 64, 8, 2, backend='simt')

@@ -202,6 +202,11 @@ class Workspace(object):
         self.rng_offset = 0
         self.last_grads = {}
         self.input_cache = {}
+        # asynchronous input queue (EnqueueBlobs): copy stream, staging slot, the batch waiting to be dequeued
+        self.copy_stream = None
+        self.queue_slot = 0
+        self.queued = None
+        self.slot_free = {}
         self.force_eager = False
         self.step = 0
         self._step_t = None
@@ -318,8 +323,58 @@ def RunNet(name, num_iter=1):
     """One forward (+ backward + all-reduce + SGD for a training net) pass (tools/train_net.py:152)."""
     net = _ws.nets[str(name)]
     for _ in range(num_iter):
+        _dequeue_blobs()
         net.run()
     return True
+
+
+def EnqueueBlobs(feed):
+    """Asynchronous feeding: stands in for the reference's BlobsQueue + DequeueBlobs pair (dataloader.py:278-290,
+    model_builder_video.py add_inputs).  `feed` maps blob names to (pinned) host tensors of the NEXT batch; the
+    host-to-device copies run on a side stream into one of two staging slots, i.e. behind the step that is
+    currently executing, and the next RunNet dequeues them (layout conversion + TF32 rounding into the static
+    input buffers) before it starts.  One batch can be queued at a time."""
+    ws = _ws
+    if X.DEVICE == 'cpu':
+        for name, arr in feed.items():
+            FeedBlob(name, arr)
+        return True
+    assert ws.queued is None, 'EnqueueBlobs: the previous batch has not been consumed by RunNet yet'
+    if ws.copy_stream is None:
+        ws.copy_stream = torch.cuda.Stream()
+    slot = ws.queue_slot
+    ws.queue_slot ^= 1
+    main = torch.cuda.current_stream()
+    free = ws.slot_free.get(slot)
+    if free is not None:
+        ws.copy_stream.wait_event(free)            # the conversion kernels that read this slot have finished
+    staged = {}
+    with torch.cuda.stream(ws.copy_stream):
+        for name, arr in feed.items():
+            src = arr if isinstance(arr, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(arr))
+            is_int = src.dtype in (torch.int32, torch.int64, torch.uint8, torch.bool, torch.int16, torch.int8)
+            st = _static('%s/stage%d' % (_unscoped(name), slot), src.shape, torch.int32 if is_int else X.DTYPE)
+            st.copy_(src, non_blocking=True)
+            staged[_unscoped(name)] = st
+        ev = torch.cuda.Event()
+        ev.record(ws.copy_stream)
+    ws.queued = (slot, staged, ev)
+    del main
+    return True
+
+
+def _dequeue_blobs():
+    ws = _ws
+    if ws.queued is None:
+        return
+    slot, staged, ev = ws.queued
+    ws.queued = None
+    torch.cuda.current_stream().wait_event(ev)
+    for name, st in staged.items():
+        _feed_activation(name, st)
+    done = torch.cuda.Event()
+    done.record(torch.cuda.current_stream())
+    ws.slot_free[slot] = done
 
 
 def _static(key, shape, dtype):
@@ -344,8 +399,11 @@ def _feed_activation(name, arr):
         n, c = src.shape[0], src.shape[1]
         inner = src.shape[2] * src.shape[3] * src.shape[4]
         cpad = 4 if c == 3 else c
-        stage = _static(name + '/ncthw', src.shape, X.DTYPE)
-        stage.copy_(src, non_blocking=True)                       # H2D (async from pinned memory)
+        if src.is_cuda and src.dtype == X.DTYPE:
+            stage = src                                           # already staged on the device (EnqueueBlobs)
+        else:
+            stage = _static(name + '/ncthw', src.shape, X.DTYPE)
+            stage.copy_(src, non_blocking=True)                   # H2D (async from pinned memory)
         p = _static(name, (n, src.shape[2], src.shape[3], src.shape[4], cpad), X.DTYPE)
         X.K.nc_to_cl(stage, p, n, c, inner, cpad)                 # reference NCTHW blob -> NDHWC (+pad 3->4)
         X.K.round_tf32(p.view(-1), p.view(-1))
