@@ -295,8 +295,10 @@ def run_b200(args):
                      'traffic_source': 'profiles/r01_ncu_launches_final_summary.txt: dram__bytes_read+write summed over '
                                        'the 292 GEMM launches of one step (16.2 GB) / 292',
                      'flop_per_launch': gflop_step * 1e9 / max(len(recs), 1),
-                     'kernel': 'vlfb::tc::gemm_tc_kernel (all %d launches of one step, %.2f ms of %.2f ms)' % (
-                         len(recs), gemm_ms, ms),
+                     'kernel': 'vlfb::tc::gemm_tc_kernel: all %d launches of one step timed with CUDA events around each '
+                               'launch in an eager step = %.2f ms (includes inter-launch gaps, so achieved is a lower '
+                               'bound; ncu kernel time of the same launches: profiles/r01_ncu_launches_final_summary.txt); '
+                               'the captured step takes %.2f ms in total' % (len(recs), gemm_ms, ms),
                      'peak_source': '%s bf16_tflops_sustained / 2 (kind::tf32)' % peak_src,
                      'by_kind': dict((k, {'ms': v[0], 'tflops': v[1] / 1e9 / v[0] if v[0] else 0, 'launches': v[2]})
                                      for k, v in by_kind.items())},
