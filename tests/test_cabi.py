@@ -48,3 +48,16 @@ def test_struct_layout_matches_header(tmp_path):
     assert sizes == [ctypes.sizeof(L.ConvGeom), ctypes.sizeof(L.Operand), ctypes.sizeof(L.GemmParams)]
     assert offs == [getattr(L.GemmParams, f).offset for f in fields]
 
+
+def test_wt_job_layout(tmp_path):
+    """The device job table of vlfb_weight_transpose_multi is written from numpy: 40-byte records."""
+    import subprocess
+    src = tmp_path / 'job.c'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vlfb.h"\nint main(void) {\n'
+                   '  printf("%zu %zu %zu %zu %zu\\n", sizeof(vlfb_wt_job_t), offsetof(vlfb_wt_job_t, wt), '
+                   'offsetof(vlfb_wt_job_t, scale), offsetof(vlfb_wt_job_t, Co), offsetof(vlfb_wt_job_t, block_begin));\n'
+                   '  return 0;\n}\n')
+    exe = tmp_path / 'job'
+    subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+    assert subprocess.check_output([str(exe)]).decode().split() == ['40', '8', '16', '24', '36']
+

@@ -25,6 +25,7 @@ K = K_default          # tests may swap in a torch-CPU kernel set (tests/fake_ke
 DEVICE = 'cuda'
 DTYPE = torch.float32      # the CUDA kernels are fp32-only; the CPU test stand-in may run the host logic in fp64
 STATS = {'fused_grad_finish': 0}
+SIDE_WGRAD = os.environ.get('VLFB_SIDE_WGRAD', '0') == '1'         # weight-gradient GEMMs on a second stream (experiment)
 LAZY_GRAD_SUM = os.environ.get('VLFB_LAZY_GRAD_SUM', '1') != '0'   # defer residual + dgrad sums into the consumer's mask/round pass
 # Fold the ReLU backward + TF32 rounding of a conv's incoming gradient (and the sum of its earlier contributions)
 # into the epilogue of the dgrad GEMM that delivers the last contribution.  Exact (tests run both ways), but OFF by
@@ -129,6 +130,21 @@ class Ctx(object):
         # lazy two-term sums: grads[key] (owned) + pending[key] (an alias of somebody else's gradient, e.g. the
         # residual branch).  A conv that owns `key` folds the sum into its ReLU-backward / rounding pass.
         self.pending = {}
+        self.keepalive = []
+
+    def side_stream(self):
+        if not SIDE_WGRAD or DEVICE == 'cpu':
+            return None
+        if self.net._side is None:
+            self.net._side = torch.cuda.Stream()
+        return self.net._side
+
+    def join_side(self):
+        if self.net._side is not None and self.keepalive:
+            ev = torch.cuda.Event()
+            ev.record(self.net._side)
+            torch.cuda.current_stream().wait_event(ev)
+        self.keepalive = []
 
     # ---- blobs
     def get(self, name):
@@ -295,7 +311,18 @@ class ConvStep(Step):
         store = ctx.ws.params
         if store.trainable(self.w):
             mask = store.stem_mask() if g.C == 4 else None
-            K.conv_wgrad(gp, xp, store.grad(self.w), g, row_scale=scale, col_mask=mask)
+            side = ctx.side_stream()
+            if side is None:
+                K.conv_wgrad(gp, xp, store.grad(self.w), g, row_scale=scale, col_mask=mask)
+            else:
+                # the weight gradient is off the critical path (nothing in backward reads it): run it on a second
+                # stream next to the dgrad chain so that its CTAs fill the SMs the small-M layers leave idle
+                ev = torch.cuda.Event()
+                ev.record()
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    K.conv_wgrad(gp, xp, store.grad(self.w), g, row_scale=scale, col_mask=mask)
+                ctx.keepalive.extend([gp, xp])        # no reuse of these blocks before the join
         if self.b and store.trainable(self.b):
             db = store.grad(self.b)
             rows = gp.numel() // g.Co
@@ -817,6 +844,7 @@ class CompiledNet(object):
         self.wt_buffers = {}         # id(ConvStep) -> persistent [Ci][taps][Co] dgrad weight operand
         self._wt_jobs = None
         self._wt_cache = {}
+        self._side = None
         produced = set()
         self.external_inputs = []
         for op in ops:
@@ -972,6 +1000,7 @@ class CompiledNet(object):
                 st.bwd(ctx)
             elif any(k in ctx.grads for k in st.out_keys):
                 st.bwd(ctx)
+        ctx.join_side()
         if self.contrib is None:
             self.contrib = dict(ctx.counts)
         else:
