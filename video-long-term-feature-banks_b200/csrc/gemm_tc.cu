@@ -4,10 +4,12 @@
 //
 // Persistent kernel: grid = min(#tiles, #SMs), one CTA per SM walks a static sequence of 128 x BN output
 // tiles (UMMA M=128, N=BN, cta_group::1), 544 threads:
-//   warps 0-7  PRODUCERS -- im2col-free gather of the A/B K-chunks (32 fp32 = one 128-byte swizzle row)
-//              straight from NDHWC tensors into the UMMA canonical swizzled shared-memory layouts with
-//              16-byte cp.async (zero-fill = conv padding); dense operands are fetched by TMA instead
-//              (cp.async.bulk.tensor, SWIZZLE_128B for K-major, SWIZZLE_128B_ATOM_32B for MN-major);
+//   warps 0-7  PRODUCERS -- the A/B K-chunks (32 fp32 = one 128-byte swizzle row) go straight from NDHWC
+//              tensors into the UMMA canonical swizzled shared-memory layouts, never through an im2col
+//              buffer: dense operands by TMA tiled boxes (SWIZZLE_128B K-major, SWIZZLE_128B_ATOM_32B
+//              MN-major), convolution gathers by TMA im2col copies (conv fwd, unit-stride dgrad, wgrad;
+//              one thread issues), and what TMA cannot express (conv1 stem with 16-byte pixels, strided
+//              dgrad, unaligned operands) by 16-byte cp.async with zero-fill = padding (all 8 warps);
 //   warp 8     TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit releases each smem
 //              stage back to the producers and hands finished accumulators to the epilogue;
 //   warps 9-16 EPILOGUE -- tcgen05.ld TMEM -> registers -> smem transpose -> fused affine / residual /
@@ -491,7 +493,9 @@ struct Launch {
   PosDiv in;     // ... and of the INPUT extents (W, H, T) for the dgrad row decode
   FastDiv cdiv;  // input channels C (wgrad: n -> (tap, ci))
   FastDiv kwdiv; // kW
-  int tma_a, tma_b;  // operand fetched by TMA instead of cp.async: 1 = dense tiled boxes, 2 = im2col (conv gathers)
+  int tma_a, tma_b;  // operand fetched by TMA instead of cp.async: 1 = dense tiled boxes, 2 = im2col (conv gathers),
+                     // 3 = conv1 stem im2col (16-byte pixels, no-swizzle K-major tile [kw][row][16 B])
+  int stem_lbo, stem_sbo;  // UMMA descriptor strides of that tile (bytes)
   int lag;           // cp.async groups kept in flight before a stage is published (< stages)
   int tiles_m, tiles_n, total_tiles;
   int fence_mode;    // 0: producers fence.proxy.async before publishing a stage; 1: the MMA thread fences after acquiring it
@@ -557,6 +561,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  const bool stem_a = AK == VLFB_OP_STEM_K && L.tma_a == 3;
+  if (stem_a) {
+    // the 8th pixel of a conv1 filter row is padding (kW = 7): its weights are zero, its 2 KB slice of every
+    // stage is zeroed once here and never written again
+    for (int s = 0; s < S; ++s)
+      for (int i = tid; i < 2048 / 16; i += NTHREADS)
+        *reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)) + s * stage_bytes + 7 * 2048 + i * 16) =
+            make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_proxy_async();
+  }
   const uint32_t tmem_cols = (uint32_t)(2 * bn < 32 ? 32 : 2 * bn);
   if (warp == NPW) tmem_alloc(tptr_addr, tmem_cols);
   tc_fence_before();
@@ -594,7 +608,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
           if (!tma_b) { if (is_mn(BK)) mb.init(p, p.b, ti.n0, bn, p.N, ti.batch, ti.tap, L.cdiv, L.kwdiv); else { kb.init(p, p.b, ti.n0, bn, p.N, ti.batch, L.out, L.in, ti.k_begin / KC); kb.kend = ti.k_end; } }
         }
         const int kc0 = ti.k_begin / KC;
-        uint32_t tma_bytes = (tma_a ? (uint32_t)A_TILE_BYTES : 0u) + (tma_b ? b_tile_bytes : 0u);
+        uint32_t tma_bytes = (tma_a ? (stem_a ? 7u * 2048u : (uint32_t)A_TILE_BYTES) : 0u) + (tma_b ? b_tile_bytes : 0u);
+        if (tid == 0 && stem_a) {
+          const vlfb_conv_geom_t& g = p.g;
+          const Pos4 o = decode_pos_fast((uint32_t)ti.m0, L.out);
+          ia_w = o.w * g.sW - g.pW; ia_h = o.h * g.sH - g.pH; ia_d = o.t * g.sT - g.pT; ia_n = o.n;
+          ic_t = kc0 / g.kH;
+          ic_h = kc0 - ic_t * g.kH;
+        }
         if (tid == 0 && im2col_a) {
           const vlfb_conv_geom_t& g = p.g;
           if (AK == VLFB_OP_CONV_K) {
@@ -636,7 +657,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
           const uint32_t b_tile = a_tile + A_TILE_BYTES;
           if (tid == 0 && tma_bytes) {
             mbar_expect_tx(full0 + 8 * s_cur, tma_bytes);
-            if (im2col_a) {
+            if (stem_a) {
+              // one (kt,kh) filter row = 7 copies of 128 pixels x 16 bytes, each a [row][16 B] slab
+              const vlfb_conv_geom_t& g = p.g;
+#pragma unroll
+              for (int kw = 0; kw < 7; ++kw)
+                if (kw < g.kW) tma_load_im2col(a_tile + kw * 2048, &tmA, 0, ia_w, ia_h, ia_d, ia_n, kw, ic_h, ic_t, full0 + 8 * s_cur);
+              if (++ic_h == g.kH) { ic_h = 0; ++ic_t; }
+            } else if (im2col_a) {
               const vlfb_conv_geom_t& g = p.g;
               if (AK == VLFB_OP_CONV_K)
                 tma_load_im2col(a_tile, &tmA, ic_c * KC, ia_w, ia_h, ia_d, ia_n, ic_w * g.dW, ic_h * g.dH, ic_t * g.dT,
@@ -726,7 +754,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
 #pragma unroll
           for (int j = 0; j < KC / 8; ++j) {          // UMMA K = 8 for tf32
             uint64_t da, db;
-            if (!is_mn(AK)) da = make_desc(a_tile + j * 32, 16, 1024);
+            if (stem_a) da = make_desc(a_tile + j * 4096, (uint32_t)L.stem_lbo, (uint32_t)L.stem_sbo, 0);
+            else if (!is_mn(AK)) da = make_desc(a_tile + j * 32, 16, 1024);
             else da = make_desc(a_tile + j * 1024, 4096, 512, 1);
             if (!is_mn(BK)) db = make_desc(b_tile + j * 32, 16, 1024);
             else db = make_desc(b_tile + j * 1024, 4096, 512, 1);
@@ -988,7 +1017,8 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                    CUtensorMapFloatOOBfill);
 static bool make_tmap_im2col(CUtensorMap* tm, const float* base, int N, int D, int H, int W, int C, const int lower[3],
-                             const int upper[3], const int strides[3], int pixels, CUtensorMapSwizzle swz) {
+                             const int upper[3], const int strides[3], int pixels, CUtensorMapSwizzle swz,
+                             int chan = KC) {
   static EncodeIm2colFn enc = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -999,19 +1029,19 @@ static bool make_tmap_im2col(CUtensorMap* tm, const float* base, int N, int D, i
         q == cudaDriverEntryPointSuccess)
       enc = reinterpret_cast<EncodeIm2colFn>(ptr);
   }
-  if (!enc || (C % KC) != 0 || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+  if (!enc || (C % chan) != 0 || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
   for (int i = 0; i < 3; ++i)
     if (lower[i] < -16 || lower[i] > 15 || upper[i] < -16 || upper[i] > 15 || strides[i] < 1 || strides[i] > 8) return false;
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
   cuuint64_t gstr[4] = {(cuuint64_t)C * 4, (cuuint64_t)C * 4 * W, (cuuint64_t)C * 4 * W * H, (cuuint64_t)C * 4 * W * H * D};
   cuuint32_t estr[5] = {1, (cuuint32_t)strides[0], (cuuint32_t)strides[1], (cuuint32_t)strides[2], 1};
-  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, gstr, lower, upper, KC,
-             (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, gstr, lower, upper,
+             (cuuint32_t)chan, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // tuning overrides, read once (scripts/tune_gemm.py)
-struct Env { int bn, stages, lag, fence; bool tma_mn, im2col; };
+struct Env { int bn, stages, lag, fence, stem_im2col, stem_lbo, stem_sbo; bool tma_mn, im2col; };
 static Env read_env() {
   Env e;
   auto geti = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
@@ -1021,6 +1051,9 @@ static Env read_env() {
   e.fence = geti("VLFB_FENCE", 0);
   e.tma_mn = geti("VLFB_TMA_MN", 1) != 0;
   e.im2col = geti("VLFB_IM2COL", 1) != 0;
+  e.stem_im2col = geti("VLFB_STEM_IM2COL", 0);
+  e.stem_lbo = geti("VLFB_STEM_LBO", 2048);
+  e.stem_sbo = geti("VLFB_STEM_SBO", 128);
   return e;
 }
 
@@ -1077,6 +1110,8 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
   L.lag = L.stages - 1 < 2 ? L.stages - 1 : 2;
   if (env.lag >= 1 && env.lag < L.stages && env.lag <= 5) L.lag = env.lag;
   L.fence_mode = env.fence;
+  L.stem_lbo = env.stem_lbo;
+  L.stem_sbo = env.stem_sbo;
   L.tiles_m = tiles_m;
   L.tiles_n = ceil_div(p.N, L.bn);
   L.total_tiles = (int)((int64_t)L.tiles_m * L.tiles_n * zdim);
@@ -1116,6 +1151,9 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
       if (make_tmap_im2col(&tmA, p.a.ptr, g.N, g.To, g.Ho, g.Wo, g.Co, lo, hi, ones, BM, CU_TENSOR_MAP_SWIZZLE_128B))
         L.tma_a = 2;
     }
+    if (AK == VLFB_OP_STEM_K && env.stem_im2col &&
+        make_tmap_im2col(&tmA, p.a.ptr, g.N, g.T, g.H, g.W, 4, pad_lo, pad_hi, cstr, BM, CU_TENSOR_MAP_SWIZZLE_NONE, 4))
+      L.tma_a = 3;
     if (BK == VLFB_OP_CONV_MN && (g.C % KC) == 0 && L.tma_a &&
         make_tmap_im2col(&tmB, p.b.ptr, g.N, g.T, g.H, g.W, g.C, pad_lo, pad_hi, cstr, KC,
                          CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
