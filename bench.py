@@ -40,6 +40,23 @@ def fbo_gflop(rois, bank_rows, layers):
     return 3.0 * fwd / 1e9
 
 
+def stage_of(label):
+    """Blob name of a graph step -> stage of the network (the north star quotes res4/res5 separately)."""
+    n = label.split('/')[-1]
+    if n.startswith('conv1') or n.startswith('res_conv1'):
+        return 'conv1'
+    for st in ('res2', 'res3', 'res4', 'res5'):
+        if n.startswith(st + '_'):
+            return st
+    if n.startswith('nonlocal_conv3'):
+        return 'nl3'
+    if n.startswith('nonlocal_conv4'):
+        return 'nl4'
+    if n.startswith('lfb') or 'fbonl' in n:
+        return 'fbo'
+    return 'head'
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
@@ -239,26 +256,38 @@ def run_b200(args):
     recs = K.stop_profile()
     workspace.current().force_eager = False
     gemm_ms = sum(r[1] for r in recs)
-    by_kind = {}
+    by_kind, by_stage = {}, {}
     if rank == 0 and args.dump_gemms:
         with open(args.dump_gemms, 'w') as f:
-            for kind, t, fl in sorted(recs, key=lambda r: -r[1]):
-                f.write('%8.3f ms %8.1f TFLOP/s  %s\n' % (t, fl / 1e9 / t if t else 0, kind))
-    for kind, t, f in recs:
-        kind = kind.split(' ')[0]
-        a = by_kind.setdefault(kind, [0.0, 0.0, 0])
-        a[0] += t
-        a[1] += f
-        a[2] += 1
+            for kind, t, fl, nb, lab in sorted(recs, key=lambda r: -r[1]):
+                f.write('%8.3f ms %8.1f TFLOP/s %7.0f GB/s  %-28s %s\n' % (
+                    t, fl / 1e9 / t if t else 0, nb / 1e6 / t if t else 0, lab.split('/')[-1], kind))
     if rank != 0:
         return
-    assert np.isfinite(loss), 'loss is not finite'
     peaks, peak_src = measured_peaks()
+    peak_tf32 = peaks['bf16_tflops_sustained'] / 2.0                  # kind::tf32 issues at half the bf16 rate
+    roof_ms = 0.0            # sum over launches of max(flops / tensor peak, algorithmic bytes / HBM peak)
+    for kind, t, f, nb, lab in recs:
+        t_roof = max(f / (peak_tf32 * 1e9), nb / (peaks['hbm_gbs'] * 1e6))        # ms
+        roof_ms += t_roof
+        for table, key in ((by_kind, kind.split(' ')[0]), (by_stage, stage_of(lab))):
+            a = table.setdefault(key, [0.0, 0.0, 0, 0.0, 0.0])
+            a[0] += t
+            a[1] += f
+            a[2] += 1
+            a[3] += nb
+            a[4] += t_roof
+
+    def table_json(tb):
+        return dict((k, {'ms': round(v[0], 4), 'tflops': round(v[1] / 1e9 / v[0], 1) if v[0] else 0, 'launches': v[2],
+                         'tensor_frac': round(v[1] / 1e9 / v[0] / peak_tf32, 3) if v[0] else 0,
+                         'alg_gbs': round(v[3] / 1e6 / v[0], 0) if v[0] else 0,
+                         'roof_frac': round(v[4] / v[0], 3) if v[0] else 0}) for k, v in sorted(tb.items()))
+    assert np.isfinite(loss), 'loss is not finite'
     layers = cfg.FBO_NL.NUM_LAYERS
     rois = CLIPS_PER_GPU * ROIS_PER_CLIP
     gflop_step = CLIPS_PER_GPU * GFLOP_PER_CLIP_FWD_BWD + fbo_gflop(rois, BANK_ROWS, layers)
     achieved = gflop_step / gemm_ms if gemm_ms > 0 else 0.0          # GFLOP/ms == TFLOP/s
-    peak_tf32 = peaks['bf16_tflops_sustained'] / 2.0                  # kind::tf32 issues at half the bf16 rate
     clips = CLIPS_PER_GPU * n_gpus
 
     # ---- CPU baseline: the oracle on this box's host cores, bounded sample (N=1 only)
@@ -300,8 +329,13 @@ def run_b200(args):
                                'bound; ncu kernel time of the same launches: profiles/r01_ncu_launches_final_summary.txt); '
                                'the captured step takes %.2f ms in total' % (len(recs), gemm_ms, ms),
                      'peak_source': '%s bf16_tflops_sustained / 2 (kind::tf32)' % peak_src,
-                     'by_kind': dict((k, {'ms': v[0], 'tflops': v[1] / 1e9 / v[0] if v[0] else 0, 'launches': v[2]})
-                                     for k, v in by_kind.items())},
+                     'per_launch_roofline': {
+                         'what': 'sum over the GEMM launches of max(flops / tensor peak, algorithmic bytes / HBM peak) '
+                                 '/ measured time: the fp32 activations make the res2/res3/stem layers HBM-bound',
+                         'roof_ms': round(roof_ms, 3), 'measured_ms': round(gemm_ms, 3),
+                         'frac': round(roof_ms / gemm_ms, 3) if gemm_ms else None,
+                         'hbm_peak_gbs': peaks['hbm_gbs']},
+                     'by_kind': table_json(by_kind), 'by_stage': table_json(by_stage)},
         'cpu_baseline': cpu,
         'loss': loss,
     }))

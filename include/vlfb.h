@@ -31,6 +31,7 @@ extern "C" {
 #define VLFB_E_BADARG (-1)
 #define VLFB_E_UNSUPPORTED (-2)
 #define VLFB_E_CUDA (-3)
+#define VLFB_E_WORKSPACE (-4)   /* caller-provided workspace too small (see the *_workspace query) */
 
 /* ---- library ------------------------------------------------------------------------- */
 int vlfb_version(void);                 /* 100 * major + minor */
@@ -215,6 +216,26 @@ int vlfb_fbo_attend_fwd(const float* theta, const float* phi, const float* g, fl
 int vlfb_fbo_attend_bwd(const float* theta, const float* phi, const float* g, const float* prob,
                         const float* dy, float* dtheta, float* dphi,
                         float* dg, int R, int L, int d, float scale, void* stream);
+
+/* ---- inference-mode FBO-NL over the RAW bank (csrc/fbo.cu) --------------------------------
+ * Replaces, per FBO-NL layer of a test-mode graph (no dropout between 'lfb_1x1' and phi/g), the operators
+ * Conv 'lfb_1x1' (lfb_helper.py:320-338), Conv '{prefix}_phi' / '{prefix}_g' (:183-202), BatchMatMul / Scale /
+ * Softmax / BatchMatMul (:223-234) by ONE pass over the bank: with q = W_1^T W_phi^T theta (computed by the caller),
+ *   out[r][:] = sum_j softmax_j(scale * q[r].bank[r][j]) * bank[r][j][:]            (then y = W_g (W_1 out + c_1) + c_g).
+ * bank [R][L][D] fp32 (D in {1024, 2048, 4096}), q [R][D], out [R][D]; prob [R][L] optional (NULL: not kept).
+ * tf32_out != 0 rounds `out` to TF32 (it feeds a tensor-core matmul).  The L rows of a RoI are split over
+ * vlfb_fbo_bank_scan_splits() CTAs whose partial (max, sum, weighted rows) land in `workspace`. */
+int vlfb_fbo_bank_scan_splits(int R, int L, int D);
+size_t vlfb_fbo_bank_scan_workspace(int R, int L, int D);
+int vlfb_fbo_bank_scan(const float* bank, const float* q, float scale, float* out, float* prob, int R, int L, int D,
+                       int tf32_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- device-resident feature bank: window assembly (tools/lfb_loader.py:51-152 builds the bank,
+ *      lib/datasets/ava.py:300-323 / charades.py:251-276 sample a window per example) -----------
+ * out[i][:] = idx[i] >= 0 ? bank[idx[i]][:] : 0 for `rows` output rows of D floats; idx is a device int32 table the
+ * host fills with the reference's own sampling logic (-1 = zero padding). */
+int vlfb_lfb_gather(const float* bank, int64_t bank_rows, const int32_t* idx, float* out, int64_t rows, int D,
+                    int tf32_out, void* stream);
 
 #ifdef __cplusplus
 }

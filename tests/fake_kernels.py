@@ -343,6 +343,25 @@ def sgd_nesterov(p, g, m, lr, momentum, wd, nesterov=True, p_tf32=None):
         p_tf32.copy_(_q(p))
 
 
+def fbo_bank_scan(bank, q, out, scale, prob=None, tf32_out=False):
+    assert bank.is_contiguous() and q.is_contiguous() and out.is_contiguous()
+    assert bank.shape[2] in (1024, 2048, 4096), 'csrc/fbo.cu supports D in {1024, 2048, 4096}'
+    p = torch.softmax(torch.einsum('rld,rd->rl', bank, q) * scale, dim=1)
+    if prob is not None:
+        prob.copy_(p)
+    out.copy_(_q(torch.einsum('rl,rld->rd', p, bank), tf32_out))
+
+
+def lfb_gather(bank, idx, out, tf32_out=False):
+    assert idx.dtype == torch.int32
+    flat_out = out.view(-1, out.shape[-1])
+    rows = bank.view(-1, bank.shape[-1])
+    i = idx.view(-1).long()
+    ok = (i >= 0) & (i < rows.shape[0])
+    flat_out.zero_()
+    flat_out[ok] = _q(rows[i[ok]], tf32_out)
+
+
 def install():
     """Route vlfb.executor / vlfb.workspace onto this module and the CPU device."""
     import sys

@@ -207,3 +207,35 @@ def test_grad_finish_fusion_is_exact_under_tf32_emulation(fake):
     finally:
         fake.EMULATE_TF32 = False
         X.FUSE_GRAD_FINISH, X.LAZY_GRAD_SUM = fuse0, lazy0
+
+
+@pytest.mark.parametrize('yaml_name,layers', [('ava_r50_lfb_nl.yaml', 2), ('ava_r50_lfb_nl_3l.yaml', 3),
+                                               ('charades_r50_lfb_nl.yaml', 2)])
+def test_inference_fbo_fold_matches_oracle_and_unfolded_graph(fake, yaml_name, layers):
+    """Test-mode nets run every FBO-NL layer as one pass over the raw bank (executor.FboFoldStep); the result must
+    equal the oracle's as-written graph and the engine's own unfolded lowering."""
+    from oracle import model as OM
+    from vlfb import workspace
+    from vlfb import executor as X
+    from core.config import config as cfg
+    ov = TINY + (['MODEL.NUM_CLASSES', 157] if 'charades' in yaml_name else [])
+    ocfg = H.oracle_cfg(yaml_name, ov)
+    params = OM.make_params(ocfg, seed=2, split='val')
+    inputs = OM.make_inputs(ocfg, n_clips=2, rois_per_clip=3, crop=64, frames=8)
+    blobs, _, _ = OM.forward(ocfg, dict((k, v.double()) for k, v in params.items()),
+                             dict((k, (v.double() if v.dtype == torch.float32 else v)) for k, v in inputs.items()), 'val')
+    got = {}
+    for fold in (True, False):
+        H.setup_cfg(yaml_name, ov)
+        cfg.B200.FBO_FOLD = fold
+        workspace.ResetWorkspace()
+        model, sfx = H.build('val', False)
+        H.feed_params(params)
+        H.feed_inputs(inputs, sfx)
+        net = workspace.current().nets[model.net.Proto().name]
+        assert sum(isinstance(s, X.FboFoldStep) for s in net.steps) == (layers if fold else 0)
+        workspace.RunNet(model.net.Proto().name)
+        for b in ['lfb_nl0_affinity_prob', 'lfb_nl%d_sum' % (layers - 1), 'pool5', 'pred', 'prob']:
+            got[(fold, b)] = workspace.FetchBlob('gpu_0/' + b)
+            assert H.rel(got[(fold, b)].reshape(-1), blobs[b].detach().numpy().reshape(-1)) < 1e-9, (fold, b)
+        assert workspace.HasBlob('gpu_0/lfb_1x1') == (not fold)

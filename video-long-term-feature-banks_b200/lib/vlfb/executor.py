@@ -618,6 +618,56 @@ class BatchMatMulStep(Step):
             ctx.add_grad(self.in_keys[1], db, owned=True)
 
 
+class FboFoldStep(Step):
+    """Inference-mode FBO-NL layer folded onto the RAW bank (csrc/fbo.cu header; SURVEY 8d "eval mode").
+
+    Replaces Conv lfb_1x1 -> {Conv phi, Conv g} -> Reshape x2 -> BatchMatMul(theta, phi, trans_a) -> Scale ->
+    Softmax -> BatchMatMul(g, p, trans_b) of lfb_helper.py:320-338,175-234 when the graph has no dropout between
+    them (test / val nets) and one query per RoI:
+        u = theta W_phi ; q = u W_1 ; s = sum_j softmax_j(scale q.b_j) b_j ; t = s W_1^T + c_1 ; y = t W_g^T + c_g.
+    The four R-row matmuls run on the tensor-core GEMM; the bank pass is the HBM-bound kernel fbo_bank_scan.  The
+    intermediate blobs of the replaced operators (lfb_1x1, *_phi, *_g, *_affinity) are not materialised;
+    *_affinity_prob is (it is what visualisation code fetches).  B200.FBO_FOLD False keeps the as-written graph."""
+
+    def __init__(self, op, in_keys, out_keys, theta, bank, w1, b1, wphi, wg, bg, scale, prob_name):
+        Step.__init__(self, op, in_keys, out_keys)
+        self.theta, self.bank = theta, bank
+        self.w1, self.b1, self.wphi, self.wg, self.bg = w1, b1, wphi, wg, bg
+        self.scale, self.prob_name = float(scale), prob_name
+
+    def fwd(self, ctx):
+        P = ctx.ws.params
+        theta = ctx.rounded(self.theta)
+        assert theta.dim() == 3 and theta.shape[2] == 1, 'FBO fold needs one query per RoI'
+        R, d = int(theta.shape[0]), int(theta.shape[1])
+        bank = phys(ctx.get(self.bank))                         # [R, L, 1, 1, D] over the fed (R, L, D) blob
+        L_, D = int(bank.shape[1]), int(bank.shape[-1])
+        bank = bank.reshape(R, L_, D)
+        w1 = P.tf32(self.w1).view(1, -1, D)                     # [d1][D]
+        d1 = int(w1.shape[1])
+        wphi = P.tf32(self.wphi).view(1, d, d1)                 # [d][d1]
+        wg = P.tf32(self.wg).view(1, -1, d1)                    # [dg][d1]
+        dg = int(wg.shape[1])
+        u = empty((1, R, d1))
+        K.matmul(flat(theta).view(1, R, d), wphi, u, tf32_out=True)
+        q = empty((1, R, D))
+        K.matmul(u, w1, q)
+        s = empty((R, D))
+        prob = empty((R, L_)) if self.prob_name else None
+        K.fbo_bank_scan(bank, q.view(R, D), s, self.scale, prob=prob, tf32_out=True)
+        t = empty((1, R, d1))
+        K.matmul(s.view(1, R, D), w1.transpose(1, 2), t, bias=None if self.b1 is None else P.phys(self.b1),
+                 tf32_out=True)
+        y = empty((1, R, dg))
+        K.matmul(t, wg.transpose(1, 2), y, bias=None if self.bg is None else P.phys(self.bg), tf32_out=True)
+        if prob is not None:
+            ctx.put(self.prob_name, prob.view(R, 1, L_))
+        ctx.put(self.op.outputs[0], y.view(R, dg, 1), rounded=True)
+
+    def bwd(self, ctx):
+        raise NotImplementedError('FboFoldStep is an inference-mode lowering')
+
+
 class LayerNormStep(Step):
     def fwd(self, ctx):
         x = ctx.get(self.op.inputs[0])
@@ -880,11 +930,79 @@ class CompiledNet(object):
             return c[0]
         return None
 
+    def _producer_index(self, key, ops):
+        for i in range(len(ops)):
+            if key in self.out_keys[i]:
+                return i
+        return None
+
+    def _match_fbo_fold(self, ops, consumed, placed):
+        """Find Conv(1x1x1 'lfb_1x1') whose consumers are the phi / g projections of single-query NL layers and
+        replace each layer's bank-side operators by a FboFoldStep (test-mode graphs only: no Dropout in between)."""
+        def pointwise(op):
+            return op.type == 'Conv' and list(op.args.get('kernels', [])) == [1, 1, 1] and \
+                list(op.args.get('strides', [1, 1, 1])) == [1, 1, 1]
+
+        for i, c1 in enumerate(ops):
+            if i in consumed or not pointwise(c1) or c1.outputs[0] in self.losses:
+                continue
+            users = self.consumers.get(self.out_keys[i][0], [])
+            if len(users) < 2 or len(users) % 2 or not all(pointwise(ops[j]) and j not in consumed for j in users):
+                continue
+            layers = []
+            for j in users:                                     # phi: Conv -> Reshape -> BatchMatMul(theta, ., trans_a=1)
+                jr = self._sole_consumer(self.out_keys[j][0], ops, 'Reshape', consumed)
+                if jr is None:
+                    continue
+                jb = self._sole_consumer(self.out_keys[jr][0], ops, 'BatchMatMul', consumed)
+                if jb is None or not ops[jb].args.get('trans_a', 0) or ops[jb].args.get('trans_b', 0) or \
+                        self.in_keys[jb][1] != self.out_keys[jr][0]:
+                    continue
+                theta_key = self.in_keys[jb][0]
+                tp = self._producer_index(theta_key, ops)
+                if tp is None or ops[tp].type != 'Reshape' or list(ops[tp].args.get('shape', [0]))[-1] != 1:
+                    continue
+                key, chain, scale = self.out_keys[jb][0], [j, jr, jb], 1.0
+                js = self._sole_consumer(key, ops, 'Scale', consumed)
+                if js is not None:
+                    scale = float(ops[js].args['scale'])
+                    chain.append(js)
+                    key = self.out_keys[js][0]
+                jsm = self._sole_consumer(key, ops, 'Softmax', consumed)
+                if jsm is None or ops[jsm].args.get('axis', 1) != 2:
+                    continue
+                chain.append(jsm)
+                prob_key = self.out_keys[jsm][0]
+                jy = self._sole_consumer(prob_key, ops, 'BatchMatMul', consumed)
+                if jy is None or not ops[jy].args.get('trans_b', 0) or ops[jy].args.get('trans_a', 0) or \
+                        self.in_keys[jy][1] != prob_key:
+                    continue
+                gr = self._producer_index(self.in_keys[jy][0], ops)          # g: Conv -> Reshape -> BatchMatMul input 0
+                if gr is None or ops[gr].type != 'Reshape' or gr in consumed:
+                    continue
+                gc = self._producer_index(self.in_keys[gr][0], ops)
+                if gc not in users or gc == j or len(self.consumers.get(self.out_keys[gc][0], [])) != 1 or \
+                        len(self.consumers.get(self.out_keys[gr][0], [])) != 1:
+                    continue
+                layers.append((chain + [gc, gr, jy], theta_key, ops[j], ops[gc], scale, prob_key, jy))
+            if 2 * len(layers) != len(users):
+                continue
+            consumed.add(i)
+            for chain, theta_key, phi, g, scale, prob_key, jy in layers:
+                consumed.update(chain)
+                placed[jy] = FboFoldStep(
+                    ops[jy], [theta_key, self.in_keys[i][0]], self.out_keys[jy], theta=theta_key[0], bank=c1.inputs[0],
+                    w1=c1.inputs[1], b1=c1.inputs[2] if len(c1.inputs) > 2 else None, wphi=phi.inputs[1],
+                    wg=g.inputs[1], bg=g.inputs[2] if len(g.inputs) > 2 else None, scale=scale, prob_name=prob_key[0])
+
     def _lower(self, ops):
+        from core.config import config as cfg
         consumed = set()
         placed = {}                     # op index where a fused step is emitted -> step
+        if not self.train and not self.losses and cfg.B200.get('FBO_FOLD', True):
+            self._match_fbo_fold(ops, consumed, placed)
         for i, op in enumerate(ops):
-            if i in consumed:
+            if i in consumed or i in placed:
                 continue
             if op.type == 'Conv':
                 chain = [i]
@@ -988,6 +1106,7 @@ class CompiledNet(object):
 
     def _forward_backward(self, ctx):
         for st in self.steps:
+            K.LABEL = st.out_keys[0][0] if st.out_keys else ''
             st.fwd(ctx)
         if not self.train:
             return
@@ -996,6 +1115,7 @@ class CompiledNet(object):
         for n in self.losses:
             ctx.grads[(n, self.final_ver.get(n, 1))] = None
         for st in reversed(self.steps):
+            K.LABEL = st.out_keys[0][0] if st.out_keys else ''
             if isinstance(st, (SigmoidCELossStep, SoftmaxCELossStep)):
                 st.bwd(ctx)
             elif any(k in ctx.grads for k in st.out_keys):

@@ -14,7 +14,8 @@ NUM_SMS = 148
 
 
 LAUNCHES = 0            # kernels launched through this module (bench.py reports it as gpu_launches)
-_PROFILE = None         # when a list: (name, start_event, end_event, flops) per tensor-core GEMM launch
+_PROFILE = None         # when a list: (name, start_event, end_event, flops, bytes, label) per tensor-core GEMM launch
+LABEL = ''              # blob name of the graph step being executed (set by the executor; profile records carry it)
 
 
 def _check(rc, what):
@@ -29,11 +30,12 @@ def start_profile():
 
 
 def stop_profile():
-    """Returns [(kind, milliseconds, flops)] of the GEMM launches since start_profile()."""
+    """Returns [(kind, milliseconds, flops, algorithmic_bytes, label)] of the GEMM launches since start_profile().
+    algorithmic bytes = every operand / result tensor of the launch once (the im2col expansion is not counted)."""
     global _PROFILE
     recs, _PROFILE = _PROFILE, None
     torch.cuda.synchronize()
-    return [(k, s.elapsed_time(e), f) for k, s, e, f in (recs or [])]
+    return [(k, s.elapsed_time(e), f, b, lab) for k, s, e, f, b, lab in (recs or [])]
 
 
 def _stream():
@@ -95,7 +97,11 @@ def _operand(ptr_t, kind, ld=0, batch_stride=0):
     return o
 
 
-def _run_gemm(p, kind='gemm', flops=None):
+def _nbytes(*ts):
+    return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
+
+
+def _run_gemm(p, kind='gemm', flops=None, nbytes=0.0):
     if _PROFILE is not None:
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
@@ -103,7 +109,8 @@ def _run_gemm(p, kind='gemm', flops=None):
         e.record()
         if flops is None:
             flops = 2.0 * p.M * p.N * p.K * max(p.batch, 1) * max(p.taps, 1)
-        _PROFILE.append(('%s M=%d N=%d K=%d z=%d%s' % (kind, p.M, p.N, p.K, max(p.batch, p.taps), 'xauto' if p.split_k == 0 else ''), s, e, flops))
+        _PROFILE.append(('%s M=%d N=%d K=%d z=%d%s' % (kind, p.M, p.N, p.K, max(p.batch, p.taps), 'xauto' if p.split_k == 0 else ''), s, e, flops,
+                         nbytes, LABEL))
         return
     _check(L.load().vlfb_gemm(C.byref(p), _stream()), 'vlfb_gemm')
 
@@ -162,7 +169,8 @@ def conv_fwd(x, w, y, g, scale=None, bias=None, residual=None, relu=False, tf32_
     p.b = _operand(w, L.OP_DENSE_K, ld=K)
     p.g = g
     _set_epilogue(p, scale, bias, None, residual, relu, tf32_out)
-    _run_gemm(p, 'conv_fwd', 2.0 * M * g.Co * g.kT * g.kH * g.kW * (3 if g.C == 4 else g.C))
+    _run_gemm(p, 'conv_fwd', 2.0 * M * g.Co * g.kT * g.kH * g.kW * (3 if g.C == 4 else g.C),
+              _nbytes(x, w, y, residual))
 
 
 def conv_dgrad(dy, wt, dx, g, accumulate=False, residual=None, relu_mask=None, tf32_out=False):
@@ -194,7 +202,8 @@ def conv_dgrad(dy, wt, dx, g, accumulate=False, residual=None, relu_mask=None, t
     if tf32_out:
         p.flags |= L.EPI_TF32
     # algorithmic dgrad work = forward MACs of the same layer
-    _run_gemm(p, 'conv_dgrad', 2.0 * g.N * g.To * g.Ho * g.Wo * g.Co * g.kT * g.kH * g.kW * g.C)
+    _run_gemm(p, 'conv_dgrad', 2.0 * g.N * g.To * g.Ho * g.Wo * g.Co * g.kT * g.kH * g.kW * g.C,
+              _nbytes(dy, wt, dx, residual, relu_mask) + (_nbytes(dx) if accumulate else 0.0))
 
 
 def conv_wgrad(dy, x, dw, g, row_scale=None, col_mask=None):
@@ -223,7 +232,8 @@ def conv_wgrad(dy, x, dw, g, row_scale=None, col_mask=None):
     p.split_k = 0            # split-K and the tile width are chosen together by the library (gemm_tc.cu launch())
     p.flags |= L.EPI_ATOMIC
     _set_epilogue(p, col_mask, None, row_scale, None, False)
-    _run_gemm(p, 'conv_wgrad', 2.0 * Kpos * g.Co * g.kT * g.kH * g.kW * (3 if g.C == 4 else g.C))
+    _run_gemm(p, 'conv_wgrad', 2.0 * Kpos * g.Co * g.kT * g.kH * g.kW * (3 if g.C == 4 else g.C),
+              _nbytes(dy, x, dw))
 
 
 def weight_transpose(w, wt, scale=None):
@@ -288,7 +298,7 @@ def matmul(a, b, d, alpha=1.0, accumulate=False, bias=None, tf32_out=False):
     elif accumulate:
         p.flags |= L.EPI_ACCUM
     _set_epilogue(p, None, bias, None, None, False, tf32_out)
-    _run_gemm(p, 'matmul', 2.0 * Bt * M * N * K)
+    _run_gemm(p, 'matmul', 2.0 * Bt * M * N * K, 4.0 * Bt * (M * K + K * N + M * N * (2 if accumulate else 1)))
 
 
 def weight_transpose_multi(jobs, cache):
@@ -505,3 +515,37 @@ def fbo_attend_bwd(theta, phi, g, prob, dy, dtheta, dphi, dg, scale):
     _check(L.load().vlfb_fbo_attend_bwd(_ptr(_f32c(theta)), _ptr(_f32c(phi)), _ptr(_f32c(g)), _ptr(_f32c(prob)),
                                          _ptr(_f32c(dy)), _ptr(_f32c(dtheta)), _ptr(_f32c(dphi)), _ptr(_f32c(dg)),
                                          r, l, d, float(scale), _stream()), 'fbo_attend_bwd')
+
+
+# --------------------------------------------------------------------------- raw feature-bank kernels (csrc/fbo.cu)
+def fbo_bank_scan(bank, q, out, scale, prob=None, tf32_out=False):
+    """out[r] = sum_j softmax_j(scale * q[r].bank[r,j]) * bank[r,j]: the folded inference-mode FBO-NL layer, one pass
+    over the raw bank.  bank [R,L,D], q [R,D], out [R,D], prob [R,L] or None."""
+    _f32c(bank, 'bank'), _f32c(q, 'q'), _f32c(out, 'out')
+    r, l, d = bank.shape
+    assert tuple(q.shape) == (r, d) and tuple(out.shape) == (r, d)
+    if prob is not None:
+        assert tuple(_f32c(prob, 'prob').shape) == (r, l)
+    lib = L.load()
+    nbytes = int(lib.vlfb_fbo_bank_scan_workspace(r, l, d))
+    if nbytes == 0 and r > 0:
+        raise L.VlfbError('fbo_bank_scan: unsupported bank row width %d (1024, 2048 or 4096)' % d)
+    wsp = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=bank.device)
+    if _PROFILE is not None:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+    _check(lib.vlfb_fbo_bank_scan(_ptr(bank), _ptr(q), float(scale), _ptr(out), _ptr(prob), r, l, d, int(tf32_out),
+                                  _ptr(wsp), C.c_size_t(nbytes), _stream()), 'fbo_bank_scan')
+    if _PROFILE is not None:
+        e.record()
+        _PROFILE.append(('fbo_bank_scan R=%d L=%d D=%d' % (r, l, d), s, e, 4.0 * r * l * d, _nbytes(bank, q, out), LABEL))
+
+
+def lfb_gather(bank, idx, out, tf32_out=False):
+    """out[i] = bank[idx[i]] (zeros where idx[i] < 0).  bank [rows, D] fp32, idx int32 [n], out [n, D]."""
+    _f32c(bank, 'bank'), _f32c(out, 'out')
+    assert idx.dtype == torch.int32 and idx.is_contiguous() and idx.is_cuda
+    n, d = out.shape[0], out.shape[-1]
+    assert idx.numel() == out.numel() // d and bank.shape[-1] == d
+    _check(L.load().vlfb_lfb_gather(_ptr(bank), bank.numel() // d, _ptr(idx), _ptr(out), idx.numel(), d, int(tf32_out),
+                                    _stream()), 'lfb_gather')

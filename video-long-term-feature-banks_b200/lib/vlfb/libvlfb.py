@@ -81,7 +81,12 @@ SIGNATURES = {
     'vlfb_sgd_nesterov': [_P, _P, _P, _P, _L, _P, _F, _F, _I, _P],
     'vlfb_fbo_attend_fwd': [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     'vlfb_fbo_attend_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
+    'vlfb_fbo_bank_scan_splits': [_I, _I, _I],
+    'vlfb_fbo_bank_scan_workspace': [_I, _I, _I],
+    'vlfb_fbo_bank_scan': [_P, _P, _F, _P, _P, _I, _I, _I, _I, _P, C.c_size_t, _P],
+    'vlfb_lfb_gather': [_P, _L, _P, _P, _L, _I, _I, _P],
 }
+RESTYPES = {'vlfb_last_error': C.c_char_p, 'vlfb_fbo_bank_scan_workspace': C.c_size_t}
 
 _lib = None
 
@@ -99,7 +104,7 @@ def load():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)        # AttributeError if the symbol is missing
         fn.argtypes = argtypes
-        fn.restype = C.c_char_p if name == 'vlfb_last_error' else C.c_int
+        fn.restype = RESTYPES.get(name, C.c_int)
     _lib = lib
     return lib
 
