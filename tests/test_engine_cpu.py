@@ -88,7 +88,8 @@ def test_charades_post_act_variant(fake):
     _run('charades_r50_lfb_nl.yaml', TINY + ['MODEL.NUM_CLASSES', 157], fake, ['pool5', 'pred'])
 
 
-@pytest.mark.parametrize('yaml_name', ['ava_r50_lfb_avg.yaml', 'ava_r50_lfb_max.yaml', 'ava_r50_baseline.yaml'])
+@pytest.mark.parametrize('yaml_name', ['ava_r50_lfb_avg.yaml', 'ava_r50_lfb_max.yaml', 'ava_r50_baseline.yaml',
+                                       'ava_r101_lfb_nl_3l.yaml'])
 def test_other_heads(fake, yaml_name):
     _run(yaml_name, TINY, fake, ['pool5', 'pred'])
 

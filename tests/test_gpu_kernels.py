@@ -468,3 +468,78 @@ def test_weight_transpose_multi_matches_single(K):
     torch.cuda.synchronize()
     for (w, wt, sc), ref in zip(jobs, refs):
         assert torch.equal(wt, ref)
+
+
+# -------------------------------------------------------------------------- raw-bank kernels (csrc/fbo.cu)
+@pytest.mark.parametrize('R,Lb,D', [(1, 1, 2048), (3, 7, 2048), (4, 300, 2048), (2, 301, 1024), (5, 60, 4096),
+                                     (37, 120, 2048), (3, 3600, 2048)])
+def test_fbo_bank_scan(K, R, Lb, D):
+    """One pass over the raw bank: scores q.b_j, softmax over the L rows, weighted row sum -- against fp64; ragged
+    tails (L not a multiple of the 8-row tile or of the split), one-row banks, zero-padded rows, every supported D."""
+    g = torch.Generator().manual_seed(R * 1000 + Lb)
+    bank = torch.randn((R, Lb, D), generator=g) * 0.5
+    bank[:, Lb - Lb // 4:] = 0.0                        # the reference zero-pads short windows (ava.py:310-321)
+    q = torch.randn((R, D), generator=g) * 0.2
+    sc = 512 ** -0.5
+    p = torch.softmax(torch.einsum('rld,rd->rl', bank.double(), q.double()) * sc, dim=1)
+    ref = torch.einsum('rl,rld->rd', p, bank.double())
+    out = torch.full((R, D), float('nan'), device='cuda')
+    prob = torch.full((R, Lb), float('nan'), device='cuda')
+    K.fbo_bank_scan(bank.cuda(), q.cuda(), out, sc, prob=prob)
+    torch.cuda.synchronize()
+    assert rel_err(prob, p) < 1e-5 and rel_err(out, ref) < 1e-5
+    out2 = torch.empty_like(out)
+    K.fbo_bank_scan(bank.cuda(), q.cuda(), out2, sc, prob=None, tf32_out=True)
+    assert torch.equal(out2.cpu(), tf32_round(out.cpu()))
+
+
+def test_fbo_bank_scan_peaked_softmax_and_split_table(K):
+    """Scores far apart (one row dominates): the online softmax must not overflow / lose the winner across CTA splits;
+    and the split chooser keeps every CTA non-empty."""
+    from vlfb import libvlfb as L
+    lib = L.load()
+    for R, Lb in [(1, 1), (4, 300), (256, 3600), (64, 60), (3, 9), (1000, 17)]:
+        s = lib.vlfb_fbo_bank_scan_splits(R, Lb, 2048)
+        per = (Lb + s - 1) // s
+        assert s >= 1 and (s - 1) * per < Lb
+    assert lib.vlfb_fbo_bank_scan_splits(4, 300, 1000) == 0
+    R, Lb, D = 2, 300, 2048
+    bank = torch.randn(R, Lb, D)
+    q = torch.zeros(R, D)
+    q[0] = bank[0, 123] * 5.0          # score(123) ~ 5 * 2048: every other row underflows to exactly 0
+    q[1] = -bank[1, 299] * 5.0         # the last row gets the most NEGATIVE score
+    out = torch.empty((R, D), device='cuda')
+    prob = torch.empty((R, Lb), device='cuda')
+    K.fbo_bank_scan(bank.cuda(), q.cuda(), out, 1.0, prob=prob)
+    p = torch.softmax(torch.einsum('rld,rd->rl', bank.double(), q.double()), dim=1)
+    assert torch.isfinite(out).all() and rel_err(prob, p) < 1e-5
+    assert rel_err(out, torch.einsum('rl,rld->rd', p, bank.double())) < 1e-5
+    assert abs(float(prob[0, 123]) - 1.0) < 1e-6
+
+
+def test_fbo_bank_scan_rejects_bad_arguments(K):
+    from vlfb import libvlfb as L
+    bank, q, out = torch.zeros((2, 8, 512), device='cuda'), torch.zeros((2, 512), device='cuda'), torch.zeros((2, 512), device='cuda')
+    with pytest.raises(L.VlfbError):
+        K.fbo_bank_scan(bank, q, out, 1.0)
+    lib = L.load()
+    b2 = torch.zeros((2, 8, 2048), device='cuda')
+    rc = lib.vlfb_fbo_bank_scan(b2.data_ptr(), b2.data_ptr(), 1.0, b2.data_ptr(), None, 2, 8, 2048, 0, None, 0, None)
+    assert rc == -4 and b'workspace' in lib.vlfb_last_error()
+
+
+@pytest.mark.parametrize('rows,n,D', [(1000, 600, 2048), (17, 5, 64), (3, 0, 2048), (50000, 4800, 2048)])
+def test_lfb_gather_is_bit_exact(K, rows, n, D):
+    g = torch.Generator().manual_seed(rows + n)
+    bank = torch.randn((rows, D), generator=g)
+    idx = torch.randint(-1, rows, (n,), generator=g, dtype=torch.int32)
+    if n > 2:
+        idx[0], idx[-1] = -1, rows - 1
+    ref = torch.zeros((n, D))
+    ok = idx >= 0
+    ref[ok] = bank[idx[ok].long()]
+    out = torch.full((n, D), float('nan'), device='cuda')
+    K.lfb_gather(bank.cuda(), idx.cuda(), out)
+    assert torch.equal(out.cpu(), ref)
+    K.lfb_gather(bank.cuda(), idx.cuda(), out, tf32_out=True)
+    assert torch.equal(out.cpu(), tf32_round(ref))

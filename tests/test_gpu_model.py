@@ -243,6 +243,49 @@ def test_full_size_config1_baseline_forward_test_crop(ws):
         assert e < FWD_TOL, (b, e)
 
 
+def _val_lfb_case(ws, yaml_name, overrides, crop, frames, rois_per_clip, fold, runs=1):
+    from oracle import model as OM
+    from core.config import config as cfg
+    from vlfb import executor as X
+    H.setup_cfg(yaml_name, overrides)
+    cfg.B200.FBO_FOLD = fold
+    ocfg = H.oracle_cfg(yaml_name, overrides)
+    params = OM.make_params(ocfg, seed=2, split='val')
+    inputs = OM.make_inputs(ocfg, n_clips=2, rois_per_clip=rois_per_clip, crop=crop, frames=frames)
+    model, sfx = H.build('val', False)
+    H.feed_params(params)
+    H.feed_inputs(inputs, sfx)
+    net = ws.current().nets[model.net.Proto().name]
+    assert sum(isinstance(s, X.FboFoldStep) for s in net.steps) == (cfg.FBO_NL.NUM_LAYERS if fold else 0)
+    _, blobs, _ = _oracle(ocfg, params, inputs, 'val', False)
+    out = {}
+    for run in range(runs):                      # runs >= 4: the last ones are CUDA-graph replays
+        ws.RunNet(model.net.Proto().name)
+        for b in ['lfb_nl0_affinity_prob', 'lfb_nl%d_sum' % (cfg.FBO_NL.NUM_LAYERS - 1), 'pool5', 'pred', 'prob']:
+            e = H.rel(ws.FetchBlob('gpu_0/' + b).reshape(-1), blobs[b].detach().numpy().reshape(-1))
+            out[b] = e
+            assert e < FWD_TOL, (b, e, fold, run)
+    print('[%s val fold=%s] %s' % (yaml_name, fold, ' '.join('%s=%.2e' % kv for kv in out.items())))
+
+
+@pytest.mark.parametrize('fold', [True, False])
+def test_tiny_inference_fbo_fold(ws, fold):
+    """Test-mode LFB net: every FBO-NL layer is one pass over the raw bank (FboFoldStep) -- and the as-written
+    lowering of the same graph -- against the oracle; eager runs and graph replays."""
+    _val_lfb_case(ws, 'ava_r50_lfb_nl_3l.yaml', TINY, 64, 8, 3, fold, runs=5)
+
+
+def test_full_size_inference_with_bank_fold(ws):
+    """ava_r50_lfb_nl shapes at inference: 2 clips of 32x224x224, R=4, L=300 bank rows x 2048."""
+    _val_lfb_case(ws, 'ava_r50_lfb_nl.yaml', FULL + ['TEST.CROP_SIZE', 224], 224, 32, 2, True)
+
+
+def test_tiny_r101_3l_train_step(ws):
+    """BASELINE.json config 4 architecture (R101-I3D-NL + FBO-NL-3L: 23 res4 blocks, NL at conv4_{6,13,20}), tiny
+    clips, tf32 parity mode."""
+    _train_case(ws, 'ava_r101_lfb_nl_3l.yaml', TINY, 64, 8, 2)
+
+
 def test_sgd_step_and_determinism_of_forward(ws):
     from oracle import ops as O
     from core.config import config as cfg
