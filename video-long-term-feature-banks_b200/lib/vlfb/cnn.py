@@ -34,6 +34,12 @@ class CNNModelHelper(object):
     def GetParams(self, namescope=None):
         return list(self.params)
 
+    def GetComputedParams(self, namescope=None):
+        return []                       # SpatialBN running statistics: the Affine variant has none
+
+    def GetAllParams(self, namescope=None):
+        return self.GetParams(namescope) + self.GetComputedParams(namescope)
+
     def _make_param(self, name, shape, init, is_weight):
         init_type, init_args = init
         getattr(self.param_init_net, init_type)([], name, shape=list(shape), **init_args)

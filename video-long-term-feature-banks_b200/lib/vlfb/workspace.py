@@ -427,6 +427,7 @@ def FeedBlob(name, arr, device_option=None):
         return True
     if name.endswith('_momentum') and _ws.params.has(name[:-len('_momentum')]):
         base = name[:-len('_momentum')]
+        _ws.params._ensure_state()
         _ws.params.logical(base, 'Mo').copy_(torch.as_tensor(np.asarray(arr)).to(X.DTYPE).to(X.DEVICE))
         return True
     if np.ndim(arr) == 0 or name in ('lr', 'weight_decay', 'weight_decay_bn', 'ONE'):
