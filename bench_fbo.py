@@ -10,7 +10,8 @@ builder API / workspace / C ABI as the full model, in three modes:
   train        train-mode graph (dropout on) forward + backward + SGD, as written
 
 One JSON line per (mode, R, L, layers) on stdout:
-  ms, GB/s = SURVEY 8(d) compulsory bytes / time, against MEASURED_PEAKS.json hbm_gbs; TFLOP/s = as-written FLOPs / time
+  ms = device time of the captured step (CUDA-graph replay bracketed by events; runnet_ms = the same through
+  workspace.RunNet, which adds ~0.2 ms of python per call and is what bounds tiny cases), GB/s = SURVEY 8(d) compulsory bytes / time, against MEASURED_PEAKS.json hbm_gbs; TFLOP/s = as-written FLOPs / time
   (for infer_fold this is "effective" throughput: the folded path does not execute those FLOPs);
   scan = the fbo_bank_scan launches alone (CUDA events around each, eager pass): achieved GB/s of the dominant kernel.
 Inputs are resident in HBM; L2 is flushed (256 MB write) before every timed iteration, so a bank that would fit the
@@ -85,8 +86,10 @@ def build_case(mode, R, L, layers):
     for l in range(layers):
         shape = workspace.current().params.logical_shape('lfb_nl%d_out_w' % l)
         workspace.FeedBlob('gpu_0/lfb_nl%d_out_w' % l, (torch.randn(shape, generator=g) * 0.02).numpy())
-    bank = torch.randn((R, L, 2048), generator=g) * 0.5
+    uniq = min(R, 16)                       # distinct RoI banks; repeated along R (timing does not depend on values)
+    bank = torch.randn((uniq, L, 2048), generator=g) * 0.5
     bank[:, L - (L + 3) // 4:] = 0.0
+    bank = bank.repeat((R + uniq - 1) // uniq, 1, 1)[:R].contiguous()
     workspace.FeedBlob('gpu_0/data' + sfx, torch.relu(torch.randn((R, 2048, 1, 1, 1), generator=g)).numpy())
     workspace.FeedBlob('gpu_0/lfb' + sfx, bank.numpy())
     workspace.FeedBlob('gpu_0/labels' + sfx, (torch.rand((R, cfg.MODEL.NUM_CLASSES), generator=g) < 0.05).to(torch.int32).numpy())
@@ -108,20 +111,33 @@ def run_case(mode, R, L, layers, steps, warmup, peaks):
     for _ in range(max(warmup, 3)):
         workspace.RunNet(name)
     torch.cuda.synchronize()
+    net = workspace.current().nets[name]
+    assert net._graphs is not None, 'the step should have been captured after the warm-up runs'
+    g1, g2, n1, n2 = net._graphs
+
+    def timed(fn):
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sorted(a.elapsed_time(b) for a, b in evs)
+
+    def replay():                 # the captured step itself: what the device executes, without RunNet's host work
+        g1.replay()
+        if g2 is not None:
+            g2.replay()
+
     K.LAUNCHES = 0
-    tot = 0.0
-    evs = []
-    for _ in range(steps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        workspace.RunNet(name)
-        e1.record()
-        evs.append((e0, e1))
-    torch.cuda.synchronize()
-    times = sorted(a.elapsed_time(b) for a, b in evs)
-    ms = times[len(times) // 2]
+    api_times = timed(lambda: workspace.RunNet(name))
     launches = K.LAUNCHES // max(steps, 1)
+    times = timed(replay)
+    ms = times[len(times) // 2]
+    api_ms = api_times[len(api_times) // 2]
     out = float(np.abs(workspace.FetchBlob('gpu_0/prob')).sum())
     assert np.isfinite(out)
     # the dominant kernel alone (eager pass with per-launch events)
@@ -143,6 +159,7 @@ def run_case(mode, R, L, layers, steps, warmup, peaks):
     workspace.ResetWorkspace()
     torch.cuda.empty_cache()
     return {'bench': 'fbo_nl', 'mode': mode, 'R': R, 'L': L, 'layers': layers, 'ms': round(ms, 4), 'ms_min': round(times[0], 4),
+            'runnet_ms': round(api_ms, 4),
             'launches': launches, 'alg_bytes': nbytes, 'gbs': round(nbytes / 1e6 / ms, 1),
             'hbm_frac': round(nbytes / 1e6 / ms / peaks['hbm_gbs'], 4), 'as_written_gflop': round(flops / 1e9, 2),
             'tflops_as_written': round(flops / 1e9 / ms, 1), 'scan': scan, 'gemm_ms_eager': round(gemm_ms, 4),
@@ -181,13 +198,13 @@ def main():
     if args.out:
         with open(args.out, 'w') as f:
             f.write('# FBO-NL microbench (bench_fbo.py), HBM peak %.0f GB/s (MEASURED_PEAKS.json)\n' % peaks['hbm_gbs'])
-            f.write('%-11s %4s %5s %2s %9s %8s %8s %9s %7s  %s\n' % ('mode', 'R', 'L', 'l', 'ms', 'GB/s', 'hbm_frac', 'TF/s(aw)',
-                                                                  'launch', 'scan kernel GB/s (frac)'))
+            f.write('%-11s %4s %5s %2s %9s %9s %8s %8s %9s %7s  %s\n' % ('mode', 'R', 'L', 'l', 'ms', 'runnet_ms', 'GB/s', 'hbm_frac',
+                                                                      'TF/s(aw)', 'launch', 'scan kernel GB/s (frac)'))
             for r in rows:
                 sc = '%.0f (%.2f)' % (r['scan']['gbs'], r['scan']['frac']) if r['scan'] else '-'
-                f.write('%-11s %4d %5d %2d %9.4f %8.0f %8.3f %9.1f %7d  %s\n' % (
-                    r['mode'], r['R'], r['L'], r['layers'], r['ms'], r['gbs'], r['hbm_frac'], r['tflops_as_written'],
-                    r['launches'], sc))
+                f.write('%-11s %4d %5d %2d %9.4f %9.4f %8.0f %8.3f %9.1f %7d  %s\n' % (
+                    r['mode'], r['R'], r['L'], r['layers'], r['ms'], r['runnet_ms'], r['gbs'], r['hbm_frac'],
+                    r['tflops_as_written'], r['launches'], sc))
 
 
 if __name__ == '__main__':

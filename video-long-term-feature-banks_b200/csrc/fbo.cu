@@ -240,8 +240,9 @@ int vlfb_fbo_bank_scan(const float* bank, const float* q, float scale, float* ou
 
 int vlfb_lfb_gather(const float* bank, int64_t bank_rows, const int32_t* idx, float* out, int64_t rows, int D,
                     int tf32_out, void* stream) {
-  VLFB_CHECK_ARG(bank && idx && out && rows >= 0 && bank_rows >= 0 && D > 0 && (D & 3) == 0);
-  if (rows == 0) return VLFB_OK;
+  VLFB_CHECK_ARG(rows >= 0 && bank_rows >= 0 && D > 0 && (D & 3) == 0);
+  if (rows == 0) return VLFB_OK;            /* an empty table: nothing to write (pointers may be NULL) */
+  VLFB_CHECK_ARG(idx && out && (bank || bank_rows == 0));
   launch_k(lfb_gather_k, stream_grid(rows * (D >> 2), 256, 4), 256, 0, ST(stream), (const float4*)bank, idx, (float4*)out,
            rows, D >> 2, bank_rows, tf32_out);
   VLFB_CHECK_LAUNCH();

@@ -547,5 +547,7 @@ def lfb_gather(bank, idx, out, tf32_out=False):
     assert idx.dtype == torch.int32 and idx.is_contiguous() and idx.is_cuda
     n, d = out.shape[0], out.shape[-1]
     assert idx.numel() == out.numel() // d and bank.shape[-1] == d
+    if idx.numel() == 0:
+        return
     _check(L.load().vlfb_lfb_gather(_ptr(bank), bank.numel() // d, _ptr(idx), _ptr(out), idx.numel(), d, int(tf32_out),
                                     _stream()), 'lfb_gather')
