@@ -209,6 +209,22 @@ def test_enqueue_blobs_matches_feed_blob(ws):
             ws.EnqueueBlobs(host[i + 1])             # overlaps the step that is running
         assert abs(float(ws.FetchBlob('gpu_0/loss')) - want[i][0]) <= 1e-6 * abs(want[i][0])
         assert H.rel(ws.FetchBlob('gpu_0/pred'), want[i][1]) < 1e-6
+    # pipelined read-back: step i's loss / pred are collected after step i+1 has been launched
+    ws.EnqueueBlobs(host[0])
+    pending = None
+    got = []
+    for i in range(4):
+        ws.RunNet(model.net.Proto().name)
+        if i + 1 < 4:
+            ws.EnqueueBlobs(host[i + 1])
+        nxt = (ws.FetchBlobAsync('gpu_0/loss'), ws.FetchBlobAsync('gpu_0/pred'))
+        if pending is not None:
+            got.append((float(pending[0].get()), pending[1].get()))
+        pending = nxt
+    got.append((float(pending[0].get()), pending[1].get()))
+    for i in range(4):
+        assert abs(got[i][0] - want[i][0]) <= 1e-6 * abs(want[i][0])
+        assert got[i][1].shape == want[i][1].shape and H.rel(got[i][1], want[i][1]) < 1e-6
 
 
 def test_tiny_simt_engine_agrees(ws):

@@ -442,6 +442,49 @@ def FeedBlob(name, arr, device_option=None):
     return True
 
 
+class _PendingFetch(object):
+    """Handle returned by FetchBlobAsync: .get() waits for the device->host copy and returns the numpy value."""
+
+    def __init__(self, host, event, scalar):
+        self._host, self._event, self._scalar = host, event, scalar
+
+    def ready(self):
+        return self._event is None or self._event.query()
+
+    def get(self):
+        if self._event is not None:
+            self._event.synchronize()
+        a = self._host if isinstance(self._host, np.ndarray) else self._host.numpy().copy()
+        return a.reshape(()) if (self._scalar and a.size == 1) else a
+
+
+def FetchBlobAsync(name):
+    """Non-blocking FetchBlob for small activation blobs (loss, pred, metrics): the device->host copy is enqueued on
+    the current stream behind the work already submitted, into one of four pinned staging buffers per blob; the
+    returned handle's .get() waits for that copy only.  A training loop reads step i's loss after it has launched
+    step i+1, so the device never idles behind the host (the reference's FetchBlob after every RunNet,
+    tools/train_net.py:152-160, serialises the two)."""
+    name = _unscoped(name)
+    scalar = name in ('loss', 'lr') or name.startswith('loss')
+    if X.DEVICE == 'cpu' or _ws.params.has(name):
+        return _PendingFetch(np.asarray(FetchBlob(name)), None, scalar)
+    t = _ws.blobs[name]
+    assert isinstance(t, torch.Tensor), 'FetchBlobAsync: %s is not a tensor blob' % name
+    ring = _ws.input_cache.setdefault('fetch_ring/' + name, [[], 0])
+    if len(ring[0]) < 4 or tuple(ring[0][0].shape) != tuple(t.shape):
+        if ring[0] and tuple(ring[0][0].shape) != tuple(t.shape):
+            ring[0], ring[1] = [], 0
+        ring[0].append(torch.empty(tuple(t.shape), dtype=t.dtype).pin_memory())
+        host = ring[0][-1]
+    else:
+        host = ring[0][ring[1] % 4]
+    ring[1] += 1
+    host.copy_(t, non_blocking=True)         # strided logical views are copied element-wise: logical layout on the host
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    return _PendingFetch(host, ev, scalar)
+
+
 def FetchBlob(name):
     name = _unscoped(name)
     if _ws.params.has(name):
