@@ -86,3 +86,30 @@ def sample_verb_lfb_epic(center_idx, video_lfb, window_size, lfb_dim):
             new[:out_lfb.shape[0]] = out_lfb
         out_lfb = new
     return out_lfb.astype(np.float32)
+
+
+def sample_noun_lfb_epic(center_idx, video_lfb, window_size, max_num_feat_per_frame, frames_per_second, lfb_dim):
+    """lib/datasets/epic.py:338-374 (several detections per frame; the first `max_num_feat_per_frame` of each frame
+    are taken in frame order until `window_size` rows are collected)."""
+    secs = float(window_size) / (max_num_feat_per_frame * frames_per_second)
+    lower = int(center_idx - (secs / 2) * FPS)
+    upper = int(lower + secs * FPS)
+    out_lfb = []
+    num_feat = 0
+    for frame_idx in range(lower, upper + 1):
+        if frame_idx in video_lfb:
+            frame_lfb = video_lfb[frame_idx]
+            if not (isinstance(frame_lfb, list) and len(frame_lfb) == 0):
+                curr_num = min(max_num_feat_per_frame, frame_lfb.shape[0])
+                num_feat += curr_num
+                out_lfb.append(frame_lfb[:curr_num])
+                if num_feat >= window_size:
+                    break
+    if len(out_lfb) == 0:
+        return np.zeros((window_size, lfb_dim))
+    out_lfb = np.vstack(out_lfb)[:window_size].astype(np.float32)
+    if out_lfb.shape[0] < window_size:
+        new = np.zeros((window_size, lfb_dim))
+        new[:out_lfb.shape[0]] = out_lfb
+        out_lfb = new
+    return out_lfb

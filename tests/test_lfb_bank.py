@@ -89,6 +89,23 @@ def test_index_tables_reproduce_reference_sampling_cpu(fake):
         assert np.array_equal(got, ref)
 
 
+def test_epic_noun_bank_with_several_detections_per_frame(fake):
+    from datasets import lfb_bank as LB
+    rng = np.random.RandomState(4)
+    video = {}
+    for f in range(0, 900, 24):                          # NOUN_LFB_FRAMES_PER_SECOND = 1 at 24 fps
+        n = int(rng.randint(0, 14))
+        video[f] = rng.randn(n, DIM).astype(np.float32) if n else []
+    bank = LB.DeviceLfb({'P01_01': video}, DIM)
+    assert bank.rows == sum(v.shape[0] for v in video.values() if not isinstance(v, list))
+    for center in (0, 100, 433, 880, 2000):
+        for W, per_frame, fps in [(60, 10, 1), (40, 10, 1), (30, 3, 1), (7, 10, 1)]:
+            ref = OS.sample_noun_lfb_epic(center, video, W, per_frame, fps, DIM)
+            idx = bank.sample_indices_epic_noun('P01_01', center, W, per_frame, fps)
+            got = bank.gather(idx[None])[0].float().numpy()
+            assert got.shape == ref.shape and np.array_equal(got, ref.astype(np.float32)), (center, W, per_frame)
+
+
 def test_feed_matches_feedblob_of_host_windows(fake):
     """DeviceLfb.feed(blob, indices) leaves the workspace exactly as FeedBlob(blob, host-assembled windows) does."""
     from datasets import lfb_bank as LB

@@ -128,6 +128,26 @@ class DeviceLfb(object):
                 k += 1
         return out
 
+    def sample_indices_epic_noun(self, video_key, center_idx, window_size, max_num_feat_per_frame, frames_per_second):
+        """lib/datasets/epic.py:338-374: up to `max_num_feat_per_frame` detections of every stored frame inside the
+        window, in frame order, until `window_size` rows are collected."""
+        video = self.start[video_key]
+        secs = float(window_size) / (max_num_feat_per_frame * frames_per_second)
+        lower = int(center_idx - (secs / 2) * FPS)
+        upper = int(lower + secs * FPS)
+        out = np.full((window_size,), -1, dtype=np.int32)
+        k = 0
+        for frame_idx in range(lower, upper + 1):
+            if frame_idx in video and video[frame_idx][1] > 0:
+                first, count = video[frame_idx]
+                take = min(max_num_feat_per_frame, count)
+                fit = min(take, window_size - k)
+                out[k:k + fit] = first + np.arange(fit, dtype=np.int32)
+                k += take
+                if k >= window_size:
+                    break
+        return out
+
     # -- device side
     def gather(self, index_table, out=None, tf32_out=False):
         """index_table int32 [R, L] (host numpy / tensor) -> device tensor [R, L, dim]."""
