@@ -176,6 +176,9 @@ int vlfb_copy2d(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t 
                 int accumulate, void* stream);
 /* layout: NCTHW (reference blob layout) <-> NDHWC; inner = T*H*W */
 int vlfb_nc_to_cl(const float* src, float* dst, int N, int C, int64_t inner, int Cpad, void* stream);
+/* the same with the TF32 rounding of the result fused (tf32_out != 0): the dequeue of a fed clip (`data` blob,
+ * model_builder_video.py:335-345) is ONE pass: NCTHW fp32 -> NDHWC, C 3 -> 4, rounded conv1 operand */
+int vlfb_nc_to_cl_round(const float* src, float* dst, int N, int C, int64_t inner, int Cpad, int tf32_out, void* stream);
 int vlfb_cl_to_nc(const float* src, float* dst, int N, int C, int64_t inner, int Cpad, void* stream);
 /* weights: wt[ci][tap][co] = round_tf32( w[co][tap][ci] * (scale ? scale[co] : 1) )  (dgrad B operand) */
 int vlfb_weight_transpose(const float* w, float* wt, const float* scale, int Co, int taps, int Ci,

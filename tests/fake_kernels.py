@@ -288,11 +288,11 @@ def copy2d(src, lds, dst, ldd, rows, cols, accumulate=False, src_off=0, dst_off=
         d.copy_(s)
 
 
-def nc_to_cl(src, dst, n, c, inner, cpad=None):
+def nc_to_cl(src, dst, n, c, inner, cpad=None, tf32_out=False):
     cpad = cpad or c
     d = dst.view(n, inner, cpad)
     d.zero_()
-    d[:, :, :c] = src.reshape(n, c, inner).permute(0, 2, 1)
+    d[:, :, :c] = _q(src.reshape(n, c, inner).permute(0, 2, 1), tf32_out)
 
 
 def cl_to_nc(src, dst, n, c, inner, cpad=None):

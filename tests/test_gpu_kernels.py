@@ -360,6 +360,17 @@ def test_elementwise_and_layout(K):
     cl = torch.empty((2, 4, 5, 6, 4), device='cuda')
     K.nc_to_cl(t.cuda(), cl, 2, 3, 4 * 5 * 6, 4)
     assert torch.equal(cl[..., :3].cpu(), to_cl(t)) and float(cl[..., 3].abs().max()) == 0
+    # clip feeding: the vectorised C<=4 path (inner % 4 == 0), with and without the fused TF32 rounding, the generic
+    # path for a ragged inner extent (7*5*3 = 105), and a 1-plane / 4-plane input
+    for shape in [(2, 3, 8, 16, 16), (1, 3, 7, 5, 3), (2, 1, 4, 4, 4), (3, 4, 2, 6, 6)]:
+        tc_ = torch.randn(shape)
+        n_, c_, inner_ = shape[0], shape[1], shape[2] * shape[3] * shape[4]
+        for rnd_ in (False, True):
+            o = torch.full((n_,) + shape[2:] + (4,), float('nan'), device='cuda')
+            K.nc_to_cl(tc_.cuda(), o, n_, c_, inner_, 4, tf32_out=rnd_)
+            want = to_cl(tc_)
+            assert torch.equal(o[..., :c_].cpu(), tf32_round(want) if rnd_ else want), (shape, rnd_)
+            assert c_ == 4 or float(o[..., c_:].abs().max()) == 0
     t2 = torch.randn(3, 70, 2, 3, 3)
     cl2 = torch.empty((3, 2, 3, 3, 70), device='cuda')
     K.nc_to_cl(t2.cuda(), cl2, 3, 70, 18)

@@ -488,7 +488,34 @@ __global__ void colsum_k(const float* __restrict__ x, int64_t ld, float* __restr
 
 // ------------------------------------------------------------------ layouts
 // src [N][C][inner] <-> dst [N][inner][Cpad]; tiled 32x32 transposes through shared memory.
-__global__ void nc_to_cl_k(const float* __restrict__ src, float* __restrict__ dst, int C, int64_t inner, int Cpad) {
+// Clip feeding (C <= 4 planes -> 4-channel pixels): one thread converts 4 consecutive positions: C coalesced 16-byte
+// plane loads -> four 16-byte pixel stores (64 contiguous bytes per thread), optional TF32 rounding of the conv1 operand.
+// The generic 32x32 tile kernel below moves only 3 of its 32 tile rows for a clip (0.39 TB/s measured).
+__global__ void nc_to_cl4_k(const float* __restrict__ src, float4* __restrict__ dst, int C, int64_t inner4,
+                            int64_t total, int tf32) {
+  pdl_prologue();
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = q / inner4, i4 = q - n * inner4;
+    float4 p[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      p[c] = c < C ? *reinterpret_cast<const float4*>(src + ((n * C + c) * inner4 + i4) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tf32) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        p[c].x = round_tf32(p[c].x); p[c].y = round_tf32(p[c].y); p[c].z = round_tf32(p[c].z); p[c].w = round_tf32(p[c].w);
+      }
+    }
+    float4* o = dst + (n * inner4 + i4) * 4;
+    o[0] = make_float4(p[0].x, p[1].x, p[2].x, p[3].x);
+    o[1] = make_float4(p[0].y, p[1].y, p[2].y, p[3].y);
+    o[2] = make_float4(p[0].z, p[1].z, p[2].z, p[3].z);
+    o[3] = make_float4(p[0].w, p[1].w, p[2].w, p[3].w);
+  }
+}
+
+__global__ void nc_to_cl_k(const float* __restrict__ src, float* __restrict__ dst, int C, int64_t inner, int Cpad,
+                           int tf32) {
   pdl_prologue();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
@@ -503,7 +530,10 @@ __global__ void nc_to_cl_k(const float* __restrict__ src, float* __restrict__ ds
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int64_t i = i0 + r;
     const int c = c0 + threadIdx.x;
-    if (i < inner && c < Cpad) dst[((int64_t)n * inner + i) * Cpad + c] = tile[threadIdx.x][r];
+    if (i < inner && c < Cpad) {
+      const float v = tile[threadIdx.x][r];
+      dst[((int64_t)n * inner + i) * Cpad + c] = tf32 ? round_tf32(v) : v;
+    }
   }
 }
 
@@ -957,12 +987,22 @@ int vlfb_copy2d(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t 
   return VLFB_OK;
 }
 
-int vlfb_nc_to_cl(const float* src, float* dst, int N, int C, int64_t inner, int Cpad, void* stream) {
+int vlfb_nc_to_cl_round(const float* src, float* dst, int N, int C, int64_t inner, int Cpad, int tf32_out, void* stream) {
   VLFB_CHECK_ARG(src && dst && N > 0 && C > 0 && inner > 0 && Cpad >= C);
+  if (Cpad == 4 && (inner & 3) == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0) {
+    const int64_t total = (int64_t)N * (inner >> 2);
+    launch_k(nc_to_cl4_k, stream_grid(total, TPB), TPB, 0, ST(stream), src, (float4*)dst, C, inner >> 2, total, tf32_out);
+    VLFB_CHECK_LAUNCH();
+    return VLFB_OK;
+  }
   dim3 grid(ceil_div(inner, 32), ceil_div(Cpad, 32), N), block(32, 8);
-  launch_k(nc_to_cl_k, grid, block, 0, ST(stream), src, dst, C, inner, Cpad);
+  launch_k(nc_to_cl_k, grid, block, 0, ST(stream), src, dst, C, inner, Cpad, tf32_out);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
+}
+
+int vlfb_nc_to_cl(const float* src, float* dst, int N, int C, int64_t inner, int Cpad, void* stream) {
+  return vlfb_nc_to_cl_round(src, dst, N, C, inner, Cpad, 0, stream);
 }
 
 int vlfb_cl_to_nc(const float* src, float* dst, int N, int C, int64_t inner, int Cpad, void* stream) {

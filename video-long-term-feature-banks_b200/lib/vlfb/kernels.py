@@ -468,8 +468,9 @@ def copy2d(src, lds, dst, ldd, rows, cols, accumulate=False, src_off=0, dst_off=
             'copy2d')
 
 
-def nc_to_cl(src, dst, n, c, inner, cpad=None):
-    _check(L.load().vlfb_nc_to_cl(_ptr(_f32c(src)), _ptr(_f32c(dst)), n, c, inner, cpad or c, _stream()), 'nc_to_cl')
+def nc_to_cl(src, dst, n, c, inner, cpad=None, tf32_out=False):
+    _check(L.load().vlfb_nc_to_cl_round(_ptr(_f32c(src)), _ptr(_f32c(dst)), n, c, inner, cpad or c, int(tf32_out),
+                                        _stream()), 'nc_to_cl')
 
 
 def cl_to_nc(src, dst, n, c, inner, cpad=None):

@@ -405,8 +405,7 @@ def _feed_activation(name, arr):
             stage = _static(name + '/ncthw', src.shape, X.DTYPE)
             stage.copy_(src, non_blocking=True)                   # H2D (async from pinned memory)
         p = _static(name, (n, src.shape[2], src.shape[3], src.shape[4], cpad), X.DTYPE)
-        X.K.nc_to_cl(stage, p, n, c, inner, cpad)                 # reference NCTHW blob -> NDHWC (+pad 3->4)
-        X.K.round_tf32(p.view(-1), p.view(-1))
+        X.K.nc_to_cl(stage, p, n, c, inner, cpad, tf32_out=True)  # reference NCTHW blob -> NDHWC (+pad 3->4), TF32-rounded
         _ws.blobs[name] = p.permute(0, 4, 1, 2, 3)
         _ws.rounded.add(name)
         return
