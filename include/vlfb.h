@@ -43,6 +43,10 @@ int vlfb_get_gemm_backend(void);
 /* Programmatic dependent launch of every kernel of the library (default off; env VLFB_PDL=1 enables): each
  * kernel's launch and prologue overlap the tail of its predecessor in the stream. */
 int vlfb_set_pdl(int enabled);
+/* GEMM output-tile widths: 0 = {32, 64, 128, 256} columns (default), 1 = also {96, 160, 192, 224} so that small-M
+ * layers (res4/res5: 49 row tiles) can fill the 148 SMs in one round (env VLFB_BN_EXTRA=1). */
+int vlfb_set_tile_widths(int extra);
+
 
 /* ---- gathered GEMM: D[m,n] = epi( sum_k A[m,k] * B[n,k] ) ------------------------------ */
 /* One descriptor per operand.  `kind`:
@@ -105,6 +109,9 @@ typedef struct {
  * FC at resnet_video.py:327-331; and the AffineNd / Relu / Sum epilogues that follow
  * them (model_builder_video.py:218-219, resnet_helper.py:112-117). */
 int vlfb_gemm(const vlfb_gemm_params_t* p, void* stream);
+/* Host-only query: the output-tile width, split-K factor and tile count vlfb_gemm would use for `p` on a device with
+ * `num_sms` SMs (<= 0: 148).  No launch, no device access. */
+int vlfb_gemm_plan(const vlfb_gemm_params_t* p, int num_sms, int* bn, int* split_k, int* tiles);
 
 /* ---- AffineNd (standalone; caffe2_customized_ops/video/affine_nd_op.cu:62-104) ---------- */
 int vlfb_affine_nd_fwd(const float* x, const float* scale, const float* bias, float* y,

@@ -61,3 +61,35 @@ def test_wt_job_layout(tmp_path):
     subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
     assert subprocess.check_output([str(exe)]).decode().split() == ['40', '8', '16', '24', '36']
 
+
+
+def test_gemm_plan_query_and_optional_tile_widths():
+    """Host-only: the (tile width, split-K, tile count) the tensor-core GEMM would use.  Default widths are powers of
+    two; vlfb_set_tile_widths(1) adds 96/160/192/224 so that the 49-row-tile layers of res4/res5 fill 148 SMs."""
+    import ctypes as C
+    from vlfb import libvlfb as L
+    lib = L.load()
+
+    def plan(M, N, K, extra, split=1, taps=1):
+        lib.vlfb_set_tile_widths(extra)
+        p = L.GemmParams()
+        p.M, p.N, p.K, p.batch, p.taps, p.split_k = M, N, K, 1, taps, split
+        bn, sp, t = C.c_int(), C.c_int(), C.c_int()
+        assert lib.vlfb_gemm_plan(C.byref(p), 148, C.byref(bn), C.byref(sp), C.byref(t)) == 0
+        return bn.value, sp.value, t.value
+
+    try:
+        assert plan(6272, 512, 4608, 0) == (256, 1, 98)          # res5 3x3: 98 of 148 SMs
+        assert plan(6272, 512, 4608, 1) == (192, 1, 147)         # one full round
+        assert plan(6272, 256, 3072, 0) == (128, 1, 98) and plan(6272, 256, 3072, 1) == (96, 1, 147)
+        assert plan(200704, 256, 64, 1) == plan(200704, 256, 64, 0)      # large-M layers keep 256
+        for M, N, K in [(4, 80, 2560), (3136, 784, 256), (512, 4608, 6272), (64, 224, 802816), (1, 300, 512)]:
+            for extra in (0, 1):
+                bn, sp, tiles = plan(M, N, K, extra, split=0)
+                assert bn % 32 == 0 and 32 <= bn <= 256 and sp >= 1
+                assert extra or bn & (bn - 1) == 0
+                assert bn == 32 or N > bn // 2                   # never pad N by 2x or more
+                assert tiles == -(-M // 128) * -(-N // bn) * sp
+        assert lib.vlfb_gemm_plan(None, 148, None, None, None) == -1
+    finally:
+        lib.vlfb_set_tile_widths(0)

@@ -554,3 +554,52 @@ def test_lfb_gather_is_bit_exact(K, rows, n, D):
     assert torch.equal(out.cpu(), ref)
     K.lfb_gather(bank.cuda(), idx.cuda(), out, tf32_out=True)
     assert torch.equal(out.cpu(), tf32_round(ref))
+
+
+# -------------------------------------------------------------------------- optional tile widths (96/160/192/224)
+def test_extra_tile_widths_give_the_same_results(K):
+    """vlfb_set_tile_widths(1): the res4/res5-shaped GEMMs switch to 96- / 192-column tiles (147 tiles = one round on
+    148 SMs).  Without split-K the K reduction order per output element is unchanged, so results must be bit-identical
+    to the power-of-two tiling; fp64 reference for one case."""
+    from vlfb import libvlfb as L
+    lib = L.load()
+    K.set_gemm_backend('tcgen05')
+
+    def conv_case(Ci, Co, ker, pd, dil=(1, 1, 1), residual=False, seed=0):
+        g = K.conv_geom((2, 16, 14, 14, Ci), Co, ker, (1, 1, 1), pd, dil)
+        x, w = rnd((2, 16, 14, 14, Ci), seed).cuda(), (rnd((Co,) + tuple(ker) + (Ci,), seed + 1) * 0.05).cuda()
+        s, b = (torch.rand(Co) + 0.5).cuda(), torch.randn(Co).cuda()
+        res = torch.randn(K.out_shape(g)).cuda() if residual else None
+        return g, x, w, s, b, res
+
+    cases = [conv_case(512, 512, (1, 3, 3), (0, 2, 2), (1, 2, 2)),            # res5 branch2b: 256 -> 192
+             conv_case(1024, 256, (3, 1, 1), (1, 0, 0), seed=3),              # res4 branch2a: 128 -> 96
+             conv_case(256, 1024, (1, 1, 1), (0, 0, 0), residual=True, seed=5),  # res4 branch2c (+residual): 256 -> 192
+             conv_case(256, 200, (1, 3, 3), (0, 1, 1), seed=7)]               # ragged N (200 = 192 + 8 / 160 + 40)
+    try:
+        outs = {}
+        for extra in (0, 1):
+            lib.vlfb_set_tile_widths(extra)
+            for i, (g, x, w, s, b, res) in enumerate(cases):
+                y = torch.full(K.out_shape(g), float('nan'), device='cuda')
+                K.conv_fwd(x, w, y, g, scale=s, bias=b, residual=res, relu=True, tf32_out=True)
+                taps = g.kT * g.kH * g.kW
+                wt = torch.empty((g.C, taps, g.Co), device='cuda')
+                K.weight_transpose(w, wt, s)
+                dx = torch.full((2, 16, 14, 14, g.C), float('nan'), device='cuda')
+                K.conv_dgrad(y, wt, dx, g, tf32_out=True)
+                a = rnd((2, 392, 256), 20 + i).cuda()
+                bm = rnd((2, 256, 784 if i % 2 == 0 else 520), 30 + i).cuda()
+                d = torch.full((2, 392, bm.shape[2]), float('nan'), device='cuda')
+                K.matmul(a, bm, d, tf32_out=True)
+                torch.cuda.synchronize()
+                outs[(extra, i)] = (y.cpu(), dx.cpu(), d.cpu())
+        for i in range(len(cases)):
+            for u, v in zip(outs[(0, i)], outs[(1, i)]):
+                assert torch.isfinite(v).all() and torch.equal(u, v), i
+        g, x, w, s, b, res = cases[0]
+        ref = F.conv3d(to_nc(x.cpu()).double(), w.cpu().permute(0, 4, 1, 2, 3).double(), None, (1, 1, 1), (0, 2, 2), (1, 2, 2))
+        ref = torch.relu(ref * s.cpu().double().view(1, -1, 1, 1, 1) + b.cpu().double().view(1, -1, 1, 1, 1))
+        assert rel_err(to_nc(outs[(1, 0)][0]), ref) < 1e-3            # output itself is TF32-rounded (tf32_out)
+    finally:
+        lib.vlfb_set_tile_widths(0)

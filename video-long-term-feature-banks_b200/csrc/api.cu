@@ -10,6 +10,15 @@ namespace vlfb {
 static thread_local char g_err[512] = "";
 static int g_backend = 0;
 static int g_pdl = -1;          // -1: read VLFB_PDL on first use
+static int g_extra_bn = -1;     // -1: read VLFB_BN_EXTRA on first use
+bool extra_tile_widths() {
+  if (g_extra_bn < 0) {
+    const char* e = getenv("VLFB_BN_EXTRA");
+    g_extra_bn = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return g_extra_bn != 0;
+}
+void set_extra_tile_widths(int on) { g_extra_bn = on ? 1 : 0; }
 bool pdl_enabled() {
   if (g_pdl < 0) {
     const char* e = getenv("VLFB_PDL");
@@ -103,6 +112,17 @@ int vlfb_set_gemm_backend(int backend) {
   return VLFB_OK;
 }
 int vlfb_get_gemm_backend(void) { return g_backend; }
+int vlfb_gemm_plan(const vlfb_gemm_params_t* p, int num_sms, int* bn, int* split_k, int* tiles) {
+  VLFB_CHECK_ARG(p && bn && split_k && tiles && p->M > 0 && p->N > 0 && p->K > 0);
+  gemm_tc_plan(*p, num_sms > 0 ? num_sms : 148, bn, split_k, tiles);
+  return VLFB_OK;
+}
+
+int vlfb_set_tile_widths(int extra) {
+  set_extra_tile_widths(extra);
+  return VLFB_OK;
+}
+
 int vlfb_set_pdl(int enabled) {
   g_pdl = enabled ? 1 : 0;
   return VLFB_OK;

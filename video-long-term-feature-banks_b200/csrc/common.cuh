@@ -40,6 +40,9 @@ static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b)
 // captured training step it changes nothing (18.04 vs 17.97 ms; 18.2 with the early trigger) -- the step is bound
 // by kernel execution, not by launch gaps.  Without the attribute the instructions are no-ops.
 bool pdl_enabled();
+// GEMM tile widths beyond the power-of-two set (96/160/192/224 columns): see gemm_tc.cu launch()
+bool extra_tile_widths();
+void set_extra_tile_widths(int on);
 __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 #ifndef VLFB_PDL_NO_TRIGGER
@@ -169,5 +172,6 @@ __device__ __forceinline__ void epilogue_store(const vlfb_gemm_params_t& p, int 
 
 int gemm_simt(const vlfb_gemm_params_t& p, cudaStream_t stream);
 int gemm_tc(const vlfb_gemm_params_t& p, cudaStream_t stream);
+void gemm_tc_plan(const vlfb_gemm_params_t& p, int num_sms, int* bn, int* split_k, int* tiles);
 
 }  // namespace vlfb

@@ -571,7 +571,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
             make_float4(0.f, 0.f, 0.f, 0.f);
     fence_proxy_async();
   }
-  const uint32_t tmem_cols = (uint32_t)(2 * bn < 32 ? 32 : 2 * bn);
+  uint32_t tmem_cols = 32;              // tcgen05.alloc takes a power of two >= 32; two accumulators of bn columns
+  while (tmem_cols < (uint32_t)(2 * bn)) tmem_cols <<= 1;
   if (warp == NPW) tmem_alloc(tptr_addr, tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -1057,6 +1058,42 @@ static Env read_env() {
   return e;
 }
 
+// Tile width and split-K (p.split_k == 0: chosen here).  The persistent grid runs ceil(tiles / #SMs) rounds;
+// a round of a 128 x bn tile costs ~(128 + bn) bytes of operand traffic per k over (K / split) chunks plus a
+// fixed fill + epilogue overhead (~8 chunks), so take the (bn, split) pair that minimises
+// rounds * (chunks + 8) * (128 + bn).  With the old fixed rules conv1's wgrad ran 300 tiles on 148 SMs
+// (3 rounds for 2.03 waves of work) and the res2 3x3 wgrads 192 tiles (2 rounds for 1.3 waves).
+void choose_tile(const vlfb_gemm_params_t& p, int num_sms, int* bn_out, int* split_out) {
+  const int zbase = p.taps > 1 ? p.taps : p.batch;
+  const int tiles_m = ceil_div(p.M, BM);
+  int best_bn = 32, best_split = p.split_k > 0 ? p.split_k : 1;
+  double best_score = 1e30;
+  const int smax = p.split_k > 0 ? p.split_k : (p.K >= 512 ? (p.K / 256 < 128 ? p.K / 256 : 128) : 1);
+  // Candidate widths.  The power-of-two set leaves the small-M layers badly quantised: res5's 3x3 convolutions
+  // (M = 6272 = 49 row tiles, N = 512) run 98 tiles of 128 x 256 on 148 SMs -- ncu: tensor pipe 65 % of the ACTIVE
+  // cycles but 40 % of the elapsed ones (profiles/r01_ncu_full_gemm3_res45_summary.csv); 147 tiles of 128 x 192
+  // fill the machine in one round.  UMMA takes any N % 16 == 0 (M = 128); the loaders / epilogue work in
+  // 32-column atoms.  Enabled by vlfb_set_tile_widths(1) / VLFB_BN_EXTRA=1 (default off until measured).
+  static const int kWidths[] = {256, 224, 192, 160, 128, 96, 64, 32};
+  const bool extra = extra_tile_widths();
+  for (int wi = 0; wi < 8; ++wi) {
+    const int bn = kWidths[wi];
+    if (!extra && (bn & (bn - 1)) != 0) continue;
+    if (bn > 32 && p.N <= bn / 2) continue;                       // do not pad N by 2x
+    if ((bn & (bn - 1)) != 0 && (int64_t)ceil_div(p.N, bn) * bn >= 2 * (int64_t)p.N) continue;
+    const int64_t base_tiles = (int64_t)tiles_m * ceil_div(p.N, bn) * zbase;
+    for (int sp = (p.split_k > 0 ? p.split_k : 1); sp <= smax; ++sp) {
+      const int64_t tiles = base_tiles * sp;
+      const double rounds = (double)((tiles + num_sms - 1) / num_sms);
+      const double chunks = (double)ceil_div(ceil_div(p.K, sp), KC) + 8.0;
+      const double score = rounds * chunks * (128 + bn);
+      if (score < best_score * 0.999) { best_score = score; best_bn = bn; best_split = sp; }
+    }
+  }
+  *bn_out = best_bn;
+  *split_out = best_split;
+}
+
 template <int AK, int BK, bool MASK>
 int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
   vlfb_gemm_params_t p = p_in;       // split_k == 0 is resolved below
@@ -1078,26 +1115,9 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
   static const Env env = read_env();
   const int zbase = p.taps > 1 ? p.taps : p.batch;
   const int tiles_m = ceil_div(p.M, BM);
-  // Tile width and split-K (p.split_k == 0: chosen here).  The persistent grid runs ceil(tiles / #SMs) rounds;
-  // a round of a 128 x bn tile costs ~(128 + bn) bytes of operand traffic per k over (K / split) chunks plus a
-  // fixed fill + epilogue overhead (~8 chunks), so take the (bn, split) pair that minimises
-  // rounds * (chunks + 8) * (128 + bn).  With the old fixed rules conv1's wgrad ran 300 tiles on 148 SMs
-  // (3 rounds for 2.03 waves of work) and the res2 3x3 wgrads 192 tiles (2 rounds for 1.3 waves).
   {
-    int best_bn = 32, best_split = p.split_k > 0 ? p.split_k : 1;
-    double best_score = 1e30;
-    const int smax = p.split_k > 0 ? p.split_k : (p.K >= 512 ? (p.K / 256 < 128 ? p.K / 256 : 128) : 1);
-    for (int bn = 256; bn >= 32; bn >>= 1) {
-      if (bn > 32 && p.N <= bn / 2) continue;                       // do not pad N by 2x
-      const int64_t base_tiles = (int64_t)tiles_m * ceil_div(p.N, bn) * zbase;
-      for (int sp = (p.split_k > 0 ? p.split_k : 1); sp <= smax; ++sp) {
-        const int64_t tiles = base_tiles * sp;
-        const double rounds = (double)((tiles + num_sms - 1) / num_sms);
-        const double chunks = (double)ceil_div(ceil_div(p.K, sp), KC) + 8.0;
-        const double score = rounds * chunks * (128 + bn);
-        if (score < best_score * 0.999) { best_score = score; best_bn = bn; best_split = sp; }
-      }
-    }
+    int best_bn = 32, best_split = 1;
+    choose_tile(p, num_sms, &best_bn, &best_split);
     L.bn = best_bn;
     p.split_k = best_split;
   }
@@ -1165,6 +1185,12 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
 }
 
 }  // namespace tc
+
+void gemm_tc_plan(const vlfb_gemm_params_t& p, int num_sms, int* bn, int* split_k, int* tiles) {
+  tc::choose_tile(p, num_sms, bn, split_k);
+  const int zbase = p.taps > 1 ? p.taps : p.batch;
+  *tiles = ceil_div(p.M, tc::BM) * ceil_div(p.N, *bn) * zbase * *split_k;
+}
 
 int gemm_tc(const vlfb_gemm_params_t& p, cudaStream_t stream) {
   const int ak = p.a.kind, bk = p.b.kind;
