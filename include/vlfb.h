@@ -46,6 +46,7 @@ int vlfb_set_pdl(int enabled);
 /* GEMM output-tile widths: 0 = {32, 64, 128, 256} columns (default), 1 = also {96, 160, 192, 224} so that small-M
  * layers (res4/res5: 49 row tiles) can fill the 148 SMs in one round (env VLFB_BN_EXTRA=1). */
 int vlfb_set_tile_widths(int extra);
+int vlfb_get_tile_widths(void);
 
 
 /* ---- gathered GEMM: D[m,n] = epi( sum_k A[m,k] * B[n,k] ) ------------------------------ */

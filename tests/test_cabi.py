@@ -69,6 +69,7 @@ def test_gemm_plan_query_and_optional_tile_widths():
     import ctypes as C
     from vlfb import libvlfb as L
     lib = L.load()
+    before = lib.vlfb_get_tile_widths()
 
     def plan(M, N, K, extra, split=1, taps=1):
         lib.vlfb_set_tile_widths(extra)
@@ -92,4 +93,4 @@ def test_gemm_plan_query_and_optional_tile_widths():
                 assert tiles == -(-M // 128) * -(-N // bn) * sp
         assert lib.vlfb_gemm_plan(None, 148, None, None, None) == -1
     finally:
-        lib.vlfb_set_tile_widths(0)
+        lib.vlfb_set_tile_widths(before)

@@ -563,6 +563,7 @@ def test_extra_tile_widths_give_the_same_results(K):
     to the power-of-two tiling; fp64 reference for one case."""
     from vlfb import libvlfb as L
     lib = L.load()
+    before = lib.vlfb_get_tile_widths()
     K.set_gemm_backend('tcgen05')
 
     def conv_case(Ci, Co, ker, pd, dil=(1, 1, 1), residual=False, seed=0):
@@ -602,4 +603,4 @@ def test_extra_tile_widths_give_the_same_results(K):
         ref = torch.relu(ref * s.cpu().double().view(1, -1, 1, 1, 1) + b.cpu().double().view(1, -1, 1, 1, 1))
         assert rel_err(to_nc(outs[(1, 0)][0]), ref) < 1e-3            # output itself is TF32-rounded (tf32_out)
     finally:
-        lib.vlfb_set_tile_widths(0)
+        lib.vlfb_set_tile_widths(before)

@@ -118,6 +118,8 @@ int vlfb_gemm_plan(const vlfb_gemm_params_t* p, int num_sms, int* bn, int* split
   return VLFB_OK;
 }
 
+int vlfb_get_tile_widths(void) { return extra_tile_widths() ? 1 : 0; }
+
 int vlfb_set_tile_widths(int extra) {
   set_extra_tile_widths(extra);
   return VLFB_OK;

@@ -44,6 +44,7 @@ SIGNATURES = {
     'vlfb_get_gemm_backend': [],
     'vlfb_set_pdl': [_I],
     'vlfb_set_tile_widths': [_I],
+    'vlfb_get_tile_widths': [],
     'vlfb_gemm': [C.POINTER(GemmParams), _P],
     'vlfb_gemm_plan': [C.POINTER(GemmParams), _I, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
     'vlfb_affine_nd_fwd': [_P, _P, _P, _P, _L, _I, _P],
