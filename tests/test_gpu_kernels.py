@@ -576,7 +576,7 @@ def test_extra_tile_widths_give_the_same_results(K):
     cases = [conv_case(512, 512, (1, 3, 3), (0, 2, 2), (1, 2, 2)),            # res5 branch2b: 256 -> 192
              conv_case(1024, 256, (3, 1, 1), (1, 0, 0), seed=3),              # res4 branch2a: 128 -> 96
              conv_case(256, 1024, (1, 1, 1), (0, 0, 0), residual=True, seed=5),  # res4 branch2c (+residual): 256 -> 192
-             conv_case(256, 200, (1, 3, 3), (0, 1, 1), seed=7)]               # ragged N (200 = 192 + 8 / 160 + 40)
+             conv_case(256, 224, (1, 3, 3), (0, 1, 1), seed=7)]               # N = 224: one 224-column tile
     try:
         outs = {}
         for extra in (0, 1):
