@@ -29,8 +29,8 @@ ROIS_PER_CLIP = 2
 BANK_ROWS = 300
 # algorithmic FLOPs per 32x224x224 clip, R50-I3D-NL, fwd+bwd (3x fwd - conv1 dgrad)
 GFLOP_PER_CLIP_FWD_BWD = 1106.0
-# ncu (profiles/r01_ncu_launches_final.csv): DRAM bytes of the 292 gemm_tc_kernel launches of one training step
-# = 14503 MB read + 1705 MB written -> average per launch.  bench.py cannot run ncu itself; re-measure per round.
+# ncu (profiles/r01_ncu_launches_final_s2.csv): DRAM bytes of the 292 gemm_tc_kernel launches of one training step
+# = 14496 MB read + 1700 MB written -> average per launch.  bench.py cannot run ncu itself; re-measure per round.
 NCU_DRAM_BYTES_PER_GEMM_LAUNCH = 55.5e6
 
 
@@ -352,12 +352,12 @@ def run_b200(args):
         'clocks': sampler.summary(),
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf32, 'unit': 'TFLOP/s',
                      'frac': achieved / peak_tf32 if peak_tf32 else None, 'traffic': NCU_DRAM_BYTES_PER_GEMM_LAUNCH,
-                     'traffic_source': 'profiles/r01_ncu_launches_final_summary.txt: dram__bytes_read+write summed over '
+                     'traffic_source': 'profiles/r01_ncu_launches_final_s2_summary.txt: dram__bytes_read+write summed over '
                                        'the 292 GEMM launches of one step (16.2 GB) / 292',
                      'flop_per_launch': gflop_step * 1e9 / max(len(recs), 1),
                      'kernel': 'vlfb::tc::gemm_tc_kernel: all %d launches of one step timed with CUDA events around each '
                                'launch in an eager step = %.2f ms (includes inter-launch gaps, so achieved is a lower '
-                               'bound; ncu kernel time of the same launches: profiles/r01_ncu_launches_final_summary.txt); '
+                               'bound; ncu kernel time of the same launches: profiles/r01_ncu_launches_final_s2_summary.txt); '
                                'the captured step takes %.2f ms in total' % (len(recs), gemm_ms, ms),
                      'peak_source': '%s bf16_tflops_sustained / 2 (kind::tf32)' % peak_src,
                      'per_launch_roofline': {
