@@ -94,3 +94,22 @@ def test_gemm_plan_query_and_optional_tile_widths():
         assert lib.vlfb_gemm_plan(None, 148, None, None, None) == -1
     finally:
         lib.vlfb_set_tile_widths(before)
+
+
+def test_fbo_bank_scan_split_table_properties():
+    """Host-only: the split of a RoI's L bank rows over CTAs never leaves an empty split, covers all rows, and the
+    workspace query matches it (csrc/fbo.cu vlfb_fbo_bank_scan_splits)."""
+    from vlfb import libvlfb as L
+    lib = L.load()
+    for D, rows_per_tile in [(1024, 8), (2048, 8), (4096, 4)]:
+        for R in (1, 2, 3, 4, 16, 37, 64, 255, 256, 1000):
+            for Lb in (1, 2, 7, 8, 9, 60, 300, 301, 1200, 3600):
+                s = lib.vlfb_fbo_bank_scan_splits(R, Lb, D)
+                per = -(-Lb // s)
+                assert 1 <= s <= 1024 and (s - 1) * per < Lb <= s * per, (R, Lb, D, s)
+                assert s <= -(-Lb // rows_per_tile), 'a split holds at least one tile of rows'
+                assert lib.vlfb_fbo_bank_scan_workspace(R, Lb, D) == (R * s * D + R * s * 2) * 4
+    for bad in [(0, 300, 2048), (4, 0, 2048), (4, 300, 512), (4, 300, 2047)]:
+        assert lib.vlfb_fbo_bank_scan_splits(*bad) == 0 and lib.vlfb_fbo_bank_scan_workspace(*bad) == 0
+    # many RoIs: enough CTAs for two per SM without splitting rows needlessly
+    assert lib.vlfb_fbo_bank_scan_splits(1000, 17, 2048) <= 3

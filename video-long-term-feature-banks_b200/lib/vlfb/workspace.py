@@ -119,7 +119,9 @@ class ParamStore(object):
         self.refresh_tf32(name)
 
     def fetch(self, name, which='P'):
-        return self.logical(name, which).detach().cpu().contiguous().numpy()
+        t = self.logical(name, which).detach()
+        a = t.cpu().contiguous().numpy()
+        return a if t.is_cuda else a.copy()
 
     def stem_mask(self):
         if self._mask is None:
@@ -499,6 +501,8 @@ def FetchBlob(name):
     if t.dim() == 5 and t.shape[1] == 4 and name.startswith('data'):
         t = t[:, :3]
     a = t.detach().cpu().contiguous().numpy()
+    if not t.is_cuda:
+        a = a.copy()              # the CPU test engine would otherwise hand out a view of a reusable input buffer
     if name in ('loss', 'lr') or a.size == 1 and name.startswith('loss'):
         return a.reshape(()) if a.size == 1 else a
     return a
