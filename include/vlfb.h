@@ -14,7 +14,9 @@
  *   - activations are fp32, channels-last ("NDHWC": [N][T][H][W][C]); conv weights are
  *     [Cout][kT][kH][kW][Cin]
  *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), never
- *     synchronise, never allocate, keep no mutable global state
+ *     synchronise, never allocate, keep no mutable global state (engine / tiling choices are per-call
+ *     fields of vlfb_gemm_params_t; the only process state is immutable: cached driver entry points,
+ *     occupancy queries and environment overrides read once)
  *   - return value: 0 = ok, <0 = error (see VLFB_E_*); vlfb_last_error() gives the text
  */
 #ifndef VLFB_H_
@@ -36,18 +38,6 @@ extern "C" {
 /* ---- library ------------------------------------------------------------------------- */
 int vlfb_version(void);                 /* 100 * major + minor */
 const char* vlfb_last_error(void);      /* thread-local message of the last failing call */
-/* which contraction engine vlfb_gemm uses: 0 = tcgen05 tensor cores (default),
- * 1 = SIMT fp32 debug kernel (bring-up / on-GPU cross-check only). */
-int vlfb_set_gemm_backend(int backend);
-int vlfb_get_gemm_backend(void);
-/* Programmatic dependent launch of every kernel of the library (default off; env VLFB_PDL=1 enables): each
- * kernel's launch and prologue overlap the tail of its predecessor in the stream. */
-int vlfb_set_pdl(int enabled);
-/* GEMM output-tile widths: 0 = {32, 64, 128, 256} columns (default), 1 = also {96, 160, 192, 224} so that small-M
- * layers (res4/res5: 49 row tiles) can fill the 148 SMs in one round (env VLFB_BN_EXTRA=1). */
-int vlfb_set_tile_widths(int extra);
-int vlfb_get_tile_widths(void);
-
 
 /* ---- gathered GEMM: D[m,n] = epi( sum_k A[m,k] * B[n,k] ) ------------------------------ */
 /* One descriptor per operand.  `kind`:
@@ -102,7 +92,30 @@ typedef struct {
                                * residual / ReLU, before the TF32 rounding).  Backward of a ReLU fused into the
                                * dgrad GEMM that produces the gradient: mask = the ReLU's output */
   int flags;                  /* VLFB_EPI_*                                  */
+  /* ---- per-call execution options (0 = library default) ---- */
+  void* workspace;            /* stream-K scratch (partial tiles + arrival counters) of >= vlfb_gemm_workspace_bytes()
+                               * bytes, 16-byte aligned, ZERO-FILLED ONCE by the caller before its first use and then
+                               * only touched by vlfb_gemm (the counters are zero again when a launch ends); calls that
+                               * share it must be ordered on one stream.  NULL: stream-K is not used for non-atomic
+                               * epilogues. */
+  size_t workspace_bytes;
+  int engine;                 /* VLFB_ENGINE_TCGEN05 (0, default) or VLFB_ENGINE_SIMT (fp32 cross-check engine) */
+  int tile_n;                 /* 0 = chosen by the library, else the output-tile width (32..256, multiple of 32) */
+  int pair;                   /* 0 = auto, 1 = CTA pairs (cta_group::2, 256-row tiles) whenever legal, -1 = never */
+  int stream_k;               /* 0 = auto, 1 = stream-K whenever legal, -1 = never */
 } vlfb_gemm_params_t;
+
+enum { VLFB_ENGINE_TCGEN05 = 0, VLFB_ENGINE_SIMT = 1 };
+
+/* What vlfb_gemm would do for `p` (host-only, no launch). */
+typedef struct {
+  int tile_n;                 /* output-tile width */
+  int split_k;                /* plain split-K factor (atomic epilogues) */
+  int pair;                   /* 1: 256 x tile_n tiles on CTA pairs (tcgen05 cta_group::2) */
+  int stream_k;               /* 1: equal (tile, K-chunk) ranges per SM (pair), shared tiles fixed up in the workspace */
+  int tiles;                  /* output tiles (x split_k) */
+  int units;                  /* CTAs (or CTA pairs) of the persistent grid */
+} vlfb_gemm_plan_t;
 
 /* Replaces: Caffe2 Conv (cuDNN) at resnet_video.py:169-179, model_builder_video.py:211-217,
  * nonlocal_helper.py:36-78,131-144, lfb_helper.py:175-202,244-251,305-334; its gradients;
@@ -110,9 +123,11 @@ typedef struct {
  * FC at resnet_video.py:327-331; and the AffineNd / Relu / Sum epilogues that follow
  * them (model_builder_video.py:218-219, resnet_helper.py:112-117). */
 int vlfb_gemm(const vlfb_gemm_params_t* p, void* stream);
-/* Host-only query: the output-tile width, split-K factor and tile count vlfb_gemm would use for `p` on a device with
- * `num_sms` SMs (<= 0: 148).  No launch, no device access. */
-int vlfb_gemm_plan(const vlfb_gemm_params_t* p, int num_sms, int* bn, int* split_k, int* tiles);
+/* Host-only query: the tiling / schedule vlfb_gemm would use for `p` on a device with `num_sms` SMs (<= 0: 148),
+ * assuming every operand is TMA-addressable.  No launch, no device access. */
+int vlfb_gemm_plan(const vlfb_gemm_params_t* p, int num_sms, vlfb_gemm_plan_t* plan);
+/* Bytes of vlfb_gemm_params_t.workspace that enable stream-K for every problem size (a constant of the build). */
+size_t vlfb_gemm_workspace_bytes(void);
 
 /* ---- AffineNd (standalone; caffe2_customized_ops/video/affine_nd_op.cu:62-104) ---------- */
 int vlfb_affine_nd_fwd(const float* x, const float* scale, const float* bias, float* y,

@@ -27,7 +27,12 @@ def test_argument_validation_without_gpu():
     lib = libvlfb.load()
     assert lib.vlfb_gemm(None, None) == -1
     assert b'bad argument' in lib.vlfb_last_error()
-    assert lib.vlfb_set_gemm_backend(7) == -1
+    p = libvlfb.GemmParams()
+    p.a.ptr = p.b.ptr = p.d = 256                       # never dereferenced: validation fails first
+    p.M, p.N, p.K, p.batch, p.taps, p.split_k, p.engine = 128, 128, 128, 1, 1, 1, 7
+    assert lib.vlfb_gemm(ctypes.byref(p), None) == -1 and b'engine' in lib.vlfb_last_error()
+    p.engine, p.tile_n = 0, 48
+    assert lib.vlfb_gemm(ctypes.byref(p), None) == -1 and b'tile_n' in lib.vlfb_last_error()
     assert lib.vlfb_relu_fwd(None, None, 4, None) == -1
 
 
@@ -35,17 +40,18 @@ def test_struct_layout_matches_header(tmp_path):
     """sizeof / offsetof of the C structs, as the C compiler sees include/vlfb.h, equal the ctypes mirror."""
     import subprocess
     from vlfb import libvlfb as L
-    fields = ['a', 'b', 'g', 'M', 'split_k', 'd', 'ldd', 'alpha', 'col_scale', 'residual', 'relu_mask', 'flags']
+    fields = ['a', 'b', 'g', 'M', 'split_k', 'd', 'ldd', 'alpha', 'col_scale', 'residual', 'relu_mask', 'flags',
+              'workspace', 'workspace_bytes', 'engine', 'tile_n', 'pair', 'stream_k']
     src = tmp_path / 'layout.c'
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vlfb.h"\nint main(void) {\n'
-                   '  printf("%zu %zu %zu\\n", sizeof(vlfb_conv_geom_t), sizeof(vlfb_operand_t), sizeof(vlfb_gemm_params_t));\n'
+                   '  printf("%zu %zu %zu %zu\\n", sizeof(vlfb_conv_geom_t), sizeof(vlfb_operand_t), sizeof(vlfb_gemm_params_t), sizeof(vlfb_gemm_plan_t));\n'
                    + ''.join('  printf("%%zu\\n", offsetof(vlfb_gemm_params_t, %s));\n' % f for f in fields)
                    + '  return 0;\n}\n')
     exe = tmp_path / 'layout'
     subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
     out = subprocess.check_output([str(exe)]).decode().split()
-    sizes, offs = [int(v) for v in out[:3]], [int(v) for v in out[3:]]
-    assert sizes == [ctypes.sizeof(L.ConvGeom), ctypes.sizeof(L.Operand), ctypes.sizeof(L.GemmParams)]
+    sizes, offs = [int(v) for v in out[:4]], [int(v) for v in out[4:]]
+    assert sizes == [ctypes.sizeof(L.ConvGeom), ctypes.sizeof(L.Operand), ctypes.sizeof(L.GemmParams), ctypes.sizeof(L.GemmPlan)]
     assert offs == [getattr(L.GemmParams, f).offset for f in fields]
 
 
@@ -63,37 +69,48 @@ def test_wt_job_layout(tmp_path):
 
 
 
-def test_gemm_plan_query_and_optional_tile_widths():
-    """Host-only: the (tile width, split-K, tile count) the tensor-core GEMM would use.  Default widths are powers of
-    two; vlfb_set_tile_widths(1) adds 96/160/192/224 so that the 49-row-tile layers of res4/res5 fill 148 SMs."""
+def test_gemm_plan_query():
+    """Host-only: the tiling / schedule the tensor-core GEMM would use (vlfb_gemm_plan).  The res4/res5 layers of a
+    2-clip batch have M = 6272 = 49 row tiles of 128: with 128 x 256 tiles they fill 98 of 148 SMs (round 1).  CTA
+    pairs (cta_group::2, 256-row tiles) halve the operand bytes per SM and stream-K gives every pair the same number
+    of K chunks whatever the tile count."""
     import ctypes as C
     from vlfb import libvlfb as L
     lib = L.load()
-    before = lib.vlfb_get_tile_widths()
+    ws_bytes = lib.vlfb_gemm_workspace_bytes()
+    assert ws_bytes >= 16384 * 4 + 148 * 2 * 128 * 256 * 4
 
-    def plan(M, N, K, extra, split=1, taps=1):
-        lib.vlfb_set_tile_widths(extra)
+    def plan(M, N, K, split=1, taps=1, flags=0, ws=True, **opts):
         p = L.GemmParams()
-        p.M, p.N, p.K, p.batch, p.taps, p.split_k = M, N, K, 1, taps, split
-        bn, sp, t = C.c_int(), C.c_int(), C.c_int()
-        assert lib.vlfb_gemm_plan(C.byref(p), 148, C.byref(bn), C.byref(sp), C.byref(t)) == 0
-        return bn.value, sp.value, t.value
+        p.M, p.N, p.K, p.batch, p.taps, p.split_k, p.flags = M, N, K, 1, taps, split, flags
+        if ws:
+            p.workspace, p.workspace_bytes = 4096, ws_bytes      # host-only query: the pointer is never dereferenced
+        for k, v in opts.items():
+            setattr(p, k, v)
+        out = L.GemmPlan()
+        assert lib.vlfb_gemm_plan(C.byref(p), 148, C.byref(out)) == 0
+        return out
 
-    try:
-        assert plan(6272, 512, 4608, 0) == (256, 1, 98)          # res5 3x3: 98 of 148 SMs
-        assert plan(6272, 512, 4608, 1) == (192, 1, 147)         # one full round
-        assert plan(6272, 256, 3072, 0) == (128, 1, 98) and plan(6272, 256, 3072, 1) == (96, 1, 147)
-        assert plan(200704, 256, 64, 1) == plan(200704, 256, 64, 0)      # large-M layers keep 256
-        for M, N, K in [(4, 80, 2560), (3136, 784, 256), (512, 4608, 6272), (64, 224, 802816), (1, 300, 512)]:
-            for extra in (0, 1):
-                bn, sp, tiles = plan(M, N, K, extra, split=0)
-                assert bn % 32 == 0 and 32 <= bn <= 256 and sp >= 1
-                assert extra or bn & (bn - 1) == 0
-                assert bn == 32 or N > bn // 2                   # never pad N by 2x or more
-                assert tiles == -(-M // 128) * -(-N // bn) * sp
-        assert lib.vlfb_gemm_plan(None, 148, None, None, None) == -1
-    finally:
-        lib.vlfb_set_tile_widths(before)
+    r5 = plan(6272, 512, 4608)                                   # res5 branch2b
+    assert (r5.tile_n, r5.pair, r5.stream_k, r5.units, r5.tiles) == (256, 1, 1, 74, 50)
+    r4 = plan(6272, 256, 2304)                                   # res4 branch2b: 25 pair tiles over 74 pairs
+    assert (r4.tile_n, r4.pair, r4.stream_k, r4.units) == (256, 1, 1, 74)
+    nows = plan(6272, 512, 4608, ws=False)                       # no workspace -> no fix-up schedule
+    assert nows.stream_k == 0 and nows.pair == 1
+    off = plan(6272, 512, 4608, pair=-1, stream_k=-1)            # round-1 behaviour on request
+    assert (off.tile_n, off.pair, off.stream_k, off.tiles, off.units) == (256, 0, 0, 98, 98)
+    big = plan(200704, 256, 64)                                  # res2 1x1: thousands of tiles, static loop
+    assert big.stream_k == 0 and big.tile_n == 256
+    forced = plan(6272, 512, 4608, tile_n=192, pair=-1, stream_k=-1)
+    assert (forced.tile_n, forced.tiles) == (192, 147)
+    for M, N, K in [(4, 80, 2560), (3136, 784, 256), (512, 4608, 6272), (64, 224, 802816), (1, 300, 512)]:
+        o = plan(M, N, K, split=0, flags=L.EPI_ATOMIC)
+        assert o.tile_n % 32 == 0 and 32 <= o.tile_n <= 256 and o.split_k >= 1
+        assert o.tile_n & (o.tile_n - 1) == 0
+        assert o.tile_n == 32 or N > o.tile_n // 2               # never pad N by 2x or more
+        assert o.tiles == -(-M // (256 if o.pair else 128)) * -(-N // o.tile_n) * o.split_k
+        assert not (o.stream_k and o.split_k != 1)
+    assert lib.vlfb_gemm_plan(None, 148, None) == -1
 
 
 def test_fbo_bank_scan_split_table_properties():

@@ -556,51 +556,121 @@ def test_lfb_gather_is_bit_exact(K, rows, n, D):
     assert torch.equal(out.cpu(), tf32_round(ref))
 
 
-# -------------------------------------------------------------------------- optional tile widths (96/160/192/224)
-def test_extra_tile_widths_give_the_same_results(K):
-    """vlfb_set_tile_widths(1): the res4/res5-shaped GEMMs switch to 96- / 192-column tiles (147 tiles = one round on
-    148 SMs).  Without split-K the K reduction order per output element is unchanged, so results must be bit-identical
-    to the power-of-two tiling; fp64 reference for one case."""
-    from vlfb import libvlfb as L
-    lib = L.load()
-    before = lib.vlfb_get_tile_widths()
+# -------------------------------------------------------------------------- tiling / schedule variants
+# vlfb_gemm_params_t.{tile_n, pair, stream_k}: 256-row tiles on CTA pairs (tcgen05 cta_group::2), stream-K chunk
+# ranges with the workspace fix-up, forced tile widths.  Every variant must reproduce the fp64 reference at the
+# production shapes of res4 / res5 / the non-local blocks (M = 6272 = 2 clips x 16 x 14 x 14).
+VARIANTS = [dict(pair=-1, stream_k=-1), dict(pair=1, stream_k=-1), dict(pair=-1, stream_k=1), dict(pair=1, stream_k=1),
+            dict(pair=-1, stream_k=-1, tile_n=192), dict(pair=1, stream_k=1, tile_n=128), dict()]
+
+
+def _with_opts(K, opts):
+    K.GEMM_OPTS.update(dict(tile_n=0, pair=0, stream_k=0))
+    K.GEMM_OPTS.update(opts)
+
+
+def _conv_ref_gpu(x_cl, w_cl, st, pd, dil):
+    """fp64 reference on the GPU (cuDNN / native double convolution: independent of libvlfb)."""
+    x = x_cl.permute(0, 4, 1, 2, 3).double()
+    w = w_cl.permute(0, 4, 1, 2, 3).double()
+    return F.conv3d(x, w, None, st, pd, dil).permute(0, 2, 3, 4, 1).contiguous()
+
+
+PROD_CONVS = [
+    # Ci, Co, kernel, pads, dilation, residual        (N, T, H, W) = (2, 16, 14, 14): M = 6272
+    (512, 512, (1, 3, 3), (0, 2, 2), (1, 2, 2), False),      # res5 branch2b   K = 4608
+    (2048, 512, (3, 1, 1), (1, 0, 0), (1, 1, 1), False),     # res5 branch2a   K = 6144
+    (256, 256, (1, 3, 3), (0, 1, 1), (1, 1, 1), False),      # res4 branch2b   K = 2304
+    (1024, 256, (3, 1, 1), (1, 0, 0), (1, 1, 1), False),     # res4 branch2a   K = 3072
+    (256, 1024, (1, 1, 1), (0, 0, 0), (1, 1, 1), True),      # res4 branch2c + residual + ReLU
+    (512, 2048, (1, 1, 1), (0, 0, 0), (1, 1, 1), True),      # res5 branch2c
+]
+
+
+@pytest.mark.parametrize('case', range(len(PROD_CONVS)))
+def test_production_conv_shapes_all_tiling_variants(K, case):
     K.set_gemm_backend('tcgen05')
-
-    def conv_case(Ci, Co, ker, pd, dil=(1, 1, 1), residual=False, seed=0):
-        g = K.conv_geom((2, 16, 14, 14, Ci), Co, ker, (1, 1, 1), pd, dil)
-        x, w = rnd((2, 16, 14, 14, Ci), seed).cuda(), (rnd((Co,) + tuple(ker) + (Ci,), seed + 1) * 0.05).cuda()
-        s, b = (torch.rand(Co) + 0.5).cuda(), torch.randn(Co).cuda()
-        res = torch.randn(K.out_shape(g)).cuda() if residual else None
-        return g, x, w, s, b, res
-
-    cases = [conv_case(512, 512, (1, 3, 3), (0, 2, 2), (1, 2, 2)),            # res5 branch2b: 256 -> 192
-             conv_case(1024, 256, (3, 1, 1), (1, 0, 0), seed=3),              # res4 branch2a: 128 -> 96
-             conv_case(256, 1024, (1, 1, 1), (0, 0, 0), residual=True, seed=5),  # res4 branch2c (+residual): 256 -> 192
-             conv_case(256, 224, (1, 3, 3), (0, 1, 1), seed=7)]               # N = 224: one 224-column tile
+    Ci, Co, ker, pd, dil, use_res = PROD_CONVS[case]
+    g = K.conv_geom((2, 16, 14, 14, Ci), Co, ker, (1, 1, 1), pd, dil)
+    x = rnd((2, 16, 14, 14, Ci), 40 + case).cuda()
+    w = rnd((Co,) + tuple(ker) + (Ci,), 50 + case, 0.05).cuda()
+    s, b = (torch.rand(Co) + 0.5).cuda(), torch.randn(Co).cuda()
+    res = rnd(K.out_shape(g), 60 + case).cuda() if use_res else None
+    dy = rnd(K.out_shape(g), 70 + case).cuda()
+    y_ref = _conv_ref_gpu(x, w, (1, 1, 1), pd, dil)
+    out_ref = y_ref * s.double() + b.double()
+    if use_res:
+        out_ref = out_ref + res.double()
+    out_ref = torch.relu(out_ref)
+    taps = ker[0] * ker[1] * ker[2]
+    wt = torch.empty((Ci, taps, Co), device='cuda')
+    K.weight_transpose(w, wt)
+    # dgrad reference: conv_transpose == autograd of the fp64 conv
+    xd = x.permute(0, 4, 1, 2, 3).double().requires_grad_(True)
+    wd = w.permute(0, 4, 1, 2, 3).double().requires_grad_(True)
+    yy = F.conv3d(xd, wd, None, (1, 1, 1), pd, dil)
+    yy.backward(dy.permute(0, 4, 1, 2, 3).double())
+    dx_ref = xd.grad.permute(0, 2, 3, 4, 1)
+    dw_ref = wd.grad.permute(0, 2, 3, 4, 1) * s.double().view(-1, 1, 1, 1, 1)
     try:
-        outs = {}
-        for extra in (0, 1):
-            lib.vlfb_set_tile_widths(extra)
-            for i, (g, x, w, s, b, res) in enumerate(cases):
-                y = torch.full(K.out_shape(g), float('nan'), device='cuda')
-                K.conv_fwd(x, w, y, g, scale=s, bias=b, residual=res, relu=True, tf32_out=True)
-                taps = g.kT * g.kH * g.kW
-                wt = torch.empty((g.C, taps, g.Co), device='cuda')
-                K.weight_transpose(w, wt, s)
-                dx = torch.full((2, 16, 14, 14, g.C), float('nan'), device='cuda')
-                K.conv_dgrad(y, wt, dx, g, tf32_out=True)
-                a = rnd((2, 392, 256), 20 + i).cuda()
-                bm = rnd((2, 256, 784 if i % 2 == 0 else 520), 30 + i).cuda()
-                d = torch.full((2, 392, bm.shape[2]), float('nan'), device='cuda')
-                K.matmul(a, bm, d, tf32_out=True)
-                torch.cuda.synchronize()
-                outs[(extra, i)] = (y.cpu(), dx.cpu(), d.cpu())
-        for i in range(len(cases)):
-            for u, v in zip(outs[(0, i)], outs[(1, i)]):
-                assert torch.isfinite(v).all() and torch.equal(u, v), i
-        g, x, w, s, b, res = cases[0]
-        ref = F.conv3d(to_nc(x.cpu()).double(), w.cpu().permute(0, 4, 1, 2, 3).double(), None, (1, 1, 1), (0, 2, 2), (1, 2, 2))
-        ref = torch.relu(ref * s.cpu().double().view(1, -1, 1, 1, 1) + b.cpu().double().view(1, -1, 1, 1, 1))
-        assert rel_err(to_nc(outs[(1, 0)][0]), ref) < 1e-3            # output itself is TF32-rounded (tf32_out)
+        for opts in VARIANTS:
+            _with_opts(K, opts)
+            y = torch.full(K.out_shape(g), float('nan'), device='cuda')
+            K.conv_fwd(x, w, y, g, scale=s, bias=b, residual=res, relu=True)
+            dx = torch.full((2, 16, 14, 14, Ci), float('nan'), device='cuda')
+            K.conv_dgrad(dy, wt, dx, g)
+            dw = torch.zeros((Co,) + tuple(ker) + (Ci,), device='cuda')
+            K.conv_wgrad(dy, x, dw, g, row_scale=s)
+            torch.cuda.synchronize()
+            assert rel_err(y, out_ref) < 2e-5, ('fwd', opts)
+            assert rel_err(dx, dx_ref) < 2e-5, ('dgrad', opts)
+            assert rel_err(dw, dw_ref) < 2e-5, ('wgrad', opts)
+            # the counters of the stream-K workspace are zero again after every launch
+            assert int(K.gemm_workspace(x.device)[:16384].view(torch.int32).abs().sum()) == 0, opts
     finally:
-        lib.vlfb_set_tile_widths(before)
+        _with_opts(K, {})
+
+
+@pytest.mark.parametrize('B,M,N,K_,ta,tb', [(2, 3136, 784, 512, 1, 0),      # NL4 affinity theta^T phi (MN-major A)
+                                            (2, 512, 3136, 784, 0, 1),      # NL4 y = g p^T
+                                            (8, 3136, 784, 256, 1, 0),      # NL3 (grouped) affinity
+                                            (1, 6272, 1024, 512, 0, 1),     # NL4 out projection as a matmul
+                                            (1, 300, 520, 2048, 0, 1)])     # ragged M / N
+def test_production_matmul_shapes_all_tiling_variants(K, B, M, N, K_, ta, tb):
+    K.set_gemm_backend('tcgen05')
+    a = rnd((B, K_, M) if ta else (B, M, K_), 81).cuda()
+    b = rnd((B, N, K_) if tb else (B, K_, N), 82).cuda()
+    A = a.transpose(1, 2) if ta else a
+    Bm = b.transpose(1, 2) if tb else b
+    bias = torch.randn(N).cuda()
+    ref = torch.bmm(A.double(), Bm.double()) + bias.double()
+    try:
+        for opts in VARIANTS:
+            _with_opts(K, opts)
+            d = torch.full((B, M, N), float('nan'), device='cuda')
+            K.matmul(A, Bm, d, bias=bias)
+            torch.cuda.synchronize()
+            assert rel_err(d, ref) < 2e-5, opts
+            K.matmul(A, Bm, d, accumulate=True)
+            torch.cuda.synchronize()
+            assert rel_err(d, 2 * ref - bias.double()) < 2e-5, opts
+    finally:
+        _with_opts(K, {})
+
+
+def test_stream_k_results_are_deterministic(K):
+    """The fix-up sums the pieces of a shared tile in piece order, whoever arrives last: two runs are bit-identical."""
+    K.set_gemm_backend('tcgen05')
+    g = K.conv_geom((2, 16, 14, 14, 512), 512, (1, 3, 3), (1, 1, 1), (0, 2, 2), (1, 2, 2))
+    x, w = rnd((2, 16, 14, 14, 512), 91).cuda(), rnd((512, 1, 3, 3, 512), 92, 0.05).cuda()
+    try:
+        _with_opts(K, dict(pair=1, stream_k=1))
+        outs = []
+        for _ in range(3):
+            y = torch.empty(K.out_shape(g), device='cuda')
+            K.conv_fwd(x, w, y, g, relu=True, tf32_out=True)
+            torch.cuda.synchronize()
+            outs.append(y.clone())
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    finally:
+        _with_opts(K, {})

@@ -8,25 +8,6 @@
 namespace vlfb {
 
 static thread_local char g_err[512] = "";
-static int g_backend = 0;
-static int g_pdl = -1;          // -1: read VLFB_PDL on first use
-static int g_extra_bn = -1;     // -1: read VLFB_BN_EXTRA on first use
-bool extra_tile_widths() {
-  if (g_extra_bn < 0) {
-    const char* e = getenv("VLFB_BN_EXTRA");
-    g_extra_bn = (e && atoi(e) != 0) ? 1 : 0;
-  }
-  return g_extra_bn != 0;
-}
-void set_extra_tile_widths(int on) { g_extra_bn = on ? 1 : 0; }
-bool pdl_enabled() {
-  if (g_pdl < 0) {
-    const char* e = getenv("VLFB_PDL");
-    g_pdl = (e && atoi(e) != 0) ? 1 : 0;      // default off: measured no gain inside the captured step (r01_perf_log)
-  }
-  return g_pdl != 0;
-}
-
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -44,6 +25,8 @@ static int validate_gemm(const vlfb_gemm_params_t& p, bool& tc_ok) {
   VLFB_CHECK_ARG(p.M > 0 && p.N > 0 && p.K >= 0);
   VLFB_CHECK_ARG(p.batch >= 1 && p.taps >= 1 && p.split_k >= 0);          // split_k 0 = chosen by the library
   VLFB_CHECK_ARG(!(p.taps > 1 && p.batch > 1));
+  VLFB_CHECK_ARG(p.engine == VLFB_ENGINE_TCGEN05 || p.engine == VLFB_ENGINE_SIMT);
+  VLFB_CHECK_ARG(p.tile_n == 0 || (p.tile_n >= 32 && p.tile_n <= 256 && p.tile_n % 32 == 0));
   VLFB_CHECK_ARG(p.split_k == 1 || (p.flags & VLFB_EPI_ATOMIC));
   VLFB_CHECK_ARG(!(p.split_k != 1 && (p.residual || p.relu_mask || (p.flags & (VLFB_EPI_RELU | VLFB_EPI_TF32)))));
   if (!(aligned16(p.a.ptr) && aligned16(p.b.ptr))) tc_ok = false;
@@ -106,29 +89,13 @@ extern "C" {
 
 int vlfb_version(void) { return 100; }
 const char* vlfb_last_error(void) { return g_err; }
-int vlfb_set_gemm_backend(int backend) {
-  VLFB_CHECK_ARG(backend == 0 || backend == 1);
-  g_backend = backend;
-  return VLFB_OK;
-}
-int vlfb_get_gemm_backend(void) { return g_backend; }
-int vlfb_gemm_plan(const vlfb_gemm_params_t* p, int num_sms, int* bn, int* split_k, int* tiles) {
-  VLFB_CHECK_ARG(p && bn && split_k && tiles && p->M > 0 && p->N > 0 && p->K > 0);
-  gemm_tc_plan(*p, num_sms > 0 ? num_sms : 148, bn, split_k, tiles);
+int vlfb_gemm_plan(const vlfb_gemm_params_t* p, int num_sms, vlfb_gemm_plan_t* plan) {
+  VLFB_CHECK_ARG(p && plan && p->M > 0 && p->N > 0 && p->K > 0);
+  gemm_tc_plan(*p, num_sms > 0 ? num_sms : 148, plan);
   return VLFB_OK;
 }
 
-int vlfb_get_tile_widths(void) { return extra_tile_widths() ? 1 : 0; }
-
-int vlfb_set_tile_widths(int extra) {
-  set_extra_tile_widths(extra);
-  return VLFB_OK;
-}
-
-int vlfb_set_pdl(int enabled) {
-  g_pdl = enabled ? 1 : 0;
-  return VLFB_OK;
-}
+size_t vlfb_gemm_workspace_bytes(void) { return gemm_tc_workspace_bytes(); }
 
 int vlfb_gemm(const vlfb_gemm_params_t* p, void* stream) {
   VLFB_CHECK_ARG(p != nullptr);
@@ -136,7 +103,7 @@ int vlfb_gemm(const vlfb_gemm_params_t* p, void* stream) {
   int rc = validate_gemm(*p, tc_ok);
   if (rc != VLFB_OK) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return (g_backend == 1 || !tc_ok) ? gemm_simt(*p, s) : gemm_tc(*p, s);
+  return (p->engine == VLFB_ENGINE_SIMT || !tc_ok) ? gemm_simt(*p, s) : gemm_tc(*p, s);
 }
 
 }  // extern "C"

@@ -29,26 +29,6 @@ void set_error(const char* fmt, ...);
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
-// A training step is ~650 dependent kernels of 5-200 us each, so launch latency and every kernel's prologue
-// (barrier init, TMEM allocation, tensor-map fetch) are a measurable share of the step.  All kernels of this
-// library are launched with cudaLaunchAttributeProgrammaticStreamSerialization and start with pdl_prologue():
-// `griddepcontrol.wait` blocks until the previous grid in the stream has completed and its memory is visible,
-// `griddepcontrol.launch_dependents` then lets the NEXT kernel's CTAs be scheduled as soon as SMs free up, so its
-// launch + prologue overlap this kernel's tail.  Nothing before pdl_prologue() may touch global memory.
-// The edges survive CUDA-graph capture.  OFF by default (VLFB_PDL=1 / vlfb_set_pdl(1) enables): measured on the
-// captured training step it changes nothing (18.04 vs 17.97 ms; 18.2 with the early trigger) -- the step is bound
-// by kernel execution, not by launch gaps.  Without the attribute the instructions are no-ops.
-bool pdl_enabled();
-// GEMM tile widths beyond the power-of-two set (96/160/192/224 columns): see gemm_tc.cu launch()
-bool extra_tile_widths();
-void set_extra_tile_widths(int on);
-__device__ __forceinline__ void pdl_prologue() {
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-#ifndef VLFB_PDL_NO_TRIGGER
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
-}
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                    Args&&... args) {
@@ -57,11 +37,6 @@ static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 blo
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -172,6 +147,7 @@ __device__ __forceinline__ void epilogue_store(const vlfb_gemm_params_t& p, int 
 
 int gemm_simt(const vlfb_gemm_params_t& p, cudaStream_t stream);
 int gemm_tc(const vlfb_gemm_params_t& p, cudaStream_t stream);
-void gemm_tc_plan(const vlfb_gemm_params_t& p, int num_sms, int* bn, int* split_k, int* tiles);
+void gemm_tc_plan(const vlfb_gemm_params_t& p, int num_sms, vlfb_gemm_plan_t* out);
+size_t gemm_tc_workspace_bytes();
 
 }  // namespace vlfb

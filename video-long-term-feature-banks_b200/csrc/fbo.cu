@@ -44,7 +44,6 @@ template <int V4, int ROWS>
 __global__ void __launch_bounds__(SCAN_TPB, 2)
 fbo_bank_scan_k(const float* __restrict__ bank, const float* __restrict__ q, float scale, float* __restrict__ part_acc,
                 float* __restrict__ part_ml, float* __restrict__ scores, int L, int S, int rows_per_split) {
-  pdl_prologue();
   constexpr int D = 1024 * V4;
   constexpr int NW = SCAN_TPB / 32;
   __shared__ float xch[2][NW][ROWS];
@@ -132,7 +131,6 @@ fbo_bank_scan_k(const float* __restrict__ bank, const float* __restrict__ q, flo
 __global__ void fbo_bank_combine_k(const float* __restrict__ part_acc, const float* __restrict__ part_ml,
                                    float* __restrict__ out, float* __restrict__ scores_prob, int S, int D, int L,
                                    int tf32_out) {
-  pdl_prologue();
   const int r = blockIdx.y;
   float M = -FLT_MAX;
   for (int s = 0; s < S; ++s)
@@ -162,7 +160,6 @@ __global__ void fbo_bank_combine_k(const float* __restrict__ part_acc, const flo
 // out[i][:] = idx[i] >= 0 ? bank[idx[i]][:] : 0   (rows of D floats, D % 4 == 0); one warp-wide float4 lane per 16 B.
 __global__ void lfb_gather_k(const float4* __restrict__ bank, const int32_t* __restrict__ idx, float4* __restrict__ out,
                              int64_t rows, int d4, int64_t bank_rows, int tf32_out) {
-  pdl_prologue();
   const int64_t total = rows * d4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / d4;

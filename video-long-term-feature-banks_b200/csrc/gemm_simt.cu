@@ -10,7 +10,6 @@ namespace {
 constexpr int TM = 32, TN = 32, TK = 16;
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const vlfb_gemm_params_t p) {
-  pdl_prologue();
   __shared__ float sa[TK][TM + 1];
   __shared__ float sb[TK][TN + 1];
   const int z = blockIdx.z;

@@ -25,6 +25,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace vlfb {
@@ -42,7 +44,6 @@ constexpr int RSTEP = NPROD / 8;   // rows covered by one pass of the K-major lo
 constexpr int NEPI = 256;          // 8 epilogue warps (two per TMEM lane quarter, splitting the column blocks)
 constexpr int EPC = 16;            // accumulator columns per epilogue step (tcgen05.ld.32x32b.x16)
 constexpr int EPITCH = EPC + 4;    // padded staging row (floats)
-constexpr int NTHREADS = NPROD + 32 + NEPI;  // producers + MMA warp + epilogue
 constexpr int EPI_COLV = 2 * 128;     // per-warp column scale + bias of its 128 columns (floats)
 constexpr int EPI_WARP_FLOATS = 32 * EPITCH + EPI_COLV;
 constexpr int EPI_STAGE_BYTES = (NEPI / 32) * EPI_WARP_FLOATS * 4;
@@ -146,6 +147,62 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants.  Protocol: both CTAs of a (2,1,1) cluster allocate TMEM and
+// stage their half of the operands; the barriers that order the pipeline live at the SAME shared-memory offsets in
+// both CTAs; the leader (cluster rank 0) issues the MMAs and publishes their completion to both CTAs with a
+// multicast commit; the peer's TMA loads and epilogue warps signal the LEADER's barriers (mapa address).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all prior MMAs of the pair -> one arrival on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit2(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+// TMA loads issued by either CTA of the pair; the transaction bytes land on `bar`, which may be the peer's barrier
+__device__ __forceinline__ void tma_load_3d_2(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ float4 ld_cg_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
@@ -189,7 +246,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): tf32 x tf32 -> f32, M=128, N=bn.
-__host__ __device__ inline uint32_t make_idesc(int bn, int a_mn_major, int b_mn_major) {
+__host__ __device__ inline uint32_t make_idesc(int bn, int a_mn_major, int b_mn_major, int m = BM) {
   uint32_t d = 0;
   d |= 1u << 4;                          // c_format  = F32
   d |= 2u << 7;                          // a_format  = TF32
@@ -197,7 +254,7 @@ __host__ __device__ inline uint32_t make_idesc(int bn, int a_mn_major, int b_mn_
   d |= (uint32_t)(a_mn_major & 1) << 15; // a_major
   d |= (uint32_t)(b_mn_major & 1) << 16; // b_major
   d |= (uint32_t)(bn >> 3) << 17;        // n_dim
-  d |= (uint32_t)(BM >> 4) << 24;        // m_dim
+  d |= (uint32_t)(m >> 4) << 24;         // m_dim (128, or 256 = a CTA pair with cta_group::2)
   return d;
 }
 
@@ -241,6 +298,16 @@ __device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap*
                                                 int ow, int oh, int od, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.5d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4, %5, %6}], [%7], {%8, %9, %10};"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "r"(bar),
+        "h"((uint16_t)ow), "h"((uint16_t)oh), "h"((uint16_t)od)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_im2col_2(uint32_t dst, const CUtensorMap* tm, int c, int w, int h, int d, int n,
+                                                  int ow, int oh, int od, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
       "[%0], [%1, {%2, %3, %4, %5, %6}], [%7], {%8, %9, %10};"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "r"(bar),
         "h"((uint16_t)ow), "h"((uint16_t)oh), "h"((uint16_t)od)
@@ -486,6 +553,9 @@ struct MNLoader {
 };
 
 // ---------------------------------------------------------------- the kernel
+constexpr int MAX_UNITS = 160;       // >= #SMs: CTAs (or CTA pairs) of the persistent grid
+constexpr int SK_CNT_INTS = 16384;   // arrival counters at the head of the stream-K workspace (tile x rank x epilogue warp)
+
 struct Launch {
   int bn;        // tile N (32/64/128/256) = UMMA N = TMEM columns
   int stages;
@@ -493,49 +563,113 @@ struct Launch {
   PosDiv in;     // ... and of the INPUT extents (W, H, T) for the dgrad row decode
   FastDiv cdiv;  // input channels C (wgrad: n -> (tap, ci))
   FastDiv kwdiv; // kW
-  int tma_a, tma_b;  // operand fetched by TMA instead of cp.async: 1 = dense tiled boxes, 2 = im2col (conv gathers),
-                     // 3 = conv1 stem im2col (16-byte pixels, no-swizzle K-major tile [kw][row][16 B])
-  int stem_lbo, stem_sbo;  // UMMA descriptor strides of that tile (bytes)
+  int tma_a, tma_b;  // operand fetched by TMA instead of cp.async: 1 = dense tiled boxes, 2 = im2col (conv gathers)
   int lag;           // cp.async groups kept in flight before a stage is published (< stages)
   int tiles_m, tiles_n, total_tiles;
   int fence_mode;    // 0: producers fence.proxy.async before publishing a stage; 1: the MMA thread fences after acquiring it
+  int tile_rows;     // output rows per tile: 128, or 256 when a CTA pair shares the tile (cta_group::2)
+  // Stream-K: the linear space (tile, K chunk) is cut into one contiguous range per unit (CTA or CTA pair), so every
+  // SM gets the same number of chunks whatever the tile count.  A tile whose chunks span several units is reduced
+  // through the workspace by the LAST unit to arrive at its counter (no unit ever waits for another).
+  int sk;
+  int nkt;           // K chunks per tile
+  float* ws_tiles;   // partial-sum slots: [unit][2][rank][128][bn]
+  int* ws_cnt;       // arrival counters [tile][rank][epilogue warp], zero between launches
+  int bounds[MAX_UNITS + 1];
 };
 
-struct TileInfo { int m0, n0, batch, tap, k_begin, k_end, nk; };
+struct TileInfo {
+  int m0, n0, batch, tap, k_begin, k_end, nk;
+  int tile;          // linear tile index
+  // stream-K: units sharing this tile, packed to keep the epilogue's register budget:
+  //   bits 0-7 npieces (1 = whole tile here), 8-15 first unit, 16 = workspace slot (0/1) of that first unit's piece
+  //   (every later piece is in slot 0), 17 = this unit's slot
+  int pinfo;
+  __device__ __forceinline__ int npieces() const { return pinfo & 0xFF; }
+  __device__ __forceinline__ int ufirst() const { return (pinfo >> 8) & 0xFF; }
+  __device__ __forceinline__ int first_slot() const { return (pinfo >> 16) & 1; }
+  __device__ __forceinline__ int slot() const { return (pinfo >> 17) & 1; }
+};
 
 // Linear tile index -> (m tile fastest, n tile, z = batch|tap x split): CTAs that run concurrently share the
 // same weight (B) tile in L2.
-__device__ __forceinline__ TileInfo decode_tile(const vlfb_gemm_params_t& p, const Launch& L, int t) {
-  TileInfo ti;
+__device__ __forceinline__ void decode_tile(const vlfb_gemm_params_t& p, const Launch& L, int t, int rank, int split_k,
+                                            TileInfo& ti) {
   const int mt = t % L.tiles_m;
   const int r = t / L.tiles_m;
   const int nt = r % L.tiles_n;
   const int z = r / L.tiles_n;
-  const int split = z % p.split_k, zz = z / p.split_k;
+  const int split = z % split_k, zz = z / split_k;
   ti.batch = (p.taps > 1) ? 0 : zz;
   ti.tap = (p.taps > 1) ? zz : 0;
-  ti.m0 = mt * BM;
+  ti.m0 = mt * L.tile_rows + rank * BM;
   ti.n0 = nt * L.bn;
-  int kper = (p.K + p.split_k - 1) / p.split_k;
+  int kper = (p.K + split_k - 1) / split_k;
   kper = (kper + KC - 1) / KC * KC;
   ti.k_begin = split * kper;
   ti.k_end = min(p.K, ti.k_begin + kper);
   ti.nk = (ti.k_end > ti.k_begin) ? (ti.k_end - ti.k_begin + KC - 1) / KC : 0;
-  return ti;
+  ti.tile = t;
+  ti.pinfo = 1;
 }
 
-// Persistent, warp-specialised: grid = min(#tiles, #SMs); every role walks the same static tile sequence
-// (t = blockIdx.x, += gridDim.x).  The smem ring (full/empty) runs continuously across tiles and the TMEM
-// accumulator is double-buffered (tmem_full/tmem_empty), so the epilogue of tile i overlaps the loads and
-// MMAs of tile i+1.
-template <int AK, int BK, bool MASK>
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_params_t p, const Launch L,
+// Every role of a CTA (and both CTAs of a pair) walks the same work sequence.  cur/lim = next tile index / tile
+// count (static loop, stride = #units) or next / end position in the (tile, K chunk) space (stream-K).
+struct Sched { int cur, lim; };
+__device__ __forceinline__ void sched_init(Sched& s, const Launch& L, int unit) {
+  s.cur = L.sk ? L.bounds[unit] : unit;
+  s.lim = L.sk ? L.bounds[unit + 1] : L.total_tiles;
+}
+__device__ __forceinline__ bool sched_next(const vlfb_gemm_params_t& p, const Launch& L, Sched& s, int unit, int nunits,
+                                           int rank, TileInfo& ti) {
+  if (L.sk) {
+    if (s.cur >= s.lim) return false;
+    const int tile = s.cur / L.nkt;
+    const int c0 = s.cur - tile * L.nkt;
+    const int len = min(L.nkt - c0, s.lim - s.cur);
+    decode_tile(p, L, tile, rank, 1, ti);
+    ti.k_begin = c0 * KC;
+    ti.k_end = min(p.K, (c0 + len) * KC);
+    ti.nk = len;
+    if (len != L.nkt && L.ws_tiles != nullptr) {
+      const int s0 = tile * L.nkt, e0 = s0 + L.nkt;
+      int uf = unit, ul = unit;
+      while (L.bounds[uf] > s0) --uf;
+      while (L.bounds[ul + 1] < e0) ++ul;
+      const int first_slot = (L.bounds[uf] < s0) ? 1 : 0;
+      const int slot = (unit == uf) ? first_slot : 0;
+      ti.pinfo = (ul - uf + 1) | (uf << 8) | (first_slot << 16) | (slot << 17);
+    }
+    s.cur += len;
+    return true;
+  }
+  while (s.cur < s.lim) {
+    decode_tile(p, L, s.cur, rank, p.split_k, ti);
+    s.cur += nunits;
+    if (ti.nk != 0) return true;
+  }
+  return false;
+}
+
+// Persistent, warp-specialised: grid = min(#tiles, #SMs) CTAs (PAIR: 2 x #pairs in clusters of two); every role walks
+// the same work sequence (Sched).  The smem ring (full/empty) runs continuously across tiles and the TMEM accumulator
+// is double-buffered (tmem_full/tmem_empty), so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
+// PAIR (both operands staged by TMA only): the two CTAs of a cluster own one 256 x bn tile; CTA r stages A rows
+// [m0 + 128 r, +128) and B rows [n0 + (bn/2) r, +bn/2); the leader issues tcgen05.mma.cta_group::2 (M = 256) which
+// reads both CTAs' shared memory and writes 128 accumulator lanes x bn columns into EACH CTA's TMEM, so every SM
+// receives (128 + bn/2) x 128 B per K chunk instead of (128 + bn) x 128 B for the same MACs.
+// CP = false: both operands are staged by TMA, so ONE producer warp suffices and the CTA is 10 warps (producer, MMA
+// issuer, 8 epilogue warps) with up to 168 registers per thread -- the 17-warp CP = true build (8 cp.async gather
+// warps: conv1 stem, strided dgrad, operands TMA cannot address) is capped at 96 and spills in the epilogue.
+template <int AK, int BK, bool MASK, bool PAIR, bool CP>
+__global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kernel(const vlfb_gemm_params_t p, const Launch L,
                                                               const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int bn = L.bn, S = L.stages;
-  const uint32_t b_tile_bytes = (uint32_t)bn * KC * 4;
+  const int bnh = PAIR ? (bn >> 1) : bn;                    // B rows (columns of D) staged by this CTA
+  const uint32_t b_tile_bytes = (uint32_t)bnh * KC * 4;
   const uint32_t stage_bytes = A_TILE_BYTES + b_tile_bytes;
   const uint32_t epi_base = smem_base + S * stage_bytes;                  // per-epilogue-warp transpose tiles
   const uint32_t bar_base = epi_base + EPI_STAGE_BYTES;
@@ -545,10 +679,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
   volatile uint32_t* tptr_generic =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr_addr - smem_u32(smem_raw)));
 
+  static_assert(!(PAIR && CP), "CTA pairs need both operands staged by TMA");
+  constexpr int NPRODT = CP ? NPROD : 32;        // producer threads of this build
+  constexpr int NPWT = NPRODT / 32;
+  constexpr int NTHR = NPRODT + 32 + NEPI;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int total = L.total_tiles;
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nunits = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const bool tma_a = L.tma_a != 0, tma_b = L.tma_b != 0;
-  const bool cp_any = !(tma_a && tma_b);
+  const bool cp_any = CP && !(tma_a && tma_b);
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
@@ -557,32 +697,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, NEPI);
+      mbar_init(tempty0 + 8 * a, PAIR ? 2 * (NEPI / 32) : NEPI / 32);       // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const bool stem_a = AK == VLFB_OP_STEM_K && L.tma_a == 3;
-  if (stem_a) {
-    // the 8th pixel of a conv1 filter row is padding (kW = 7): its weights are zero, its 2 KB slice of every
-    // stage is zeroed once here and never written again
-    for (int s = 0; s < S; ++s)
-      for (int i = tid; i < 2048 / 16; i += NTHREADS)
-        *reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)) + s * stage_bytes + 7 * 2048 + i * 16) =
-            make_float4(0.f, 0.f, 0.f, 0.f);
-    fence_proxy_async();
-  }
   uint32_t tmem_cols = 32;              // tcgen05.alloc takes a power of two >= 32; two accumulators of bn columns
   while (tmem_cols < (uint32_t)(2 * bn)) tmem_cols <<= 1;
-  if (warp == NPW) tmem_alloc(tptr_addr, tmem_cols);
+  if (warp == NPWT) {
+    if (PAIR) tmem_alloc2(tptr_addr, tmem_cols); else tmem_alloc(tptr_addr, tmem_cols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();     // PAIR: the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem = *tptr_generic;
-  // Everything above touched only shared memory / TMEM: it overlaps the tail of the previous kernel (PDL).
-  pdl_prologue();
 
-  if (warp < NPW) {
-    // ============================ PRODUCERS (8 warps) ============================
+  if (warp < NPWT) {
+    // ============================ PRODUCERS (8 warps; TMA: one thread) ============================
     if (cp_any || tid == 0) {
       KLoader<is_mn(AK) ? VLFB_OP_DENSE_K : AK, BM / RSTEP> ka;
       MNLoader<is_mn(AK) ? AK : VLFB_OP_DENSE_MN> ma;
@@ -597,26 +727,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
       // per 32-column atom the channel slice / tap offsets of the wgrad B tile
       int ia_w = 0, ia_h = 0, ia_d = 0, ia_n = 0, ic_t = 0, ic_h = 0, ic_w = 0, ic_c = 0, icpt = 1;
       int ib_c[NATOM], ib_off[NATOM], ib_atoms = 0;
-      // chunk counter over the CTA's whole tile sequence; ring slot / phase / lagged slot advance
+      // chunk counter over the CTA's whole work sequence; ring slot / phase / lagged slot advance
       // incrementally (S is a run-time value: `it % S` cost three integer divisions per chunk per thread)
       int it = 0, s = 0, sl = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const TileInfo ti = decode_tile(p, L, t);
-        if (ti.nk == 0) continue;
+      // PAIR: every copy of either CTA completes on the LEADER's stage barrier
+      const uint32_t fullx = PAIR ? mapa_rank(full0, 0) : full0;
+      auto ld3 = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+        if (PAIR) tma_load_3d_2(dst, tm, c0, c1, c2, bar); else tma_load_3d(dst, tm, c0, c1, c2, bar);
+      };
+      auto ldi = [&](uint32_t dst, const CUtensorMap* tm, int c, int w, int h, int d, int n, int ow, int oh, int od,
+                     uint32_t bar) {
+        if (PAIR) tma_load_im2col_2(dst, tm, c, w, h, d, n, ow, oh, od, bar);
+        else tma_load_im2col(dst, tm, c, w, h, d, n, ow, oh, od, bar);
+      };
+      Sched sc;
+      sched_init(sc, L, unit);
+      TileInfo ti;
+      while (sched_next(p, L, sc, unit, nunits, rank, ti)) {
+        const int nb0 = ti.n0 + rank * bnh;              // first D column whose B rows this CTA stages
         if (cp_any) {
           if (!tma_a) { if (is_mn(AK)) ma.init(p, p.a, ti.m0, BM, p.M, ti.batch, ti.tap, L.cdiv, L.kwdiv); else { ka.init(p, p.a, ti.m0, BM, p.M, ti.batch, L.out, L.in, ti.k_begin / KC); ka.kend = ti.k_end; } }
           if (!tma_b) { if (is_mn(BK)) mb.init(p, p.b, ti.n0, bn, p.N, ti.batch, ti.tap, L.cdiv, L.kwdiv); else { kb.init(p, p.b, ti.n0, bn, p.N, ti.batch, L.out, L.in, ti.k_begin / KC); kb.kend = ti.k_end; } }
         }
         const int kc0 = ti.k_begin / KC;
-        uint32_t tma_bytes = (tma_a ? (stem_a ? 7u * 2048u : (uint32_t)A_TILE_BYTES) : 0u) + (tma_b ? b_tile_bytes : 0u);
-        if (tid == 0 && stem_a) {
-          const vlfb_conv_geom_t& g = p.g;
-          const Pos4 o = decode_pos_fast((uint32_t)ti.m0, L.out);
-          ia_w = o.w * g.sW - g.pW; ia_h = o.h * g.sH - g.pH; ia_d = o.t * g.sT - g.pT; ia_n = o.n;
-          ic_t = kc0 / g.kH;
-          ic_h = kc0 - ic_t * g.kH;
-        }
+        // bytes the stage barrier expects: this CTA's copies (PAIR: both CTAs', posted by the leader)
+        uint32_t tma_bytes = (tma_a ? (uint32_t)A_TILE_BYTES : 0u) + (tma_b ? b_tile_bytes : 0u);
+        if (PAIR) tma_bytes *= 2u;
         if (tid == 0 && im2col_a) {
           const vlfb_conv_geom_t& g = p.g;
           if (AK == VLFB_OP_CONV_K) {
@@ -636,10 +773,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
         if (tid == 0 && im2col_b) {
           const vlfb_conv_geom_t& g = p.g;
           ib_atoms = 0;
+          int peer_atoms = 0;
 #pragma unroll
           for (int a = 0; a < NATOM; ++a) {
-            const int ncol = ti.n0 + a * 32;
-            if (a * 32 < bn && ncol < p.N) {
+            const int ncol = nb0 + a * 32;
+            if (a * 32 < bnh && ncol < p.N) {
               uint32_t tap_hw, ci, qh, qw;
               fd_divmod((uint32_t)ncol, L.cdiv, tap_hw, ci);       // n = (kh*kW + kw) * C + ci
               fd_divmod(tap_hw, L.kwdiv, qh, qw);
@@ -647,8 +785,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
               ib_off[a] = ((int)qh * g.dH << 16) | ((int)qw * g.dW);
               ib_atoms = a + 1;
             }
+            if (PAIR && a * 32 < bnh && ti.n0 + (rank ^ 1) * bnh + a * 32 < p.N) peer_atoms = a + 1;
           }
-          tma_bytes = (tma_a ? (uint32_t)A_TILE_BYTES : 0u) + 4096u * (uint32_t)ib_atoms;
+          tma_bytes = (PAIR ? 2u : 1u) * (tma_a ? (uint32_t)A_TILE_BYTES : 0u) + 4096u * (uint32_t)(ib_atoms + peer_atoms);
         }
         for (int i = 0; i < ti.nk; ++i, ++it) {
           if (it >= S) mbar_wait(empty0 + 8 * s, ph ^ 1u);
@@ -656,23 +795,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
           if (++s == S) { s = 0; ph ^= 1u; }
           const uint32_t a_tile = smem_base + s_cur * stage_bytes;
           const uint32_t b_tile = a_tile + A_TILE_BYTES;
+          const uint32_t fbar = fullx + 8 * s_cur;
           if (tid == 0 && tma_bytes) {
-            mbar_expect_tx(full0 + 8 * s_cur, tma_bytes);
-            if (stem_a) {
-              // one (kt,kh) filter row = 7 copies of 128 pixels x 16 bytes, each a [row][16 B] slab
-              const vlfb_conv_geom_t& g = p.g;
-#pragma unroll
-              for (int kw = 0; kw < 7; ++kw)
-                if (kw < g.kW) tma_load_im2col(a_tile + kw * 2048, &tmA, 0, ia_w, ia_h, ia_d, ia_n, kw, ic_h, ic_t, full0 + 8 * s_cur);
-              if (++ic_h == g.kH) { ic_h = 0; ++ic_t; }
-            } else if (im2col_a) {
+            if (!PAIR || rank == 0) mbar_expect_tx(full0 + 8 * s_cur, tma_bytes);
+            if (im2col_a) {
               const vlfb_conv_geom_t& g = p.g;
               if (AK == VLFB_OP_CONV_K)
-                tma_load_im2col(a_tile, &tmA, ic_c * KC, ia_w, ia_h, ia_d, ia_n, ic_w * g.dW, ic_h * g.dH, ic_t * g.dT,
-                                full0 + 8 * s_cur);
+                ldi(a_tile, &tmA, ic_c * KC, ia_w, ia_h, ia_d, ia_n, ic_w * g.dW, ic_h * g.dH, ic_t * g.dT, fbar);
               else
-                tma_load_im2col(a_tile, &tmA, ic_c * KC, ia_w, ia_h, ia_d, ia_n, (g.kW - 1 - ic_w) * g.dW,
-                                (g.kH - 1 - ic_h) * g.dH, (g.kT - 1 - ic_t) * g.dT, full0 + 8 * s_cur);
+                ldi(a_tile, &tmA, ic_c * KC, ia_w, ia_h, ia_d, ia_n, (g.kW - 1 - ic_w) * g.dW,
+                    (g.kH - 1 - ic_h) * g.dH, (g.kT - 1 - ic_t) * g.dT, fbar);
               if (++ic_c == icpt) {
                 ic_c = 0;
                 if (++ic_w == g.kW) { ic_w = 0; if (++ic_h == g.kH) { ic_h = 0; ++ic_t; } }
@@ -680,9 +812,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
             } else if (tma_a) {
               if (is_mn(AK)) {
                 for (int a = 0; a < BM / 32; ++a)
-                  tma_load_3d(a_tile + a * 4096, &tmA, ti.m0 + a * 32, ti.k_begin + i * KC, ti.batch, full0 + 8 * s_cur);
+                  ld3(a_tile + a * 4096, &tmA, ti.m0 + a * 32, ti.k_begin + i * KC, ti.batch, fbar);
               } else {
-                tma_load_3d(a_tile, &tmA, (kc0 + i) * KC, ti.m0, ti.batch, full0 + 8 * s_cur);
+                ld3(a_tile, &tmA, (kc0 + i) * KC, ti.m0, ti.batch, fbar);
               }
             }
             if (im2col_b) {
@@ -693,14 +825,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
 #pragma unroll
               for (int a = 0; a < NATOM; ++a)
                 if (a < ib_atoms)
-                  tma_load_im2col(b_tile + a * 4096, &tmB, ib_c[a], bw, bh, bd, o.n, ib_off[a] & 0xFFFF, ib_off[a] >> 16,
-                                  ti.tap * g.dT, full0 + 8 * s_cur);
+                  ldi(b_tile + a * 4096, &tmB, ib_c[a], bw, bh, bd, o.n, ib_off[a] & 0xFFFF, ib_off[a] >> 16,
+                      ti.tap * g.dT, fbar);
             } else if (tma_b) {
               if (is_mn(BK)) {
-                for (int a = 0; a < bn / 32; ++a)
-                  tma_load_3d(b_tile + a * 4096, &tmB, ti.n0 + a * 32, ti.k_begin + i * KC, ti.batch, full0 + 8 * s_cur);
+                for (int a = 0; a < bnh / 32; ++a)
+                  ld3(b_tile + a * 4096, &tmB, nb0 + a * 32, ti.k_begin + i * KC, ti.batch, fbar);
               } else {
-                tma_load_3d(b_tile, &tmB, (kc0 + i) * KC, ti.n0, ti.batch, full0 + 8 * s_cur);
+                ld3(b_tile, &tmB, (kc0 + i) * KC, nb0, ti.batch, fbar);
               }
             }
           }
@@ -731,17 +863,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
         }
       }
     }
-  } else if (warp == NPW) {
-    // ============================ MMA ISSUER (1 thread) ============================
-    if ((tid & 31) == 0) {
-      const uint32_t idesc = make_idesc(bn, is_mn(AK) ? 1 : 0, is_mn(BK) ? 1 : 0);
+  } else if (warp == NPWT) {
+    // ============================ MMA ISSUER (1 thread; PAIR: the leader CTA's) ============================
+    if ((tid & 31) == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc(bn, is_mn(AK) ? 1 : 0, is_mn(BK) ? 1 : 0, PAIR ? 2 * BM : BM);
       int it = 0, tile_iter = 0, s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const TileInfo ti = decode_tile(p, L, t);
-        if (ti.nk == 0) continue;
+      Sched sc;
+      sched_init(sc, L, unit);
+      TileInfo ti;
+      while (sched_next(p, L, sc, unit, nunits, rank, ti)) {
         const int acc = tile_iter & 1;
-        if (tile_iter >= 2) {                          // wait until the epilogue drained this accumulator
+        if (tile_iter >= 2) {                          // wait until the epilogue(s) drained this accumulator
           mbar_wait(tempty0 + 8 * acc, ((tile_iter >> 1) - 1) & 1);
           tc_fence_after();
         }
@@ -755,17 +888,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
 #pragma unroll
           for (int j = 0; j < KC / 8; ++j) {          // UMMA K = 8 for tf32
             uint64_t da, db;
-            if (stem_a) da = make_desc(a_tile + j * 4096, (uint32_t)L.stem_lbo, (uint32_t)L.stem_sbo, 0);
-            else if (!is_mn(AK)) da = make_desc(a_tile + j * 32, 16, 1024);
+            if (!is_mn(AK)) da = make_desc(a_tile + j * 32, 16, 1024);
             else da = make_desc(a_tile + j * 1024, 4096, 512, 1);
             if (!is_mn(BK)) db = make_desc(b_tile + j * 32, 16, 1024);
             else db = make_desc(b_tile + j * 1024, 4096, 512, 1);
-            umma_tf32(d_tmem, da, db, idesc, (i | j) ? 1u : 0u);
+            if (PAIR) umma_tf32_2(d_tmem, da, db, idesc, (i | j) ? 1u : 0u);
+            else umma_tf32(d_tmem, da, db, idesc, (i | j) ? 1u : 0u);
           }
-          umma_commit(empty0 + 8 * s);               // frees the smem stage when these MMAs retire
+          // frees the smem stage (PAIR: in both CTAs) when these MMAs retire
+          if (PAIR) umma_commit2(empty0 + 8 * s); else umma_commit(empty0 + 8 * s);
           if (++s == S) { s = 0; ph ^= 1u; }
         }
-        umma_commit(tfull0 + 8 * acc);               // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (PAIR: of both CTAs)
+        if (PAIR) umma_commit2(tfull0 + 8 * acc); else umma_commit(tfull0 + 8 * acc);
         ++tile_iter;
       }
     }
@@ -774,7 +909,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
     // TMEM lane quarter = warp % 4 (hardware rule); the two warps of a quarter take alternate 16-column
     // blocks.  Each 32x16 block is transposed through a padded shared-memory tile so that a warp store /
     // residual load / atomic covers 8 rows x 64 contiguous bytes (whole 32-byte sectors).
-    const int ew = warp - NPW - 1;
+    const int ew = warp - NPWT - 1;
     const int quarter = warp & 3;
     const int half = ew >> 2;
     const int lane = tid & 31;
@@ -790,79 +925,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
     const int col = (lane & 3) * 4;
     const bool want_res = (p.residual != nullptr) || (p.flags & VLFB_EPI_ACCUM);
     const float* res_src = p.residual ? p.residual : p.d;
+    const uint32_t tempty_x = (PAIR && rank != 0) ? mapa_rank(tempty0, 0) : tempty0;
+    const int nrank = PAIR ? 2 : 1;
+    const size_t ws_tile_floats = (size_t)BM * bn;
     int tile_iter = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x) {
-      const TileInfo ti = decode_tile(p, L, t);
-      if (ti.nk == 0) continue;
+    Sched sc;
+    sched_init(sc, L, unit);
+    TileInfo ti;
+    while (sched_next(p, L, sc, unit, nunits, rank, ti)) {
       const int acc = tile_iter & 1;
       const uint32_t lane_addr = tmem + (uint32_t)(acc * bn) + ((uint32_t)(quarter * 32) << 16);
       const int64_t tile_off = (int64_t)ti.batch * p.d_batch_stride + (int64_t)ti.tap * p.d_tap_stride;
-      if (want_res && t + (int)gridDim.x < total) {
-        // pull the NEXT tile's residual rows into L2 while this tile is being written out
-        const TileInfo tn = decode_tile(p, L, t + gridDim.x);
-        const int64_t noff = (int64_t)tn.batch * p.d_batch_stride + (int64_t)tn.tap * p.d_tap_stride;
-        const int segs = bn >> 5;
-        for (int idx = tid - (NPROD + 32); idx < BM * segs; idx += NEPI) {
-          const int row = idx / segs, seg = idx - row * segs;
-          const int m = tn.m0 + row, n = tn.n0 + seg * 32;
-          if (m < p.M && n < p.N) prefetch_l2(res_src + noff + (int64_t)m * p.ldd + n);
+      if (want_res || MASK) {
+        // pull the NEXT tile's residual / mask rows into L2 while this tile is being written out
+        Sched sn = sc;
+        TileInfo tn;
+        if (sched_next(p, L, sn, unit, nunits, rank, tn) && tn.npieces() == 1) {
+          const int64_t noff = (int64_t)tn.batch * p.d_batch_stride + (int64_t)tn.tap * p.d_tap_stride;
+          const int segs = bn >> 5;
+          for (int idx = tid - (NPRODT + 32); idx < BM * segs; idx += NEPI) {
+            const int row = idx / segs, seg = idx - row * segs;
+            const int m = tn.m0 + row, n = tn.n0 + seg * 32;
+            if (m < p.M && n < p.N) {
+              if (want_res) prefetch_l2(res_src + noff + (int64_t)m * p.ldd + n);
+              if (MASK) prefetch_l2(p.relu_mask + noff + (int64_t)m * p.ldd + n);
+            }
+          }
         }
       }
-      if (MASK && t + (int)gridDim.x < total) {
-        const TileInfo tn = decode_tile(p, L, t + gridDim.x);
-        const int64_t noff = (int64_t)tn.batch * p.d_batch_stride + (int64_t)tn.tap * p.d_tap_stride;
-        const int segs = bn >> 5;
-        for (int idx = tid - (NPROD + 32); idx < BM * segs; idx += NEPI) {
-          const int row = idx / segs, seg = idx - row * segs;
-          const int m = tn.m0 + row, n = tn.n0 + seg * 32;
-          if (m < p.M && n < p.N) prefetch_l2(p.relu_mask + noff + (int64_t)m * p.ldd + n);
-        }
-      }
-      // residual / accumulate operands are fetched one column block ahead (register double buffer): with only
-      // 8 epilogue warps per SM the loads must be in flight while the previous block is stored, otherwise the
-      // epilogue is DRAM-latency bound (Little's law) instead of bandwidth bound
-      auto load_res = [&](int c0, float4* r) {
-        const int n = ti.n0 + c0 + col;
-        const bool ok = want_res && vec_ok && c0 < bn && n + 3 < p.N;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int m = ti.m0 + quarter * 32 + (lane >> 2) + 8 * i;
-          r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok && m < p.M) r[i] = ld_nc_f4(res_src + tile_off + (int64_t)m * p.ldd + n);
-        }
-      };
-      // ReLU mask (backward of the ReLU that produced this GEMM's D-shaped input): fetched one block ahead like
-      // the residual, but AFTER the accumulator block has left the registers and packed to 16 bits as soon as
-      // it arrives, so that it never coexists with v[] / both residual buffers (the kernel is capped at 96
-      // registers; holding it as 4 more float4 spilled the whole epilogue loop -- measured 1.5-2.8x slower).
-      auto load_mask = [&](int c0, float4* mk) {
-        const int n = ti.n0 + c0 + col;
-        const bool ok = vec_ok && c0 < bn && n + 3 < p.N;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int m = ti.m0 + quarter * 32 + (lane >> 2) + 8 * i;
-          mk[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (ok && m < p.M) mk[i] = ld_nc_f4(p.relu_mask + tile_off + (int64_t)m * p.ldd + n);
-        }
-      };
-      auto pack_mask = [](const float4* mk) {
-        uint32_t b = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          b |= ((mk[i].x > 0.f ? 1u : 0u) | (mk[i].y > 0.f ? 2u : 0u) | (mk[i].z > 0.f ? 4u : 0u) |
-                (mk[i].w > 0.f ? 8u : 0u)) << (4 * i);
-        return b;
-      };
-      uint32_t mbits = 0xFFFFu;
-      if (MASK) {
-        float4 mk[4];
-        load_mask(half * EPC, mk);
-        mbits = pack_mask(mk);
-      }
-      // MASK instantiations keep one residual buffer (register budget: 96/thread with 17 warps)
-      constexpr bool DB = !MASK;
-      float4 rr[4], rn[4];
-      if (DB) load_res(half * EPC, rr);          // independent of the accumulator: issued before the wait
       if (ti.n0 != colv_n0) {
         // per-column affine of this warp's blocks -> shared memory, once per N tile (not per block: the
         // global-load latency used to sit in front of every block's first FFMA)
@@ -880,82 +970,180 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const vlfb_gemm_pa
         const int m = ti.m0 + quarter * 32 + (lane >> 2) + 8 * i;
         rs[i] = (p.row_scale && m < p.M) ? p.row_scale[m] : 1.f;
       }
-      mbar_wait(tfull0 + 8 * acc, (tile_iter >> 1) & 1);
-      tc_fence_after();
-      for (int c0 = half * EPC; c0 < bn; c0 += 2 * EPC) {
-        if (ti.n0 + c0 >= p.N) break;            // warp-uniform
-        if (DB) load_res(c0 + 2 * EPC, rn);
-        else load_res(c0, rr);                   // L2-resident (tile-ahead prefetch); overlaps the TMEM load
-        float v[EPC];
-        tmem_ld16(lane_addr + c0, v);
-        tmem_ld_wait();
+      // One pass over this warp's column blocks.  mode 0: accumulator -> fused epilogue -> D (whole tile here);
+      // mode 1 (stream-K piece): raw accumulator -> this unit's workspace slot; mode 2 (last unit to arrive at a
+      // shared tile): sum of ALL pieces' slots in piece order (deterministic) -> fused epilogue -> D.
+      auto run_blocks = [&](auto mode_c) {
+        constexpr int mode = decltype(mode_c)::value;
+        const bool wres = want_res && mode != 1;
+        // residual / accumulate operands are fetched one column block ahead (register double buffer): with only
+        // 8 epilogue warps per SM the loads must be in flight while the previous block is stored, otherwise the
+        // epilogue is DRAM-latency bound (Little's law) instead of bandwidth bound
+        auto load_res = [&](int c0, float4* r) {
+          const int n = ti.n0 + c0 + col;
+          const bool ok = wres && vec_ok && c0 < bn && n + 3 < p.N;
 #pragma unroll
-        for (int q = 0; q < EPC / 4; ++q)
-          *reinterpret_cast<float4*>(stg + lane * EPITCH + q * 4) =
-              make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        __syncwarp();
-        float4 mk[4];
-        if (MASK) load_mask(c0 + 2 * EPC, mk);
-        const int n = ti.n0 + c0 + col;
-        const bool nfull = n + 3 < p.N;
-        const int cvi = ((c0 - half * EPC) >> 1) + col;
-        const float4 cs = *reinterpret_cast<const float4*>(wsc + cvi);
-        float4 cb = *reinterpret_cast<const float4*>(wbi + cvi);
-        if (ti.k_begin != 0) cb = make_float4(0.f, 0.f, 0.f, 0.f);      // split-K: bias from the first K slice only
+          for (int i = 0; i < 4; ++i) {
+            const int m = ti.m0 + quarter * 32 + (lane >> 2) + 8 * i;
+            r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok && m < p.M) r[i] = ld_nc_f4(res_src + tile_off + (int64_t)m * p.ldd + n);
+          }
+        };
+        // ReLU mask (backward of the ReLU that produced this GEMM's D-shaped input): fetched one block ahead like
+        // the residual, but AFTER the accumulator block has left the registers and packed to 16 bits as soon as
+        // it arrives, so that it never coexists with v[] / both residual buffers (register budget of 17 warps;
+        // holding it as 4 more float4 spilled the whole epilogue loop -- measured 1.5-2.8x slower).
+        auto load_mask = [&](int c0, float4* mk) {
+          const int n = ti.n0 + c0 + col;
+          const bool ok = mode != 1 && vec_ok && c0 < bn && n + 3 < p.N;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = (lane >> 2) + 8 * i;
-          const int m = ti.m0 + quarter * 32 + row;
-          if (m >= p.M || n >= p.N) continue;
-          const float4 a4 = *reinterpret_cast<const float4*>(stg + row * EPITCH + col);
-          if (nfull && vec_ok) {
-            float4 o = make_float4(a4.x * p.alpha, a4.y * p.alpha, a4.z * p.alpha, a4.w * p.alpha);
-            o.x = (o.x * cs.x + cb.x) * rs[i]; o.y = (o.y * cs.y + cb.y) * rs[i];
-            o.z = (o.z * cs.z + cb.z) * rs[i]; o.w = (o.w * cs.w + cb.w) * rs[i];
-            const int64_t off = tile_off + (int64_t)m * p.ldd + n;
-            if (want_res) { o.x += rr[i].x; o.y += rr[i].y; o.z += rr[i].z; o.w += rr[i].w; }   // residual or D (ACCUM)
-            if (p.flags & VLFB_EPI_RELU) {
-              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-            }
-            if (MASK) {
-              const uint32_t mb = mbits >> (4 * i);
-              o.x = (mb & 1u) ? o.x : 0.f; o.y = (mb & 2u) ? o.y : 0.f;
-              o.z = (mb & 4u) ? o.z : 0.f; o.w = (mb & 8u) ? o.w : 0.f;
-            }
-            if (p.flags & VLFB_EPI_TF32) {
-              o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
-            }
-            float* dst = p.d + off;
-            if (p.flags & VLFB_EPI_ATOMIC) {
-              atomicAdd(dst, o.x); atomicAdd(dst + 1, o.y); atomicAdd(dst + 2, o.z); atomicAdd(dst + 3, o.w);
+          for (int i = 0; i < 4; ++i) {
+            const int m = ti.m0 + quarter * 32 + (lane >> 2) + 8 * i;
+            mk[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (ok && m < p.M) mk[i] = ld_nc_f4(p.relu_mask + tile_off + (int64_t)m * p.ldd + n);
+          }
+        };
+        auto pack_mask = [](const float4* mk) {
+          uint32_t b = 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            b |= ((mk[i].x > 0.f ? 1u : 0u) | (mk[i].y > 0.f ? 2u : 0u) | (mk[i].z > 0.f ? 4u : 0u) |
+                  (mk[i].w > 0.f ? 8u : 0u)) << (4 * i);
+          return b;
+        };
+        uint32_t mbits = 0xFFFFu;
+        if (MASK) {
+          float4 mk[4];
+          load_mask(half * EPC, mk);
+          mbits = pack_mask(mk);
+        }
+        // MASK instantiations keep one residual buffer (register budget)
+        constexpr bool DB = !MASK;
+        float4 rr[4], rn[4];
+        if (DB) load_res(half * EPC, rr);          // independent of the accumulator: issued before the wait
+        if (mode != 2) {
+          mbar_wait(tfull0 + 8 * acc, (tile_iter >> 1) & 1);
+          tc_fence_after();
+        }
+        for (int c0 = half * EPC; c0 < bn; c0 += 2 * EPC) {
+          if (ti.n0 + c0 >= p.N) break;            // warp-uniform
+          if (DB) load_res(c0 + 2 * EPC, rn);
+          else load_res(c0, rr);                   // L2-resident (tile-ahead prefetch); overlaps the TMEM load
+          if (mode != 2) {
+            float v[EPC];
+            tmem_ld16(lane_addr + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < EPC / 4; ++q)
+              *reinterpret_cast<float4*>(stg + lane * EPITCH + q * 4) =
+                  make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            __syncwarp();
+          }
+          float4 mk[4];
+          if (MASK) load_mask(c0 + 2 * EPC, mk);
+          const int n = ti.n0 + c0 + col;
+          const bool nfull = n + 3 < p.N;
+          const int cvi = ((c0 - half * EPC) >> 1) + col;
+          const float4 cs = *reinterpret_cast<const float4*>(wsc + cvi);
+          float4 cb = *reinterpret_cast<const float4*>(wbi + cvi);
+          if (mode == 0 && ti.k_begin != 0) cb = make_float4(0.f, 0.f, 0.f, 0.f);      // split-K: bias from the first K slice only
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = (lane >> 2) + 8 * i;
+            const int m = ti.m0 + quarter * 32 + row;
+            float4 a4;
+            if (mode == 2) {
+              const size_t wso = (size_t)(quarter * 32 + row) * bn + c0 + col;
+              a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int j = 0; j < ti.npieces(); ++j) {
+                const int sl = (j == 0) ? ti.first_slot() : 0;
+                const float4 w4 = ld_cg_f4(L.ws_tiles + ((size_t)((ti.ufirst() + j) * 2 + sl) * nrank + rank) * ws_tile_floats + wso);
+                a4.x += w4.x; a4.y += w4.y; a4.z += w4.z; a4.w += w4.w;
+              }
             } else {
-              *reinterpret_cast<float4*>(dst) = o;
+              a4 = *reinterpret_cast<const float4*>(stg + row * EPITCH + col);
             }
-          } else {
-            const float e4[4] = {a4.x, a4.y, a4.z, a4.w};
+            if (mode == 1) {
+              float* const ws_mine = L.ws_tiles + ((size_t)(unit * 2 + ti.slot()) * nrank + rank) * ws_tile_floats;
+              *reinterpret_cast<float4*>(ws_mine + (size_t)(quarter * 32 + row) * bn + c0 + col) = a4;
+              continue;
+            }
+            if (m >= p.M || n >= p.N) continue;
+            if (nfull && vec_ok) {
+              float4 o = make_float4(a4.x * p.alpha, a4.y * p.alpha, a4.z * p.alpha, a4.w * p.alpha);
+              o.x = (o.x * cs.x + cb.x) * rs[i]; o.y = (o.y * cs.y + cb.y) * rs[i];
+              o.z = (o.z * cs.z + cb.z) * rs[i]; o.w = (o.w * cs.w + cb.w) * rs[i];
+              const int64_t off = tile_off + (int64_t)m * p.ldd + n;
+              if (want_res) { o.x += rr[i].x; o.y += rr[i].y; o.z += rr[i].z; o.w += rr[i].w; }   // residual or D (ACCUM)
+              if (p.flags & VLFB_EPI_RELU) {
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+              }
+              if (MASK) {
+                const uint32_t mb = mbits >> (4 * i);
+                o.x = (mb & 1u) ? o.x : 0.f; o.y = (mb & 2u) ? o.y : 0.f;
+                o.z = (mb & 4u) ? o.z : 0.f; o.w = (mb & 8u) ? o.w : 0.f;
+              }
+              if (p.flags & VLFB_EPI_TF32) {
+                o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+              }
+              float* dst = p.d + off;
+              if (p.flags & VLFB_EPI_ATOMIC) {
+                atomicAdd(dst, o.x); atomicAdd(dst + 1, o.y); atomicAdd(dst + 2, o.z); atomicAdd(dst + 3, o.w);
+              } else {
+                *reinterpret_cast<float4*>(dst) = o;
+              }
+            } else {
+              const float e4[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (n + e < p.N) epilogue_store(p, ti.batch, ti.tap, m, n + e, e4[e], ti.k_begin == 0);
+              for (int e = 0; e < 4; ++e)
+                if (n + e < p.N) epilogue_store(p, ti.batch, ti.tap, m, n + e, e4[e], mode != 0 || ti.k_begin == 0);
+            }
+          }
+          __syncwarp();
+          if (MASK) mbits = pack_mask(mk);
+          if (DB) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rr[i] = rn[i];
           }
         }
-        __syncwarp();
-        if (MASK) mbits = pack_mask(mk);
-        if (DB) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) rr[i] = rn[i];
-        }
+      };
+      // (the 17-warp cp.async builds never take the fix-up path: the host plans stream-K fix-ups for TMA-fed launches only)
+      const bool split_tile = !CP && ti.npieces() > 1;
+      if constexpr (!CP) {
+        if (split_tile) run_blocks(std::integral_constant<int, 1>{});
+        else run_blocks(std::integral_constant<int, 0>{});
+      } else {
+        run_blocks(std::integral_constant<int, 0>{});
       }
       // every TMEM read of this accumulator has completed (tcgen05.wait::ld above): hand it back to the MMA warp
       tc_fence_before();
-      mbar_arrive(tempty0 + 8 * acc);
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR && rank != 0) mbar_arrive_cluster(tempty_x + 8 * acc);
+        else mbar_arrive(tempty0 + 8 * acc);
+      }
       ++tile_iter;
+      if constexpr (!CP) if (split_tile) {
+        // publish this piece, count it; the warp that arrives last owns the reduction of its sub-blocks
+        __threadfence();
+        __syncwarp();
+        int* cnt = L.ws_cnt + ((size_t)ti.tile * nrank + rank) * (NEPI / 32) + ew;
+        int old = 0;
+        if (lane == 0) old = atomicAdd(cnt, 1);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old == ti.npieces() - 1) {
+          __threadfence();
+          run_blocks(std::integral_constant<int, 2>{});
+          if (lane == 0) *cnt = 0;                 // counters are zero again when the launch ends
+        }
+      }
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == NPW) {
+  if (PAIR) cluster_sync_all(); else __syncthreads();       // PAIR: no CTA exits (or frees TMEM) while its peer can still signal it
+  if (warp == NPWT) {
     tc_fence_after();
-    tmem_dealloc(tmem, tmem_cols);
+    if (PAIR) tmem_dealloc2(tmem, tmem_cols); else tmem_dealloc(tmem, tmem_cols);
   }
 }
 
@@ -1041,8 +1229,8 @@ static bool make_tmap_im2col(CUtensorMap* tm, const float* base, int N, int D, i
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// tuning overrides, read once (scripts/tune_gemm.py)
-struct Env { int bn, stages, lag, fence, stem_im2col, stem_lbo, stem_sbo; bool tma_mn, im2col; };
+// tuning overrides, read once (scripts/tune_gemm.py); the per-call fields of vlfb_gemm_params_t take precedence
+struct Env { int bn, stages, lag, fence, pair, sk; bool tma_mn, im2col; };
 static Env read_env() {
   Env e;
   auto geti = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
@@ -1050,54 +1238,164 @@ static Env read_env() {
   e.stages = geti("VLFB_STAGES", 0);
   e.lag = geti("VLFB_LAG", 0);
   e.fence = geti("VLFB_FENCE", 0);
+  e.pair = geti("VLFB_PAIR", 0);
+  e.sk = geti("VLFB_SK", 0);
   e.tma_mn = geti("VLFB_TMA_MN", 1) != 0;
   e.im2col = geti("VLFB_IM2COL", 1) != 0;
-  e.stem_im2col = geti("VLFB_STEM_IM2COL", 0);
-  e.stem_lbo = geti("VLFB_STEM_LBO", 2048);
-  e.stem_sbo = geti("VLFB_STEM_SBO", 128);
+  return e;
+}
+static const Env& env() {
+  static const Env e = read_env();
   return e;
 }
 
-// Tile width and split-K (p.split_k == 0: chosen here).  The persistent grid runs ceil(tiles / #SMs) rounds;
-// a round of a 128 x bn tile costs ~(128 + bn) bytes of operand traffic per k over (K / split) chunks plus a
-// fixed fill + epilogue overhead (~8 chunks), so take the (bn, split) pair that minimises
-// rounds * (chunks + 8) * (128 + bn).  With the old fixed rules conv1's wgrad ran 300 tiles on 148 SMs
-// (3 rounds for 2.03 waves of work) and the res2 3x3 wgrads 192 tiles (2 rounds for 1.3 waves).
-void choose_tile(const vlfb_gemm_params_t& p, int num_sms, int* bn_out, int* split_out) {
+// ---- plan: tile width x CTA pairing x schedule, chosen together by a cycle model of one SM -----------------
+// A K chunk (32 fp32 of K) of a 128 x bn tile costs max(tensor pipe, operand delivery):
+//   tensor   = 4 MMAs x (128 x bn x 8 MACs) / 2048 MAC/clk = 2 bn clocks (kind::tf32 issues at half the bf16 rate);
+//   delivery = (128 + bn) x 128 B, or (128 + bn/2) x 128 B for a CTA pair, at ~58 B/clk through the SM's
+//              L2 port (ncu r01: 694 MB -> 98 SMs in 70.9 us on res5 branch2b).
+// A tile adds a fixed fill + epilogue cost (~8 chunks' worth); a stream-K launch adds the fix-up of the shared tiles.
+static double chunk_cost(int bn, bool pair) {
+  const double tensor = 2.0 * bn;
+  const double port = (16384.0 + (pair ? 64.0 : 128.0) * bn) / 58.0;
+  return tensor > port ? tensor : port;
+}
+
+struct Plan { int bn, split_k, pair, sk; int tiles, units; double cost; };
+
+static constexpr bool kind_tma_capable(int kind) { return kind != VLFB_OP_STEM_K && kind != VLFB_OP_STEM_MN; }
+
+// `pairs` = co-resident CTA pairs (0: pairing unavailable); pair_ok / sk_ok = what the operands / workspace allow.
+static Plan make_plan(const vlfb_gemm_params_t& p, int num_sms, int pairs, bool pair_ok, bool sk_ok) {
   const int zbase = p.taps > 1 ? p.taps : p.batch;
-  const int tiles_m = ceil_div(p.M, BM);
-  int best_bn = 32, best_split = p.split_k > 0 ? p.split_k : 1;
-  double best_score = 1e30;
-  const int smax = p.split_k > 0 ? p.split_k : (p.K >= 512 ? (p.K / 256 < 128 ? p.K / 256 : 128) : 1);
-  // Candidate widths.  The power-of-two set leaves the small-M layers badly quantised: res5's 3x3 convolutions
-  // (M = 6272 = 49 row tiles, N = 512) run 98 tiles of 128 x 256 on 148 SMs -- ncu: tensor pipe 65 % of the ACTIVE
-  // cycles but 40 % of the elapsed ones (profiles/r01_ncu_full_gemm3_res45_summary.csv); 147 tiles of 128 x 192
-  // fill the machine in one round.  UMMA takes any N % 16 == 0 (M = 128); the loaders / epilogue work in
-  // 32-column atoms.  Enabled by vlfb_set_tile_widths(1) / VLFB_BN_EXTRA=1 (default off until measured).
-  static const int kWidths[] = {256, 224, 192, 160, 128, 96, 64, 32};
-  const bool extra = extra_tile_widths();
-  for (int wi = 0; wi < 8; ++wi) {
-    const int bn = kWidths[wi];
-    if (!extra && (bn & (bn - 1)) != 0) continue;
-    if (bn > 32 && p.N <= bn / 2) continue;                       // do not pad N by 2x
-    if ((bn & (bn - 1)) != 0 && (int64_t)ceil_div(p.N, bn) * bn >= 2 * (int64_t)p.N) continue;
-    const int64_t base_tiles = (int64_t)tiles_m * ceil_div(p.N, bn) * zbase;
-    for (int sp = (p.split_k > 0 ? p.split_k : 1); sp <= smax; ++sp) {
-      const int64_t tiles = base_tiles * sp;
-      const double rounds = (double)((tiles + num_sms - 1) / num_sms);
-      const double chunks = (double)ceil_div(ceil_div(p.K, sp), KC) + 8.0;
-      const double score = rounds * chunks * (128 + bn);
-      if (score < best_score * 0.999) { best_score = score; best_bn = bn; best_split = sp; }
+  const bool atomic = (p.flags & VLFB_EPI_ATOMIC) != 0;
+  const int want_bn = p.tile_n > 0 ? p.tile_n : env().bn;
+  const int want_pair = p.pair != 0 ? p.pair : env().pair;
+  const int want_sk = p.stream_k != 0 ? p.stream_k : env().sk;
+  Plan best, best_sk;
+  best.cost = 1e30; best.bn = 32; best.split_k = p.split_k > 0 ? p.split_k : 1; best.pair = 0; best.sk = 0;
+  best.tiles = 0; best.units = 0;
+  best_sk = best;
+  static const int kWidths[] = {256, 192, 128, 96, 64, 32};
+  for (int pr = 0; pr < 2; ++pr) {
+    const bool can_pair = pair_ok && pairs >= 1 && p.M > BM;
+    if (pr == 1 && (!can_pair || want_pair < 0)) continue;
+    if (pr == 0 && want_pair > 0 && can_pair) continue;
+    const int U = pr ? pairs : num_sms;
+    for (int wi = 0; wi < 6; ++wi) {
+      const int bn = kWidths[wi];
+      if (want_bn > 0 ? bn != want_bn : ((bn & (bn - 1)) != 0)) continue;       // 96 / 192 only on request
+      if (pr && (bn & 63)) continue;                                            // each CTA of a pair stages whole 32-column atoms
+      if (want_bn <= 0 && bn > 32 && p.N <= bn / 2) continue;                   // do not pad N by 2x
+      const int tiles_m = ceil_div(p.M, pr ? 2 * BM : BM);
+      const int64_t T = (int64_t)tiles_m * ceil_div(p.N, bn) * zbase;
+      const int nkt = ceil_div(p.K, KC);
+      const double cc = chunk_cost(bn, pr != 0);
+      const double fixed = 8.0 * cc;
+      // (a) static tile loop, optional plain split-K (atomic epilogues only)
+      const int smax = p.split_k > 0 ? p.split_k : (atomic && p.K >= 512 ? (p.K / 256 < 128 ? p.K / 256 : 128) : 1);
+      for (int sp = (p.split_k > 0 ? p.split_k : 1); sp <= smax; ++sp) {
+        const int64_t tiles = T * sp;
+        const double rounds = (double)((tiles + U - 1) / U);
+        const double cost = rounds * (ceil_div(ceil_div(p.K, sp), KC) * cc + fixed);
+        if (cost < best.cost * 0.999) {
+          best.cost = cost; best.bn = bn; best.split_k = sp; best.pair = pr; best.sk = 0;
+          best.tiles = (int)tiles; best.units = (int)(tiles < U ? tiles : U);
+        }
+      }
+      // (b) stream-K: equal chunk ranges; shared tiles reduced through the workspace (or by atomics)
+      const int64_t total = T * nkt;
+      const bool sk_legal = (atomic ? p.split_k != 1 : (sk_ok && p.split_k <= 1)) && want_sk >= 0 && nkt >= 2 &&
+                            total >= 2 * (int64_t)U && T * (pr ? 2 : 1) * (NEPI / 32) <= SK_CNT_INTS && U <= MAX_UNITS;
+      if (sk_legal && (T % U) != 0) {
+        const double per_unit = (double)((total + U - 1) / U);
+        const double cost = per_unit * cc + fixed * (double)((T + U - 1) / U) + (atomic ? 1.0 : 2.0) * fixed;
+        if (cost < best_sk.cost * 0.999) {
+          best_sk.cost = cost; best_sk.bn = bn; best_sk.split_k = 1; best_sk.pair = pr; best_sk.sk = 1;
+          best_sk.tiles = (int)T; best_sk.units = U;
+        }
+      }
     }
   }
-  *bn_out = best_bn;
-  *split_out = best_split;
+  if (best_sk.cost < 1e29 && (want_sk > 0 || best_sk.cost < best.cost * 0.999)) return best_sk;
+  return best;
+}
+
+// Chunk ranges of the stream-K units.  A boundary that would leave a piece of fewer than `minp` chunks at either end
+// of a tile is moved onto the tile boundary.
+static void make_bounds(int* b, int U, int64_t T, int nkt) {
+  const int64_t total = T * nkt;
+  const int minp = nkt >= 16 ? 4 : (nkt >= 8 ? 2 : 1);
+  for (int u = 0; u <= U; ++u) {
+    int64_t x = (int64_t)u * total / U;
+    const int r = (int)(x % nkt);
+    if (r && r < minp) x -= r;
+    else if (r && nkt - r < minp) x += nkt - r;
+    b[u] = (int)x;
+  }
+  b[0] = 0; b[U] = (int)total;
+  bool ok = true;
+  for (int u = 0; u < U; ++u) if (b[u + 1] <= b[u]) ok = false;
+  if (!ok) for (int u = 0; u <= U; ++u) b[u] = (int)((int64_t)u * total / U);
+}
+
+size_t gemm_tc_workspace_bytes() {
+  return (size_t)SK_CNT_INTS * 4 + (size_t)MAX_UNITS * 2 * BM * 256 * 4;
+}
+
+template <int AK, int BK, bool MASK>
+static int max_pairs() {
+  static int cached = -1;
+  if constexpr (!(kind_tma_capable(AK) && kind_tma_capable(BK))) return 0;
+  else if (cached < 0) {
+    cached = 0;
+    if (cudaFuncSetAttribute(gemm_tc_kernel<AK, BK, MASK, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             227 * 1024) == cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * MAX_UNITS);
+      cfg.blockDim = dim3(32 + 32 + NEPI);
+      cfg.dynamicSmemBytes = 200 * 1024;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<AK, BK, MASK, true, false>, &cfg) == cudaSuccess && n > 0)
+        cached = n < MAX_UNITS ? n : MAX_UNITS;
+    }
+    cudaGetLastError();
+  }
+  return cached;
+}
+
+template <int AK, int BK, bool MASK, bool PAIR, bool CP>
+static int launch_variant(const cudaLaunchConfig_t& cfg, const vlfb_gemm_params_t& p, const Launch& L, const CUtensorMap& tmA,
+                          const CUtensorMap& tmB) {
+  static bool attr_done = false;
+  cudaError_t e;
+  if (!attr_done) {
+    e = cudaFuncSetAttribute(gemm_tc_kernel<AK, BK, MASK, PAIR, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
+      return VLFB_E_CUDA;
+    }
+    attr_done = true;
+  }
+  e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<AK, BK, MASK, PAIR, CP>, p, L, tmA, tmB);
+  if (e != cudaSuccess) {
+    set_error("gemm_tc launch: %s", cudaGetErrorString(e));
+    return VLFB_E_CUDA;
+  }
+  VLFB_CHECK_LAUNCH();
+  return VLFB_OK;
 }
 
 template <int AK, int BK, bool MASK>
 int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
   vlfb_gemm_params_t p = p_in;       // split_k == 0 is resolved below
   Launch L;
+  memset(&L, 0, sizeof(L));
   L.out.w = make_fastdiv(p.g.Wo);
   L.out.h = make_fastdiv(p.g.Ho);
   L.out.t = make_fastdiv(p.g.To);
@@ -1111,86 +1409,112 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+    if (num_sms > MAX_UNITS) num_sms = MAX_UNITS;
   }
-  static const Env env = read_env();
-  const int zbase = p.taps > 1 ? p.taps : p.batch;
-  const int tiles_m = ceil_div(p.M, BM);
-  {
-    int best_bn = 32, best_split = 1;
-    choose_tile(p, num_sms, &best_bn, &best_split);
-    L.bn = best_bn;
-    p.split_k = best_split;
-  }
-  if (env.bn >= 32 && (p.N > env.bn / 2 || env.bn == 32)) L.bn = env.bn;      // tuning overrides (scripts/tune_gemm.py)
-  const int64_t zdim = (int64_t)zbase * p.split_k;
-  const int stage_bytes = A_TILE_BYTES + L.bn * KC * 4;
-  L.stages = (227 * 1024 - EPI_STAGE_BYTES - 2048) / stage_bytes;
-  if (L.stages > 6) L.stages = 6;
-  if (env.stages >= 2 && env.stages <= L.stages) L.stages = env.stages;
-  L.lag = L.stages - 1 < 2 ? L.stages - 1 : 2;
-  if (env.lag >= 1 && env.lag < L.stages && env.lag <= 5) L.lag = env.lag;
-  L.fence_mode = env.fence;
-  L.stem_lbo = env.stem_lbo;
-  L.stem_sbo = env.stem_sbo;
-  L.tiles_m = tiles_m;
-  L.tiles_n = ceil_div(p.N, L.bn);
-  L.total_tiles = (int)((int64_t)L.tiles_m * L.tiles_n * zdim);
-  const int smem = L.stages * stage_bytes + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<AK, BK, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
-      return VLFB_E_CUDA;
-    }
-    attr_done = true;
-  }
-  dim3 grid((unsigned)(L.total_tiles < num_sms ? L.total_tiles : num_sms));
+  const Env& ev = env();
+  const vlfb_conv_geom_t& g = p.g;
+  const bool unit_dgrad = g.sT == 1 && g.sH == 1 && g.sW == 1;
+  // can both operands be staged by TMA (the precondition of CTA pairs)?  Decided on the cheap conditions here; the
+  // tensor maps themselves are encoded after the plan (their boxes depend on it) and a failure falls back below.
+  bool pair_ok = kind_tma_capable(AK) && kind_tma_capable(BK) && encode_fn() != nullptr && ev.im2col &&
+                 (ev.tma_mn || !(is_mn(AK) || is_mn(BK))) && !(AK == VLFB_OP_DGRAD_K && !unit_dgrad) && p.K >= KC;
+  bool sk_ws = p.workspace != nullptr && p.workspace_bytes >= gemm_tc_workspace_bytes() &&
+                     (reinterpret_cast<uintptr_t>(p.workspace) & 15) == 0;
   alignas(64) CUtensorMap tmA, tmB;
-  memset(&tmA, 0, sizeof(tmA));
-  memset(&tmB, 0, sizeof(tmB));
-  const bool mn_tma = env.tma_mn;
-  L.tma_a = (AK == VLFB_OP_DENSE_K && make_tmap(&tmA, p.a, p.M, p.K, p.batch, BM)) ||
-            (AK == VLFB_OP_DENSE_MN && mn_tma && make_tmap_mn(&tmA, p.a, p.M, p.K, p.batch)) ? 1 : 0;
-  L.tma_b = (BK == VLFB_OP_DENSE_K && make_tmap(&tmB, p.b, p.N, p.K, p.batch, L.bn)) ||
-            (BK == VLFB_OP_DENSE_MN && mn_tma && make_tmap_mn(&tmB, p.b, p.N, p.K, p.batch)) ? 1 : 0;
-  if (env.im2col) {
-    // conv gathers as TMA im2col copies: one instruction per K chunk instead of 1024 16-byte cp.asyncs
-    const vlfb_conv_geom_t& g = p.g;
-    const int pad_lo[3] = {-g.pW, -g.pH, -g.pT};
-    const int pad_hi[3] = {g.pW - (g.kW - 1) * g.dW, g.pH - (g.kH - 1) * g.dH, g.pT - (g.kT - 1) * g.dT};
-    const int cstr[3] = {g.sW, g.sH, g.sT};
-    const int ones[3] = {1, 1, 1};
-    if (AK == VLFB_OP_CONV_K &&
-        make_tmap_im2col(&tmA, p.a.ptr, g.N, g.T, g.H, g.W, g.C, pad_lo, pad_hi, cstr, BM, CU_TENSOR_MAP_SWIZZLE_128B))
-      L.tma_a = 2;
-    if (AK == VLFB_OP_DGRAD_K && g.sT == 1 && g.sH == 1 && g.sW == 1) {
-      const int lo[3] = {g.pW - (g.kW - 1) * g.dW, g.pH - (g.kH - 1) * g.dH, g.pT - (g.kT - 1) * g.dT};
-      const int hi[3] = {-g.pW, -g.pH, -g.pT};
-      if (make_tmap_im2col(&tmA, p.a.ptr, g.N, g.To, g.Ho, g.Wo, g.Co, lo, hi, ones, BM, CU_TENSOR_MAP_SWIZZLE_128B))
+  Plan plan;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    plan = make_plan(p, num_sms, pair_ok ? max_pairs<AK, BK, MASK>() : 0, pair_ok, sk_ws);
+    L.bn = plan.bn;
+    p.split_k = plan.split_k;
+    const int bnh = plan.pair ? L.bn / 2 : L.bn;
+    memset(&tmA, 0, sizeof(tmA));
+    memset(&tmB, 0, sizeof(tmB));
+    const bool mn_tma = ev.tma_mn;
+    L.tma_a = (AK == VLFB_OP_DENSE_K && make_tmap(&tmA, p.a, p.M, p.K, p.batch, BM)) ||
+              (AK == VLFB_OP_DENSE_MN && mn_tma && make_tmap_mn(&tmA, p.a, p.M, p.K, p.batch)) ? 1 : 0;
+    L.tma_b = (BK == VLFB_OP_DENSE_K && make_tmap(&tmB, p.b, p.N, p.K, p.batch, bnh)) ||
+              (BK == VLFB_OP_DENSE_MN && mn_tma && make_tmap_mn(&tmB, p.b, p.N, p.K, p.batch)) ? 1 : 0;
+    if (ev.im2col) {
+      // conv gathers as TMA im2col copies: one instruction per K chunk instead of 1024 16-byte cp.asyncs
+      const int pad_lo[3] = {-g.pW, -g.pH, -g.pT};
+      const int pad_hi[3] = {g.pW - (g.kW - 1) * g.dW, g.pH - (g.kH - 1) * g.dH, g.pT - (g.kT - 1) * g.dT};
+      const int cstr[3] = {g.sW, g.sH, g.sT};
+      const int ones[3] = {1, 1, 1};
+      if (AK == VLFB_OP_CONV_K &&
+          make_tmap_im2col(&tmA, p.a.ptr, g.N, g.T, g.H, g.W, g.C, pad_lo, pad_hi, cstr, BM, CU_TENSOR_MAP_SWIZZLE_128B))
         L.tma_a = 2;
+      if (AK == VLFB_OP_DGRAD_K && unit_dgrad) {
+        const int lo[3] = {g.pW - (g.kW - 1) * g.dW, g.pH - (g.kH - 1) * g.dH, g.pT - (g.kT - 1) * g.dT};
+        const int hi[3] = {-g.pW, -g.pH, -g.pT};
+        if (make_tmap_im2col(&tmA, p.a.ptr, g.N, g.To, g.Ho, g.Wo, g.Co, lo, hi, ones, BM, CU_TENSOR_MAP_SWIZZLE_128B))
+          L.tma_a = 2;
+      }
+      if (BK == VLFB_OP_CONV_MN && (g.C % KC) == 0 && L.tma_a &&
+          make_tmap_im2col(&tmB, p.b.ptr, g.N, g.T, g.H, g.W, g.C, pad_lo, pad_hi, cstr, KC,
+                           CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+        L.tma_b = 2;
     }
-    if (AK == VLFB_OP_STEM_K && env.stem_im2col &&
-        make_tmap_im2col(&tmA, p.a.ptr, g.N, g.T, g.H, g.W, 4, pad_lo, pad_hi, cstr, BM, CU_TENSOR_MAP_SWIZZLE_NONE, 4))
-      L.tma_a = 3;
-    if (BK == VLFB_OP_CONV_MN && (g.C % KC) == 0 && L.tma_a &&
-        make_tmap_im2col(&tmB, p.b.ptr, g.N, g.T, g.H, g.W, g.C, pad_lo, pad_hi, cstr, KC,
-                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
-      L.tma_b = 2;
+    const bool fixup = plan.sk && !(p.flags & VLFB_EPI_ATOMIC);
+    if (!(plan.pair || fixup) || (L.tma_a && L.tma_b)) break;
+    pair_ok = false;                   // an operand fell back to cp.async: plan again without pairing / fix-ups
+    sk_ws = false;
   }
-  launch_k(gemm_tc_kernel<AK, BK, MASK>, grid, dim3(NTHREADS), (size_t)smem, stream, p, L, tmA, tmB);
-  VLFB_CHECK_LAUNCH();
-  return VLFB_OK;
+  const int zbase = p.taps > 1 ? p.taps : p.batch;
+  L.tile_rows = plan.pair ? 2 * BM : BM;
+  L.tiles_m = ceil_div(p.M, L.tile_rows);
+  L.tiles_n = ceil_div(p.N, L.bn);
+  L.total_tiles = (int)((int64_t)L.tiles_m * L.tiles_n * zbase * p.split_k);
+  const int stage_bytes = A_TILE_BYTES + (plan.pair ? L.bn / 2 : L.bn) * KC * 4;
+  L.stages = (227 * 1024 - EPI_STAGE_BYTES - 2048) / stage_bytes;
+  if (L.stages > (plan.pair ? 7 : 6)) L.stages = plan.pair ? 7 : 6;
+  if (ev.stages >= 2 && ev.stages <= L.stages) L.stages = ev.stages;
+  L.lag = L.stages - 1 < 2 ? L.stages - 1 : 2;
+  if (ev.lag >= 1 && ev.lag < L.stages && ev.lag <= 5) L.lag = ev.lag;
+  L.fence_mode = ev.fence;
+  const int cap = plan.pair ? max_pairs<AK, BK, MASK>() : num_sms;
+  int units = L.total_tiles < cap ? L.total_tiles : cap;
+  L.sk = 0;
+  if (plan.sk) {
+    L.sk = 1;
+    L.nkt = ceil_div(p.K, KC);
+    units = cap;
+    make_bounds(L.bounds, units, (int64_t)L.total_tiles, L.nkt);
+    if (!(p.flags & VLFB_EPI_ATOMIC)) {
+      L.ws_cnt = reinterpret_cast<int*>(p.workspace);
+      L.ws_tiles = reinterpret_cast<float*>(reinterpret_cast<char*>(p.workspace) + (size_t)SK_CNT_INTS * 4);
+    }
+  }
+  const int smem = L.stages * stage_bytes + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  const bool cp = !(L.tma_a && L.tma_b);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(plan.pair ? 2 * units : units));
+  cfg.blockDim = dim3((unsigned)((cp ? NPROD : 32) + 32 + NEPI));
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = plan.pair ? 1 : 0;
+  if constexpr (kind_tma_capable(AK) && kind_tma_capable(BK)) {
+    if (plan.pair) return launch_variant<AK, BK, MASK, true, false>(cfg, p, L, tmA, tmB);
+    if (!cp) return launch_variant<AK, BK, MASK, false, false>(cfg, p, L, tmA, tmB);
+  }
+  return launch_variant<AK, BK, MASK, false, true>(cfg, p, L, tmA, tmB);
 }
 
 }  // namespace tc
 
-void gemm_tc_plan(const vlfb_gemm_params_t& p, int num_sms, int* bn, int* split_k, int* tiles) {
-  tc::choose_tile(p, num_sms, bn, split_k);
-  const int zbase = p.taps > 1 ? p.taps : p.batch;
-  *tiles = ceil_div(p.M, tc::BM) * ceil_div(p.N, *bn) * zbase * *split_k;
+void gemm_tc_plan(const vlfb_gemm_params_t& p, int num_sms, vlfb_gemm_plan_t* out) {
+  // host-only view of the plan: pairing assumes both operands are TMA-addressable and one pair per two SMs
+  const bool pair_ok = tc::kind_tma_capable(p.a.kind) && tc::kind_tma_capable(p.b.kind) && p.K >= tc::KC;
+  bool sk_ws = p.workspace != nullptr && p.workspace_bytes >= tc::gemm_tc_workspace_bytes();
+  const tc::Plan pl = tc::make_plan(p, num_sms, num_sms / 2, pair_ok, sk_ws);
+  out->tile_n = pl.bn; out->split_k = pl.split_k; out->pair = pl.pair; out->stream_k = pl.sk;
+  out->tiles = pl.tiles; out->units = pl.units;
 }
+
+size_t gemm_tc_workspace_bytes() { return tc::gemm_tc_workspace_bytes(); }
 
 int gemm_tc(const vlfb_gemm_params_t& p, cudaStream_t stream) {
   const int ak = p.a.kind, bk = p.b.kind;

@@ -48,7 +48,6 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // ------------------------------------------------------------------ AffineNd
 __global__ void affine_fwd_k(const float4* __restrict__ x, const float4* __restrict__ s, const float4* __restrict__ b,
                              float4* __restrict__ y, int64_t n4, int c4) {
-  pdl_prologue();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % c4);
     const float4 v = x[i], sc = s[c];
@@ -66,7 +65,6 @@ __global__ void affine_fwd_k(const float4* __restrict__ x, const float4* __restr
 // ------------------------------------------------------------------ pooling
 __global__ void maxpool_fwd_k(const float* __restrict__ x, float* __restrict__ y, int32_t* __restrict__ arg,
                               const vlfb_conv_geom_t g, int64_t total) {
-  pdl_prologue();
   const int c4 = g.C >> 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % c4) * 4;
@@ -98,7 +96,6 @@ __global__ void maxpool_fwd_k(const float* __restrict__ x, float* __restrict__ y
 
 __global__ void maxpool_bwd_k(const float* __restrict__ dy, const int32_t* __restrict__ arg, float* __restrict__ dx,
                               int C, int64_t total) {
-  pdl_prologue();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int pos = arg[i];
     if (pos >= 0) atomicAdd(dx + (int64_t)pos * C + (i % C), dy[i]);
@@ -107,7 +104,6 @@ __global__ void maxpool_bwd_k(const float* __restrict__ dy, const int32_t* __res
 
 __global__ void avgpool_fwd_k(const float* __restrict__ x, float* __restrict__ y, const vlfb_conv_geom_t g,
                               int64_t total) {
-  pdl_prologue();
   const int c4 = g.C >> 2;
   const float inv = 1.f / (float)(g.kT * g.kH * g.kW);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -128,7 +124,6 @@ __global__ void avgpool_fwd_k(const float* __restrict__ x, float* __restrict__ y
 
 __global__ void avgpool_bwd_k(const float* __restrict__ dy, float* __restrict__ dx, const vlfb_conv_geom_t g,
                               int accumulate, int64_t total) {
-  pdl_prologue();
   const int c4 = g.C >> 2;
   const float inv = 1.f / (float)(g.kT * g.kH * g.kW);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -199,7 +194,6 @@ __device__ __forceinline__ bool roi_sample(const RoiBox& b, int ph, int pw, int 
 
 __global__ void roi_align_fwd_k(const float* __restrict__ feat, const float* __restrict__ rois, float* __restrict__ out,
                                 int H, int W, int C, int PH, int PW, float scale, int sr, int64_t total) {
-  pdl_prologue();
   const int c4 = C >> 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % c4) * 4;
@@ -228,7 +222,6 @@ __global__ void roi_align_fwd_k(const float* __restrict__ feat, const float* __r
 
 __global__ void roi_align_bwd_k(const float* __restrict__ dout, const float* __restrict__ rois, float* __restrict__ dfeat,
                                 int H, int W, int C, int PH, int PW, float scale, int sr, int64_t total) {
-  pdl_prologue();
   const int c4 = C >> 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % c4) * 4;
@@ -259,7 +252,6 @@ __global__ void roi_align_bwd_k(const float* __restrict__ dout, const float* __r
 __global__ void roi_table_k(const float* __restrict__ rois, int32_t* __restrict__ pos, float* __restrict__ wts,
                             int32_t* __restrict__ grid, int H, int W, int R, int PH, int PW, int mg, float scale,
                             int sr) {
-  pdl_prologue();
   const int64_t total = (int64_t)R * PH * PW * mg * mg;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t q = i;
@@ -281,7 +273,6 @@ __global__ void roi_table_k(const float* __restrict__ rois, int32_t* __restrict_
 // ------------------------------------------------------------------ softmax / layernorm (warp per row)
 __global__ void softmax_fwd_k(const float* __restrict__ x, float* __restrict__ p, int64_t rows, int cols, float scale,
                               int tf32) {
-  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t wpb = blockDim.x >> 5;
   for (int64_t row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
@@ -303,7 +294,6 @@ __global__ void softmax_fwd_k(const float* __restrict__ x, float* __restrict__ p
 
 __global__ void softmax_bwd_k(const float* __restrict__ p, const float* __restrict__ dp, float* __restrict__ dx,
                               int64_t rows, int cols, float scale) {
-  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t wpb = blockDim.x >> 5;
   for (int64_t row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
@@ -318,7 +308,6 @@ __global__ void softmax_bwd_k(const float* __restrict__ p, const float* __restri
 
 __global__ void layernorm_fwd_k(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ mean,
                                 float* __restrict__ sd, int64_t rows, int cols, float eps) {
-  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t wpb = blockDim.x >> 5;
   for (int64_t row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
@@ -336,7 +325,6 @@ __global__ void layernorm_fwd_k(const float* __restrict__ x, float* __restrict__
 
 __global__ void layernorm_bwd_k(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ sd,
                                 float* __restrict__ dx, int64_t rows, int cols) {
-  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t wpb = blockDim.x >> 5;
   for (int64_t row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
@@ -370,7 +358,6 @@ __device__ __forceinline__ float ew_op(float a, float b, float s0, float s1) {
 template <int OP>
 __global__ void ew_k(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, int64_t n,
                      float s0, float s1, int vec) {
-  pdl_prologue();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (vec) {
@@ -400,7 +387,6 @@ int ew_launch(const float* a, const float* b, float* o, int64_t n, float s0, flo
 // of the layer that owns the gradient and the TF32 rounding its GEMMs need, in ONE pass (4 tensor streams instead
 // of the 6 of axpby + relu_bwd_tf32).  `out` may alias a or b.
 __global__ void add_mask_tf32_k(const float* a, const float* b, const float* y, float* o, int64_t n, int vec) {
-  pdl_prologue();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (vec) {
@@ -435,7 +421,6 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t ctr, uint64_t key) {
 
 __global__ void dropout_k(const float* __restrict__ x, float* __restrict__ y, int64_t n, float ratio, float inv_keep,
                           uint64_t seed, uint64_t offset, const int64_t* __restrict__ step) {
-  pdl_prologue();
   const int64_t n4 = (n + 3) >> 2;
   if (step) offset += (uint64_t)step[0] << 32;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -454,7 +439,6 @@ __global__ void dropout_k(const float* __restrict__ x, float* __restrict__ y, in
 
 __global__ void copy2d_k(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int64_t rows,
                          int cols, int accumulate) {
-  pdl_prologue();
   const int64_t total = rows * cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols;
@@ -468,7 +452,6 @@ __global__ void copy2d_k(const float* __restrict__ src, int64_t lds, float* __re
 // one atomicAdd per column (out is zeroed first unless accumulating).
 __global__ void colsum_k(const float* __restrict__ x, int64_t ld, float* __restrict__ out, int64_t rows, int cols,
                          int64_t rows_per_block) {
-  pdl_prologue();
   __shared__ float part[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
@@ -493,7 +476,6 @@ __global__ void colsum_k(const float* __restrict__ x, int64_t ld, float* __restr
 // The generic 32x32 tile kernel below moves only 3 of its 32 tile rows for a clip (0.39 TB/s measured).
 __global__ void nc_to_cl4_k(const float* __restrict__ src, float4* __restrict__ dst, int C, int64_t inner4,
                             int64_t total, int tf32) {
-  pdl_prologue();
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t n = q / inner4, i4 = q - n * inner4;
     float4 p[4];
@@ -516,7 +498,6 @@ __global__ void nc_to_cl4_k(const float* __restrict__ src, float4* __restrict__ 
 
 __global__ void nc_to_cl_k(const float* __restrict__ src, float* __restrict__ dst, int C, int64_t inner, int Cpad,
                            int tf32) {
-  pdl_prologue();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int64_t i0 = (int64_t)blockIdx.x * 32;
@@ -538,7 +519,6 @@ __global__ void nc_to_cl_k(const float* __restrict__ src, float* __restrict__ ds
 }
 
 __global__ void cl_to_nc_k(const float* __restrict__ src, float* __restrict__ dst, int C, int64_t inner, int Cpad) {
-  pdl_prologue();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int64_t i0 = (int64_t)blockIdx.x * 32;
@@ -559,7 +539,6 @@ __global__ void cl_to_nc_k(const float* __restrict__ src, float* __restrict__ ds
 // wt[ci][tap][co] = w[co][tap][ci] * scale[co]
 __global__ void weight_transpose_k(const float* __restrict__ w, float* __restrict__ wt, const float* __restrict__ scale,
                                    int Co, int taps, int Ci) {
-  pdl_prologue();
   __shared__ float tile[32][33];
   const int tap = blockIdx.z;
   const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
@@ -581,7 +560,6 @@ __global__ void weight_transpose_k(const float* __restrict__ w, float* __restric
 
 // the same for every convolution of the net in one launch (block -> job by binary search over block_begin)
 __global__ void weight_transpose_multi_k(const vlfb_wt_job_t* __restrict__ jobs, int njobs) {
-  pdl_prologue();
   __shared__ float tile[32][33];
   int lo = 0, hi = njobs - 1;
   while (lo < hi) {
@@ -617,7 +595,6 @@ __device__ __forceinline__ float sce_elem(float x, float t) {
 
 __global__ void sigmoid_ce_fwd_k(const float* __restrict__ x, const int32_t* __restrict__ t, float* __restrict__ loss,
                                  int64_t n, float scale) {
-  pdl_prologue();
   __shared__ float red[32];
   float s = 0.f, cnt = 0.f;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
@@ -631,7 +608,6 @@ __global__ void sigmoid_ce_fwd_k(const float* __restrict__ x, const int32_t* __r
 
 __global__ void sigmoid_ce_bwd_k(const float* __restrict__ x, const int32_t* __restrict__ t,
                                  const float* __restrict__ dloss, float* __restrict__ dx, int64_t n, float scale) {
-  pdl_prologue();
   __shared__ float red[32];
   float cnt = 0.f;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) cnt += (t[i] != -1) ? 1.f : 0.f;
@@ -645,7 +621,6 @@ __global__ void sigmoid_ce_bwd_k(const float* __restrict__ x, const int32_t* __r
 
 __global__ void softmax_ce_fwd_k(const float* __restrict__ x, const int32_t* __restrict__ lab, float* __restrict__ prob,
                                  float* __restrict__ loss, int rows, int cols, float scale) {
-  pdl_prologue();
   __shared__ float red[32];
   float total = 0.f;
   for (int r = 0; r < rows; ++r) {
@@ -664,7 +639,6 @@ __global__ void softmax_ce_fwd_k(const float* __restrict__ x, const int32_t* __r
 
 __global__ void softmax_ce_bwd_k(const float* __restrict__ prob, const int32_t* __restrict__ lab, float* __restrict__ dx,
                                  int rows, int cols, float scale) {
-  pdl_prologue();
   const int64_t total = (int64_t)rows * cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols), c = (int)(i % cols);
@@ -675,7 +649,6 @@ __global__ void softmax_ce_bwd_k(const float* __restrict__ prob, const int32_t* 
 // ------------------------------------------------------------------ optimizer
 __global__ void sgd_k(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ pt, int64_t n,
                       const float* __restrict__ lrp, float mom, float wd, int nesterov) {
-  pdl_prologue();
   const float lr = lrp[0];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float pi = p[i], mi = m[i];
@@ -694,7 +667,6 @@ __global__ void sgd_k(float* __restrict__ p, float* __restrict__ g, float* __res
 __global__ void fbo_attend_fwd_k(const float* __restrict__ theta, const float* __restrict__ phi,
                                  const float* __restrict__ g, float* __restrict__ prob, float* __restrict__ y, int L,
                                  int d, float scale) {
-  pdl_prologue();
   extern __shared__ float sc[];
   __shared__ float red[32];
   const int r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -732,7 +704,6 @@ __global__ void fbo_attend_bwd_k(const float* __restrict__ theta, const float* _
                                  const float* __restrict__ g, const float* __restrict__ prob,
                                  const float* __restrict__ dy, float* __restrict__ dtheta, float* __restrict__ dphi,
                                  float* __restrict__ dg, int L, int d, float scale) {
-  pdl_prologue();
   extern __shared__ float ds[];   // L floats: dp then ds
   __shared__ float red[32];
   const int r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;

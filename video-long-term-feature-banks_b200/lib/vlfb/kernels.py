@@ -54,13 +54,32 @@ def _f32c(t, name='tensor'):
     return t
 
 
+# Per-call execution options of vlfb_gemm (vlfb_gemm_params_t.engine / tile_n / pair / stream_k): host-side settings of
+# THIS module, copied into every parameter block -- the library itself keeps no mutable state.
+_ENGINE = L.ENGINE_TCGEN05
+GEMM_OPTS = {'tile_n': 0, 'pair': 0, 'stream_k': 0}       # 0 = library default; tests / tuning scripts override
+_GEMM_WS = {}                                             # device index -> stream-K workspace tensor
+
+
 def set_gemm_backend(name):
     """'tcgen05' (default) or 'simt' (debug cross-check engine)."""
-    L.check(L.load().vlfb_set_gemm_backend({'tcgen05': 0, 'simt': 1}[name]), 'set_gemm_backend')
+    global _ENGINE
+    _ENGINE = {'tcgen05': L.ENGINE_TCGEN05, 'simt': L.ENGINE_SIMT}[name]
 
 
 def get_gemm_backend():
-    return ['tcgen05', 'simt'][L.load().vlfb_get_gemm_backend()]
+    return ['tcgen05', 'simt'][_ENGINE]
+
+
+def gemm_workspace(device):
+    """Stream-K scratch of vlfb_gemm (partial tiles + arrival counters): one zero-filled buffer per device, shared
+    by every launch (they are stream-ordered; the kernel leaves the counters zeroed)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    ws = _GEMM_WS.get(idx)
+    if ws is None:
+        ws = torch.zeros(int(L.load().vlfb_gemm_workspace_bytes()) // 4, dtype=torch.float32, device=device)
+        _GEMM_WS[idx] = ws
+    return ws
 
 
 # --------------------------------------------------------------------------- geometry
@@ -125,6 +144,11 @@ def _base_params(M, N, K, d, ldd, alpha=1.0):
     p.d_tap_stride = 0
     p.alpha = float(alpha)
     p.flags = 0
+    p.engine = _ENGINE
+    p.tile_n, p.pair, p.stream_k = GEMM_OPTS['tile_n'], GEMM_OPTS['pair'], GEMM_OPTS['stream_k']
+    ws = gemm_workspace(d.device)
+    p.workspace = ws.data_ptr()
+    p.workspace_bytes = ws.numel() * 4
     return p
 
 

@@ -30,7 +30,16 @@ class GemmParams(C.Structure):
                 ('d', C.c_void_p), ('ldd', C.c_int64), ('d_batch_stride', C.c_int64),
                 ('d_tap_stride', C.c_int64), ('alpha', C.c_float),
                 ('col_scale', C.c_void_p), ('col_bias', C.c_void_p), ('row_scale', C.c_void_p),
-                ('residual', C.c_void_p), ('relu_mask', C.c_void_p), ('flags', C.c_int)]
+                ('residual', C.c_void_p), ('relu_mask', C.c_void_p), ('flags', C.c_int),
+                ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
+                ('engine', C.c_int), ('tile_n', C.c_int), ('pair', C.c_int), ('stream_k', C.c_int)]
+
+
+class GemmPlan(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ('tile_n', 'split_k', 'pair', 'stream_k', 'tiles', 'units')]
+
+
+ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
 
 
 _P, _I, _L, _F, _U = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
@@ -40,13 +49,9 @@ _GP = C.POINTER(ConvGeom)
 SIGNATURES = {
     'vlfb_version': [],
     'vlfb_last_error': [],
-    'vlfb_set_gemm_backend': [_I],
-    'vlfb_get_gemm_backend': [],
-    'vlfb_set_pdl': [_I],
-    'vlfb_set_tile_widths': [_I],
-    'vlfb_get_tile_widths': [],
     'vlfb_gemm': [C.POINTER(GemmParams), _P],
-    'vlfb_gemm_plan': [C.POINTER(GemmParams), _I, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    'vlfb_gemm_plan': [C.POINTER(GemmParams), _I, C.POINTER(GemmPlan)],
+    'vlfb_gemm_workspace_bytes': [],
     'vlfb_affine_nd_fwd': [_P, _P, _P, _P, _L, _I, _P],
     'vlfb_affine_nd_bwd': [_P, _P, _P, _L, _I, _P],
     'vlfb_maxpool3d_fwd': [_P, _P, _P, _GP, _P],
@@ -90,7 +95,8 @@ SIGNATURES = {
     'vlfb_fbo_bank_scan': [_P, _P, _F, _P, _P, _I, _I, _I, _I, _P, C.c_size_t, _P],
     'vlfb_lfb_gather': [_P, _L, _P, _P, _L, _I, _I, _P],
 }
-RESTYPES = {'vlfb_last_error': C.c_char_p, 'vlfb_fbo_bank_scan_workspace': C.c_size_t}
+RESTYPES = {'vlfb_last_error': C.c_char_p, 'vlfb_fbo_bank_scan_workspace': C.c_size_t,
+            'vlfb_gemm_workspace_bytes': C.c_size_t}
 
 _lib = None
 
