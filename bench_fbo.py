@@ -112,8 +112,8 @@ def run_case(mode, R, L, layers, steps, warmup, peaks):
         workspace.RunNet(name)
     torch.cuda.synchronize()
     net = workspace.current().nets[name]
-    assert net._graphs is not None, 'the step should have been captured after the warm-up runs'
-    g1, g2, n1, n2 = net._graphs
+    assert len(net._graphs) == 1, 'the step should have been captured after the warm-up runs'
+    g1, g2, n1, n2 = list(net._graphs.values())[0][:4]
 
     def timed(fn):
         evs = []

@@ -1,0 +1,78 @@
+"""Device-time table of the production GEMM shapes under the tiling / schedule variants of vlfb_gemm
+(tile_n, pair = tcgen05 cta_group::2, stream_k).  Each entry = mean of `reps` back-to-back launches (CUDA events
+around the batch; operands stay L2-resident as they are inside a training step)."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'video-long-term-feature-banks_b200', 'lib'))
+from vlfb import kernels as K  # noqa: E402
+
+REPS = int(os.environ.get('REPS', '20'))
+VARIANTS = [('off', dict(pair=-1, stream_k=-1)), ('sk', dict(pair=-1, stream_k=1)), ('pair', dict(pair=1, stream_k=-1)),
+            ('pair+sk', dict(pair=1, stream_k=1)), ('pair128+sk', dict(pair=1, stream_k=1, tile_n=128)),
+            ('pair128', dict(pair=1, stream_k=-1, tile_n=128)), ('auto', dict())]
+# name, Ci, Co, kernel, pads, dilation, (N, T, H, W)
+CONVS = [
+    ('res5_2b 3x3 512->512', 512, 512, (1, 3, 3), (0, 2, 2), (1, 2, 2), (2, 16, 14, 14)),
+    ('res5_2a 3x1x1 2048->512', 2048, 512, (3, 1, 1), (1, 0, 0), (1, 1, 1), (2, 16, 14, 14)),
+    ('res5_2a 1x1 2048->512', 2048, 512, (1, 1, 1), (0, 0, 0), (1, 1, 1), (2, 16, 14, 14)),
+    ('res5_2c 1x1 512->2048', 512, 2048, (1, 1, 1), (0, 0, 0), (1, 1, 1), (2, 16, 14, 14)),
+    ('res4_2b 3x3 256->256', 256, 256, (1, 3, 3), (0, 1, 1), (1, 1, 1), (2, 16, 14, 14)),
+    ('res4_2a 3x1x1 1024->256', 1024, 256, (3, 1, 1), (1, 0, 0), (1, 1, 1), (2, 16, 14, 14)),
+    ('res4_2c 1x1 256->1024', 256, 1024, (1, 1, 1), (0, 0, 0), (1, 1, 1), (2, 16, 14, 14)),
+    ('res3_2b 3x3 128->128', 128, 128, (1, 3, 3), (0, 1, 1), (1, 1, 1), (2, 16, 28, 28)),
+    ('res3_2a 3x1x1 512->128', 512, 128, (3, 1, 1), (1, 0, 0), (1, 1, 1), (2, 16, 28, 28)),
+    ('res2_2b 3x3 64->64', 64, 64, (1, 3, 3), (0, 1, 1), (1, 1, 1), (2, 32, 56, 56)),
+    ('res2_2c 1x1 64->256', 64, 256, (1, 1, 1), (0, 0, 0), (1, 1, 1), (2, 32, 56, 56)),
+]
+
+
+def timed(fn):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(REPS):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / REPS * 1e3      # us
+
+
+def main():
+    only = sys.argv[1:] or None
+    print('%-28s %-6s' % ('layer', 'op') + ''.join('%12s' % n for n, _ in VARIANTS) + '   GFLOP   best TF/s')
+    for name, ci, co, ker, pd, dil, shp in CONVS:
+        if only and not any(o in name for o in only):
+            continue
+        g = K.conv_geom(shp + (ci,), co, ker, (1, 1, 1), pd, dil)
+        x = torch.randn(shp + (ci,), device='cuda')
+        w = torch.randn((co,) + ker + (ci,), device='cuda') * 0.05
+        taps = ker[0] * ker[1] * ker[2]
+        wt = torch.randn((ci, taps, co), device='cuda') * 0.05
+        s, b = torch.rand(co, device='cuda') + 0.5, torch.randn(co, device='cuda')
+        y = torch.empty(K.out_shape(g), device='cuda')
+        dy = torch.randn(K.out_shape(g), device='cuda')
+        dx = torch.empty(shp + (ci,), device='cuda')
+        dw = torch.zeros((co,) + ker + (ci,), device='cuda')
+        flop = 2.0 * y.numel() * taps * ci / 1e9
+        ops = [('fwd', lambda: K.conv_fwd(x, w, y, g, scale=s, bias=b, relu=True, tf32_out=True)),
+               ('dgrad', lambda: K.conv_dgrad(dy, wt, dx, g)),
+               ('wgrad', lambda: K.conv_wgrad(dy, x, dw, g, row_scale=s))]
+        for opname, fn in ops:
+            row = []
+            for _, opts in VARIANTS:
+                K.GEMM_OPTS.update(dict(tile_n=0, pair=0, stream_k=0))
+                K.GEMM_OPTS.update(opts)
+                row.append(timed(fn))
+            K.GEMM_OPTS.update(dict(tile_n=0, pair=0, stream_k=0))
+            print('%-28s %-6s' % (name, opname) + ''.join('%10.1fus' % t for t in row) +
+                  '  %6.1f  %8.1f' % (flop, flop / min(row) * 1e3), flush=True)
+
+
+if __name__ == '__main__':
+    main()

@@ -128,3 +128,76 @@ def test_kinetics_conversion_fold_inflate_and_classifier_rules(fake, tmp_path):
         pickle.dump(blobs, f, 2)
     with pytest.raises(Exception):
         CK.initialize_params_from_file(model, p2)
+
+
+def test_resume_rules_follow_the_reference(fake, tmp_path):
+    """load_model_from_params_file (reference lib/utils/checkpoints.py:180-230): cases 1, 2a, 2b, 3a, 3b, the
+    '<DIR>/checkpoints/c2_model_iter{N}.pkl' layout, no momentum from a pre-trained PARAMS_FILE, current_lr, and the
+    RESUME_FROM_BATCH_SIZE / RESET_START_ITER corrections."""
+    from oracle import model as OM
+    from utils import checkpoints as CK
+    from vlfb import workspace
+    from core.config import config as cfg
+    base = str(tmp_path)
+    ov = TINY + ['CHECKPOINT.DIR', base]
+    H.setup_cfg('ava_r50_lfb_nl.yaml', ov)
+    ocfg = H.oracle_cfg('ava_r50_lfb_nl.yaml', TINY)
+    params = OM.make_params(ocfg, seed=2)
+    inputs = OM.make_inputs(ocfg, n_clips=2, rois_per_clip=2, crop=64, frames=8)
+    model, sfx = H.build('train', True)
+    H.feed_params(params)
+    H.feed_inputs(inputs, sfx)
+    model.UpdateWorkspaceLr(10)
+    workspace.RunNet(model.net.Proto().name)
+    ckdir = CK.create_and_get_checkpoint_directory()
+    assert ckdir == os.path.join(os.path.abspath(base), 'checkpoints') and os.path.isdir(ckdir)
+    assert not CK.find_checkpoint() and CK.get_checkpoint_resume_file() is None
+    pre = os.path.join(base, 'pretrained.pkl')
+    CK.save_model_params(model, pre, 99)                                # "pre-trained" file: iter 100, has momentum
+    w_pre = workspace.FetchBlob('gpu_0/pred_w').copy()
+    workspace.RunNet(model.net.Proto().name)                            # train on: the checkpoints differ from it
+    CK.save_model_params(model, os.path.join(ckdir, 'c2_model_iter20.pkl'), 19)
+    workspace.RunNet(model.net.Proto().name)
+    CK.save_model_params(model, os.path.join(ckdir, 'c2_model_iter200.pkl'), 199)
+    w_200 = workspace.FetchBlob('gpu_0/pred_w').copy()
+    m_200 = workspace.FetchBlob('gpu_0/pred_w_momentum').copy()
+    assert CK.find_checkpoint() and CK.get_checkpoint_resume_file().endswith('c2_model_iter200.pkl')   # numeric, not lexical
+
+    def fresh(extra):
+        H.setup_cfg('ava_r50_lfb_nl.yaml', ov + extra)
+        workspace.ResetWorkspace()
+        m, _ = H.build('train', True)
+        return m
+
+    # case 2a / 3a: RESUME and a checkpoint exists -> the latest checkpoint wins over PARAMS_FILE, momentum restored
+    for extra in (['TRAIN.PARAMS_FILE', pre], []):
+        m = fresh(extra)
+        assert CK.load_model_from_params_file(m) == 200
+        assert np.allclose(workspace.FetchBlob('gpu_0/pred_w'), w_200, rtol=1e-6, atol=1e-10)
+        assert np.allclose(workspace.FetchBlob('gpu_0/pred_w_momentum'), m_200, rtol=1e-6, atol=1e-12)
+        assert abs(m.current_lr - float(workspace.FetchBlob('gpu_0/lr'))) < 1e-9
+    # case 1: RESUME False -> PARAMS_FILE, never its momentum; start iteration from the file
+    m = fresh(['TRAIN.PARAMS_FILE', pre, 'CHECKPOINT.RESUME', False])
+    assert CK.load_model_from_params_file(m) == 100
+    assert np.allclose(workspace.FetchBlob('gpu_0/pred_w'), w_pre, rtol=1e-6, atol=1e-10)
+    assert np.abs(workspace.FetchBlob('gpu_0/pred_w_momentum')).max() == 0
+    # ... rescaled when the file was trained with another batch size, zeroed by RESET_START_ITER
+    m = fresh(['TRAIN.PARAMS_FILE', pre, 'CHECKPOINT.RESUME', False, 'TRAIN.RESUME_FROM_BATCH_SIZE', 8])
+    assert CK.load_model_from_params_file(m) == int(100 * 8 / cfg.TRAIN.BATCH_SIZE)
+    m = fresh(['TRAIN.PARAMS_FILE', pre, 'CHECKPOINT.RESUME', False, 'TRAIN.RESET_START_ITER', True])
+    assert CK.load_model_from_params_file(m) == 0
+    # case 2b / 3b: RESUME but no checkpoint yet
+    empty = os.path.join(base, 'empty')
+    os.makedirs(empty)
+    m = fresh(['TRAIN.PARAMS_FILE', pre, 'CHECKPOINT.DIR', empty])
+    assert CK.load_model_from_params_file(m) == 100
+    m = fresh(['CHECKPOINT.DIR', empty])
+    pw = workspace.FetchBlob('gpu_0/pred_w').copy()
+    assert CK.load_model_from_params_file(m) == 0 and np.array_equal(workspace.FetchBlob('gpu_0/pred_w'), pw)
+    # a file from a differently named net loads nothing: that is an error, not a silent from-scratch run
+    bad = os.path.join(base, 'renamed.pkl')
+    with open(bad, 'wb') as f:
+        pickle.dump({'blobs': {'lr': 0.1, 'something_else_w': np.zeros((3, 3), np.float32)}}, f, 2)
+    m = fresh(['TRAIN.PARAMS_FILE', bad, 'CHECKPOINT.RESUME', False])
+    with pytest.raises(Exception):
+        CK.load_model_from_params_file(m)

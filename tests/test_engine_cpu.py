@@ -246,6 +246,30 @@ def test_inference_fbo_fold_matches_oracle_and_unfolded_graph(fake, yaml_name, l
         assert workspace.HasBlob('gpu_0/lfb_1x1') == (not fold)
 
 
+def test_fbo_fold_is_skipped_for_bank_widths_the_scan_kernel_lacks(fake):
+    """LFB.LFB_DIM = 512: vlfb_fbo_bank_scan only has 1024 / 2048 / 4096-float rows, so the test-mode graph must keep
+    the as-written Conv / BatchMatMul lowering (and still match the oracle) instead of failing at run time."""
+    from oracle import model as OM
+    from vlfb import workspace
+    from vlfb import executor as X
+    ov = TINY + ['LFB.LFB_DIM', 512]
+    ocfg = H.oracle_cfg('ava_r50_lfb_nl.yaml', ov)
+    params = OM.make_params(ocfg, seed=2, split='val')
+    inputs = OM.make_inputs(ocfg, n_clips=2, rois_per_clip=2, crop=64, frames=8)
+    assert inputs['lfb'].shape[-1] == 512
+    blobs, _, _ = OM.forward(ocfg, dict((k, v.double()) for k, v in params.items()),
+                             dict((k, (v.double() if v.dtype == torch.float32 else v)) for k, v in inputs.items()), 'val')
+    H.setup_cfg('ava_r50_lfb_nl.yaml', ov)
+    workspace.ResetWorkspace()
+    model, sfx = H.build('val', False)
+    H.feed_params(params)
+    H.feed_inputs(inputs, sfx)
+    net = workspace.current().nets[model.net.Proto().name]
+    assert not any(isinstance(s, X.FboFoldStep) for s in net.steps)
+    workspace.RunNet(model.net.Proto().name)
+    assert H.rel(workspace.FetchBlob('gpu_0/pred').reshape(-1), blobs['pred'].detach().numpy().reshape(-1)) < 1e-9
+
+
 def test_fetch_blob_async_equals_fetch_blob(fake):
     from vlfb import workspace
     _run('ava_r50_lfb_nl.yaml', TINY, fake, [])

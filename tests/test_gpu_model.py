@@ -176,7 +176,7 @@ def test_grad_finish_fusion_and_graph_replay_agree_with_first_run(ws):
             assert (X.STATS['fused_grad_finish'] - n0 > 40) == (rep == 1)
         runs.append(dict((n, ws.FetchBlob('gpu_0/' + n + '_grad').copy()) for n in model.TrainableParams()))
     X.FUSE_GRAD_FINISH, X.LAZY_GRAD_SUM = fuse0, lazy0
-    assert net._graphs is not None, 'the step should have been captured into a CUDA graph by now'
+    assert len(net._graphs) == 1, 'the step should have been captured into a CUDA graph by now'
     for rep in (1, 2, 3):
         worst = max(float(np.abs(runs[rep][n] - runs[0][n]).max() / (np.abs(runs[0][n]).max() + 1e-12)) for n in runs[0])
         print('run %d vs run 0: worst gradient difference %.2e' % (rep, worst))
@@ -323,3 +323,53 @@ def test_sgd_step_and_determinism_of_forward(ws):
         assert np.linalg.norm(step_gpu - step_ref) / np.linalg.norm(step_ref) < 0.15, name
     assert np.array_equal(ws.FetchBlob('gpu_0/res2_0_branch2a_bn_s'), params['res2_0_branch2a_bn_s'].numpy())
     assert not np.array_equal(a, 0 * a)
+
+
+def test_graph_replay_rebinds_its_blobs_after_another_net_ran(ws):
+    """ws.blobs is shared by all nets.  Net A (train) is captured; net B (the test net on other inputs) then runs and
+    rebinds 'pred', 'pool5', 'box_pooled', ...; a replay of A must hand FetchBlob ITS tensors again.  Also: a second
+    input signature (another RoI count) gets its own cached graph instead of evicting the first."""
+    from oracle import model as OM
+    H.setup_cfg('ava_r50_lfb_nl.yaml', TINY)
+    ocfg = H.oracle_cfg('ava_r50_lfb_nl.yaml', TINY)
+    params = OM.make_params(ocfg, seed=2)
+    model_a, sfx_a = H.build('train', True)
+    model_b, sfx_b = H.build('test', False)
+    H.feed_params(params)
+    name_a, name_b = model_a.net.Proto().name, model_b.net.Proto().name
+    net_a = ws.current().nets[name_a]
+    net_a.update_ops = []                                   # keep the weights fixed: every run of A is the same function
+    in_a = OM.make_inputs(ocfg, n_clips=2, rois_per_clip=2, crop=64, frames=8, seed=70)
+    in_a2 = OM.make_inputs(ocfg, n_clips=2, rois_per_clip=3, crop=64, frames=8, seed=71)
+    in_b = OM.make_inputs(ocfg, n_clips=2, rois_per_clip=2, crop=64, frames=8, seed=72)
+    H.feed_inputs(in_a, sfx_a)
+    ws.RunNet(name_a)
+    torch.cuda.synchronize()
+    want = dict((n, ws.FetchBlob('gpu_0/' + n).copy()) for n in ('pred', 'pool5', 'box_pooled', 'loss'))
+    for _ in range(3):
+        ws.RunNet(name_a)
+    assert len(net_a._graphs) == 1
+    H.feed_inputs(in_b, sfx_b)
+    ws.RunNet(name_b)                                       # rebinds the shared output names
+    torch.cuda.synchronize()
+    other = ws.FetchBlob('gpu_0/pred').copy()
+    H.feed_inputs(in_a, sfx_a)
+    ws.RunNet(name_a)                                       # replay of the captured step
+    torch.cuda.synchronize()
+    for n, v in want.items():
+        got = ws.FetchBlob('gpu_0/' + n)
+        assert np.allclose(got, v, rtol=1e-5, atol=1e-6), n
+    assert not np.allclose(other, want['pred'], rtol=1e-3, atol=1e-5), 'net B should have produced different predictions'
+    # a second signature: captured next to the first, both replay correctly afterwards
+    H.feed_inputs(in_a2, sfx_a)
+    for _ in range(4):
+        ws.RunNet(name_a)
+    torch.cuda.synchronize()
+    assert len(net_a._graphs) == 2
+    pred2 = ws.FetchBlob('gpu_0/pred').copy()
+    assert pred2.shape[0] == 6
+    H.feed_inputs(in_a, sfx_a)
+    ws.RunNet(name_a)
+    torch.cuda.synchronize()
+    assert np.allclose(ws.FetchBlob('gpu_0/pred'), want['pred'], rtol=1e-5, atol=1e-6)
+    assert len(net_a._graphs) == 2

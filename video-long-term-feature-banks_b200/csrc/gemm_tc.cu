@@ -1230,7 +1230,7 @@ static bool make_tmap_im2col(CUtensorMap* tm, const float* base, int N, int D, i
 }
 
 // tuning overrides, read once (scripts/tune_gemm.py); the per-call fields of vlfb_gemm_params_t take precedence
-struct Env { int bn, stages, lag, fence, pair, sk; bool tma_mn, im2col; };
+struct Env { int bn, stages, lag, fence, pair, sk, debug; bool tma_mn, im2col; };
 static Env read_env() {
   Env e;
   auto geti = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
@@ -1240,6 +1240,7 @@ static Env read_env() {
   e.fence = geti("VLFB_FENCE", 0);
   e.pair = geti("VLFB_PAIR", 0);
   e.sk = geti("VLFB_SK", 0);
+  e.debug = geti("VLFB_DEBUG", 0);
   e.tma_mn = geti("VLFB_TMA_MN", 1) != 0;
   e.im2col = geti("VLFB_IM2COL", 1) != 0;
   return e;
@@ -1486,6 +1487,9 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
   }
   const int smem = L.stages * stage_bytes + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   const bool cp = !(L.tma_a && L.tma_b);
+  if (ev.debug)
+    fprintf(stderr, "vlfb gemm_tc: kinds %d,%d M=%d N=%d K=%d z=%d | bn=%d pair=%d sk=%d split=%d tiles=%d units=%d stages=%d tma=%d,%d cap=%d\n",
+            AK, BK, p.M, p.N, p.K, zbase, L.bn, plan.pair, L.sk, p.split_k, L.total_tiles, units, L.stages, L.tma_a, L.tma_b, cap);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(plan.pair ? 2 * units : units));
   cfg.blockDim = dim3((unsigned)((cp ? NPROD : 32) + 32 + NEPI));

@@ -75,7 +75,7 @@ def load_and_convert_caffe2_cls_model(model_file_name):
 def convert_model(model_path, out_dir=None):
     """Kinetics-pretrained classification model -> initialisation file: classifier and momentum dropped,
     lr = 0.00125 recorded (reference :145-177).  Returns the path of 'converted_model.pkl'."""
-    out_dir = out_dir or get_checkpoint_directory()
+    out_dir = out_dir or create_and_get_checkpoint_directory()
     blobs = load_and_convert_caffe2_cls_model(model_path)['blobs']
     for name in list(blobs.keys()):
         if 'pred' in name or 'momentum' in name:
@@ -88,9 +88,38 @@ def convert_model(model_path, out_dir=None):
 
 
 def get_checkpoint_directory():
-    d = cfg.CHECKPOINT.DIR if 'CHECKPOINT' in cfg and cfg.CHECKPOINT.get('DIR') else '.'
+    """<CHECKPOINT.DIR>/checkpoints (reference :233-238)."""
+    if cfg.CHECKPOINT.DIR:
+        return os.path.abspath(os.path.join(cfg.CHECKPOINT.DIR, 'checkpoints'))
+    raise Exception('No cfg.CHECKPOINT.DIR specified.')
+
+
+def create_and_get_checkpoint_directory():
+    d = get_checkpoint_directory()
     os.makedirs(d, exist_ok=True)
     return d
+
+
+def _checkpoint_iters():
+    d = get_checkpoint_directory()
+    if not os.path.isdir(d):
+        return []
+    its = []
+    for f in os.listdir(d):
+        if f.endswith('.pkl') and f.startswith('c2_model_iter'):
+            its.append(int(f[len('c2_model_iter'):-len('.pkl')]))
+    return sorted(its)
+
+
+def find_checkpoint():
+    """True when <dir>/c2_model_iter*.pkl exists (reference :73-82)."""
+    return bool(_checkpoint_iters())
+
+
+def get_checkpoint_resume_file():
+    """The latest c2_model_iter{N}.pkl, or None (reference :50-70)."""
+    its = _checkpoint_iters()
+    return os.path.join(get_checkpoint_directory(), 'c2_model_iter{}.pkl'.format(its[-1])) if its else None
 
 
 # ---- loading --------------------------------------------------------------------------------------------------------
@@ -136,16 +165,28 @@ def initialize_master_gpu_model_params(model, weights_file, load_momentum=True):
         wanted[_unscope(p)] = True
     store = workspace.current().params
     root = 'gpu_{}/'.format(cfg.ROOT_GPU_ID)
+    loaded, missing = 0, []
     for name in wanted:
         if name not in blobs:
             logger.info('%s not found', name)
+            if not name.endswith('_momentum') and 'pred' not in name:
+                missing.append(name)
             continue
         base = name[:-len('_momentum')] if name.endswith('_momentum') else name
-        if not store.has(base):
-            continue
-        value = _fit_to_workspace(name, blobs[name], store.logical_shape(base))
-        if value is not None:
-            workspace.FeedBlob(root + name, value)
+        if store.has(base):
+            value = _fit_to_workspace(name, blobs[name], store.logical_shape(base))
+            if value is None:
+                continue
+        else:
+            value = np.asarray(blobs[name]).astype(np.float32, copy=False)     # the reference feeds it anyway
+        workspace.FeedBlob(root + name, value)
+        loaded += 1
+    if missing:
+        # a mis-built net (renamed layers) would otherwise "load" a checkpoint and silently train from scratch
+        logger.warning('%d of %d model parameters are absent from %s (first: %s)', len(missing), len(wanted),
+                       weights_file, ', '.join(missing[:5]))
+    if wanted and loaded == 0:
+        raise Exception('none of the model parameters was found in {}'.format(weights_file))
     workspace.FeedBlob(root + 'lr', np.array(prev_lr, dtype=np.float32))
     return model_iter, prev_lr
 
@@ -168,13 +209,37 @@ def load_model_from_params_file_for_test(model, weights_file):
     initialize_params_from_file(model=model, weights_file=weights_file)
 
 
+def resume_from(start_model_iter):
+    """Iteration count of a run trained with another batch size (reference lib/utils/misc.py resume_from)."""
+    assert cfg.TRAIN.RESUME_FROM_BATCH_SIZE > 0
+    return int(start_model_iter * cfg.TRAIN.RESUME_FROM_BATCH_SIZE / cfg.TRAIN.BATCH_SIZE)
+
+
 def load_model_from_params_file(model):
-    """Resume / initialise as tools/train_net.py does (reference :180-214): returns (start_model_iter, prev_lr)."""
-    params_file = cfg.TRAIN.PARAMS_FILE if cfg.TRAIN.get('PARAMS_FILE') else ''
-    if not params_file:
-        return 0, None
-    model_iter, prev_lr = initialize_params_from_file(model, params_file, load_momentum=not cfg.TRAIN.RESET_START_ITER)
-    return (0 if cfg.TRAIN.RESET_START_ITER else model_iter), prev_lr
+    """Resume / initialise as tools/train_net.py does (reference :180-230).  Returns start_model_iter (int).
+      case 0  CHECKPOINT.CONVERT_MODEL: convert TRAIN.PARAMS_FILE (BN -> Affine, classifier dropped) first
+      case 1  RESUME False, PARAMS_FILE set: load it (never its momentum)
+      case 2  RESUME True,  PARAMS_FILE set: latest c2_model_iter*.pkl if one exists, else PARAMS_FILE
+      case 3  RESUME True,  no PARAMS_FILE : latest checkpoint if one exists, else start from scratch (0)"""
+    use_checkpoint = bool(cfg.CHECKPOINT.RESUME) and find_checkpoint()
+    if cfg.TRAIN.PARAMS_FILE and cfg.CHECKPOINT.CONVERT_MODEL:
+        assert cfg.MODEL.USE_AFFINE, 'a converted model uses affine layers'
+        cfg.TRAIN.PARAMS_FILE = convert_model(cfg.TRAIN.PARAMS_FILE)
+    if cfg.TRAIN.PARAMS_FILE and not use_checkpoint:
+        start_model_iter, prev_lr = initialize_params_from_file(model=model, weights_file=cfg.TRAIN.PARAMS_FILE,
+                                                                load_momentum=False)
+        model.current_lr = prev_lr
+        if cfg.TRAIN.RESUME_FROM_BATCH_SIZE > 0:
+            start_model_iter = resume_from(start_model_iter)
+        if cfg.TRAIN.RESET_START_ITER:
+            start_model_iter = 0
+    elif use_checkpoint:
+        start_model_iter, prev_lr = initialize_params_from_file(model=model, weights_file=get_checkpoint_resume_file())
+        model.current_lr = prev_lr
+    else:
+        start_model_iter = 0
+        logger.info('No checkpoint found; training from scratch...')
+    return int(start_model_iter)
 
 
 # ---- saving ---------------------------------------------------------------------------------------------------------

@@ -13,8 +13,8 @@ Representation
   * every tensor that feeds a tensor-core GEMM is rounded to TF32 (round-to-nearest) by its
     producer, because kind::tf32 MMAs truncate fp32 operands.
 """
+import collections
 import math
-
 import os
 
 import torch
@@ -25,7 +25,6 @@ K = K_default          # tests may swap in a torch-CPU kernel set (tests/fake_ke
 DEVICE = 'cuda'
 DTYPE = torch.float32      # the CUDA kernels are fp32-only; the CPU test stand-in may run the host logic in fp64
 STATS = {'fused_grad_finish': 0}
-SIDE_WGRAD = os.environ.get('VLFB_SIDE_WGRAD', '0') == '1'         # weight-gradient GEMMs on a second stream (experiment)
 LAZY_GRAD_SUM = os.environ.get('VLFB_LAZY_GRAD_SUM', '1') != '0'   # defer residual + dgrad sums into the consumer's mask/round pass
 # Fold the ReLU backward + TF32 rounding of a conv's incoming gradient (and the sum of its earlier contributions)
 # into the epilogue of the dgrad GEMM that delivers the last contribution.  Exact (tests run both ways), but OFF by
@@ -130,21 +129,7 @@ class Ctx(object):
         # lazy two-term sums: grads[key] (owned) + pending[key] (an alias of somebody else's gradient, e.g. the
         # residual branch).  A conv that owns `key` folds the sum into its ReLU-backward / rounding pass.
         self.pending = {}
-        self.keepalive = []
-
-    def side_stream(self):
-        if not SIDE_WGRAD or DEVICE == 'cpu':
-            return None
-        if self.net._side is None:
-            self.net._side = torch.cuda.Stream()
-        return self.net._side
-
-    def join_side(self):
-        if self.net._side is not None and self.keepalive:
-            ev = torch.cuda.Event()
-            ev.record(self.net._side)
-            torch.cuda.current_stream().wait_event(ev)
-        self.keepalive = []
+        self.bound = {}          # blob name -> rounded flag of everything this run bound (re-installed after a graph replay)
 
     # ---- blobs
     def get(self, name):
@@ -152,6 +137,7 @@ class Ctx(object):
 
     def put(self, name, t, rounded=False):
         self.ws.blobs[name] = t
+        self.bound[name] = bool(rounded)
         if rounded:
             self.ws.rounded.add(name)
         else:
@@ -311,18 +297,7 @@ class ConvStep(Step):
         store = ctx.ws.params
         if store.trainable(self.w):
             mask = store.stem_mask() if g.C == 4 else None
-            side = ctx.side_stream()
-            if side is None:
-                K.conv_wgrad(gp, xp, store.grad(self.w), g, row_scale=scale, col_mask=mask)
-            else:
-                # the weight gradient is off the critical path (nothing in backward reads it): run it on a second
-                # stream next to the dgrad chain so that its CTAs fill the SMs the small-M layers leave idle
-                ev = torch.cuda.Event()
-                ev.record()
-                side.wait_event(ev)
-                with torch.cuda.stream(side):
-                    K.conv_wgrad(gp, xp, store.grad(self.w), g, row_scale=scale, col_mask=mask)
-                ctx.keepalive.extend([gp, xp])        # no reuse of these blocks before the join
+            K.conv_wgrad(gp, xp, store.grad(self.w), g, row_scale=scale, col_mask=mask)
         if self.b and store.trainable(self.b):
             db = store.grad(self.b)
             rows = gp.numel() // g.Co
@@ -519,7 +494,7 @@ class ReshapeStep(Step):
         y = x.view(shape)        # metadata only; raises if a copy would be needed
         ctx.put(self.op.outputs[0], y, rounded=self.op.inputs[0] in ctx.ws.rounded)
         if len(self.op.outputs) > 1:
-            ctx.ws.blobs[self.op.outputs[1]] = tuple(x.shape)
+            ctx.put(self.op.outputs[1], tuple(x.shape))
         ctx.saved[id(self)] = tuple(x.shape)
 
     def bwd(self, ctx):
@@ -894,7 +869,6 @@ class CompiledNet(object):
         self.wt_buffers = {}         # id(ConvStep) -> persistent [Ci][taps][Co] dgrad weight operand
         self._wt_jobs = None
         self._wt_cache = {}
-        self._side = None
         produced = set()
         self.external_inputs = []
         for op in ops:
@@ -902,10 +876,8 @@ class CompiledNet(object):
                 if n not in produced and n not in self.external_inputs and n not in model.params:
                     self.external_inputs.append(n)
             produced.update(op.outputs)
-        self._graphs = None
-        self._graph_key = None
-        self._eager_key = None
-        self._eager_runs = 0
+        self._graphs = collections.OrderedDict()     # input signature -> captured step (LRU)
+        self._eager_runs = {}                        # input signature -> eager runs so far (two before capture)
 
     # ---- SSA-style versioning of in-place blobs
     def _version(self, ops):
@@ -945,6 +917,10 @@ class CompiledNet(object):
 
         for i, c1 in enumerate(ops):
             if i in consumed or not pointwise(c1) or c1.outputs[0] in self.losses:
+                continue
+            # the bank-scan kernel handles rows of 1024 / 2048 / 4096 floats (csrc/fbo.cu); any other LFB_DIM keeps the
+            # as-written Conv / BatchMatMul lowering, which works for every width
+            if self.ws.params.has(c1.inputs[1]) and int(self.ws.params.logical_shape(c1.inputs[1])[1]) not in (1024, 2048, 4096):
                 continue
             users = self.consumers.get(self.out_keys[i][0], [])
             if len(users) < 2 or len(users) % 2 or not all(pointwise(ops[j]) and j not in consumed for j in users):
@@ -1096,8 +1072,9 @@ class CompiledNet(object):
 
     # ---- execution
     def _input_key(self):
-        """Shapes + addresses of every external input: a captured graph is only valid for these."""
-        key = []
+        """Shapes + addresses of every external input and the run-mode switches the lowering reads: a captured
+        graph is only valid for these."""
+        key = [('dropout', bool(self.ws.dropout_enabled))]
         for name in self.external_inputs:
             t = self.ws.blobs.get(name)
             if isinstance(t, torch.Tensor):
@@ -1120,7 +1097,6 @@ class CompiledNet(object):
                 st.bwd(ctx)
             elif any(k in ctx.grads for k in st.out_keys):
                 st.bwd(ctx)
-        ctx.join_side()
         if self.contrib is None:
             self.contrib = dict(ctx.counts)
         else:
@@ -1147,32 +1123,32 @@ class CompiledNet(object):
         if self._wt_jobs:
             K.weight_transpose_multi(self._wt_jobs, self._wt_cache)
 
+    MAX_GRAPHS = 4          # captured steps kept per net (each owns its activation memory): LRU over input signatures
+
     def run(self):
         """One pass.  Eager for the first runs of a given input signature; after that the whole
         step (forward + backward [+ SGD]) is replayed from a captured CUDA graph, which removes the
-        per-launch host cost of the ~700 kernels of a step.  The gradient all-reduce (N > 1) stays
-        eager between the two captured halves."""
+        per-launch host cost of the ~600 kernels of a step.  The gradient all-reduce (N > 1) stays
+        eager between the two captured halves.  Graphs are cached per input signature (e.g. per RoI count)."""
         from core.config import config as cfg
         ws = self.ws
         ws.begin_run()
         use_graph = (DEVICE != 'cpu' and cfg.B200.CUDA_GRAPH and not ws.force_eager and K is K_default)
         key = self._input_key() if use_graph else None
-        if use_graph and self._graphs is not None and self._graph_key == key:
-            g1, g2, n1, n2 = self._graphs
-            g1.replay()
-            K.LAUNCHES += n1
-            if self.train and ws.allreduce is not None:
-                ws.allreduce(ws.params)
-            if g2 is not None:
-                g2.replay()
-                K.LAUNCHES += n2
-            return
-        if use_graph and self._eager_key == key and self._eager_runs >= 2:
-            self._capture(key)
-            return self.run_replay_after_capture()
-        if self._eager_key != key:
-            self._eager_key, self._eager_runs = key, 0
-        self._eager_runs += 1
+        if use_graph:
+            entry = self._graphs.get(key)
+            if entry is not None:
+                self._graphs.move_to_end(key)
+                return self._replay(entry)
+            if self._eager_runs.get(key, 0) >= 2:
+                entry = self._capture()
+                self._graphs[key] = entry
+                while len(self._graphs) > self.MAX_GRAPHS:
+                    self._graphs.popitem(last=False)
+                return self._replay(entry)
+            self._eager_runs[key] = self._eager_runs.get(key, 0) + 1
+            while len(self._eager_runs) > 4 * self.MAX_GRAPHS:
+                self._eager_runs.pop(next(iter(self._eager_runs)))
         ctx = Ctx(ws, self)
         self._forward_backward(ctx)
         if not self.train:
@@ -1182,7 +1158,11 @@ class CompiledNet(object):
         if self.update_ops:
             self._update(ws.params)
 
-    def _capture(self, key):
+    def _capture(self):
+        """Capture the step for the current input signature.  Returns (g1, g2, n1, n2, written, rounded): `written`
+        = every blob the captured run bound (tensors and shape tuples), `rounded` = which of them are TF32-rounded;
+        both are re-installed after every replay, because ws.blobs is shared by all nets and an eager run of another
+        net (or of this one with another signature) rebinds the same names in between."""
         ws = self.ws
         torch.cuda.synchronize()
         split = self.train and ws.allreduce is not None
@@ -1201,18 +1181,23 @@ class CompiledNet(object):
                 self._update(ws.params)
             n2 = K.LAUNCHES - n0 - n1
         K.LAUNCHES = n0
-        self._graphs = (g1, g2, n1, n2)
-        self._graph_key = key
+        written = dict((k, ws.blobs[k]) for k in ctx.bound)
+        rounded = set(k for k, r in ctx.bound.items() if r)
+        return (g1, g2, n1, n2, written, rounded)
 
-    def run_replay_after_capture(self):
-        g1, g2, n1, n2 = self._graphs
+    def _replay(self, entry):
+        g1, g2, n1, n2, written, rounded = entry
+        ws = self.ws
         g1.replay()
         K.LAUNCHES += n1
-        if self.train and self.ws.allreduce is not None:
-            self.ws.allreduce(self.ws.params)
+        if self.train and ws.allreduce is not None:
+            ws.allreduce(ws.params)
         if g2 is not None:
             g2.replay()
             K.LAUNCHES += n2
+        ws.blobs.update(written)
+        ws.rounded.difference_update(written)
+        ws.rounded.update(rounded)
 
     def _update(self, store):
         from core.config import config as cfg
