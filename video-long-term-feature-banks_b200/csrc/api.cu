@@ -97,6 +97,11 @@ int vlfb_gemm_plan(const vlfb_gemm_params_t* p, int num_sms, vlfb_gemm_plan_t* p
 
 size_t vlfb_gemm_workspace_bytes(void) { return gemm_tc_workspace_bytes(); }
 
+#ifdef VLFB_TRACE
+/* diagnostic build only (libvlfb_trace.so, scripts/trace_gemm.py): device buffer of 64 x gridDim clock64 slots */
+int vlfb_debug_set_trace(void* buf) { vlfb::gemm_tc_set_trace(buf); return VLFB_OK; }
+#endif
+
 int vlfb_gemm(const vlfb_gemm_params_t* p, void* stream) {
   VLFB_CHECK_ARG(p != nullptr);
   bool tc_ok = true;

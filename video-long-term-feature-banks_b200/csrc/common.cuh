@@ -149,5 +149,8 @@ int gemm_simt(const vlfb_gemm_params_t& p, cudaStream_t stream);
 int gemm_tc(const vlfb_gemm_params_t& p, cudaStream_t stream);
 void gemm_tc_plan(const vlfb_gemm_params_t& p, int num_sms, vlfb_gemm_plan_t* out);
 size_t gemm_tc_workspace_bytes();
+#ifdef VLFB_TRACE
+void gemm_tc_set_trace(void* buf);
+#endif
 
 }  // namespace vlfb

@@ -198,6 +198,9 @@ __device__ __forceinline__ void tma_load_3d_2(uint32_t dst, const CUtensorMap* t
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void red_add_f4(float* p, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ float4 ld_cg_f4(const float* p) {
   float4 v;
   asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
@@ -553,6 +556,16 @@ struct MNLoader {
 };
 
 // ---------------------------------------------------------------- the kernel
+// Timeline instrumentation of the diagnostic build (-DVLFB_TRACE, scripts/trace_gemm.py): per CTA 64 clock64 slots.
+//   0 entry, 1 globaltimer at entry, 2 prologue done, 3 exit; producer 8+2i / 9+2i = work item i first / last copy issued;
+//   MMA 16+2i first chunk landed, 17+2i last MMA issued; epilogue warp 0: 24+4i accumulator ready, 25+4i blocks done,
+//   26+4i piece counted, 27+4i fix-up done.
+#ifdef VLFB_TRACE
+unsigned long long* g_trace_buf = nullptr;
+#define TR(slot) do { if (L.trace) L.trace[(size_t)blockIdx.x * 64 + (slot)] = (unsigned long long)clock64(); } while (0)
+#else
+#define TR(slot) do { } while (0)
+#endif
 constexpr int MAX_UNITS = 160;       // >= #SMs: CTAs (or CTA pairs) of the persistent grid
 constexpr int SK_CNT_INTS = 16384;   // arrival counters at the head of the stream-K workspace (tile x rank x epilogue warp)
 
@@ -566,7 +579,6 @@ struct Launch {
   int tma_a, tma_b;  // operand fetched by TMA instead of cp.async: 1 = dense tiled boxes, 2 = im2col (conv gathers)
   int lag;           // cp.async groups kept in flight before a stage is published (< stages)
   int tiles_m, tiles_n, total_tiles;
-  int fence_mode;    // 0: producers fence.proxy.async before publishing a stage; 1: the MMA thread fences after acquiring it
   int tile_rows;     // output rows per tile: 128, or 256 when a CTA pair shares the tile (cta_group::2)
   // Stream-K: the linear space (tile, K chunk) is cut into one contiguous range per unit (CTA or CTA pair), so every
   // SM gets the same number of chunks whatever the tile count.  A tile whose chunks span several units is reduced
@@ -575,6 +587,7 @@ struct Launch {
   int nkt;           // K chunks per tile
   float* ws_tiles;   // partial-sum slots: [unit][2][rank][128][bn]
   int* ws_cnt;       // arrival counters [tile][rank][epilogue warp], zero between launches
+  unsigned long long* trace;   // diagnostic build only
   int bounds[MAX_UNITS + 1];
 };
 
@@ -690,6 +703,14 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
   const bool tma_a = L.tma_a != 0, tma_b = L.tma_b != 0;
   const bool cp_any = CP && !(tma_a && tma_b);
 
+#ifdef VLFB_TRACE
+  if (tid == 0 && L.trace) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    L.trace[(size_t)blockIdx.x * 64 + 1] = gt;
+    TR(0);
+  }
+#endif
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full0 + 8 * s, (cp_any ? NPROD : 0) + ((tma_a || tma_b) ? 1 : 0));
@@ -710,6 +731,7 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
   if (PAIR) cluster_sync_all(); else __syncthreads();     // PAIR: the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem = *tptr_generic;
+  if (tid == 0) TR(2);
 
   if (warp < NPWT) {
     // ============================ PRODUCERS (8 warps; TMA: one thread) ============================
@@ -744,7 +766,9 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
       Sched sc;
       sched_init(sc, L, unit);
       TileInfo ti;
+      int witem = 0;
       while (sched_next(p, L, sc, unit, nunits, rank, ti)) {
+        if (tid == 0 && witem < 4) TR(8 + 2 * witem);
         const int nb0 = ti.n0 + rank * bnh;              // first D column whose B rows this CTA stages
         if (cp_any) {
           if (!tma_a) { if (is_mn(AK)) ma.init(p, p.a, ti.m0, BM, p.M, ti.batch, ti.tap, L.cdiv, L.kwdiv); else { ka.init(p, p.a, ti.m0, BM, p.M, ti.batch, L.out, L.in, ti.k_begin / KC); ka.kend = ti.k_end; } }
@@ -848,11 +872,13 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
           cp_async_commit();
           if (it >= LAG) {
             cp_async_wait_dyn(LAG);
-            if (L.fence_mode == 0) fence_proxy_async();
+            fence_proxy_async();
             mbar_arrive(full0 + 8 * sl);
             if (++sl == S) sl = 0;
           }
         }
+        if (tid == 0 && witem < 4) TR(9 + 2 * witem);
+        ++witem;
       }
       if (cp_any) {
         cp_async_wait<0>();
@@ -867,6 +893,14 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
     // ============================ MMA ISSUER (1 thread; PAIR: the leader CTA's) ============================
     if ((tid & 31) == 0 && rank == 0) {
       const uint32_t idesc = make_idesc(bn, is_mn(AK) ? 1 : 0, is_mn(BK) ? 1 : 0, PAIR ? 2 * BM : BM);
+      // K-major tile: SWIZZLE_128B, LBO 16, SBO 1024, K step 32 B; MN-major: SWIZZLE_128B_BASE32B, LBO 4096, SBO 512,
+      // K step 1024 B (4 k-rows of 128 B per 32-element atom)
+      const uint64_t a_d0 = is_mn(AK) ? make_desc(smem_base, 4096, 512, 1) : make_desc(smem_base, 16, 1024);
+      const uint64_t b_d0 = is_mn(BK) ? make_desc(smem_base + A_TILE_BYTES, 4096, 512, 1) : make_desc(smem_base + A_TILE_BYTES, 16, 1024);
+      const uint32_t a_hi = (uint32_t)(a_d0 >> 32), b_hi = (uint32_t)(b_d0 >> 32);
+      const uint32_t a_lo0 = (uint32_t)a_d0, b_lo0 = (uint32_t)b_d0;
+      const uint32_t stage_units = stage_bytes >> 4;
+      constexpr uint32_t a_kstep = is_mn(AK) ? (1024u >> 4) : (32u >> 4), b_kstep = is_mn(BK) ? (1024u >> 4) : (32u >> 4);
       int it = 0, tile_iter = 0, s = 0;
       uint32_t ph = 0;
       Sched sc;
@@ -881,17 +915,16 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
         const uint32_t d_tmem = tmem + (uint32_t)(acc * bn);
         for (int i = 0; i < ti.nk; ++i, ++it) {
           mbar_wait(full0 + 8 * s, ph);
-          if (L.fence_mode == 1) fence_proxy_async();
+          if (i == 0 && tile_iter < 4) TR(16 + 2 * tile_iter);
           tc_fence_after();
-          const uint32_t a_tile = smem_base + s * stage_bytes;
-          const uint32_t b_tile = a_tile + A_TILE_BYTES;
+          // descriptors of the stage: only the 14-bit start-address field moves (by stage, then by the 32-byte /
+          // 1024-byte K step of a K-major / MN-major tile), so each MMA costs one 32-bit add per operand instead of
+          // re-encoding the descriptor (trace r2b: the issue loop, not the tensor pipe, paced tiles narrower than 256)
+          const uint32_t a_lo = a_lo0 + (uint32_t)s * stage_units, b_lo = b_lo0 + (uint32_t)s * stage_units;
 #pragma unroll
           for (int j = 0; j < KC / 8; ++j) {          // UMMA K = 8 for tf32
-            uint64_t da, db;
-            if (!is_mn(AK)) da = make_desc(a_tile + j * 32, 16, 1024);
-            else da = make_desc(a_tile + j * 1024, 4096, 512, 1);
-            if (!is_mn(BK)) db = make_desc(b_tile + j * 32, 16, 1024);
-            else db = make_desc(b_tile + j * 1024, 4096, 512, 1);
+            const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)j * a_kstep);
+            const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)j * b_kstep);
             if (PAIR) umma_tf32_2(d_tmem, da, db, idesc, (i | j) ? 1u : 0u);
             else umma_tf32(d_tmem, da, db, idesc, (i | j) ? 1u : 0u);
           }
@@ -901,6 +934,7 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
         }
         // accumulator complete -> epilogue (PAIR: of both CTAs)
         if (PAIR) umma_commit2(tfull0 + 8 * acc); else umma_commit(tfull0 + 8 * acc);
+        if (tile_iter < 4) TR(17 + 2 * tile_iter);
         ++tile_iter;
       }
     }
@@ -1024,6 +1058,7 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
         if (mode != 2) {
           mbar_wait(tfull0 + 8 * acc, (tile_iter >> 1) & 1);
           tc_fence_after();
+          if (ew == 0 && lane == 0 && tile_iter < 4) TR(24 + 4 * tile_iter);
         }
         for (int c0 = half * EPC; c0 < bn; c0 += 2 * EPC) {
           if (ti.n0 + c0 >= p.N) break;            // warp-uniform
@@ -1107,14 +1142,140 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
           }
         }
       };
+      // The same pass, lean: for tiles whose rows are 16-byte addressable and whose N extent is a whole number of
+      // 16-column blocks (every layer of the networks).  run_blocks spends ~830 instructions per 32 x 16 block
+      // (ncu r2b: per-float4 flag tests, 64-bit address arithmetic and bounds checks) -- 6.3 us for a 128 x 256 tile,
+      // longer than the K loop of most res2 / res3 / res4 layers; here every run-time switch is tested once per tile
+      // (warp-uniform), rows are four precomputed pointers and the column offset is one add per block.
+      auto run_fast = [&](auto mode_c) {
+        constexpr int mode = decltype(mode_c)::value;
+        const int r0 = quarter * 32 + (lane >> 2);                         // tile rows r0 + 8 i of this lane
+        const int cbase = half * EPC + col;
+        uint32_t rowok = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rowok |= (ti.m0 + r0 + 8 * i < p.M) ? (1u << i) : 0u;
+        const int ncols = min(bn, p.N - ti.n0);                            // multiple of 16
+        // destination rows: D (modes 0 / 2) or this unit's workspace slot (mode 1)
+        float* drow;
+        int64_t dstep;
+        if (mode == 1) {
+          drow = L.ws_tiles + ((size_t)(unit * 2 + ti.slot()) * nrank + rank) * ws_tile_floats + (size_t)r0 * bn + cbase;
+          dstep = 8 * (int64_t)bn;
+        } else {
+          drow = p.d + tile_off + (int64_t)(ti.m0 + r0) * p.ldd + ti.n0 + cbase;
+          dstep = 8 * p.ldd;
+        }
+        const bool wres = want_res && mode != 1;
+        const float* rrow = wres ? res_src + tile_off + (int64_t)(ti.m0 + r0) * p.ldd + ti.n0 + cbase : nullptr;
+        const bool relu = (p.flags & VLFB_EPI_RELU) != 0, tf32 = (p.flags & VLFB_EPI_TF32) != 0;
+        const bool atomic = (p.flags & VLFB_EPI_ATOMIC) != 0, has_rs = p.row_scale != nullptr;
+        const bool nobias = mode == 0 && ti.k_begin != 0;                  // split-K: bias from the first K slice only
+        const float alpha = p.alpha;
+        auto load_res = [&](int cofs, bool valid, float4* r) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (wres && valid && ((rowok >> i) & 1u)) r[i] = ld_nc_f4(rrow + i * dstep + cofs);
+          }
+        };
+        // ReLU-backward mask (MASK builds): the activation whose sign gates this gradient, same addressing as D
+        const float* mrow = (MASK && mode != 1) ? p.relu_mask + tile_off + (int64_t)(ti.m0 + r0) * p.ldd + ti.n0 + cbase : nullptr;
+        auto load_mask = [&](int cofs, bool valid, float4* r) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            r[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (MASK && mode != 1 && valid && ((rowok >> i) & 1u)) r[i] = ld_nc_f4(mrow + i * dstep + cofs);
+          }
+        };
+        // residual / accumulate / mask operands one block ahead (register double buffer), the first before the
+        // accumulator wait
+        float4 rr[4], rn[4], mr[4], mn[4];
+        load_res(0, half * EPC < ncols, rr);
+        if (MASK) load_mask(0, half * EPC < ncols, mr);
+        if (mode != 2) {
+          mbar_wait(tfull0 + 8 * acc, (tile_iter >> 1) & 1);
+          tc_fence_after();
+          if (ew == 0 && lane == 0 && tile_iter < 4) TR(24 + 4 * tile_iter);
+        }
+        int cofs = 0;                                                       // column offset of the block from cbase
+        for (int c0 = half * EPC; c0 < ncols; c0 += 2 * EPC, cofs += 2 * EPC) {
+          load_res(cofs + 2 * EPC, c0 + 2 * EPC < ncols, rn);
+          if (MASK) load_mask(cofs + 2 * EPC, c0 + 2 * EPC < ncols, mn);
+          float4 a4[4];
+          if (mode != 2) {
+            float v[EPC];
+            tmem_ld16(lane_addr + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < EPC / 4; ++q)
+              *reinterpret_cast<float4*>(stg + lane * EPITCH + q * 4) =
+                  make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              a4[i] = *reinterpret_cast<const float4*>(stg + ((lane >> 2) + 8 * i) * EPITCH + col);
+            __syncwarp();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < ti.npieces(); ++j) {                        // piece order: deterministic sum
+              const int sl = (j == 0) ? ti.first_slot() : 0;
+              const float* w = L.ws_tiles + ((size_t)((ti.ufirst() + j) * 2 + sl) * nrank + rank) * ws_tile_floats +
+                               (size_t)r0 * bn + cbase + cofs;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 w4 = ld_cg_f4(w + (size_t)i * 8 * bn);
+                a4[i].x += w4.x; a4[i].y += w4.y; a4[i].z += w4.z; a4[i].w += w4.w;
+              }
+            }
+          }
+          if (mode == 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(drow + i * dstep + cofs) = a4[i];
+            continue;
+          }
+          const int cvi = ((c0 - half * EPC) >> 1) + col;
+          float4 cs = *reinterpret_cast<const float4*>(wsc + cvi);
+          float4 cb = *reinterpret_cast<const float4*>(wbi + cvi);
+          cs.x *= alpha; cs.y *= alpha; cs.z *= alpha; cs.w *= alpha;
+          if (nobias) cb = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 o;
+            o.x = fmaf(a4[i].x, cs.x, cb.x); o.y = fmaf(a4[i].y, cs.y, cb.y);
+            o.z = fmaf(a4[i].z, cs.z, cb.z); o.w = fmaf(a4[i].w, cs.w, cb.w);
+            if (has_rs) { o.x *= rs[i]; o.y *= rs[i]; o.z *= rs[i]; o.w *= rs[i]; }
+            if (wres) { o.x += rr[i].x; o.y += rr[i].y; o.z += rr[i].z; o.w += rr[i].w; }
+            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (MASK) {
+              o.x = mr[i].x > 0.f ? o.x : 0.f; o.y = mr[i].y > 0.f ? o.y : 0.f;
+              o.z = mr[i].z > 0.f ? o.z : 0.f; o.w = mr[i].w > 0.f ? o.w : 0.f;
+            }
+            if (tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+            if ((rowok >> i) & 1u) {
+              if (atomic) red_add_f4(drow + i * dstep + cofs, o);
+              else *reinterpret_cast<float4*>(drow + i * dstep + cofs) = o;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { rr[i] = rn[i]; if (MASK) mr[i] = mn[i]; }
+        }
+      };
       // (the 17-warp cp.async builds never take the fix-up path: the host plans stream-K fix-ups for TMA-fed launches only)
       const bool split_tile = !CP && ti.npieces() > 1;
+      const bool fast_tile = !CP && vec_ok && (p.N & 15) == 0;
       if constexpr (!CP) {
-        if (split_tile) run_blocks(std::integral_constant<int, 1>{});
-        else run_blocks(std::integral_constant<int, 0>{});
+        if (fast_tile) {
+          if (split_tile) run_fast(std::integral_constant<int, 1>{});
+          else run_fast(std::integral_constant<int, 0>{});
+        } else {
+          if (split_tile) run_blocks(std::integral_constant<int, 1>{});
+          else run_blocks(std::integral_constant<int, 0>{});
+        }
       } else {
         run_blocks(std::integral_constant<int, 0>{});
       }
+      if (ew == 0 && lane == 0 && tile_iter < 4) TR(25 + 4 * tile_iter);
       // every TMEM read of this accumulator has completed (tcgen05.wait::ld above): hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -1131,14 +1292,18 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
         int old = 0;
         if (lane == 0) old = atomicAdd(cnt, 1);
         old = __shfl_sync(0xffffffffu, old, 0);
+        if (ew == 0 && lane == 0 && tile_iter <= 4) TR(26 + 4 * (tile_iter - 1));
         if (old == ti.npieces() - 1) {
           __threadfence();
-          run_blocks(std::integral_constant<int, 2>{});
+          if (fast_tile) run_fast(std::integral_constant<int, 2>{});
+          else run_blocks(std::integral_constant<int, 2>{});
           if (lane == 0) *cnt = 0;                 // counters are zero again when the launch ends
+          if (ew == 0 && lane == 0 && tile_iter <= 4) TR(27 + 4 * (tile_iter - 1));
         }
       }
     }
   }
+  if (tid == 0) TR(3);
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();       // PAIR: no CTA exits (or frees TMEM) while its peer can still signal it
   if (warp == NPWT) {
@@ -1230,14 +1395,13 @@ static bool make_tmap_im2col(CUtensorMap* tm, const float* base, int N, int D, i
 }
 
 // tuning overrides, read once (scripts/tune_gemm.py); the per-call fields of vlfb_gemm_params_t take precedence
-struct Env { int bn, stages, lag, fence, pair, sk, debug; bool tma_mn, im2col; };
+struct Env { int bn, stages, lag, pair, sk, debug; bool tma_mn, im2col; };
 static Env read_env() {
   Env e;
   auto geti = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
   e.bn = geti("VLFB_BN", 0);
   e.stages = geti("VLFB_STAGES", 0);
   e.lag = geti("VLFB_LAG", 0);
-  e.fence = geti("VLFB_FENCE", 0);
   e.pair = geti("VLFB_PAIR", 0);
   e.sk = geti("VLFB_SK", 0);
   e.debug = geti("VLFB_DEBUG", 0);
@@ -1471,9 +1635,11 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
   if (ev.stages >= 2 && ev.stages <= L.stages) L.stages = ev.stages;
   L.lag = L.stages - 1 < 2 ? L.stages - 1 : 2;
   if (ev.lag >= 1 && ev.lag < L.stages && ev.lag <= 5) L.lag = ev.lag;
-  L.fence_mode = ev.fence;
   const int cap = plan.pair ? max_pairs<AK, BK, MASK>() : num_sms;
   int units = L.total_tiles < cap ? L.total_tiles : cap;
+#ifdef VLFB_TRACE
+  L.trace = g_trace_buf;
+#endif
   L.sk = 0;
   if (plan.sk) {
     L.sk = 1;
@@ -1519,6 +1685,9 @@ void gemm_tc_plan(const vlfb_gemm_params_t& p, int num_sms, vlfb_gemm_plan_t* ou
 }
 
 size_t gemm_tc_workspace_bytes() { return tc::gemm_tc_workspace_bytes(); }
+#ifdef VLFB_TRACE
+void gemm_tc_set_trace(void* buf) { tc::g_trace_buf = reinterpret_cast<unsigned long long*>(buf); }
+#endif
 
 int gemm_tc(const vlfb_gemm_params_t& p, cudaStream_t stream) {
   const int ak = p.a.kind, bk = p.b.kind;
