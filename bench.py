@@ -23,15 +23,29 @@ for p in (os.path.join(ROOT, 'video-long-term-feature-banks_b200', 'lib'), ROOT,
     if p not in sys.path:
         sys.path.insert(0, p)
 
-YAML = 'ava_r50_lfb_nl.yaml'
+YAML = 'ava_r50_lfb_nl.yaml'           # --config selects another (CONFIGS below)
 CLIPS_PER_GPU = 2
 ROIS_PER_CLIP = 2
 BANK_ROWS = 300
-# algorithmic FLOPs per 32x224x224 clip, R50-I3D-NL, fwd+bwd (3x fwd - conv1 dgrad)
-GFLOP_PER_CLIP_FWD_BWD = 1106.0
-# ncu (profiles/r01_ncu_launches_final_s2.csv): DRAM bytes of the 292 gemm_tc_kernel launches of one training step
-# = 14496 MB read + 1700 MB written -> average per launch.  bench.py cannot run ncu itself; re-measure per round.
-NCU_DRAM_BYTES_PER_GEMM_LAUNCH = 55.5e6
+CONFIGS = {'r50_2l': 'ava_r50_lfb_nl.yaml', 'r50_3l': 'ava_r50_lfb_nl_3l.yaml', 'r101_3l': 'ava_r101_lfb_nl_3l.yaml'}
+GFLOP_PER_CLIP = {'r50_2l': 1106.0, 'r50_3l': 1106.0, 'r101_3l': 1551.0}      # SURVEY 8(d), backbone fwd+bwd
+
+
+def ncu_traffic():
+    """DRAM bytes per gemm_tc launch from the tracked ncu summary (profiles/ncu_traffic.json, written by
+    scripts/summarize_ncu_launches.py).  bench.py cannot run ncu itself; the file names the kernel source it was
+    measured on (sha256 of csrc/gemm_tc.cu) and a stale file is reported as such instead of being quoted."""
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+            rec = json.load(f)
+        src = os.path.join(ROOT, 'video-long-term-feature-banks_b200', 'csrc', 'gemm_tc.cu')
+        sha = hashlib.sha256(open(src, 'rb').read()).hexdigest()
+        if rec.get('gemm_tc_sha256') != sha:
+            return None, 'profiles/ncu_traffic.json is stale (measured on another gemm_tc.cu: %s)' % rec.get('commit', '?')
+        return float(rec['dram_bytes_per_gemm_launch']), rec.get('source', 'profiles/ncu_traffic.json')
+    except Exception as exc:
+        return None, 'no tracked ncu summary (%r)' % (exc,)
 
 
 def fbo_gflop(rois, bank_rows, layers):
@@ -114,14 +128,21 @@ def oracle_setup(n_clips, num_gpus):
     return OM, ocfg, params, inputs
 
 
-def oracle_step(OM, ocfg, params, inputs, lr=0.01):
+def oracle_step(OM, ocfg, params, inputs, state, lr=1e-4, momentum=0.9):
+    """The same step as the GPU arm: forward, backward, weight decay + Nesterov momentum SGD in the Caffe2 form
+    (model_builder_video.py:375-388: g += wd p; m' = mu m + lr g; p -= (1 + mu) m' - mu m), frozen affine layers."""
     import torch
     blobs, prob, loss = OM.forward(ocfg, params, inputs, 'train')
     loss.backward()
+    wd, wd_bn = float(ocfg['SOLVER']['WEIGHT_DECAY']), float(ocfg['SOLVER']['WEIGHT_DECAY_BN'])
     with torch.no_grad():
         for name, p in params.items():
             if p.grad is not None and not (name.endswith('_bn_s') or name.endswith('_bn_b')):
-                p.add_(p.grad, alpha=-lr)
+                g = p.grad.add(p, alpha=wd_bn if '_bn' in name else wd)
+                m = state.setdefault(name, torch.zeros_like(p))
+                m_new = m.mul(momentum).add_(g, alpha=lr)
+                p.sub_(m_new.mul(1.0 + momentum).sub_(m, alpha=momentum))
+                state[name] = m_new
             p.grad = None
     return float(loss)
 
@@ -133,25 +154,36 @@ def run_reference(args):
         return
     cores = cpu_threads()
     torch.set_num_threads(cores)
-    OM, ocfg, params, inputs = oracle_setup(1, 1)
+    OM, ocfg, params, inputs = oracle_setup(CLIPS_PER_GPU, 1)
+    state = {}
     for _ in range(args.warmup):
-        oracle_step(OM, ocfg, params, inputs)
+        oracle_step(OM, ocfg, params, inputs, state)
     t0 = time.time()
     for _ in range(args.steps):
-        oracle_step(OM, ocfg, params, inputs)
+        oracle_step(OM, ocfg, params, inputs, state)
     dt = (time.time() - t0) / max(args.steps, 1)
-    value = 1.0 / dt
-    sample = '1 clip (32x224x224, 2 RoIs, 300-row bank) fwd+bwd+SGD per step, oracle restatement on PyTorch-CPU fp32'
+    value = CLIPS_PER_GPU / dt
+    sample = ('%d clips (32x224x224, R=%d RoIs, L=%d) fwd+bwd+wd+Nesterov SGD per step, oracle restatement on PyTorch-CPU '
+              'fp32' % (CLIPS_PER_GPU, CLIPS_PER_GPU * ROIS_PER_CLIP, BANK_ROWS))
     print(json.dumps({
-        'impl': 'reference', 'metric': 'clips/sec (32x224^2) R50-I3D-NL+FBO-NL-2L fwd+bwd', 'value': value,
+        'impl': 'reference', 'metric': METRIC, 'value': value,
         'unit': 'clips/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'BASELINE.json configs[1]: R50-I3D-NL + FBO-NL-2L fwd+bwd, 32x224x224 clips, '
-                               'R=2 RoIs/clip, L=300 bank rows', 'clips_per_step': 1},
+        'config': workload_config(1),
         'cpu_baseline': {'value': value, 'unit': 'clips/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'clips/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }))
+
+
+METRIC = 'clips/sec (32x224^2) R50-I3D-NL+FBO-NL fwd+bwd'
+
+
+def workload_config(n_gpus):
+    """Identical for both arms (the driver compares them)."""
+    return {'workload': '%s: %d clips/GPU 32x224^2, R=%d, L=%d, fwd+bwd+SGD' % (
+                YAML.replace('.yaml', ''), CLIPS_PER_GPU, CLIPS_PER_GPU * ROIS_PER_CLIP, BANK_ROWS),
+            'clips_per_gpu': CLIPS_PER_GPU, 'parallelism': 'dp%d' % n_gpus}
 
 
 # ------------------------------------------------------------------------------------ B200 arm
@@ -279,8 +311,9 @@ def run_b200(args):
         e2e_ms, e2e_mode = e2e_async_ms, 'FetchBlobAsync(loss): step i read back after step i+1 was launched'
     sampler.stop_flag = True
 
-    # ---- roofline of the dominant kernel: every tcgen05 GEMM launch of one more step, CUDA events
-    workspace.current().force_eager = True       # per-launch CUDA events need the eager path
+    # ---- roofline of the dominant kernel: every tcgen05 GEMM launch of one more (eager) step is recorded and then
+    # replayed back to back between CUDA events (device time per launch; kernels.stop_profile)
+    workspace.current().force_eager = True
     K.start_profile()
     workspace.RunNet(name)
     recs = K.stop_profile()
@@ -316,8 +349,9 @@ def run_b200(args):
     assert np.isfinite(loss), 'loss is not finite'
     layers = cfg.FBO_NL.NUM_LAYERS
     rois = CLIPS_PER_GPU * ROIS_PER_CLIP
-    gflop_step = CLIPS_PER_GPU * GFLOP_PER_CLIP_FWD_BWD + fbo_gflop(rois, BANK_ROWS, layers)
+    gflop_step = CLIPS_PER_GPU * GFLOP_PER_CLIP[args.config] + fbo_gflop(rois, BANK_ROWS, layers)
     achieved = gflop_step / gemm_ms if gemm_ms > 0 else 0.0          # GFLOP/ms == TFLOP/s
+    traffic, traffic_src = ncu_traffic()
     clips = CLIPS_PER_GPU * n_gpus
 
     # ---- CPU baseline: the oracle on this box's host cores, bounded sample (N=1 only)
@@ -325,40 +359,38 @@ def run_b200(args):
     if n_gpus == 1 and not args.no_cpu_baseline:
         cores = cpu_threads()
         torch.set_num_threads(cores)
-        OMo, oc, op, oi = oracle_setup(1, 1)
-        oracle_step(OMo, oc, op, oi)
+        OMo, oc, op, oi = oracle_setup(CLIPS_PER_GPU, 1)
+        ost = {}
+        oracle_step(OMo, oc, op, oi, ost)
         t0 = time.time()
         nrep = 2
         for _ in range(nrep):
-            oracle_step(OMo, oc, op, oi)
-        cpu = {'value': nrep / (time.time() - t0), 'unit': 'clips/s', 'cores': cores, 'kind': 'port',
-               'sample': '%d timed steps of 1 clip (32x224x224, 2 RoIs, L=300) fwd+bwd+SGD, PyTorch-CPU fp32 '
-                         'oracle restatement (the Caffe2 reference cannot run here)' % nrep}
+            oracle_step(OMo, oc, op, oi, ost)
+        cpu = {'value': nrep * CLIPS_PER_GPU / (time.time() - t0), 'unit': 'clips/s', 'cores': cores, 'kind': 'port',
+               'sample': '%d timed steps of %d clips (32x224x224, R=%d, L=%d) fwd+bwd+wd+Nesterov SGD, PyTorch-CPU fp32 '
+                         'oracle restatement (the Caffe2 reference cannot run here)' % (
+                             nrep, CLIPS_PER_GPU, CLIPS_PER_GPU * ROIS_PER_CLIP, BANK_ROWS)}
 
     print(json.dumps({
-        'metric': 'clips/sec (32x224^2) R50-I3D-NL+FBO-NL-2L fwd+bwd', 'value': clips / (ms / 1e3),
+        'metric': METRIC, 'value': clips / (ms / 1e3),
         'unit': 'clips/s', 'n_gpus': n_gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32', 'data': 'synthetic',
-        'config': {'workload': 'BASELINE.json configs[1]: R50-I3D-NL + FBO-NL-2L fwd+bwd+SGD, %d clips/GPU of '
-                               '32x224x224, R=%d RoIs, L=%d bank rows x 2048; random-init weights' % (
-                                   CLIPS_PER_GPU, rois, BANK_ROWS),
-                   'clips_per_gpu': CLIPS_PER_GPU, 'parallelism': 'dp%d' % n_gpus,
-                   'l2': 'activations (>1 GB/step) exceed the 126 MB L2 between launches; no explicit flush',
-                   'dropout': 'Philox, enabled', 'cuda_graph': bool(cfg.B200.CUDA_GRAPH)},
+        'config': dict(workload_config(n_gpus),
+                       l2='activations (>1 GB/step) exceed the 126 MB L2 between launches; no explicit flush',
+                       dropout='Philox, enabled', cuda_graph=bool(cfg.B200.CUDA_GRAPH), weights='random-init'),
         'e2e': {'value': clips / (e2e_ms / 1e3), 'unit': 'clips/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms, 'loss_readback': e2e_mode,
                 'ms_per_step_blocking_fetch': e2e_blocking_ms, 'ms_per_step_async_fetch': e2e_async_ms},
         'gpu_launches': launches,
         'clocks': sampler.summary(),
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf32, 'unit': 'TFLOP/s',
-                     'frac': achieved / peak_tf32 if peak_tf32 else None, 'traffic': NCU_DRAM_BYTES_PER_GEMM_LAUNCH,
-                     'traffic_source': 'profiles/r01_ncu_launches_final_s2_summary.txt: dram__bytes_read+write summed over '
-                                       'the 292 GEMM launches of one step (16.2 GB) / 292',
+                     'frac': achieved / peak_tf32 if peak_tf32 else None, 'traffic': traffic,
+                     'traffic_source': traffic_src,
                      'flop_per_launch': gflop_step * 1e9 / max(len(recs), 1),
-                     'kernel': 'vlfb::tc::gemm_tc_kernel: all %d launches of one step timed with CUDA events around each '
-                               'launch in an eager step = %.2f ms (includes inter-launch gaps, so achieved is a lower '
-                               'bound; ncu kernel time of the same launches: profiles/r01_ncu_launches_final_s2_summary.txt); '
-                               'the captured step takes %.2f ms in total' % (len(recs), gemm_ms, ms),
+                     'kernel': 'vlfb::tc::gemm_tc_kernel: all %d launches of one step; device time of each launch = its '
+                               'parameter block replayed 5x back to back between two CUDA events on the launching stream '
+                               '(no host launch latency in the number): sum %.2f ms; the captured step takes %.2f ms in '
+                               'total' % (len(recs), gemm_ms, ms),
                      'peak_source': '%s bf16_tflops_sustained / 2 (kind::tf32)' % peak_src,
                      'per_launch_roofline': {
                          'what': 'sum over the GEMM launches of max(flops / tensor peak, algorithmic bytes / HBM peak) '
@@ -381,7 +413,11 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--dump-gemms', default='', help='write the per-launch GEMM table of one step here')
     ap.add_argument('--no-graph', action='store_true', help='eager launches (for ncu / debugging)')
+    ap.add_argument('--config', default='r50_2l', choices=sorted(CONFIGS), help='r50_2l = BASELINE configs[1] (default), '
+                    'r50_3l = configs[2] (ava_r50_lfb_nl_3l.yaml), r101_3l = configs[3] architecture')
     args = ap.parse_args()
+    global YAML
+    YAML = CONFIGS[args.config]
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':
         run_reference(args)

@@ -234,15 +234,6 @@ int vlfb_sgd_nesterov(float* p, float* g, float* m, float* p_tf32, int64_t n,
                       const float* lr /* device scalar */, float momentum, float wd, int nesterov,
                       void* stream);
 
-/* ---- fused FBO-NL attention core: one query per RoI over L bank rows
- *      (lfb_helper.NLCore :223-234 BatchMatMul/Scale/Softmax/BatchMatMul) ----------------- */
-/* theta [R][d], phi,g [R][L][d] -> prob [R][L], y [R][d] */
-int vlfb_fbo_attend_fwd(const float* theta, const float* phi, const float* g, float* prob, float* y,
-                        int R, int L, int d, float scale, void* stream);
-int vlfb_fbo_attend_bwd(const float* theta, const float* phi, const float* g, const float* prob,
-                        const float* dy, float* dtheta, float* dphi,
-                        float* dg, int R, int L, int d, float scale, void* stream);
-
 /* ---- inference-mode FBO-NL over the RAW bank (csrc/fbo.cu) --------------------------------
  * Replaces, per FBO-NL layer of a test-mode graph (no dropout between 'lfb_1x1' and phi/g), the operators
  * Conv 'lfb_1x1' (lfb_helper.py:320-338), Conv '{prefix}_phi' / '{prefix}_g' (:183-202), BatchMatMul / Scale /
@@ -255,6 +246,51 @@ int vlfb_fbo_bank_scan_splits(int R, int L, int D);
 size_t vlfb_fbo_bank_scan_workspace(int R, int L, int D);
 int vlfb_fbo_bank_scan(const float* bank, const float* q, float scale, float* out, float* prob, int R, int L, int D,
                        int tf32_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- training-mode FBO-NL stack, one launch per direction (csrc/fbo.cu section 3) ---------------------
+ * Replaces, for ALL layers of lfb_helper.NLLayers (:266-292) with one query per RoI and FBO_NL.PRE_ACT, the operators of
+ * NLCore (:170-263): Conv theta / phi / g, BatchMatMul, Scale, Softmax, BatchMatMul, LayerNorm, Relu, Conv out, Dropout,
+ * Sum -- phi and g are folded onto the shared projected bank bp (prepare_lfb :320-338 output, after its dropout):
+ * score_j = (W_phi^T theta) . bp_j (+ const), y = W_g (sum_j p_j bp_j) + b_g.  Weights are [out][in] row-major fp32. */
+typedef struct {
+  const float *w_theta, *b_theta;   /* [d][dA], [d] or NULL   '{prefix}_theta_w/_b'  */
+  const float *w_phi, *b_phi;       /* [d][dB], [d] or NULL   '{prefix}_phi_w/_b'    */
+  const float *w_g, *b_g;           /* [d][dB], [d] or NULL   '{prefix}_g_w/_b'      */
+  const float *w_out, *b_out;       /* [dA][d], [dA] or NULL  '{prefix}_out_w/_b'    */
+  float *gw_theta, *gb_theta, *gw_phi, *gb_phi, *gw_g, *gb_g, *gw_out, *gb_out;   /* bwd: accumulated (+=), NULL = skip */
+  /* activations written by fwd and read by bwd, [R][...] */
+  float *theta;                     /* [R][d]   '{prefix}_theta'                  */
+  float *prob;                      /* [R][L]   '{prefix}_affinity_prob'          */
+  float *s;                         /* [R][dB]  sum_j p_j bp_j                    */
+  float *t;                         /* [R][d]   '{prefix}_y'                      */
+  float *xhat;                      /* [R][d]   LayerNorm output (t itself without PRE_ACT_LN); relu(xhat) feeds out */
+  float *ln_mean, *ln_std;          /* [R]                                         */
+  float *out;                       /* [R][dA]  '{prefix}_out' (before dropout)   */
+  float *a_out;                     /* [R][dA]  '{prefix}_sum' = input + dropout(out) */
+  uint64_t drop_offset;             /* Philox counter offset of this layer's dropout (vlfb_dropout_fwd's generator) */
+} vlfb_fbo_layer_t;
+
+typedef struct {
+  int R, L;                         /* RoIs, bank rows per RoI                     */
+  int dA, d, dB;                    /* query width, latent width, projected-bank width */
+  int layers;                       /* 1..4                                        */
+  float scale;                      /* d^-0.5 with FBO_NL.SCALE, else 1            */
+  int pre_act;                      /* must be 1 (post-activation graphs keep the as-written lowering) */
+  int pre_act_ln;                   /* FBO_NL.PRE_ACT_LN                           */
+  float ln_eps;
+  float drop_ratio;                 /* 0 = no dropout on the layer outputs         */
+  uint64_t seed;
+  const int64_t* step;              /* optional device scalar added to the counter (<< 32), as in vlfb_dropout_fwd */
+} vlfb_fbo_cfg_t;
+
+size_t vlfb_fbo_nl_scratch_floats(const vlfb_fbo_cfg_t* cfg);
+/* a0 [R][dA] (prepare_nl_input output), bp [R][L][dB] */
+int vlfb_fbo_nl_fwd(const vlfb_fbo_cfg_t* cfg, const vlfb_fbo_layer_t* layers, const float* a0, const float* bp,
+                    void* stream);
+/* da_last [R][dA] = gradient of the last layer's sum; writes da0 [R][dA] and dbp [R][L][dB] (overwritten) and accumulates
+ * the weight / bias gradients of every layer. */
+int vlfb_fbo_nl_bwd(const vlfb_fbo_cfg_t* cfg, const vlfb_fbo_layer_t* layers, const float* a0, const float* bp,
+                    const float* da_last, float* da0, float* dbp, float* scratch, size_t scratch_floats, void* stream);
 
 /* ---- device-resident feature bank: window assembly (tools/lfb_loader.py:51-152 builds the bank,
  *      lib/datasets/ava.py:300-323 / charades.py:251-276 sample a window per example) -----------

@@ -352,6 +352,61 @@ def fbo_bank_scan(bank, q, out, scale, prob=None, tf32_out=False):
     out.copy_(_q(torch.einsum('rl,rld->rd', p, bank), tf32_out))
 
 
+def _fbo_nl_forward(cfgd, layers, a0, bp):
+    """Folded NLLayers forward (csrc/fbo.cu section 3) in torch; returns the final A and the per-layer activations."""
+    A = a0
+    acts = []
+    for ld in layers:
+        theta = A @ ld['w_theta'].t() + (ld['b_theta'] if ld.get('b_theta') is not None else 0)
+        u = theta @ ld['w_phi']                                               # W_phi^T theta
+        const = (theta * ld['b_phi']).sum(1, keepdim=True) if ld.get('b_phi') is not None else 0
+        p = torch.softmax((torch.einsum('rd,rld->rl', u, bp) + const) * cfgd['scale'], dim=1)
+        s = torch.einsum('rl,rld->rd', p, bp)
+        t = s @ ld['w_g'].t() + (ld['b_g'] if ld.get('b_g') is not None else 0)
+        if cfgd['pre_act_ln']:
+            mean = t.mean(1, keepdim=True)
+            std = torch.sqrt(((t - mean) ** 2).mean(1, keepdim=True) + cfgd.get('ln_eps', 1e-5))
+            xhat = (t - mean) / std
+        else:
+            mean, std = torch.zeros_like(t[:, :1]), torch.ones_like(t[:, :1])
+            xhat = t
+        out = torch.relu(xhat) @ ld['w_out'].t() + (ld['b_out'] if ld.get('b_out') is not None else 0)
+        o = out
+        if cfgd.get('drop_ratio', 0.0) > 0.0:
+            step = cfgd.get('step')
+            g = torch.Generator().manual_seed(int(cfgd.get('seed', 0)) * 1000003 + int(ld.get('drop_offset', 0)) +
+                                              (int(step.item()) << 20 if step is not None else 0))
+            mask = (torch.rand(out.shape, generator=g) >= cfgd['drop_ratio']).to(out.dtype)
+            o = out * mask / (1.0 - cfgd['drop_ratio'])
+        A = A + o
+        acts.append(dict(theta=theta, prob=p, s=s, t=t, xhat=xhat, ln_mean=mean[:, 0], ln_std=std[:, 0], out=out, a_out=A))
+    return A, acts
+
+
+def fbo_nl_fwd(cfgd, layers, a0, bp):
+    with torch.no_grad():
+        _, acts = _fbo_nl_forward(cfgd, layers, a0, bp)
+    for ld, ac in zip(layers, acts):
+        for k, v in ac.items():
+            ld[k].copy_(v)
+
+
+def fbo_nl_bwd(cfgd, layers, a0, bp, da_last, da0, dbp):
+    a = a0.detach().clone().requires_grad_(True)
+    b = bp.detach().clone().requires_grad_(True)
+    wk = ('w_theta', 'b_theta', 'w_phi', 'b_phi', 'w_g', 'b_g', 'w_out', 'b_out')
+    lay = [dict(ld, **dict((k, ld[k].detach().clone().requires_grad_(True)) for k in wk if ld.get(k) is not None))
+           for ld in layers]
+    A, _ = _fbo_nl_forward(cfgd, lay, a, b)
+    (A * da_last).sum().backward()
+    da0.copy_(a.grad)
+    dbp.copy_(b.grad)
+    for ld, l2 in zip(layers, lay):
+        for k in wk:
+            if ld.get('g' + k) is not None and l2.get(k) is not None and l2[k].grad is not None:
+                ld['g' + k].add_(l2[k].grad)
+
+
 def lfb_gather(bank, idx, out, tf32_out=False):
     assert idx.dtype == torch.int32
     flat_out = out.view(-1, out.shape[-1])

@@ -146,7 +146,20 @@ def test_fusion_plan(fake):
     s = by_name['nonlocal_conv4_1_sum']
     assert s.affine and s.res_key[0] == 'res4_1_branch2c_bn' and not s.relu and s.b
     assert len([s for s in net.steps if isinstance(s, X.ScaleStep)]) == 0       # folded into the softmax
-    assert len(convs) == 53 + 20 + 2 + 8
+    # 53 backbone + 20 NL convs, reduc + lfb_1x1; the 8 theta / phi / g / out projections of the two FBO-NL layers
+    # live inside ONE FboStackStep (B200.FBO_STACK), with the parameters the as-written graph creates
+    assert len(convs) == 53 + 20 + 2
+    stacks = [s for s in net.steps if isinstance(s, X.FboStackStep)]
+    assert len(stacks) == 1 and len(stacks[0].params) == 16
+    assert set(stacks[0].params) <= set(model.params) and 'lfb_nl1_out_w' in stacks[0].params
+    from core.config import config as cfg
+    H.setup_cfg('ava_r50_lfb_nl.yaml', TINY)
+    cfg.B200.FBO_STACK = False
+    workspace.ResetWorkspace()
+    model2, _ = H.build('train', True)
+    net2 = workspace.current().nets[model2.net.Proto().name]
+    assert len([s for s in net2.steps if isinstance(s, X.ConvStep)]) == 53 + 20 + 2 + 8
+    assert sorted(model2.params) == sorted(model.params)            # identical parameter inventory either way
 
 
 def test_tf32_rounding_points_match_oracle_emulation(fake):

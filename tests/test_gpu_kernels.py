@@ -431,25 +431,6 @@ def test_losses_and_sgd(K):
     assert torch.equal(pt.cpu(), tf32_round(pd_.cpu()))
 
 
-def test_fbo_attend(K):
-    R, Lb, d = 3, 300, 512
-    th = (torch.randn(R, d) * 0.3).double().requires_grad_(True)
-    ph = (torch.randn(R, Lb, d) * 0.3).double().requires_grad_(True)
-    gg = torch.randn(R, Lb, d).double().requires_grad_(True)
-    sc = d ** -0.5
-    p = torch.softmax(torch.einsum('rd,rld->rl', th, ph) * sc, dim=1)
-    y = torch.einsum('rl,rld->rd', p, gg)
-    dy = torch.randn(R, d).double()
-    y.backward(dy)
-    f = lambda t: t.detach().float().cuda()
-    pd, yd = torch.empty((R, Lb), device='cuda'), torch.empty((R, d), device='cuda')
-    K.fbo_attend_fwd(f(th), f(ph), f(gg), pd, yd, sc)
-    assert rel_err(pd, p) < 1e-5 and rel_err(yd, y) < 1e-5
-    dth, dph, dg = torch.empty_like(yd), torch.empty((R, Lb, d), device='cuda'), torch.empty((R, Lb, d), device='cuda')
-    K.fbo_attend_bwd(f(th), f(ph), f(gg), pd, f(dy), dth, dph, dg, sc)
-    assert rel_err(dth, th.grad) < 1e-4 and rel_err(dph, ph.grad) < 1e-4 and rel_err(dg, gg.grad) < 1e-5
-
-
 @pytest.mark.parametrize('rows,cols', [(1200, 512), (25088, 256), (3, 80), (70000, 64)])
 def test_colsum(K, rows, cols):
     x = torch.randn(rows, cols)
@@ -674,3 +655,103 @@ def test_stream_k_results_are_deterministic(K):
         assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     finally:
         _with_opts(K, {})
+
+
+# -------------------------------------------------------------------------- training-mode FBO-NL stack (one launch)
+def _fbo_ref(a0, bp, Ws, scale, pre_act_ln, eps=1e-5):
+    """As-written NLLayers / NLCore (lfb_helper.py:170-292) in fp64 with autograd: phi and g ARE formed here."""
+    A = a0
+    outs = []
+    for W in Ws:
+        theta = A @ W['w_theta'].t() + W['b_theta']                       # (R, d)
+        phi = bp @ W['w_phi'].t() + W['b_phi']                             # (R, L, d)
+        g = bp @ W['w_g'].t() + W['b_g']
+        aff = torch.einsum('rd,rld->rl', theta, phi) * scale
+        p = torch.softmax(aff, dim=1)
+        t = torch.einsum('rl,rld->rd', p, g)
+        x = F.layer_norm(t, (t.shape[1],), eps=eps) if pre_act_ln else t
+        out = torch.relu(x) @ W['w_out'].t() + W['b_out']
+        A = A + out
+        outs.append(dict(theta=theta, prob=p, t=t, out=out, a_out=A))
+    return A, outs
+
+
+@pytest.mark.parametrize('R,L,dA,d,dB,layers,ln', [(4, 300, 512, 512, 512, 2, True), (3, 37, 512, 512, 512, 3, True),
+                                                    (5, 60, 2048, 512, 512, 2, True), (2, 120, 512, 512, 512, 1, False)])
+def test_fbo_nl_stack_fwd_bwd(K, R, L, dA, d, dB, layers, ln):
+    """vlfb_fbo_nl_fwd / _bwd (phi and g folded onto the projected bank) against the as-written graph in fp64:
+    every saved activation, the input / bank gradients and all weight / bias gradients, incl. zero-padded bank rows
+    (they still receive softmax mass, lfb_helper.py NTC_to_NCT11 note) and a b_phi whose gradient is exactly 0."""
+    g = torch.Generator().manual_seed(7)
+    rn = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc)
+    a0 = rn(R, dA)
+    bp = rn(R, L, dB, sc=0.7)
+    bp[:, L - L // 4:] = 0.0
+    scale = d ** -0.5
+    Ws = [dict(w_theta=rn(d, dA, sc=0.05), b_theta=rn(d, sc=0.1), w_phi=rn(d, dB, sc=0.08), b_phi=rn(d, sc=0.1),
+               w_g=rn(d, dB, sc=0.05), b_g=rn(d, sc=0.1), w_out=rn(dA, d, sc=0.05), b_out=rn(dA, sc=0.1))
+          for _ in range(layers)]
+    a64 = a0.double().requires_grad_(True)
+    b64 = bp.double().requires_grad_(True)
+    W64 = [dict((k, v.double().requires_grad_(True)) for k, v in W.items()) for W in Ws]
+    A_ref, outs = _fbo_ref(a64, b64, W64, scale, ln)
+    dlast = rn(R, dA)
+    (A_ref * dlast.double()).sum().backward()
+
+    dev = lambda t: t.float().cuda().contiguous()
+    lay = []
+    for W in Ws:
+        ld = dict((k, dev(v)) for k, v in W.items())
+        for k, v in W.items():
+            ld['g' + k] = torch.full(v.shape, 0.25, device='cuda')             # accumulated into: starts non-zero
+        ld.update(theta=torch.empty(R, d, device='cuda'), prob=torch.empty(R, L, device='cuda'),
+                  s=torch.empty(R, dB, device='cuda'), t=torch.empty(R, d, device='cuda'),
+                  xhat=torch.empty(R, d, device='cuda'), ln_mean=torch.empty(R, device='cuda'),
+                  ln_std=torch.empty(R, device='cuda'), out=torch.empty(R, dA, device='cuda'),
+                  a_out=torch.empty(R, dA, device='cuda'))
+        lay.append(ld)
+    cfgd = dict(R=R, L=L, dA=dA, d=d, dB=dB, scale=scale, pre_act_ln=ln)
+    K.fbo_nl_fwd(cfgd, lay, dev(a0), dev(bp))
+    torch.cuda.synchronize()
+    for ld, o in zip(lay, outs):
+        for k in ('theta', 'prob', 't', 'out', 'a_out'):
+            assert rel_err(ld[k], o[k]) < 2e-5, k
+    da0 = torch.full((R, dA), float('nan'), device='cuda')
+    dbp = torch.full((R, L, dB), float('nan'), device='cuda')
+    K.fbo_nl_bwd(cfgd, lay, dev(a0), dev(bp), dev(dlast), da0, dbp)
+    torch.cuda.synchronize()
+    assert rel_err(da0, a64.grad) < 5e-5
+    assert rel_err(dbp, b64.grad) < 5e-5
+    for ld, W in zip(lay, W64):
+        for k, v in W.items():
+            got = ld['g' + k].cpu().double() - 0.25
+            if k == 'b_phi':                                                   # exactly zero in exact arithmetic
+                assert float(got.abs().max()) < 1e-5 and float(v.grad.abs().max()) < 1e-9
+            else:
+                assert rel_err(got, v.grad) < 1e-4, k
+
+
+def test_fbo_nl_stack_dropout_is_an_unbiased_philox_mask(K):
+    """drop_ratio > 0: each element of a layer's output is kept with probability 1 - ratio and scaled by 1 / (1 - ratio);
+    the same (seed, offset) gives the same mask forward and backward (da0 of a pure-residual probe)."""
+    R, L, dA = 8, 20, 512
+    ld = dict(w_theta=torch.zeros(512, dA, device='cuda'), b_theta=torch.zeros(512, device='cuda'),
+              w_phi=torch.zeros(512, 512, device='cuda'), b_phi=None, w_g=torch.zeros(512, 512, device='cuda'),
+              b_g=torch.ones(512, device='cuda'), w_out=torch.zeros(dA, 512, device='cuda'),
+              b_out=torch.ones(dA, device='cuda'), theta=torch.empty(R, 512, device='cuda'),
+              prob=torch.empty(R, L, device='cuda'), s=torch.empty(R, 512, device='cuda'),
+              t=torch.empty(R, 512, device='cuda'), xhat=torch.empty(R, 512, device='cuda'),
+              ln_mean=torch.empty(R, device='cuda'), ln_std=torch.empty(R, device='cuda'),
+              out=torch.empty(R, dA, device='cuda'), a_out=torch.empty(R, dA, device='cuda'), drop_offset=12345)
+    a0 = torch.zeros(R, dA, device='cuda')
+    bp = torch.randn(R, L, 512, device='cuda')
+    cfgd = dict(R=R, L=L, dA=dA, d=512, dB=512, scale=1.0, pre_act_ln=False, drop_ratio=0.2, seed=99)
+    K.fbo_nl_fwd(cfgd, [ld], a0, bp)
+    torch.cuda.synchronize()
+    a = ld['a_out'].cpu()                                   # out == 1 everywhere -> a_out is the scaled keep mask
+    vals = set(np.round(a.unique().numpy(), 5).tolist())
+    assert vals == {0.0, 1.25}
+    assert abs(float((a > 0).float().mean()) - 0.8) < 0.02
+    x = torch.empty(R * dA, device='cuda')
+    K.dropout(torch.ones(R * dA, device='cuda'), x, 0.2, 99, 12345)
+    assert torch.equal(x.view(R, dA).cpu(), a), 'same generator as vlfb_dropout_fwd'

@@ -13,6 +13,7 @@
 // 2. lfb_gather: builds the per-sample (L x D) bank windows on the device from a resident bank tensor and a host
 //    computed row-index table (tools/lfb_loader.py:51-152 + lib/datasets/ava.py:300-323: -1 = zero padding).
 #include <float.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -172,6 +173,374 @@ __global__ void lfb_gather_k(const float4* __restrict__ bank, const int32_t* __r
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3. fbo_nl_fwd / fbo_nl_bwd: the TRAINING-mode FBO-NL stack (lfb_helper.NLLayers :266-292 over NLCore :170-263) with
+//    one query per RoI, as ONE launch per direction.  Dropout sits between 'lfb_1x1' and the phi / g projections
+//    (prepare_lfb :320-338), so the raw-bank fold of the inference graph is not valid -- but the SAME algebra applies
+//    one step later, on the projected (and dropped-out) bank B' [R][L][dB] that all layers share:
+//        score_j = theta . (W_phi B'_j + b_phi) = (W_phi^T theta) . B'_j + const       (const drops out of the softmax)
+//        sum_j p_j (W_g B'_j + b_g) = W_g (sum_j p_j B'_j) + b_g                        (sum_j p_j = 1)
+//    i.e. phi and g (2 x R*L x dB x d MACs per layer forward, 4 more GEMMs backward) are never formed: a layer is four
+//    d x d mat-vecs and two passes over B' per RoI.  The as-written graph spends 41 GEMM launches + ~70 streaming
+//    launches of 10-25 us each on R*L = 1200 rows (r01: 0.97 ms of a 15.8 ms step); here one CTA per RoI walks all
+//    layers.  Gradients: exact (the b_phi / theta terms that multiply sum_j dscore_j = 0 are kept for parity with the
+//    reference's autograd); the rank-R weight gradients are accumulated by fbo_nl_outer_k from the per-RoI vectors.
+constexpr int NL_TPB = 512;
+constexpr int NL_MAX_LAYERS = 4;
+
+struct NlParams {
+  vlfb_fbo_cfg_t c;
+  vlfb_fbo_layer_t l[NL_MAX_LAYERS];
+  const float* a0;       // [R][dA] query input of layer 0
+  const float* bp;       // [R][L][dB] projected bank (after dropout)
+  const float* da_last;  // bwd: gradient of the last layer's sum [R][dA]
+  float* da0;            // bwd: gradient of a0
+  float* dbp;            // bwd: gradient of bp (overwritten)
+  float* scratch;        // bwd: per layer [R][dA + d + dB + d + 4]: do, dt, du, dtheta, sum_j dscore_j
+};
+
+__device__ __forceinline__ float block_sum_nl(float v, float* red) {
+  v = warp_sum_f(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = (threadIdx.x < NL_TPB / 32) ? red[threadIdx.x] : 0.f;
+  if (threadIdx.x < 32) {
+    t = warp_sum_f(t);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  return red[0];
+}
+__device__ __forceinline__ float block_max_nl(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = (threadIdx.x < NL_TPB / 32) ? red[threadIdx.x] : -FLT_MAX;
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, o));
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  return red[0];
+}
+// out[row] = bias[row] + sum_c W[row][c] x[c]   (one warp per row, 128-bit lanes; cols % 4 == 0)
+__device__ __forceinline__ void matvec_rows(const float* __restrict__ W, const float* x, float* out,
+                                            const float* __restrict__ bias, int rows, int cols) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int row = warp; row < rows; row += NL_TPB / 32) {
+    const float4* w4 = reinterpret_cast<const float4*>(W + (int64_t)row * cols);
+    float acc = 0.f;
+    for (int c = lane; c < (cols >> 2); c += 32) {
+      const float4 a = w4[c];
+      const float4 b = *reinterpret_cast<const float4*>(x + 4 * c);
+      acc += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+    }
+    acc = warp_sum_f(acc);
+    if (lane == 0) out[row] = acc + (bias ? bias[row] : 0.f);
+  }
+}
+// out[c] = sum_row W[row][c] x[row]   (= W^T x; threads over columns, coalesced rows)
+__device__ __forceinline__ void matvec_cols(const float* __restrict__ W, const float* x, float* out, int rows, int cols) {
+  for (int c = threadIdx.x; c < cols; c += NL_TPB) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int r = 0;
+    for (; r + 3 < rows; r += 4) {
+      a0 += W[(int64_t)r * cols + c] * x[r];
+      a1 += W[(int64_t)(r + 1) * cols + c] * x[r + 1];
+      a2 += W[(int64_t)(r + 2) * cols + c] * x[r + 2];
+      a3 += W[(int64_t)(r + 3) * cols + c] * x[r + 3];
+    }
+    for (; r < rows; ++r) a0 += W[(int64_t)r * cols + c] * x[r];
+    out[c] = (a0 + a1) + (a2 + a3);
+  }
+}
+// the generator of vlfb_dropout_fwd (csrc/ops.cu): element idx keeps iff u(idx) >= ratio, scaled by 1 / (1 - ratio)
+__device__ __forceinline__ float philox_keep(uint64_t seed, uint64_t offset, int64_t idx, float ratio) {
+  const uint64_t ctr = offset + (uint64_t)(idx >> 2);
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0u, c3 = 0u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = h1 ^ c1 ^ k0, n1 = l1, n2 = h0 ^ c3 ^ k1, n3 = l0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  const uint32_t rr[4] = {c0, c1, c2, c3};
+  const float u = (float)(rr[idx & 3] >> 8) * (1.0f / 16777216.0f);
+  return (u >= ratio) ? 1.f / (1.f - ratio) : 0.f;
+}
+
+// smem: sA[dA] | sTh[d] | sU[dB] | sS[dB] | sT[d] | sAct[d] | sO[dA] | sE[L] | red[32]
+__global__ void __launch_bounds__(NL_TPB, 1) fbo_nl_fwd_k(const NlParams P) {
+  extern __shared__ float sm[];
+  const vlfb_fbo_cfg_t& c = P.c;
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* sA = sm;
+  float* sTh = sA + c.dA;
+  float* sU = sTh + c.d;
+  float* sS = sU + c.dB;
+  float* sT = sS + c.dB;
+  float* sAct = sT + c.d;
+  float* sO = sAct + c.d;
+  float* sE = sO + c.dA;
+  float* red = sE + ((c.L + 3) & ~3);
+  const float* B = P.bp + (int64_t)r * c.L * c.dB;
+  for (int i = tid; i < c.dA; i += NL_TPB) sA[i] = P.a0[(int64_t)r * c.dA + i];
+  __syncthreads();
+  uint64_t step_off = c.step ? ((uint64_t)c.step[0] << 32) : 0ull;
+  for (int li = 0; li < c.layers; ++li) {
+    const vlfb_fbo_layer_t& l = P.l[li];
+    matvec_rows(l.w_theta, sA, sTh, l.b_theta, c.d, c.dA);
+    __syncthreads();
+    for (int i = tid; i < c.d; i += NL_TPB) l.theta[(int64_t)r * c.d + i] = sTh[i];
+    matvec_cols(l.w_phi, sTh, sU, c.d, c.dB);
+    __syncthreads();
+    for (int j = warp; j < c.L; j += NL_TPB / 32) {             // scores (the theta . b_phi constant is dropped)
+      const float4* b4 = reinterpret_cast<const float4*>(B + (int64_t)j * c.dB);
+      float acc = 0.f;
+      for (int q = lane; q < (c.dB >> 2); q += 32) {
+        const float4 a = b4[q];
+        const float4 u = *reinterpret_cast<const float4*>(sU + 4 * q);
+        acc += a.x * u.x + a.y * u.y + a.z * u.z + a.w * u.w;
+      }
+      acc = warp_sum_f(acc);
+      if (lane == 0) sE[j] = acc * c.scale;
+    }
+    __syncthreads();
+    float mx = -FLT_MAX;
+    for (int j = tid; j < c.L; j += NL_TPB) mx = fmaxf(mx, sE[j]);
+    mx = block_max_nl(mx, red);
+    float sum = 0.f;
+    for (int j = tid; j < c.L; j += NL_TPB) { const float e = __expf(sE[j] - mx); sE[j] = e; sum += e; }
+    sum = block_sum_nl(sum, red);
+    const float inv = 1.f / sum;
+    for (int j = tid; j < c.L; j += NL_TPB) { const float pv = sE[j] * inv; sE[j] = pv; l.prob[(int64_t)r * c.L + j] = pv; }
+    __syncthreads();
+    for (int i = tid; i < c.dB; i += NL_TPB) {                  // s = sum_j p_j B'_j
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int j = 0;
+      for (; j + 3 < c.L; j += 4) {
+        a0 += sE[j] * B[(int64_t)j * c.dB + i];
+        a1 += sE[j + 1] * B[(int64_t)(j + 1) * c.dB + i];
+        a2 += sE[j + 2] * B[(int64_t)(j + 2) * c.dB + i];
+        a3 += sE[j + 3] * B[(int64_t)(j + 3) * c.dB + i];
+      }
+      for (; j < c.L; ++j) a0 += sE[j] * B[(int64_t)j * c.dB + i];
+      const float v = (a0 + a1) + (a2 + a3);
+      sS[i] = v;
+      l.s[(int64_t)r * c.dB + i] = v;
+    }
+    __syncthreads();
+    matvec_rows(l.w_g, sS, sT, l.b_g, c.d, c.dB);
+    __syncthreads();
+    for (int i = tid; i < c.d; i += NL_TPB) l.t[(int64_t)r * c.d + i] = sT[i];
+    // pre-activation: LayerNorm over the d channels (no affine, biased variance) then ReLU
+    float mean = 0.f, rstd = 1.f;
+    if (c.pre_act_ln) {
+      float a = 0.f;
+      for (int i = tid; i < c.d; i += NL_TPB) a += sT[i];
+      mean = block_sum_nl(a, red) / (float)c.d;
+      float v = 0.f;
+      for (int i = tid; i < c.d; i += NL_TPB) { const float dlt = sT[i] - mean; v += dlt * dlt; }
+      const float var = block_sum_nl(v, red) / (float)c.d;
+      const float sd = sqrtf(var + c.ln_eps);
+      rstd = 1.f / sd;
+      if (tid == 0) { l.ln_std[r] = sd; l.ln_mean[r] = mean; }
+    }
+    for (int i = tid; i < c.d; i += NL_TPB) {
+      const float xh = (sT[i] - mean) * rstd;
+      l.xhat[(int64_t)r * c.d + i] = xh;
+      sAct[i] = fmaxf(xh, 0.f);
+    }
+    __syncthreads();
+    matvec_rows(l.w_out, sAct, sO, l.b_out, c.dA, c.d);
+    __syncthreads();
+    for (int i = tid; i < c.dA; i += NL_TPB) {                  // out -> dropout -> residual sum
+      float o = sO[i];
+      l.out[(int64_t)r * c.dA + i] = o;
+      if (c.drop_ratio > 0.f) o *= philox_keep(c.seed, l.drop_offset + step_off, (int64_t)r * c.dA + i, c.drop_ratio);
+      const float a = sA[i] + o;
+      sA[i] = a;
+      l.a_out[(int64_t)r * c.dA + i] = a;
+    }
+    __syncthreads();
+  }
+}
+
+// smem: sA[dA] | sTh[d] | sU[dB] | sS[dB] | sX[d] (xhat) | sV1[max(dA,d,dB)] | sV2[max] | sV3[max] | sDA[dA] | sP[L] | sD[L] | red
+__global__ void __launch_bounds__(NL_TPB, 1) fbo_nl_bwd_k(const NlParams P) {
+  extern __shared__ float sm[];
+  const vlfb_fbo_cfg_t& c = P.c;
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int mx3 = max(c.dA, max(c.d, c.dB));
+  float* sA = sm;
+  float* sTh = sA + c.dA;
+  float* sU = sTh + c.d;
+  float* sS = sU + c.dB;
+  float* sX = sS + c.dB;
+  float* sV1 = sX + c.d;
+  float* sV2 = sV1 + mx3;
+  float* sV3 = sV2 + mx3;
+  float* sDA = sV3 + mx3;
+  float* sP = sDA + c.dA;
+  float* sD = sP + ((c.L + 3) & ~3);
+  float* red = sD + ((c.L + 3) & ~3);
+  const float* B = P.bp + (int64_t)r * c.L * c.dB;
+  float* dB = P.dbp + (int64_t)r * c.L * c.dB;
+  const int per_roi = c.dA + c.d + c.dB + c.d + 4;
+  for (int i = tid; i < c.dA; i += NL_TPB) sDA[i] = P.da_last[(int64_t)r * c.dA + i];
+  __syncthreads();
+  const uint64_t step_off = c.step ? ((uint64_t)c.step[0] << 32) : 0ull;
+  for (int li = c.layers - 1; li >= 0; --li) {
+    const vlfb_fbo_layer_t& l = P.l[li];
+    float* scr = P.scratch + ((int64_t)li * c.R + r) * per_roi;
+    float* g_do = scr;
+    float* g_dt = g_do + c.dA;
+    float* g_du = g_dt + c.d;
+    float* g_dth = g_du + c.dB;
+    float* g_sum = g_dth + c.d;
+    const float* a_in = li == 0 ? P.a0 : P.l[li - 1].a_out;
+    for (int i = tid; i < c.dA; i += NL_TPB) sA[i] = a_in[(int64_t)r * c.dA + i];
+    for (int i = tid; i < c.d; i += NL_TPB) { sTh[i] = l.theta[(int64_t)r * c.d + i]; sX[i] = l.xhat[(int64_t)r * c.d + i]; }
+    for (int i = tid; i < c.dB; i += NL_TPB) sS[i] = l.s[(int64_t)r * c.dB + i];
+    for (int j = tid; j < c.L; j += NL_TPB) sP[j] = l.prob[(int64_t)r * c.L + j];
+    // d(out) = dropout backward of the residual branch; the identity branch keeps sDA
+    for (int i = tid; i < c.dA; i += NL_TPB) {
+      float v = sDA[i];
+      if (c.drop_ratio > 0.f) v *= philox_keep(c.seed, l.drop_offset + step_off, (int64_t)r * c.dA + i, c.drop_ratio);
+      sV1[i] = v;
+      g_do[i] = v;
+    }
+    __syncthreads();
+    matvec_cols(l.w_out, sV1, sV2, c.dA, c.d);                  // d(act) = W_out^T d(out)
+    __syncthreads();
+    // ReLU + LayerNorm backward: dt = (dy - mean(dy) - xhat mean(dy xhat)) / std, dy = d(act) where xhat > 0
+    float m1 = 0.f, m2 = 0.f;
+    for (int i = tid; i < c.d; i += NL_TPB) {
+      const float dy = sX[i] > 0.f ? sV2[i] : 0.f;
+      sV2[i] = dy;
+      m1 += dy; m2 += dy * sX[i];
+    }
+    if (c.pre_act_ln) {
+      m1 = block_sum_nl(m1, red) / (float)c.d;
+      m2 = block_sum_nl(m2, red) / (float)c.d;
+      const float rstd = 1.f / l.ln_std[r];
+      for (int i = tid; i < c.d; i += NL_TPB) sV2[i] = (sV2[i] - m1 - sX[i] * m2) * rstd;
+    }
+    __syncthreads();
+    for (int i = tid; i < c.d; i += NL_TPB) g_dt[i] = sV2[i];
+    matvec_cols(l.w_g, sV2, sV1, c.d, c.dB);                     // ds = W_g^T dt
+    matvec_cols(l.w_phi, sTh, sU, c.d, c.dB);                    // u (recomputed)
+    __syncthreads();
+    for (int j = warp; j < c.L; j += NL_TPB / 32) {              // dp_j = ds . B'_j
+      const float4* b4 = reinterpret_cast<const float4*>(B + (int64_t)j * c.dB);
+      float acc = 0.f;
+      for (int q = lane; q < (c.dB >> 2); q += 32) {
+        const float4 a = b4[q];
+        const float4 v = *reinterpret_cast<const float4*>(sV1 + 4 * q);
+        acc += a.x * v.x + a.y * v.y + a.z * v.z + a.w * v.w;
+      }
+      acc = warp_sum_f(acc);
+      if (lane == 0) sD[j] = acc;
+    }
+    __syncthreads();
+    float dot = 0.f;
+    for (int j = tid; j < c.L; j += NL_TPB) dot += sP[j] * sD[j];
+    dot = block_sum_nl(dot, red);
+    float sds = 0.f;
+    for (int j = tid; j < c.L; j += NL_TPB) { const float v = c.scale * sP[j] * (sD[j] - dot); sD[j] = v; sds += v; }
+    sds = block_sum_nl(sds, red);                                // sum_j dscore_j (= 0 up to rounding)
+    if (tid == 0) g_sum[0] = sds;
+    // du = sum_j dscore_j B'_j ; dB'_j (+)= p_j ds + dscore_j u
+    for (int i = tid; i < c.dB; i += NL_TPB) {
+      const float dsi = sV1[i], ui = sU[i];
+      float a0 = 0.f, a1 = 0.f;
+      int j = 0;
+      const bool first = li == c.layers - 1;                     // the last layer (first visited) overwrites dB'
+      for (; j + 1 < c.L; j += 2) {
+        const int64_t o0 = (int64_t)j * c.dB + i, o1 = o0 + c.dB;
+        a0 += sD[j] * B[o0];
+        a1 += sD[j + 1] * B[o1];
+        const float g0 = sP[j] * dsi + sD[j] * ui, g1 = sP[j + 1] * dsi + sD[j + 1] * ui;
+        dB[o0] = first ? g0 : dB[o0] + g0;
+        dB[o1] = first ? g1 : dB[o1] + g1;
+      }
+      for (; j < c.L; ++j) {
+        const int64_t o0 = (int64_t)j * c.dB + i;
+        a0 += sD[j] * B[o0];
+        const float g0 = sP[j] * dsi + sD[j] * ui;
+        dB[o0] = first ? g0 : dB[o0] + g0;
+      }
+      const float du = a0 + a1;
+      sV3[i] = du;
+      g_du[i] = du;
+    }
+    __syncthreads();
+    matvec_rows(l.w_phi, sV3, sV2, nullptr, c.d, c.dB);          // dtheta = W_phi du (+ b_phi sum_j dscore_j)
+    __syncthreads();
+    for (int i = tid; i < c.d; i += NL_TPB) {
+      const float v = sV2[i] + (l.b_phi ? l.b_phi[i] * sds : 0.f);
+      sV2[i] = v;
+      g_dth[i] = v;
+    }
+    __syncthreads();
+    matvec_cols(l.w_theta, sV2, sV1, c.d, c.dA);                 // dA += W_theta^T dtheta
+    __syncthreads();
+    for (int i = tid; i < c.dA; i += NL_TPB) sDA[i] += sV1[i];
+    __syncthreads();
+  }
+  for (int i = tid; i < c.dA; i += NL_TPB) P.da0[(int64_t)r * c.dA + i] = sDA[i];
+}
+
+// Weight gradients of all layers: dW[o][i] += sum_r left[r][o] right[r][i]; biases: sum_r left[r][o].
+// grid = (row blocks, 4 * layers); which: 0 = out (do x act), 1 = g (dt x s), 2 = phi (theta x du), 3 = theta (dtheta x a_in)
+__global__ void __launch_bounds__(256) fbo_nl_outer_k(const NlParams P) {
+  const vlfb_fbo_cfg_t& c = P.c;
+  const int li = blockIdx.y >> 2, which = blockIdx.y & 3;
+  const vlfb_fbo_layer_t& l = P.l[li];
+  const int per_roi = c.dA + c.d + c.dB + c.d + 4;
+  const float* scr = P.scratch + (int64_t)li * c.R * per_roi;
+  const float* left;
+  const float* right;
+  int rows, cols, lstride, rstride;
+  float* gw;
+  float* gb;
+  const float* a_in = li == 0 ? P.a0 : P.l[li - 1].a_out;
+  if (which == 0) { left = scr; lstride = per_roi; right = l.xhat; rstride = c.d; rows = c.dA; cols = c.d; gw = l.gw_out; gb = l.gb_out; }
+  else if (which == 1) { left = scr + c.dA; lstride = per_roi; right = l.s; rstride = c.dB; rows = c.d; cols = c.dB; gw = l.gw_g; gb = l.gb_g; }
+  else if (which == 2) { left = l.theta; lstride = c.d; right = scr + c.dA + c.d; rstride = per_roi; rows = c.d; cols = c.dB; gw = l.gw_phi; gb = l.gb_phi; }
+  else { left = scr + c.dA + c.d + c.dB; lstride = per_roi; right = a_in; rstride = c.dA; rows = c.d; cols = c.dA; gw = l.gw_theta; gb = l.gb_theta; }
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    if (gw) {
+      for (int i = threadIdx.x; i < cols; i += blockDim.x) {
+        float acc = 0.f;
+        for (int r = 0; r < c.R; ++r) {
+          float rv = right[(int64_t)r * rstride + i];
+          if (which == 0) rv = fmaxf(rv, 0.f);                   // act = relu(xhat)
+          acc += left[(int64_t)r * lstride + row] * rv;
+        }
+        gw[(int64_t)row * cols + i] += acc;
+      }
+    }
+    if (gb && threadIdx.x == 0) {
+      float acc = 0.f;
+      for (int r = 0; r < c.R; ++r) {
+        float lv = left[(int64_t)r * lstride + row];
+        if (which == 2) lv *= scr[(int64_t)r * per_roi + c.dA + c.d + c.dB + c.d];   // theta_o * sum_j dscore_j
+        acc += lv;
+      }
+      gb[row] += acc;
+    }
+  }
+}
+
 }  // namespace
 }  // namespace vlfb
 
@@ -231,6 +600,83 @@ int vlfb_fbo_bank_scan(const float* bank, const float* q, float scale, float* ou
   VLFB_CHECK_LAUNCH();
   launch_k(fbo_bank_combine_k, dim3((unsigned)(D / 256), (unsigned)R), 256, 0, ST(stream), (const float*)part_acc,
            (const float*)part_ml, out, prob, S, D, L, tf32_out);
+  VLFB_CHECK_LAUNCH();
+  return VLFB_OK;
+}
+
+static int nl_validate(const vlfb_fbo_cfg_t* c, const vlfb_fbo_layer_t* layers) {
+  VLFB_CHECK_ARG(c && layers);
+  VLFB_CHECK_ARG(c->R >= 1 && c->L >= 1 && c->layers >= 1 && c->layers <= NL_MAX_LAYERS);
+  VLFB_CHECK_ARG(c->dA >= 4 && c->d >= 4 && c->dB >= 4 && (c->dA & 3) == 0 && (c->d & 3) == 0 && (c->dB & 3) == 0);
+  VLFB_CHECK_ARG(c->pre_act == 1 && c->drop_ratio >= 0.f && c->drop_ratio < 1.f);
+  for (int i = 0; i < c->layers; ++i) {
+    const vlfb_fbo_layer_t& l = layers[i];
+    VLFB_CHECK_ARG(l.w_theta && l.w_phi && l.w_g && l.w_out && l.theta && l.prob && l.s && l.t && l.xhat && l.ln_mean &&
+                   l.ln_std && l.out && l.a_out);
+  }
+  return VLFB_OK;
+}
+
+static void nl_fill(NlParams& P, const vlfb_fbo_cfg_t* c, const vlfb_fbo_layer_t* layers) {
+  memset(&P, 0, sizeof(P));
+  P.c = *c;
+  for (int i = 0; i < c->layers; ++i) P.l[i] = layers[i];
+}
+
+size_t vlfb_fbo_nl_scratch_floats(const vlfb_fbo_cfg_t* c) {
+  if (!c || c->R < 1 || c->layers < 1) return 0;
+  return (size_t)c->layers * c->R * (size_t)(c->dA + c->d + c->dB + c->d + 4);
+}
+
+int vlfb_fbo_nl_fwd(const vlfb_fbo_cfg_t* c, const vlfb_fbo_layer_t* layers, const float* a0, const float* bp,
+                    void* stream) {
+  const int rc = nl_validate(c, layers);
+  if (rc != VLFB_OK) return rc;
+  VLFB_CHECK_ARG(a0 && bp);
+  NlParams P;
+  nl_fill(P, c, layers);
+  P.a0 = a0; P.bp = bp;
+  const size_t smem = ((size_t)2 * c->dA + 3 * c->d + 2 * c->dB + ((c->L + 3) & ~3) + 32) * sizeof(float);
+  VLFB_CHECK_ARG(smem <= 200 * 1024);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    if (cudaFuncSetAttribute(fbo_nl_fwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+      set_error("fbo_nl_fwd: cudaFuncSetAttribute failed");
+      return VLFB_E_CUDA;
+    }
+    attr = 200 * 1024;
+  }
+  launch_k(fbo_nl_fwd_k, dim3(c->R), dim3(NL_TPB), smem, ST(stream), P);
+  VLFB_CHECK_LAUNCH();
+  return VLFB_OK;
+}
+
+int vlfb_fbo_nl_bwd(const vlfb_fbo_cfg_t* c, const vlfb_fbo_layer_t* layers, const float* a0, const float* bp,
+                    const float* da_last, float* da0, float* dbp, float* scratch, size_t scratch_floats, void* stream) {
+  const int rc = nl_validate(c, layers);
+  if (rc != VLFB_OK) return rc;
+  VLFB_CHECK_ARG(a0 && bp && da_last && da0 && dbp && scratch);
+  if (scratch_floats < vlfb_fbo_nl_scratch_floats(c)) {
+    set_error("vlfb_fbo_nl_bwd: scratch of %zu floats, %zu needed", scratch_floats, vlfb_fbo_nl_scratch_floats(c));
+    return VLFB_E_WORKSPACE;
+  }
+  NlParams P;
+  nl_fill(P, c, layers);
+  P.a0 = a0; P.bp = bp; P.da_last = da_last; P.da0 = da0; P.dbp = dbp; P.scratch = scratch;
+  const int mx3 = c->dA > c->d ? (c->dA > c->dB ? c->dA : c->dB) : (c->d > c->dB ? c->d : c->dB);
+  const size_t smem = ((size_t)2 * c->dA + 2 * c->d + 2 * c->dB + 3 * mx3 + 2 * ((c->L + 3) & ~3) + 32) * sizeof(float);
+  VLFB_CHECK_ARG(smem <= 200 * 1024);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    if (cudaFuncSetAttribute(fbo_nl_bwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+      set_error("fbo_nl_bwd: cudaFuncSetAttribute failed");
+      return VLFB_E_CUDA;
+    }
+    attr = 200 * 1024;
+  }
+  launch_k(fbo_nl_bwd_k, dim3(c->R), dim3(NL_TPB), smem, ST(stream), P);
+  VLFB_CHECK_LAUNCH();
+  launch_k(fbo_nl_outer_k, dim3(128, 4 * c->layers), dim3(256), 0, ST(stream), P);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }

@@ -662,88 +662,6 @@ __global__ void sgd_k(float* __restrict__ p, float* __restrict__ g, float* __res
   }
 }
 
-// ------------------------------------------------------------------ fused FBO attention core
-// One block per RoI: scores -> softmax -> weighted sum.  smem: L floats.
-__global__ void fbo_attend_fwd_k(const float* __restrict__ theta, const float* __restrict__ phi,
-                                 const float* __restrict__ g, float* __restrict__ prob, float* __restrict__ y, int L,
-                                 int d, float scale) {
-  extern __shared__ float sc[];
-  __shared__ float red[32];
-  const int r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const float* th = theta + (int64_t)r * d;
-  const float* ph = phi + (int64_t)r * L * d;
-  const float* gg = g + (int64_t)r * L * d;
-  for (int l = warp; l < L; l += nw) {
-    float s = 0.f;
-    for (int c = lane * 4; c < d; c += 128) {
-      const float4 a = *reinterpret_cast<const float4*>(th + c);
-      const float4 b = *reinterpret_cast<const float4*>(ph + (int64_t)l * d + c);
-      s += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
-    }
-    s = warp_sum(s);
-    if (lane == 0) sc[l] = s * scale;
-  }
-  __syncthreads();
-  float mx = -FLT_MAX;
-  for (int l = threadIdx.x; l < L; l += blockDim.x) mx = fmaxf(mx, sc[l]);
-  mx = block_max(mx, red);
-  float sum = 0.f;
-  for (int l = threadIdx.x; l < L; l += blockDim.x) { const float e = __expf(sc[l] - mx); sc[l] = e; sum += e; }
-  sum = block_sum(sum, red);
-  const float inv = 1.f / sum;
-  for (int l = threadIdx.x; l < L; l += blockDim.x) { const float pv = sc[l] * inv; sc[l] = pv; prob[(int64_t)r * L + l] = pv; }
-  __syncthreads();
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    float acc = 0.f;
-    for (int l = 0; l < L; ++l) acc += sc[l] * gg[(int64_t)l * d + c];
-    y[(int64_t)r * d + c] = acc;
-  }
-}
-
-__global__ void fbo_attend_bwd_k(const float* __restrict__ theta, const float* __restrict__ phi,
-                                 const float* __restrict__ g, const float* __restrict__ prob,
-                                 const float* __restrict__ dy, float* __restrict__ dtheta, float* __restrict__ dphi,
-                                 float* __restrict__ dg, int L, int d, float scale) {
-  extern __shared__ float ds[];   // L floats: dp then ds
-  __shared__ float red[32];
-  const int r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const float* th = theta + (int64_t)r * d;
-  const float* ph = phi + (int64_t)r * L * d;
-  const float* gg = g + (int64_t)r * L * d;
-  const float* pr = prob + (int64_t)r * L;
-  const float* dyr = dy + (int64_t)r * d;
-  for (int l = warp; l < L; l += nw) {            // dp[l] = g[l].dy ; dg[l] = p[l]*dy
-    float s = 0.f;
-    const float pl = pr[l];
-    for (int c = lane * 4; c < d; c += 128) {
-      const float4 a = *reinterpret_cast<const float4*>(dyr + c);
-      const float4 b = *reinterpret_cast<const float4*>(gg + (int64_t)l * d + c);
-      s += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
-      *reinterpret_cast<float4*>(dg + ((int64_t)r * L + l) * d + c) = make_float4(pl * a.x, pl * a.y, pl * a.z, pl * a.w);
-    }
-    s = warp_sum(s);
-    if (lane == 0) ds[l] = s;
-  }
-  __syncthreads();
-  float dot = 0.f;
-  for (int l = threadIdx.x; l < L; l += blockDim.x) dot += pr[l] * ds[l];
-  dot = block_sum(dot, red);
-  for (int l = threadIdx.x; l < L; l += blockDim.x) ds[l] = scale * pr[l] * (ds[l] - dot);
-  __syncthreads();
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {   // dtheta = sum_l ds[l]*phi[l]
-    float acc = 0.f;
-    for (int l = 0; l < L; ++l) acc += ds[l] * ph[(int64_t)l * d + c];
-    dtheta[(int64_t)r * d + c] = acc;
-  }
-  for (int l = warp; l < L; l += nw) {            // dphi[l] = ds[l]*theta
-    const float s = ds[l];
-    for (int c = lane * 4; c < d; c += 128) {
-      const float4 a = *reinterpret_cast<const float4*>(th + c);
-      *reinterpret_cast<float4*>(dphi + ((int64_t)r * L + l) * d + c) = make_float4(s * a.x, s * a.y, s * a.z, s * a.w);
-    }
-  }
-}
-
 }  // namespace
 }  // namespace vlfb
 
@@ -1036,25 +954,6 @@ int vlfb_sgd_nesterov(float* p, float* g, float* m, float* p_tf32, int64_t n, co
   VLFB_CHECK_ARG(p && g && m && lr && n >= 0);
   if (n == 0) return VLFB_OK;
   launch_k(sgd_k, stream_grid(n, TPB, 4), TPB, 0, ST(stream), p, g, m, p_tf32, n, lr, momentum, wd, nesterov);
-  VLFB_CHECK_LAUNCH();
-  return VLFB_OK;
-}
-
-int vlfb_fbo_attend_fwd(const float* theta, const float* phi, const float* g, float* prob, float* y, int R, int L, int d,
-                        float scale, void* stream) {
-  VLFB_CHECK_ARG(theta && phi && g && prob && y && R >= 0 && L > 0 && d > 0 && (d & 3) == 0 && L <= 12000);
-  if (R == 0) return VLFB_OK;
-  launch_k(fbo_attend_fwd_k, R, 512, L * sizeof(float), ST(stream), theta, phi, g, prob, y, L, d, scale);
-  VLFB_CHECK_LAUNCH();
-  return VLFB_OK;
-}
-
-int vlfb_fbo_attend_bwd(const float* theta, const float* phi, const float* g, const float* prob, const float* dy,
-                        float* dtheta, float* dphi, float* dg, int R, int L, int d, float scale, void* stream) {
-  VLFB_CHECK_ARG(theta && phi && g && prob && dy && dtheta && dphi && dg && R >= 0 && L > 0 && d > 0 && (d & 3) == 0 &&
-                 L <= 12000);
-  if (R == 0) return VLFB_OK;
-  launch_k(fbo_attend_bwd_k, R, 512, L * sizeof(float), ST(stream), theta, phi, g, prob, dy, dtheta, dphi, dg, L, d, scale);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }

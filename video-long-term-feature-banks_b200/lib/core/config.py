@@ -101,7 +101,7 @@ __C = _tree({
     # ---- additions of this implementation (not in the reference) -------------
     # B200.COMPUTE: 'tf32' = parity mode (fp32 storage, tcgen05 kind::tf32, fp32 accumulate).
     # B200.FBO_FOLD: inference nets run each FBO-NL layer as one pass over the raw bank (vlfb.executor.FboFoldStep).
-    'B200': {'COMPUTE': 'tf32', 'GEMM_BACKEND': 'tcgen05', 'CUDA_GRAPH': True, 'FBO_FOLD': True},
+    'B200': {'COMPUTE': 'tf32', 'GEMM_BACKEND': 'tcgen05', 'CUDA_GRAPH': True, 'FBO_FOLD': True, 'FBO_STACK': True},
 })
 config = __C
 _DEFAULTS = None

@@ -131,6 +131,14 @@ def NLCore(model, in_blob1, in_blob2, in_dim1, in_dim2, latent_dim, num_feat1, n
 
 def NLLayers(model, A, B, in_dim1, in_dim2, latent_dim, num_feat1, num_feat2, prefix, test_mode):
     """Stack FBO_NL.NUM_LAYERS residual NL layers; only A is updated between layers."""
+    if (cfg.B200.get('FBO_STACK', True) and not test_mode and num_feat1 == 1 and cfg.FBO_NL.PRE_ACT
+            and cfg.FBO_NL.NUM_LAYERS <= 4 and in_dim2 == latent_dim):
+        # training graphs, one query per RoI: all layers in one launch per direction, phi / g folded onto the shared
+        # projected bank (same parameters, same output blobs; B200.FBO_STACK False keeps the as-written operators)
+        drop = cfg.FBO_NL.DROPOUT_RATE if cfg.FBO_NL.LFB_DROPOUT_ON else 0.0
+        return model.FboNLStack(A, B, prefix, in_dim1, in_dim2, latent_dim, num_feat2, cfg.FBO_NL.NUM_LAYERS,
+                                init_params1, init_params2, scale=latent_dim ** -.5 if cfg.FBO_NL.SCALE else 1.0,
+                                pre_act_ln=cfg.FBO_NL.PRE_ACT_LN, dropout_ratio=drop)
     nl_out = None
     for layer in range(cfg.FBO_NL.NUM_LAYERS):
         name = prefix + '_nl%d' % layer

@@ -75,6 +75,30 @@ class CNNModelHelper(object):
             'SpatialBN (trainable BN) is a "next" row (SURVEY.md section 8f rank 4); every shipped config '
             'uses the Affine (frozen-BN) variant: set MODEL.USE_AFFINE / NONLOCAL.USE_AFFINE True')
 
+    def FboNLStack(self, blob_a, blob_b, prefix, dim_a, dim_b, latent_dim, num_feat2, num_layers, init1, init2,
+                   scale=1.0, pre_act_ln=True, dropout_ratio=0.0):
+        """All layers of lfb_helper.NLLayers (one query per RoI, FBO_NL.PRE_ACT) as ONE operator (B200.FBO_STACK).
+        Creates exactly the parameters NLCore's four ConvNd calls create -- '{prefix}_nl{l}_{theta,phi,g,out}_w/_b'
+        with their 5-D conv shapes and initialisers -- so checkpoints are interchangeable with the as-written graph,
+        and emits the blobs '{prefix}_nl{l}_{theta,affinity_prob,y,out,sum}'; phi / g / affinity are never formed
+        (vlfb_fbo_nl_fwd, csrc/fbo.cu section 3).  Returns the last layer's sum."""
+        inputs, outputs = [blob_a, blob_b], []
+        for layer in range(num_layers):
+            name = prefix + '_nl%d' % layer
+            for part, (dout, din, init) in (('theta', (latent_dim, dim_a, init1)), ('phi', (latent_dim, dim_b, init1)),
+                                            ('g', (latent_dim, dim_b, init1)), ('out', (dim_a, latent_dim, init2))):
+                inputs.append(self._make_param('%s_%s_w' % (name, part), [dout, din, 1, 1, 1],
+                                               init.get('weight_init') or ('XavierFill', {}), True))
+                if not init.get('no_bias', 0):
+                    inputs.append(self._make_param('%s_%s_b' % (name, part), [dout],
+                                                   init.get('bias_init') or ('ConstantFill', {'value': 0.}), False))
+            outputs += [name + '_theta', name + '_affinity_prob', name + '_y', name + '_out', name + '_sum']
+        outs = self.net.FboNLStack(inputs, outputs, prefix=prefix, dim_a=int(dim_a), dim_b=int(dim_b),
+                                   latent_dim=int(latent_dim), num_feat2=int(num_feat2), num_layers=int(num_layers),
+                                   scale=float(scale), pre_act_ln=bool(pre_act_ln), ratio=float(dropout_ratio),
+                                   no_bias=[int(bool(i.get('no_bias', 0))) for i in (init1, init1, init1, init2)])
+        return outs[-1]
+
     # ---- parameter-free layers -------------------------------------------------
     def MaxPool(self, blob_in, blob_out, kernels=None, strides=None, pads=None, **kwargs):
         return self.net.MaxPool(blob_in, blob_out, kernels=list(kernels), strides=list(strides or [1] * len(kernels)),

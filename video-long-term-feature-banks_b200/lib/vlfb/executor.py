@@ -643,6 +643,91 @@ class FboFoldStep(Step):
         raise NotImplementedError('FboFoldStep is an inference-mode lowering')
 
 
+class FboStackStep(Step):
+    """Training-mode FBO-NL stack: every layer of lfb_helper.NLLayers in one launch per direction (the builder emits
+    one 'FboNLStack' operator when B200.FBO_STACK is on; cnn.CNNModelHelper.FboNLStack).  phi and g are folded onto
+    the shared projected bank B' (csrc/fbo.cu section 3): the as-written graph spends 4 GEMMs forward + 8 backward
+    per layer on R*L = 1200 rows plus ~35 streaming launches; this step is 1 + 2 kernels whatever the layer count."""
+    PARTS = ('theta', 'phi', 'g', 'out')
+
+    def __init__(self, op, in_keys, out_keys):
+        Step.__init__(self, op, in_keys, out_keys)
+        a = op.args
+        self.n = a['num_layers']
+        names = list(op.inputs[2:])
+        self.layer_params = []
+        for _ in range(self.n):
+            lp = {}
+            for part, nb in zip(self.PARTS, a['no_bias']):
+                lp['w_' + part] = names.pop(0)
+                lp['b_' + part] = None if nb else names.pop(0)
+            self.layer_params.append(lp)
+        assert not names
+        self.params = list(op.inputs[2:])
+
+    def _cfg(self, ctx, R, L_, dropout):
+        a = self.op.args
+        return dict(R=R, L=L_, dA=a['dim_a'], d=a['latent_dim'], dB=a['dim_b'], scale=a['scale'], pre_act_ln=a['pre_act_ln'],
+                    ln_eps=1e-5, drop_ratio=a['ratio'] if dropout else 0.0, seed=ctx.ws.rng_seed,
+                    step=ctx.ws.step_tensor() if dropout else None)
+
+    def fwd(self, ctx):
+        a = self.op.args
+        P = ctx.ws.params
+        A = ctx.get(self.op.inputs[0])
+        B = ctx.get(self.op.inputs[1])
+        R, dA, d, dB = int(A.shape[0]), a['dim_a'], a['latent_dim'], a['dim_b']
+        a0 = flat(A).view(R, dA)
+        bp = phys(B).reshape(R, -1, dB)                       # channels-last storage of (R, dB, L, 1, 1) = [R][L][dB]
+        L_ = int(bp.shape[1])
+        assert L_ == a['num_feat2']
+        dropout = a['ratio'] > 0.0 and ctx.ws.dropout_enabled and ctx.net.train
+        layers = []
+        for li, lp in enumerate(self.layer_params):
+            ld = dict((k, None if n is None else P.phys(n).view(-1) if k.startswith('b_') else P.phys(n).view(P.phys(n).shape[0], -1))
+                      for k, n in lp.items())
+            ld.update(theta=empty((R, d)), prob=empty((R, L_)), s=empty((R, dB)), t=empty((R, d)), xhat=empty((R, d)),
+                      ln_mean=empty((R,)), ln_std=empty((R,)), out=empty((R, dA)), a_out=empty((R, dA)))
+            ld['drop_offset'] = ctx.ws.next_rng(R * dA)[1] if dropout else 0
+            layers.append(ld)
+        cfgd = self._cfg(ctx, R, L_, dropout)
+        K.fbo_nl_fwd(cfgd, layers, a0, bp)
+        outs = self.op.outputs
+        for li, ld in enumerate(layers):
+            th, pr, y, out, sm = outs[5 * li:5 * li + 5]
+            ctx.put(th, ld['theta'].view(R, d, 1))
+            ctx.put(pr, ld['prob'].view(R, 1, L_))
+            ctx.put(y, ld['t'].view(R, d, 1, 1, 1))
+            ctx.put(out, ld['out'].view(R, dA, 1, 1, 1))
+            ctx.put(sm, ld['a_out'].view(R, dA, 1, 1, 1))
+        ctx.saved[id(self)] = (cfgd, layers, a0, bp, A.shape, B.shape, B.stride())
+
+    def bwd(self, ctx):
+        for k in self.out_keys[:-1]:
+            assert ctx.pop_grad(k) is None, 'only the last sum of an FBO-NL stack is consumed downstream'
+        gy = ctx.pop_grad(self.out_keys[-1])
+        if gy is None:
+            return
+        cfgd, layers, a0, bp, ashape, bshape, bstride = ctx.saved.pop(id(self))
+        store = ctx.ws.params
+        for ld, lp in zip(layers, self.layer_params):
+            for k, n in lp.items():
+                ld['g' + k] = None
+                if n is not None and store.trainable(n):
+                    g = store.grad(n)
+                    ld['g' + k] = g.view(-1) if k.startswith('b_') else g.view(g.shape[0], -1)
+        R = cfgd['R']
+        da0 = empty((R, cfgd['dA']))
+        dbl = torch.empty_strided(bshape, bstride, dtype=DTYPE, device=DEVICE)       # gradient of B in B's own layout
+        dbp = phys(dbl).reshape(R, -1, cfgd['dB'])
+        gyf = flat(gy).view(R, cfgd['dA'])
+        if not gyf.is_contiguous():
+            gyf = gyf.contiguous()
+        K.fbo_nl_bwd(cfgd, layers, a0, bp, gyf, da0, dbp)
+        ctx.add_grad(self.in_keys[0], da0.view(ashape), owned=True)
+        ctx.add_grad(self.in_keys[1], dbl, owned=True)
+
+
 class LayerNormStep(Step):
     def fwd(self, ctx):
         x = ctx.get(self.op.inputs[0])
@@ -839,7 +924,7 @@ STEP_TYPES = {
     'Squeeze': SqueezeStep, 'StopGradient': StopGradientStep, 'BatchMatMul': BatchMatMulStep,
     'LayerNorm': LayerNormStep, 'Dropout': DropoutStep, 'FC': FCStep, 'Concat': ConcatStep,
     'RoIAlign': RoIAlignStep, 'Sigmoid': SigmoidStep, 'SigmoidCrossEntropyLoss': SigmoidCELossStep,
-    'SoftmaxWithLoss': SoftmaxCELossStep, 'DequeueBlobs': NoopStep,
+    'SoftmaxWithLoss': SoftmaxCELossStep, 'DequeueBlobs': NoopStep, 'FboNLStack': FboStackStep,
 }
 OPTIMIZER_OPS = ('WeightedSum', 'MomentumSGDUpdate')
 

@@ -14,7 +14,7 @@ NUM_SMS = 148
 
 
 LAUNCHES = 0            # kernels launched through this module (bench.py reports it as gpu_launches)
-_PROFILE = None         # when a list: (name, start_event, end_event, flops, bytes, label) per tensor-core GEMM launch
+_PROFILE = None         # when a list: (name, relaunch closure, flops, bytes, label, kept-alive operands) per profiled launch
 LABEL = ''              # blob name of the graph step being executed (set by the executor; profile records carry it)
 
 
@@ -25,17 +25,34 @@ def _check(rc, what):
 
 
 def start_profile():
+    """Record every tensor-core GEMM launch (its parameter block and operand tensors) until stop_profile()."""
     global _PROFILE
     _PROFILE = []
 
 
-def stop_profile():
+def stop_profile(reps=5):
     """Returns [(kind, milliseconds, flops, algorithmic_bytes, label)] of the GEMM launches since start_profile().
+    milliseconds = DEVICE time of the launch: each recorded launch is replayed `reps` times back to back on the
+    stream between two CUDA events (after one warm-up replay), so the host's launch latency -- which dominates an
+    eager step of ~600 short kernels -- is not in the number.  The replays re-run the same parameter block on the
+    same (kept-alive) operands; accumulating launches therefore leave garbage in their outputs: profile LAST.
     algorithmic bytes = every operand / result tensor of the launch once (the im2col expansion is not counted)."""
-    global _PROFILE
+    global _PROFILE, LAUNCHES
     recs, _PROFILE = _PROFILE, None
     torch.cuda.synchronize()
-    return [(k, s.elapsed_time(e), f, b, lab) for k, s, e, f, b, lab in (recs or [])]
+    out = []
+    n0 = LAUNCHES
+    for name, relaunch, flops, nbytes, label, _keep in (recs or []):
+        L.check(relaunch(), name + ' (profile replay)')
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            relaunch()
+        e.record()
+        e.synchronize()
+        out.append((name, s.elapsed_time(e) / reps, flops, nbytes, label))
+    LAUNCHES = n0
+    return out
 
 
 def _stream():
@@ -120,18 +137,17 @@ def _nbytes(*ts):
     return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
 
 
-def _run_gemm(p, kind='gemm', flops=None, nbytes=0.0):
+def _run_gemm(p, kind='gemm', flops=None, nbytes=0.0, keep=()):
+    _check(L.load().vlfb_gemm(C.byref(p), _stream()), 'vlfb_gemm')
     if _PROFILE is not None:
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        _check(L.load().vlfb_gemm(C.byref(p), _stream()), 'vlfb_gemm')
-        e.record()
         if flops is None:
             flops = 2.0 * p.M * p.N * p.K * max(p.batch, 1) * max(p.taps, 1)
-        _PROFILE.append(('%s M=%d N=%d K=%d z=%d%s' % (kind, p.M, p.N, p.K, max(p.batch, p.taps), 'xauto' if p.split_k == 0 else ''), s, e, flops,
-                         nbytes, LABEL))
-        return
-    _check(L.load().vlfb_gemm(C.byref(p), _stream()), 'vlfb_gemm')
+        q = L.GemmParams()
+        C.memmove(C.byref(q), C.byref(p), C.sizeof(L.GemmParams))
+        lib, st = L.load(), _stream()
+        _PROFILE.append(('%s M=%d N=%d K=%d z=%d%s' % (kind, p.M, p.N, p.K, max(p.batch, p.taps),
+                                                      'xauto' if p.split_k == 0 else ''),
+                         lambda: lib.vlfb_gemm(C.byref(q), st), flops, nbytes, LABEL, keep))
 
 
 def _base_params(M, N, K, d, ldd, alpha=1.0):
@@ -194,7 +210,7 @@ def conv_fwd(x, w, y, g, scale=None, bias=None, residual=None, relu=False, tf32_
     p.g = g
     _set_epilogue(p, scale, bias, None, residual, relu, tf32_out)
     _run_gemm(p, 'conv_fwd', 2.0 * M * g.Co * g.kT * g.kH * g.kW * (3 if g.C == 4 else g.C),
-              _nbytes(x, w, y, residual))
+              _nbytes(x, w, y, residual), keep=(x, w, y, scale, bias, residual))
 
 
 def conv_dgrad(dy, wt, dx, g, accumulate=False, residual=None, relu_mask=None, tf32_out=False):
@@ -227,7 +243,8 @@ def conv_dgrad(dy, wt, dx, g, accumulate=False, residual=None, relu_mask=None, t
         p.flags |= L.EPI_TF32
     # algorithmic dgrad work = forward MACs of the same layer
     _run_gemm(p, 'conv_dgrad', 2.0 * g.N * g.To * g.Ho * g.Wo * g.Co * g.kT * g.kH * g.kW * g.C,
-              _nbytes(dy, wt, dx, residual, relu_mask) + (_nbytes(dx) if accumulate else 0.0))
+              _nbytes(dy, wt, dx, residual, relu_mask) + (_nbytes(dx) if accumulate else 0.0),
+              keep=(dy, wt, dx, residual, relu_mask))
 
 
 def conv_wgrad(dy, x, dw, g, row_scale=None, col_mask=None):
@@ -257,7 +274,7 @@ def conv_wgrad(dy, x, dw, g, row_scale=None, col_mask=None):
     p.flags |= L.EPI_ATOMIC
     _set_epilogue(p, col_mask, None, row_scale, None, False)
     _run_gemm(p, 'conv_wgrad', 2.0 * Kpos * g.Co * g.kT * g.kH * g.kW * (3 if g.C == 4 else g.C),
-              _nbytes(dy, x, dw))
+              _nbytes(dy, x, dw), keep=(dy, x, dw, row_scale, col_mask))
 
 
 def weight_transpose(w, wt, scale=None):
@@ -322,7 +339,8 @@ def matmul(a, b, d, alpha=1.0, accumulate=False, bias=None, tf32_out=False):
     elif accumulate:
         p.flags |= L.EPI_ACCUM
     _set_epilogue(p, None, bias, None, None, False, tf32_out)
-    _run_gemm(p, 'matmul', 2.0 * Bt * M * N * K, 4.0 * Bt * (M * K + K * N + M * N * (2 if accumulate else 1)))
+    _run_gemm(p, 'matmul', 2.0 * Bt * M * N * K, 4.0 * Bt * (M * K + K * N + M * N * (2 if accumulate else 1)),
+              keep=(a, b, d, bias))
 
 
 def weight_transpose_multi(jobs, cache):
@@ -529,17 +547,54 @@ def sgd_nesterov(p, g, m, lr, momentum, wd, nesterov=True, p_tf32=None):
                                        float(momentum), float(wd), int(bool(nesterov)), _stream()), 'sgd_nesterov')
 
 
-def fbo_attend_fwd(theta, phi, g, prob, y, scale):
-    r, l, d = phi.shape
-    _check(L.load().vlfb_fbo_attend_fwd(_ptr(_f32c(theta)), _ptr(_f32c(phi)), _ptr(_f32c(g)), _ptr(_f32c(prob)),
-                                         _ptr(_f32c(y)), r, l, d, float(scale), _stream()), 'fbo_attend_fwd')
+# --------------------------------------------------------------------------- training-mode FBO-NL stack (csrc/fbo.cu 3)
+FBO_LAYER_KEYS = ('w_theta', 'b_theta', 'w_phi', 'b_phi', 'w_g', 'b_g', 'w_out', 'b_out',
+                  'gw_theta', 'gb_theta', 'gw_phi', 'gb_phi', 'gw_g', 'gb_g', 'gw_out', 'gb_out',
+                  'theta', 'prob', 's', 't', 'xhat', 'ln_mean', 'ln_std', 'out', 'a_out')
 
 
-def fbo_attend_bwd(theta, phi, g, prob, dy, dtheta, dphi, dg, scale):
-    r, l, d = phi.shape
-    _check(L.load().vlfb_fbo_attend_bwd(_ptr(_f32c(theta)), _ptr(_f32c(phi)), _ptr(_f32c(g)), _ptr(_f32c(prob)),
-                                         _ptr(_f32c(dy)), _ptr(_f32c(dtheta)), _ptr(_f32c(dphi)), _ptr(_f32c(dg)),
-                                         r, l, d, float(scale), _stream()), 'fbo_attend_bwd')
+def _fbo_structs(cfgd, layers):
+    c = L.FboCfg()
+    for k in ('R', 'L', 'dA', 'd', 'dB'):
+        setattr(c, k, int(cfgd[k]))
+    c.layers = len(layers)
+    c.scale, c.pre_act, c.pre_act_ln = float(cfgd['scale']), 1, int(bool(cfgd['pre_act_ln']))
+    c.ln_eps, c.drop_ratio, c.seed = float(cfgd.get('ln_eps', 1e-5)), float(cfgd.get('drop_ratio', 0.0)), int(cfgd.get('seed', 0))
+    step = cfgd.get('step')
+    c.step = step.data_ptr() if step is not None else None
+    arr = (L.FboLayer * len(layers))()
+    for i, ld in enumerate(layers):
+        for k in FBO_LAYER_KEYS:
+            t = ld.get(k)
+            if t is not None:
+                _f32c(t, k)
+                assert t.is_cuda
+            setattr(arr[i], k, None if t is None else t.data_ptr())
+        arr[i].drop_offset = int(ld.get('drop_offset', 0))
+    return c, arr
+
+
+def fbo_nl_fwd(cfgd, layers, a0, bp):
+    """All FBO-NL layers forward in one launch.  cfgd: R, L, dA, d, dB, scale, pre_act_ln, [ln_eps, drop_ratio, seed,
+    step]; layers: dicts of tensors keyed by FBO_LAYER_KEYS (weights [out][in], saved activations [R][...])."""
+    _f32c(a0, 'a0'), _f32c(bp, 'bp')
+    assert tuple(a0.shape) == (cfgd['R'], cfgd['dA']) and tuple(bp.shape) == (cfgd['R'], cfgd['L'], cfgd['dB'])
+    c, arr = _fbo_structs(cfgd, layers)
+    _check(L.load().vlfb_fbo_nl_fwd(C.byref(c), arr, _ptr(a0), _ptr(bp), _stream()), 'fbo_nl_fwd')
+
+
+def fbo_nl_bwd(cfgd, layers, a0, bp, da_last, da0, dbp):
+    """Backward of fbo_nl_fwd: da0, dbp (overwritten) and the accumulated weight gradients (layers[i]['gw_*'])."""
+    global LAUNCHES
+    for t in (a0, bp, da_last, da0, dbp):
+        _f32c(t)
+    c, arr = _fbo_structs(cfgd, layers)
+    lib = L.load()
+    n = int(lib.vlfb_fbo_nl_scratch_floats(C.byref(c)))
+    scratch = torch.empty(n, dtype=torch.float32, device=a0.device)
+    _check(lib.vlfb_fbo_nl_bwd(C.byref(c), arr, _ptr(a0), _ptr(bp), _ptr(da_last), _ptr(da0), _ptr(dbp), _ptr(scratch),
+                               C.c_size_t(n), _stream()), 'fbo_nl_bwd')
+    LAUNCHES += 1                 # two kernels (per-RoI backward + rank-R weight gradients)
 
 
 # --------------------------------------------------------------------------- raw feature-bank kernels (csrc/fbo.cu)
@@ -556,14 +611,12 @@ def fbo_bank_scan(bank, q, out, scale, prob=None, tf32_out=False):
     if nbytes == 0 and r > 0:
         raise L.VlfbError('fbo_bank_scan: unsupported bank row width %d (1024, 2048 or 4096)' % d)
     wsp = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=bank.device)
+    args = (_ptr(bank), _ptr(q), float(scale), _ptr(out), _ptr(prob), r, l, d, int(tf32_out), _ptr(wsp), C.c_size_t(nbytes),
+            _stream())
+    _check(lib.vlfb_fbo_bank_scan(*args), 'fbo_bank_scan')
     if _PROFILE is not None:
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-    _check(lib.vlfb_fbo_bank_scan(_ptr(bank), _ptr(q), float(scale), _ptr(out), _ptr(prob), r, l, d, int(tf32_out),
-                                  _ptr(wsp), C.c_size_t(nbytes), _stream()), 'fbo_bank_scan')
-    if _PROFILE is not None:
-        e.record()
-        _PROFILE.append(('fbo_bank_scan R=%d L=%d D=%d' % (r, l, d), s, e, 4.0 * r * l * d, _nbytes(bank, q, out), LABEL))
+        _PROFILE.append(('fbo_bank_scan R=%d L=%d D=%d' % (r, l, d), lambda: lib.vlfb_fbo_bank_scan(*args), 4.0 * r * l * d,
+                         _nbytes(bank, q, out), LABEL, (bank, q, out, prob, wsp)))
 
 
 def lfb_gather(bank, idx, out, tf32_out=False):

@@ -42,6 +42,19 @@ class GemmPlan(C.Structure):
 ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
 
 
+class FboLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ('w_theta', 'b_theta', 'w_phi', 'b_phi', 'w_g', 'b_g', 'w_out', 'b_out',
+                 'gw_theta', 'gb_theta', 'gw_phi', 'gb_phi', 'gw_g', 'gb_g', 'gw_out', 'gb_out',
+                 'theta', 'prob', 's', 't', 'xhat', 'ln_mean', 'ln_std', 'out', 'a_out')] + [('drop_offset', C.c_uint64)]
+
+
+class FboCfg(C.Structure):
+    _fields_ = [('R', C.c_int), ('L', C.c_int), ('dA', C.c_int), ('d', C.c_int), ('dB', C.c_int), ('layers', C.c_int),
+                ('scale', C.c_float), ('pre_act', C.c_int), ('pre_act_ln', C.c_int), ('ln_eps', C.c_float),
+                ('drop_ratio', C.c_float), ('seed', C.c_uint64), ('step', C.c_void_p)]
+
+
 _P, _I, _L, _F, _U = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
 _GP = C.POINTER(ConvGeom)
 
@@ -88,14 +101,16 @@ SIGNATURES = {
     'vlfb_softmax_ce_fwd': [_P, _P, _P, _P, _I, _I, _F, _P],
     'vlfb_softmax_ce_bwd': [_P, _P, _P, _I, _I, _F, _P],
     'vlfb_sgd_nesterov': [_P, _P, _P, _P, _L, _P, _F, _F, _I, _P],
-    'vlfb_fbo_attend_fwd': [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
-    'vlfb_fbo_attend_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
+    'vlfb_fbo_nl_scratch_floats': [C.POINTER(FboCfg)],
+    'vlfb_fbo_nl_fwd': [C.POINTER(FboCfg), C.POINTER(FboLayer), _P, _P, _P],
+    'vlfb_fbo_nl_bwd': [C.POINTER(FboCfg), C.POINTER(FboLayer), _P, _P, _P, _P, _P, _P, C.c_size_t, _P],
     'vlfb_fbo_bank_scan_splits': [_I, _I, _I],
     'vlfb_fbo_bank_scan_workspace': [_I, _I, _I],
     'vlfb_fbo_bank_scan': [_P, _P, _F, _P, _P, _I, _I, _I, _I, _P, C.c_size_t, _P],
     'vlfb_lfb_gather': [_P, _L, _P, _P, _L, _I, _I, _P],
 }
 RESTYPES = {'vlfb_last_error': C.c_char_p, 'vlfb_fbo_bank_scan_workspace': C.c_size_t,
+            'vlfb_fbo_nl_scratch_floats': C.c_size_t,
             'vlfb_gemm_workspace_bytes': C.c_size_t}
 
 _lib = None
