@@ -7,6 +7,7 @@ FBO-Avg / FBO-Max (:106-127) pool the bank.  `RoIFeatureTransform` (:130-152) wr
 RoIAlign.  The NTC -> NCT11 transposes (:43-53) are free views on channels-last storage.
 """
 import logging
+import os
 
 from core.config import config as cfg
 
@@ -131,7 +132,7 @@ def NLCore(model, in_blob1, in_blob2, in_dim1, in_dim2, latent_dim, num_feat1, n
 
 def NLLayers(model, A, B, in_dim1, in_dim2, latent_dim, num_feat1, num_feat2, prefix, test_mode):
     """Stack FBO_NL.NUM_LAYERS residual NL layers; only A is updated between layers."""
-    if (cfg.B200.get('FBO_STACK', True) and not test_mode and num_feat1 == 1 and cfg.FBO_NL.PRE_ACT
+    if (cfg.B200.get('FBO_STACK', True) and os.environ.get('VLFB_FBO_STACK', '1') != '0' and not test_mode and num_feat1 == 1 and cfg.FBO_NL.PRE_ACT
             and cfg.FBO_NL.NUM_LAYERS <= 4 and in_dim2 == latent_dim):
         # training graphs, one query per RoI: all layers in one launch per direction, phi / g folded onto the shared
         # projected bank (same parameters, same output blobs; B200.FBO_STACK False keeps the as-written operators)
