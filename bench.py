@@ -314,9 +314,10 @@ def run_b200(args):
     # ---- roofline of the dominant kernel: every tcgen05 GEMM launch of one more (eager) step is recorded and then
     # replayed back to back between CUDA events (device time per launch; kernels.stop_profile)
     workspace.current().force_eager = True
-    K.start_profile()
+    if not args.no_roofline:
+        K.start_profile()
     workspace.RunNet(name)
-    recs = K.stop_profile()
+    recs = K.stop_profile() if not args.no_roofline else []
     workspace.current().force_eager = False
     gemm_ms = sum(r[1] for r in recs)
     by_kind, by_stage = {}, {}
@@ -413,6 +414,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--dump-gemms', default='', help='write the per-launch GEMM table of one step here')
     ap.add_argument('--no-graph', action='store_true', help='eager launches (for ncu / debugging)')
+    ap.add_argument('--no-roofline', action='store_true', help='skip the per-launch replay profile (ncu launch lists)')
     ap.add_argument('--config', default='r50_2l', choices=sorted(CONFIGS), help='r50_2l = BASELINE configs[1] (default), '
                     'r50_3l = configs[2] (ava_r50_lfb_nl_3l.yaml), r101_3l = configs[3] architecture')
     args = ap.parse_args()

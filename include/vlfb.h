@@ -46,7 +46,10 @@ const char* vlfb_last_error(void);      /* thread-local message of the last fail
  *   VLFB_OP_CONV_K    A of conv forward : row m = output position, k = (tap, cin)
  *   VLFB_OP_DGRAD_K   A of conv dgrad   : row m = input position,  k = (tap, cout)
  *   VLFB_OP_CONV_MN   B of conv wgrad   : k = output position, n = (kh,kw,cin), one kt per z-slice
- *   VLFB_OP_STEM_K / VLFB_OP_STEM_MN    conv1 (Cin padded to 4): k (resp. n) = (kt,kh) x (8 pixels x 4 ch)
+ *   VLFB_OP_STEM_K / VLFB_OP_STEM_MN    conv1 (Cin padded to 4): k (resp. n) = (kt,kh) x (8 pixels x 4 ch).
+ *                     ptr = first real pixel; ld = row pitch in PIXELS (0 = W).  With zero pad pixels around every row
+ *                     (pW to the left, pitch >= max(pW + W, (Wo-1)*sW + 8)) and Wo % 16 == 0 the operand is staged by TMA
+ *                     (overlapping-window tensor map) instead of 16-byte cp.async gathers.
  */
 enum {
   VLFB_OP_DENSE_K = 0, VLFB_OP_DENSE_MN = 1, VLFB_OP_CONV_K = 2, VLFB_OP_DGRAD_K = 3,
@@ -202,6 +205,10 @@ int vlfb_nc_to_cl(const float* src, float* dst, int N, int C, int64_t inner, int
 /* the same with the TF32 rounding of the result fused (tf32_out != 0): the dequeue of a fed clip (`data` blob,
  * model_builder_video.py:335-345) is ONE pass: NCTHW fp32 -> NDHWC, C 3 -> 4, rounded conv1 operand */
 int vlfb_nc_to_cl_round(const float* src, float* dst, int N, int C, int64_t inner, int Cpad, int tf32_out, void* stream);
+/* the same into W-padded rows: inner = rows * W; row r's W real pixels go to dst pixels [r*pitch + left, +W); the pad
+ * pixels are not written (the caller zero-fills the buffer once).  C <= 4 = Cpad, W % 4 == 0.  The stem (conv1) operand. */
+int vlfb_nc_to_cl_pitched(const float* src, float* dst, int N, int C, int64_t inner, int Cpad, int tf32_out, int W, int pitch,
+                          int left, void* stream);
 int vlfb_cl_to_nc(const float* src, float* dst, int N, int C, int64_t inner, int Cpad, void* stream);
 /* weights: wt[ci][tap][co] = round_tf32( w[co][tap][ci] * (scale ? scale[co] : 1) )  (dgrad B operand) */
 int vlfb_weight_transpose(const float* w, float* wt, const float* scale, int Co, int taps, int Ci,

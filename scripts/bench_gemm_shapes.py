@@ -43,8 +43,33 @@ def timed(fn):
     return e0.elapsed_time(e1) / REPS * 1e3      # us
 
 
+def stem():
+    """conv1 (5x7x7, stride 1x2x2, Cin 3 padded to 4) forward + weight gradient on a dense clip (16-byte cp.async gathers)
+    and on the W-padded clip workspace feeds (TMA-staged overlapping-window operand)."""
+    N, T, S = 2, 32, 224
+    g = K.conv_geom((N, T, S, S, 4), 64, (5, 7, 7), (1, 2, 2), (2, 3, 3))
+    w = torch.randn((64, 5, 7, 8, 4), device='cuda') * 0.05
+    y = torch.empty(K.out_shape(g), device='cuda')
+    dy = torch.randn(K.out_shape(g), device='cuda')
+    dw = torch.zeros((64, 5, 7, 8, 4), device='cuda')
+    s, b = torch.rand(64, device='cuda') + 0.5, torch.randn(64, device='cuda')
+    dense = torch.randn((N, T, S, S, 4), device='cuda')
+    pitch = 232
+    buf = torch.zeros((N, T, S, pitch, 4), device='cuda')
+    buf[:, :, :, 3:3 + S] = dense
+    padded = buf[:, :, :, 3:3 + S]
+    flop = 2.0 * y.numel() * 5 * 7 * 7 * 3 / 1e9
+    for name, x in (('dense clip (cp.async)', dense), ('W-padded clip (TMA)', padded)):
+        tf = timed(lambda: K.conv_fwd(x, w, y, g, scale=s, bias=b, relu=True, tf32_out=True))
+        tw = timed(lambda: K.conv_wgrad(dy, x, dw, g, row_scale=s))
+        print('conv1 %-24s fwd %8.1fus (%6.1f TF/s)   wgrad %8.1fus (%6.1f TF/s)' % (name, tf, flop / tf * 1e3, tw, flop / tw * 1e3),
+              flush=True)
+
+
 def main():
     only = sys.argv[1:] or None
+    if not only or 'conv1' in only:
+        stem()
     print('%-28s %-6s' % ('layer', 'op') + ''.join('%12s' % n for n, _ in VARIANTS) + '   GFLOP   best TF/s')
     for name, ci, co, ker, pd, dil, shp in CONVS:
         if only and not any(o in name for o in only):

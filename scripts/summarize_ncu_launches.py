@@ -5,7 +5,7 @@ import csv
 import sys
 
 
-def main(path, out=None):
+def main(path, out=None, traffic_json=None):
     rows = list(csv.reader(open(path, errors='replace')))
     h = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
     hdr = rows[h]
@@ -47,7 +47,21 @@ def main(path, out=None):
     print(text)
     if out:
         open(out, 'w').write(text + '\n')
+    if traffic_json:
+        import hashlib
+        import json
+        import os
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        src = os.path.join(root, 'video-long-term-feature-banks_b200', 'csrc', 'gemm_tc.cu')
+        rec = {'gemm_tc_sha256': hashlib.sha256(open(src, 'rb').read()).hexdigest(),
+               'dram_bytes_per_gemm_launch': (gr + gw) * 1e6 / max(gn, 1), 'gemm_launches_per_step': gn,
+               'gemm_dram_read_mb': gr, 'gemm_dram_write_mb': gw, 'gemm_us': gt, 'step_kernels': len(step),
+               'step_us_serialised': total,
+               'step_dram_mb': sum(g[2] + g[3] for g in groups.values()),
+               'source': '%s: dram__bytes_read.sum + dram__bytes_write.sum over the %d gemm_tc_kernel launches of one '
+                         'training step (ncu launch list of `bench.py --steps 1 --no-graph`)' % (out or path, gn)}
+        json.dump(rec, open(traffic_json, 'w'), indent=1)
 
 
 if __name__ == '__main__':
-    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None, sys.argv[3] if len(sys.argv) > 3 else None)

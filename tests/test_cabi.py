@@ -91,13 +91,13 @@ def test_gemm_plan_query():
         assert lib.vlfb_gemm_plan(C.byref(p), 148, C.byref(out)) == 0
         return out
 
-    r5 = plan(6272, 512, 4608)                                   # res5 branch2b
+    r5 = plan(6272, 512, 4608, pair=1, stream_k=1)               # res5 branch2b on pairs + stream-K (opt-in)
     assert (r5.tile_n, r5.pair, r5.stream_k, r5.units, r5.tiles) == (256, 1, 1, 74, 50)
-    r4 = plan(6272, 256, 2304)                                   # res4 branch2b: 25 pair tiles over 74 pairs
+    r4 = plan(6272, 256, 2304, pair=1, stream_k=1)               # res4 branch2b: 25 pair tiles over 74 pairs
     assert (r4.tile_n, r4.pair, r4.stream_k, r4.units) == (256, 1, 1, 74)
-    nows = plan(6272, 512, 4608, ws=False)                       # no workspace -> no fix-up schedule
+    nows = plan(6272, 512, 4608, ws=False, pair=1, stream_k=1)   # no workspace -> no fix-up schedule
     assert nows.stream_k == 0 and nows.pair == 1
-    off = plan(6272, 512, 4608, pair=-1, stream_k=-1)            # round-1 behaviour on request
+    off = plan(6272, 512, 4608)                                  # default: the static tile loop on single CTAs
     assert (off.tile_n, off.pair, off.stream_k, off.tiles, off.units) == (256, 0, 0, 98, 98)
     big = plan(200704, 256, 64)                                  # res2 1x1: thousands of tiles, static loop
     assert big.stream_k == 0 and big.tile_n == 256

@@ -183,6 +183,47 @@ def test_stem_conv(K, backend):
     assert float(dw[:, :, :, 7, :].abs().max()) == 0.0 and float(dw[..., 3].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize('backend', BACKENDS)
+@pytest.mark.parametrize('N,T,S', [(2, 6, 64), (1, 3, 96), (3, 4, 32)])
+def test_stem_conv_w_padded_clip_tma_path(K, backend, N, T, S):
+    """conv1 on a clip whose rows are stored W-padded with zero pixels (how workspace feeds it): with Wo % 16 == 0 the
+    tcgen05 engine stages the operand by TMA from the overlapping-window view (csrc/gemm_tc.cu make_tmap_stem) instead of
+    16-byte cp.async gathers; results must equal the fp64 convolution for forward and weight gradient, including the
+    left / right / top / bottom / temporal padding.  The layout kernel itself is checked bit for bit."""
+    K.set_gemm_backend(backend)
+    x = rnd((N, 3, T, S, S), 17)
+    w = rnd((64, 3, 5, 7, 7), 18, 0.1)
+    xd = x.double().requires_grad_(True)
+    wd = w.double().requires_grad_(True)
+    y = F.conv3d(xd, wd, None, (1, 2, 2), (2, 3, 3))
+    g = K.conv_geom((N, T, S, S, 4), 64, (5, 7, 7), (1, 2, 2), (2, 3, 3))
+    assert g.Wo % 16 == 0
+    left, pitch = 3, (3 + S + 5 + 3) // 4 * 4
+    buf = torch.zeros((N, T, S, pitch, 4), device='cuda')
+    K.nc_to_cl(x.cuda().contiguous(), buf, N, 3, T * S * S, 4, tf32_out=True, width=S, pitch=pitch, left=left)
+    torch.cuda.synchronize()
+    want = torch.zeros((N, T, S, pitch, 4))
+    want[:, :, :, left:left + S, :3] = to_cl(x)
+    assert torch.equal(buf.cpu(), want)
+    x4 = buf[:, :, :, left:left + S, :]
+    assert not x4.is_contiguous()
+    ws = stem_pack(w).cuda()
+    yd = torch.full(K.out_shape(g), float('nan'), device='cuda')
+    K.conv_fwd(x4, ws, yd, g)
+    torch.cuda.synchronize()
+    assert rel_err(to_nc(yd), y) < 2e-5
+    dy = rnd(tuple(y.shape), 19)
+    y.backward(dy.double())
+    dw = torch.zeros((64, 5, 7, 8, 4), device='cuda')
+    mask = torch.ones((8, 4))
+    mask[7, :] = 0
+    mask[:, 3] = 0
+    K.conv_wgrad(to_cl(dy).cuda(), x4, dw, g, col_mask=mask.reshape(32).cuda())
+    torch.cuda.synchronize()
+    assert rel_err(dw, stem_pack(wd.grad)) < 2e-5
+    assert float(dw[:, :, :, 7, :].abs().max()) == 0.0 and float(dw[..., 3].abs().max()) == 0.0
+
+
 # -------------------------------------------------------------------------- TF32 rounding
 def test_round_tf32(K):
     x = torch.randn(10007)

@@ -102,13 +102,14 @@ __device__ __forceinline__ float operand_elem(const vlfb_operand_t& op, const vl
       if (ti < 0 || ti >= g.T || hi < 0 || hi >= g.H || wi < 0 || wi >= g.W) return 0.f;
       return op.ptr[((((int64_t)o.n * g.T + ti) * g.H + hi) * g.W + wi) * g.C + ci];
     }
-    case VLFB_OP_STEM_K: {   // C == 4 (3 + zero pad); k = (kt*kH+kh)*32 + px*4 + ch
+    case VLFB_OP_STEM_K: {   // C == 4 (3 + zero pad); k = (kt*kH+kh)*32 + px*4 + ch; op.ld = row pitch in pixels (0 = W)
       Pos4 o = decode_pos(row, g.To, g.Ho, g.Wo);
       int j = k >> 5, e = k & 31, px = e >> 2, ch = e & 3;
       int kt = j / g.kH, kh = j % g.kH;
       int ti = o.t * g.sT - g.pT + kt, hi = o.h * g.sH - g.pH + kh, wi = o.w * g.sW - g.pW + px;
       if (ti < 0 || ti >= g.T || hi < 0 || hi >= g.H || wi < 0 || wi >= g.W) return 0.f;
-      return op.ptr[((((int64_t)o.n * g.T + ti) * g.H + hi) * g.W + wi) * 4 + ch];
+      const int64_t pitch = op.ld > 0 ? op.ld : g.W;
+      return op.ptr[((((int64_t)o.n * g.T + ti) * g.H + hi) * pitch + wi) * 4 + ch];
     }
     case VLFB_OP_STEM_MN: {  // k = output position, row = kh*32 + px*4 + ch, tap_z = kt
       Pos4 o = decode_pos(k, g.To, g.Ho, g.Wo);
@@ -116,7 +117,8 @@ __device__ __forceinline__ float operand_elem(const vlfb_operand_t& op, const vl
       int kt = tap_z;
       int ti = o.t * g.sT - g.pT + kt, hi = o.h * g.sH - g.pH + kh, wi = o.w * g.sW - g.pW + px;
       if (ti < 0 || ti >= g.T || hi < 0 || hi >= g.H || wi < 0 || wi >= g.W) return 0.f;
-      return op.ptr[((((int64_t)o.n * g.T + ti) * g.H + hi) * g.W + wi) * 4 + ch];
+      const int64_t pitch = op.ld > 0 ? op.ld : g.W;
+      return op.ptr[((((int64_t)o.n * g.T + ti) * g.H + hi) * pitch + wi) * 4 + ch];
     }
   }
   return 0.f;

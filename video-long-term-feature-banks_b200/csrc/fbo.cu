@@ -228,36 +228,85 @@ __device__ __forceinline__ float block_max_nl(float v, float* red) {
   __syncthreads();
   return red[0];
 }
-// out[row] = bias[row] + sum_c W[row][c] x[c]   (one warp per row, 128-bit lanes; cols % 4 == 0)
+// One CTA streams ~5 MB of weights / bank rows per layer from L2: the loads must be deep enough in flight to hide the
+// ~1 us latency (Little's law).  r2 call C: with 4 scalar loads per thread in flight (8 KB per CTA) the stack ran at
+// ~10 GB/s per CTA and was slower than the 40 launches it replaces -- hence 4 rows per warp (matvec_rows: 16 x 16-byte
+// loads per lane) and 8 rows x 16 bytes per thread (colsum_w) below.
+// out[row] = bias[row] + sum_c W[row][c] x[c]   (one warp per 4 rows, 128-bit lanes; cols % 4 == 0)
 __device__ __forceinline__ void matvec_rows(const float* __restrict__ W, const float* x, float* out,
                                             const float* __restrict__ bias, int rows, int cols) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int row = warp; row < rows; row += NL_TPB / 32) {
-    const float4* w4 = reinterpret_cast<const float4*>(W + (int64_t)row * cols);
-    float acc = 0.f;
-    for (int c = lane; c < (cols >> 2); c += 32) {
-      const float4 a = w4[c];
+  const int c4n = cols >> 2;
+  for (int row0 = warp * 4; row0 < rows; row0 += 4 * (NL_TPB / 32)) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = lane; c < c4n; c += 32) {
       const float4 b = *reinterpret_cast<const float4*>(x + 4 * c);
-      acc += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+      float4 a[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        a[r] = (row0 + r < rows) ? reinterpret_cast<const float4*>(W + (int64_t)(row0 + r) * cols)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] += a[r].x * b.x + a[r].y * b.y + a[r].z * b.z + a[r].w * b.w;
     }
-    acc = warp_sum_f(acc);
-    if (lane == 0) out[row] = acc + (bias ? bias[row] : 0.f);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float v = warp_sum_f(acc[r]);
+      if (lane == 0 && row0 + r < rows) out[row0 + r] = v + (bias ? bias[row0 + r] : 0.f);
+    }
   }
 }
-// out[c] = sum_row W[row][c] x[row]   (= W^T x; threads over columns, coalesced rows)
-__device__ __forceinline__ void matvec_cols(const float* __restrict__ W, const float* x, float* out, int rows, int cols) {
-  for (int c = threadIdx.x; c < cols; c += NL_TPB) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int r = 0;
-    for (; r + 3 < rows; r += 4) {
-      a0 += W[(int64_t)r * cols + c] * x[r];
-      a1 += W[(int64_t)(r + 1) * cols + c] * x[r + 1];
-      a2 += W[(int64_t)(r + 2) * cols + c] * x[r + 2];
-      a3 += W[(int64_t)(r + 3) * cols + c] * x[r + 3];
+// out[c] = sum_r w[r] M[r][c]  (M row-major [rows][cols], cols % 4 == 0; w, out in shared memory; `part` = scratch of
+// NL_TPB float4).  Thread groups of cols/4 threads own disjoint row sets; each thread keeps 8 rows x 16 bytes in flight.
+// Ends with a __syncthreads(); the caller synchronises before (w ready) as usual.
+__device__ __forceinline__ void colsum_w(const float* __restrict__ M, int rows, int cols, const float* w, float* out,
+                                         float4* part) {
+  const int c4n = cols >> 2;
+  const int G = NL_TPB / c4n > 0 ? NL_TPB / c4n : 1;            // row groups (cols = 512: 4; cols = 2048: 1)
+  for (int cbase = 0; cbase < c4n; cbase += NL_TPB) {            // cols > 4 * NL_TPB: several column passes
+    const int tg = G > 1 ? threadIdx.x / c4n : 0;
+    const int c4 = G > 1 ? threadIdx.x - tg * c4n : cbase + threadIdx.x;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < c4n && tg < G) {
+      const float4* m4 = reinterpret_cast<const float4*>(M) + c4;
+      int r = tg;
+      for (; r + 7 * G < rows; r += 8 * G) {
+        float4 v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = m4[(int64_t)(r + q * G) * c4n];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float ww = w[r + q * G];
+          acc.x += ww * v[q].x; acc.y += ww * v[q].y; acc.z += ww * v[q].z; acc.w += ww * v[q].w;
+        }
+      }
+      for (; r < rows; r += G) {
+        const float4 v = m4[(int64_t)r * c4n];
+        const float ww = w[r];
+        acc.x += ww * v.x; acc.y += ww * v.y; acc.z += ww * v.z; acc.w += ww * v.w;
+      }
     }
-    for (; r < rows; ++r) a0 += W[(int64_t)r * cols + c] * x[r];
-    out[c] = (a0 + a1) + (a2 + a3);
+    if (G > 1) {
+      part[threadIdx.x] = acc;
+      __syncthreads();
+      if (threadIdx.x < c4n) {
+        float4 t = part[threadIdx.x];
+        for (int g = 1; g < G; ++g) {
+          const float4 u = part[g * c4n + threadIdx.x];
+          t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+        *reinterpret_cast<float4*>(out + 4 * threadIdx.x) = t;
+      }
+      __syncthreads();
+      return;                                                    // G > 1 implies a single column pass
+    }
+    if (c4 < c4n) *reinterpret_cast<float4*>(out + 4 * c4) = acc;
   }
+  __syncthreads();
+}
+// out[c] = sum_row W[row][c] x[row]   (= W^T x)
+__device__ __forceinline__ void matvec_cols(const float* __restrict__ W, const float* x, float* out, int rows, int cols,
+                                            float4* part) {
+  colsum_w(W, rows, cols, x, out, part);
 }
 // the generator of vlfb_dropout_fwd (csrc/ops.cu): element idx keeps iff u(idx) >= ratio, scaled by 1 / (1 - ratio)
 __device__ __forceinline__ float philox_keep(uint64_t seed, uint64_t offset, int64_t idx, float ratio) {
@@ -277,12 +326,13 @@ __device__ __forceinline__ float philox_keep(uint64_t seed, uint64_t offset, int
   return (u >= ratio) ? 1.f / (1.f - ratio) : 0.f;
 }
 
-// smem: sA[dA] | sTh[d] | sU[dB] | sS[dB] | sT[d] | sAct[d] | sO[dA] | sE[L] | red[32]
+// smem: part[NL_TPB float4] | sA[dA] | sTh[d] | sU[dB] | sS[dB] | sT[d] | sAct[d] | sO[dA] | sE[L] | red[32]
 __global__ void __launch_bounds__(NL_TPB, 1) fbo_nl_fwd_k(const NlParams P) {
   extern __shared__ float sm[];
   const vlfb_fbo_cfg_t& c = P.c;
   const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* sA = sm;
+  float4* part = reinterpret_cast<float4*>(sm);
+  float* sA = sm + 4 * NL_TPB;
   float* sTh = sA + c.dA;
   float* sU = sTh + c.d;
   float* sS = sU + c.dB;
@@ -300,8 +350,7 @@ __global__ void __launch_bounds__(NL_TPB, 1) fbo_nl_fwd_k(const NlParams P) {
     matvec_rows(l.w_theta, sA, sTh, l.b_theta, c.d, c.dA);
     __syncthreads();
     for (int i = tid; i < c.d; i += NL_TPB) l.theta[(int64_t)r * c.d + i] = sTh[i];
-    matvec_cols(l.w_phi, sTh, sU, c.d, c.dB);
-    __syncthreads();
+    matvec_cols(l.w_phi, sTh, sU, c.d, c.dB, part);
     for (int j = warp; j < c.L; j += NL_TPB / 32) {             // scores (the theta . b_phi constant is dropped)
       const float4* b4 = reinterpret_cast<const float4*>(B + (int64_t)j * c.dB);
       float acc = 0.f;
@@ -323,21 +372,8 @@ __global__ void __launch_bounds__(NL_TPB, 1) fbo_nl_fwd_k(const NlParams P) {
     const float inv = 1.f / sum;
     for (int j = tid; j < c.L; j += NL_TPB) { const float pv = sE[j] * inv; sE[j] = pv; l.prob[(int64_t)r * c.L + j] = pv; }
     __syncthreads();
-    for (int i = tid; i < c.dB; i += NL_TPB) {                  // s = sum_j p_j B'_j
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      int j = 0;
-      for (; j + 3 < c.L; j += 4) {
-        a0 += sE[j] * B[(int64_t)j * c.dB + i];
-        a1 += sE[j + 1] * B[(int64_t)(j + 1) * c.dB + i];
-        a2 += sE[j + 2] * B[(int64_t)(j + 2) * c.dB + i];
-        a3 += sE[j + 3] * B[(int64_t)(j + 3) * c.dB + i];
-      }
-      for (; j < c.L; ++j) a0 += sE[j] * B[(int64_t)j * c.dB + i];
-      const float v = (a0 + a1) + (a2 + a3);
-      sS[i] = v;
-      l.s[(int64_t)r * c.dB + i] = v;
-    }
-    __syncthreads();
+    colsum_w(B, c.L, c.dB, sE, sS, part);                       // s = sum_j p_j B'_j
+    for (int i = tid; i < c.dB; i += NL_TPB) l.s[(int64_t)r * c.dB + i] = sS[i];
     matvec_rows(l.w_g, sS, sT, l.b_g, c.d, c.dB);
     __syncthreads();
     for (int i = tid; i < c.d; i += NL_TPB) l.t[(int64_t)r * c.d + i] = sT[i];
@@ -374,13 +410,14 @@ __global__ void __launch_bounds__(NL_TPB, 1) fbo_nl_fwd_k(const NlParams P) {
   }
 }
 
-// smem: sA[dA] | sTh[d] | sU[dB] | sS[dB] | sX[d] (xhat) | sV1[max(dA,d,dB)] | sV2[max] | sV3[max] | sDA[dA] | sP[L] | sD[L] | red
+// smem: part[NL_TPB float4] | sA[dA] | sTh[d] | sU[dB] | sS[dB] | sX[d] (xhat) | sV1[max(dA,d,dB)] | sV2[max] | sV3[max] | sDA[dA] | sP[L] | sD[L] | red
 __global__ void __launch_bounds__(NL_TPB, 1) fbo_nl_bwd_k(const NlParams P) {
   extern __shared__ float sm[];
   const vlfb_fbo_cfg_t& c = P.c;
   const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int mx3 = max(c.dA, max(c.d, c.dB));
-  float* sA = sm;
+  float4* part = reinterpret_cast<float4*>(sm);
+  float* sA = sm + 4 * NL_TPB;
   float* sTh = sA + c.dA;
   float* sU = sTh + c.d;
   float* sS = sU + c.dB;
@@ -419,8 +456,7 @@ __global__ void __launch_bounds__(NL_TPB, 1) fbo_nl_bwd_k(const NlParams P) {
       g_do[i] = v;
     }
     __syncthreads();
-    matvec_cols(l.w_out, sV1, sV2, c.dA, c.d);                  // d(act) = W_out^T d(out)
-    __syncthreads();
+    matvec_cols(l.w_out, sV1, sV2, c.dA, c.d, part);            // d(act) = W_out^T d(out)
     // ReLU + LayerNorm backward: dt = (dy - mean(dy) - xhat mean(dy xhat)) / std, dy = d(act) where xhat > 0
     float m1 = 0.f, m2 = 0.f;
     for (int i = tid; i < c.d; i += NL_TPB) {
@@ -436,9 +472,8 @@ __global__ void __launch_bounds__(NL_TPB, 1) fbo_nl_bwd_k(const NlParams P) {
     }
     __syncthreads();
     for (int i = tid; i < c.d; i += NL_TPB) g_dt[i] = sV2[i];
-    matvec_cols(l.w_g, sV2, sV1, c.d, c.dB);                     // ds = W_g^T dt
-    matvec_cols(l.w_phi, sTh, sU, c.d, c.dB);                    // u (recomputed)
-    __syncthreads();
+    matvec_cols(l.w_g, sV2, sV1, c.d, c.dB, part);               // ds = W_g^T dt
+    matvec_cols(l.w_phi, sTh, sU, c.d, c.dB, part);              // u (recomputed)
     for (int j = warp; j < c.L; j += NL_TPB / 32) {              // dp_j = ds . B'_j
       const float4* b4 = reinterpret_cast<const float4*>(B + (int64_t)j * c.dB);
       float acc = 0.f;
@@ -459,28 +494,21 @@ __global__ void __launch_bounds__(NL_TPB, 1) fbo_nl_bwd_k(const NlParams P) {
     sds = block_sum_nl(sds, red);                                // sum_j dscore_j (= 0 up to rounding)
     if (tid == 0) g_sum[0] = sds;
     // du = sum_j dscore_j B'_j ; dB'_j (+)= p_j ds + dscore_j u
-    for (int i = tid; i < c.dB; i += NL_TPB) {
-      const float dsi = sV1[i], ui = sU[i];
-      float a0 = 0.f, a1 = 0.f;
-      int j = 0;
+    colsum_w(B, c.L, c.dB, sD, sV3, part);
+    for (int i = tid; i < c.dB; i += NL_TPB) g_du[i] = sV3[i];
+    {
       const bool first = li == c.layers - 1;                     // the last layer (first visited) overwrites dB'
-      for (; j + 1 < c.L; j += 2) {
-        const int64_t o0 = (int64_t)j * c.dB + i, o1 = o0 + c.dB;
-        a0 += sD[j] * B[o0];
-        a1 += sD[j + 1] * B[o1];
-        const float g0 = sP[j] * dsi + sD[j] * ui, g1 = sP[j + 1] * dsi + sD[j + 1] * ui;
-        dB[o0] = first ? g0 : dB[o0] + g0;
-        dB[o1] = first ? g1 : dB[o1] + g1;
+      const int c4n = c.dB >> 2;
+      float4* dB4 = reinterpret_cast<float4*>(dB);
+      for (int64_t e = tid; e < (int64_t)c.L * c4n; e += NL_TPB) {
+        const int j = (int)(e / c4n), q = (int)(e - (int64_t)j * c4n);
+        const float4 dsv = *reinterpret_cast<const float4*>(sV1 + 4 * q);
+        const float4 uv = *reinterpret_cast<const float4*>(sU + 4 * q);
+        const float pj = sP[j], dj = sD[j];
+        float4 gq = make_float4(pj * dsv.x + dj * uv.x, pj * dsv.y + dj * uv.y, pj * dsv.z + dj * uv.z, pj * dsv.w + dj * uv.w);
+        if (!first) { const float4 o = dB4[e]; gq.x += o.x; gq.y += o.y; gq.z += o.z; gq.w += o.w; }
+        dB4[e] = gq;
       }
-      for (; j < c.L; ++j) {
-        const int64_t o0 = (int64_t)j * c.dB + i;
-        a0 += sD[j] * B[o0];
-        const float g0 = sP[j] * dsi + sD[j] * ui;
-        dB[o0] = first ? g0 : dB[o0] + g0;
-      }
-      const float du = a0 + a1;
-      sV3[i] = du;
-      g_du[i] = du;
     }
     __syncthreads();
     matvec_rows(l.w_phi, sV3, sV2, nullptr, c.d, c.dB);          // dtheta = W_phi du (+ b_phi sum_j dscore_j)
@@ -491,8 +519,7 @@ __global__ void __launch_bounds__(NL_TPB, 1) fbo_nl_bwd_k(const NlParams P) {
       g_dth[i] = v;
     }
     __syncthreads();
-    matvec_cols(l.w_theta, sV2, sV1, c.d, c.dA);                 // dA += W_theta^T dtheta
-    __syncthreads();
+    matvec_cols(l.w_theta, sV2, sV1, c.d, c.dA, part);           // dA += W_theta^T dtheta
     for (int i = tid; i < c.dA; i += NL_TPB) sDA[i] += sV1[i];
     __syncthreads();
   }
@@ -636,7 +663,7 @@ int vlfb_fbo_nl_fwd(const vlfb_fbo_cfg_t* c, const vlfb_fbo_layer_t* layers, con
   NlParams P;
   nl_fill(P, c, layers);
   P.a0 = a0; P.bp = bp;
-  const size_t smem = ((size_t)2 * c->dA + 3 * c->d + 2 * c->dB + ((c->L + 3) & ~3) + 32) * sizeof(float);
+  const size_t smem = ((size_t)4 * NL_TPB + 2 * c->dA + 3 * c->d + 2 * c->dB + ((c->L + 3) & ~3) + 32) * sizeof(float);
   VLFB_CHECK_ARG(smem <= 200 * 1024);
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
@@ -664,7 +691,7 @@ int vlfb_fbo_nl_bwd(const vlfb_fbo_cfg_t* c, const vlfb_fbo_layer_t* layers, con
   nl_fill(P, c, layers);
   P.a0 = a0; P.bp = bp; P.da_last = da_last; P.da0 = da0; P.dbp = dbp; P.scratch = scratch;
   const int mx3 = c->dA > c->d ? (c->dA > c->dB ? c->dA : c->dB) : (c->d > c->dB ? c->d : c->dB);
-  const size_t smem = ((size_t)2 * c->dA + 2 * c->d + 2 * c->dB + 3 * mx3 + 2 * ((c->L + 3) & ~3) + 32) * sizeof(float);
+  const size_t smem = ((size_t)4 * NL_TPB + 2 * c->dA + 2 * c->d + 2 * c->dB + 3 * mx3 + 2 * ((c->L + 3) & ~3) + 32) * sizeof(float);
   VLFB_CHECK_ARG(smem <= 200 * 1024);
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {

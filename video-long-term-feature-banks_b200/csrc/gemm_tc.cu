@@ -106,6 +106,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -345,6 +352,7 @@ struct KLoader {
     nrow = rows / RSTEP;
     base = op.ptr;
     ld = op.ld;
+    if (KIND == VLFB_OP_STEM_K && ld <= 0) ld = p.g.W;
     kend = p.K;
     rowmask = 0;
     row0 = row0_;
@@ -442,7 +450,7 @@ struct KLoader {
         if (j >= nrow) break;
         const int ti = s_t[j] + kt, hi = (s_hw[j] >> 16) + kh, wi = (int)(short)(s_hw[j] & 0xFFFF) + c;
         const bool ok = (unsigned)ti < (unsigned)g.T && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
-        const int o = ok ? (((s_n[j] + ti) * g.H + hi) * g.W + wi) * 4 : 0;
+        const int o = ok ? (((s_n[j] + ti) * g.H + hi) * (int)ld + wi) * 4 : 0;      // ld = row pitch in pixels
         cp_async16(tile + dst[j], base + o, ok);
       }
       if (++kh == g.kH) { kh = 0; ++kt; }
@@ -499,9 +507,10 @@ struct MNLoader {
       fd_divmod(tap_hw, kwdiv, qh, qw);
       slotoff = ((int)qh * g.dH * g.W + (int)qw * g.dW) * g.C + (int)cc;
       sh = (int)qh; sw = 8 + (int)qw;
-    } else if (KIND == VLFB_OP_STEM_MN) {            // n = kh*32 + px*4 (+ch)
+    } else if (KIND == VLFB_OP_STEM_MN) {            // n = kh*32 + px*4 (+ch); ld = row pitch in pixels (0 = W)
+      if (ld <= 0) ld = g.W;
       const int qh = mn >> 5, qw = (mn & 31) >> 2;
-      slotoff = (qh * g.W + qw) * 4;
+      slotoff = (qh * (int)ld + qw) * 4;
       sh = qh; sw = 8 + qw;
     }
   }
@@ -521,7 +530,7 @@ struct MNLoader {
       const int t0 = o.t * g.sT - g.pT + tapz * g.dT;          // z slice = temporal tap
       const bool okt = okr && (unsigned)t0 < (unsigned)g.T;
       const int h0 = o.h * g.sH - g.pH, w0 = o.w * g.sW - g.pW;
-      info_a = (((o.n * g.T + t0) * g.H + h0) * g.W + w0) * g.C;
+      info_a = (((o.n * g.T + t0) * g.H + h0) * (KIND == VLFB_OP_STEM_MN ? (int)ld : g.W) + w0) * g.C;
       const int nh = g.kH, nw = (KIND == VLFB_OP_STEM_MN) ? 8 : g.kW;
       const int dh = (KIND == VLFB_OP_STEM_MN) ? 1 : g.dH, dw = (KIND == VLFB_OP_STEM_MN) ? 1 : g.dW;
       int hm = 0, wm = 0;
@@ -576,7 +585,9 @@ struct Launch {
   PosDiv in;     // ... and of the INPUT extents (W, H, T) for the dgrad row decode
   FastDiv cdiv;  // input channels C (wgrad: n -> (tap, ci))
   FastDiv kwdiv; // kW
-  int tma_a, tma_b;  // operand fetched by TMA instead of cp.async: 1 = dense tiled boxes, 2 = im2col (conv gathers)
+  int tma_a, tma_b;  // operand fetched by TMA instead of cp.async: 1 = dense tiled boxes, 2 = im2col (conv gathers),
+                     // 3 = conv1 stem rows: {8 px x 4 ch = 128 B, 16 output positions} boxes of the overlapping-window
+                     //     view of a W-padded clip (make_tmap_stem)
   int lag;           // cp.async groups kept in flight before a stage is published (< stages)
   int tiles_m, tiles_n, total_tiles;
   int tile_rows;     // output rows per tile: 128, or 256 when a CTA pair shares the tile (cta_group::2)
@@ -749,6 +760,12 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
       // per 32-column atom the channel slice / tap offsets of the wgrad B tile
       int ia_w = 0, ia_h = 0, ia_d = 0, ia_n = 0, ic_t = 0, ic_h = 0, ic_w = 0, ic_c = 0, icpt = 1;
       int ib_c[NATOM], ib_off[NATOM], ib_atoms = 0;
+      // conv1 stem rows (tma 3): the 128 tile rows = 8 groups of 16 consecutive output positions (16 | Wo, so a group
+      // never crosses an output row): per group the window origin (wo, hi0 = ho sH - pH, ti0 = to sT - pT, n)
+      const bool stem_a = !PAIR && AK == VLFB_OP_STEM_K && L.tma_a == 3;
+      const bool stem_b = !PAIR && BK == VLFB_OP_STEM_MN && L.tma_b == 3;
+      constexpr int NSG = AK == VLFB_OP_STEM_K ? 8 : 1;
+      int sg_w[NSG], sg_ht[NSG], sg_n[NSG];
       // chunk counter over the CTA's whole work sequence; ring slot / phase / lagged slot advance
       // incrementally (S is a run-time value: `it % S` cost three integer divisions per chunk per thread)
       int it = 0, s = 0, sl = 0;
@@ -778,6 +795,20 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
         // bytes the stage barrier expects: this CTA's copies (PAIR: both CTAs', posted by the leader)
         uint32_t tma_bytes = (tma_a ? (uint32_t)A_TILE_BYTES : 0u) + (tma_b ? b_tile_bytes : 0u);
         if (PAIR) tma_bytes *= 2u;
+        if (tid == 0 && stem_a) {
+          const vlfb_conv_geom_t& g = p.g;
+          Pos4 o = decode_pos_fast((uint32_t)ti.m0, L.out);
+#pragma unroll
+          for (int q = 0; q < NSG; ++q) {
+            sg_w[q] = o.w;
+            sg_ht[q] = ((o.h * g.sH - g.pH) << 16) | ((o.t * g.sT - g.pT) & 0xFFFF);
+            sg_n[q] = (ti.m0 + 16 * q < p.M) ? o.n : g.N;          // rows past M: out of bounds in N -> zeros
+            o.w += 16;
+            if (o.w >= g.Wo) { o.w = 0; if (++o.h == g.Ho) { o.h = 0; if (++o.t == g.To) { o.t = 0; ++o.n; } } }
+          }
+          ic_t = kc0 / g.kH;
+          ic_h = kc0 - ic_t * g.kH;
+        }
         if (tid == 0 && im2col_a) {
           const vlfb_conv_geom_t& g = p.g;
           if (AK == VLFB_OP_CONV_K) {
@@ -813,6 +844,11 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
           }
           tma_bytes = (PAIR ? 2u : 1u) * (tma_a ? (uint32_t)A_TILE_BYTES : 0u) + 4096u * (uint32_t)(ib_atoms + peer_atoms);
         }
+        if (tid == 0 && stem_b) {
+          ib_atoms = 0;                                             // atoms = filter rows kh of this N tile
+          for (int a = 0; a * 32 < bn && ti.n0 + a * 32 < p.N; ++a) ib_atoms = a + 1;
+          tma_bytes = (tma_a ? (uint32_t)A_TILE_BYTES : 0u) + 4096u * (uint32_t)ib_atoms;
+        }
         for (int i = 0; i < ti.nk; ++i, ++it) {
           if (it >= S) mbar_wait(empty0 + 8 * s, ph ^ 1u);
           const int s_cur = s;
@@ -822,7 +858,14 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
           const uint32_t fbar = fullx + 8 * s_cur;
           if (tid == 0 && tma_bytes) {
             if (!PAIR || rank == 0) mbar_expect_tx(full0 + 8 * s_cur, tma_bytes);
-            if (im2col_a) {
+            if (stem_a) {
+              const vlfb_conv_geom_t& g = p.g;
+#pragma unroll
+              for (int q = 0; q < NSG; ++q)
+                tma_load_5d(a_tile + q * 2048, &tmA, 0, sg_w[q], (sg_ht[q] >> 16) + ic_h, (int)(short)(sg_ht[q] & 0xFFFF) + ic_t,
+                            sg_n[q], fbar);
+              if (++ic_h == g.kH) { ic_h = 0; ++ic_t; }
+            } else if (im2col_a) {
               const vlfb_conv_geom_t& g = p.g;
               if (AK == VLFB_OP_CONV_K)
                 ldi(a_tile, &tmA, ic_c * KC, ia_w, ia_h, ia_d, ia_n, ic_w * g.dW, ic_h * g.dH, ic_t * g.dT, fbar);
@@ -841,7 +884,21 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
                 ld3(a_tile, &tmA, (kc0 + i) * KC, ti.m0, ti.batch, fbar);
               }
             }
-            if (im2col_b) {
+            if (stem_b) {
+              // conv1 wgrad B tile: 32 output positions (k rows) = 2 groups of 16; per filter row kh one 32-column atom
+              // (8 px x 4 ch) = two {128 B x 16 positions} boxes of the overlapping-window view
+              const vlfb_conv_geom_t& g = p.g;
+              const int kh0 = ti.n0 >> 5;
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                const int kpos = ti.k_begin + i * KC + 16 * hf;
+                const Pos4 o = decode_pos_fast((uint32_t)(kpos < p.K ? kpos : 0), L.out);
+                const int bn_ = kpos < p.K ? o.n : g.N;
+                const int bh = o.h * g.sH - g.pH + kh0, bt = o.t * g.sT - g.pT + ti.tap;
+                for (int a = 0; a < ib_atoms; ++a)
+                  tma_load_5d(b_tile + a * 4096 + hf * 2048, &tmB, 0, o.w, bh + a, bt, bn_, fbar);
+              }
+            } else if (im2col_b) {
               // wgrad B tile: 32 output positions (k rows) x one (kh, kw, 32-channel) atom per copy
               const vlfb_conv_geom_t& g = p.g;
               const Pos4 o = decode_pos_fast((uint32_t)(ti.k_begin + i * KC), L.out);
@@ -1394,6 +1451,26 @@ static bool make_tmap_im2col(CUtensorMap* tm, const float* base, int N, int D, i
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// conv1 stem (C padded to 4, 16-byte pixels): overlapping-window view of a clip whose rows are stored with `pitch`
+// >= pW + W + right pad pixels, the pad pixels zero.  dim0 = the 8 px x 4 ch = 32 floats of one filter row starting
+// at padded pixel wo * sW (i.e. real pixel wo * sW - pW), dim1 = wo (stride sW pixels: consecutive windows OVERLAP),
+// dim2 / dim3 = input row / frame (their out-of-range coordinates read as zeros = the H / T padding), dim4 = clip.
+// One box = 16 consecutive output positions of one output row.
+static bool make_tmap_stem(CUtensorMap* tm, const float* ptr, const vlfb_conv_geom_t& g, int64_t pitch, CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc || g.C != 4 || (g.Wo & 15) || g.dT != 1 || g.dH != 1 || g.dW != 1 || g.kW > 8) return false;
+  if (pitch < g.pW + g.W || pitch < (int64_t)(g.Wo - 1) * g.sW + 8 || (reinterpret_cast<uintptr_t>(ptr) & 15)) return false;
+  const float* base = ptr - (int64_t)g.pW * 4;                     // padded pixel 0 of row 0
+  cuuint64_t dims[5] = {32, (cuuint64_t)g.Wo, (cuuint64_t)g.H, (cuuint64_t)g.T, (cuuint64_t)g.N};
+  cuuint64_t gstr[4] = {(cuuint64_t)g.sW * 16, (cuuint64_t)pitch * 16, (cuuint64_t)pitch * 16 * g.H,
+                        (cuuint64_t)pitch * 16 * g.H * g.T};
+  cuuint32_t box[5] = {32, 16, 1, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // tuning overrides, read once (scripts/tune_gemm.py); the per-call fields of vlfb_gemm_params_t take precedence
 struct Env { int bn, stages, lag, pair, sk, debug; bool tma_mn, im2col; };
 static Env read_env() {
@@ -1428,7 +1505,8 @@ static double chunk_cost(int bn, bool pair) {
 
 struct Plan { int bn, split_k, pair, sk; int tiles, units; double cost; };
 
-static constexpr bool kind_tma_capable(int kind) { return kind != VLFB_OP_STEM_K && kind != VLFB_OP_STEM_MN; }
+static constexpr bool kind_pair_capable(int kind) { return kind != VLFB_OP_STEM_K && kind != VLFB_OP_STEM_MN; }
+static constexpr bool kind_tma_capable(int) { return true; }
 
 // `pairs` = co-resident CTA pairs (0: pairing unavailable); pair_ok / sk_ok = what the operands / workspace allow.
 static Plan make_plan(const vlfb_gemm_params_t& p, int num_sms, int pairs, bool pair_ok, bool sk_ok) {
@@ -1443,8 +1521,12 @@ static Plan make_plan(const vlfb_gemm_params_t& p, int num_sms, int pairs, bool 
   best_sk = best;
   static const int kWidths[] = {256, 192, 128, 96, 64, 32};
   for (int pr = 0; pr < 2; ++pr) {
+    // CTA pairs and stream-K are opt-in (p.pair / p.stream_k = 1, VLFB_PAIR / VLFB_SK): measured on B200 (profiles/
+    // r02_gemm_variants.txt, r02_trace_*.txt) the K loop of a 128 x 256 tf32 tile already runs at the tensor-pipe
+    // rate (0.287 us per 32-deep chunk = 4 x 128-cycle MMAs), so halving the operand bytes per SM buys nothing, and
+    // the stream-K fix-up costs more than the idle SMs of a 98-tile launch.
     const bool can_pair = pair_ok && pairs >= 1 && p.M > BM;
-    if (pr == 1 && (!can_pair || want_pair < 0)) continue;
+    if (pr == 1 && (!can_pair || want_pair <= 0)) continue;
     if (pr == 0 && want_pair > 0 && can_pair) continue;
     const int U = pr ? pairs : num_sms;
     for (int wi = 0; wi < 6; ++wi) {
@@ -1470,7 +1552,7 @@ static Plan make_plan(const vlfb_gemm_params_t& p, int num_sms, int pairs, bool 
       }
       // (b) stream-K: equal chunk ranges; shared tiles reduced through the workspace (or by atomics)
       const int64_t total = T * nkt;
-      const bool sk_legal = (atomic ? p.split_k != 1 : (sk_ok && p.split_k <= 1)) && want_sk >= 0 && nkt >= 2 &&
+      const bool sk_legal = (atomic ? p.split_k != 1 : (sk_ok && p.split_k <= 1)) && want_sk > 0 && nkt >= 2 &&
                             total >= 2 * (int64_t)U && T * (pr ? 2 : 1) * (NEPI / 32) <= SK_CNT_INTS && U <= MAX_UNITS;
       if (sk_legal && (T % U) != 0) {
         const double per_unit = (double)((total + U - 1) / U);
@@ -1511,7 +1593,7 @@ size_t gemm_tc_workspace_bytes() {
 template <int AK, int BK, bool MASK>
 static int max_pairs() {
   static int cached = -1;
-  if constexpr (!(kind_tma_capable(AK) && kind_tma_capable(BK))) return 0;
+  if constexpr (!(kind_pair_capable(AK) && kind_pair_capable(BK))) return 0;
   else if (cached < 0) {
     cached = 0;
     if (cudaFuncSetAttribute(gemm_tc_kernel<AK, BK, MASK, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1581,7 +1663,7 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
   const bool unit_dgrad = g.sT == 1 && g.sH == 1 && g.sW == 1;
   // can both operands be staged by TMA (the precondition of CTA pairs)?  Decided on the cheap conditions here; the
   // tensor maps themselves are encoded after the plan (their boxes depend on it) and a failure falls back below.
-  bool pair_ok = kind_tma_capable(AK) && kind_tma_capable(BK) && encode_fn() != nullptr && ev.im2col &&
+  bool pair_ok = kind_pair_capable(AK) && kind_pair_capable(BK) && encode_fn() != nullptr && ev.im2col &&
                  (ev.tma_mn || !(is_mn(AK) || is_mn(BK))) && !(AK == VLFB_OP_DGRAD_K && !unit_dgrad) && p.K >= KC;
   bool sk_ws = p.workspace != nullptr && p.workspace_bytes >= gemm_tc_workspace_bytes() &&
                      (reinterpret_cast<uintptr_t>(p.workspace) & 15) == 0;
@@ -1614,6 +1696,11 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
         if (make_tmap_im2col(&tmA, p.a.ptr, g.N, g.To, g.Ho, g.Wo, g.Co, lo, hi, ones, BM, CU_TENSOR_MAP_SWIZZLE_128B))
           L.tma_a = 2;
       }
+      if (AK == VLFB_OP_STEM_K && p.a.ld > 0 && make_tmap_stem(&tmA, p.a.ptr, g, p.a.ld, CU_TENSOR_MAP_SWIZZLE_128B))
+        L.tma_a = 3;
+      if (BK == VLFB_OP_STEM_MN && p.b.ld > 0 && L.tma_a &&
+          make_tmap_stem(&tmB, p.b.ptr, g, p.b.ld, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+        L.tma_b = 3;
       if (BK == VLFB_OP_CONV_MN && (g.C % KC) == 0 && L.tma_a &&
           make_tmap_im2col(&tmB, p.b.ptr, g.N, g.T, g.H, g.W, g.C, pad_lo, pad_hi, cstr, KC,
                            CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
@@ -1666,10 +1753,10 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = plan.pair ? 1 : 0;
-  if constexpr (kind_tma_capable(AK) && kind_tma_capable(BK)) {
+  if constexpr (kind_pair_capable(AK) && kind_pair_capable(BK)) {
     if (plan.pair) return launch_variant<AK, BK, MASK, true, false>(cfg, p, L, tmA, tmB);
-    if (!cp) return launch_variant<AK, BK, MASK, false, false>(cfg, p, L, tmA, tmB);
   }
+  if (!cp) return launch_variant<AK, BK, MASK, false, false>(cfg, p, L, tmA, tmB);
   return launch_variant<AK, BK, MASK, false, true>(cfg, p, L, tmA, tmB);
 }
 
@@ -1677,7 +1764,7 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
 
 void gemm_tc_plan(const vlfb_gemm_params_t& p, int num_sms, vlfb_gemm_plan_t* out) {
   // host-only view of the plan: pairing assumes both operands are TMA-addressable and one pair per two SMs
-  const bool pair_ok = tc::kind_tma_capable(p.a.kind) && tc::kind_tma_capable(p.b.kind) && p.K >= tc::KC;
+  const bool pair_ok = tc::kind_pair_capable(p.a.kind) && tc::kind_pair_capable(p.b.kind) && p.K >= tc::KC;
   bool sk_ws = p.workspace != nullptr && p.workspace_bytes >= tc::gemm_tc_workspace_bytes();
   const tc::Plan pl = tc::make_plan(p, num_sms, num_sms / 2, pair_ok, sk_ws);
   out->tile_n = pl.bn; out->split_k = pl.split_k; out->pair = pl.pair; out->stream_k = pl.sk;

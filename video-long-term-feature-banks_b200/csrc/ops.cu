@@ -496,6 +496,31 @@ __global__ void nc_to_cl4_k(const float* __restrict__ src, float4* __restrict__ 
   }
 }
 
+// ... into rows of `pitch` pixels starting at pixel `left` (W4 = W / 4 groups of 4 pixels per row)
+__global__ void nc_to_cl4p_k(const float* __restrict__ src, float4* __restrict__ dst, int C, int64_t inner4, int64_t total,
+                             int tf32, int W4, int pitch, int left) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = q / inner4, i4 = q - n * inner4;
+    float4 p[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      p[c] = c < C ? *reinterpret_cast<const float4*>(src + ((n * C + c) * inner4 + i4) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tf32) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        p[c].x = round_tf32(p[c].x); p[c].y = round_tf32(p[c].y); p[c].z = round_tf32(p[c].z); p[c].w = round_tf32(p[c].w);
+      }
+    }
+    const int64_t row = (n * inner4 + i4) / W4;
+    const int w4 = (int)((n * inner4 + i4) - row * W4);
+    float4* o = dst + row * pitch + left + w4 * 4;
+    o[0] = make_float4(p[0].x, p[1].x, p[2].x, p[3].x);
+    o[1] = make_float4(p[0].y, p[1].y, p[2].y, p[3].y);
+    o[2] = make_float4(p[0].z, p[1].z, p[2].z, p[3].z);
+    o[3] = make_float4(p[0].w, p[1].w, p[2].w, p[3].w);
+  }
+}
+
 __global__ void nc_to_cl_k(const float* __restrict__ src, float* __restrict__ dst, int C, int64_t inner, int Cpad,
                            int tf32) {
   __shared__ float tile[32][33];
@@ -886,6 +911,18 @@ int vlfb_nc_to_cl_round(const float* src, float* dst, int N, int C, int64_t inne
   }
   dim3 grid(ceil_div(inner, 32), ceil_div(Cpad, 32), N), block(32, 8);
   launch_k(nc_to_cl_k, grid, block, 0, ST(stream), src, dst, C, inner, Cpad, tf32_out);
+  VLFB_CHECK_LAUNCH();
+  return VLFB_OK;
+}
+
+int vlfb_nc_to_cl_pitched(const float* src, float* dst, int N, int C, int64_t inner, int Cpad, int tf32_out, int W, int pitch,
+                          int left, void* stream) {
+  VLFB_CHECK_ARG(src && dst && N > 0 && C > 0 && C <= 4 && Cpad == 4 && inner > 0 && W > 0 && (W & 3) == 0);
+  VLFB_CHECK_ARG(inner % W == 0 && left >= 0 && pitch >= left + W);
+  VLFB_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0);
+  const int64_t total = (int64_t)N * (inner >> 2);
+  launch_k(nc_to_cl4p_k, stream_grid(total, TPB), TPB, 0, ST(stream), src, (float4*)dst, C, inner >> 2, total, tf32_out, W >> 2,
+           pitch, left);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }

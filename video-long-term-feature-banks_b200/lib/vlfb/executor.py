@@ -63,6 +63,8 @@ def phys(t):
         assert t.is_contiguous()
         return t
     p = t.permute([0] + list(range(2, t.dim())) + [1])
+    if not p.is_contiguous() and t.dim() == 5 and t.shape[1] == 4 and p.stride(4) == 1 and p.stride(3) == 4:
+        return p            # the fed clip: rows padded in W (workspace._feed_activation), conv1's TMA-staged operand
     assert p.is_contiguous(), 'blob is not channels-last contiguous: shape %s strides %s' % (
         tuple(t.shape), tuple(t.stride()))
     return p
@@ -957,6 +959,13 @@ class CompiledNet(object):
         produced = set()
         self.external_inputs = []
         for op in ops:
+            if op.type == 'DequeueBlobs':
+                # the data loader's blobs are fed from outside (FeedBlob / EnqueueBlobs): they are inputs of the step,
+                # and their shapes / addresses (e.g. the RoI count of an AVA batch) select the captured graph
+                for n in op.outputs:
+                    if n not in self.external_inputs:
+                        self.external_inputs.append(n)
+                continue
             for n in op.inputs:
                 if n not in produced and n not in self.external_inputs and n not in model.params:
                     self.external_inputs.append(n)

@@ -133,6 +133,17 @@ def _operand(ptr_t, kind, ld=0, batch_stride=0):
     return o
 
 
+def _stem_pitch(x, g):
+    """conv1 input [N,T,H,W,4]: dense, or a view of a W-padded buffer [N,T,H,pitch,4] (zero pad pixels; workspace feeds
+    the clip that way so that the stem operand is staged by TMA).  Returns the row pitch in pixels."""
+    assert x.dtype == torch.float32 and x.shape[-1] == 4 and x.stride(4) == 1 and x.stride(3) == 4
+    pitch = x.stride(2) // 4
+    assert x.stride(2) == pitch * 4 and pitch >= g.W
+    assert x.stride(1) == pitch * 4 * g.H and (g.N == 1 or x.stride(0) == pitch * 4 * g.H * g.T), \
+        'stem input must be [N,T,H,W,4] with padded rows only'
+    return pitch
+
+
 def _nbytes(*ts):
     return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
 
@@ -190,20 +201,20 @@ def conv_fwd(x, w, y, g, scale=None, bias=None, residual=None, relu=False, tf32_
     """y = epi(conv(x, w)).  x [N,T,H,W,C], w [Co,kT,kH,kW,C], y [N,To,Ho,Wo,Co];
     epi: *scale[co] + bias[co] (+ residual) (ReLU).  C == 4 selects the stem (conv1) path with
     w [Co,kT,kH,8,4]."""
-    _f32c(x, 'x'), _f32c(w, 'w'), _f32c(y, 'y')
+    _f32c(w, 'w'), _f32c(y, 'y')
     assert tuple(x.shape) == (g.N, g.T, g.H, g.W, g.C) and tuple(y.shape) == out_shape(g)
     M = g.N * g.To * g.Ho * g.Wo
     if g.C == 4:
         K = g.kT * g.kH * 32
         assert tuple(w.shape) == (g.Co, g.kT, g.kH, 8, 4)
-        a = _operand(x, L.OP_STEM_K)
+        a = _operand(x, L.OP_STEM_K, ld=_stem_pitch(x, g))
     elif _is_pointwise(g):
         K = g.C
-        a = _operand(x, L.OP_DENSE_K, ld=g.C)
+        a = _operand(_f32c(x, 'x'), L.OP_DENSE_K, ld=g.C)
     else:
         K = g.kT * g.kH * g.kW * g.C
         assert tuple(w.shape) == (g.Co, g.kT, g.kH, g.kW, g.C)
-        a = _operand(x, L.OP_CONV_K)
+        a = _operand(_f32c(x, 'x'), L.OP_CONV_K)
     p = _base_params(M, g.Co, K, y, g.Co)
     p.a = a
     p.b = _operand(w, L.OP_DENSE_K, ld=K)
@@ -251,19 +262,19 @@ def conv_wgrad(dy, x, dw, g, row_scale=None, col_mask=None):
     """dw[co,tap,ci] += row_scale[co] * sum_m dy[m,co] * x[gather(m,tap),ci]  (atomic accumulate:
     dw must be zero-initialised or hold a partial sum).  Stem path when C == 4 (dw [Co,kT,kH,8,4],
     col_mask [32] zeroes the padding lanes)."""
-    _f32c(dy, 'dy'), _f32c(x, 'x'), _f32c(dw, 'dw')
+    _f32c(dy, 'dy'), _f32c(dw, 'dw')
     Kpos = g.N * g.To * g.Ho * g.Wo
     if g.C == 4:
         taps, n = g.kT, g.kH * 32
-        b = _operand(x, L.OP_STEM_MN)
+        b = _operand(x, L.OP_STEM_MN, ld=_stem_pitch(x, g))
         if col_mask is not None and col_mask.numel() == 32:
             col_mask = col_mask.repeat(g.kH)
     elif _is_pointwise(g):
         taps, n = 1, g.C
-        b = _operand(x, L.OP_DENSE_MN, ld=g.C)
+        b = _operand(_f32c(x, 'x'), L.OP_DENSE_MN, ld=g.C)
     else:
         taps, n = g.kT, g.kH * g.kW * g.C          # one z-slice per temporal tap; N spans (kh, kw, ci)
-        b = _operand(x, L.OP_CONV_MN)
+        b = _operand(_f32c(x, 'x'), L.OP_CONV_MN)
     p = _base_params(g.Co, n, Kpos, dw, taps * n)
     p.a = _operand(dy, L.OP_DENSE_MN, ld=g.Co)
     p.b = b
@@ -510,7 +521,13 @@ def copy2d(src, lds, dst, ldd, rows, cols, accumulate=False, src_off=0, dst_off=
             'copy2d')
 
 
-def nc_to_cl(src, dst, n, c, inner, cpad=None, tf32_out=False):
+def nc_to_cl(src, dst, n, c, inner, cpad=None, tf32_out=False, width=0, pitch=0, left=0):
+    """NCTHW -> NDHWC (C padded to cpad).  width / pitch / left: the destination rows are `pitch` pixels long and the
+    `width` real pixels of a row start at pixel `left` (the W-padded clip of conv1's TMA path)."""
+    if pitch:
+        _check(L.load().vlfb_nc_to_cl_pitched(_ptr(_f32c(src)), _ptr(_f32c(dst)), n, c, inner, cpad or c, int(tf32_out),
+                                              int(width), int(pitch), int(left), _stream()), 'nc_to_cl_pitched')
+        return
     _check(L.load().vlfb_nc_to_cl_round(_ptr(_f32c(src)), _ptr(_f32c(dst)), n, c, inner, cpad or c, int(tf32_out),
                                         _stream()), 'nc_to_cl')
 

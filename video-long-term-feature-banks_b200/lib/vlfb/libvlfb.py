@@ -93,6 +93,7 @@ SIGNATURES = {
     'vlfb_copy2d': [_P, _L, _P, _L, _L, _I, _I, _P],
     'vlfb_nc_to_cl': [_P, _P, _I, _I, _L, _I, _P],
     'vlfb_nc_to_cl_round': [_P, _P, _I, _I, _L, _I, _I, _P],
+    'vlfb_nc_to_cl_pitched': [_P, _P, _I, _I, _L, _I, _I, _I, _I, _I, _P],
     'vlfb_cl_to_nc': [_P, _P, _I, _I, _L, _I, _P],
     'vlfb_weight_transpose': [_P, _P, _P, _I, _I, _I, _P],
     'vlfb_weight_transpose_multi': [_P, _I, _I, _P],

@@ -14,6 +14,7 @@ import torch
 from . import executor as X
 
 _SCOPE = re.compile(r'^gpu_\d+/')
+STEM_PAD_L, STEM_PAD_R = 3, 5          # zero pixels around every row of a fed clip (conv1: kW = 7, pad 3, stride 2)
 
 
 def _unscoped(name):
@@ -406,7 +407,22 @@ def _feed_activation(name, arr):
         else:
             stage = _static(name + '/ncthw', src.shape, X.DTYPE)
             stage.copy_(src, non_blocking=True)                   # H2D (async from pinned memory)
-        p = _static(name, (n, src.shape[2], src.shape[3], src.shape[4], cpad), X.DTYPE)
+        t_, h_, w_ = int(src.shape[2]), int(src.shape[3]), int(src.shape[4])
+        if c == 3 and w_ % 4 == 0 and X.DEVICE != 'cpu':
+            # the clip feeds conv1 only: rows are stored with STEM_PAD_L zero pixels on the left and zero pixels up to
+            # the pitch on the right, so that a filter row's 8-pixel window of ANY output position is 128 contiguous
+            # in-bounds bytes and the stem operand can be staged by TMA (csrc/gemm_tc.cu make_tmap_stem)
+            pitch = (STEM_PAD_L + w_ + STEM_PAD_R + 3) // 4 * 4
+            key = name + '/padded'
+            buf = _ws.input_cache.get(key)
+            if buf is None or tuple(buf.shape) != (n, t_, h_, pitch, cpad):
+                buf = torch.zeros((n, t_, h_, pitch, cpad), dtype=X.DTYPE, device=X.DEVICE)     # pads stay zero
+                _ws.input_cache[key] = buf
+            X.K.nc_to_cl(stage, buf, n, c, inner, cpad, tf32_out=True, width=w_, pitch=pitch, left=STEM_PAD_L)
+            _ws.blobs[name] = buf[:, :, :, STEM_PAD_L:STEM_PAD_L + w_, :].permute(0, 4, 1, 2, 3)
+            _ws.rounded.add(name)
+            return
+        p = _static(name, (n, t_, h_, w_, cpad), X.DTYPE)
         X.K.nc_to_cl(stage, p, n, c, inner, cpad, tf32_out=True)  # reference NCTHW blob -> NDHWC (+pad 3->4), TF32-rounded
         _ws.blobs[name] = p.permute(0, 4, 1, 2, 3)
         _ws.rounded.add(name)
