@@ -15,6 +15,8 @@ accumulate).
     tests/test_engine_cpu.py (same host logic in fp64 vs the oracle, 1e-7 on every parameter) and
     tests/test_gpu_kernels.py (every dgrad / wgrad kernel vs fp64, 2e-5).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -373,3 +375,76 @@ def test_graph_replay_rebinds_its_blobs_after_another_net_ran(ws):
     torch.cuda.synchronize()
     assert np.allclose(ws.FetchBlob('gpu_0/pred'), want['pred'], rtol=1e-5, atol=1e-6)
     assert len(net_a._graphs) == 2
+
+
+# ---------------------------------------------------------------------------- full-size configs 3 / 4, other heads, files
+def test_full_size_config3_r50_fbo_nl_3l_all_gradients(ws):
+    """BASELINE.json config 3 shapes (ava_r50_lfb_nl_3l.yaml): full 32x224x224 train step, EVERY trainable tensor's
+    gradient against the fp64 oracle."""
+    _train_case(ws, 'ava_r50_lfb_nl_3l.yaml', FULL, 224, 32, 2, check_all_grads=True)
+
+
+def test_full_size_config4_r101_fbo_nl_3l_tf32(ws):
+    """BASELINE.json config 4 architecture (ava_r101_lfb_nl_3l.yaml: res4 = 23 blocks, NL at conv4_{6,13,20}) at full
+    size in the tf32 parity mode (the bf16 storage mode of config 4 is not built): 174 trainable tensors."""
+    _train_case(ws, 'ava_r101_lfb_nl_3l.yaml', FULL, 224, 32, 2, check_all_grads=True, median_tol=3e-2)
+
+
+def test_full_size_config2_simt_fp32_engine(ws):
+    """The same full-size step on the SIMT fp32 engine (no tensor cores, same rounding points): separates tcgen05 /
+    TMA kernel error from the ReLU-flip noise that TF32 rounding of the activations causes in both engines."""
+    _train_case(ws, 'ava_r50_lfb_nl.yaml', FULL, 224, 32, 2, backend='simt', check_all_grads=True)
+
+
+@pytest.mark.parametrize('yaml_name', ['ava_r50_lfb_avg.yaml', 'ava_r50_lfb_max.yaml'])
+def test_tiny_fbo_avg_max_heads(ws, yaml_name):
+    """the pooling feature-bank operators (lfb_helper.py:106-127) on the GPU path."""
+    _train_case(ws, yaml_name, TINY, 64, 8, 2)
+
+
+def test_checkpoint_round_trip_through_the_device_param_store(ws, tmp_path):
+    """SURVEY 8f rank 2 on the GPU: save_model_params -> fresh workspace -> initialize_params_from_file.  Exercises the
+    device layouts a file must survive: conv weights [Cout][kT][kH][kW][Cin], the stem padded to 8 px x 4 ch, the
+    TF32 operand copy (Pt) refreshed on load, momentum; the reloaded net must reproduce the step bit for bit."""
+    import pickle
+    from oracle import model as OM
+    from utils import checkpoints as CK
+    H.setup_cfg('ava_r50_lfb_nl.yaml', TINY)
+    ocfg = H.oracle_cfg('ava_r50_lfb_nl.yaml', TINY)
+    params = OM.make_params(ocfg, seed=2)
+    inputs = OM.make_inputs(ocfg, n_clips=2, rois_per_clip=2, crop=64, frames=8)
+    model, sfx = H.build('train', True)
+    H.feed_params(params)
+    H.feed_inputs(inputs, sfx)
+    model.UpdateWorkspaceLr(10)
+    name = model.net.Proto().name
+    ws.RunNet(name)                                         # one SGD step: weights moved, momentum non-zero
+    torch.cuda.synchronize()
+    path = os.path.join(str(tmp_path), 'c2_model_iter1.pkl')
+    CK.save_model_params(model, path, 0)
+    with open(path, 'rb') as f:
+        saved = pickle.load(f)['blobs']
+    assert saved['conv1_w'].shape == (64, 3, 5, 7, 7) and saved['res4_0_branch2a_w'].shape == (256, 512, 3, 1, 1)
+    assert np.abs(saved['conv1_w'] - params['conv1_w'].numpy()).max() > 0
+    ws.RunNet(name)                                         # the step the reloaded model must reproduce
+    torch.cuda.synchronize()
+    names = ['conv1_w', 'res3_1_branch2b_w', 'nonlocal_conv4_1_theta_w', 'lfb_nl1_out_w', 'pred_w', 'pred_b']
+    want = dict((k, ws.FetchBlob('gpu_0/' + k).copy()) for k in names + [n + '_momentum' for n in names])
+    want_loss = float(ws.FetchBlob('gpu_0/loss'))
+    H.setup_cfg('ava_r50_lfb_nl.yaml', TINY)
+    ws.ResetWorkspace()
+    model2, sfx2 = H.build('train', True)
+    it, lr = CK.initialize_params_from_file(model2, path)
+    assert it == 1
+    store = ws.current().params
+    stem = store.phys('conv1_w')
+    assert tuple(stem.shape) == (64, 5, 7, 8, 4) and float(stem[:, :, :, 7, :].abs().max()) == 0 and float(stem[..., 3].abs().max()) == 0
+    from util import tf32_round
+    assert torch.equal(store.tf32('res3_1_branch2b_w').cpu(), tf32_round(store.phys('res3_1_branch2b_w').cpu()))
+    H.feed_inputs(inputs, sfx2)
+    ws.RunNet(model2.net.Proto().name)
+    torch.cuda.synchronize()
+    assert abs(float(ws.FetchBlob('gpu_0/loss')) - want_loss) <= 1e-6 * abs(want_loss)
+    for k, v in want.items():
+        got = ws.FetchBlob('gpu_0/' + k)
+        assert np.allclose(got, v, rtol=1e-5, atol=1e-8), k

@@ -1204,60 +1204,70 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
       // (ncu r2b: per-float4 flag tests, 64-bit address arithmetic and bounds checks) -- 6.3 us for a 128 x 256 tile,
       // longer than the K loop of most res2 / res3 / res4 layers; here every run-time switch is tested once per tile
       // (warp-uniform), rows are four precomputed pointers and the column offset is one add per block.
-      auto run_fast = [&](auto mode_c) {
+      auto run_fast = [&](auto mode_c, auto atomic_c, auto wres_c) {
         constexpr int mode = decltype(mode_c)::value;
+        constexpr bool ATOMIC = decltype(atomic_c)::value && mode != 1;
+        constexpr bool WRES = decltype(wres_c)::value && mode != 1;
         const int r0 = quarter * 32 + (lane >> 2);                         // tile rows r0 + 8 i of this lane
         const int cbase = half * EPC + col;
         uint32_t rowok = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) rowok |= (ti.m0 + r0 + 8 * i < p.M) ? (1u << i) : 0u;
         const int ncols = min(bn, p.N - ti.n0);                            // multiple of 16
-        // destination rows: D (modes 0 / 2) or this unit's workspace slot (mode 1)
-        float* drow;
-        int64_t dstep;
-        if (mode == 1) {
-          drow = L.ws_tiles + ((size_t)(unit * 2 + ti.slot()) * nrank + rank) * ws_tile_floats + (size_t)r0 * bn + cbase;
-          dstep = 8 * (int64_t)bn;
-        } else {
-          drow = p.d + tile_off + (int64_t)(ti.m0 + r0) * p.ldd + ti.n0 + cbase;
-          dstep = 8 * p.ldd;
+        // four row pointers per stream (destination: D, or this unit's workspace slot in mode 1; residual; mask),
+        // advanced by one block (32 columns) per iteration -- no per-store address arithmetic
+        float* dp[4];
+        const float* rp[4];
+        const float* mp[4];
+        {
+          float* drow;
+          int64_t dstep;
+          if (mode == 1) {
+            drow = L.ws_tiles + ((size_t)(unit * 2 + ti.slot()) * nrank + rank) * ws_tile_floats + (size_t)r0 * bn + cbase;
+            dstep = 8 * (int64_t)bn;
+          } else {
+            drow = p.d + tile_off + (int64_t)(ti.m0 + r0) * p.ldd + ti.n0 + cbase;
+            dstep = 8 * p.ldd;
+          }
+          const int64_t roff = tile_off + (int64_t)(ti.m0 + r0) * p.ldd + ti.n0 + cbase;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            dp[i] = drow + i * dstep;
+            rp[i] = WRES ? res_src + roff + i * dstep : nullptr;
+            mp[i] = (MASK && mode != 1) ? p.relu_mask + roff + i * dstep : nullptr;
+          }
         }
-        const bool wres = want_res && mode != 1;
-        const float* rrow = wres ? res_src + tile_off + (int64_t)(ti.m0 + r0) * p.ldd + ti.n0 + cbase : nullptr;
         const bool relu = (p.flags & VLFB_EPI_RELU) != 0, tf32 = (p.flags & VLFB_EPI_TF32) != 0;
-        const bool atomic = (p.flags & VLFB_EPI_ATOMIC) != 0, has_rs = p.row_scale != nullptr;
+        const bool has_rs = p.row_scale != nullptr;
         const bool nobias = mode == 0 && ti.k_begin != 0;                  // split-K: bias from the first K slice only
         const float alpha = p.alpha;
-        auto load_res = [&](int cofs, bool valid, float4* r) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (wres && valid && ((rowok >> i) & 1u)) r[i] = ld_nc_f4(rrow + i * dstep + cofs);
-          }
-        };
-        // ReLU-backward mask (MASK builds): the activation whose sign gates this gradient, same addressing as D
-        const float* mrow = (MASK && mode != 1) ? p.relu_mask + tile_off + (int64_t)(ti.m0 + r0) * p.ldd + ti.n0 + cbase : nullptr;
-        auto load_mask = [&](int cofs, bool valid, float4* r) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            r[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (MASK && mode != 1 && valid && ((rowok >> i) & 1u)) r[i] = ld_nc_f4(mrow + i * dstep + cofs);
-          }
-        };
         // residual / accumulate / mask operands one block ahead (register double buffer), the first before the
-        // accumulator wait
+        // accumulator wait.  ReLU-backward mask (MASK builds): the activation whose sign gates this gradient.
+        auto load_ahead = [&](bool valid, float4* r, float4* m) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (WRES) {
+              r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (valid && ((rowok >> i) & 1u)) r[i] = ld_nc_f4(rp[i]);
+            }
+            if (MASK && mode != 1) {
+              m[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+              if (valid && ((rowok >> i) & 1u)) m[i] = ld_nc_f4(mp[i]);
+            }
+          }
+        };
         float4 rr[4], rn[4], mr[4], mn[4];
-        load_res(0, half * EPC < ncols, rr);
-        if (MASK) load_mask(0, half * EPC < ncols, mr);
+        load_ahead(half * EPC < ncols, rr, mr);
         if (mode != 2) {
           mbar_wait(tfull0 + 8 * acc, (tile_iter >> 1) & 1);
           tc_fence_after();
           if (ew == 0 && lane == 0 && tile_iter < 4) TR(24 + 4 * tile_iter);
         }
-        int cofs = 0;                                                       // column offset of the block from cbase
+        int cofs = 0;                                                       // column offset of the block from cbase (mode 2)
         for (int c0 = half * EPC; c0 < ncols; c0 += 2 * EPC, cofs += 2 * EPC) {
-          load_res(cofs + 2 * EPC, c0 + 2 * EPC < ncols, rn);
-          if (MASK) load_mask(cofs + 2 * EPC, c0 + 2 * EPC < ncols, mn);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { if (WRES) rp[i] += 2 * EPC; if (MASK && mode != 1) mp[i] += 2 * EPC; }
+          load_ahead(c0 + 2 * EPC < ncols, rn, mn);
           float4 a4[4];
           if (mode != 2) {
             float v[EPC];
@@ -1288,7 +1298,7 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
           }
           if (mode == 1) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(drow + i * dstep + cofs) = a4[i];
+            for (int i = 0; i < 4; ++i) { *reinterpret_cast<float4*>(dp[i]) = a4[i]; dp[i] += 2 * EPC; }
             continue;
           }
           const int cvi = ((c0 - half * EPC) >> 1) + col;
@@ -1302,7 +1312,7 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
             o.x = fmaf(a4[i].x, cs.x, cb.x); o.y = fmaf(a4[i].y, cs.y, cb.y);
             o.z = fmaf(a4[i].z, cs.z, cb.z); o.w = fmaf(a4[i].w, cs.w, cb.w);
             if (has_rs) { o.x *= rs[i]; o.y *= rs[i]; o.z *= rs[i]; o.w *= rs[i]; }
-            if (wres) { o.x += rr[i].x; o.y += rr[i].y; o.z += rr[i].z; o.w += rr[i].w; }
+            if (WRES) { o.x += rr[i].x; o.y += rr[i].y; o.z += rr[i].z; o.w += rr[i].w; }
             if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
             if (MASK) {
               o.x = mr[i].x > 0.f ? o.x : 0.f; o.y = mr[i].y > 0.f ? o.y : 0.f;
@@ -1310,21 +1320,31 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
             }
             if (tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
             if ((rowok >> i) & 1u) {
-              if (atomic) red_add_f4(drow + i * dstep + cofs, o);
-              else *reinterpret_cast<float4*>(drow + i * dstep + cofs) = o;
+              if (ATOMIC) red_add_f4(dp[i], o);
+              else *reinterpret_cast<float4*>(dp[i]) = o;
             }
+            dp[i] += 2 * EPC;
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { rr[i] = rn[i]; if (MASK) mr[i] = mn[i]; }
+          for (int i = 0; i < 4; ++i) { if (WRES) rr[i] = rn[i]; if (MASK) mr[i] = mn[i]; }
         }
+      };
+      // run-time epilogue flavour -> compile-time flags (atomic accumulate; residual / D-accumulate stream)
+      auto call_fast = [&](auto mode_c) {
+        using T = std::true_type;
+        using F = std::false_type;
+        const bool atomic = (p.flags & VLFB_EPI_ATOMIC) != 0;
+        if (decltype(mode_c)::value == 1) run_fast(mode_c, F{}, F{});
+        else if (atomic) { if (want_res) run_fast(mode_c, T{}, T{}); else run_fast(mode_c, T{}, F{}); }
+        else { if (want_res) run_fast(mode_c, F{}, T{}); else run_fast(mode_c, F{}, F{}); }
       };
       // (the 17-warp cp.async builds never take the fix-up path: the host plans stream-K fix-ups for TMA-fed launches only)
       const bool split_tile = !CP && ti.npieces() > 1;
       const bool fast_tile = !CP && vec_ok && (p.N & 15) == 0;
       if constexpr (!CP) {
         if (fast_tile) {
-          if (split_tile) run_fast(std::integral_constant<int, 1>{});
-          else run_fast(std::integral_constant<int, 0>{});
+          if (split_tile) call_fast(std::integral_constant<int, 1>{});
+          else call_fast(std::integral_constant<int, 0>{});
         } else {
           if (split_tile) run_blocks(std::integral_constant<int, 1>{});
           else run_blocks(std::integral_constant<int, 0>{});
@@ -1352,7 +1372,7 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
         if (ew == 0 && lane == 0 && tile_iter <= 4) TR(26 + 4 * (tile_iter - 1));
         if (old == ti.npieces() - 1) {
           __threadfence();
-          if (fast_tile) run_fast(std::integral_constant<int, 2>{});
+          if (fast_tile) call_fast(std::integral_constant<int, 2>{});
           else run_blocks(std::integral_constant<int, 2>{});
           if (lane == 0) *cnt = 0;                 // counters are zero again when the launch ends
           if (ew == 0 && lane == 0 && tile_iter <= 4) TR(27 + 4 * (tile_iter - 1));
