@@ -51,6 +51,63 @@ def allreduce_grads(store):
     return len(handles)
 
 
+class GradReducer(object):
+    """Bucketed gradient all-reduce OVERLAPPED with backward (the reference's per-parameter NCCLAllreduce
+    ops are scheduled by Caffe2's dag executor as their inputs become ready, model_builder_video.py:147-157).
+
+    The flat gradient buffer is cut into buckets of BUCKET_ELEMS; the executor reports every parameter whose gradient
+    is complete (`param_done`) and a bucket's all-reduce is issued -- asynchronously, on the communicator's stream, as
+    soon as its last parameter is -- while the rest of backward keeps the SMs busy; `finish` issues what is left and
+    makes the compute stream wait.  Parameters are laid out in forward order and backward visits them in reverse, so the
+    buckets complete from the end of the buffer towards its start.  Stream-ordered only (no host synchronisation): the
+    whole step, collectives included, can be captured into ONE CUDA graph."""
+
+    def __init__(self, store):
+        self.store = store
+        self.buckets = []            # (chunk index, start, end)
+        self.of_param = {}           # name -> bucket ids it overlaps
+        for ci, ch in enumerate(store.chunks):
+            n = ch['n_nonfrozen']
+            first = len(self.buckets)
+            for s in range(0, n, BUCKET_ELEMS):
+                self.buckets.append((ci, s, min(n, s + BUCKET_ELEMS)))
+            for name, (c, off, numel, _, _, _) in store.index.items():
+                if c != ci or off >= n:
+                    continue
+                lo, hi = off // BUCKET_ELEMS, (off + numel - 1) // BUCKET_ELEMS
+                self.of_param[name] = [first + b for b in range(lo, hi + 1)]
+        self.total = [0] * len(self.buckets)
+        for bs in self.of_param.values():
+            for b in bs:
+                self.total[b] += 1
+        self.remaining, self.launched, self.handles = [], [], []
+
+    def begin(self):
+        self.remaining = list(self.total)
+        self.launched = [False] * len(self.buckets)
+        self.handles = []
+
+    def _launch(self, b):
+        ci, s, e = self.buckets[b]
+        self.launched[b] = True
+        self.handles.append(dist.all_reduce(self.store.chunks[ci]['G'][s:e], op=dist.ReduceOp.SUM, async_op=True))
+
+    def param_done(self, name):
+        for b in self.of_param.get(name, ()):
+            self.remaining[b] -= 1
+            if self.remaining[b] == 0 and not self.launched[b]:
+                self._launch(b)
+
+    def finish(self):
+        for b in range(len(self.buckets)):
+            if not self.launched[b]:
+                self._launch(b)
+        for h in self.handles:
+            h.wait()
+        n, self.handles = len(self.handles), []
+        return n
+
+
 def broadcast_params(store, src=0):
     """Rank `src`'s parameters (and momentum, when allocated) become everyone's."""
     if world_size() == 1:
@@ -63,5 +120,8 @@ def broadcast_params(store, src=0):
 
 
 def install(ws):
-    """Hook the gradient all-reduce into workspace.RunNet for training nets."""
+    """Hook the gradient all-reduce into workspace.RunNet for training nets: overlapped with backward (GradReducer,
+    B200.OVERLAP_ALLREDUCE / VLFB_OVERLAP=0 to disable) or, as a fallback, after it (allreduce_grads)."""
     ws.allreduce = allreduce_grads if world_size() > 1 else None
+    ws.reducer = None
+    ws.overlap_allreduce = world_size() > 1 and os.environ.get('VLFB_OVERLAP', '1') != '0' 

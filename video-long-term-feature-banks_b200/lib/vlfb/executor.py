@@ -1183,6 +1183,9 @@ class CompiledNet(object):
             return
         self.ws.params.begin_step(self.trainable)
         self._prepare_wt(ctx)
+        red = self._reducer()
+        if red is not None:
+            red.begin()
         for n in self.losses:
             ctx.grads[(n, self.final_ver.get(n, 1))] = None
         for st in reversed(self.steps):
@@ -1191,10 +1194,29 @@ class CompiledNet(object):
                 st.bwd(ctx)
             elif any(k in ctx.grads for k in st.out_keys):
                 st.bwd(ctx)
+            if red is not None:
+                for pn in st.params:                   # this step's gradients are complete: their buckets may go
+                    red.param_done(pn)
+        if red is not None:
+            red.finish()
         if self.contrib is None:
             self.contrib = dict(ctx.counts)
         else:
             assert self.contrib == ctx.counts, 'gradient contribution counts changed between runs'
+
+    def _reducer(self):
+        """The overlapped gradient all-reduce of a data-parallel training net (None: single process, or disabled)."""
+        ws = self.ws
+        if not (self.train and ws.allreduce is not None and getattr(ws, 'overlap_allreduce', False)):
+            return None
+        from core.config import config as cfg
+        if not cfg.B200.get('OVERLAP_ALLREDUCE', True):
+            return None
+        if ws.reducer is None or ws.reducer.store is not ws.params or len(ws.reducer.store.chunks) != len(ws.params.chunks):
+            from . import dist as vdist
+            ws.params._ensure_state()
+            ws.reducer = vdist.GradReducer(ws.params)
+        return ws.reducer
 
     def _prepare_wt(self, ctx):
         """Transposed, affine-scaled, TF32-rounded weights of every conv whose input needs a gradient: persistent
@@ -1247,19 +1269,32 @@ class CompiledNet(object):
         self._forward_backward(ctx)
         if not self.train:
             return
-        if ws.allreduce is not None:
+        if ws.allreduce is not None and self._reducer() is None:
             ws.allreduce(ws.params)
         if self.update_ops:
             self._update(ws.params)
 
     def _capture(self):
-        """Capture the step for the current input signature.  Returns (g1, g2, n1, n2, written, rounded): `written`
-        = every blob the captured run bound (tensors and shape tuples), `rounded` = which of them are TF32-rounded;
-        both are re-installed after every replay, because ws.blobs is shared by all nets and an eager run of another
-        net (or of this one with another signature) rebinds the same names in between."""
+        """Capture the step for the current input signature.  Returns (g1, g2, n1, n2, written, rounded, split):
+        `written` = every blob the captured run bound (tensors and shape tuples), `rounded` = which of them are
+        TF32-rounded; both are re-installed after every replay, because ws.blobs is shared by all nets and an eager run
+        of another net (or of this one with another signature) rebinds the same names in between.  Data parallel: with
+        the all-reduce overlapped (stream-ordered NCCL issued inside backward, vlfb.dist.GradReducer) the whole step
+        is ONE graph; otherwise (`split`) two graphs with the eager all-reduce between them."""
         ws = self.ws
         torch.cuda.synchronize()
-        split = self.train and ws.allreduce is not None
+        if self._reducer() is not None:
+            try:
+                return self._capture_graphs(False)
+            except Exception as exc:                                  # e.g. a NCCL build that cannot be captured
+                import sys
+                sys.stderr.write('vlfb: capturing the overlapped all-reduce failed (%r); falling back to the split step\n' % (exc,))
+                ws.overlap_allreduce = False
+                torch.cuda.synchronize()
+        return self._capture_graphs(self.train and ws.allreduce is not None)
+
+    def _capture_graphs(self, split):
+        ws = self.ws
         n0 = K.LAUNCHES
         g1 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g1):
@@ -1277,14 +1312,14 @@ class CompiledNet(object):
         K.LAUNCHES = n0
         written = dict((k, ws.blobs[k]) for k in ctx.bound)
         rounded = set(k for k, r in ctx.bound.items() if r)
-        return (g1, g2, n1, n2, written, rounded)
+        return (g1, g2, n1, n2, written, rounded, split)
 
     def _replay(self, entry):
-        g1, g2, n1, n2, written, rounded = entry
+        g1, g2, n1, n2, written, rounded, split = entry
         ws = self.ws
         g1.replay()
         K.LAUNCHES += n1
-        if self.train and ws.allreduce is not None:
+        if split:
             ws.allreduce(ws.params)
         if g2 is not None:
             g2.replay()

@@ -200,6 +200,8 @@ class Workspace(object):
         self.params = ParamStore()
         self.nets = {}
         self.allreduce = None            # callable(ParamStore) installed by vlfb.dist
+        self.reducer = None              # vlfb.dist.GradReducer (all-reduce overlapped with backward), built lazily
+        self.overlap_allreduce = False
         self.dropout_enabled = True
         self.rng_seed = 2
         self.rng_offset = 0
