@@ -372,6 +372,21 @@ def run_b200(args):
                          'oracle restatement (the Caffe2 reference cannot run here)' % (
                              nrep, CLIPS_PER_GPU, CLIPS_PER_GPU * ROIS_PER_CLIP, BANK_ROWS)}
 
+    # ---- FBO-NL microbenchmark (BASELINE configs[4], bench_fbo.py) on the same box: the training-config bank, a folded
+    # inference bank and a large one (HBM-bound scan); resets the workspace, so it runs after everything above
+    fbo = None
+    if n_gpus == 1 and not args.no_fbo:
+        try:
+            import bench_fbo
+            fbo = []
+            for mode, R_, L_ in (('train', rois, BANK_ROWS), ('infer_fold', rois, BANK_ROWS), ('infer_fold', 64, 1200),
+                                 ('infer_fold', 256, 3600)):
+                r = bench_fbo.run_case(mode, R_, L_, 2, 10, 3, peaks)
+                fbo.append(dict((k, r[k]) for k in ('mode', 'R', 'L', 'layers', 'ms', 'launches', 'gbs', 'hbm_frac',
+                                                    'tflops_as_written', 'scan')))
+        except Exception as exc:
+            fbo = {'error': repr(exc)}
+
     print(json.dumps({
         'metric': METRIC, 'value': clips / (ms / 1e3),
         'unit': 'clips/s', 'n_gpus': n_gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
@@ -401,6 +416,7 @@ def run_b200(args):
                          'hbm_peak_gbs': peaks['hbm_gbs']},
                      'by_kind': table_json(by_kind), 'by_stage': table_json(by_stage)},
         'cpu_baseline': cpu,
+        'fbo_microbench': fbo,
         'loss': loss,
     }))
 
@@ -414,6 +430,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--dump-gemms', default='', help='write the per-launch GEMM table of one step here')
     ap.add_argument('--no-graph', action='store_true', help='eager launches (for ncu / debugging)')
+    ap.add_argument('--no-fbo', action='store_true', help='skip the FBO-NL microbenchmark cases (bench_fbo.py)')
     ap.add_argument('--no-roofline', action='store_true', help='skip the per-launch replay profile (ncu launch lists)')
     ap.add_argument('--config', default='r50_2l', choices=sorted(CONFIGS), help='r50_2l = BASELINE configs[1] (default), '
                     'r50_3l = configs[2] (ava_r50_lfb_nl_3l.yaml), r101_3l = configs[3] architecture')

@@ -168,7 +168,7 @@ def test_grad_finish_fusion_and_graph_replay_agree_with_first_run(ws):
     net = ws.current().nets[model.net.Proto().name]
     net.update_ops = []
     runs = []
-    fuse0, X.FUSE_GRAD_FINISH = X.FUSE_GRAD_FINISH, True       # off by default (slower on B200), still supported
+    fuse0, X.FUSE_GRAD_FINISH = X.FUSE_GRAD_FINISH, True       # (the default since round 2)
     lazy0, X.LAZY_GRAD_SUM = X.LAZY_GRAD_SUM, False            # same association of three-term sums in every run
     for rep in range(4):
         n0 = X.STATS['fused_grad_finish']

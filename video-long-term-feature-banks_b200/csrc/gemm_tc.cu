@@ -106,6 +106,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4,
                                             uint32_t bar) {
   asm volatile(
@@ -591,6 +597,14 @@ struct Launch {
   int lag;           // cp.async groups kept in flight before a stage is published (< stages)
   int tiles_m, tiles_n, total_tiles;
   int tile_rows;     // output rows per tile: 128, or 256 when a CTA pair shares the tile (cta_group::2)
+  int stem_patch;    // conv1 forward: an M tile = a 16 (wo) x 8 (ho) patch of one output frame instead of 128 consecutive
+                     // positions, so that ONE strided TMA box stages the whole A tile of a K chunk (tile row r =
+                     // (ho0 + r / 16, wo0 + r % 16)); the fast epilogue maps rows back (patch_row)
+  int patch_wb, patch_hb;   // patches per output row / per frame column: Wo / 16, Ho / 8 (forward), Ho / 2 (wgrad)
+                            // conv1 WGRAD (B = STEM_MN) with stem_patch: K chunk = the 32 output positions of a
+                            // 16 (wo) x 2 (ho) patch; ONE box stages the sH + kH input rows all kH filter-row atoms need
+                            // ([input row][16 windows][128 B] slabs; atom kh of output row j = slab j*sH + kh, so the UMMA
+                            // descriptor's atom stride is one slab) and one 4-D box per 32 channels stages dY^T
   // Stream-K: the linear space (tile, K chunk) is cut into one contiguous range per unit (CTA or CTA pair), so every
   // SM gets the same number of chunks whatever the tile count.  A tile whose chunks span several units is reduced
   // through the workspace by the LAST unit to arrive at its counter (no unit ever waits for another).
@@ -635,6 +649,13 @@ __device__ __forceinline__ void decode_tile(const vlfb_gemm_params_t& p, const L
   ti.nk = (ti.k_end > ti.k_begin) ? (ti.k_end - ti.k_begin + KC - 1) / KC : 0;
   ti.tile = t;
   ti.pinfo = 1;
+}
+
+// conv1 patch tiles: linear output position of tile row r of M tile `mt`
+__device__ __forceinline__ int patch_row(const vlfb_gemm_params_t& p, const Launch& L, int mt, int r) {
+  const int wb = mt % L.patch_wb, q = mt / L.patch_wb;
+  const int hb = q % L.patch_hb, rest = q / L.patch_hb;            // rest = n * To + to
+  return (rest * p.g.Ho + hb * 8 + (r >> 4)) * p.g.Wo + wb * 16 + (r & 15);
 }
 
 // Every role of a CTA (and both CTAs of a pair) walks the same work sequence.  cur/lim = next tile index / tile
@@ -795,7 +816,18 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
         // bytes the stage barrier expects: this CTA's copies (PAIR: both CTAs', posted by the leader)
         uint32_t tma_bytes = (tma_a ? (uint32_t)A_TILE_BYTES : 0u) + (tma_b ? b_tile_bytes : 0u);
         if (PAIR) tma_bytes *= 2u;
-        if (tid == 0 && stem_a) {
+        if (tid == 0 && stem_a && L.stem_patch) {
+          const vlfb_conv_geom_t& g = p.g;
+          const int mt = ti.m0 / BM;
+          const int wb = mt % L.patch_wb, q = mt / L.patch_wb;
+          const int hb = q % L.patch_hb, rest = q / L.patch_hb;
+          const int to = rest % g.To, n = rest / g.To;
+          sg_w[0] = wb * 16;
+          sg_ht[0] = ((hb * 8 * g.sH - g.pH) << 16) | ((to * g.sT - g.pT) & 0xFFFF);
+          sg_n[0] = n;
+          ic_t = kc0 / g.kH;
+          ic_h = kc0 - ic_t * g.kH;
+        } else if (tid == 0 && stem_a) {
           const vlfb_conv_geom_t& g = p.g;
           Pos4 o = decode_pos_fast((uint32_t)ti.m0, L.out);
 #pragma unroll
@@ -848,6 +880,11 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
           ib_atoms = 0;                                             // atoms = filter rows kh of this N tile
           for (int a = 0; a * 32 < bn && ti.n0 + a * 32 < p.N; ++a) ib_atoms = a + 1;
           tma_bytes = (tma_a ? (uint32_t)A_TILE_BYTES : 0u) + 4096u * (uint32_t)ib_atoms;
+          if (L.stem_patch) {
+            int a_atoms = 0;
+            for (int a = 0; a * 32 < p.M && a < BM / 32; ++a) a_atoms = a + 1;
+            tma_bytes = 4096u * (uint32_t)a_atoms + 2048u * (uint32_t)(p.g.sH + p.g.kH);
+          }
         }
         for (int i = 0; i < ti.nk; ++i, ++it) {
           if (it >= S) mbar_wait(empty0 + 8 * s, ph ^ 1u);
@@ -860,10 +897,14 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
             if (!PAIR || rank == 0) mbar_expect_tx(full0 + 8 * s_cur, tma_bytes);
             if (stem_a) {
               const vlfb_conv_geom_t& g = p.g;
+              if (L.stem_patch) {                     // one {128 B x 16 wo x 8 rows (stride sH)} box = the whole A tile
+                tma_load_5d(a_tile, &tmA, 0, sg_w[0], (sg_ht[0] >> 16) + ic_h, (int)(short)(sg_ht[0] & 0xFFFF) + ic_t, sg_n[0], fbar);
+              } else {
 #pragma unroll
-              for (int q = 0; q < NSG; ++q)
-                tma_load_5d(a_tile + q * 2048, &tmA, 0, sg_w[q], (sg_ht[q] >> 16) + ic_h, (int)(short)(sg_ht[q] & 0xFFFF) + ic_t,
-                            sg_n[q], fbar);
+                for (int q = 0; q < NSG; ++q)
+                  tma_load_5d(a_tile + q * 2048, &tmA, 0, sg_w[q], (sg_ht[q] >> 16) + ic_h, (int)(short)(sg_ht[q] & 0xFFFF) + ic_t,
+                              sg_n[q], fbar);
+              }
               if (++ic_h == g.kH) { ic_h = 0; ++ic_t; }
             } else if (im2col_a) {
               const vlfb_conv_geom_t& g = p.g;
@@ -876,7 +917,7 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
                 ic_c = 0;
                 if (++ic_w == g.kW) { ic_w = 0; if (++ic_h == g.kH) { ic_h = 0; ++ic_t; } }
               }
-            } else if (tma_a) {
+            } else if (tma_a && !(stem_b && L.stem_patch)) {
               if (is_mn(AK)) {
                 for (int a = 0; a < BM / 32; ++a)
                   ld3(a_tile + a * 4096, &tmA, ti.m0 + a * 32, ti.k_begin + i * KC, ti.batch, fbar);
@@ -884,7 +925,16 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
                 ld3(a_tile, &tmA, (kc0 + i) * KC, ti.m0, ti.batch, fbar);
               }
             }
-            if (stem_b) {
+            if (stem_b && L.stem_patch) {
+              const vlfb_conv_geom_t& g = p.g;
+              const int q = ti.k_begin / KC + i;                     // chunk -> patch (wb, row pair, frame)
+              const int wb = q % L.patch_wb, q2 = q / L.patch_wb;
+              const int hp = q2 % L.patch_hb, rest = q2 / L.patch_hb;
+              const int to = rest % g.To, n = rest / g.To;
+              tma_load_5d(b_tile, &tmB, 0, wb * 16, hp * 2 * g.sH - g.pH, to * g.sT - g.pT + ti.tap, n, fbar);
+              for (int a = 0; a * 32 < p.M && a < BM / 32; ++a)      // dY^T: {32 channels, 16 wo, 2 ho} per atom
+                tma_load_4d(a_tile + a * 4096, &tmA, ti.m0 + a * 32, wb * 16, hp * 2, rest, fbar);
+            } else if (stem_b) {
               // conv1 wgrad B tile: 32 output positions (k rows) = 2 groups of 16; per filter row kh one 32-column atom
               // (8 px x 4 ch) = two {128 B x 16 positions} boxes of the overlapping-window view
               const vlfb_conv_geom_t& g = p.g;
@@ -957,6 +1007,11 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
       const uint32_t a_hi = (uint32_t)(a_d0 >> 32), b_hi = (uint32_t)(b_d0 >> 32);
       const uint32_t a_lo0 = (uint32_t)a_d0, b_lo0 = (uint32_t)b_d0;
       const uint32_t stage_units = stage_bytes >> 4;
+      // conv1 wgrad patch chunks: atoms (filter rows) are one 2 KB input-row slab apart (LBO 2048), the second output row
+      // of the patch starts sH slabs further
+      const bool stem_pb = !PAIR && BK == VLFB_OP_STEM_MN && L.tma_b == 3 && L.stem_patch != 0;
+      const uint32_t b_lo0_pb = (uint32_t)make_desc(smem_base + A_TILE_BYTES, 2048, 512, 1);     // LBO lives in the low word
+      const uint32_t pb_rowstep = (uint32_t)(p.g.sH * 2048) >> 4;
       constexpr uint32_t a_kstep = is_mn(AK) ? (1024u >> 4) : (32u >> 4), b_kstep = is_mn(BK) ? (1024u >> 4) : (32u >> 4);
       int it = 0, tile_iter = 0, s = 0;
       uint32_t ph = 0;
@@ -981,7 +1036,10 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
 #pragma unroll
           for (int j = 0; j < KC / 8; ++j) {          // UMMA K = 8 for tf32
             const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)j * a_kstep);
-            const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)j * b_kstep);
+            uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)j * b_kstep);
+            if (BK == VLFB_OP_STEM_MN && stem_pb)     // k rows 0-15 = output row 0 (slab kh), 16-31 = output row 1 (slab sH + kh)
+              db = ((uint64_t)b_hi << 32) |
+                   (uint64_t)(b_lo0_pb + (uint32_t)s * stage_units + (uint32_t)(j >> 1) * pb_rowstep + (uint32_t)(j & 1) * (1024u >> 4));
             if (PAIR) umma_tf32_2(d_tmem, da, db, idesc, (i | j) ? 1u : 0u);
             else umma_tf32(d_tmem, da, db, idesc, (i | j) ? 1u : 0u);
           }
@@ -1210,9 +1268,10 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
         constexpr bool WRES = decltype(wres_c)::value && mode != 1;
         const int r0 = quarter * 32 + (lane >> 2);                         // tile rows r0 + 8 i of this lane
         const int cbase = half * EPC + col;
+        const bool patch = !PAIR && AK == VLFB_OP_STEM_K && L.stem_patch != 0;
         uint32_t rowok = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) rowok |= (ti.m0 + r0 + 8 * i < p.M) ? (1u << i) : 0u;
+        for (int i = 0; i < 4; ++i) rowok |= (patch || ti.m0 + r0 + 8 * i < p.M) ? (1u << i) : 0u;
         const int ncols = min(bn, p.N - ti.n0);                            // multiple of 16
         // four row pointers per stream (destination: D, or this unit's workspace slot in mode 1; residual; mask),
         // advanced by one block (32 columns) per iteration -- no per-store address arithmetic
@@ -1235,6 +1294,11 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
             dp[i] = drow + i * dstep;
             rp[i] = WRES ? res_src + roff + i * dstep : nullptr;
             mp[i] = (MASK && mode != 1) ? p.relu_mask + roff + i * dstep : nullptr;
+            if (patch && mode != 1) {                                     // conv1 patch tile: row -> (ho, wo) of the patch
+              const int64_t po = tile_off + (int64_t)patch_row(p, L, ti.m0 / BM, r0 + 8 * i) * p.ldd + ti.n0 + cbase;
+              dp[i] = p.d + po;
+              if (WRES) rp[i] = res_src + po;
+            }
           }
         }
         const bool relu = (p.flags & VLFB_EPI_RELU) != 0, tf32 = (p.flags & VLFB_EPI_TF32) != 0;
@@ -1476,7 +1540,8 @@ static bool make_tmap_im2col(CUtensorMap* tm, const float* base, int N, int D, i
 // at padded pixel wo * sW (i.e. real pixel wo * sW - pW), dim1 = wo (stride sW pixels: consecutive windows OVERLAP),
 // dim2 / dim3 = input row / frame (their out-of-range coordinates read as zeros = the H / T padding), dim4 = clip.
 // One box = 16 consecutive output positions of one output row.
-static bool make_tmap_stem(CUtensorMap* tm, const float* ptr, const vlfb_conv_geom_t& g, int64_t pitch, CUtensorMapSwizzle swz) {
+static bool make_tmap_stem(CUtensorMap* tm, const float* ptr, const vlfb_conv_geom_t& g, int64_t pitch, CUtensorMapSwizzle swz,
+                           int box_rows = 1) {
   EncodeTiledFn enc = encode_fn();
   if (!enc || g.C != 4 || (g.Wo & 15) || g.dT != 1 || g.dH != 1 || g.dW != 1 || g.kW > 8) return false;
   if (pitch < g.pW + g.W || pitch < (int64_t)(g.Wo - 1) * g.sW + 8 || (reinterpret_cast<uintptr_t>(ptr) & 15)) return false;
@@ -1484,15 +1549,33 @@ static bool make_tmap_stem(CUtensorMap* tm, const float* ptr, const vlfb_conv_ge
   cuuint64_t dims[5] = {32, (cuuint64_t)g.Wo, (cuuint64_t)g.H, (cuuint64_t)g.T, (cuuint64_t)g.N};
   cuuint64_t gstr[4] = {(cuuint64_t)g.sW * 16, (cuuint64_t)pitch * 16, (cuuint64_t)pitch * 16 * g.H,
                         (cuuint64_t)pitch * 16 * g.H * g.T};
-  cuuint32_t box[5] = {32, 16, 1, 1, 1};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  // box_rows > 1: that many input rows `sH` apart (= consecutive OUTPUT rows) in one box: boxDim = rows * stride with
+  // elementStride = stride loads ceil(boxDim / stride) = rows elements (cuTensorMapEncodeTiled)
+  // box_rows < 0: -box_rows CONSECUTIVE input rows (conv1 wgrad: the sH + kH rows two output rows' filter windows span)
+  cuuint32_t box[5] = {32, 16, (cuuint32_t)(box_rows > 1 ? box_rows * g.sH : (box_rows < 0 ? -box_rows : 1)), 1, 1};
+  cuuint32_t estr[5] = {1, 1, (cuuint32_t)(box_rows > 1 ? g.sH : 1), 1, 1};
+  if (box[2] > 256 || estr[2] > 8) return false;
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, gstr, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// conv1 wgrad A operand in patch order: dY [N*To][Ho][Wo][Co] as a 4-D map; box {32 channels, 16 wo, 2 ho} = the 32 k-rows
+// of a patch chunk for one 32-channel atom, in the MN-major atom layout (SWIZZLE_128B_ATOM_32B).
+static bool make_tmap_dy4(CUtensorMap* tm, const float* dy, const vlfb_conv_geom_t& g) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc || (g.Co & 3) || (reinterpret_cast<uintptr_t>(dy) & 15)) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)g.Co, (cuuint64_t)g.Wo, (cuuint64_t)g.Ho, (cuuint64_t)g.N * g.To};
+  cuuint64_t gstr[3] = {(cuuint64_t)g.Co * 4, (cuuint64_t)g.Co * 4 * g.Wo, (cuuint64_t)g.Co * 4 * g.Wo * g.Ho};
+  cuuint32_t box[4] = {32, 16, 2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(dy), dims, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // tuning overrides, read once (scripts/tune_gemm.py); the per-call fields of vlfb_gemm_params_t take precedence
-struct Env { int bn, stages, lag, pair, sk, debug; bool tma_mn, im2col; };
+struct Env { int bn, stages, lag, pair, sk, debug, no_patch; bool tma_mn, im2col; };
 static Env read_env() {
   Env e;
   auto geti = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
@@ -1502,6 +1585,7 @@ static Env read_env() {
   e.pair = geti("VLFB_PAIR", 0);
   e.sk = geti("VLFB_SK", 0);
   e.debug = geti("VLFB_DEBUG", 0);
+  e.no_patch = geti("VLFB_NO_PATCH", 0);
   e.tma_mn = geti("VLFB_TMA_MN", 1) != 0;
   e.im2col = geti("VLFB_IM2COL", 1) != 0;
   return e;
@@ -1716,11 +1800,41 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
         if (make_tmap_im2col(&tmA, p.a.ptr, g.N, g.To, g.Ho, g.Wo, g.Co, lo, hi, ones, BM, CU_TENSOR_MAP_SWIZZLE_128B))
           L.tma_a = 2;
       }
-      if (AK == VLFB_OP_STEM_K && p.a.ld > 0 && make_tmap_stem(&tmA, p.a.ptr, g, p.a.ld, CU_TENSOR_MAP_SWIZZLE_128B))
-        L.tma_a = 3;
-      if (BK == VLFB_OP_STEM_MN && p.b.ld > 0 && L.tma_a &&
-          make_tmap_stem(&tmB, p.b.ptr, g, p.b.ld, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
-        L.tma_b = 3;
+      if (AK == VLFB_OP_STEM_K && p.a.ld > 0) {
+        // patch tiles need the lean epilogue's row mapping: whole 16-column blocks, 16-byte addressable rows, no mask
+        const bool fast_ok = (p.N & 15) == 0 && (p.ldd & 3) == 0 && (p.d_batch_stride & 3) == 0 && (p.d_tap_stride & 3) == 0 &&
+                             (reinterpret_cast<uintptr_t>(p.d) & 15) == 0 && !p.relu_mask && !MASK &&
+                             (!p.residual || ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0 && !(p.flags & VLFB_EPI_ACCUM)));
+        L.stem_patch = 0;
+        if (fast_ok && (g.Ho & 7) == 0 && (g.Wo & 15) == 0 && !ev.no_patch &&
+            make_tmap_stem(&tmA, p.a.ptr, g, p.a.ld, CU_TENSOR_MAP_SWIZZLE_128B, 8)) {
+          L.tma_a = 3;
+          L.stem_patch = 1;
+          L.patch_wb = g.Wo / 16;
+          L.patch_hb = g.Ho / 8;
+        } else if (make_tmap_stem(&tmA, p.a.ptr, g, p.a.ld, CU_TENSOR_MAP_SWIZZLE_128B)) {
+          L.tma_a = 3;
+        }
+      }
+      if (BK == VLFB_OP_STEM_MN && p.b.ld > 0 && L.tma_a) {
+        L.stem_patch = 0;
+        CUtensorMap tmA2;
+        memset(&tmA2, 0, sizeof(tmA2));
+        // patch chunks: needs dY dense [N*To][Ho][Wo][Co] (ld == M), whole patches, all filter rows in one N tile, and the
+        // sH + kH input-row slabs (2 KB each) inside the B stage
+        if (!ev.no_patch && AK == VLFB_OP_DENSE_MN && p.a.ld == p.M && p.batch == 1 && (g.Ho & 1) == 0 && (g.Wo & 15) == 0 &&
+            p.N <= L.bn && (g.sH + g.kH) * 2048 <= L.bn * KC * 4 && (p.K % KC) == 0 && g.sH <= 8 &&
+            make_tmap_stem(&tmB, p.b.ptr, g, p.b.ld, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, -(g.sH + g.kH)) &&
+            make_tmap_dy4(&tmA2, p.a.ptr, g)) {
+          tmA = tmA2;
+          L.tma_b = 3;
+          L.stem_patch = 1;
+          L.patch_wb = g.Wo / 16;
+          L.patch_hb = g.Ho / 2;
+        } else if (make_tmap_stem(&tmB, p.b.ptr, g, p.b.ld, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) {
+          L.tma_b = 3;
+        }
+      }
       if (BK == VLFB_OP_CONV_MN && (g.C % KC) == 0 && L.tma_a &&
           make_tmap_im2col(&tmB, p.b.ptr, g.N, g.T, g.H, g.W, g.C, pad_lo, pad_hi, cstr, KC,
                            CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
@@ -1761,8 +1875,8 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
   const int smem = L.stages * stage_bytes + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   const bool cp = !(L.tma_a && L.tma_b);
   if (ev.debug)
-    fprintf(stderr, "vlfb gemm_tc: kinds %d,%d M=%d N=%d K=%d z=%d | bn=%d pair=%d sk=%d split=%d tiles=%d units=%d stages=%d tma=%d,%d cap=%d\n",
-            AK, BK, p.M, p.N, p.K, zbase, L.bn, plan.pair, L.sk, p.split_k, L.total_tiles, units, L.stages, L.tma_a, L.tma_b, cap);
+    fprintf(stderr, "vlfb gemm_tc: kinds %d,%d M=%d N=%d K=%d z=%d | bn=%d pair=%d sk=%d split=%d tiles=%d units=%d stages=%d tma=%d,%d cap=%d patch=%d\n",
+            AK, BK, p.M, p.N, p.K, zbase, L.bn, plan.pair, L.sk, p.split_k, L.total_tiles, units, L.stages, L.tma_a, L.tma_b, cap, L.stem_patch);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(plan.pair ? 2 * units : units));
   cfg.blockDim = dim3((unsigned)((cp ? NPROD : 32) + 32 + NEPI));

@@ -27,11 +27,11 @@ DTYPE = torch.float32      # the CUDA kernels are fp32-only; the CPU test stand-
 STATS = {'fused_grad_finish': 0}
 LAZY_GRAD_SUM = os.environ.get('VLFB_LAZY_GRAD_SUM', '1') != '0'   # defer residual + dgrad sums into the consumer's mask/round pass
 # Fold the ReLU backward + TF32 rounding of a conv's incoming gradient (and the sum of its earlier contributions)
-# into the epilogue of the dgrad GEMM that delivers the last contribution.  Exact (tests run both ways), but OFF by
-# default: measured on B200 the step is 2-3% SLOWER with it (19.0 vs 18.6 ms) -- the 8 epilogue warps of the
-# persistent GEMM hide the two extra operand streams far worse than the bandwidth-bound elementwise kernels they
-# replace (profiles/r01_perf_log.md).  Revisit once residual/mask tiles are staged by TMA.
-FUSE_GRAD_FINISH = os.environ.get('VLFB_FUSE_GRAD_FINISH', '0') == '1'
+# into the epilogue of the dgrad GEMM that delivers the last contribution.  Exact (tests run both ways).  Round 1
+# measured it 2-3% SLOWER (the 96-register epilogue spilled on the extra operand streams); with the 10-warp TMA-only
+# builds and the lean epilogue of round 2 (mask + residual prefetched into registers) it is 1% faster and removes 44
+# streaming launches per step (13.58 vs 13.72 ms, profiles/r02_perf_log.md): ON by default, VLFB_FUSE_GRAD_FINISH=0 disables.
+FUSE_GRAD_FINISH = os.environ.get('VLFB_FUSE_GRAD_FINISH', '1') == '1'
 
 
 def set_backend(kernels_module, device, dtype=torch.float32):
