@@ -66,10 +66,62 @@ def stem():
               flush=True)
 
 
+def strided():
+    """The networks' stride-2 layers: data gradient (parity classes on the tensor-core engine; VLFB_NO_PAR=1 = the
+    cp.async gather over all taps), plain and as the finishing contribution (+ residual, ReLU mask, TF32 rounding)."""
+    for name, ci, co, ker, pd, shp in [('res3_0_2b 3x3/2 128->128', 128, 128, (1, 3, 3), (0, 1, 1), (2, 16, 56, 56)),
+                                       ('res4_0_2b 3x3/2 256->256', 256, 256, (1, 3, 3), (0, 1, 1), (2, 16, 28, 28)),
+                                       ('res3_0_b1 1x1/2 256->512', 256, 512, (1, 1, 1), (0, 0, 0), (2, 16, 56, 56)),
+                                       ('res4_0_b1 1x1/2 512->1024', 512, 1024, (1, 1, 1), (0, 0, 0), (2, 16, 28, 28))]:
+        g = K.conv_geom(shp + (ci,), co, ker, (1, 2, 2), pd, (1, 1, 1))
+        taps = ker[0] * ker[1] * ker[2]
+        wt = torch.randn((ci, taps, co), device='cuda') * 0.05
+        dy = torch.randn(K.out_shape(g), device='cuda')
+        dx = torch.empty(shp + (ci,), device='cuda')
+        res, mask = torch.randn_like(dx), torch.randn_like(dx)
+        flop = 2.0 * dy.numel() * taps * ci / 1e9
+        t0 = timed(lambda: K.conv_dgrad(dy, wt, dx, g))
+        t1 = timed(lambda: K.conv_dgrad(dy, wt, dx, g, residual=res, relu_mask=mask, tf32_out=True))
+        print('%-28s dgrad %8.1fus (%6.1f TF/s)   finishing dgrad %8.1fus' % (name, t0, flop / t0 * 1e3, t1), flush=True)
+
+
+def epilogue_bound():
+    """Large-M, short-K layers (res2): the epilogue streams are the bound.  GB/s = algorithmic bytes / time."""
+    shp = (2, 32, 56, 56)
+    M = shp[0] * shp[1] * shp[2] * shp[3]
+    for name, ci, co, ker, pd in [('res2_2c 1x1 64->256', 64, 256, (1, 1, 1), (0, 0, 0)),
+                                  ('res2_2a 3x1x1 256->64', 256, 64, (3, 1, 1), (1, 0, 0))]:
+        g = K.conv_geom(shp + (ci,), co, ker, (1, 1, 1), pd, (1, 1, 1))
+        taps = ker[0]
+        x = torch.randn(shp + (ci,), device='cuda')
+        w = torch.randn((co,) + ker + (ci,), device='cuda') * 0.05
+        wt = torch.randn((ci, taps, co), device='cuda') * 0.05
+        s, b = torch.rand(co, device='cuda') + 0.5, torch.randn(co, device='cuda')
+        y = torch.empty(K.out_shape(g), device='cuda')
+        dy = torch.randn(K.out_shape(g), device='cuda')
+        dx = torch.empty(shp + (ci,), device='cuda')
+        resy = torch.randn_like(y)
+        res, mask = torch.randn_like(dx), torch.randn_like(dx)
+        cases = [('fwd', lambda: K.conv_fwd(x, w, y, g, scale=s, bias=b, relu=True, tf32_out=True), M * (ci + co) * 4),
+                 ('fwd+res', lambda: K.conv_fwd(x, w, y, g, scale=s, bias=b, residual=resy, relu=True, tf32_out=True), M * (ci + 2 * co) * 4),
+                 ('dgrad', lambda: K.conv_dgrad(dy, wt, dx, g), M * (ci + co) * 4),
+                 ('dgrad+res', lambda: K.conv_dgrad(dy, wt, dx, g, residual=res, tf32_out=True), M * (2 * ci + co) * 4),
+                 ('dgrad+res+mask', lambda: K.conv_dgrad(dy, wt, dx, g, residual=res, relu_mask=mask, tf32_out=True), M * (3 * ci + co) * 4)]
+        for cname, fn, nbytes in cases:
+            t = timed(fn)
+            print('%-24s %-16s %8.1fus  %7.0f GB/s' % (name, cname, t, nbytes / t / 1e3), flush=True)
+
+
 def main():
     only = sys.argv[1:] or None
     if not only or 'conv1' in only:
         stem()
+    if only and 'strided' in only:
+        strided()
+    if only and 'epi' in only:
+        epilogue_bound()
+    if only and all(o in ('conv1', 'strided', 'epi') for o in only):
+        return
     print('%-28s %-6s' % ('layer', 'op') + ''.join('%12s' % n for n, _ in VARIANTS) + '   GFLOP   best TF/s')
     for name, ci, co, ker, pd, dil, shp in CONVS:
         if only and not any(o in name for o in only):

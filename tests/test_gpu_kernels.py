@@ -84,6 +84,13 @@ GEOMS = [
     (2, 3, 6, 6, 64, 160, (1, 1, 1), (1, 1, 1), (0, 0, 0), (1, 1, 1)),
     (2, 2, 8, 8, 32, 64, (1, 1, 1), (1, 2, 2), (0, 0, 0), (1, 1, 1)),
     (1, 4, 7, 7, 256, 288, (3, 1, 1), (1, 1, 1), (1, 0, 0), (1, 1, 1)),
+    # strided dgrads: parity-class decomposition on the tensor-core engine (several M tiles with a ragged tail, a temporal
+    # kernel, one strided dimension only) and the gather fallback (odd extents)
+    (2, 2, 30, 30, 64, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1), (1, 1, 1)),
+    (1, 4, 12, 16, 64, 64, (3, 3, 3), (1, 2, 2), (1, 1, 1), (1, 1, 1)),
+    (1, 2, 8, 8, 32, 32, (1, 3, 3), (1, 2, 1), (0, 1, 1), (1, 1, 1)),
+    (3, 2, 20, 12, 128, 64, (1, 1, 1), (1, 2, 2), (0, 0, 0), (1, 1, 1)),
+    (1, 2, 15, 15, 32, 64, (1, 3, 3), (1, 2, 2), (0, 1, 1), (1, 1, 1)),
 ]
 
 

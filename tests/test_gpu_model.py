@@ -405,7 +405,7 @@ def test_tiny_fbo_avg_max_heads(ws, yaml_name):
 def test_checkpoint_round_trip_through_the_device_param_store(ws, tmp_path):
     """SURVEY 8f rank 2 on the GPU: save_model_params -> fresh workspace -> initialize_params_from_file.  Exercises the
     device layouts a file must survive: conv weights [Cout][kT][kH][kW][Cin], the stem padded to 8 px x 4 ch, the
-    TF32 operand copy (Pt) refreshed on load, momentum; the reloaded net must reproduce the step bit for bit."""
+    TF32 operand copy (Pt) refreshed on load, momentum; the reloaded net must reproduce the step (up to the order of the atomic split-K sums)."""
     import pickle
     from oracle import model as OM
     from utils import checkpoints as CK
@@ -447,4 +447,5 @@ def test_checkpoint_round_trip_through_the_device_param_store(ws, tmp_path):
     assert abs(float(ws.FetchBlob('gpu_0/loss')) - want_loss) <= 1e-6 * abs(want_loss)
     for k, v in want.items():
         got = ws.FetchBlob('gpu_0/' + k)
-        assert np.allclose(got, v, rtol=1e-5, atol=1e-8), k
+        # split-K weight gradients are accumulated with float atomics: equal up to the summation order
+        assert np.abs(got - v).max() <= 1e-5 * np.abs(v).max(), k

@@ -29,6 +29,9 @@
 
 #include "common.cuh"
 
+#ifndef VLFB_EPI_DEPTH
+#define VLFB_EPI_DEPTH 1
+#endif
 namespace vlfb {
 namespace tc {
 
@@ -584,6 +587,8 @@ unsigned long long* g_trace_buf = nullptr;
 constexpr int MAX_UNITS = 160;       // >= #SMs: CTAs (or CTA pairs) of the persistent grid
 constexpr int SK_CNT_INTS = 16384;   // arrival counters at the head of the stream-K workspace (tile x rank x epilogue warp)
 
+struct ParCls { short nh, nw, rh, rw, ph, pw; int nk; };   // taps per dim, first tap, parity, K chunks of the class
+
 struct Launch {
   int bn;        // tile N (32/64/128/256) = UMMA N = TMEM columns
   int stages;
@@ -605,6 +610,17 @@ struct Launch {
                             // 16 (wo) x 2 (ho) patch; ONE box stages the sH + kH input rows all kH filter-row atoms need
                             // ([input row][16 windows][128 B] slabs; atom kh of output row j = slab j*sH + kh, so the UMMA
                             // descriptor's atom stride is one slab) and one 4-D box per 32 channels stages dY^T
+  // Strided conv dgrad (A = DGRAD_K, sH / sW = 2) as sH * sW PARITY CLASSES: the input positions (h, w) = (sH h' + ph,
+  // sW w' + pw) of one class receive only the filter taps kh = rh + sH j, kw = rw + sW i (rh = (ph + pH) % sH ...), i.e.
+  // each class is a unit-stride convolution over dY with nh x nw taps (3x3 stride 2: 1 + 2 + 2 + 4 = 9 taps for the four
+  // classes instead of 4 x 9 with three quarters of the gathered operand zero).  The class is the tile's z index: M
+  // tiles run over the class's sub-grid (W / sW, H / sH, T, N), A is one im2col box over dY per chunk, B the chunk of
+  // the transposed weights at the ORIGINAL tap, and the epilogue maps sub-grid rows back to dX rows (par_row).
+  int par;           // number of parity classes (0 = off)
+  int par_m;         // rows of one class = N T (H / sH) (W / sW)
+  int par_lo[2];     // im2col origin offset (w, h) shared by the classes: (p + ph) / s - (taps - 1)
+  PosDiv sub;        // fast divisors of the sub-grid extents
+  ParCls par_cls[4];
   // Stream-K: the linear space (tile, K chunk) is cut into one contiguous range per unit (CTA or CTA pair), so every
   // SM gets the same number of chunks whatever the tile count.  A tile whose chunks span several units is reduced
   // through the workspace by the LAST unit to arrive at its counter (no unit ever waits for another).
@@ -647,8 +663,20 @@ __device__ __forceinline__ void decode_tile(const vlfb_gemm_params_t& p, const L
   ti.k_begin = split * kper;
   ti.k_end = min(p.K, ti.k_begin + kper);
   ti.nk = (ti.k_end > ti.k_begin) ? (ti.k_end - ti.k_begin + KC - 1) / KC : 0;
+  if (L.par) {                     // z = parity class: its own K extent (possibly zero: epilogue-only tiles)
+    ti.k_begin = 0;
+    ti.nk = L.par_cls[zz].nk;
+    ti.k_end = ti.nk * KC;
+  }
   ti.tile = t;
   ti.pinfo = 1;
+}
+
+// strided-dgrad parity classes: dX row of sub-grid row m of class c
+__device__ __forceinline__ int par_row(const vlfb_gemm_params_t& p, const Launch& L, int cls, int m) {
+  const Pos4 o = decode_pos_fast((uint32_t)m, L.sub);
+  const ParCls& c = L.par_cls[cls];
+  return ((o.n * p.g.T + o.t) * p.g.H + o.h * p.g.sH + c.ph) * p.g.W + o.w * p.g.sW + c.pw;
 }
 
 // conv1 patch tiles: linear output position of tile row r of M tile `mt`
@@ -691,7 +719,7 @@ __device__ __forceinline__ bool sched_next(const vlfb_gemm_params_t& p, const La
   while (s.cur < s.lim) {
     decode_tile(p, L, s.cur, rank, p.split_k, ti);
     s.cur += nunits;
-    if (ti.nk != 0) return true;
+    if (ti.nk != 0 || L.par) return true;
   }
   return false;
 }
@@ -847,6 +875,11 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
             const Pos4 o = decode_pos_fast((uint32_t)ti.m0, L.out);
             ia_w = o.w * g.sW - g.pW; ia_h = o.h * g.sH - g.pH; ia_d = o.t * g.sT - g.pT; ia_n = o.n;
             icpt = g.C / KC;
+          } else if (L.par) {   // parity class of a strided dgrad: unit-stride gather over dY with the class's taps
+            const Pos4 o = decode_pos_fast((uint32_t)ti.m0, L.sub);
+            ia_w = o.w + L.par_lo[0]; ia_h = o.h + L.par_lo[1];
+            ia_d = o.t + g.pT - (g.kT - 1) * g.dT; ia_n = o.n;
+            icpt = g.Co / KC;
           } else {  // DGRAD_K, unit strides: dx[i] = sum_tap dy[i + pad - tap*dil] -> origin i + pad - (k-1)*dil
             const Pos4 o = decode_pos_fast((uint32_t)ti.m0, L.in);
             ia_w = o.w + g.pW - (g.kW - 1) * g.dW; ia_h = o.h + g.pH - (g.kH - 1) * g.dH;
@@ -855,7 +888,7 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
           }
           const int tap = kc0 / icpt;
           ic_c = kc0 - tap * icpt;
-          decode_tap(tap, g.kH, g.kW, ic_t, ic_h, ic_w);
+          decode_tap(tap, g.kH, g.kW, ic_t, ic_h, ic_w);     // (par: kc0 = 0 -> all zero; ic_h / ic_w count the class's taps)
         }
         if (tid == 0 && im2col_b) {
           const vlfb_conv_geom_t& g = p.g;
@@ -908,12 +941,23 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
               if (++ic_h == g.kH) { ic_h = 0; ++ic_t; }
             } else if (im2col_a) {
               const vlfb_conv_geom_t& g = p.g;
-              if (AK == VLFB_OP_CONV_K)
+              if (AK == VLFB_OP_CONV_K) {
                 ldi(a_tile, &tmA, ic_c * KC, ia_w, ia_h, ia_d, ia_n, ic_w * g.dW, ic_h * g.dH, ic_t * g.dT, fbar);
-              else
+              } else if (AK == VLFB_OP_DGRAD_K && L.par) {
+                // tap (kt, rh + sH ic_h, rw + sW ic_w) of the class: dY offset (taps - 1 - index), weights at the original tap
+                const ParCls& c = L.par_cls[ti.batch];
+                ldi(a_tile, &tmA, ic_c * KC, ia_w, ia_h, ia_d, ia_n, c.nw - 1 - ic_w, c.nh - 1 - ic_h, (g.kT - 1 - ic_t) * g.dT, fbar);
+                const int tap = (ic_t * g.kH + c.rh + g.sH * ic_h) * g.kW + c.rw + g.sW * ic_w;
+                ld3(b_tile, &tmB, tap * g.Co + ic_c * KC, nb0, 0, fbar);
+                if (++ic_c == icpt) {
+                  ic_c = 0;
+                  if (++ic_w == c.nw) { ic_w = 0; if (++ic_h == c.nh) { ic_h = 0; ++ic_t; } }
+                }
+              } else {
                 ldi(a_tile, &tmA, ic_c * KC, ia_w, ia_h, ia_d, ia_n, (g.kW - 1 - ic_w) * g.dW,
                     (g.kH - 1 - ic_h) * g.dH, (g.kT - 1 - ic_t) * g.dT, fbar);
-              if (++ic_c == icpt) {
+              }
+              if (!(AK == VLFB_OP_DGRAD_K && L.par) && ++ic_c == icpt) {
                 ic_c = 0;
                 if (++ic_w == g.kW) { ic_w = 0; if (++ic_h == g.kH) { ic_h = 0; ++ic_t; } }
               }
@@ -958,7 +1002,7 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
                 if (a < ib_atoms)
                   ldi(b_tile + a * 4096, &tmB, ib_c[a], bw, bh, bd, o.n, ib_off[a] & 0xFFFF, ib_off[a] >> 16,
                       ti.tap * g.dT, fbar);
-            } else if (tma_b) {
+            } else if (tma_b && !(AK == VLFB_OP_DGRAD_K && L.par)) {
               if (is_mn(BK)) {
                 for (int a = 0; a < bnh / 32; ++a)
                   ld3(b_tile + a * 4096, &tmB, nb0 + a * 32, ti.k_begin + i * KC, ti.batch, fbar);
@@ -1047,8 +1091,9 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
           if (PAIR) umma_commit2(empty0 + 8 * s); else umma_commit(empty0 + 8 * s);
           if (++s == S) { s = 0; ph ^= 1u; }
         }
-        // accumulator complete -> epilogue (PAIR: of both CTAs)
-        if (PAIR) umma_commit2(tfull0 + 8 * acc); else umma_commit(tfull0 + 8 * acc);
+        // accumulator complete -> epilogue (PAIR: of both CTAs); a parity class without taps has nothing to wait for
+        if (!PAIR && ti.nk == 0) mbar_arrive(tfull0 + 8 * acc);
+        else if (PAIR) umma_commit2(tfull0 + 8 * acc); else umma_commit(tfull0 + 8 * acc);
         if (tile_iter < 4) TR(17 + 2 * tile_iter);
         ++tile_iter;
       }
@@ -1084,8 +1129,9 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
     while (sched_next(p, L, sc, unit, nunits, rank, ti)) {
       const int acc = tile_iter & 1;
       const uint32_t lane_addr = tmem + (uint32_t)(acc * bn) + ((uint32_t)(quarter * 32) << 16);
-      const int64_t tile_off = (int64_t)ti.batch * p.d_batch_stride + (int64_t)ti.tap * p.d_tap_stride;
-      if (want_res || MASK) {
+      const bool par = !PAIR && AK == VLFB_OP_DGRAD_K && L.par != 0;
+      const int64_t tile_off = par ? 0 : (int64_t)ti.batch * p.d_batch_stride + (int64_t)ti.tap * p.d_tap_stride;
+      if ((want_res || MASK) && !par) {
         // pull the NEXT tile's residual / mask rows into L2 while this tile is being written out
         Sched sn = sc;
         TileInfo tn;
@@ -1269,9 +1315,10 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
         const int r0 = quarter * 32 + (lane >> 2);                         // tile rows r0 + 8 i of this lane
         const int cbase = half * EPC + col;
         const bool patch = !PAIR && AK == VLFB_OP_STEM_K && L.stem_patch != 0;
+        const int mrows = par ? L.par_m : p.M;
         uint32_t rowok = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) rowok |= (patch || ti.m0 + r0 + 8 * i < p.M) ? (1u << i) : 0u;
+        for (int i = 0; i < 4; ++i) rowok |= (patch || ti.m0 + r0 + 8 * i < mrows) ? (1u << i) : 0u;
         const int ncols = min(bn, p.N - ti.n0);                            // multiple of 16
         // four row pointers per stream (destination: D, or this unit's workspace slot in mode 1; residual; mask),
         // advanced by one block (32 columns) per iteration -- no per-store address arithmetic
@@ -1299,6 +1346,12 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
               dp[i] = p.d + po;
               if (WRES) rp[i] = res_src + po;
             }
+            if (par && mode != 1 && ((rowok >> i) & 1u)) {                // parity class: sub-grid row -> dX row
+              const int64_t po = (int64_t)par_row(p, L, ti.batch, ti.m0 + r0 + 8 * i) * p.ldd + ti.n0 + cbase;
+              dp[i] = p.d + po;
+              if (WRES) rp[i] = res_src + po;
+              if (MASK) mp[i] = p.relu_mask + po;
+            }
           }
         }
         const bool relu = (p.flags & VLFB_EPI_RELU) != 0, tf32 = (p.flags & VLFB_EPI_TF32) != 0;
@@ -1322,6 +1375,13 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
         };
         float4 rr[4], rn[4], mr[4], mn[4];
         load_ahead(half * EPC < ncols, rr, mr);
+#if VLFB_EPI_DEPTH == 2
+        // two blocks ahead: one block takes ~0.5 us to write out, less than a DRAM round trip under load
+        float4 r2[4], m2[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { if (WRES) rp[i] += 2 * EPC; if (MASK && mode != 1) mp[i] += 2 * EPC; }
+        load_ahead(half * EPC + 2 * EPC < ncols, rn, mn);
+#endif
         if (mode != 2) {
           mbar_wait(tfull0 + 8 * acc, (tile_iter >> 1) & 1);
           tc_fence_after();
@@ -1331,7 +1391,11 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
         for (int c0 = half * EPC; c0 < ncols; c0 += 2 * EPC, cofs += 2 * EPC) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) { if (WRES) rp[i] += 2 * EPC; if (MASK && mode != 1) mp[i] += 2 * EPC; }
+#if VLFB_EPI_DEPTH == 2
+          load_ahead(c0 + 4 * EPC < ncols, r2, m2);
+#else
           load_ahead(c0 + 2 * EPC < ncols, rn, mn);
+#endif
           float4 a4[4];
           if (mode != 2) {
             float v[EPC];
@@ -1346,6 +1410,10 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
             for (int i = 0; i < 4; ++i)
               a4[i] = *reinterpret_cast<const float4*>(stg + ((lane >> 2) + 8 * i) * EPITCH + col);
             __syncwarp();
+            if (par && ti.nk == 0) {                                        // class without taps: dX = finish(0)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1390,7 +1458,14 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
             dp[i] += 2 * EPC;
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { if (WRES) rr[i] = rn[i]; if (MASK) mr[i] = mn[i]; }
+          for (int i = 0; i < 4; ++i) {
+            if (WRES) rr[i] = rn[i];
+            if (MASK) mr[i] = mn[i];
+#if VLFB_EPI_DEPTH == 2
+            if (WRES) rn[i] = r2[i];
+            if (MASK) mn[i] = m2[i];
+#endif
+          }
         }
       };
       // run-time epilogue flavour -> compile-time flags (atomic accumulate; residual / D-accumulate stream)
@@ -1575,7 +1650,7 @@ static bool make_tmap_dy4(CUtensorMap* tm, const float* dy, const vlfb_conv_geom
 }
 
 // tuning overrides, read once (scripts/tune_gemm.py); the per-call fields of vlfb_gemm_params_t take precedence
-struct Env { int bn, stages, lag, pair, sk, debug, no_patch; bool tma_mn, im2col; };
+struct Env { int bn, stages, lag, pair, sk, debug, no_patch, no_par; bool tma_mn, im2col; };
 static Env read_env() {
   Env e;
   auto geti = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
@@ -1586,6 +1661,7 @@ static Env read_env() {
   e.sk = geti("VLFB_SK", 0);
   e.debug = geti("VLFB_DEBUG", 0);
   e.no_patch = geti("VLFB_NO_PATCH", 0);
+  e.no_par = geti("VLFB_NO_PAR", 0);
   e.tma_mn = geti("VLFB_TMA_MN", 1) != 0;
   e.im2col = geti("VLFB_IM2COL", 1) != 0;
   return e;
@@ -1772,9 +1848,62 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
   bool sk_ws = p.workspace != nullptr && p.workspace_bytes >= gemm_tc_workspace_bytes() &&
                      (reinterpret_cast<uintptr_t>(p.workspace) & 15) == 0;
   alignas(64) CUtensorMap tmA, tmB;
+  // Strided dgrad as parity classes (see Launch::par): needs whole strides in H / W, unit temporal stride and dilation,
+  // both operands addressable by TMA, the lean epilogue (16-byte rows, whole 16-column blocks), and one im2col origin
+  // offset shared by all classes that have taps (true for the networks' 3x3 / pad 1 and 1x1 / pad 0 stride-2 layers).
+  int par_lo[3] = {0, 0, 0}, par_hi[3] = {0, 0, 0};
+  if (AK == VLFB_OP_DGRAD_K && BK == VLFB_OP_DENSE_K && !unit_dgrad && !ev.no_par && ev.im2col && encode_fn() != nullptr &&
+      g.sT == 1 && g.sH <= 2 && g.sW <= 2 && g.dT == 1 && g.dH == 1 && g.dW == 1 && (g.H % g.sH) == 0 && (g.W % g.sW) == 0 &&
+      (g.Co % KC) == 0 && p.batch == 1 && p.taps <= 1 && p.split_k == 1 && !p.row_scale && !(p.flags & VLFB_EPI_ATOMIC) &&
+      (p.N & 15) == 0 && (p.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(p.d) & 15) == 0 &&
+      (!p.residual || ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0 && !(p.flags & VLFB_EPI_ACCUM))) &&
+      (!p.relu_mask || (reinterpret_cast<uintptr_t>(p.relu_mask) & 15) == 0)) {
+    const int Hs = g.H / g.sH, Ws = g.W / g.sW;
+    bool ok = true, have_lo = false;
+    int ncls = 0;
+    ParCls cls[4];
+    for (int ph = 0; ph < g.sH; ++ph)
+      for (int pw = 0; pw < g.sW; ++pw) {
+        ParCls c;
+        c.ph = (short)ph; c.pw = (short)pw;
+        c.rh = (short)((ph + g.pH) % g.sH); c.rw = (short)((pw + g.pW) % g.sW);
+        c.nh = (short)(c.rh < g.kH ? (g.kH - 1 - c.rh) / g.sH + 1 : 0);
+        c.nw = (short)(c.rw < g.kW ? (g.kW - 1 - c.rw) / g.sW + 1 : 0);
+        if (c.nh == 0 || c.nw == 0) c.nh = c.nw = 0;
+        c.nk = g.kT * c.nh * c.nw * (g.Co / KC);
+        if (c.nk) {
+          const int lw = (pw + g.pW) / g.sW - (c.nw - 1), lh = (ph + g.pH) / g.sH - (c.nh - 1);
+          if (have_lo && (lw != par_lo[0] || lh != par_lo[1])) ok = false;
+          par_lo[0] = lw; par_lo[1] = lh; have_lo = true;
+        }
+        cls[ncls++] = c;
+      }
+    if (ok && have_lo && (int64_t)g.N * g.T * Hs * Ws < (1ll << 31)) {
+      // heaviest classes first: the static tile loop hands tiles out round-robin
+      for (int i = 0; i < ncls; ++i)
+        for (int j = i + 1; j < ncls; ++j)
+          if (cls[j].nk > cls[i].nk) { const ParCls t = cls[i]; cls[i] = cls[j]; cls[j] = t; }
+      L.par = ncls;
+      L.par_m = g.N * g.T * Hs * Ws;
+      L.par_lo[0] = par_lo[0]; L.par_lo[1] = par_lo[1];
+      for (int i = 0; i < ncls; ++i) L.par_cls[i] = cls[i];
+      L.sub.w = make_fastdiv(Ws); L.sub.h = make_fastdiv(Hs); L.sub.t = make_fastdiv(g.T);
+      par_lo[2] = g.pT - (g.kT - 1);
+      par_hi[0] = par_lo[0] + Ws - g.Wo; par_hi[1] = par_lo[1] + Hs - g.Ho; par_hi[2] = par_lo[2] + g.T - g.To;
+      pair_ok = false;
+      sk_ws = false;
+    }
+  }
   Plan plan;
   for (int attempt = 0; attempt < 2; ++attempt) {
-    plan = make_plan(p, num_sms, pair_ok ? max_pairs<AK, BK, MASK>() : 0, pair_ok, sk_ws);
+    if (L.par) {                       // plan for the class sub-problems: M' rows, one z slice per class
+      vlfb_gemm_params_t pp = p;
+      pp.M = L.par_m; pp.batch = L.par; pp.K = L.par_cls[0].nk * KC;
+      plan = make_plan(pp, num_sms, 0, false, false);
+      plan.split_k = 1;
+    } else {
+      plan = make_plan(p, num_sms, pair_ok ? max_pairs<AK, BK, MASK>() : 0, pair_ok, sk_ws);
+    }
     L.bn = plan.bn;
     p.split_k = plan.split_k;
     const int bnh = plan.pair ? L.bn / 2 : L.bn;
@@ -1799,6 +1928,11 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
         const int hi[3] = {-g.pW, -g.pH, -g.pT};
         if (make_tmap_im2col(&tmA, p.a.ptr, g.N, g.To, g.Ho, g.Wo, g.Co, lo, hi, ones, BM, CU_TENSOR_MAP_SWIZZLE_128B))
           L.tma_a = 2;
+      }
+      if (AK == VLFB_OP_DGRAD_K && L.par) {
+        if (L.tma_b && make_tmap_im2col(&tmA, p.a.ptr, g.N, g.To, g.Ho, g.Wo, g.Co, par_lo, par_hi, ones, BM, CU_TENSOR_MAP_SWIZZLE_128B))
+          L.tma_a = 2;
+        else { L.par = 0; continue; }   // not addressable: plan again for the cp.async gather path (any geometry)
       }
       if (AK == VLFB_OP_STEM_K && p.a.ld > 0) {
         // patch tiles need the lean epilogue's row mapping: whole 16-column blocks, 16-byte addressable rows, no mask
@@ -1845,9 +1979,9 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
     pair_ok = false;                   // an operand fell back to cp.async: plan again without pairing / fix-ups
     sk_ws = false;
   }
-  const int zbase = p.taps > 1 ? p.taps : p.batch;
+  const int zbase = L.par ? L.par : (p.taps > 1 ? p.taps : p.batch);
   L.tile_rows = plan.pair ? 2 * BM : BM;
-  L.tiles_m = ceil_div(p.M, L.tile_rows);
+  L.tiles_m = ceil_div(L.par ? L.par_m : p.M, L.tile_rows);
   L.tiles_n = ceil_div(p.N, L.bn);
   L.total_tiles = (int)((int64_t)L.tiles_m * L.tiles_n * zbase * p.split_k);
   const int stage_bytes = A_TILE_BYTES + (plan.pair ? L.bn / 2 : L.bn) * KC * 4;
@@ -1875,8 +2009,8 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
   const int smem = L.stages * stage_bytes + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   const bool cp = !(L.tma_a && L.tma_b);
   if (ev.debug)
-    fprintf(stderr, "vlfb gemm_tc: kinds %d,%d M=%d N=%d K=%d z=%d | bn=%d pair=%d sk=%d split=%d tiles=%d units=%d stages=%d tma=%d,%d cap=%d patch=%d\n",
-            AK, BK, p.M, p.N, p.K, zbase, L.bn, plan.pair, L.sk, p.split_k, L.total_tiles, units, L.stages, L.tma_a, L.tma_b, cap, L.stem_patch);
+    fprintf(stderr, "vlfb gemm_tc: kinds %d,%d M=%d N=%d K=%d z=%d | bn=%d pair=%d sk=%d split=%d tiles=%d units=%d stages=%d tma=%d,%d cap=%d patch=%d par=%d\n",
+            AK, BK, p.M, p.N, p.K, zbase, L.bn, plan.pair, L.sk, p.split_k, L.total_tiles, units, L.stages, L.tma_a, L.tma_b, cap, L.stem_patch, L.par);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(plan.pair ? 2 * units : units));
   cfg.blockDim = dim3((unsigned)((cp ? NPROD : 32) + 32 + NEPI));
