@@ -106,6 +106,11 @@ typedef struct {
   int tile_n;                 /* 0 = chosen by the library, else the output-tile width (32..256, multiple of 32) */
   int pair;                   /* 0 = auto, 1 = CTA pairs (cta_group::2, 256-row tiles) whenever legal, -1 = never */
   int stream_k;               /* 0 = auto, 1 = stream-K whenever legal, -1 = never */
+  /* ---- ReLU sign bits: one bit per element of d (bit e & 31 of word e >> 5, e = the element's offset from d) ---- */
+  const uint32_t* relu_mask_bits; /* or NULL: v = bit ? v : 0, applied where relu_mask is (not both).  The mask of a ReLU's
+                               * backward at 1/32 of the bytes of the activation itself. */
+  uint32_t* relu_bits_out;    /* or NULL: with VLFB_EPI_RELU, bit = (stored value > 0).  Dense outputs only: ldd == N,
+                               * N % 32 == 0, batch == taps == split_k == 1, no VLFB_EPI_ATOMIC; M * N / 32 words. */
 } vlfb_gemm_params_t;
 
 enum { VLFB_ENGINE_TCGEN05 = 0, VLFB_ENGINE_SIMT = 1 };
@@ -183,6 +188,9 @@ int vlfb_fill(float* x, float v, int64_t n, void* stream);
 /* TF32-rounding variants used where the result feeds a tensor-core GEMM */
 int vlfb_add_tf32(const float* x, const float* y, float* out, int64_t n, void* stream);   /* round(x+y) */
 int vlfb_relu_tf32(const float* x, float* y, int64_t n, void* stream);                    /* round(max(x,0)) */
+/* bits[e >> 5] bit (e & 31) = x[e] > 0 for e < n (n % 32 == 0): the mask vlfb_gemm_params_t.relu_mask_bits reads,
+ * for activations that were not produced by a vlfb_gemm with relu_bits_out. */
+int vlfb_relu_bits(const float* x, uint32_t* bits, int64_t n, void* stream);
 int vlfb_relu_bwd_tf32(const float* dy, const float* y, float* dx, int64_t n, void* stream); /* round(dy*(y>0)) */
 /* out = (y == NULL || y > 0) ? round_tf32(a + b) : 0 : sum of two gradient contributions + ReLU backward + TF32
  * rounding in one pass (out may alias a or b). */

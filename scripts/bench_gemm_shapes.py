@@ -102,11 +102,18 @@ def epilogue_bound():
         dx = torch.empty(shp + (ci,), device='cuda')
         resy = torch.randn_like(y)
         res, mask = torch.randn_like(dx), torch.randn_like(dx)
+        mbits = torch.empty((dx.numel() // 32,), dtype=torch.int32, device='cuda')
+        K.relu_bits(mask, mbits)
+        ybits = torch.empty((y.numel() // 32,), dtype=torch.int32, device='cuda')
         cases = [('fwd', lambda: K.conv_fwd(x, w, y, g, scale=s, bias=b, relu=True, tf32_out=True), M * (ci + co) * 4),
                  ('fwd+res', lambda: K.conv_fwd(x, w, y, g, scale=s, bias=b, residual=resy, relu=True, tf32_out=True), M * (ci + 2 * co) * 4),
                  ('dgrad', lambda: K.conv_dgrad(dy, wt, dx, g), M * (ci + co) * 4),
                  ('dgrad+res', lambda: K.conv_dgrad(dy, wt, dx, g, residual=res, tf32_out=True), M * (2 * ci + co) * 4),
-                 ('dgrad+res+mask', lambda: K.conv_dgrad(dy, wt, dx, g, residual=res, relu_mask=mask, tf32_out=True), M * (3 * ci + co) * 4)]
+                 ('dgrad+res+mask', lambda: K.conv_dgrad(dy, wt, dx, g, residual=res, relu_mask=mask, tf32_out=True), M * (3 * ci + co) * 4),
+                 ('dgrad+res+bits', lambda: K.conv_dgrad(dy, wt, dx, g, residual=res, relu_mask_bits=mbits, tf32_out=True),
+                  M * (2 * ci + co) * 4 + M * ci / 8),
+                 ('fwd+res+bits out', lambda: K.conv_fwd(x, w, y, g, scale=s, bias=b, residual=resy, relu=True, tf32_out=True, relu_bits=ybits),
+                  M * (ci + 2 * co) * 4 + M * co / 8)]
         for cname, fn, nbytes in cases:
             t = timed(fn)
             print('%-24s %-16s %8.1fus  %7.0f GB/s' % (name, cname, t, nbytes / t / 1e3), flush=True)

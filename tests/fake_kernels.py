@@ -44,7 +44,22 @@ def _stem_w(w, g):
     return w[:, :, :, :g.kW, :3].permute(0, 4, 1, 2, 3)
 
 
-def conv_fwd(x, w, y, g, scale=None, bias=None, residual=None, relu=False, tf32_out=False):
+def _pack_bits(x, bits):
+    b = (x.reshape(-1, 32) > 0).to(torch.int64)
+    v = (b << torch.arange(32, dtype=torch.int64)).sum(1)
+    bits.copy_(torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32))
+
+
+def _unpack_bits(bits, shape):
+    v = bits.to(torch.int64) & 0xFFFFFFFF
+    return ((v.view(-1, 1) >> torch.arange(32, dtype=torch.int64)) & 1).reshape(shape) > 0
+
+
+def relu_bits(x, bits):
+    _pack_bits(x, bits)
+
+
+def conv_fwd(x, w, y, g, scale=None, bias=None, residual=None, relu=False, tf32_out=False, relu_bits=None):
     if g.C == 4:
         o = F.conv3d(_nc(x)[:, :3], _stem_w(w, g), None, (g.sT, g.sH, g.sW), (g.pT, g.pH, g.pW))
     else:
@@ -59,9 +74,12 @@ def conv_fwd(x, w, y, g, scale=None, bias=None, residual=None, relu=False, tf32_
     if relu:
         o = torch.relu(o)
     y.copy_(_q(o, tf32_out))
+    if relu_bits is not None:
+        assert relu
+        _pack_bits(y, relu_bits)
 
 
-def conv_dgrad(dy, wt, dx, g, accumulate=False, residual=None, relu_mask=None, tf32_out=False):
+def conv_dgrad(dy, wt, dx, g, accumulate=False, residual=None, relu_mask=None, tf32_out=False, relu_mask_bits=None):
     taps = g.kT * g.kH * g.kW
     w = wt.view(g.C, taps, g.Co).permute(2, 1, 0).reshape(g.Co, g.kT, g.kH, g.kW, g.C)
     x = torch.zeros((g.N, g.C, g.T, g.H, g.W), dtype=dy.dtype, requires_grad=True)
@@ -74,6 +92,8 @@ def conv_dgrad(dy, wt, dx, g, accumulate=False, residual=None, relu_mask=None, t
         r = r + residual
     if relu_mask is not None:
         r = torch.where(relu_mask > 0, r, torch.zeros_like(r))
+    if relu_mask_bits is not None:
+        r = torch.where(_unpack_bits(relu_mask_bits, r.shape), r, torch.zeros_like(r))
     dx.copy_(_q(r, tf32_out))
 
 

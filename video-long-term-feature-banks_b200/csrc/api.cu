@@ -28,7 +28,15 @@ static int validate_gemm(const vlfb_gemm_params_t& p, bool& tc_ok) {
   VLFB_CHECK_ARG(p.engine == VLFB_ENGINE_TCGEN05 || p.engine == VLFB_ENGINE_SIMT);
   VLFB_CHECK_ARG(p.tile_n == 0 || (p.tile_n >= 32 && p.tile_n <= 256 && p.tile_n % 32 == 0));
   VLFB_CHECK_ARG(p.split_k == 1 || (p.flags & VLFB_EPI_ATOMIC));
-  VLFB_CHECK_ARG(!(p.split_k != 1 && (p.residual || p.relu_mask || (p.flags & (VLFB_EPI_RELU | VLFB_EPI_TF32)))));
+  VLFB_CHECK_ARG(!(p.split_k != 1 && (p.residual || p.relu_mask || p.relu_mask_bits || (p.flags & (VLFB_EPI_RELU | VLFB_EPI_TF32)))));
+  VLFB_CHECK_ARG(!(p.relu_mask && p.relu_mask_bits));
+  if (p.relu_bits_out) {
+    if (!((p.flags & VLFB_EPI_RELU) && !(p.flags & VLFB_EPI_ATOMIC) && p.split_k == 1 && p.batch == 1 && p.taps == 1 &&
+          p.ldd == p.N && (p.N & 31) == 0 && (reinterpret_cast<uintptr_t>(p.relu_bits_out) & 3) == 0)) {
+      set_error("vlfb_gemm: relu_bits_out needs VLFB_EPI_RELU and a dense, non-atomic, unsplit output with N %% 32 == 0");
+      return VLFB_E_BADARG;
+    }
+  }
   if (!(aligned16(p.a.ptr) && aligned16(p.b.ptr))) tc_ok = false;
   const vlfb_operand_t* ops[2] = {&p.a, &p.b};
   for (int i = 0; i < 2; ++i) {
@@ -108,7 +116,15 @@ int vlfb_gemm(const vlfb_gemm_params_t* p, void* stream) {
   int rc = validate_gemm(*p, tc_ok);
   if (rc != VLFB_OK) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return (p->engine == VLFB_ENGINE_SIMT || !tc_ok) ? gemm_simt(*p, s) : gemm_tc(*p, s);
+  if (p->engine == VLFB_ENGINE_SIMT || !tc_ok) {
+    // the cross-check engine stores element by element: the sign bits are a second pass over the dense output
+    vlfb_gemm_params_t q = *p;
+    q.relu_bits_out = nullptr;
+    rc = gemm_simt(q, s);
+    if (rc == VLFB_OK && p->relu_bits_out) rc = relu_bits(p->d, p->relu_bits_out, (int64_t)p->M * p->N, s);
+    return rc;
+  }
+  return gemm_tc(*p, s);
 }
 
 }  // extern "C"

@@ -142,12 +142,14 @@ __device__ __forceinline__ void epilogue_store(const vlfb_gemm_params_t& p, int 
   if (p.flags & VLFB_EPI_ACCUM) v += p.d[off];
   if (p.flags & VLFB_EPI_RELU) v = fmaxf(v, 0.f);
   if (p.relu_mask && !(p.relu_mask[off] > 0.f)) v = 0.f;
+  if (p.relu_mask_bits && !((p.relu_mask_bits[off >> 5] >> (off & 31)) & 1u)) v = 0.f;
   if (p.flags & VLFB_EPI_TF32) v = round_tf32(v);
   if (p.flags & VLFB_EPI_ATOMIC) atomicAdd(p.d + off, v);
   else p.d[off] = v;
 }
 
 int gemm_simt(const vlfb_gemm_params_t& p, cudaStream_t stream);
+int relu_bits(const float* x, uint32_t* bits, int64_t n, cudaStream_t stream);     // ops.cu
 int gemm_tc(const vlfb_gemm_params_t& p, cudaStream_t stream);
 void gemm_tc_plan(const vlfb_gemm_params_t& p, int num_sms, vlfb_gemm_plan_t* out);
 size_t gemm_tc_workspace_bytes();

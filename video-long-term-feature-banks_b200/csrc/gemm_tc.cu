@@ -30,7 +30,7 @@
 #include "common.cuh"
 
 #ifndef VLFB_EPI_DEPTH
-#define VLFB_EPI_DEPTH 1
+#define VLFB_EPI_DEPTH 2
 #endif
 namespace vlfb {
 namespace tc {
@@ -238,6 +238,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 // residual / accumulate reads: plain (coherent) 128-bit loads -- D may have been written by an earlier launch
 // on the same stream, never by this one
 __device__ __forceinline__ float4 ld_nc_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ uint32_t ld_nc_u16(const unsigned short* p) {
+  unsigned short v;
+  asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return (uint32_t)v;
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -586,6 +591,12 @@ unsigned long long* g_trace_buf = nullptr;
 #endif
 constexpr int MAX_UNITS = 160;       // >= #SMs: CTAs (or CTA pairs) of the persistent grid
 constexpr int SK_CNT_INTS = 16384;   // arrival counters at the head of the stream-K workspace (tile x rank x epilogue warp)
+
+// the lean epilogue addresses D / residual / sign bits with 32-bit element offsets
+__host__ __device__ inline bool span32_ok(const vlfb_gemm_params_t& p) {
+  const long long z = p.taps > 1 ? (long long)(p.taps - 1) * p.d_tap_stride : (long long)(p.batch - 1) * p.d_batch_stride;
+  return z >= 0 && p.ldd > 0 && (long long)p.M * p.ldd + z < (1ll << 32);
+}
 
 struct ParCls { short nh, nw, rh, rw, ph, pw; int nk; };   // taps per dim, first tap, parity, K chunks of the class
 
@@ -1143,7 +1154,7 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
             const int m = tn.m0 + row, n = tn.n0 + seg * 32;
             if (m < p.M && n < p.N) {
               if (want_res) prefetch_l2(res_src + noff + (int64_t)m * p.ldd + n);
-              if (MASK) prefetch_l2(p.relu_mask + noff + (int64_t)m * p.ldd + n);
+              if (MASK && p.relu_mask) prefetch_l2(p.relu_mask + noff + (int64_t)m * p.ldd + n);
             }
           }
         }
@@ -1195,7 +1206,15 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
           for (int i = 0; i < 4; ++i) {
             const int m = ti.m0 + quarter * 32 + (lane >> 2) + 8 * i;
             mk[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (ok && m < p.M) mk[i] = ld_nc_f4(p.relu_mask + tile_off + (int64_t)m * p.ldd + n);
+            if (ok && m < p.M) {
+              const int64_t e = tile_off + (int64_t)m * p.ldd + n;
+              if (p.relu_mask) {
+                mk[i] = ld_nc_f4(p.relu_mask + e);
+              } else {                                 // sign bits (n % 4 == 0: the four bits sit in one word)
+                const uint32_t nib = p.relu_mask_bits[e >> 5] >> (e & 31);
+                mk[i] = make_float4((nib & 1u) ? 1.f : 0.f, (nib & 2u) ? 1.f : 0.f, (nib & 4u) ? 1.f : 0.f, (nib & 8u) ? 1.f : 0.f);
+              }
+            }
           }
         };
         auto pack_mask = [](const float4* mk) {
@@ -1320,83 +1339,67 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
 #pragma unroll
         for (int i = 0; i < 4; ++i) rowok |= (patch || ti.m0 + r0 + 8 * i < mrows) ? (1u << i) : 0u;
         const int ncols = min(bn, p.N - ti.n0);                            // multiple of 16
-        // four row pointers per stream (destination: D, or this unit's workspace slot in mode 1; residual; mask),
-        // advanced by one block (32 columns) per iteration -- no per-store address arithmetic
-        float* dp[4];
-        const float* rp[4];
-        const float* mp[4];
-        {
-          float* drow;
-          int64_t dstep;
-          if (mode == 1) {
-            drow = L.ws_tiles + ((size_t)(unit * 2 + ti.slot()) * nrank + rank) * ws_tile_floats + (size_t)r0 * bn + cbase;
-            dstep = 8 * (int64_t)bn;
-          } else {
-            drow = p.d + tile_off + (int64_t)(ti.m0 + r0) * p.ldd + ti.n0 + cbase;
-            dstep = 8 * p.ldd;
-          }
-          const int64_t roff = tile_off + (int64_t)(ti.m0 + r0) * p.ldd + ti.n0 + cbase;
+        // ONE 32-bit element offset per row, shared by every stream (D, residual, sign bits: same addressing), advanced by
+        // one block (32 columns) per step; 64-bit row pointers per stream cost 24 registers, which the look-ahead
+        // buffers need (the host / fast_tile test guarantees offsets < 2^32)
+        uint32_t eo[4];
+        float* wsp = nullptr;                  // mode 1: this unit's workspace slot (rows 8 bn apart)
+        unsigned short* bout = nullptr;        // relu_bits_out group of tile row r0 + 8 (lane & 3) (this lane stores that row's)
+        const bool emit_bits = mode != 1 && !ATOMIC && p.relu_bits_out != nullptr;
+        if (mode == 1)
+          wsp = L.ws_tiles + ((size_t)(unit * 2 + ti.slot()) * nrank + rank) * ws_tile_floats + (size_t)r0 * bn + cbase;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            dp[i] = drow + i * dstep;
-            rp[i] = WRES ? res_src + roff + i * dstep : nullptr;
-            mp[i] = (MASK && mode != 1) ? p.relu_mask + roff + i * dstep : nullptr;
-            if (patch && mode != 1) {                                     // conv1 patch tile: row -> (ho, wo) of the patch
-              const int64_t po = tile_off + (int64_t)patch_row(p, L, ti.m0 / BM, r0 + 8 * i) * p.ldd + ti.n0 + cbase;
-              dp[i] = p.d + po;
-              if (WRES) rp[i] = res_src + po;
-            }
-            if (par && mode != 1 && ((rowok >> i) & 1u)) {                // parity class: sub-grid row -> dX row
-              const int64_t po = (int64_t)par_row(p, L, ti.batch, ti.m0 + r0 + 8 * i) * p.ldd + ti.n0 + cbase;
-              dp[i] = p.d + po;
-              if (WRES) rp[i] = res_src + po;
-              if (MASK) mp[i] = p.relu_mask + po;
-            }
-          }
+        for (int i = 0; i < 4; ++i) {
+          int64_t row = ti.m0 + r0 + 8 * i;
+          if (patch) row = patch_row(p, L, ti.m0 / BM, r0 + 8 * i);      // conv1 patch tile: row -> (ho, wo) of the patch
+          if (par && ((rowok >> i) & 1u)) row = par_row(p, L, ti.batch, ti.m0 + r0 + 8 * i);   // parity class: sub-grid row -> dX row
+          eo[i] = (uint32_t)(tile_off + row * p.ldd + ti.n0 + cbase);
         }
+        if (emit_bits) {
+          const int rb = r0 + 8 * (lane & 3);
+          int64_t row = ti.m0 + rb;
+          if (patch) row = patch_row(p, L, ti.m0 / BM, rb);
+          bout = reinterpret_cast<unsigned short*>(p.relu_bits_out) + ((tile_off + row * p.ldd + ti.n0 + half * EPC) >> 4);
+        }
+        const unsigned short* mbase = reinterpret_cast<const unsigned short*>(p.relu_mask_bits);
         const bool relu = (p.flags & VLFB_EPI_RELU) != 0, tf32 = (p.flags & VLFB_EPI_TF32) != 0;
         const bool has_rs = p.row_scale != nullptr;
         const bool nobias = mode == 0 && ti.k_begin != 0;                  // split-K: bias from the first K slice only
         const float alpha = p.alpha;
-        // residual / accumulate / mask operands one block ahead (register double buffer), the first before the
-        // accumulator wait.  ReLU-backward mask (MASK builds): the activation whose sign gates this gradient.
-        auto load_ahead = [&](bool valid, float4* r, float4* m) {
+        // residual / accumulate / mask operands of the block `ahead` blocks after the current one.  ReLU-backward mask
+        // (MASK builds): the sign bits of the activation that gates this gradient, one 16-bit group per row and block.
+        auto load_ahead = [&](bool valid, int ahead, float4* r, uint32_t* m) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
+            const uint32_t e = eo[i] + (uint32_t)(ahead * 2 * EPC);
             if (WRES) {
               r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (valid && ((rowok >> i) & 1u)) r[i] = ld_nc_f4(rp[i]);
+              if (valid && ((rowok >> i) & 1u)) r[i] = ld_nc_f4(res_src + e);
             }
             if (MASK && mode != 1) {
-              m[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-              if (valid && ((rowok >> i) & 1u)) m[i] = ld_nc_f4(mp[i]);
+              m[i] = 0xFFFFu;
+              if (valid && ((rowok >> i) & 1u)) m[i] = ld_nc_u16(mbase + ((e - (uint32_t)col) >> 4));
             }
           }
         };
-        float4 rr[4], rn[4], mr[4], mn[4];
-        load_ahead(half * EPC < ncols, rr, mr);
-#if VLFB_EPI_DEPTH == 2
-        // two blocks ahead: one block takes ~0.5 us to write out, less than a DRAM round trip under load
-        float4 r2[4], m2[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { if (WRES) rp[i] += 2 * EPC; if (MASK && mode != 1) mp[i] += 2 * EPC; }
-        load_ahead(half * EPC + 2 * EPC < ncols, rn, mn);
-#endif
+        // Residual / mask operands are fetched VLFB_EPI_DEPTH blocks ahead into a ring of register buffers; the loop is
+        // unrolled over the ring so that no buffer is ever copied (a `cur = next` move at the end of an iteration waits
+        // for the load it copies: the first version's look-ahead was worth less than one block, call G).
+        constexpr int NBUF = VLFB_EPI_DEPTH + 1;
+        float4 rbuf[NBUF][4];
+        uint32_t mbuf[NBUF][4];
+        load_ahead(half * EPC < ncols, 0, rbuf[0], mbuf[0]);
+        if (NBUF == 3) load_ahead(half * EPC + 2 * EPC < ncols, 1, rbuf[1], mbuf[1]);
         if (mode != 2) {
           mbar_wait(tfull0 + 8 * acc, (tile_iter >> 1) & 1);
           tc_fence_after();
           if (ew == 0 && lane == 0 && tile_iter < 4) TR(24 + 4 * tile_iter);
         }
-        int cofs = 0;                                                       // column offset of the block from cbase (mode 2)
-        for (int c0 = half * EPC; c0 < ncols; c0 += 2 * EPC, cofs += 2 * EPC) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { if (WRES) rp[i] += 2 * EPC; if (MASK && mode != 1) mp[i] += 2 * EPC; }
-#if VLFB_EPI_DEPTH == 2
-          load_ahead(c0 + 4 * EPC < ncols, r2, m2);
-#else
-          load_ahead(c0 + 2 * EPC < ncols, rn, mn);
-#endif
+        // one 32 x 16 block: operands of block c0 in (rc, mc); the block VLFB_EPI_DEPTH ahead is fetched into (rl, ml)
+        auto step = [&](int c0, int cofs, const float4* rc, const uint32_t* mc, float4* rl, uint32_t* ml) {
+          load_ahead(c0 + 2 * EPC * VLFB_EPI_DEPTH < ncols, VLFB_EPI_DEPTH, rl, ml);
           float4 a4[4];
+          uint32_t obits = 0;
           if (mode != 2) {
             float v[EPC];
             tmem_ld16(lane_addr + c0, v);
@@ -1430,8 +1433,9 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
           }
           if (mode == 1) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { *reinterpret_cast<float4*>(dp[i]) = a4[i]; dp[i] += 2 * EPC; }
-            continue;
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(wsp + (size_t)i * 8 * bn) = a4[i];
+            wsp += 2 * EPC;
+            return;
           }
           const int cvi = ((c0 - half * EPC) >> 1) + col;
           float4 cs = *reinterpret_cast<const float4*>(wsc + cvi);
@@ -1444,27 +1448,40 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
             o.x = fmaf(a4[i].x, cs.x, cb.x); o.y = fmaf(a4[i].y, cs.y, cb.y);
             o.z = fmaf(a4[i].z, cs.z, cb.z); o.w = fmaf(a4[i].w, cs.w, cb.w);
             if (has_rs) { o.x *= rs[i]; o.y *= rs[i]; o.z *= rs[i]; o.w *= rs[i]; }
-            if (WRES) { o.x += rr[i].x; o.y += rr[i].y; o.z += rr[i].z; o.w += rr[i].w; }
+            if (WRES) { o.x += rc[i].x; o.y += rc[i].y; o.z += rc[i].z; o.w += rc[i].w; }
             if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
             if (MASK) {
-              o.x = mr[i].x > 0.f ? o.x : 0.f; o.y = mr[i].y > 0.f ? o.y : 0.f;
-              o.z = mr[i].z > 0.f ? o.z : 0.f; o.w = mr[i].w > 0.f ? o.w : 0.f;
+              const uint32_t nib = mc[i] >> ((lane & 3) * 4);
+              o.x = (nib & 1u) ? o.x : 0.f; o.y = (nib & 2u) ? o.y : 0.f;
+              o.z = (nib & 4u) ? o.z : 0.f; o.w = (nib & 8u) ? o.w : 0.f;
             }
             if (tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
             if ((rowok >> i) & 1u) {
-              if (ATOMIC) red_add_f4(dp[i], o);
-              else *reinterpret_cast<float4*>(dp[i]) = o;
+              if (ATOMIC) red_add_f4(p.d + eo[i], o);
+              else *reinterpret_cast<float4*>(p.d + eo[i]) = o;
             }
-            dp[i] += 2 * EPC;
+            eo[i] += 2 * EPC;
+            if (!ATOMIC && emit_bits) {             // the row's 16 sign bits: 4 lanes x 4 columns (warp-uniform branch)
+              uint32_t nb = (o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u);
+              nb <<= (lane & 3) * 4;
+              nb |= __shfl_xor_sync(0xffffffffu, nb, 1);
+              nb |= __shfl_xor_sync(0xffffffffu, nb, 2);
+              if ((lane & 3) == i) obits = nb;
+            }
           }
+          if (!ATOMIC && emit_bits) {
+            if ((rowok >> (lane & 3)) & 1u) *bout = (unsigned short)obits;
+            bout += 2 * EPC / 16;
+          }
+        };
+        {
+          int c0 = half * EPC, cofs = 0;                                    // cofs: column offset of the block from cbase (mode 2)
+          while (c0 < ncols) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (WRES) rr[i] = rn[i];
-            if (MASK) mr[i] = mn[i];
-#if VLFB_EPI_DEPTH == 2
-            if (WRES) rn[i] = r2[i];
-            if (MASK) mn[i] = m2[i];
-#endif
+            for (int b = 0; b < NBUF; ++b) {
+              if (c0 < ncols) step(c0, cofs, rbuf[b], mbuf[b], rbuf[(b + NBUF - 1) % NBUF], mbuf[(b + NBUF - 1) % NBUF]);
+              c0 += 2 * EPC; cofs += 2 * EPC;
+            }
           }
         }
       };
@@ -1479,7 +1496,9 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
       };
       // (the 17-warp cp.async builds never take the fix-up path: the host plans stream-K fix-ups for TMA-fed launches only)
       const bool split_tile = !CP && ti.npieces() > 1;
-      const bool fast_tile = !CP && vec_ok && (p.N & 15) == 0;
+      // (MASK builds: the lean path reads the mask as sign bits; a float mask takes the general path)
+      const bool bits_ok = (p.ldd & 15) == 0 && (p.d_batch_stride & 15) == 0 && (p.d_tap_stride & 15) == 0;
+      const bool fast_tile = !CP && vec_ok && (p.N & 15) == 0 && span32_ok(p) && !(MASK && (p.relu_mask != nullptr || !bits_ok));
       if constexpr (!CP) {
         if (fast_tile) {
           if (split_tile) call_fast(std::integral_constant<int, 1>{});
@@ -1857,7 +1876,7 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
       (g.Co % KC) == 0 && p.batch == 1 && p.taps <= 1 && p.split_k == 1 && !p.row_scale && !(p.flags & VLFB_EPI_ATOMIC) &&
       (p.N & 15) == 0 && (p.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(p.d) & 15) == 0 &&
       (!p.residual || ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0 && !(p.flags & VLFB_EPI_ACCUM))) &&
-      (!p.relu_mask || (reinterpret_cast<uintptr_t>(p.relu_mask) & 15) == 0)) {
+      !p.relu_mask && (!p.relu_mask_bits || (p.ldd & 15) == 0)) {
     const int Hs = g.H / g.sH, Ws = g.W / g.sW;
     bool ok = true, have_lo = false;
     int ncls = 0;
@@ -2021,11 +2040,21 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = plan.pair ? 1 : 0;
+  // ReLU sign bits are emitted by the lean epilogue; any other path writes them in a second pass over the dense output
+  const bool lean = !cp && (p.ldd & 3) == 0 && (p.N & 15) == 0 && span32_ok(p) && (reinterpret_cast<uintptr_t>(p.d) & 15) == 0 &&
+                    (!p.residual || ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0 && !(p.flags & VLFB_EPI_ACCUM)));
+  uint32_t* bits_after = nullptr;
+  if (p.relu_bits_out && !lean) { bits_after = p.relu_bits_out; p.relu_bits_out = nullptr; }
+  int rc = VLFB_OK;
+  bool done = false;
   if constexpr (kind_pair_capable(AK) && kind_pair_capable(BK)) {
-    if (plan.pair) return launch_variant<AK, BK, MASK, true, false>(cfg, p, L, tmA, tmB);
+    if (plan.pair) { rc = launch_variant<AK, BK, MASK, true, false>(cfg, p, L, tmA, tmB); done = true; }
   }
-  if (!cp) return launch_variant<AK, BK, MASK, false, false>(cfg, p, L, tmA, tmB);
-  return launch_variant<AK, BK, MASK, false, true>(cfg, p, L, tmA, tmB);
+  if (done) {}
+  else if (!cp) rc = launch_variant<AK, BK, MASK, false, false>(cfg, p, L, tmA, tmB);
+  else rc = launch_variant<AK, BK, MASK, false, true>(cfg, p, L, tmA, tmB);
+  if (rc == VLFB_OK && bits_after) rc = relu_bits(p.d, bits_after, (int64_t)p.M * p.N, stream);
+  return rc;
 }
 
 }  // namespace tc
@@ -2046,7 +2075,7 @@ void gemm_tc_set_trace(void* buf) { tc::g_trace_buf = reinterpret_cast<unsigned 
 
 int gemm_tc(const vlfb_gemm_params_t& p, cudaStream_t stream) {
   const int ak = p.a.kind, bk = p.b.kind;
-  if (p.relu_mask) {
+  if (p.relu_mask || p.relu_mask_bits) {
     // ReLU-backward mask: only the dgrad shapes need it (two more instantiations, not eighteen)
     if (ak == VLFB_OP_DGRAD_K && bk == VLFB_OP_DENSE_K) return tc::launch<VLFB_OP_DGRAD_K, VLFB_OP_DENSE_K, true>(p, stream);
     if (ak == VLFB_OP_DENSE_K && bk == VLFB_OP_DENSE_K) return tc::launch<VLFB_OP_DENSE_K, VLFB_OP_DENSE_K, true>(p, stream);

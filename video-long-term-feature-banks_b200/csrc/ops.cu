@@ -688,6 +688,26 @@ __global__ void sgd_k(float* __restrict__ p, float* __restrict__ g, float* __res
 }
 
 }  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// ReLU sign bits: word w = ballot of x[32 w + lane] > 0 (the layout vlfb_gemm_params_t.relu_mask_bits reads).
+__global__ void relu_bits_k(const float* __restrict__ x, uint32_t* __restrict__ bits, int64_t words) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = warp0; w < words; w += nwarps) {
+    const unsigned b = __ballot_sync(0xffffffffu, x[w * 32 + lane] > 0.f);
+    if (lane == 0) bits[w] = b;
+  }
+}
+
+int relu_bits(const float* x, uint32_t* bits, int64_t n, cudaStream_t stream) {
+  if (n == 0) return VLFB_OK;
+  launch_k(relu_bits_k, stream_grid(n, TPB), TPB, 0, stream, x, bits, n >> 5);
+  VLFB_CHECK_LAUNCH();
+  return VLFB_OK;
+}
+
 }  // namespace vlfb
 
 using namespace vlfb;
@@ -846,6 +866,10 @@ int vlfb_add_tf32(const float* x, const float* y, float* out, int64_t n, void* s
 int vlfb_relu_tf32(const float* x, float* y, int64_t n, void* stream) {
   VLFB_CHECK_ARG(x && y && n >= 0);
   return ew_launch<EW_RELU_TF32>(x, nullptr, y, n, 0.f, 0.f, ST(stream));
+}
+int vlfb_relu_bits(const float* x, uint32_t* bits, int64_t n, void* stream) {
+  VLFB_CHECK_ARG(x && bits && n >= 0 && (n & 31) == 0);
+  return relu_bits(x, bits, n, ST(stream));
 }
 int vlfb_relu_bwd_tf32(const float* dy, const float* y, float* dx, int64_t n, void* stream) {
   VLFB_CHECK_ARG(dy && y && dx && n >= 0);

@@ -32,6 +32,8 @@ LAZY_GRAD_SUM = os.environ.get('VLFB_LAZY_GRAD_SUM', '1') != '0'   # defer resid
 # builds and the lean epilogue of round 2 (mask + residual prefetched into registers) it is 1% faster and removes 44
 # streaming launches per step (13.58 vs 13.72 ms, profiles/r02_perf_log.md): ON by default, VLFB_FUSE_GRAD_FINISH=0 disables.
 FUSE_GRAD_FINISH = os.environ.get('VLFB_FUSE_GRAD_FINISH', '1') == '1'
+# ... with the mask read as sign bits written by the producing conv's epilogue instead of the fp32 activation
+RELU_BITS = os.environ.get('VLFB_RELU_BITS', '1') == '1'
 
 
 def set_backend(kernels_module, device, dtype=torch.float32):
@@ -128,6 +130,7 @@ class Ctx(object):
         # and TF32 rounding from that last contributor's GEMM epilogue.
         self.counts = {}
         self.final = set()
+        self.relu_bits = {}      # conv + ReLU output key -> its sign bits (int32, 1 bit per element)
         # lazy two-term sums: grads[key] (owned) + pending[key] (an alias of somebody else's gradient, e.g. the
         # residual branch).  A conv that owns `key` folds the sum into its ReLU-backward / rounding pass.
         self.pending = {}
@@ -274,7 +277,12 @@ class ConvStep(Step):
         res = None
         if self.res_key is not None:
             res = phys(ctx.get(self.res_key[0]))
-        K.conv_fwd(xp, w, phys(y), g, scale=scale, bias=bias, residual=res, relu=self.relu, tf32_out=True)
+        bits = None
+        if id(self) in ctx.net.want_relu_bits and (g.Co & 31) == 0 and g.C != 4:
+            # sign bits of the ReLU output: the backward mask the consumer's dgrad epilogue reads (1/32 of the bytes)
+            bits = empty((y.numel() // 32,), torch.int32)
+            ctx.relu_bits[self.out_keys[0]] = bits
+        K.conv_fwd(xp, w, phys(y), g, scale=scale, bias=bias, residual=res, relu=self.relu, tf32_out=True, relu_bits=bits)
         ctx.saved[id(self)] = (xp, g)
         ctx.put(self.out, y, rounded=True)
 
@@ -326,16 +334,19 @@ class ConvStep(Step):
                 # conv's ReLU backward (mask = its output = our input xp) and the TF32 rounding its own
                 # dgrad / wgrad GEMMs need -- all in this GEMM's epilogue (saves ~6 passes over the tensor).
                 mask = xp if prod.relu else None
+                mbits = ctx.relu_bits.get(xkey) if prod.relu else None
+                if mbits is not None:
+                    mask = None
                 ctx._settle(xkey)                 # a deferred sum must be complete before the gradient is finalised
                 if cur is not None and ctx.owned.get(xkey, False):
                     dx = cur
-                    K.conv_dgrad(gp, wt, as5d(phys(cur)), g, accumulate=True, relu_mask=mask, tf32_out=True)
+                    K.conv_dgrad(gp, wt, as5d(phys(cur)), g, accumulate=True, relu_mask=mask, relu_mask_bits=mbits, tf32_out=True)
                 else:
                     dx = cl_alloc((g.N, g.C, g.T, g.H, g.W))
                     if dx.shape != ctx.get(self.x).shape:
                         dx = dx.view(ctx.get(self.x).shape)
                     K.conv_dgrad(gp, wt, as5d(phys(dx)), g, residual=None if cur is None else as5d(phys(cur)),
-                                 relu_mask=mask, tf32_out=True)
+                                 relu_mask=mask, relu_mask_bits=mbits, tf32_out=True)
                 ctx.set_final_grad(xkey, dx)
                 STATS['fused_grad_finish'] += 1
             elif cur is not None and ctx.owned.get(xkey, False):
@@ -952,6 +963,15 @@ class CompiledNet(object):
         for st in self.steps:
             for k in st.out_keys:
                 self.producer[k] = st
+        # conv + ReLU outputs whose backward mask a consumer conv's dgrad epilogue may apply (grad-finish fusion): they
+        # also emit their sign bits
+        self.want_relu_bits = set()
+        if self.train and FUSE_GRAD_FINISH and RELU_BITS:
+            for st in self.steps:
+                if isinstance(st, ConvStep) and self.requires.get(st.in_keys[0], False):
+                    pr = self.producer.get(st.in_keys[0])
+                    if isinstance(pr, ConvStep) and pr.relu:
+                        self.want_relu_bits.add(id(pr))
         self.contrib = None          # key -> number of gradient contributions, recorded by the first eager run
         self.wt_buffers = {}         # id(ConvStep) -> persistent [Ci][taps][Co] dgrad weight operand
         self._wt_jobs = None

@@ -197,10 +197,11 @@ def _set_epilogue(p, scale=None, bias=None, row_scale=None, residual=None, relu=
 
 
 # --------------------------------------------------------------------------- convolution
-def conv_fwd(x, w, y, g, scale=None, bias=None, residual=None, relu=False, tf32_out=False):
+def conv_fwd(x, w, y, g, scale=None, bias=None, residual=None, relu=False, tf32_out=False, relu_bits=None):
     """y = epi(conv(x, w)).  x [N,T,H,W,C], w [Co,kT,kH,kW,C], y [N,To,Ho,Wo,Co];
     epi: *scale[co] + bias[co] (+ residual) (ReLU).  C == 4 selects the stem (conv1) path with
-    w [Co,kT,kH,8,4]."""
+    w [Co,kT,kH,8,4].  relu_bits (int32 [y.numel() / 32], with relu): also the sign bits of y, the mask of the
+    ReLU's backward (conv_dgrad relu_mask_bits)."""
     _f32c(w, 'w'), _f32c(y, 'y')
     assert tuple(x.shape) == (g.N, g.T, g.H, g.W, g.C) and tuple(y.shape) == out_shape(g)
     M = g.N * g.To * g.Ho * g.Wo
@@ -220,11 +221,15 @@ def conv_fwd(x, w, y, g, scale=None, bias=None, residual=None, relu=False, tf32_
     p.b = _operand(w, L.OP_DENSE_K, ld=K)
     p.g = g
     _set_epilogue(p, scale, bias, None, residual, relu, tf32_out)
+    if relu_bits is not None:
+        assert relu and relu_bits.dtype == torch.int32 and relu_bits.numel() * 32 == y.numel() and relu_bits.is_contiguous()
+        p.relu_bits_out = relu_bits.data_ptr()
     _run_gemm(p, 'conv_fwd', 2.0 * M * g.Co * g.kT * g.kH * g.kW * (3 if g.C == 4 else g.C),
-              _nbytes(x, w, y, residual), keep=(x, w, y, scale, bias, residual))
+              _nbytes(x, w, y, residual) + (relu_bits.numel() * 4.0 if relu_bits is not None else 0.0),
+              keep=(x, w, y, scale, bias, residual, relu_bits))
 
 
-def conv_dgrad(dy, wt, dx, g, accumulate=False, residual=None, relu_mask=None, tf32_out=False):
+def conv_dgrad(dy, wt, dx, g, accumulate=False, residual=None, relu_mask=None, tf32_out=False, relu_mask_bits=None):
     """dx = finish(conv_transpose(dy, w) [+ dx if accumulate] [+ residual]).  wt [C, kT,kH,kW, Co] (see
     weight_transpose), dx [N,T,H,W,C].  finish = the backward of the ReLU that produced this layer's input
     (relu_mask = that activation, dx zeroed where it is <= 0) and the TF32 rounding the next GEMM needs: when
@@ -248,14 +253,18 @@ def conv_dgrad(dy, wt, dx, g, accumulate=False, residual=None, relu_mask=None, t
         assert tuple(residual.shape) == tuple(dx.shape)
         p.residual = _f32c(residual, 'residual').data_ptr()
     if relu_mask is not None:
-        assert tuple(relu_mask.shape) == tuple(dx.shape)
+        assert tuple(relu_mask.shape) == tuple(dx.shape) and relu_mask_bits is None
         p.relu_mask = _f32c(relu_mask, 'relu_mask').data_ptr()
+    if relu_mask_bits is not None:          # the same mask as sign bits (conv_fwd relu_bits / relu_bits): 1/32 of the bytes
+        assert relu_mask_bits.dtype == torch.int32 and relu_mask_bits.numel() * 32 == dx.numel()
+        p.relu_mask_bits = relu_mask_bits.data_ptr()
     if tf32_out:
         p.flags |= L.EPI_TF32
     # algorithmic dgrad work = forward MACs of the same layer
     _run_gemm(p, 'conv_dgrad', 2.0 * g.N * g.To * g.Ho * g.Wo * g.Co * g.kT * g.kH * g.kW * g.C,
-              _nbytes(dy, wt, dx, residual, relu_mask) + (_nbytes(dx) if accumulate else 0.0),
-              keep=(dy, wt, dx, residual, relu_mask))
+              _nbytes(dy, wt, dx, residual, relu_mask) + (_nbytes(dx) if accumulate else 0.0) +
+              (relu_mask_bits.numel() * 4.0 if relu_mask_bits is not None else 0.0),
+              keep=(dy, wt, dx, residual, relu_mask, relu_mask_bits))
 
 
 def conv_wgrad(dy, x, dw, g, row_scale=None, col_mask=None):
@@ -491,6 +500,12 @@ def add_relu_bwd_tf32(a, b, y, out):
     """out = (y is None or y > 0) ? round_tf32(a + b) : 0 (one pass; out may alias a or b)."""
     _check(L.load().vlfb_add_relu_bwd_tf32(_ptr(_f32c(a)), _ptr(_f32c(b)), _ptr(y), _ptr(_f32c(out)), a.numel(),
                                             _stream()), 'add_relu_bwd_tf32')
+
+
+def relu_bits(x, bits):
+    """bits (int32 [x.numel() / 32]): bit e = x.flat[e] > 0."""
+    assert bits.dtype == torch.int32 and bits.numel() * 32 == x.numel()
+    _check(L.load().vlfb_relu_bits(_ptr(_f32c(x)), bits.data_ptr(), x.numel(), _stream()), 'relu_bits')
 
 
 def relu_bwd_tf32(dy, y, dx):

@@ -32,7 +32,8 @@ class GemmParams(C.Structure):
                 ('col_scale', C.c_void_p), ('col_bias', C.c_void_p), ('row_scale', C.c_void_p),
                 ('residual', C.c_void_p), ('relu_mask', C.c_void_p), ('flags', C.c_int),
                 ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
-                ('engine', C.c_int), ('tile_n', C.c_int), ('pair', C.c_int), ('stream_k', C.c_int)]
+                ('engine', C.c_int), ('tile_n', C.c_int), ('pair', C.c_int), ('stream_k', C.c_int),
+                ('relu_mask_bits', C.c_void_p), ('relu_bits_out', C.c_void_p)]
 
 
 class GemmPlan(C.Structure):
@@ -85,6 +86,7 @@ SIGNATURES = {
     'vlfb_round_tf32': [_P, _P, _L, _P],
     'vlfb_add_tf32': [_P, _P, _P, _L, _P],
     'vlfb_relu_tf32': [_P, _P, _L, _P],
+    'vlfb_relu_bits': [_P, _P, _L, _P],
     'vlfb_relu_bwd_tf32': [_P, _P, _P, _L, _P],
     'vlfb_add_relu_bwd_tf32': [_P, _P, _P, _P, _L, _P],
     'vlfb_colsum': [_P, _L, _P, _L, _I, _I, _P],
