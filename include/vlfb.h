@@ -171,7 +171,8 @@ int vlfb_roi_align_table(const float* rois, int32_t* pos, float* w, int32_t* gri
  *      lfb_helper.py:226-231) -------------------------------------------------------------- */
 /* tf32 != 0: store TF32-rounded probabilities (they are the A operand of the next GEMM) */
 int vlfb_softmax_fwd(const float* x, float* p, int64_t rows, int cols, float scale, int tf32, void* stream);
-int vlfb_softmax_bwd(const float* p, const float* dp, float* dx, int64_t rows, int cols, float scale,
+/* tf32 != 0: store the TF32-rounded gradient (when it is the only contribution to a GEMM operand) */
+int vlfb_softmax_bwd(const float* p, const float* dp, float* dx, int64_t rows, int cols, float scale, int tf32,
                      void* stream);
 
 /* ---- LayerNorm(axis=1, eps, no affine) over rows (lfb_helper.py:160-167,253-256) ------- */

@@ -213,9 +213,9 @@ def softmax_fwd(x, p, scale=1.0, tf32_out=False):
     p.copy_(_q(torch.softmax(x * scale, dim=-1), tf32_out))
 
 
-def softmax_bwd(p, dp, dx, scale=1.0):
+def softmax_bwd(p, dp, dx, scale=1.0, tf32_out=False):
     dot = (p * dp).sum(-1, keepdim=True)
-    dx.copy_(scale * p * (dp - dot))
+    dx.copy_(_q(scale * p * (dp - dot), tf32_out))
 
 
 def layernorm_fwd(x, y, mean, std, cols, eps=1e-5):

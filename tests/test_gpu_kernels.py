@@ -392,6 +392,12 @@ def test_softmax(K, rows, cols):
     dx = torch.empty_like(pd)
     K.softmax_bwd(pd, dp.float().cuda(), dx, 0.25)
     assert rel_err(dx, x.grad) < 1e-4
+    dxr = torch.empty_like(pd)
+    K.softmax_bwd(pd, dp.float().cuda(), dxr, 0.25, tf32_out=True)      # the same values, stored TF32-rounded
+    want = torch.empty_like(dx)
+    K.round_tf32(dx, want)
+    torch.cuda.synchronize()
+    assert torch.equal(dxr, want)
 
 
 def test_layernorm(K):

@@ -1327,10 +1327,11 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
       // (ncu r2b: per-float4 flag tests, 64-bit address arithmetic and bounds checks) -- 6.3 us for a 128 x 256 tile,
       // longer than the K loop of most res2 / res3 / res4 layers; here every run-time switch is tested once per tile
       // (warp-uniform), rows are four precomputed pointers and the column offset is one add per block.
-      auto run_fast = [&](auto mode_c, auto atomic_c, auto wres_c) {
+      auto run_fast = [&](auto mode_c, auto atomic_c, auto wres_c, auto bits_c) {
         constexpr int mode = decltype(mode_c)::value;
         constexpr bool ATOMIC = decltype(atomic_c)::value && mode != 1;
         constexpr bool WRES = decltype(wres_c)::value && mode != 1;
+        constexpr bool BITS = decltype(bits_c)::value && mode != 1 && !ATOMIC;      // emit the ReLU sign bits of the result
         const int r0 = quarter * 32 + (lane >> 2);                         // tile rows r0 + 8 i of this lane
         const int cbase = half * EPC + col;
         const bool patch = !PAIR && AK == VLFB_OP_STEM_K && L.stem_patch != 0;
@@ -1345,7 +1346,7 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
         uint32_t eo[4];
         float* wsp = nullptr;                  // mode 1: this unit's workspace slot (rows 8 bn apart)
         unsigned short* bout = nullptr;        // relu_bits_out group of tile row r0 + 8 (lane & 3) (this lane stores that row's)
-        const bool emit_bits = mode != 1 && !ATOMIC && p.relu_bits_out != nullptr;
+        constexpr bool emit_bits = BITS;
         if (mode == 1)
           wsp = L.ws_tiles + ((size_t)(unit * 2 + ti.slot()) * nrank + rank) * ws_tile_floats + (size_t)r0 * bn + cbase;
 #pragma unroll
@@ -1461,7 +1462,7 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
               else *reinterpret_cast<float4*>(p.d + eo[i]) = o;
             }
             eo[i] += 2 * EPC;
-            if (!ATOMIC && emit_bits) {             // the row's 16 sign bits: 4 lanes x 4 columns (warp-uniform branch)
+            if (emit_bits) {             // the row's 16 sign bits: 4 lanes x 4 columns (warp-uniform branch)
               uint32_t nb = (o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u);
               nb <<= (lane & 3) * 4;
               nb |= __shfl_xor_sync(0xffffffffu, nb, 1);
@@ -1469,7 +1470,7 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
               if ((lane & 3) == i) obits = nb;
             }
           }
-          if (!ATOMIC && emit_bits) {
+          if (emit_bits) {
             if ((rowok >> (lane & 3)) & 1u) *bout = (unsigned short)obits;
             bout += 2 * EPC / 16;
           }
@@ -1490,9 +1491,10 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
         using T = std::true_type;
         using F = std::false_type;
         const bool atomic = (p.flags & VLFB_EPI_ATOMIC) != 0;
-        if (decltype(mode_c)::value == 1) run_fast(mode_c, F{}, F{});
-        else if (atomic) { if (want_res) run_fast(mode_c, T{}, T{}); else run_fast(mode_c, T{}, F{}); }
-        else { if (want_res) run_fast(mode_c, F{}, T{}); else run_fast(mode_c, F{}, F{}); }
+        if (decltype(mode_c)::value == 1) run_fast(mode_c, F{}, F{}, F{});
+        else if (atomic) { if (want_res) run_fast(mode_c, T{}, T{}, F{}); else run_fast(mode_c, T{}, F{}, F{}); }
+        else if (!MASK && p.relu_bits_out != nullptr) { if (want_res) run_fast(mode_c, F{}, T{}, T{}); else run_fast(mode_c, F{}, F{}, T{}); }
+        else { if (want_res) run_fast(mode_c, F{}, T{}, F{}); else run_fast(mode_c, F{}, F{}, F{}); }
       };
       // (the 17-warp cp.async builds never take the fix-up path: the host plans stream-K fix-ups for TMA-fed launches only)
       const bool split_tile = !CP && ti.npieces() > 1;
@@ -2044,7 +2046,7 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
   const bool lean = !cp && (p.ldd & 3) == 0 && (p.N & 15) == 0 && span32_ok(p) && (reinterpret_cast<uintptr_t>(p.d) & 15) == 0 &&
                     (!p.residual || ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0 && !(p.flags & VLFB_EPI_ACCUM)));
   uint32_t* bits_after = nullptr;
-  if (p.relu_bits_out && !lean) { bits_after = p.relu_bits_out; p.relu_bits_out = nullptr; }
+  if (p.relu_bits_out && (!lean || MASK)) { bits_after = p.relu_bits_out; p.relu_bits_out = nullptr; }
   int rc = VLFB_OK;
   bool done = false;
   if constexpr (kind_pair_capable(AK) && kind_pair_capable(BK)) {

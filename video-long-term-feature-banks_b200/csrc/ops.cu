@@ -293,7 +293,7 @@ __global__ void softmax_fwd_k(const float* __restrict__ x, float* __restrict__ p
 }
 
 __global__ void softmax_bwd_k(const float* __restrict__ p, const float* __restrict__ dp, float* __restrict__ dx,
-                              int64_t rows, int cols, float scale) {
+                              int64_t rows, int cols, float scale, int tf32) {
   const int lane = threadIdx.x & 31;
   const int64_t wpb = blockDim.x >> 5;
   for (int64_t row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * wpb) {
@@ -302,7 +302,10 @@ __global__ void softmax_bwd_k(const float* __restrict__ p, const float* __restri
     float dot = 0.f;
     for (int c = lane; c < cols; c += 32) dot += pr[c] * dr[c];
     dot = warp_sum(dot);
-    for (int c = lane; c < cols; c += 32) dx[row * cols + c] = scale * pr[c] * (dr[c] - dot);
+    for (int c = lane; c < cols; c += 32) {
+      const float v = scale * pr[c] * (dr[c] - dot);
+      dx[row * cols + c] = tf32 ? round_tf32(v) : v;
+    }
   }
 }
 
@@ -813,10 +816,10 @@ int vlfb_softmax_fwd(const float* x, float* p, int64_t rows, int cols, float sca
   return VLFB_OK;
 }
 
-int vlfb_softmax_bwd(const float* p, const float* dp, float* dx, int64_t rows, int cols, float scale, void* stream) {
+int vlfb_softmax_bwd(const float* p, const float* dp, float* dx, int64_t rows, int cols, float scale, int tf32, void* stream) {
   VLFB_CHECK_ARG(p && dp && dx && rows >= 0 && cols > 0);
   if (rows == 0) return VLFB_OK;
-  launch_k(softmax_bwd_k, stream_grid(rows, TPB / 32), TPB, 0, ST(stream), p, dp, dx, rows, cols, scale);
+  launch_k(softmax_bwd_k, stream_grid(rows, TPB / 32), TPB, 0, ST(stream), p, dp, dx, rows, cols, scale, tf32);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }

@@ -131,6 +131,7 @@ class Ctx(object):
         self.counts = {}
         self.final = set()
         self.relu_bits = {}      # conv + ReLU output key -> its sign bits (int32, 1 bit per element)
+        self.grad_rounded = set()   # keys whose (single-contribution) gradient was stored TF32-rounded by its producer
         # lazy two-term sums: grads[key] (owned) + pending[key] (an alias of somebody else's gradient, e.g. the
         # residual branch).  A conv that owns `key` folds the sum into its ReLU-backward / rounding pass.
         self.pending = {}
@@ -169,7 +170,23 @@ class Ctx(object):
         self.owned[key] = True
         self.final.add(key)
 
-    def add_grad(self, key, g, owned):
+    def sole(self, key):
+        """True when `key` receives exactly one gradient contribution (known after the first eager run) and the step
+        that consumes this gradient -- the blob's producer, through views -- feeds it to GEMMs, i.e. would round it to
+        TF32 anyway: the kernel that computes the gradient then stores it rounded, and the consumer's copy + rounding
+        passes disappear.  (A pooling / ReLU / LayerNorm backward keeps receiving the unrounded fp32 values.)"""
+        if self.net.contrib is None:
+            return False
+        while True:
+            if self.net.contrib.get(key) != 1:
+                return False
+            st = self.net.producer.get(key)
+            if isinstance(st, (ReshapeStep, TransposeStep, SqueezeStep)):
+                key = st.in_keys[0]
+                continue
+            return isinstance(st, (ConvStep, BatchMatMulStep))
+
+    def add_grad(self, key, g, owned, rounded=False):
         if not self.net.requires.get(key, False):
             return
         assert key not in self.final, 'gradient of %s was finalised before its last contribution' % (key,)
@@ -178,7 +195,10 @@ class Ctx(object):
         if cur is None:
             self.grads[key] = g
             self.owned[key] = owned
+            if rounded:
+                self.grad_rounded.add(key)
         else:
+            self.grad_rounded.discard(key)
             if self.owned[key]:
                 K.axpby(flat(cur), 1.0, flat(g), 1.0, flat(cur))
             elif (LAZY_GRAD_SUM and owned and key not in self.pending and cur.shape == g.shape
@@ -204,6 +224,8 @@ class Ctx(object):
         output, or None) and TF32-rounded -- in one pass when a deferred sum is pending."""
         pend = self.pending.pop(key, None)
         if pend is None:
+            if y is None and key in self.grad_rounded:
+                return self.pop_grad(key)            # complete and rounded by its producer: a read-only operand
             g = self.pop_grad_owned(key)
             if g is not None:
                 if y is not None:
@@ -219,11 +241,18 @@ class Ctx(object):
     def pop_grad(self, key):
         self._settle(key)
         self.owned.pop(key, None)
+        self.grad_rounded.discard(key)
         return self.grads.pop(key, None)
+
+    def pop_grad_meta(self, key):
+        """(gradient, owned, rounded) for steps that pass a view of it on."""
+        owned, rounded = self.owned.get(key, False), key in self.grad_rounded
+        return self.pop_grad(key), owned, rounded
 
     def pop_grad_owned(self, key):
         """Gradient that may be modified in place."""
         self._settle(key)
+        self.grad_rounded.discard(key)
         own = self.owned.pop(key, False)
         g = self.grads.pop(key, None)
         if g is not None and not own:
@@ -302,7 +331,7 @@ class ConvStep(Step):
             xp, g = ctx.saved.pop(id(self))
             gp = as5d(phys(gy))
         if self.res_key is not None:
-            ctx.add_grad(self.res_key, gy, owned=False)
+            ctx.add_grad(self.res_key, gy, owned=False, rounded=True)       # gy is masked + rounded already
         scale = ctx.ws.params.phys(self.affine[0]) if self.affine else None
         store = ctx.ws.params
         if store.trainable(self.w):
@@ -354,9 +383,10 @@ class ConvStep(Step):
                 K.conv_dgrad(gp, wt, as5d(phys(cur)), g, accumulate=True)
             else:
                 dx = cl_alloc((g.N, g.C, g.T, g.H, g.W))
-                K.conv_dgrad(gp, wt, phys(dx), g, accumulate=False)
+                sole = ctx.sole(xkey)
+                K.conv_dgrad(gp, wt, phys(dx), g, accumulate=False, tf32_out=sole)
                 ctx.add_grad(xkey, dx.view(ctx.get(self.x).shape) if dx.shape != ctx.get(self.x).shape else dx,
-                             owned=True)
+                             owned=True, rounded=sole)
 
 
 class AffineStep(Step):
@@ -448,8 +478,9 @@ class SoftmaxStep(Step):
         if not gp.is_contiguous():
             gp = gp.contiguous()
         dx = empty(p.shape)
-        K.softmax_bwd(p, gp, dx, self.scale)
-        ctx.add_grad(self.in_keys[0], dx, owned=True)
+        sole = ctx.sole(self.in_keys[0])
+        K.softmax_bwd(p, gp, dx, self.scale, tf32_out=sole)
+        ctx.add_grad(self.in_keys[0], dx, owned=True, rounded=sole)
 
 
 class PoolStep(Step):
@@ -511,10 +542,10 @@ class ReshapeStep(Step):
         ctx.saved[id(self)] = tuple(x.shape)
 
     def bwd(self, ctx):
-        gy = ctx.pop_grad(self.out_keys[0])
+        gy, owned, rounded = ctx.pop_grad_meta(self.out_keys[0])
         if gy is None:
             return
-        ctx.add_grad(self.in_keys[0], gy.view(ctx.saved.pop(id(self))), owned=ctx.owned.get(self.out_keys[0], False))
+        ctx.add_grad(self.in_keys[0], gy.view(ctx.saved.pop(id(self))), owned=owned, rounded=rounded)
 
 
 class TransposeStep(Step):
@@ -523,14 +554,14 @@ class TransposeStep(Step):
         ctx.put(self.op.outputs[0], x.permute(self.op.args['axes']), rounded=self.op.inputs[0] in ctx.ws.rounded)
 
     def bwd(self, ctx):
-        gy = ctx.pop_grad(self.out_keys[0])
+        gy, _, rounded = ctx.pop_grad_meta(self.out_keys[0])
         if gy is None:
             return
         axes = self.op.args['axes']
         inv = [0] * len(axes)
         for i, a in enumerate(axes):
             inv[a] = i
-        ctx.add_grad(self.in_keys[0], gy.permute(inv), owned=False)
+        ctx.add_grad(self.in_keys[0], gy.permute(inv), owned=False, rounded=rounded)
 
 
 class SqueezeStep(Step):
@@ -543,10 +574,10 @@ class SqueezeStep(Step):
         ctx.saved[id(self)] = tuple(x.shape)
 
     def bwd(self, ctx):
-        gy = ctx.pop_grad(self.out_keys[0])
+        gy, _, rounded = ctx.pop_grad_meta(self.out_keys[0])
         if gy is None:
             return
-        ctx.add_grad(self.in_keys[0], gy.view(ctx.saved.pop(id(self))), owned=False)
+        ctx.add_grad(self.in_keys[0], gy.view(ctx.saved.pop(id(self))), owned=False, rounded=rounded)
 
 
 class StopGradientStep(Step):
@@ -587,23 +618,28 @@ class BatchMatMulStep(Step):
         ctx.put(self.op.outputs[0], d, rounded=True)
 
     def bwd(self, ctx):
-        g = ctx.pop_grad_owned(self.out_keys[0])
-        if g is None:
-            return
-        K.round_tf32(flat(g), flat(g))
+        if self.out_keys[0] in ctx.grad_rounded:
+            g = ctx.pop_grad(self.out_keys[0])       # stored rounded by its producer: a read-only operand
+        else:
+            g = ctx.pop_grad_owned(self.out_keys[0])
+            if g is None:
+                return
+            K.round_tf32(flat(g), flat(g))
         a, b = ctx.saved.pop(id(self))
         A, B = self._views(a, b)
         ta, tb = self.op.args.get('trans_a', 0), self.op.args.get('trans_b', 0)
         if ctx.net.requires.get(self.in_keys[0], False):
             da = empty_like_strided(a)
             dA = da.transpose(1, 2) if ta else da
-            K.matmul(g, B.transpose(1, 2), dA)
-            ctx.add_grad(self.in_keys[0], da, owned=True)
+            sole = ctx.sole(self.in_keys[0])
+            K.matmul(g, B.transpose(1, 2), dA, tf32_out=sole)
+            ctx.add_grad(self.in_keys[0], da, owned=True, rounded=sole)
         if ctx.net.requires.get(self.in_keys[1], False):
             db = empty_like_strided(b)
             dB = db.transpose(1, 2) if tb else db
-            K.matmul(A.transpose(1, 2), g, dB)
-            ctx.add_grad(self.in_keys[1], db, owned=True)
+            sole = ctx.sole(self.in_keys[1])
+            K.matmul(A.transpose(1, 2), g, dB, tf32_out=sole)
+            ctx.add_grad(self.in_keys[1], db, owned=True, rounded=sole)
 
 
 class FboFoldStep(Step):

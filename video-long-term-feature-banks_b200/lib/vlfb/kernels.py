@@ -449,10 +449,10 @@ def softmax_fwd(x, p, scale=1.0, tf32_out=False):
                                       int(tf32_out), _stream()), 'softmax_fwd')
 
 
-def softmax_bwd(p, dp, dx, scale=1.0):
+def softmax_bwd(p, dp, dx, scale=1.0, tf32_out=False):
     cols = p.shape[-1]
     _check(L.load().vlfb_softmax_bwd(_ptr(_f32c(p)), _ptr(_f32c(dp)), _ptr(_f32c(dx)), p.numel() // cols, cols,
-                                      float(scale), _stream()), 'softmax_bwd')
+                                      float(scale), 1 if tf32_out else 0, _stream()), 'softmax_bwd')
 
 
 def layernorm_fwd(x, y, mean, std, cols, eps=1e-5):

@@ -76,7 +76,7 @@ SIGNATURES = {
     'vlfb_roi_align_bwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     'vlfb_roi_align_table': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     'vlfb_softmax_fwd': [_P, _P, _L, _I, _F, _I, _P],
-    'vlfb_softmax_bwd': [_P, _P, _P, _L, _I, _F, _P],
+    'vlfb_softmax_bwd': [_P, _P, _P, _L, _I, _F, _I, _P],
     'vlfb_layernorm_fwd': [_P, _P, _P, _P, _L, _I, _F, _P],
     'vlfb_layernorm_bwd': [_P, _P, _P, _P, _L, _I, _P],
     'vlfb_relu_fwd': [_P, _P, _L, _P],
