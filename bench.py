@@ -422,6 +422,7 @@ def run_b200(args):
 
 
 def main():
+    global YAML, CLIPS_PER_GPU
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
@@ -434,9 +435,11 @@ def main():
     ap.add_argument('--no-roofline', action='store_true', help='skip the per-launch replay profile (ncu launch lists)')
     ap.add_argument('--config', default='r50_2l', choices=sorted(CONFIGS), help='r50_2l = BASELINE configs[1] (default), '
                     'r50_3l = configs[2] (ava_r50_lfb_nl_3l.yaml), r101_3l = configs[3] architecture')
+    ap.add_argument('--clips-per-gpu', type=int, default=CLIPS_PER_GPU, help='clips per GPU and step (default 2 = the '
+                    "reference's TRAIN.BATCH_SIZE 16 on 8 GPUs; larger batches fill the 148 SMs better)")
     args = ap.parse_args()
-    global YAML
     YAML = CONFIGS[args.config]
+    CLIPS_PER_GPU = args.clips_per_gpu
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':
         run_reference(args)

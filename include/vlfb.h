@@ -143,6 +143,29 @@ int vlfb_affine_nd_fwd(const float* x, const float* scale, const float* bias, fl
 int vlfb_affine_nd_bwd(const float* dy, const float* scale, float* dx, int64_t rows, int C,
                        void* stream);
 
+/* ---- SpatialBN (trainable batch normalisation; replaces Caffe2 SpatialBN / SpatialBNGradient as emitted by
+ *      model_builder_video.py:176-197 Conv3dBN, resnet_video.py:185-188, nonlocal_helper.py:146-155).
+ *      x, y, dy, dx: channels-last [rows][C] (rows = N*T*H*W), C % 4 == 0.  Per-channel vectors are C floats.
+ *      `workspace` (>= vlfb_spatial_bn_workspace_bytes(C), 16-byte aligned, owned by the caller) holds the fp64
+ *      reduction accumulators and the per-channel coefficients of the apply pass between the call's launches.
+ *   fwd   (is_test = False): batch mean / biased variance over the rows -> saved_mean (`_bn_sm`), saved_inv_std
+ *         = 1/sqrt(var + eps) (`_bn_siv`, read by lib/utils/bn_helper.py:170-173); y = (x - mean) * inv_std * scale
+ *         + bias; running_mean (`_bn_rm`) = running_mean * momentum + mean * (1 - momentum), running_var (`_bn_riv`:
+ *         a VARIANCE despite its name, bn_helper.py:216-219) likewise from the unbiased batch variance; both may be
+ *         NULL (bn_aux_model of precise-BN ignores them).
+ *   infer (is_test = True): y = (x - running_mean) / sqrt(running_var + eps) * scale + bias.
+ *   bwd:  dx; dscale += sum dy * xhat, dbias += sum dy (either may be NULL).                                        */
+size_t vlfb_spatial_bn_workspace_bytes(int C);
+int vlfb_spatial_bn_fwd(const float* x, const float* scale, const float* bias, float* running_mean, float* running_var,
+                        float* saved_mean, float* saved_inv_std, float* y, int64_t rows, int C, float eps, float momentum,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int vlfb_spatial_bn_infer(const float* x, const float* scale, const float* bias, const float* running_mean,
+                          const float* running_var, float* y, int64_t rows, int C, float eps, void* workspace,
+                          size_t workspace_bytes, void* stream);
+int vlfb_spatial_bn_bwd(const float* dy, const float* x, const float* scale, const float* saved_mean,
+                        const float* saved_inv_std, float* dx, float* dscale, float* dbias, int64_t rows, int C,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- pooling (MaxPool/AveragePool: resnet_video.py:190-196,219-225, nonlocal_helper.py:48-54,
  *      head_helper.py:37-40,92-98,113-115) -------------------------------------------------- */
 int vlfb_maxpool3d_fwd(const float* x, float* y, int32_t* argmax /* may be NULL */,

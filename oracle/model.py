@@ -88,10 +88,35 @@ class Graph(object):
         self.blobs[name] = y
         return y
 
+    def spatial_bn(self, x, name, dim, eps, momentum, gamma_kind='affine_s'):
+        """model.SpatialBN (trainable BN): '_s' / '_b' trained, '_rm' / '_riv' running statistics; a training graph
+        also yields '_sm' / '_siv' and the updated running statistics (recorded as '{name}_rm' / '{name}_riv')."""
+        s = self._p(name + '_s', (dim,), gamma_kind)
+        b = self._p(name + '_b', (dim,), 'affine_b')
+        rm = self._p(name + '_rm', (dim,), 'bn_rm')
+        rv = self._p(name + '_riv', (dim,), 'bn_riv')
+        if not self.run:
+            return None
+        y, nrm, nrv, sm, siv = ops.spatial_bn(x, s, b, rm.detach(), rv.detach(), eps, momentum, self.test_mode)
+        self.blobs[name] = y
+        if not self.test_mode:
+            self.blobs[name + '_rm'], self.blobs[name + '_riv'] = nrm, nrv
+            self.blobs[name + '_sm'], self.blobs[name + '_siv'] = sm, siv
+        return y
+
+    def norm(self, x, name, dim):
+        """AffineNd (MODEL.USE_AFFINE, every shipped config) or SpatialBN (resnet_helper.py / resnet_video.py:183-188)."""
+        if self.cfg.MODEL.USE_AFFINE:
+            return self.affine(x, name, dim)
+        return self.spatial_bn(x, name, dim, self.cfg.MODEL.BN_EPSILON, self.cfg.MODEL.BN_MOMENTUM)
+
     def conv_affine(self, x, prefix, cin, cout, kernels, strides, pads, dilations=(1, 1, 1)):
-        """ModelBuilder.Conv3dAffine (model_builder_video.py:200-221)."""
+        """ModelBuilder.Conv3dAffine (model_builder_video.py:200-221) / Conv3dBN (:176-197; it swallows `dilations` in
+        **kwargs and never passes it to ConvNd, so a SpatialBN net only builds with MODEL.DILATIONS_AFTER_CONV5 False)."""
+        if not self.cfg.MODEL.USE_AFFINE:
+            dilations = (1, 1, 1)
         y = self.conv(x, prefix, cin, cout, kernels, strides, pads, dilations, no_bias=1, round_out=False)
-        return self.affine(y, prefix + '_bn', cout)
+        return self.norm(y, prefix + '_bn', cout)
 
     def relu(self, x):
         return self.q(torch.relu(x)) if self.run else None
@@ -185,8 +210,9 @@ class Graph(object):
             self.blobs[prefix + '_y'] = y
         kind = 'zero_w' if nl.USE_ZERO_INIT_CONV else 'nl'
         out = self.conv(y, prefix + '_out', dim_inner, dim_out, (1, 1, 1), no_bias=nb, kind=kind,
-                        round_out=not nl.USE_AFFINE)
-        assert not nl.USE_BN, 'oracle covers NONLOCAL.USE_BN False (all shipped configs)'
+                        round_out=not (nl.USE_AFFINE or nl.USE_BN))
+        if nl.USE_BN:                                             # nonlocal_helper.py:146-155
+            out = self.spatial_bn(out, prefix + '_bn', dim_out, nl.BN_EPSILON, nl.BN_MOMENTUM)
         if nl.USE_AFFINE:
             out = self.affine(out, prefix + '_bn', dim_out)
         return out
@@ -365,11 +391,11 @@ class Graph(object):
             crop = data.shape[-1]
             batch_size = data.shape[0]
         tc, ts, pool_stride = obtain_arc(cfg.MODEL.VIDEO_ARC_CHOICE, cfg.TRAIN.VIDEO_LENGTH)
-        assert cfg.MODEL.USE_AFFINE, 'oracle covers the Affine (frozen-BN) variant'
+        self.test_mode = test_mode
 
         x = self.conv(data, 'conv1', 3, 64, (1 + tc[0][0] * 2, 7, 7), (ts[0][0], 2, 2), (tc[0][0], 3, 3),
                       round_out=False)
-        x = self.affine(x, 'res_conv1_bn', 64)
+        x = self.norm(x, 'res_conv1_bn', 64)
         if self.run:
             x = self.q(torch.relu(x))
             self.blobs['res_conv1_bn'] = x
@@ -457,8 +483,10 @@ def make_params(cfg, seed=2, split='train', lfb_infer_only=False, dtype=torch.fl
             t = torch.rand(shape, generator=gen) + 0.5
             if name.endswith('branch2c_bn_s') or name.startswith('nonlocal'):
                 t = t * 0.25      # keep the residual stream O(1) through 16 blocks
-        elif kind == 'affine_b':
+        elif kind in ('affine_b', 'bn_rm'):
             t = torch.randn(shape, generator=gen) * 0.1
+        elif kind == 'bn_riv':
+            t = torch.rand(shape, generator=gen) + 0.5
         elif kind in ('nl', 'nl_default'):
             t = torch.randn(shape, generator=gen) * nl_std
         elif kind == 'zero_w':

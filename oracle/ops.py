@@ -23,6 +23,29 @@ def affine_nd_grad(dy, s):
     return dy * s.view(shape)
 
 
+def spatial_bn(x, s, b, running_mean, running_var, eps=1e-5, momentum=0.9, is_test=False):
+    """Caffe2 SpatialBN, order NCHW, any number of spatial dims (emitted by model_builder_video.py:186-190,
+    resnet_video.py:185-188, nonlocal_helper.py:146-150).  Returns (y, new_running_mean, new_running_var, saved_mean,
+    saved_inv_std).  Training mode normalises with the batch mean and the BIASED batch variance; the running statistics
+    follow `running = running * momentum + batch * (1 - momentum)` with the UNBIASED batch variance; `saved_inv_std` =
+    1 / sqrt(biased var + eps) is the '_bn_siv' blob lib/utils/bn_helper.py:170-176 inverts.  Test mode normalises
+    with the running statistics ('_bn_riv' is a variance, bn_helper.py:216-219; lib/utils/checkpoints.py:108-110 folds
+    it as scale / sqrt(riv + eps))."""
+    shape = [1, -1] + [1] * (x.dim() - 2)
+    if is_test:
+        f = s / torch.sqrt(running_var + eps)
+        return x * f.view(shape) + (b - running_mean * f).view(shape), running_mean, running_var, None, None
+    dims = [0] + list(range(2, x.dim()))
+    m = x.numel() // x.shape[1]
+    mean = x.mean(dim=dims)
+    var = ((x - mean.view(shape)) ** 2).mean(dim=dims)
+    inv_std = 1.0 / torch.sqrt(var + eps)
+    y = (x - mean.view(shape)) * (inv_std * s).view(shape) + b.view(shape)
+    new_rm = running_mean * momentum + mean.detach() * (1.0 - momentum)
+    new_rv = running_var * momentum + var.detach() * (float(m) / max(m - 1, 1)) * (1.0 - momentum)
+    return y, new_rm, new_rv, mean.detach(), inv_std.detach()
+
+
 def conv_nd(x, w, b=None, strides=(1, 1, 1), pads=(0, 0, 0), dilations=(1, 1, 1)):
     """Caffe2 Conv (NCTHW cross-correlation, symmetric pads) as emitted at
     lib/models/resnet_video.py:169-179 and model_builder_video.py:211-217."""

@@ -32,12 +32,13 @@ _DEFAULTS = {
     'MODEL': {'NUM_CLASSES': -1, 'VIDEO_ARC_CHOICE': 2, 'DEPTH': 50,         # :146-152
               'FC_INIT_STD': 0.01, 'USE_AFFINE': False, 'MULTI_LABEL': True,
               'DILATIONS_AFTER_CONV5': True, 'FREEZE_BACKBONE': False,
-              'BN_EPSILON': 1.0000001e-5},
+              'BN_EPSILON': 1.0000001e-5, 'BN_MOMENTUM': 0.9},                # :159-160
     'RESNETS': {'NUM_GROUPS': 1, 'WIDTH_PER_GROUP': 64},
     'NONLOCAL': {'CONV_INIT_STD': 0.01, 'NO_BIAS': 0, 'USE_MAXPOOL': True,   # :243-262
                  'USE_SOFTMAX': True, 'USE_ZERO_INIT_CONV': False, 'USE_BN': True,
                  'USE_SCALE': True, 'USE_AFFINE': False, 'LAYER_MOD': 2,
-                 'CONV3_NONLOCAL': True, 'CONV4_NONLOCAL': True},
+                 'CONV3_NONLOCAL': True, 'CONV4_NONLOCAL': True,
+                 'BN_MOMENTUM': 0.9, 'BN_EPSILON': 1.0000001e-5},
     'AVA': {'LFB_MAX_NUM_FEAT_PER_STEP': 5},                                 # :311
     'ROI': {'SCALE_FACTOR': 16, 'XFORM_RESOLUTION': 7},                      # :339-340
     'LFB': {'ENABLED': False, 'LFB_DIM': 2048, 'WINDOW_SIZE': 100,           # :345-352

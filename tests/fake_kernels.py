@@ -157,6 +157,38 @@ def affine_bwd(dy, s, dx):
     dx.copy_(dy * s)
 
 
+def spatial_bn_fwd(x, s, b, rm, rv, sm, siv, y, eps, momentum):
+    c = x.shape[-1]
+    x2 = x.reshape(-1, c).double()
+    m = x2.shape[0]
+    mean, var = x2.mean(0), x2.var(0, unbiased=False)
+    inv = 1.0 / torch.sqrt(var + eps)
+    sm.copy_(mean.to(sm.dtype))
+    siv.copy_(inv.to(siv.dtype))
+    if rm is not None:
+        rm.copy_((rm.double() * momentum + mean * (1.0 - momentum)).to(rm.dtype))
+        rv.copy_((rv.double() * momentum + var * (m / max(m - 1.0, 1.0)) * (1.0 - momentum)).to(rv.dtype))
+    y.copy_((((x2 - mean) * inv) * s.double() + b.double()).to(y.dtype).view(y.shape))
+
+
+def spatial_bn_infer(x, s, b, rm, rv, y, eps):
+    f = s / torch.sqrt(rv + eps)
+    y.copy_(x * f + (b - rm * f))
+
+
+def spatial_bn_bwd(dy, x, s, sm, siv, dx, ds, db):
+    c = x.shape[-1]
+    x2, d2 = x.reshape(-1, c).double(), dy.reshape(-1, c).double()
+    m = x2.shape[0]
+    xh = (x2 - sm.double()) * siv.double()
+    s1, s2 = d2.sum(0), (d2 * xh).sum(0)
+    if ds is not None:
+        ds.add_(s2.to(ds.dtype))
+    if db is not None:
+        db.add_(s1.to(db.dtype))
+    dx.copy_(((s.double() * siv.double() / m) * (m * d2 - s1 - xh * s2)).to(dx.dtype).view(dx.shape))
+
+
 def _pool_args(g):
     return (g.kT, g.kH, g.kW), (g.sT, g.sH, g.sW), (g.pT, g.pH, g.pW)
 

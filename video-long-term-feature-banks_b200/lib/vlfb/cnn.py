@@ -27,7 +27,8 @@ class CNNModelHelper(object):
         self.weights = []
         self.biases = []
         self.param_to_grad = {}
-        self.frozen_params = set()                      # AffineNd scale/bias: no gradient op
+        self.frozen_params = set()                      # AffineNd scale/bias, SpatialBN running statistics: no gradient op
+        self.computed_params = []                       # SpatialBN '_rm' / '_riv' (Caffe2: computed params)
         self._owner = None                              # CompiledNet once created
 
     # ---- parameters ------------------------------------------------------------
@@ -35,7 +36,7 @@ class CNNModelHelper(object):
         return list(self.params)
 
     def GetComputedParams(self, namescope=None):
-        return []                       # SpatialBN running statistics: the Affine variant has none
+        return list(self.computed_params)       # SpatialBN running statistics ('_rm', '_riv'); none in the Affine variant
 
     def GetAllParams(self, namescope=None):
         return self.GetParams(namescope) + self.GetComputedParams(namescope)
@@ -70,10 +71,27 @@ class CNNModelHelper(object):
         b = self._make_param(blob_out + '_b', [dim_out], bias_init or ('ConstantFill', {'value': 0.}), False)
         return self.net.FC([blob_in, w, b], blob_out)
 
-    def SpatialBN(self, blob_in, blob_out, dim_in, **kwargs):
-        raise NotImplementedError(
-            'SpatialBN (trainable BN) is a "next" row (SURVEY.md section 8f rank 4); every shipped config '
-            'uses the Affine (frozen-BN) variant: set MODEL.USE_AFFINE / NONLOCAL.USE_AFFINE True')
+    def SpatialBN(self, blob_in, blob_out, dim_in, epsilon=1e-5, momentum=0.9, is_test=False, **kwargs):
+        """Trainable batch normalisation as the reference emits it (model_builder_video.py:186-190,
+        resnet_video.py:185-188, nonlocal_helper.py:146-150): parameters '{out}_s' (1) / '{out}_b' (0) are trained,
+        '{out}_rm' (0) / '{out}_riv' (1; a running VARIANCE, lib/utils/bn_helper.py:216-219) are computed parameters.
+        Training nets also emit '{out}_sm' / '{out}_siv' (batch mean / inverse std), which precise-BN reads
+        (bn_helper.py:170-173).  Statistics are per process (= per GPU), as in the reference."""
+        scale = self._make_param(blob_out + '_s', [dim_in], ('ConstantFill', {'value': 1.}), True)
+        bias = self._make_param(blob_out + '_b', [dim_in], ('ConstantFill', {'value': 0.}), False)
+        stats = []
+        for sfx, val in (('_rm', 0.), ('_riv', 1.)):
+            name = blob_out + sfx
+            self.param_init_net.ConstantFill([], name, shape=[dim_in], value=val)
+            if name not in self.computed_params:
+                self.computed_params.append(name)
+                self.net.Proto().external_input.append(name)
+            self.frozen_params.add(name)
+            stats.append(name)
+        outs = [blob_out] if is_test else [blob_out, stats[0], stats[1], blob_out + '_sm', blob_out + '_siv']
+        res = self.net.SpatialBN([blob_in, scale, bias] + stats, outs, epsilon=float(epsilon), momentum=float(momentum),
+                                 is_test=bool(is_test), order=self.order)
+        return res[0] if isinstance(res, (list, tuple)) else res
 
     def FboNLStack(self, blob_a, blob_b, prefix, dim_a, dim_b, latent_dim, num_feat2, num_layers, init1, init2,
                    scale=1.0, pre_act_ln=True, dropout_ratio=0.0):

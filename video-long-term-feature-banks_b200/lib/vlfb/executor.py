@@ -279,6 +279,7 @@ class ConvStep(Step):
         self.relu = relu
         self.out = out_name or op.outputs[0]
         self.params = [self.w] + ([self.b] if self.b else [])
+        self.round_out = True             # False: the consumer is not a GEMM (SpatialBN) and wants the fp32 sums
 
     def _geom(self, ctx, xp):
         a = self.op.args
@@ -311,9 +312,10 @@ class ConvStep(Step):
             # sign bits of the ReLU output: the backward mask the consumer's dgrad epilogue reads (1/32 of the bytes)
             bits = empty((y.numel() // 32,), torch.int32)
             ctx.relu_bits[self.out_keys[0]] = bits
-        K.conv_fwd(xp, w, phys(y), g, scale=scale, bias=bias, residual=res, relu=self.relu, tf32_out=True, relu_bits=bits)
+        K.conv_fwd(xp, w, phys(y), g, scale=scale, bias=bias, residual=res, relu=self.relu, tf32_out=self.round_out,
+                   relu_bits=bits)
         ctx.saved[id(self)] = (xp, g)
-        ctx.put(self.out, y, rounded=True)
+        ctx.put(self.out, y, rounded=self.round_out)
 
     def bwd(self, ctx):
         # the gradient is a GEMM operand of dgrad/wgrad: mask (ReLU) and round it to TF32 in one pass
@@ -406,6 +408,54 @@ class AffineStep(Step):
         dx = empty_like_strided(gy)
         K.affine_bwd(phys(gy), ctx.ws.params.phys(self.op.inputs[1]), phys(dx))
         ctx.add_grad(self.in_keys[0], dx, owned=True)
+
+
+class SpatialBNStep(Step):
+    """Trainable batch normalisation (Caffe2 SpatialBN as emitted by model_builder_video.py:186-190): batch statistics in
+    a training net (outputs y, '_sm', '_siv'; running '_rm' / '_riv' updated in place in the ParamStore), running
+    statistics in a test net.  Two streaming passes forward, two backward (csrc/bn.cu)."""
+
+    def __init__(self, op, in_keys, out_keys):
+        Step.__init__(self, op, in_keys, out_keys)
+        self.x, self.s, self.b, self.rm, self.riv = op.inputs
+        self.is_test = bool(op.args.get('is_test', False))
+        self.eps = float(op.args.get('epsilon', 1e-5))
+        self.momentum = float(op.args.get('momentum', 0.9))
+        self.params = [self.s, self.b]
+
+    def fwd(self, ctx):
+        x = ctx.get(self.x)
+        xp = phys(x)
+        y = empty_like_strided(x)
+        st = ctx.ws.params
+        if self.is_test:
+            K.spatial_bn_infer(xp, st.phys(self.s), st.phys(self.b), st.phys(self.rm), st.phys(self.riv), phys(y), self.eps)
+        else:
+            c = xp.shape[-1]
+            sm, siv = empty((c,)), empty((c,))
+            K.spatial_bn_fwd(xp, st.phys(self.s), st.phys(self.b), st.phys(self.rm), st.phys(self.riv), sm, siv, phys(y),
+                             self.eps, self.momentum)
+            ctx.put(self.op.outputs[3], sm)
+            ctx.put(self.op.outputs[4], siv)
+            ctx.saved[id(self)] = (xp, sm, siv)
+        ctx.put(self.op.outputs[0], y)
+
+    def bwd(self, ctx):
+        gy = ctx.pop_grad(self.out_keys[0])
+        if gy is None:
+            return
+        assert not self.is_test, 'a test-mode SpatialBN has no backward'
+        xp, sm, siv = ctx.saved.pop(id(self))
+        gp = phys(gy)
+        assert gp.shape == xp.shape, 'gradient layout differs from the SpatialBN input'
+        st = ctx.ws.params
+        need_dx = ctx.net.requires.get(self.in_keys[0], False)
+        dx = empty_like_strided(gy)
+        K.spatial_bn_bwd(gp, xp, st.phys(self.s), sm, siv, phys(dx),
+                         st.grad(self.s) if st.trainable(self.s) else None,
+                         st.grad(self.b) if st.trainable(self.b) else None)
+        if need_dx:
+            ctx.add_grad(self.in_keys[0], dx, owned=True)
 
 
 class ReluStep(Step):
@@ -974,6 +1024,7 @@ STEP_TYPES = {
     'LayerNorm': LayerNormStep, 'Dropout': DropoutStep, 'FC': FCStep, 'Concat': ConcatStep,
     'RoIAlign': RoIAlignStep, 'Sigmoid': SigmoidStep, 'SigmoidCrossEntropyLoss': SigmoidCELossStep,
     'SoftmaxWithLoss': SoftmaxCELossStep, 'DequeueBlobs': NoopStep, 'FboNLStack': FboStackStep,
+    'SpatialBN': SpatialBNStep,
 }
 OPTIMIZER_OPS = ('WeightedSum', 'MomentumSGDUpdate')
 
@@ -1023,7 +1074,8 @@ class CompiledNet(object):
                         self.external_inputs.append(n)
                 continue
             for n in op.inputs:
-                if n not in produced and n not in self.external_inputs and n not in model.params:
+                if n not in produced and n not in self.external_inputs and n not in model.params and \
+                        n not in model.computed_params:
                     self.external_inputs.append(n)
             produced.update(op.outputs)
         self._graphs = collections.OrderedDict()     # input signature -> captured step (LRU)
@@ -1155,6 +1207,8 @@ class CompiledNet(object):
                     key = self.out_keys[j][0]
                 consumed.update(chain)
                 placed[chain[-1]] = ConvStep(op, self.in_keys[i], [key], affine, res_key, relu, key[0])
+                if len(chain) == 1 and self._sole_consumer(key, ops, 'SpatialBN') is not None:
+                    placed[i].round_out = False
             elif op.type == 'Scale':
                 key = self.out_keys[i][0]
                 j = self._sole_consumer(key, ops, 'Softmax', consumed)

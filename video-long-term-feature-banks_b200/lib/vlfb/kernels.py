@@ -398,6 +398,35 @@ def affine_bwd(dy, s, dx):
                                         dy.numel() // dy.shape[-1], dy.shape[-1], _stream()), 'affine_bwd')
 
 
+def _bn_workspace(C_):
+    nbytes = int(L.load().vlfb_spatial_bn_workspace_bytes(int(C_)))
+    return torch.empty((nbytes + 15) // 16 * 16, dtype=torch.uint8, device='cuda'), nbytes
+
+
+def spatial_bn_fwd(x, s, b, rm, rv, sm, siv, y, eps, momentum):
+    """Training-mode SpatialBN of a channels-last [..., C] tensor: batch statistics -> sm / siv (saved mean, inverse std),
+    running statistics rm / rv updated in place (None: left alone), y = normalised * s + b."""
+    ws, nb = _bn_workspace(x.shape[-1])
+    _check(L.load().vlfb_spatial_bn_fwd(_ptr(_f32c(x)), _ptr(s), _ptr(b), _ptr(rm), _ptr(rv), _ptr(sm), _ptr(siv),
+                                        _ptr(_f32c(y)), x.numel() // x.shape[-1], x.shape[-1], float(eps), float(momentum),
+                                        _ptr(ws), nb, _stream()), 'spatial_bn_fwd')
+
+
+def spatial_bn_infer(x, s, b, rm, rv, y, eps):
+    ws, nb = _bn_workspace(x.shape[-1])
+    _check(L.load().vlfb_spatial_bn_infer(_ptr(_f32c(x)), _ptr(s), _ptr(b), _ptr(rm), _ptr(rv), _ptr(_f32c(y)),
+                                          x.numel() // x.shape[-1], x.shape[-1], float(eps), _ptr(ws), nb, _stream()),
+           'spatial_bn_infer')
+
+
+def spatial_bn_bwd(dy, x, s, sm, siv, dx, ds, db):
+    """dx of training-mode SpatialBN; ds += sum dy * xhat, db += sum dy (either may be None)."""
+    ws, nb = _bn_workspace(x.shape[-1])
+    _check(L.load().vlfb_spatial_bn_bwd(_ptr(_f32c(dy)), _ptr(_f32c(x)), _ptr(s), _ptr(sm), _ptr(siv), _ptr(_f32c(dx)),
+                                        _ptr(ds), _ptr(db), x.numel() // x.shape[-1], x.shape[-1], _ptr(ws), nb, _stream()),
+           'spatial_bn_bwd')
+
+
 def maxpool_fwd(x, y, argmax, g):
     _check(L.load().vlfb_maxpool3d_fwd(_ptr(_f32c(x)), _ptr(_f32c(y)), _ptr(argmax), C.byref(g), _stream()),
             'maxpool_fwd')

@@ -68,6 +68,10 @@ SIGNATURES = {
     'vlfb_gemm_workspace_bytes': [],
     'vlfb_affine_nd_fwd': [_P, _P, _P, _P, _L, _I, _P],
     'vlfb_affine_nd_bwd': [_P, _P, _P, _L, _I, _P],
+    'vlfb_spatial_bn_workspace_bytes': [_I],
+    'vlfb_spatial_bn_fwd': [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _F, _P, C.c_size_t, _P],
+    'vlfb_spatial_bn_infer': [_P, _P, _P, _P, _P, _P, _L, _I, _F, _P, C.c_size_t, _P],
+    'vlfb_spatial_bn_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, C.c_size_t, _P],
     'vlfb_maxpool3d_fwd': [_P, _P, _P, _GP, _P],
     'vlfb_maxpool3d_bwd': [_P, _P, _P, _GP, _P],
     'vlfb_avgpool3d_fwd': [_P, _P, _GP, _P],
@@ -114,7 +118,7 @@ SIGNATURES = {
 }
 RESTYPES = {'vlfb_last_error': C.c_char_p, 'vlfb_fbo_bank_scan_workspace': C.c_size_t,
             'vlfb_fbo_nl_scratch_floats': C.c_size_t,
-            'vlfb_gemm_workspace_bytes': C.c_size_t}
+            'vlfb_gemm_workspace_bytes': C.c_size_t, 'vlfb_spatial_bn_workspace_bytes': C.c_size_t}
 
 _lib = None
 

@@ -284,7 +284,7 @@ def RunNetOnce(net):
     """Execute a param_init_net: allocate + fill parameters (tools/train_net.py:74)."""
     from core.config import config as cfg
     model = getattr(net, '_model', None)
-    params = set(model.params) if model is not None else set()
+    params = (set(model.params) | set(getattr(model, 'computed_params', ()))) if model is not None else set()
     frozen = model.frozen_params if model is not None else set()
     specs, fills = [], []
     for op in net.ops:
