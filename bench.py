@@ -380,7 +380,7 @@ def run_b200(args):
             import bench_fbo
             fbo = []
             for mode, R_, L_ in (('train', rois, BANK_ROWS), ('infer_fold', rois, BANK_ROWS), ('infer_fold', 64, 1200),
-                                 ('infer_fold', 256, 3600)):
+                                 ('infer_fold', 256, 3600), ('infer_fold_bf16', 64, 1200), ('infer_fold_bf16', 256, 3600)):
                 r = bench_fbo.run_case(mode, R_, L_, 2, 10, 3, peaks)
                 fbo.append(dict((k, r[k]) for k in ('mode', 'R', 'L', 'layers', 'ms', 'launches', 'gbs', 'hbm_frac',
                                                     'tflops_as_written', 'scan')))

@@ -6,6 +6,7 @@ reduction 2048->512, bank projection 'lfb_1x1', NUM_LAYERS single-query non-loca
 builder API / workspace / C ABI as the full model, in three modes:
 
   infer_fold   test-mode graph, every layer = ONE pass over the raw bank (executor.FboFoldStep + fbo_bank_scan): HBM-bound
+  infer_fold_bf16  the same with the bank stored as bf16 (B200.LFB_DTYPE; fp32 scores / softmax / sums): half the bytes
   infer        test-mode graph as written (B200.FBO_FOLD False): bank projections on the tensor-core GEMM
   train        train-mode graph (dropout on) forward + backward + SGD, as written
 
@@ -32,9 +33,11 @@ YAML = {2: 'ava_r50_lfb_nl.yaml', 3: 'ava_r50_lfb_nl_3l.yaml'}
 STATE = {'L': 300}
 
 
-def fbo_bytes(R, L, layers, s=4):
-    """compulsory bytes of the FBO-NL block (bank + box_pooled + out + weights/biases)."""
-    return s * (R * L * 2048 + R * 2048 + R * 512) + s * (2 * 2048 * 512 + layers * 4 * 512 ** 2 + (2 + 4 * layers) * 512)
+def fbo_bytes(R, L, layers, s=4, bank_s=None):
+    """compulsory bytes of the FBO-NL block (bank + box_pooled + out + weights/biases); `bank_s` =
+    bytes per bank element when the bank's storage type differs from the rest (bf16 bank, fp32 weights)."""
+    bank_s = s if bank_s is None else bank_s
+    return bank_s * R * L * 2048 + s * (R * 2048 + R * 512) + s * (2 * 2048 * 512 + layers * 4 * 512 ** 2 + (2 + 4 * layers) * 512)
 
 
 def fbo_flops(R, L, layers):
@@ -74,7 +77,8 @@ def build_case(mode, R, L, layers):
     train = mode == 'train'
     H.setup_cfg(YAML[layers], ['NUM_GPUS', 1, 'TRAIN.BATCH_SIZE', 2, 'TEST.BATCH_SIZE', 2])
     cfg.MODEL.MODEL_NAME = 'fbo_nl_only'
-    cfg.B200.FBO_FOLD = mode == 'infer_fold'
+    cfg.B200.FBO_FOLD = mode.startswith('infer_fold')
+    cfg.B200.LFB_DTYPE = 'bf16' if mode.endswith('_bf16') else 'f32'
     cfg.RNG_SEED = 2
     MB.model_creator_map['fbo_nl_only'] = _creator()
     STATE['L'] = L
@@ -154,7 +158,8 @@ def run_case(mode, R, L, layers, steps, warmup, peaks):
         scan = {'launches': len(srecs), 'ms': round(t, 4), 'alg_bytes_per_launch': srecs[0][3],
                 'gbs': round(sum(r[3] for r in srecs) / 1e6 / t, 1), 'frac': round(sum(r[3] for r in srecs) / 1e6 / t / peaks['hbm_gbs'], 3)}
     gemm_ms = sum(r[1] for r in recs if not r[0].startswith('fbo_bank_scan'))
-    nbytes = fbo_bytes(R, L, layers)
+    bf16 = mode.endswith('_bf16')
+    nbytes = fbo_bytes(R, L, layers, bank_s=2 if bf16 else 4)
     flops = fbo_flops(R, L, layers) * (3.0 if train else 1.0)
     workspace.ResetWorkspace()
     torch.cuda.empty_cache()
@@ -163,7 +168,8 @@ def run_case(mode, R, L, layers, steps, warmup, peaks):
             'launches': launches, 'alg_bytes': nbytes, 'gbs': round(nbytes / 1e6 / ms, 1),
             'hbm_frac': round(nbytes / 1e6 / ms / peaks['hbm_gbs'], 4), 'as_written_gflop': round(flops / 1e9, 2),
             'tflops_as_written': round(flops / 1e9 / ms, 1), 'scan': scan, 'gemm_ms_eager': round(gemm_ms, 4),
-            'rois_per_s': round(R / ms * 1e3, 0), 'dtype': 'tf32' if mode != 'infer_fold' else 'f32 scan + tf32 R-row matmuls',
+            'rois_per_s': round(R / ms * 1e3, 0),
+            'dtype': 'tf32' if not mode.startswith('infer_fold') else ('bf16 bank, ' if bf16 else '') + 'f32 scan + tf32 R-row matmuls',
             'l2': 'flushed before every iteration', 'cuda_graph': True}
 
 
@@ -172,7 +178,7 @@ def main():
     ap.add_argument('--R', default='4,16,64,256')
     ap.add_argument('--L', default='60,300,1200,3600')
     ap.add_argument('--layers', default='2,3')
-    ap.add_argument('--modes', default='infer_fold,infer,train')
+    ap.add_argument('--modes', default='infer_fold,infer_fold_bf16,infer,train')
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--max-rows', type=int, default=256 * 3600, help='skip cases with R*L above this')

@@ -35,6 +35,9 @@ extern "C" {
 #define VLFB_E_CUDA (-3)
 #define VLFB_E_WORKSPACE (-4)   /* caller-provided workspace too small (see the *_workspace query) */
 
+/* Storage types of operands that are not fp32 (fp32 is the parity mode of every other entry point). */
+typedef enum { VLFB_DT_F32 = 0, VLFB_DT_BF16 = 1 } vlfb_dtype_t;
+
 /* ---- library ------------------------------------------------------------------------- */
 int vlfb_version(void);                 /* 100 * major + minor */
 const char* vlfb_last_error(void);      /* thread-local message of the last failing call */
@@ -285,6 +288,15 @@ int vlfb_fbo_bank_scan_splits(int R, int L, int D);
 size_t vlfb_fbo_bank_scan_workspace(int R, int L, int D);
 int vlfb_fbo_bank_scan(const float* bank, const float* q, float scale, float* out, float* prob, int R, int L, int D,
                        int tf32_out, void* workspace, size_t workspace_bytes, void* stream);
+/* The same scan over a bank stored as `bank_dtype` (vlfb_dtype_t): VLFB_DT_F32 (D = 1024 / 2048 / 4096) or
+ * VLFB_DT_BF16 (D = 2048 / 4096; half the HBM bytes per row -- BASELINE configs[4] "fp32 and bf16 banks").  Queries,
+ * scores, softmax and the weighted sum stay fp32.  The splits / workspace queries depend on the storage type (a tile
+ * is 64 KB of rows either way).  vlfb_cast_f32_to_bf16 (round to nearest even, n % 8 == 0) produces such a bank. */
+int vlfb_fbo_bank_scan_splits_dt(int R, int L, int D, int bank_dtype);
+size_t vlfb_fbo_bank_scan_workspace_dt(int R, int L, int D, int bank_dtype);
+int vlfb_fbo_bank_scan_dt(const void* bank, int bank_dtype, const float* q, float scale, float* out, float* prob, int R,
+                          int L, int D, int tf32_out, void* workspace, size_t workspace_bytes, void* stream);
+int vlfb_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
 
 /* ---- training-mode FBO-NL stack, one launch per direction (csrc/fbo.cu section 3) ---------------------
  * Replaces, for ALL layers of lfb_helper.NLLayers (:266-292) with one query per RoI and FBO_NL.PRE_ACT, the operators of

@@ -5,6 +5,7 @@ cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
 timeout 400 python -m pytest tests/test_spatial_bn.py -m gpu -q > $O/r2j_bn_tests.log 2>&1; echo "bn tests rc=$?"; tail -n 15 $O/r2j_bn_tests.log
+timeout 300 python -m pytest tests/test_gpu_kernels.py -k "bank_scan" -q > $O/r2j_scan_tests.log 2>&1; echo "scan tests rc=$?"; tail -n 6 $O/r2j_scan_tests.log   # bf16_bank
 echo "tests: skipped (green in the first attempt of this call: 150 passed, 5 skipped)"
 timeout 600 python bench.py --steps 10 --warmup 3 --dump-gemms $O/r2j_gemm_table.txt > $O/r2j_bench.log 2> $O/r2j_bench.err; echo "bench rc=$?"
 timeout 400 python bench.py --steps 10 --warmup 3 --clips-per-gpu 8 --no-cpu-baseline --no-fbo --dump-gemms $O/r2j_gemm_table_c8.txt > $O/r2j_bench_c8.log 2> $O/r2j_bench_c8.err; echo "bench c8 rc=$?"

@@ -396,6 +396,7 @@ def sgd_nesterov(p, g, m, lr, momentum, wd, nesterov=True, p_tf32=None):
 
 
 def fbo_bank_scan(bank, q, out, scale, prob=None, tf32_out=False):
+    bank = bank.to(q.dtype)                      # a bf16 bank is a storage type: the arithmetic is the query's
     assert bank.is_contiguous() and q.is_contiguous() and out.is_contiguous()
     assert bank.shape[2] in (1024, 2048, 4096), 'csrc/fbo.cu supports D in {1024, 2048, 4096}'
     p = torch.softmax(torch.einsum('rld,rd->rl', bank, q) * scale, dim=1)
@@ -457,6 +458,10 @@ def fbo_nl_bwd(cfgd, layers, a0, bp, da_last, da0, dbp):
         for k in wk:
             if ld.get('g' + k) is not None and l2.get(k) is not None and l2[k].grad is not None:
                 ld['g' + k].add_(l2[k].grad)
+
+
+def cast_bf16(x, y):
+    y.copy_(x.to(torch.bfloat16))
 
 
 def lfb_gather(bank, idx, out, tf32_out=False):

@@ -259,6 +259,48 @@ def test_inference_fbo_fold_matches_oracle_and_unfolded_graph(fake, yaml_name, l
         assert workspace.HasBlob('gpu_0/lfb_1x1') == (not fold)
 
 
+def test_inference_fbo_fold_on_a_bf16_bank(fake):
+    """B200.LFB_DTYPE 'bf16': feeding the bank also stores a bf16 copy, the folded FBO scans that copy.  The result
+    equals the oracle evaluated on the bf16-rounded bank exactly (storage type only: fp32 arithmetic) and the fp32-bank
+    oracle within the bf16 tolerance of BASELINE configs[3]/[4] (1e-2)."""
+    from oracle import model as OM
+    from vlfb import workspace
+    from vlfb import executor as X
+    from core.config import config as cfg
+    yaml_name = 'ava_r50_lfb_nl.yaml'
+    ocfg = H.oracle_cfg(yaml_name, TINY)
+    params = OM.make_params(ocfg, seed=2, split='val')
+    inputs = OM.make_inputs(ocfg, n_clips=2, rois_per_clip=3, crop=64, frames=8)
+    p64 = dict((k, v.double()) for k, v in params.items())
+    i64 = dict((k, (v.double() if v.dtype == torch.float32 else v)) for k, v in inputs.items())
+    exact, _, _ = OM.forward(ocfg, p64, i64, 'val')
+    i16 = dict(i64, lfb=inputs['lfb'].to(torch.bfloat16).double())
+    rounded, _, _ = OM.forward(ocfg, p64, i16, 'val')
+    H.setup_cfg(yaml_name, TINY)
+    cfg.B200.LFB_DTYPE = 'bf16'
+    workspace.ResetWorkspace()
+    model, sfx = H.build('val', False)
+    H.feed_params(params)
+    H.feed_inputs(inputs, sfx)
+    assert workspace.current().blobs['lfb' + sfx + '@bf16'].dtype == torch.bfloat16
+    seen = []
+    scan = fake.fbo_bank_scan
+    fake.fbo_bank_scan = lambda bank, *a, **k: (seen.append(bank.dtype), scan(bank, *a, **k))[1]
+    try:
+        workspace.RunNet(model.net.Proto().name)
+    finally:
+        fake.fbo_bank_scan = scan
+    assert seen == [torch.bfloat16, torch.bfloat16]
+    for b in ['lfb_nl0_affinity_prob', 'lfb_nl1_sum', 'pred', 'prob']:
+        got = workspace.FetchBlob('gpu_0/' + b).reshape(-1)
+        assert H.rel(got, rounded[b].detach().numpy().reshape(-1)) < 1e-9, b
+        assert H.rel(got, exact[b].detach().numpy().reshape(-1)) < 1e-2, b
+    # switching the mode off drops the copy at the next feed
+    cfg.B200.LFB_DTYPE = 'f32'
+    H.feed_inputs(inputs, sfx)
+    assert not workspace.HasBlob('gpu_0/lfb' + sfx + '@bf16')
+
+
 def test_fbo_fold_is_skipped_for_bank_widths_the_scan_kernel_lacks(fake):
     """LFB.LFB_DIM = 512: vlfb_fbo_bank_scan only has 1024 / 2048 / 4096-float rows, so the test-mode graph must keep
     the as-written Conv / BatchMatMul lowering (and still match the oracle) instead of failing at run time."""

@@ -569,6 +569,34 @@ def test_fbo_bank_scan(K, R, Lb, D):
     assert torch.equal(out2.cpu(), tf32_round(out.cpu()))
 
 
+@pytest.mark.parametrize('R,Lb,D', [(1, 1, 2048), (3, 7, 2048), (4, 300, 2048), (5, 61, 4096), (37, 120, 2048),
+                                     (2, 3600, 2048)])
+def test_fbo_bank_scan_bf16_bank(K, R, Lb, D):
+    """The same pass over a bank STORED as bf16 (vlfb_fbo_bank_scan_dt, VLFB_DT_BF16): the cast kernel rounds to nearest
+    even bit-exactly like torch, and the scan of the bf16 bank equals the fp64 evaluation on the rounded values (the
+    arithmetic stays fp32), ragged tails and zero-padded rows included."""
+    g = torch.Generator().manual_seed(R * 1000 + Lb + 1)
+    bank = torch.randn((R, Lb, D), generator=g) * 0.5
+    bank[:, Lb - Lb // 4:] = 0.0
+    q = torch.randn((R, D), generator=g) * 0.2
+    b16 = torch.empty((R, Lb, D), dtype=torch.bfloat16, device='cuda')
+    K.cast_bf16(bank.cuda().view(-1), b16.view(-1))
+    assert torch.equal(b16.cpu(), bank.to(torch.bfloat16))
+    sc = 512 ** -0.5
+    bd = b16.cpu().double()
+    p = torch.softmax(torch.einsum('rld,rd->rl', bd, q.double()) * sc, dim=1)
+    ref = torch.einsum('rl,rld->rd', p, bd)
+    out = torch.full((R, D), float('nan'), device='cuda')
+    prob = torch.full((R, Lb), float('nan'), device='cuda')
+    K.fbo_bank_scan(b16, q.cuda(), out, sc, prob=prob)
+    torch.cuda.synchronize()
+    assert rel_err(prob, p) < 1e-5 and rel_err(out, ref) < 1e-5
+    lib = K.L.load()
+    s = lib.vlfb_fbo_bank_scan_splits_dt(R, Lb, D, 1)
+    assert s >= 1 and lib.vlfb_fbo_bank_scan_workspace_dt(R, Lb, D, 1) == (R * s * D + R * s * 2) * 4
+    assert lib.vlfb_fbo_bank_scan_splits_dt(R, Lb, 1024, 1) == 0          # bf16 rows: 2048 / 4096 features only
+
+
 def test_fbo_bank_scan_peaked_softmax_and_split_table(K):
     """Scores far apart (one row dominates): the online softmax must not overflow / lose the winner across CTA splits;
     and the split chooser keeps every CTA non-empty."""

@@ -28,56 +28,80 @@ __device__ __forceinline__ float warp_sum_f(float v) {
   return v;
 }
 
-__device__ __forceinline__ float4 ldg_stream(const float4* p) {   // read-once data: do not keep it in L1
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {   // read-once data: do not keep it in L1
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                : "l"(p));
   return v;
 }
+// 16 bytes of bank row -> EPL floats: 4 fp32, or 8 bf16 (element 2i in the low half of word i)
+template <int EPL>
+__device__ __forceinline__ void unpack16(const uint4& u, float (&f)[EPL]) {
+  if (EPL == 4) {
+    f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+  } else {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[(2 * i) % EPL] = __uint_as_float(w[i] << 16);
+      f[(2 * i + 1) % EPL] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+}
 
-// One CTA = rows [row_begin, row_end) of one RoI.  V4 = float4 per thread per row (D = 1024 * V4), ROWS = rows per
-// tile: ROWS*V4 independent 16-byte loads per thread are in flight before the first use (ROWS*D*4 = 64 KB per
-// CTA, two CTAs per SM).  Per tile: partial dots -> warp shuffles -> one shared-memory exchange between the 8
-// warps (double buffered: one __syncthreads per tile) -> every thread redoes the tiny online-softmax update and
-// rescales / accumulates its 4*V4 columns from the registers that still hold the rows.
-template <int V4, int ROWS>
-__global__ void __launch_bounds__(SCAN_TPB, 2)
-fbo_bank_scan_k(const float* __restrict__ bank, const float* __restrict__ q, float scale, float* __restrict__ part_acc,
+// One CTA = rows [row_begin, row_end) of one RoI.  EPL = bank elements per 16-byte load (4: fp32 bank, 8: bf16 bank),
+// V = 16-byte loads per thread per row (D = 256 * V * EPL), ROWS = rows per tile: ROWS*V independent 16-byte loads per
+// thread are in flight before the first use (fp32: 64 KB per CTA, two CTAs per SM; bf16: 32 KB, more CTAs).  Per tile: partial dots -> warp
+// shuffles -> one shared-memory exchange between the 8 warps (double buffered: one __syncthreads per tile) -> every
+// thread redoes the tiny online-softmax update and rescales / accumulates its V*EPL columns from the registers that
+// still hold the rows.  Scores, softmax and the weighted sum are fp32 whatever the bank's storage type.
+template <int EPL, int V, int ROWS>
+__global__ void __launch_bounds__(SCAN_TPB, (EPL == 8 && V == 1) ? 3 : 2)
+fbo_bank_scan_k(const void* __restrict__ bank, const float* __restrict__ q, float scale, float* __restrict__ part_acc,
                 float* __restrict__ part_ml, float* __restrict__ scores, int L, int S, int rows_per_split) {
-  constexpr int D = 1024 * V4;
+  constexpr int D = SCAN_TPB * V * EPL;
   constexpr int NW = SCAN_TPB / 32;
   __shared__ float xch[2][NW][ROWS];
   const int r = blockIdx.x / S, sp = blockIdx.x % S;
   const int row_begin = sp * rows_per_split;
   const int row_end = min(L, row_begin + rows_per_split);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float4* brow = reinterpret_cast<const float4*>(bank + (int64_t)r * L * D);
-  const float4* q4 = reinterpret_cast<const float4*>(q + (int64_t)r * D);
-  float4 qv[V4], acc[V4];
+  const uint4* brow = reinterpret_cast<const uint4*>(bank) + (int64_t)r * L * (SCAN_TPB * V);
+  const float* qr = q + (int64_t)r * D;
+  float qv[V][EPL], acc[V][EPL];
 #pragma unroll
-  for (int v = 0; v < V4; ++v) {
-    qv[v] = q4[v * SCAN_TPB + tid];
-    acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int v = 0; v < V; ++v) {
+#pragma unroll
+    for (int e = 0; e < EPL; e += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(qr + (v * SCAN_TPB + tid) * EPL + e);
+      qv[v][e] = t.x; qv[v][e + 1] = t.y; qv[v][e + 2] = t.z; qv[v][e + 3] = t.w;
+    }
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[v][e] = 0.f;
   }
   float m = -FLT_MAX, l = 0.f;
   int buf = 0;
   for (int j0 = row_begin; j0 < row_end; j0 += ROWS, buf ^= 1) {
-    float4 x[ROWS][V4];
+    uint4 x[ROWS][V];
 #pragma unroll
     for (int i = 0; i < ROWS; ++i) {
       const bool ok = j0 + i < row_end;
 #pragma unroll
-      for (int v = 0; v < V4; ++v)
-        x[i][v] = ok ? ldg_stream(brow + (int64_t)(j0 + i) * (D / 4) + v * SCAN_TPB + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int v = 0; v < V; ++v)
+        x[i][v] = ok ? ldg_stream_u4(brow + (int64_t)(j0 + i) * (SCAN_TPB * V) + v * SCAN_TPB + tid) : make_uint4(0u, 0u, 0u, 0u);
     }
     float part[ROWS];
 #pragma unroll
     for (int i = 0; i < ROWS; ++i) {
       float s = 0.f;
 #pragma unroll
-      for (int v = 0; v < V4; ++v)
-        s += x[i][v].x * qv[v].x + x[i][v].y * qv[v].y + x[i][v].z * qv[v].z + x[i][v].w * qv[v].w;
+      for (int v = 0; v < V; ++v) {
+        float f[EPL];
+        unpack16<EPL>(x[i][v], f);
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) s += f[e] * qv[v][e];
+      }
       part[i] = warp_sum_f(s);
     }
     if (lane == 0) {
@@ -104,26 +128,50 @@ fbo_bank_scan_k(const float* __restrict__ bank, const float* __restrict__ q, flo
     const float corr = __expf(m - mx);      // m == -FLT_MAX on the first tile: exp(-huge) == 0 and acc, l are 0
     l *= corr;
 #pragma unroll
-    for (int v = 0; v < V4; ++v) {
-      acc[v].x *= corr; acc[v].y *= corr; acc[v].z *= corr; acc[v].w *= corr;
+    for (int v = 0; v < V; ++v) {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) acc[v][e] *= corr;
     }
 #pragma unroll
     for (int i = 0; i < ROWS; ++i) {
       const float p = (j0 + i < row_end) ? __expf(sc[i] - mx) : 0.f;
       l += p;
 #pragma unroll
-      for (int v = 0; v < V4; ++v) {
-        acc[v].x += p * x[i][v].x; acc[v].y += p * x[i][v].y; acc[v].z += p * x[i][v].z; acc[v].w += p * x[i][v].w;
+      for (int v = 0; v < V; ++v) {
+        float f[EPL];
+        unpack16<EPL>(x[i][v], f);
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) acc[v][e] += p * f[e];
       }
     }
     m = mx;
   }
-  float4* pa = reinterpret_cast<float4*>(part_acc + ((int64_t)r * S + sp) * D);
+  float* pa = part_acc + ((int64_t)r * S + sp) * D;
 #pragma unroll
-  for (int v = 0; v < V4; ++v) pa[v * SCAN_TPB + tid] = acc[v];
+  for (int v = 0; v < V; ++v) {
+#pragma unroll
+    for (int e = 0; e < EPL; e += 4)
+      *reinterpret_cast<float4*>(pa + (v * SCAN_TPB + tid) * EPL + e) =
+          make_float4(acc[v][e], acc[v][e + 1], acc[v][e + 2], acc[v][e + 3]);
+  }
   if (tid == 0) {
     part_ml[((int64_t)r * S + sp) * 2 + 0] = m;
     part_ml[((int64_t)r * S + sp) * 2 + 1] = l;
+  }
+}
+
+// y = bf16(x), round to nearest even (the storage type of a bf16 feature bank); 8 elements per thread and iteration
+__global__ void f32_to_bf16_k(const float4* __restrict__ x, uint4* __restrict__ y, int64_t n8) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = x[2 * i], b = x[2 * i + 1];
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t h[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t u = __float_as_uint(f[k]);
+      h[k] = (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;          // NaN payloads aside (banks are finite features)
+    }
+    y[i] = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
   }
 }
 
@@ -576,11 +624,18 @@ using namespace vlfb;
 
 extern "C" {
 
+/* Rows per tile of the scan kernel for a bank of `D`-element rows stored as `dt` (0 = unsupported). */
+static int scan_rows(int D, int dt) {
+  if (dt == VLFB_DT_F32) return D == 4096 ? 4 : (D == 1024 || D == 2048) ? 8 : 0;
+  if (dt == VLFB_DT_BF16) return D == 4096 ? 4 : D == 2048 ? 8 : 0;
+  return 0;
+}
+
 /* Split of the L bank rows of every RoI over `S` CTAs: minimise waves x (tiles per CTA + partial-result cost) with
  * 2 resident CTAs per SM (296 per wave on B200). */
-int vlfb_fbo_bank_scan_splits(int R, int L, int D) {
-  if (R <= 0 || L <= 0 || (D != 1024 && D != 2048 && D != 4096)) return 0;
-  const int rows = D == 4096 ? 4 : 8;
+int vlfb_fbo_bank_scan_splits_dt(int R, int L, int D, int bank_dtype) {
+  const int rows = scan_rows(D, bank_dtype);
+  if (R <= 0 || L <= 0 || rows == 0) return 0;
   const int max_s = (L + rows - 1) / rows;
   const int wave = 296;
   int best = 1;
@@ -595,38 +650,60 @@ int vlfb_fbo_bank_scan_splits(int R, int L, int D) {
   }
   return best;
 }
+int vlfb_fbo_bank_scan_splits(int R, int L, int D) { return vlfb_fbo_bank_scan_splits_dt(R, L, D, VLFB_DT_F32); }
 
-size_t vlfb_fbo_bank_scan_workspace(int R, int L, int D) {
-  const int S = vlfb_fbo_bank_scan_splits(R, L, D);
+size_t vlfb_fbo_bank_scan_workspace_dt(int R, int L, int D, int bank_dtype) {
+  const int S = vlfb_fbo_bank_scan_splits_dt(R, L, D, bank_dtype);
   if (S <= 0) return 0;
   return ((size_t)R * S * D + (size_t)R * S * 2) * sizeof(float);
 }
+size_t vlfb_fbo_bank_scan_workspace(int R, int L, int D) { return vlfb_fbo_bank_scan_workspace_dt(R, L, D, VLFB_DT_F32); }
 
-int vlfb_fbo_bank_scan(const float* bank, const float* q, float scale, float* out, float* prob, int R, int L, int D,
-                       int tf32_out, void* workspace, size_t workspace_bytes, void* stream) {
+int vlfb_fbo_bank_scan_dt(const void* bank, int bank_dtype, const float* q, float scale, float* out, float* prob, int R,
+                          int L, int D, int tf32_out, void* workspace, size_t workspace_bytes, void* stream) {
   VLFB_CHECK_ARG(bank && q && out && R >= 0 && L > 0);
-  VLFB_CHECK_ARG(D == 1024 || D == 2048 || D == 4096);
+  VLFB_CHECK_ARG(bank_dtype == VLFB_DT_F32 || bank_dtype == VLFB_DT_BF16);
+  VLFB_CHECK_ARG(scan_rows(D, bank_dtype) > 0);
+  VLFB_CHECK_ARG((reinterpret_cast<uintptr_t>(bank) & 15) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0);
   if (R == 0) return VLFB_OK;
-  const int S = vlfb_fbo_bank_scan_splits(R, L, D);
+  const int S = vlfb_fbo_bank_scan_splits_dt(R, L, D, bank_dtype);
   VLFB_CHECK_ARG(S > 0 && (int64_t)R * S < (1ll << 31));
-  if (workspace == nullptr || workspace_bytes < vlfb_fbo_bank_scan_workspace(R, L, D)) {
-    set_error("vlfb_fbo_bank_scan: workspace of %zu bytes needed, %zu given", vlfb_fbo_bank_scan_workspace(R, L, D),
-              workspace_bytes);
+  const size_t need = vlfb_fbo_bank_scan_workspace_dt(R, L, D, bank_dtype);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("vlfb_fbo_bank_scan: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
     return VLFB_E_WORKSPACE;
   }
   float* part_acc = static_cast<float*>(workspace);
   float* part_ml = part_acc + (size_t)R * S * D;
   const int per = (L + S - 1) / S;
   const dim3 grid((unsigned)(R * S));
-  if (D == 1024)
-    launch_k(fbo_bank_scan_k<1, 8>, grid, SCAN_TPB, 0, ST(stream), bank, q, scale, part_acc, part_ml, prob, L, S, per);
-  else if (D == 2048)
-    launch_k(fbo_bank_scan_k<2, 8>, grid, SCAN_TPB, 0, ST(stream), bank, q, scale, part_acc, part_ml, prob, L, S, per);
-  else
-    launch_k(fbo_bank_scan_k<4, 4>, grid, SCAN_TPB, 0, ST(stream), bank, q, scale, part_acc, part_ml, prob, L, S, per);
+#define VLFB_SCAN(EPL, V, ROWS) \
+  launch_k(fbo_bank_scan_k<EPL, V, ROWS>, grid, SCAN_TPB, 0, ST(stream), bank, q, scale, part_acc, part_ml, prob, L, S, per)
+  if (bank_dtype == VLFB_DT_F32) {
+    if (D == 1024) VLFB_SCAN(4, 1, 8);
+    else if (D == 2048) VLFB_SCAN(4, 2, 8);
+    else VLFB_SCAN(4, 4, 4);
+  } else {
+    if (D == 2048) VLFB_SCAN(8, 1, 8);       // 32 KB of rows per tile: fewer registers, more resident CTAs
+    else VLFB_SCAN(8, 2, 4);
+  }
+#undef VLFB_SCAN
   VLFB_CHECK_LAUNCH();
   launch_k(fbo_bank_combine_k, dim3((unsigned)(D / 256), (unsigned)R), 256, 0, ST(stream), (const float*)part_acc,
            (const float*)part_ml, out, prob, S, D, L, tf32_out);
+  VLFB_CHECK_LAUNCH();
+  return VLFB_OK;
+}
+int vlfb_fbo_bank_scan(const float* bank, const float* q, float scale, float* out, float* prob, int R, int L, int D,
+                       int tf32_out, void* workspace, size_t workspace_bytes, void* stream) {
+  return vlfb_fbo_bank_scan_dt(bank, VLFB_DT_F32, q, scale, out, prob, R, L, D, tf32_out, workspace, workspace_bytes, stream);
+}
+
+int vlfb_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream) {
+  VLFB_CHECK_ARG(x && y && n >= 0 && (n & 7) == 0);
+  VLFB_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  if (n == 0) return VLFB_OK;
+  launch_k(f32_to_bf16_k, stream_grid(n / 8, 256), 256, 0, ST(stream), (const float4*)x, (uint4*)y, n / 8);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }

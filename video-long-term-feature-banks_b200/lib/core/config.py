@@ -101,7 +101,10 @@ __C = _tree({
     # ---- additions of this implementation (not in the reference) -------------
     # B200.COMPUTE: 'tf32' = parity mode (fp32 storage, tcgen05 kind::tf32, fp32 accumulate).
     # B200.FBO_FOLD: inference nets run each FBO-NL layer as one pass over the raw bank (vlfb.executor.FboFoldStep).
-    'B200': {'COMPUTE': 'tf32', 'GEMM_BACKEND': 'tcgen05', 'CUDA_GRAPH': True, 'FBO_FOLD': True, 'FBO_STACK': True},
+    # B200.LFB_DTYPE: 'f32' | 'bf16' = storage type of the feature-bank windows the folded inference FBO scans (a bf16
+    #   copy is made when the bank is fed; scores / softmax / sums stay fp32; parity tolerance 1e-2 instead of 1e-3).
+    'B200': {'COMPUTE': 'tf32', 'GEMM_BACKEND': 'tcgen05', 'CUDA_GRAPH': True, 'FBO_FOLD': True, 'FBO_STACK': True,
+             'LFB_DTYPE': 'f32'},
 })
 config = __C
 _DEFAULTS = None

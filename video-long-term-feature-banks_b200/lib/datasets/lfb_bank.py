@@ -172,6 +172,7 @@ class DeviceLfb(object):
         shape = tuple(np.shape(index_table)) + (self.dim,)
         dst = workspace._static(name, shape, self.bank.dtype)
         self.gather(index_table, out=dst, tf32_out=True)
+        workspace.bank_companion(name, dst)                  # B200.LFB_DTYPE 'bf16': the scan operand of the folded FBO
         ws = workspace.current()
         ws.blobs[name] = dst
         ws.rounded.add(name)

@@ -717,6 +717,9 @@ class FboFoldStep(Step):
         bank = phys(ctx.get(self.bank))                         # [R, L, 1, 1, D] over the fed (R, L, D) blob
         L_, D = int(bank.shape[1]), int(bank.shape[-1])
         bank = bank.reshape(R, L_, D)
+        b16 = self._bf16_bank(ctx)
+        if b16 is not None and tuple(b16.shape) == (R, L_, D):
+            bank = b16                                          # B200.LFB_DTYPE 'bf16': half the bytes per pass
         w1 = P.tf32(self.w1).view(1, -1, D)                     # [d1][D]
         d1 = int(w1.shape[1])
         wphi = P.tf32(self.wphi).view(1, d, d1)                 # [d][d1]
@@ -737,6 +740,23 @@ class FboFoldStep(Step):
         if prob is not None:
             ctx.put(self.prob_name, prob.view(R, 1, L_))
         ctx.put(self.op.outputs[0], y.view(R, dg, 1), rounded=True)
+
+    def _bf16_bank(self, ctx):
+        """The bf16 copy of the bank made when it was fed (workspace.bank_companion), found through the view chain
+        (Transpose / Reshape of lfb_helper.NTC_to_NCT11) that leads from the fed blob to this step's bank input."""
+        from core.config import config as cfg
+        if cfg.B200.get('LFB_DTYPE', 'f32') != 'bf16':
+            return None
+        key = self.in_keys[1]
+        for _ in range(8):
+            t = ctx.ws.blobs.get(key[0] + '@bf16')
+            if t is not None:
+                return t
+            st = ctx.net.producer.get(key)
+            if not isinstance(st, (ReshapeStep, TransposeStep, SqueezeStep)):
+                return None
+            key = st.in_keys[0]
+        return None
 
     def bwd(self, ctx):
         raise NotImplementedError('FboFoldStep is an inference-mode lowering')

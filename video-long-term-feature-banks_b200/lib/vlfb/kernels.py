@@ -661,23 +661,33 @@ def fbo_nl_bwd(cfgd, layers, a0, bp, da_last, da0, dbp):
 # --------------------------------------------------------------------------- raw feature-bank kernels (csrc/fbo.cu)
 def fbo_bank_scan(bank, q, out, scale, prob=None, tf32_out=False):
     """out[r] = sum_j softmax_j(scale * q[r].bank[r,j]) * bank[r,j]: the folded inference-mode FBO-NL layer, one pass
-    over the raw bank.  bank [R,L,D], q [R,D], out [R,D], prob [R,L] or None."""
-    _f32c(bank, 'bank'), _f32c(q, 'q'), _f32c(out, 'out')
+    over the raw bank.  bank [R,L,D] fp32 or bf16 (storage type only: the arithmetic is fp32), q [R,D], out [R,D],
+    prob [R,L] or None."""
+    assert bank.is_contiguous() and bank.dtype in (torch.float32, torch.bfloat16), 'bank must be contiguous fp32 / bf16'
+    _f32c(q, 'q'), _f32c(out, 'out')
+    dt = L.DT_BF16 if bank.dtype == torch.bfloat16 else L.DT_F32
     r, l, d = bank.shape
     assert tuple(q.shape) == (r, d) and tuple(out.shape) == (r, d)
     if prob is not None:
         assert tuple(_f32c(prob, 'prob').shape) == (r, l)
     lib = L.load()
-    nbytes = int(lib.vlfb_fbo_bank_scan_workspace(r, l, d))
+    nbytes = int(lib.vlfb_fbo_bank_scan_workspace_dt(r, l, d, dt))
     if nbytes == 0 and r > 0:
-        raise L.VlfbError('fbo_bank_scan: unsupported bank row width %d (1024, 2048 or 4096)' % d)
+        raise L.VlfbError('fbo_bank_scan: unsupported bank row width %d (fp32: 1024, 2048 or 4096; bf16: 2048 or 4096)' % d)
     wsp = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=bank.device)
-    args = (_ptr(bank), _ptr(q), float(scale), _ptr(out), _ptr(prob), r, l, d, int(tf32_out), _ptr(wsp), C.c_size_t(nbytes),
-            _stream())
-    _check(lib.vlfb_fbo_bank_scan(*args), 'fbo_bank_scan')
+    args = (_ptr(bank), dt, _ptr(q), float(scale), _ptr(out), _ptr(prob), r, l, d, int(tf32_out), _ptr(wsp),
+            C.c_size_t(nbytes), _stream())
+    _check(lib.vlfb_fbo_bank_scan_dt(*args), 'fbo_bank_scan')
     if _PROFILE is not None:
-        _PROFILE.append(('fbo_bank_scan R=%d L=%d D=%d' % (r, l, d), lambda: lib.vlfb_fbo_bank_scan(*args), 4.0 * r * l * d,
-                         _nbytes(bank, q, out), LABEL, (bank, q, out, prob, wsp)))
+        _PROFILE.append(('fbo_bank_scan R=%d L=%d D=%d %s' % (r, l, d, 'bf16' if dt else 'f32'),
+                         lambda: lib.vlfb_fbo_bank_scan_dt(*args), 4.0 * r * l * d, _nbytes(bank, q, out), LABEL,
+                         (bank, q, out, prob, wsp)))
+
+
+def cast_bf16(x, y):
+    """y (bf16) = x (fp32), round to nearest even; numel % 8 == 0."""
+    assert y.dtype == torch.bfloat16 and y.is_contiguous() and y.numel() == x.numel()
+    _check(L.load().vlfb_cast_f32_to_bf16(_ptr(_f32c(x)), _ptr(y), x.numel(), _stream()), 'cast_bf16')
 
 
 def lfb_gather(bank, idx, out, tf32_out=False):

@@ -41,6 +41,7 @@ class GemmPlan(C.Structure):
 
 
 ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
+DT_F32, DT_BF16 = 0, 1              # vlfb_dtype_t
 
 
 class FboLayer(C.Structure):
@@ -114,9 +115,14 @@ SIGNATURES = {
     'vlfb_fbo_bank_scan_splits': [_I, _I, _I],
     'vlfb_fbo_bank_scan_workspace': [_I, _I, _I],
     'vlfb_fbo_bank_scan': [_P, _P, _F, _P, _P, _I, _I, _I, _I, _P, C.c_size_t, _P],
+    'vlfb_fbo_bank_scan_splits_dt': [_I, _I, _I, _I],
+    'vlfb_fbo_bank_scan_workspace_dt': [_I, _I, _I, _I],
+    'vlfb_fbo_bank_scan_dt': [_P, _I, _P, _F, _P, _P, _I, _I, _I, _I, _P, C.c_size_t, _P],
+    'vlfb_cast_f32_to_bf16': [_P, _P, _L, _P],
     'vlfb_lfb_gather': [_P, _L, _P, _P, _L, _I, _I, _P],
 }
 RESTYPES = {'vlfb_last_error': C.c_char_p, 'vlfb_fbo_bank_scan_workspace': C.c_size_t,
+            'vlfb_fbo_bank_scan_workspace_dt': C.c_size_t,
             'vlfb_fbo_nl_scratch_floats': C.c_size_t,
             'vlfb_gemm_workspace_bytes': C.c_size_t, 'vlfb_spatial_bn_workspace_bytes': C.c_size_t}
 

@@ -431,12 +431,28 @@ def _feed_activation(name, arr):
         return
     dst = _static(name, src.shape, X.DTYPE)
     dst.copy_(src, non_blocking=True)
+    bank_companion(name, dst)
     if dst.dim() >= 2 and dst.shape[-1] >= 64:                    # feature banks are GEMM operands
         X.K.round_tf32(dst.view(-1), dst.view(-1))
         _ws.rounded.add(name)
     else:
         _ws.rounded.discard(name)
     _ws.blobs[name] = dst
+
+
+def bank_companion(name, dst):
+    """B200.LFB_DTYPE 'bf16': keep a bf16 copy of a fed feature bank ('lfb*' blobs, rows of 2048 / 4096 features) under
+    '<name>@bf16' -- the operand of the folded inference FBO's bank scan (executor.FboFoldStep), half the HBM bytes per
+    pass.  The fp32 blob stays (the as-written / training lowerings read it).  Any other setting drops a stale copy."""
+    from core.config import config as cfg
+    key = name + '@bf16'
+    if (cfg.B200.get('LFB_DTYPE', 'f32') == 'bf16' and name.startswith('lfb') and dst.dim() == 3
+            and int(dst.shape[-1]) in (2048, 4096)):
+        comp = _static(key, dst.shape, torch.bfloat16)
+        X.K.cast_bf16(dst.view(-1), comp.view(-1))
+        _ws.blobs[key] = comp
+    else:
+        _ws.blobs.pop(key, None)
 
 
 def FeedBlob(name, arr, device_option=None):
