@@ -175,6 +175,12 @@ int vlfb_maxpool3d_fwd(const float* x, float* y, int32_t* argmax /* may be NULL 
                        const vlfb_conv_geom_t* g, void* stream);
 int vlfb_maxpool3d_bwd(const float* dy, const int32_t* argmax, float* dx /* pre-zeroed or accumulated */,
                        const vlfb_conv_geom_t* g, void* stream);
+/* Gather form of the max-pool backward: dx (written completely, no pre-zeroing, no atomics) = for every input element the
+ * sum of dy over the windows that cover it and whose argmax it is.  y (may be NULL) = the pool's forward OUTPUT: windows
+ * whose maximum is <= 0 pass no gradient, i.e. the backward of a ReLU that produced the pool's input is folded in
+ * (resnet_video.py:189-196: conv1 -> AffineNd -> Relu -> MaxPool 'pool1'); tf32_out rounds dx (a GEMM operand). */
+int vlfb_maxpool3d_bwd_gather(const float* dy, const int32_t* argmax, const float* y, float* dx,
+                              const vlfb_conv_geom_t* g, int tf32_out, void* stream);
 int vlfb_avgpool3d_fwd(const float* x, float* y, const vlfb_conv_geom_t* g, void* stream);
 int vlfb_avgpool3d_bwd(const float* dy, float* dx, const vlfb_conv_geom_t* g, int accumulate,
                        void* stream);

@@ -152,8 +152,9 @@ class Graph(object):
         if dim_in == dim_out and ts == 1 and stride == 1:
             sc = x
         else:
-            sc = self.q(self.conv_affine(x, prefix + '_branch1', dim_in, dim_out, (1, 1, 1),
-                                         (ts, stride, stride), (0, 0, 0)))
+            sc = self.conv_affine(x, prefix + '_branch1', dim_in, dim_out, (1, 1, 1), (ts, stride, stride), (0, 0, 0))
+            if self.cfg.MODEL.USE_AFFINE:          # emulate_tf32: the fused conv + AffineNd epilogue stores it rounded
+                sc = self.q(sc)
         if not self.run:
             return None
         y = self.q(torch.relu(tr + sc))

@@ -138,7 +138,7 @@ def _check_addressable(a, b, d):
     RK._mat_operand(b, 2, 1)
 
 
-def matmul(a, b, d, alpha=1.0, accumulate=False, bias=None, tf32_out=False):
+def matmul(a, b, d, alpha=1.0, accumulate=False, bias=None, tf32_out=False, tf32_optional=False):
     _check_addressable(a, b, d)
     r = torch.bmm(a, b) * alpha
     if bias is not None:
@@ -147,6 +147,7 @@ def matmul(a, b, d, alpha=1.0, accumulate=False, bias=None, tf32_out=False):
         d.add_(r)
     else:
         d.copy_(_q(r, tf32_out))
+    return bool(tf32_out)
 
 
 def affine_fwd(x, s, b, y):
@@ -172,8 +173,7 @@ def spatial_bn_fwd(x, s, b, rm, rv, sm, siv, y, eps, momentum):
 
 
 def spatial_bn_infer(x, s, b, rm, rv, y, eps):
-    f = s / torch.sqrt(rv + eps)
-    y.copy_(x * f + (b - rm * f))
+    y.copy_((x - rm) * (s / torch.sqrt(rv + eps)) + b)
 
 
 def spatial_bn_bwd(dy, x, s, sm, siv, dx, ds, db):
@@ -208,6 +208,17 @@ def maxpool_bwd(dy, argmax, dx, g):
     flat = dx.view(-1, c)
     idx = argmax.view(-1, c).long()
     flat.scatter_add_(0, idx, dy.reshape(-1, c))
+
+
+def maxpool_bwd_gather(dy, argmax, y, dx, g, tf32_out=False):
+    c = dy.shape[-1]
+    d = dy.reshape(-1, c)
+    if y is not None:
+        d = d * (y.reshape(-1, c) > 0).to(d.dtype)
+    dx.zero_()
+    dx.view(-1, c).scatter_add_(0, argmax.view(-1, c).long(), d)
+    if tf32_out:
+        dx.copy_(_q(dx))
 
 
 def avgpool_fwd(x, y, g):

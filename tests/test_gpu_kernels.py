@@ -317,6 +317,24 @@ def test_maxpool(K, ker, st, pd, shape):
     dx = torch.zeros_like(xd)
     K.maxpool_bwd(to_cl(dy.float()).cuda(), arg, dx, g)
     assert rel_err(to_nc(dx), x.grad) < 1e-5
+    # gather form: no pre-zeroed buffer, same values (sums of at most a few terms, in window order)
+    dxg = torch.full_like(xd, float('nan'))
+    K.maxpool_bwd_gather(to_cl(dy.float()).cuda(), arg, None, dxg, g)
+    assert rel_err(to_nc(dxg), x.grad) < 1e-6
+    # ... with the backward of a ReLU in front of the pool folded in (mask from the pool OUTPUT) and TF32 rounding
+    xr = torch.relu(x.detach()).requires_grad_(True)
+    yr = F.max_pool3d(xr, ker, st, pd)
+    xdr = to_cl(xr.detach().float()).cuda()
+    K.maxpool_fwd(xdr, yd, arg, g)
+    dxr = torch.full_like(xd, float('nan'))
+    K.maxpool_bwd_gather(to_cl(dy.float()).cuda(), arg, yd, dxr, g, tf32_out=True)
+    gy = to_nc(dxr).cpu()
+    # reference: autograd through max-pool (ties: any winner among equal zeros is masked anyway), then relu' = (x > 0)
+    yr.backward(dy)
+    ref = tf32_round((xr.grad * (xr.detach() > 0)).float())
+    pos = (xr.detach() > 0)
+    assert torch.equal(gy[~pos], torch.zeros_like(gy[~pos]))
+    assert rel_err(gy, ref) < 1e-6
 
 
 @pytest.mark.parametrize('ker,shape', [((4, 1, 1), (2, 64, 4, 7, 7)), ((4, 7, 7), (2, 64, 4, 7, 7)),

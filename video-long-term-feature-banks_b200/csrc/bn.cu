@@ -3,9 +3,9 @@
 // Conv3dBN, resnet_video.py:185-188, nonlocal_helper.py:146-155) and produces the `_bn_sm` / `_bn_siv` blobs
 // lib/utils/bn_helper.py:170-173 reads for precise-BN.  HBM-bound streaming kernels:
 //   training forward  = one reduction pass (per-channel sum / sum of squares about a pivot, fp32 per thread,
-//                       fp64 across blocks) + one apply pass y = x * fs[c] + fb[c]
+//                       fp64 across blocks) + one apply pass y = (x - mean[c]) * fs[c] + b[c]
 //   training backward = one reduction pass (sum dy, sum dy * (x - mean)) + one apply pass dx = A dy + B x + C
-//   inference         = y = x * s / sqrt(var + eps) + (b - mean * s / sqrt(var + eps)): one apply pass
+//   inference         = y = (x - mean) * s / sqrt(var + eps) + b: one apply pass
 // Bytes per unit: forward 2 reads + 1 write of the tensor, backward 4 reads + 1 write.
 #include "common.cuh"
 
@@ -64,7 +64,7 @@ __global__ void bn_reduce_k(const float* __restrict__ a, const float* __restrict
 __global__ void bn_finalize_fwd_k(const double* __restrict__ acc, const float* __restrict__ x0, int64_t rows, int C, float eps,
                                   float momentum, const float* __restrict__ scale, const float* __restrict__ bias,
                                   float* __restrict__ run_mean, float* __restrict__ run_var, float* __restrict__ saved_mean,
-                                  float* __restrict__ saved_inv_std, float* __restrict__ fs, float* __restrict__ fb) {
+                                  float* __restrict__ saved_inv_std, float* __restrict__ fs) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double m = (double)rows;
@@ -80,18 +80,13 @@ __global__ void bn_finalize_fwd_k(const double* __restrict__ acc, const float* _
     run_mean[c] = (float)((double)run_mean[c] * momentum + mean * (1.0 - (double)momentum));
     run_var[c] = (float)((double)run_var[c] * momentum + unbiased * (1.0 - (double)momentum));
   }
-  const double f = (double)scale[c] * inv_std;
-  fs[c] = (float)f;
-  fb[c] = (float)((double)bias[c] - mean * f);
+  fs[c] = (float)((double)scale[c] * inv_std);           // apply pass: y = (x - saved_mean) * fs + bias
 }
 
-__global__ void bn_infer_params_k(const float* __restrict__ scale, const float* __restrict__ bias, const float* __restrict__ mean,
-                                  const float* __restrict__ var, float eps, int C, float* __restrict__ fs, float* __restrict__ fb) {
+__global__ void bn_infer_params_k(const float* __restrict__ scale, const float* __restrict__ var, float eps, int C,
+                                  float* __restrict__ fs) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float f = scale[c] / sqrtf(var[c] + eps);
-  fs[c] = f;
-  fb[c] = bias[c] - mean[c] * f;
+  if (c < C) fs[c] = scale[c] / sqrtf(var[c] + eps);
 }
 
 // dscale += sum dy * xhat, dbias += sum dy; coefficients of dx = A dy + B x + Cc:
@@ -113,13 +108,19 @@ __global__ void bn_finalize_bwd_k(const double* __restrict__ acc, int64_t rows, 
   cC[c] = (float)(-A * s1 / m - B * mu);
 }
 
-// y = x * s[c] + b[c]  (u == nullptr)   or   y = x * s[c] + u * t[c] + b[c]
-__global__ void bn_apply_k(const float4* __restrict__ x, const float4* __restrict__ s, const float4* __restrict__ u,
-                           const float4* __restrict__ t, const float4* __restrict__ b, float4* __restrict__ y, int64_t n4,
-                           int c4) {
+// y = (x - m[c]) * s[c] + b[c]  (u == nullptr; m may be nullptr = 0)   or   y = x * s[c] + u * t[c] + b[c]
+// (the forward subtracts the mean BEFORE scaling: x * (s inv_std) + (b - mean s inv_std) cancels badly when inv_std is large)
+__global__ void bn_apply_k(const float4* __restrict__ x, const float4* __restrict__ m, const float4* __restrict__ s,
+                           const float4* __restrict__ u, const float4* __restrict__ t, const float4* __restrict__ b,
+                           float4* __restrict__ y, int64_t n4, int c4) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % c4);
-    const float4 v = x[i], sc = s[c], bi = b[c];
+    float4 v = x[i];
+    const float4 sc = s[c], bi = b[c];
+    if (m) {
+      const float4 mc = m[c];
+      v.x -= mc.x; v.y -= mc.y; v.z -= mc.z; v.w -= mc.w;
+    }
     float4 o = make_float4(v.x * sc.x + bi.x, v.y * sc.y + bi.y, v.z * sc.z + bi.z, v.w * sc.w + bi.w);
     if (u) {
       const float4 w = u[i], tc = t[c];
@@ -179,11 +180,11 @@ int vlfb_spatial_bn_fwd(const float* x, const float* scale, const float* bias, f
   launch_k(bn_reduce_k<0>, grid, dim3(32, 8), 0, ST(stream), x, (const float*)nullptr, x, rows, C, rpb, w.acc);
   VLFB_CHECK_LAUNCH();
   launch_k(bn_finalize_fwd_k, dim3(ceil_div(C, 128)), dim3(128), 0, ST(stream), (const double*)w.acc, x, rows, C, eps, momentum,
-           scale, bias, running_mean, running_var, saved_mean, saved_inv_std, w.f0, w.f1);
+           scale, bias, running_mean, running_var, saved_mean, saved_inv_std, w.f0);
   VLFB_CHECK_LAUNCH();
   const int64_t n4 = rows * (C >> 2);
-  launch_k(bn_apply_k, stream_grid(n4, TPB), TPB, 0, ST(stream), (const float4*)x, (const float4*)w.f0, (const float4*)nullptr,
-           (const float4*)nullptr, (const float4*)w.f1, (float4*)y, n4, C >> 2);
+  launch_k(bn_apply_k, stream_grid(n4, TPB), TPB, 0, ST(stream), (const float4*)x, (const float4*)saved_mean,
+           (const float4*)w.f0, (const float4*)nullptr, (const float4*)nullptr, (const float4*)bias, (float4*)y, n4, C >> 2);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -196,12 +197,11 @@ int vlfb_spatial_bn_infer(const float* x, const float* scale, const float* bias,
                  (reinterpret_cast<uintptr_t>(workspace) & 15) == 0);
   if (rows == 0) return VLFB_OK;
   const Ws w = carve(workspace, C);
-  launch_k(bn_infer_params_k, dim3(ceil_div(C, 128)), dim3(128), 0, ST(stream), scale, bias, running_mean, running_var, eps, C,
-           w.f0, w.f1);
+  launch_k(bn_infer_params_k, dim3(ceil_div(C, 128)), dim3(128), 0, ST(stream), scale, running_var, eps, C, w.f0);
   VLFB_CHECK_LAUNCH();
   const int64_t n4 = rows * (C >> 2);
-  launch_k(bn_apply_k, stream_grid(n4, TPB), TPB, 0, ST(stream), (const float4*)x, (const float4*)w.f0, (const float4*)nullptr,
-           (const float4*)nullptr, (const float4*)w.f1, (float4*)y, n4, C >> 2);
+  launch_k(bn_apply_k, stream_grid(n4, TPB), TPB, 0, ST(stream), (const float4*)x, (const float4*)running_mean,
+           (const float4*)w.f0, (const float4*)nullptr, (const float4*)nullptr, (const float4*)bias, (float4*)y, n4, C >> 2);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }
@@ -226,8 +226,8 @@ int vlfb_spatial_bn_bwd(const float* dy, const float* x, const float* scale, con
            saved_inv_std, dscale, dbias, w.f0, w.f1, w.f2);
   VLFB_CHECK_LAUNCH();
   const int64_t n4 = rows * (C >> 2);
-  launch_k(bn_apply_k, stream_grid(n4, TPB), TPB, 0, ST(stream), (const float4*)dy, (const float4*)w.f0, (const float4*)x,
-           (const float4*)w.f1, (const float4*)w.f2, (float4*)dx, n4, C >> 2);
+  launch_k(bn_apply_k, stream_grid(n4, TPB), TPB, 0, ST(stream), (const float4*)dy, (const float4*)nullptr,
+           (const float4*)w.f0, (const float4*)x, (const float4*)w.f1, (const float4*)w.f2, (float4*)dx, n4, C >> 2);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }

@@ -102,6 +102,46 @@ __global__ void maxpool_bwd_k(const float* __restrict__ dy, const int32_t* __res
   }
 }
 
+// Gather form of the max-pool backward: every INPUT element sums the gradients of the (few) windows that cover it and
+// picked it -- each dx element is written exactly once, so there is no zero fill and there are no atomics (the scatter
+// form above: fill + one scalar atomic per output element).  Optional fusions for a pool whose input is a conv + ReLU
+// output with no other consumer (pool1): `y` = the pool's OUTPUT gives the ReLU-backward mask of the winner
+// (y[o] = x[argmax] > 0; a window whose maximum is 0 passes no gradient), `tf32` rounds the result -- dx is then the
+// finished gradient operand of the producer's wgrad GEMM.
+__global__ void maxpool_bwd_gather_k(const float* __restrict__ dy, const int32_t* __restrict__ arg,
+                                     const float* __restrict__ y, float* __restrict__ dx, const vlfb_conv_geom_t g,
+                                     int64_t total, int tf32) {
+  const int c4 = g.C >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4) * 4;
+    const int64_t pos64 = i / c4;
+    const int pos = (int)pos64;
+    const Pos4 p = decode_pos(pos64, g.T, g.H, g.W);
+    // windows covering coordinate x: o * s - pad <= x <= o * s - pad + k - 1
+    const int t0 = max(0, (p.t + g.pT - g.kT + g.sT) / g.sT), t1 = min(g.To - 1, (p.t + g.pT) / g.sT);
+    const int h0 = max(0, (p.h + g.pH - g.kH + g.sH) / g.sH), h1 = min(g.Ho - 1, (p.h + g.pH) / g.sH);
+    const int w0 = max(0, (p.w + g.pW - g.kW + g.sW) / g.sW), w1 = min(g.Wo - 1, (p.w + g.pW) / g.sW);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ot = t0; ot <= t1; ++ot)
+      for (int oh = h0; oh <= h1; ++oh)
+        for (int ow = w0; ow <= w1; ++ow) {
+          const int64_t o = ((((int64_t)p.n * g.To + ot) * g.Ho + oh) * g.Wo + ow) * g.C + c;
+          const int4 a = *reinterpret_cast<const int4*>(arg + o);
+          float4 d = *reinterpret_cast<const float4*>(dy + o);
+          if (y != nullptr) {
+            const float4 m = *reinterpret_cast<const float4*>(y + o);
+            d.x = m.x > 0.f ? d.x : 0.f; d.y = m.y > 0.f ? d.y : 0.f; d.z = m.z > 0.f ? d.z : 0.f; d.w = m.w > 0.f ? d.w : 0.f;
+          }
+          if (a.x == pos) acc.x += d.x;
+          if (a.y == pos) acc.y += d.y;
+          if (a.z == pos) acc.z += d.z;
+          if (a.w == pos) acc.w += d.w;
+        }
+    if (tf32) { acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y); acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w); }
+    *reinterpret_cast<float4*>(dx + i * 4) = acc;
+  }
+}
+
 __global__ void avgpool_fwd_k(const float* __restrict__ x, float* __restrict__ y, const vlfb_conv_geom_t g,
                               int64_t total) {
   const int c4 = g.C >> 2;
@@ -753,6 +793,17 @@ int vlfb_maxpool3d_bwd(const float* dy, const int32_t* argmax, float* dx, const 
   const int64_t total = (int64_t)g->N * g->To * g->Ho * g->Wo * g->C;
   if (total == 0) return VLFB_OK;
   launch_k(maxpool_bwd_k, stream_grid(total, TPB), TPB, 0, ST(stream), dy, argmax, dx, g->C, total);
+  VLFB_CHECK_LAUNCH();
+  return VLFB_OK;
+}
+
+int vlfb_maxpool3d_bwd_gather(const float* dy, const int32_t* argmax, const float* y, float* dx,
+                               const vlfb_conv_geom_t* g, int tf32_out, void* stream) {
+  VLFB_CHECK_ARG(dy && argmax && dx && g && (g->C & 3) == 0 && g->Co == g->C);
+  VLFB_CHECK_ARG(g->sT > 0 && g->sH > 0 && g->sW > 0 && (int64_t)g->N * g->T * g->H * g->W < (1ll << 31));
+  const int64_t total = (int64_t)g->N * g->T * g->H * g->W * (g->C >> 2);
+  if (total == 0) return VLFB_OK;
+  launch_k(maxpool_bwd_gather_k, stream_grid(total, TPB), TPB, 0, ST(stream), dy, argmax, y, dx, *g, total, tf32_out);
   VLFB_CHECK_LAUNCH();
   return VLFB_OK;
 }

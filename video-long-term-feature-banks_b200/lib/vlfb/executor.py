@@ -557,25 +557,36 @@ class PoolStep(Step):
         if self.op.type == 'MaxPool':
             arg = empty(yp.shape, torch.int32) if ctx.net.train else None
             K.maxpool_fwd(xp, yp, arg, g)
-            ctx.saved[id(self)] = (g, arg, x.shape, x.stride())
+            ctx.saved[id(self)] = (g, arg, x.shape, x.stride(), yp)
         else:
             K.avgpool_fwd(xp, yp, g)
-            ctx.saved[id(self)] = (g, None, x.shape, x.stride())
+            ctx.saved[id(self)] = (g, None, x.shape, x.stride(), None)
         ctx.put(self.op.outputs[0], y, rounded=(self.op.type == 'MaxPool' and xname in ctx.ws.rounded))
 
     def bwd(self, ctx):
         gy = ctx.pop_grad(self.out_keys[0])
         if gy is None:
             return
-        g, arg, xshape, xstride = ctx.saved.pop(id(self))
+        g, arg, xshape, xstride, yp = ctx.saved.pop(id(self))
         dx = torch.empty_strided(xshape, xstride, dtype=DTYPE, device=DEVICE)
         gp = as5d(phys(gy))
+        xkey = self.in_keys[0]
         if self.op.type == 'MaxPool':
-            K.fill(flat(dx), 0.0)
-            K.maxpool_bwd(gp, arg, as5d(phys(dx)), g)
+            # gather form: every dx element is written once (no zero fill, no atomics).  When the pooled blob is a
+            # conv + ReLU output that nothing else reads (pool1), the ReLU backward (mask from the pool OUTPUT: the
+            # winner of a window is positive iff the window's maximum is) and the TF32 rounding of the conv's wgrad
+            # operand are folded in and the conv receives a finished gradient.
+            prod = ctx.net.producer.get(xkey)
+            fuse = (FUSE_GRAD_FINISH and isinstance(prod, ConvStep) and prod.relu and ctx.net.contrib is not None
+                    and ctx.net.contrib.get(xkey) == 1)
+            K.maxpool_bwd_gather(gp, arg, yp if fuse else None, as5d(phys(dx)), g, tf32_out=fuse)
+            if fuse:
+                ctx.set_final_grad(xkey, dx)
+                STATS['fused_grad_finish'] += 1
+                return
         else:
             K.avgpool_bwd(gp, as5d(phys(dx)), g, accumulate=False)
-        ctx.add_grad(self.in_keys[0], dx, owned=True)
+        ctx.add_grad(xkey, dx, owned=True)
 
 
 class ReshapeStep(Step):
@@ -681,14 +692,12 @@ class BatchMatMulStep(Step):
         if ctx.net.requires.get(self.in_keys[0], False):
             da = empty_like_strided(a)
             dA = da.transpose(1, 2) if ta else da
-            sole = ctx.sole(self.in_keys[0])
-            K.matmul(g, B.transpose(1, 2), dA, tf32_out=sole)
+            sole = K.matmul(g, B.transpose(1, 2), dA, tf32_out=ctx.sole(self.in_keys[0]), tf32_optional=True)
             ctx.add_grad(self.in_keys[0], da, owned=True, rounded=sole)
         if ctx.net.requires.get(self.in_keys[1], False):
             db = empty_like_strided(b)
             dB = db.transpose(1, 2) if tb else db
-            sole = ctx.sole(self.in_keys[1])
-            K.matmul(A.transpose(1, 2), g, dB, tf32_out=sole)
+            sole = K.matmul(A.transpose(1, 2), g, dB, tf32_out=ctx.sole(self.in_keys[1]), tf32_optional=True)
             ctx.add_grad(self.in_keys[1], db, owned=True, rounded=sole)
 
 

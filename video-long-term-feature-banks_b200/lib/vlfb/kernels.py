@@ -328,9 +328,12 @@ def _mat_operand(t, rows_dim, k_dim):
                      % (tuple(t.shape), tuple(t.stride())))
 
 
-def matmul(a, b, d, alpha=1.0, accumulate=False, bias=None, tf32_out=False):
+def matmul(a, b, d, alpha=1.0, accumulate=False, bias=None, tf32_out=False, tf32_optional=False):
     """d[i] (+)= alpha * a[i] @ b[i] (+ bias[n]) for 3-D strided views a (B,M,K), b (B,K,N), d (B,M,N).
-    Each matrix needs unit stride along one of its two dims (16-byte aligned rows)."""
+    Each matrix needs unit stride along one of its two dims (16-byte aligned rows).  Returns whether d was stored
+    TF32-rounded: with `tf32_optional` a product that qualifies for split-K (atomic accumulation cannot round) keeps
+    the split and leaves the rounding to the consumer -- the split is worth 2x on the K = 3136 non-local gradient
+    products, the saved rounding pass ~5 us (call J/K: 0.046 vs 0.022 ms per launch)."""
     assert a.dim() == 3 and b.dim() == 3 and d.dim() == 3
     Bt, M, K = a.shape
     N = b.shape[2]
@@ -339,7 +342,8 @@ def matmul(a, b, d, alpha=1.0, accumulate=False, bias=None, tf32_out=False):
         # output is column-major: compute d^T = b^T a^T
         assert _dim_ok(d.stride(1), M), 'matmul output needs a unit stride'
         assert bias is None
-        return matmul(b.transpose(1, 2), a.transpose(1, 2), d.transpose(1, 2), alpha, accumulate, None, tf32_out)
+        return matmul(b.transpose(1, 2), a.transpose(1, 2), d.transpose(1, 2), alpha, accumulate, None, tf32_out,
+                      tf32_optional)
     ka, lda, sba = _mat_operand(a, 1, 2)
     kb, ldb, sbb = _mat_operand(b, 2, 1)
     p = _base_params(M, N, K, d, d.stride(1) if M > 1 else N, alpha)
@@ -348,6 +352,8 @@ def matmul(a, b, d, alpha=1.0, accumulate=False, bias=None, tf32_out=False):
     p.batch = Bt
     p.d_batch_stride = d.stride(0) if Bt > 1 else 0
     tiles = Bt * ((M + 127) // 128) * ((N + 255) // 256)
+    if tiles <= NUM_SMS // 2 and K >= 1024 and tf32_out and tf32_optional:
+        tf32_out = False
     if tiles <= NUM_SMS // 2 and K >= 1024 and not tf32_out:
         # few output tiles with a long reduction (the 4 x 80 x 2560 classifier ran 0.19 ms on ONE CTA; the non-local
         # affinity products fill 28-56 of 148 SMs): split K over the SMs -- atomic accumulation into a zeroed / kept
@@ -361,6 +367,7 @@ def matmul(a, b, d, alpha=1.0, accumulate=False, bias=None, tf32_out=False):
     _set_epilogue(p, None, bias, None, None, False, tf32_out)
     _run_gemm(p, 'matmul', 2.0 * Bt * M * N * K, 4.0 * Bt * (M * K + K * N + M * N * (2 if accumulate else 1)),
               keep=(a, b, d, bias))
+    return bool(tf32_out)
 
 
 def weight_transpose_multi(jobs, cache):
@@ -435,6 +442,13 @@ def maxpool_fwd(x, y, argmax, g):
 def maxpool_bwd(dy, argmax, dx, g):
     _check(L.load().vlfb_maxpool3d_bwd(_ptr(_f32c(dy)), _ptr(argmax), _ptr(_f32c(dx)), C.byref(g), _stream()),
             'maxpool_bwd')
+
+
+def maxpool_bwd_gather(dy, argmax, y, dx, g, tf32_out=False):
+    """dx = max-pool backward in gather form (every element written once: no fill, no atomics); y = the pool output
+    (or None): windows with a maximum <= 0 pass nothing (the backward of the ReLU feeding the pool)."""
+    _check(L.load().vlfb_maxpool3d_bwd_gather(_ptr(_f32c(dy)), _ptr(argmax), _ptr(y), _ptr(_f32c(dx)), C.byref(g),
+                                              int(tf32_out), _stream()), 'maxpool_bwd_gather')
 
 
 def avgpool_fwd(x, y, g):

@@ -75,6 +75,7 @@ SIGNATURES = {
     'vlfb_spatial_bn_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, C.c_size_t, _P],
     'vlfb_maxpool3d_fwd': [_P, _P, _P, _GP, _P],
     'vlfb_maxpool3d_bwd': [_P, _P, _P, _GP, _P],
+    'vlfb_maxpool3d_bwd_gather': [_P, _P, _P, _P, _GP, _I, _P],
     'vlfb_avgpool3d_fwd': [_P, _P, _GP, _P],
     'vlfb_avgpool3d_bwd': [_P, _P, _GP, _I, _P],
     'vlfb_roi_align_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
