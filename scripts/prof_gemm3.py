@@ -19,9 +19,12 @@ sys.path.insert(0, os.path.join(ROOT, 'video-long-term-feature-banks_b200', 'lib
 from vlfb import kernels as K  # noqa: E402
 
 
+CLIPS = int(os.environ.get('VLFB_PROF_CLIPS', '2'))      # 8: the large-batch shapes (M = 25088)
+
+
 def case(Ci, Co, ker, pd, dil=(1, 1, 1), residual=False):
-    g = K.conv_geom((2, 16, 14, 14, Ci), Co, ker, (1, 1, 1), pd, dil)
-    x = torch.randn((2, 16, 14, 14, Ci), device='cuda')
+    g = K.conv_geom((CLIPS, 16, 14, 14, Ci), Co, ker, (1, 1, 1), pd, dil)
+    x = torch.randn((CLIPS, 16, 14, 14, Ci), device='cuda')
     w = torch.randn((Co,) + tuple(ker) + (Ci,), device='cuda') * 0.05
     y = torch.empty(K.out_shape(g), device='cuda')
     s = torch.rand(Co, device='cuda') + 0.5

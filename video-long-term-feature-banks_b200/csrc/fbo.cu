@@ -21,6 +21,18 @@ namespace vlfb {
 namespace {
 
 constexpr int SCAN_TPB = 256;
+// bf16 bank rows (2048 elements = 4 KB): rows per tile / resident CTAs per SM of the scan.  Measured (calls J / K): 8 rows
+// (32 KB tiles) at 3 CTAs per SM scan 4.8 TB/s, 12 rows (48 KB) at 2 CTAs per SM 3.7 TB/s -- occupancy beats tile depth
+// because the unpacked rows cost registers.
+#ifndef VLFB_SCAN16_ROWS
+#define VLFB_SCAN16_ROWS 8
+#endif
+#ifndef VLFB_SCAN16_MINB
+#define VLFB_SCAN16_MINB 3
+#endif
+#ifndef VLFB_SCAN16_VOLATILE
+#define VLFB_SCAN16_VOLATILE 0
+#endif
 
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
@@ -41,14 +53,16 @@ __device__ __forceinline__ void unpack16(const uint4& u, float (&f)[EPL]) {
   if (EPL == 4) {
     f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
   } else {
-    // volatile: the rows are unpacked twice (dot product, weighted sum); without it the compiler keeps all ROWS * 8
-    // unpacked floats live between the two uses and spills (the packed rows are what should stay in registers)
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
+#if VLFB_SCAN16_VOLATILE      // forces the second use (weighted sum) to unpack again instead of keeping 8 floats per row live
       uint32_t lo, hi;
       asm volatile("shl.b32 %0, %1, 16;" : "=r"(lo) : "r"(w[i]));
       asm volatile("and.b32 %0, %1, 0xffff0000;" : "=r"(hi) : "r"(w[i]));
+#else
+      const uint32_t lo = w[i] << 16, hi = w[i] & 0xffff0000u;
+#endif
       f[(2 * i) % EPL] = __uint_as_float(lo);
       f[(2 * i + 1) % EPL] = __uint_as_float(hi);
     }
@@ -57,12 +71,12 @@ __device__ __forceinline__ void unpack16(const uint4& u, float (&f)[EPL]) {
 
 // One CTA = rows [row_begin, row_end) of one RoI.  EPL = bank elements per 16-byte load (4: fp32 bank, 8: bf16 bank),
 // V = 16-byte loads per thread per row (D = 256 * V * EPL), ROWS = rows per tile: ROWS*V independent 16-byte loads per
-// thread are in flight before the first use (fp32: 64 KB per CTA, bf16: 48 KB; two CTAs per SM).  Per tile: partial dots -> warp
+// thread are in flight before the first use (fp32: 64 KB per CTA, two CTAs per SM; bf16: 32 KB, three CTAs per SM).  Per tile: partial dots -> warp
 // shuffles -> one shared-memory exchange between the 8 warps (double buffered: one __syncthreads per tile) -> every
 // thread redoes the tiny online-softmax update and rescales / accumulates its V*EPL columns from the registers that
 // still hold the rows.  Scores, softmax and the weighted sum are fp32 whatever the bank's storage type.
 template <int EPL, int V, int ROWS>
-__global__ void __launch_bounds__(SCAN_TPB, 2)
+__global__ void __launch_bounds__(SCAN_TPB, (EPL == 8 && V == 1) ? VLFB_SCAN16_MINB : 2)
 fbo_bank_scan_k(const void* __restrict__ bank, const float* __restrict__ q, float scale, float* __restrict__ part_acc,
                 float* __restrict__ part_ml, float* __restrict__ scores, int L, int S, int rows_per_split) {
   constexpr int D = SCAN_TPB * V * EPL;
@@ -632,7 +646,7 @@ extern "C" {
 /* Rows per tile of the scan kernel for a bank of `D`-element rows stored as `dt` (0 = unsupported). */
 static int scan_rows(int D, int dt) {
   if (dt == VLFB_DT_F32) return D == 4096 ? 4 : (D == 1024 || D == 2048) ? 8 : 0;
-  if (dt == VLFB_DT_BF16) return D == 4096 ? 6 : D == 2048 ? 12 : 0;
+  if (dt == VLFB_DT_BF16) return D == 4096 ? 4 : D == 2048 ? VLFB_SCAN16_ROWS : 0;
   return 0;
 }
 
@@ -689,8 +703,8 @@ int vlfb_fbo_bank_scan_dt(const void* bank, int bank_dtype, const float* q, floa
     else if (D == 2048) VLFB_SCAN(4, 2, 8);
     else VLFB_SCAN(4, 4, 4);
   } else {
-    if (D == 2048) VLFB_SCAN(8, 1, 12);      // 48 KB tiles: 16 rows spill at the 128-register cap of 2 CTAs per SM
-    else VLFB_SCAN(8, 2, 6);
+    if (D == 2048) VLFB_SCAN(8, 1, VLFB_SCAN16_ROWS);
+    else VLFB_SCAN(8, 2, 4);
   }
 #undef VLFB_SCAN
   VLFB_CHECK_LAUNCH();
