@@ -21,14 +21,15 @@ namespace vlfb {
 namespace {
 
 constexpr int SCAN_TPB = 256;
-// bf16 bank rows (2048 elements = 4 KB): rows per tile / resident CTAs per SM of the scan.  Measured (calls J / K): 8 rows
-// (32 KB tiles) at 3 CTAs per SM scan 4.8 TB/s, 12 rows (48 KB) at 2 CTAs per SM 3.7 TB/s -- occupancy beats tile depth
-// because the unpacked rows cost registers.
+// bf16 bank rows (2048 elements = 4 KB): rows per tile / resident CTAs per SM of the scan.  Measured at R=256, L=3600
+// (calls J / K / M, profiles/r02_fbo_bf16_scan_variants.txt): 12 rows at 2 CTAs per SM 3.7 TB/s, 8 rows at 3 CTAs
+// 4.8, 6 rows at 3 CTAs 4.7, 4 rows at 4 CTAs (64 registers, no spills) 5.0 TB/s -- occupancy beats tile depth because the
+// unpacked rows cost registers.
 #ifndef VLFB_SCAN16_ROWS
-#define VLFB_SCAN16_ROWS 8
+#define VLFB_SCAN16_ROWS 4
 #endif
 #ifndef VLFB_SCAN16_MINB
-#define VLFB_SCAN16_MINB 3
+#define VLFB_SCAN16_MINB 4
 #endif
 #ifndef VLFB_SCAN16_VOLATILE
 #define VLFB_SCAN16_VOLATILE 0
@@ -71,7 +72,7 @@ __device__ __forceinline__ void unpack16(const uint4& u, float (&f)[EPL]) {
 
 // One CTA = rows [row_begin, row_end) of one RoI.  EPL = bank elements per 16-byte load (4: fp32 bank, 8: bf16 bank),
 // V = 16-byte loads per thread per row (D = 256 * V * EPL), ROWS = rows per tile: ROWS*V independent 16-byte loads per
-// thread are in flight before the first use (fp32: 64 KB per CTA, two CTAs per SM; bf16: 32 KB, three CTAs per SM).  Per tile: partial dots -> warp
+// thread are in flight before the first use (fp32: 64 KB per CTA, two CTAs per SM; bf16: 16 KB, four CTAs per SM).  Per tile: partial dots -> warp
 // shuffles -> one shared-memory exchange between the 8 warps (double buffered: one __syncthreads per tile) -> every
 // thread redoes the tiny online-softmax update and rescales / accumulates its V*EPL columns from the registers that
 // still hold the rows.  Scores, softmax and the weighted sum are fp32 whatever the bank's storage type.

@@ -43,6 +43,16 @@ constexpr int NPROD = 256;     // 8 producer warps = 2 per scheduler, so the add
                                // 7 producer warps (16 warps total -> 128 instead of 96 registers, no spills) lose
                                // 3-5% of the step on the gather-bound convs; 4 epilogue warps lose ~4%.
 constexpr int NPW = NPROD / 32;
+// TMA-only builds: warps whose lane 0 issues the TMA boxes of a K chunk (box b by warp b % NTMAW).  The wgrad chunk is 4
+// (dY^T atoms) + 8 (im2col atoms of 32 columns) small boxes and its K loop runs at 33-37 % of the tensor pipe (ncu call M),
+// so round 2 tried 2 and 3 issuing warps: parity-green and MUCH slower (call Q: step 16.6 ms instead of 12.7, wgrad 5.7 ms
+// instead of 3.1, every other kind slower too) -- the boxes are not limited by the issuing thread but by the TMA unit's
+// per-box cost, and concurrent issuers only interleave the boxes of different stages.  Kept as a build parameter with the
+// measured default of ONE issuer; the remedy is fewer, larger boxes (one 4-D box per MN-major operand tile, below).
+#ifndef VLFB_TMA_WARPS
+#define VLFB_TMA_WARPS 1
+#endif
+constexpr int NTMAW = VLFB_TMA_WARPS;
 constexpr int RSTEP = NPROD / 8;   // rows covered by one pass of the K-major loaders
 constexpr int NEPI = 256;          // 8 epilogue warps (two per TMEM lane quarter, splitting the column blocks)
 constexpr int EPC = 16;            // accumulator columns per epilogue step (tcgen05.ld.32x32b.x16)
@@ -746,7 +756,7 @@ __device__ __forceinline__ bool sched_next(const vlfb_gemm_params_t& p, const La
 // issuer, 8 epilogue warps) with up to 168 registers per thread -- the 17-warp CP = true build (8 cp.async gather
 // warps: conv1 stem, strided dgrad, operands TMA cannot address) is capped at 96 and spills in the epilogue.
 template <int AK, int BK, bool MASK, bool PAIR, bool CP>
-__global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kernel(const vlfb_gemm_params_t p, const Launch L,
+__global__ void __launch_bounds__((CP ? NPROD : 32 * NTMAW) + 32 + NEPI, 1) gemm_tc_kernel(const vlfb_gemm_params_t p, const Launch L,
                                                               const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB) {
   extern __shared__ uint8_t smem_raw[];
@@ -764,7 +774,7 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr_addr - smem_u32(smem_raw)));
 
   static_assert(!(PAIR && CP), "CTA pairs need both operands staged by TMA");
-  constexpr int NPRODT = CP ? NPROD : 32;        // producer threads of this build
+  constexpr int NPRODT = CP ? NPROD : 32 * NTMAW;   // producer threads of this build
   constexpr int NPWT = NPRODT / 32;
   constexpr int NTHR = NPRODT + 32 + NEPI;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -805,8 +815,14 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
   if (tid == 0) TR(2);
 
   if (warp < NPWT) {
-    // ============================ PRODUCERS (8 warps; TMA: one thread) ============================
-    if (cp_any || tid == 0) {
+    // ============================ PRODUCERS (8 cp.async warps / NTMAW TMA issuers) ============================
+    // TMA issuers: thread 0 in a CP build; lane 0 of every producer warp in a TMA-only build.  All issuers walk the same
+    // tile / chunk sequence with their own copy of the (deterministic) gather state and wait for the free stage
+    // themselves; issuer `hid` launches the boxes b with b % NISS == hid; issuer 0 posts the expected byte count.
+    constexpr int NISS = CP ? 1 : NTMAW;
+    const int hid = CP ? 0 : (tid >> 5);
+    const bool issuer = CP ? (tid == 0) : ((tid & 31) == 0);
+    if (cp_any || issuer) {
       KLoader<is_mn(AK) ? VLFB_OP_DENSE_K : AK, BM / RSTEP> ka;
       MNLoader<is_mn(AK) ? AK : VLFB_OP_DENSE_MN> ma;
       KLoader<is_mn(BK) ? VLFB_OP_DENSE_K : BK, 256 / RSTEP> kb;
@@ -855,7 +871,7 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
         // bytes the stage barrier expects: this CTA's copies (PAIR: both CTAs', posted by the leader)
         uint32_t tma_bytes = (tma_a ? (uint32_t)A_TILE_BYTES : 0u) + (tma_b ? b_tile_bytes : 0u);
         if (PAIR) tma_bytes *= 2u;
-        if (tid == 0 && stem_a && L.stem_patch) {
+        if (issuer && stem_a && L.stem_patch) {
           const vlfb_conv_geom_t& g = p.g;
           const int mt = ti.m0 / BM;
           const int wb = mt % L.patch_wb, q = mt / L.patch_wb;
@@ -866,7 +882,7 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
           sg_n[0] = n;
           ic_t = kc0 / g.kH;
           ic_h = kc0 - ic_t * g.kH;
-        } else if (tid == 0 && stem_a) {
+        } else if (issuer && stem_a) {
           const vlfb_conv_geom_t& g = p.g;
           Pos4 o = decode_pos_fast((uint32_t)ti.m0, L.out);
 #pragma unroll
@@ -880,7 +896,7 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
           ic_t = kc0 / g.kH;
           ic_h = kc0 - ic_t * g.kH;
         }
-        if (tid == 0 && im2col_a) {
+        if (issuer && im2col_a) {
           const vlfb_conv_geom_t& g = p.g;
           if (AK == VLFB_OP_CONV_K) {
             const Pos4 o = decode_pos_fast((uint32_t)ti.m0, L.out);
@@ -901,7 +917,7 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
           ic_c = kc0 - tap * icpt;
           decode_tap(tap, g.kH, g.kW, ic_t, ic_h, ic_w);     // (par: kc0 = 0 -> all zero; ic_h / ic_w count the class's taps)
         }
-        if (tid == 0 && im2col_b) {
+        if (issuer && im2col_b) {
           const vlfb_conv_geom_t& g = p.g;
           ib_atoms = 0;
           int peer_atoms = 0;
@@ -920,7 +936,7 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
           }
           tma_bytes = (PAIR ? 2u : 1u) * (tma_a ? (uint32_t)A_TILE_BYTES : 0u) + 4096u * (uint32_t)(ib_atoms + peer_atoms);
         }
-        if (tid == 0 && stem_b) {
+        if (issuer && stem_b) {
           ib_atoms = 0;                                             // atoms = filter rows kh of this N tile
           for (int a = 0; a * 32 < bn && ti.n0 + a * 32 < p.N; ++a) ib_atoms = a + 1;
           tma_bytes = (tma_a ? (uint32_t)A_TILE_BYTES : 0u) + 4096u * (uint32_t)ib_atoms;
@@ -931,41 +947,58 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
           }
         }
         for (int i = 0; i < ti.nk; ++i, ++it) {
-          if (it >= S) mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          // Helper issuers (hid > 0) wait for the free stage LAZILY, right before their first box of the chunk: an issuer
+          // without a box in a chunk (2-box chunks on 3 issuers) must not wait at all -- nothing would depend on it, the
+          // others would lap it by two phases of the stage barrier and its parity wait would then never return (call P:
+          // exactly that hang, 4 s later the watchdog trap, in the full-size captured step).
+          const bool need_wait = it >= S;
+          const uint32_t wpar = ph ^ 1u;
           const int s_cur = s;
+          if (need_wait && (NISS == 1 || hid == 0 || cp_any)) mbar_wait(empty0 + 8 * s_cur, wpar);
           if (++s == S) { s = 0; ph ^= 1u; }
           const uint32_t a_tile = smem_base + s_cur * stage_bytes;
           const uint32_t b_tile = a_tile + A_TILE_BYTES;
           const uint32_t fbar = fullx + 8 * s_cur;
-          if (tid == 0 && tma_bytes) {
-            if (!PAIR || rank == 0) mbar_expect_tx(full0 + 8 * s_cur, tma_bytes);
+          if (issuer && tma_bytes) {
+            if (hid == 0 && (!PAIR || rank == 0)) mbar_expect_tx(full0 + 8 * s_cur, tma_bytes);
+            int box = 0;                                  // boxes of this chunk, in issue order
+            bool waited = NISS == 1 || hid == 0;
+            auto mine = [&]() {
+              const bool m = NISS == 1 || (box % NISS) == hid;
+              ++box;
+              if (m && !waited) {
+                if (need_wait) mbar_wait(empty0 + 8 * s_cur, wpar);
+                waited = true;
+              }
+              return m;
+            };
             if (stem_a) {
               const vlfb_conv_geom_t& g = p.g;
               if (L.stem_patch) {                     // one {128 B x 16 wo x 8 rows (stride sH)} box = the whole A tile
-                tma_load_5d(a_tile, &tmA, 0, sg_w[0], (sg_ht[0] >> 16) + ic_h, (int)(short)(sg_ht[0] & 0xFFFF) + ic_t, sg_n[0], fbar);
+                if (mine()) tma_load_5d(a_tile, &tmA, 0, sg_w[0], (sg_ht[0] >> 16) + ic_h, (int)(short)(sg_ht[0] & 0xFFFF) + ic_t, sg_n[0], fbar);
               } else {
 #pragma unroll
                 for (int q = 0; q < NSG; ++q)
-                  tma_load_5d(a_tile + q * 2048, &tmA, 0, sg_w[q], (sg_ht[q] >> 16) + ic_h, (int)(short)(sg_ht[q] & 0xFFFF) + ic_t,
+                  if (mine()) tma_load_5d(a_tile + q * 2048, &tmA, 0, sg_w[q], (sg_ht[q] >> 16) + ic_h, (int)(short)(sg_ht[q] & 0xFFFF) + ic_t,
                               sg_n[q], fbar);
               }
               if (++ic_h == g.kH) { ic_h = 0; ++ic_t; }
             } else if (im2col_a) {
               const vlfb_conv_geom_t& g = p.g;
               if (AK == VLFB_OP_CONV_K) {
-                ldi(a_tile, &tmA, ic_c * KC, ia_w, ia_h, ia_d, ia_n, ic_w * g.dW, ic_h * g.dH, ic_t * g.dT, fbar);
+                if (mine()) ldi(a_tile, &tmA, ic_c * KC, ia_w, ia_h, ia_d, ia_n, ic_w * g.dW, ic_h * g.dH, ic_t * g.dT, fbar);
               } else if (AK == VLFB_OP_DGRAD_K && L.par) {
                 // tap (kt, rh + sH ic_h, rw + sW ic_w) of the class: dY offset (taps - 1 - index), weights at the original tap
                 const ParCls& c = L.par_cls[ti.batch];
-                ldi(a_tile, &tmA, ic_c * KC, ia_w, ia_h, ia_d, ia_n, c.nw - 1 - ic_w, c.nh - 1 - ic_h, (g.kT - 1 - ic_t) * g.dT, fbar);
+                if (mine()) ldi(a_tile, &tmA, ic_c * KC, ia_w, ia_h, ia_d, ia_n, c.nw - 1 - ic_w, c.nh - 1 - ic_h, (g.kT - 1 - ic_t) * g.dT, fbar);
                 const int tap = (ic_t * g.kH + c.rh + g.sH * ic_h) * g.kW + c.rw + g.sW * ic_w;
-                ld3(b_tile, &tmB, tap * g.Co + ic_c * KC, nb0, 0, fbar);
+                if (mine()) ld3(b_tile, &tmB, tap * g.Co + ic_c * KC, nb0, 0, fbar);
                 if (++ic_c == icpt) {
                   ic_c = 0;
                   if (++ic_w == c.nw) { ic_w = 0; if (++ic_h == c.nh) { ic_h = 0; ++ic_t; } }
                 }
               } else {
-                ldi(a_tile, &tmA, ic_c * KC, ia_w, ia_h, ia_d, ia_n, (g.kW - 1 - ic_w) * g.dW,
+                if (mine()) ldi(a_tile, &tmA, ic_c * KC, ia_w, ia_h, ia_d, ia_n, (g.kW - 1 - ic_w) * g.dW,
                     (g.kH - 1 - ic_h) * g.dH, (g.kT - 1 - ic_t) * g.dT, fbar);
               }
               if (!(AK == VLFB_OP_DGRAD_K && L.par) && ++ic_c == icpt) {
@@ -973,11 +1006,13 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
                 if (++ic_w == g.kW) { ic_w = 0; if (++ic_h == g.kH) { ic_h = 0; ++ic_t; } }
               }
             } else if (tma_a && !(stem_b && L.stem_patch)) {
-              if (is_mn(AK)) {
+              if (is_mn(AK) && L.tma_a == 4) {            // all atoms of the tile in one box
+                if (mine()) tma_load_4d(a_tile, &tmA, 0, ti.k_begin + i * KC, ti.m0 >> 5, ti.batch, fbar);
+              } else if (is_mn(AK)) {
                 for (int a = 0; a < BM / 32; ++a)
-                  ld3(a_tile + a * 4096, &tmA, ti.m0 + a * 32, ti.k_begin + i * KC, ti.batch, fbar);
+                  if (mine()) ld3(a_tile + a * 4096, &tmA, ti.m0 + a * 32, ti.k_begin + i * KC, ti.batch, fbar);
               } else {
-                ld3(a_tile, &tmA, (kc0 + i) * KC, ti.m0, ti.batch, fbar);
+                if (mine()) ld3(a_tile, &tmA, (kc0 + i) * KC, ti.m0, ti.batch, fbar);
               }
             }
             if (stem_b && L.stem_patch) {
@@ -986,9 +1021,9 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
               const int wb = q % L.patch_wb, q2 = q / L.patch_wb;
               const int hp = q2 % L.patch_hb, rest = q2 / L.patch_hb;
               const int to = rest % g.To, n = rest / g.To;
-              tma_load_5d(b_tile, &tmB, 0, wb * 16, hp * 2 * g.sH - g.pH, to * g.sT - g.pT + ti.tap, n, fbar);
+              if (mine()) tma_load_5d(b_tile, &tmB, 0, wb * 16, hp * 2 * g.sH - g.pH, to * g.sT - g.pT + ti.tap, n, fbar);
               for (int a = 0; a * 32 < p.M && a < BM / 32; ++a)      // dY^T: {32 channels, 16 wo, 2 ho} per atom
-                tma_load_4d(a_tile + a * 4096, &tmA, ti.m0 + a * 32, wb * 16, hp * 2, rest, fbar);
+                if (mine()) tma_load_4d(a_tile + a * 4096, &tmA, ti.m0 + a * 32, wb * 16, hp * 2, rest, fbar);
             } else if (stem_b) {
               // conv1 wgrad B tile: 32 output positions (k rows) = 2 groups of 16; per filter row kh one 32-column atom
               // (8 px x 4 ch) = two {128 B x 16 positions} boxes of the overlapping-window view
@@ -1001,8 +1036,17 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
                 const int bn_ = kpos < p.K ? o.n : g.N;
                 const int bh = o.h * g.sH - g.pH + kh0, bt = o.t * g.sT - g.pT + ti.tap;
                 for (int a = 0; a < ib_atoms; ++a)
-                  tma_load_5d(b_tile + a * 4096 + hf * 2048, &tmB, 0, o.w, bh + a, bt, bn_, fbar);
+                  if (mine()) tma_load_5d(b_tile + a * 4096 + hf * 2048, &tmB, 0, o.w, bh + a, bt, bn_, fbar);
               }
+            } else if (BK == VLFB_OP_CONV_MN && L.tma_b == 5) {
+              // wgrad B tile of a convolution without spatial taps: 32 consecutive positions of one clip, shifted by whole
+              // frames for the temporal tap, all channel atoms of the tile in ONE box (make_tmap_conv_flat)
+              const vlfb_conv_geom_t& g = p.g;
+              const uint32_t hw = (uint32_t)(g.H * g.W), thw = (uint32_t)g.T * hw;
+              const uint32_t kpos = (uint32_t)(ti.k_begin + i * KC);
+              const uint32_t n = kpos / thw;
+              const int pos = (int)(kpos - n * thw) + (ti.tap * g.dT - g.pT) * (int)hw;
+              if (mine()) tma_load_4d(b_tile, &tmB, 0, pos, nb0 >> 5, (int)n, fbar);
             } else if (im2col_b) {
               // wgrad B tile: 32 output positions (k rows) x one (kh, kw, 32-channel) atom per copy
               const vlfb_conv_geom_t& g = p.g;
@@ -1011,14 +1055,16 @@ __global__ void __launch_bounds__((CP ? NPROD : 32) + 32 + NEPI, 1) gemm_tc_kern
 #pragma unroll
               for (int a = 0; a < NATOM; ++a)
                 if (a < ib_atoms)
-                  ldi(b_tile + a * 4096, &tmB, ib_c[a], bw, bh, bd, o.n, ib_off[a] & 0xFFFF, ib_off[a] >> 16,
+                  if (mine()) ldi(b_tile + a * 4096, &tmB, ib_c[a], bw, bh, bd, o.n, ib_off[a] & 0xFFFF, ib_off[a] >> 16,
                       ti.tap * g.dT, fbar);
             } else if (tma_b && !(AK == VLFB_OP_DGRAD_K && L.par)) {
-              if (is_mn(BK)) {
+              if (is_mn(BK) && L.tma_b == 4) {
+                if (mine()) tma_load_4d(b_tile, &tmB, 0, ti.k_begin + i * KC, nb0 >> 5, ti.batch, fbar);
+              } else if (is_mn(BK)) {
                 for (int a = 0; a < bnh / 32; ++a)
-                  ld3(b_tile + a * 4096, &tmB, nb0 + a * 32, ti.k_begin + i * KC, ti.batch, fbar);
+                  if (mine()) ld3(b_tile + a * 4096, &tmB, nb0 + a * 32, ti.k_begin + i * KC, ti.batch, fbar);
               } else {
-                ld3(b_tile, &tmB, (kc0 + i) * KC, nb0, ti.batch, fbar);
+                if (mine()) ld3(b_tile, &tmB, (kc0 + i) * KC, nb0, ti.batch, fbar);
               }
             }
           }
@@ -1601,6 +1647,42 @@ static bool make_tmap_mn(CUtensorMap* tm, const vlfb_operand_t& op, int extent, 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// The same operand as ONE box per tile: a 4-D view {32 elements of an atom, K rows, atom index, batch} -- the atom
+// dimension has the SMALLEST stride (128 B), which a tiled map may have -- with box {32, 32 k-rows, natoms, 1}: the copy
+// writes atom after atom, i.e. exactly the [atom][k][32] layout the per-atom copies produce, in one instruction instead
+// of 4 (A) / 8 (B).  The TMA unit's cost is per BOX: the 12 small boxes of a wgrad K chunk took 0.72 us against 0.27 us
+// of MMAs (tensor pipe 33-37 % active in every wgrad launch, ncu call M).  Needs whole atoms (extent % 32 == 0).
+static bool make_tmap_mn4(CUtensorMap* tm, const vlfb_operand_t& op, int extent, int K, int batch, int natoms) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc || op.kind != VLFB_OP_DENSE_MN || K < KC || extent < 32 || (extent & 31) || natoms < 1 || natoms > 8) return false;
+  cuuint64_t dims[4] = {32, (cuuint64_t)K, (cuuint64_t)(extent / 32), (cuuint64_t)(batch > 1 ? batch : 1)};
+  cuuint64_t strides[3] = {(cuuint64_t)op.ld * 4, 128, (cuuint64_t)(batch > 1 ? op.batch_stride : (int64_t)K * op.ld) * 4};
+  if ((strides[0] & 15) || (strides[2] & 15) || strides[2] == 0) return false;
+  cuuint32_t box[4] = {32, (cuuint32_t)KC, (cuuint32_t)natoms, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(op.ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// wgrad activation operand of a convolution WITHOUT spatial taps (1x1x1 and kTx1x1, unit strides, no spatial padding --
+// two thirds of the convolutions of the nets): the k rows of a chunk are 32 consecutive positions of one clip, shifted by
+// whole frames for the temporal tap, so the gather is a dense 4-D view {32 channels of an atom, T*H*W positions of a
+// clip, atom index, clip}; frames outside the clip are out of range in the position dimension and read as zeros.
+// ONE box per K chunk instead of up to 8 im2col copies.  Needs T*H*W % 32 == 0 (a chunk never straddles two clips).
+static bool make_tmap_conv_flat(CUtensorMap* tm, const float* x, const vlfb_conv_geom_t& g, int natoms) {
+  EncodeTiledFn enc = encode_fn();
+  const int64_t thw = (int64_t)g.T * g.H * g.W;
+  if (!enc || g.kH != 1 || g.kW != 1 || g.sT != 1 || g.sH != 1 || g.sW != 1 || g.pH != 0 || g.pW != 0) return false;
+  if ((g.C & 31) || (thw & 31) || g.To != g.T || g.Ho != g.H || g.Wo != g.W || natoms < 1 || natoms > 8) return false;
+  cuuint64_t dims[4] = {32, (cuuint64_t)thw, (cuuint64_t)(g.C / 32), (cuuint64_t)g.N};
+  cuuint64_t strides[3] = {(cuuint64_t)g.C * 4, 128, (cuuint64_t)thw * g.C * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)KC, (cuuint32_t)natoms, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // 5-D im2col map of an NDHWC fp32 tensor [N, D, H, W, C]: `pixels` window origins x 32 channels per copy.
 // lower/upper = bounding-box corners {W, H, D}; strides = traversal strides {W, H, D}.
 typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1671,7 +1753,7 @@ static bool make_tmap_dy4(CUtensorMap* tm, const float* dy, const vlfb_conv_geom
 }
 
 // tuning overrides, read once (scripts/tune_gemm.py); the per-call fields of vlfb_gemm_params_t take precedence
-struct Env { int bn, stages, lag, pair, sk, debug, no_patch, no_par; bool tma_mn, im2col; };
+struct Env { int bn, stages, lag, pair, sk, debug, no_patch, no_par; bool tma_mn, im2col, fuse_atoms; };
 static Env read_env() {
   Env e;
   auto geti = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
@@ -1685,6 +1767,7 @@ static Env read_env() {
   e.no_par = geti("VLFB_NO_PAR", 0);
   e.tma_mn = geti("VLFB_TMA_MN", 1) != 0;
   e.im2col = geti("VLFB_IM2COL", 1) != 0;
+  e.fuse_atoms = geti("VLFB_FUSE_ATOMS", 1) != 0;
   return e;
 }
 static const Env& env() {
@@ -1935,6 +2018,11 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
               (AK == VLFB_OP_DENSE_MN && mn_tma && make_tmap_mn(&tmA, p.a, p.M, p.K, p.batch)) ? 1 : 0;
     L.tma_b = (BK == VLFB_OP_DENSE_K && make_tmap(&tmB, p.b, p.N, p.K, p.batch, bnh)) ||
               (BK == VLFB_OP_DENSE_MN && mn_tma && make_tmap_mn(&tmB, p.b, p.N, p.K, p.batch)) ? 1 : 0;
+    // MN-major tiles as ONE box (all atoms of the tile) instead of one box per 32-element atom
+    if (ev.fuse_atoms && !plan.pair) {
+      if (AK == VLFB_OP_DENSE_MN && L.tma_a == 1 && make_tmap_mn4(&tmA, p.a, p.M, p.K, p.batch, BM / 32)) L.tma_a = 4;
+      if (BK == VLFB_OP_DENSE_MN && L.tma_b == 1 && make_tmap_mn4(&tmB, p.b, p.N, p.K, p.batch, bnh / 32)) L.tma_b = 4;
+    }
     if (ev.im2col) {
       // conv gathers as TMA im2col copies: one instruction per K chunk instead of 1024 16-byte cp.asyncs
       const int pad_lo[3] = {-g.pW, -g.pH, -g.pT};
@@ -1994,6 +2082,10 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
           make_tmap_im2col(&tmB, p.b.ptr, g.N, g.T, g.H, g.W, g.C, pad_lo, pad_hi, cstr, KC,
                            CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
         L.tma_b = 2;
+      // ... and without spatial taps the whole B tile of a chunk is one dense box (make_tmap_conv_flat)
+      if (BK == VLFB_OP_CONV_MN && L.tma_b == 2 && ev.fuse_atoms && !plan.pair &&
+          make_tmap_conv_flat(&tmB, p.b.ptr, g, bnh / 32))
+        L.tma_b = 5;
     }
     const bool fixup = plan.sk && !(p.flags & VLFB_EPI_ATOMIC);
     if (!(plan.pair || fixup) || (L.tma_a && L.tma_b)) break;
@@ -2034,7 +2126,7 @@ int launch(const vlfb_gemm_params_t& p_in, cudaStream_t stream) {
             AK, BK, p.M, p.N, p.K, zbase, L.bn, plan.pair, L.sk, p.split_k, L.total_tiles, units, L.stages, L.tma_a, L.tma_b, cap, L.stem_patch, L.par);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(plan.pair ? 2 * units : units));
-  cfg.blockDim = dim3((unsigned)((cp ? NPROD : 32) + 32 + NEPI));
+  cfg.blockDim = dim3((unsigned)((cp ? NPROD : 32 * NTMAW) + 32 + NEPI));
   cfg.dynamicSmemBytes = (size_t)smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
