@@ -487,7 +487,10 @@ def main():
     else:
         run_b200(args)
         from vlfb import dist as vdist
-        vdist.shutdown()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if not vdist.shutdown():
+            os._exit(0)          # the result line is out; never hang the launcher on a communicator teardown
 
 
 if __name__ == '__main__':

@@ -1,6 +1,6 @@
 #!/bin/bash
 # final validation of round 2: whole GPU suite, smoke, bench (both arms), ncu launch list of one eager step ->
-# profiles/ncu_traffic.json, ncu --set full of the res4 / res5 launches at 2 and 8 clips per GPU
+# profiles/ncu_traffic.json
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
@@ -15,18 +15,9 @@ try:
 except Exception as e: print('ERR', e)
 "
 tail -1 $O/final_bench_ref.json | cut -c1-400
-timeout 700 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv -c 1300 \
+timeout 700 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv -c 1250 \
   --log-file /tmp/final_ncu_launches.csv python bench.py --steps 1 --warmup 3 --no-graph --no-roofline --no-cpu-baseline --no-fbo --large-batch 0 > $O/final_ncu_bench.log 2>&1
 echo "ncu launches rc=$?"
 python scripts/summarize_ncu_launches.py /tmp/final_ncu_launches.csv $O/final_ncu_launches_summary.txt $O/final_ncu_traffic.json > /dev/null 2>&1
 gzip -c /tmp/final_ncu_launches.csv > $O/final_ncu_launches.csv.gz
 head -24 $O/final_ncu_launches_summary.txt; tail -1 $O/final_ncu_launches_summary.txt
-for c in 2 8; do
-  VLFB_PROF_CLIPS=$c timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -f -o /tmp/rep_res45_c$c \
-    python scripts/prof_gemm3.py > $O/final_ncu_res45_c$c.log 2>&1
-  echo "ncu res45 clips=$c rc=$?"
-  ncu -i /tmp/rep_res45_c$c.ncu-rep --page raw --csv > /tmp/res45_c${c}_raw.csv 2>/dev/null
-  python scripts/summarize_ncu_full.py /tmp/res45_c${c}_raw.csv $O/final_ncu_full_res45_clips${c}_summary.txt > /dev/null
-  gzip -c /tmp/res45_c${c}_raw.csv > $O/final_ncu_full_res45_clips${c}_raw.csv.gz
-  cut -c1-120 $O/final_ncu_full_res45_clips${c}_summary.txt
-done
