@@ -112,3 +112,50 @@ def test_reference_yaml_files_load_when_reference_is_present():
         C.cfg_from_file(f)
         C.assert_and_infer_cfg()
     assert len(files) >= 26
+
+
+def test_oracle_ops_agree_with_independent_implementations():
+    """The reference ships no golden vectors and Caffe2 cannot run here ("parity unpinned"); what CAN be
+    pinned is every restated operator that has an independent implementation of the same published definition in
+    PyTorch: LayerNorm, sigmoid / softmax cross-entropy, Nesterov SGD with weight decay (Caffe2's lr-folded momentum form
+    against torch.optim.SGD over several steps), pooling, softmax, batched matmul.  (RoIAlign: torchvision, above;
+    SpatialBN: F.batch_norm, tests/test_spatial_bn.py.)"""
+    import torch.nn.functional as F
+    from oracle import ops as O
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn((5, 512, 1, 1, 1), generator=g, dtype=torch.float64) * 3 + 1
+    y, mean, std = O.layer_norm_axis1(x, eps=1e-5)
+    assert (y.reshape(5, 512) - F.layer_norm(x.reshape(5, 512), (512,), eps=1e-5)).abs().max() < 1e-12
+    assert (std.view(-1) - torch.sqrt(x.reshape(5, -1).var(dim=1, unbiased=False) + 1e-5)).abs().max() < 1e-12
+    # Detectron SigmoidCrossEntropyLoss: sum over the valid elements / #valid * scale; targets -1 are ignored
+    logits = torch.randn((6, 80), generator=g, dtype=torch.float64) * 4
+    t = (torch.rand((6, 80), generator=g) < 0.1).to(torch.int32)
+    t[1, :7] = -1
+    valid = t != -1
+    ref = F.binary_cross_entropy_with_logits(logits[valid], t[valid].double(), reduction='sum') / valid.sum() * 0.125
+    assert abs(float(O.sigmoid_cross_entropy_loss(logits, t, scale=0.125) - ref)) < 1e-12
+    labels = torch.randint(0, 80, (6,), generator=g)
+    prob, loss = O.softmax_with_loss(logits, labels, scale=0.5)
+    assert abs(float(loss - 0.5 * F.cross_entropy(logits, labels))) < 1e-12
+    assert (prob - torch.softmax(logits, dim=1)).abs().max() < 1e-15
+    # WeightedSum + MomentumSGDUpdate(nesterov) == torch.optim.SGD(nesterov, weight_decay) at constant lr, 4 steps
+    p0 = torch.randn(257, generator=g, dtype=torch.float64)
+    grads = [torch.randn(257, generator=g, dtype=torch.float64) for _ in range(4)]
+    p, m = p0.clone(), torch.zeros_like(p0)
+    tp = p0.clone().requires_grad_(True)
+    opt = torch.optim.SGD([tp], lr=0.03, momentum=0.9, nesterov=True, weight_decay=1e-4)
+    for gr in grads:
+        p, m = O.nesterov_update(p, gr, m, 0.03, 0.9, 1e-4)
+        tp.grad = gr.clone()
+        opt.step()
+    assert (p - tp.detach()).abs().max() < 1e-13
+    # pooling / softmax(axis=2) / BatchMatMul(trans_a, trans_b)
+    v = torch.randn((2, 8, 4, 9, 9), generator=g, dtype=torch.float64)
+    assert torch.equal(O.max_pool_nd(v, (1, 3, 3), (1, 2, 2), (0, 1, 1)), F.max_pool3d(v, (1, 3, 3), (1, 2, 2), (0, 1, 1)))
+    assert (O.avg_pool_nd(v, (4, 1, 1), (1, 1, 1), (0, 0, 0)) - v.mean(dim=2, keepdim=True)).abs().max() < 1e-14
+    a3 = torch.randn((3, 5, 7), generator=g, dtype=torch.float64)
+    assert (O.softmax_axis2(a3) - torch.softmax(a3, dim=2)).abs().max() < 1e-15
+    b3 = torch.randn((3, 5, 4), generator=g, dtype=torch.float64)
+    assert (O.batch_matmul(a3, b3, trans_a=1) - torch.einsum('bkm,bkn->bmn', a3, b3)).abs().max() < 1e-13
+    c3 = torch.randn((3, 4, 7), generator=g, dtype=torch.float64)
+    assert (O.batch_matmul(a3, c3, trans_b=1) - torch.einsum('bmk,bnk->bmn', a3, c3)).abs().max() < 1e-13
