@@ -95,3 +95,25 @@ def test_two_rank_step_equals_single_process_step():
         d = np.abs(r0[name] - single[name]).max() / max(np.abs(single[name]).max(), 1e-12)
         assert d < 1e-9, (name, d)                                           # == the big-batch step
         assert np.abs(single[name] - params[name].numpy()).max() > 0         # and the step moved the weights
+
+
+def _bn_rank_worker(rank, world, port, ret):
+    sys.path.insert(0, HERE)
+    import conftest  # noqa: F401  (sys.path setup)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.distributed.init_process_group('gloo', rank=rank, world_size=world)
+    from utils import bn_helper
+    ret[rank] = bn_helper._mean_over_ranks(np.array([1.0 + rank, 10.0 * rank, -3.0], dtype=np.float64))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_precise_bn_statistics_are_averaged_over_ranks():
+    """lib/utils/bn_helper.py: the reference divides E[x], E[x^2] by ITER * NUM_GPUS inside its one process
+    (bn_helper.py:186); with one process per GPU the per-rank means are all-reduced instead."""
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_bn_rank_worker, args=(2, port, ret), nprocs=2, join=True)
+    for r in (0, 1):
+        assert np.allclose(ret[r], [1.5, 5.0, -3.0])
