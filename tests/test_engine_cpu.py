@@ -331,3 +331,25 @@ def test_fetch_blob_async_equals_fetch_blob(fake):
     for name in ['loss', 'pred', 'pool5', 'conv1_w']:
         a, b = workspace.FetchBlob('gpu_0/' + name), workspace.FetchBlobAsync('gpu_0/' + name)
         assert b.ready() and np.array_equal(np.asarray(a), b.get()) and np.asarray(a).shape == b.get().shape, name
+
+
+@pytest.mark.parametrize('stack', [True, False])
+def test_training_nets_never_lower_to_the_inference_fold(fake, stack):
+    """FboFoldStep has no backward (it is valid only without dropout between lfb_1x1 and phi / g): whatever the switches,
+    a net with a loss must keep a differentiable lowering -- the FboNLStack operator or the as-written Conv / BatchMatMul
+    graph -- and a forward-only TRAIN-split net (precise-BN's aux model, lfb_infer_only extraction aside) as well when
+    dropout is on."""
+    from core.config import config as cfg
+    from vlfb import workspace
+    from vlfb import executor as X
+    ov = TINY + ['FBO_NL.LFB_DROPOUT_ON', True, 'FBO_NL.DROPOUT_RATE', 0.2]
+    H.setup_cfg('ava_r50_lfb_nl.yaml', ov)
+    cfg.B200.FBO_FOLD = True
+    cfg.B200.FBO_STACK = stack
+    workspace.ResetWorkspace()
+    model, sfx = H.build('train', True)
+    net = workspace.current().nets[model.net.Proto().name]
+    assert net.train and net.losses
+    assert not any(isinstance(s, X.FboFoldStep) for s in net.steps)
+    assert sum(isinstance(s, X.FboStackStep) for s in net.steps) == (1 if stack else 0)
+    assert any(isinstance(s, X.DropoutStep) for s in net.steps) or stack       # the stack applies the dropout itself
