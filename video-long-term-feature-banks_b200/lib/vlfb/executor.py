@@ -34,6 +34,9 @@ LAZY_GRAD_SUM = os.environ.get('VLFB_LAZY_GRAD_SUM', '1') != '0'   # defer resid
 FUSE_GRAD_FINISH = os.environ.get('VLFB_FUSE_GRAD_FINISH', '1') == '1'
 # ... with the mask read as sign bits written by the producing conv's epilogue instead of the fp32 activation
 RELU_BITS = os.environ.get('VLFB_RELU_BITS', '1') == '1'
+# max-pool backward in gather form (no fill, no atomics, pool1 folds conv1's ReLU backward + rounding); '0' = the scatter
+# form (zero fill + one atomic per output element + the separate ReLU-backward pass)
+POOL_GATHER = int(os.environ.get('VLFB_POOL_GATHER', '1'))     # 2 = gather form only for non-overlapping windows
 
 
 def set_backend(kernels_module, device, dtype=torch.float32):
@@ -571,7 +574,11 @@ class PoolStep(Step):
         dx = torch.empty_strided(xshape, xstride, dtype=DTYPE, device=DEVICE)
         gp = as5d(phys(gy))
         xkey = self.in_keys[0]
-        if self.op.type == 'MaxPool':
+        overlap = g.kT > g.sT or g.kH > g.sH or g.kW > g.sW
+        if self.op.type == 'MaxPool' and (POOL_GATHER == 0 or (POOL_GATHER == 2 and overlap)):
+            K.fill(flat(dx), 0.0)
+            K.maxpool_bwd(gp, arg, as5d(phys(dx)), g)
+        elif self.op.type == 'MaxPool':
             # gather form: every dx element is written once (no zero fill, no atomics).  When the pooled blob is a
             # conv + ReLU output that nothing else reads (pool1), the ReLU backward (mask from the pool OUTPUT: the
             # winner of a window is positive iff the window's maximum is) and the TF32 rounding of the conv's wgrad
