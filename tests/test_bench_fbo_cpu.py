@@ -28,6 +28,14 @@ def test_fbo_only_net_modes_agree(fake):
         out[mode] = workspace.FetchBlob('gpu_0/prob').copy()
     assert np.abs(out['infer_fold'] - out['infer']).max() < 1e-10
     assert out['infer'].std() > 0
+    # the bf16-bank mode of the microbenchmark: same net, the scan reads the bf16 copy made when the bank was fed
+    model, name = B.build_case('infer_fold_bf16', 3, 20, 3)
+    import torch
+    assert workspace.current().blobs['lfb_test@bf16'].dtype == torch.bfloat16
+    workspace.RunNet(name)
+    p16 = workspace.FetchBlob('gpu_0/prob')
+    assert 0 < np.abs(p16 - out['infer_fold']).max() < 2e-2
+    assert B.fbo_bytes(4, 300, 3, bank_s=2) == B.fbo_bytes(4, 300, 3) - 2 * 4 * 300 * 2048
     model, name = B.build_case('train', 3, 20, 2)
     workspace.RunNet(name)
     assert np.isfinite(workspace.FetchBlob('gpu_0/loss'))
