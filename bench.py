@@ -5,10 +5,13 @@ forward + backward + SGD, 2 synthetic 32x224x224 clips / 4 RoIs / 300-row bank p
   python bench.py --gpus N --steps K --warmup W            # this implementation (tcgen05 path)
   python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle restatement)
 
-One JSON line on stdout (rank 0).  `value` = device-resident throughput (inputs already in
-HBM), `e2e` = through FeedBlob/RunNet/FetchBlob with pinned host buffers (H2D + D2H inside the
-timed region), `roofline` = the tcgen05 gathered-GEMM kernel (all launches of one step) against the
-measured tensor peak, `cpu_baseline` = the oracle timed on the host cores.
+One JSON line on stdout (rank 0).  `value` = device-resident throughput (inputs already in HBM, CUDA-graph replay),
+`e2e` = through EnqueueBlobs / RunNet / FetchBlob with pinned host buffers (H2D + loss D2H inside the timed region),
+`roofline` = the tcgen05 gathered-GEMM kernel (all launches of one step; by_stage / by_kind; DRAM traffic from the tracked
+ncu launch list) against the measured tensor peak, `cpu_baseline` = the oracle timed on the host cores, `fbo_microbench` =
+bench_fbo.py cases (BASELINE configs[4]), `large_batch` = the same step at 8 clips per GPU (sub-process), `clocks` =
+nvidia-smi samples taken while the timed regions ran.  N > 1 (torchrun): max over ranks, weak scaling, the N=1-only extras
+are skipped.
 """
 import argparse
 import json
